@@ -1,0 +1,169 @@
+/*
+ * automoe_b200.h — C-ABI of the B200-native AutoMoE forward hot path.
+ *
+ * The reference (immanuel-peter/self-driving-model) has no FFI: its boundary is
+ * the Python nn.Module API.  Each entry point below replaces the stock
+ * torch/cuDNN/cuBLAS/scipy call sequence of one reference function and is what a
+ * maintainer would bind (ctypes stub in INTEGRATION.md) from that function.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  Device pointers unless a name
+ *     ends in _host.  The caller (PyTorch) owns every buffer.
+ *   - every launch goes to the cudaStream_t passed in (as void*); nothing here
+ *     synchronises the device or allocates device memory, except amoe_create
+ *     (one 4-byte flag) and the host-side LSAP (host memory only).
+ *   - return 0 on success, <0 on error; amoe_last_error() gives the message
+ *     (thread-local).
+ *   - dtype enum: AMOE_F32 = 0, AMOE_BF16 = 1.
+ *   - activations are NHWC ("channels-last"): x[n][h][w][c]; conv weights are
+ *     packed [Cout][KH][KW][Cin] (K-major for the implicit GEMM).
+ *   - "groups" G = number of experts run in one launch: activations are stacked
+ *     on the batch axis ([G*B,H,W,C]) and weights/scale/bias on the Cout axis
+ *     ([G*Cout,...]).  G=1 is an ordinary convolution.
+ */
+#ifndef AUTOMOE_B200_H_
+#define AUTOMOE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMOE_F32 0
+#define AMOE_BF16 1
+
+typedef struct amoe_ctx amoe_ctx;
+
+/* ---- library / context ------------------------------------------------- */
+int amoe_abi_version(void);
+const char* amoe_last_error(void);
+/* One context per device: resolves cuTensorMapEncodeTiled, caches SM count,
+ * sets the max-dynamic-smem attribute of the tcgen05 kernels. */
+int amoe_create(int device, amoe_ctx** out);
+int amoe_destroy(amoe_ctx* ctx);
+int amoe_sm_count(amoe_ctx* ctx);
+/* number of kernels launched through this context since creation (bench.py's
+ * "gpu_launches" counter) */
+int64_t amoe_launch_count(amoe_ctx* ctx);
+
+/* ---- layout / weight packing ------------------------------------------- */
+/* batch['image'] [B,C,H,W] fp32 NCHW (models/automoe.py:212-218 consumers) ->
+ * NHWC with C padded to Cp (zeros).  dst dtype f32 or bf16. */
+int amoe_image_nchw_to_nhwc(amoe_ctx*, const float* src, void* dst, int B, int C,
+                            int H, int W, int Cp, int dst_dtype, void* stream);
+/* nn.Conv2d weight [Cout,Cin,KH,KW] fp32 -> packed [Cout][KH][KW][Cin_pad]
+ * (dtype f32|bf16, zero-padded channels).  dst points at the first row of this
+ * conv inside a (possibly grouped) packed buffer. */
+int amoe_pack_conv_weight(amoe_ctx*, const float* w_oihw, void* dst, int Cout, int Cin,
+                          int KH, int KW, int Cin_pad, int dst_dtype, void* stream);
+/* eval-mode BatchNorm2d folded with the optional conv bias into y = scale*conv + bias
+ * (torchvision resnet BasicBlock bn1/bn2, models/policy/trajectory_head.py:8-24).
+ * gamma==NULL -> no BN: scale=1, bias=conv_bias (or 0). */
+int amoe_fold_bn(amoe_ctx*, const float* gamma, const float* beta, const float* mean,
+                 const float* var, float eps, const float* conv_bias, int C,
+                 float* scale, float* bias, void* stream);
+
+/* ---- convolution (replaces nn.Conv2d + BatchNorm2d + ReLU + residual add;
+ *      torchvision BasicBlock.forward, models/experts/bdd_*_expert.py:12-24,
+ *      models/policy/trajectory_head.py:27-33) --------------------------- */
+/* y = act( scale[c]*conv(x,w) + bias[c] (+ residual) )
+ *   x: [G*B,H,W,Cin] (or [B,H,W,Cin] shared by all groups when x_shared!=0)
+ *   w: [G*Cout,KH,KW,Cin]   scale,bias: [G*Cout] fp32
+ *   y, residual: [G*B,Ho,Wo,Cout]
+ *   input pixel of tap (kh,kw) for output (oh,ow): (oh*stride_h - pad_h + kh,
+ *   ow*stride_w - pad_w + kw); pad_* are the top/left pads, Ho/Wo are explicit so a
+ *   caller can express asymmetric padding (nn.Conv2d: Ho=(H+2*pad-KH)/stride+1).
+ * dtype selects activation+weight storage (f32: SIMT fp32 kernel; bf16: tcgen05
+ * implicit GEMM when the shape qualifies, else the SIMT kernel with fp32 accum).
+ * impl: 0 = auto, 1 = force SIMT, 2 = force tcgen05 (error if unsupported). */
+int amoe_conv2d_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
+                    const float* bias, const void* residual, void* y, int G, int x_shared,
+                    int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride_h,
+                    int stride_w, int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype,
+                    int impl, void* stream);
+/* 1 if amoe_conv2d_fwd(impl=auto, dtype=bf16) would take the tcgen05 path. */
+int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w);
+/* nn.MaxPool2d(3, stride 2, pad 1) of the ResNet stem, NHWC. */
+int amoe_maxpool3x3s2_fwd(amoe_ctx*, const void* x, void* y, int NB, int H, int W, int C,
+                          int dtype, void* stream);
+
+/* ---- expert heads ------------------------------------------------------ */
+/* 1x1 conv (head[2] / decoder[2]) + global mean over pixels.
+ *   x: [B,HW,Cin] (dtype)  w: [N,Cin] fp32  b: [N] fp32
+ *   low: [B,HW,N] fp32 (low-res logits, NHWC)   pooled[b*pooled_ld + n] = mean_hw(low)
+ *   (pooled_ld >= N lets several experts share one [B,sumC] buffer)
+ * pooled feeds the extractors: mean over the x32 bilinear up-sampled map equals
+ * the mean over the low-res map (expert_extractors.py:62,89 + interpolate). */
+int amoe_head1x1_pool_fwd(amoe_ctx*, const void* x, const float* w, const float* b,
+                          float* low, float* pooled, int pooled_ld, int B, int HW, int Cin,
+                          int N, int x_dtype, void* stream);
+/* F.interpolate(low, size=(H,W), mode="bilinear", align_corners=False) and the
+ * NHWC->NCHW transpose in one writer (bdd_segmentation_expert.py:22,
+ * bdd_drivable_expert.py:22).  low: [B,h,w,C] fp32 -> out: [B,C,H,W] (dtype). */
+int amoe_upsample_bilinear_nchw_fwd(amoe_ctx*, const float* low, void* out, int B, int h,
+                                    int w, int C, int H, int W, int out_dtype, void* stream);
+/* mean over H*W of an NCHW tensor -> [B,C] fp32 (AdaptiveAvgPool2d(1); only used
+ * when the up-sampling factor is not an integer so the identity above fails). */
+int amoe_mean_hw_nchw_fwd(amoe_ctx*, const void* x, float* out, int B, int C, int HW,
+                          int dtype, void* stream);
+
+/* ---- fused gate (context extractor + expert extractors + GatingNetwork) ---
+ * Replaces SimpleContextExtractor.forward (context_features.py:151-165),
+ * *ExpertExtractor MLP+LN (expert_extractors.py:27-35), GatingNetwork.forward
+ * (gating_network.py:122-175) — eval semantics (dropout = identity), softmax
+ * gate, no top-k (unreachable through AutoMoE, automoe.py:83-91).
+ *   state:   [B,4] fp32 (speed, steering, throttle, brake)
+ *   pooled:  [B,sumC] fp32, experts' pooled logits concatenated (E experts,
+ *            channel counts in n_ch[E], E<=4)
+ *   params:  flat fp32 buffer, layout documented in gate.cu / models/automoe.py
+ *   outputs (all fp32): context [B,ctx_dim], features [E][B,256],
+ *            processed [E][B,256], gate_logits [B,E], weights [B,E],
+ *            combined [B,256] (after output_projection)
+ * mode bits: 1 = context-only path of get_expert_weights (zeros for experts, weights only);
+ *   2 = `state` holds an encoded context [B,ctx_dim] (context extractor skipped);
+ *   4 = `pooled` holds expert features [E][B,256] (extractors skipped);
+ *   8 = stop after the context extractor; 16 = stop after the expert extractors.
+ * Output pointers may be NULL when not wanted. */
+int amoe_gate_fwd(amoe_ctx*, const float* state, const float* pooled, const float* params,
+                  int64_t n_params, int B, int E, const int* n_ch_host, int ctx_dim,
+                  int hidden, float temperature, int mode, float* context, float* features,
+                  float* processed, float* gate_logits, float* weights, float* combined,
+                  void* stream);
+
+/* ---- policy head ------------------------------------------------------- */
+/* EasyBackbone pool+fc and both TrajectoryPolicy MLP heads
+ * (trajectory_head.py:25-33,44-63) after the 4 convs:
+ *   x: [B,HW,Cf] (dtype) conv4 output   ctx: [B,ctx_dim] fp32 (combined) or NULL
+ *   params: flat fp32 (fc, head_wp[0,2,4], head_spd[0,2,4] weight+bias in order)
+ *   waypoints: [B,2*horizon] fp32   speed: [B,horizon] fp32 */
+int amoe_policy_head_fwd(amoe_ctx*, const void* x, const float* ctx, const float* params,
+                         int64_t n_params, int B, int HW, int Cf, int backbone_dim,
+                         int ctx_dim, int hidden, int horizon, int x_dtype,
+                         float* waypoints, float* speed, void* stream);
+
+/* ---- Hungarian matcher ------------------------------------------------- */
+/* Batched cost matrix of HungarianMatcher.forward (training/hungarian_matcher.py:34-76):
+ *   cost[b,q,n] = w_bbox*L1(pb,tb) - w_class*softmax(logits)[q,label_n] - w_giou*GIoU
+ * D==4: cxcywh boxes; D==7: BEV GIoU from (x,y,w,l); other D: L1 only.
+ *   logits [B,Q,C] fp32, boxes [B,Q,D] fp32, tgt_boxes [B,Nmax,D] fp32 (padded),
+ *   tgt_labels [B,Nmax] int64 (padded), n_tgt [B] int32, cost [B,Q,Nmax] fp32
+ * Columns n >= n_tgt[b] are written as 0. */
+int amoe_hungarian_cost_fwd(amoe_ctx*, const float* logits, const float* boxes,
+                            const float* tgt_boxes, const int64_t* tgt_labels,
+                            const int32_t* n_tgt, float* cost, int B, int Q, int C, int D,
+                            int Nmax, float w_class, float w_bbox, float w_giou,
+                            void* stream);
+/* Host-side rectangular LSAP (shortest augmenting path, same algorithm and
+ * tie-breaking as scipy.optimize.linear_sum_assignment, hungarian_matcher.py:79).
+ *   cost_host [B,Q,Nmax] fp32 (row-major, only the first n_tgt[b] columns used)
+ *   rows_host/cols_host [B,min(Q,Nmax)] int64, n_match_host[b] = min(Q,n_tgt[b])
+ * returns -2 if a cost entry is NaN/-inf (scipy raises ValueError). */
+int amoe_lsap_batched_host(const float* cost_host, const int32_t* n_tgt_host, int B, int Q,
+                           int Nmax, int64_t* rows_host, int64_t* cols_host,
+                           int32_t* n_match_host, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOMOE_B200_H_ */

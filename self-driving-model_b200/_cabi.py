@@ -1,0 +1,121 @@
+"""ctypes binding of include/automoe_b200.h (libautomoe_b200.so).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this
+module raises.  Tensors cross the boundary as raw device pointers + sizes and the
+current CUDA stream; PyTorch owns every buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libautomoe_b200.so"
+
+F32, BF16 = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+_ctxs: dict[int, C.c_void_p] = {}
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/automoe_b200.h one to one
+SIGNATURES = {
+    "amoe_abi_version": (_I, []),
+    "amoe_last_error": (C.c_char_p, []),
+    "amoe_create": (_I, [_I, C.POINTER(_P)]),
+    "amoe_destroy": (_I, [_P]),
+    "amoe_sm_count": (_I, [_P]),
+    "amoe_launch_count": (_L, [_P]),
+    "amoe_image_nchw_to_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "amoe_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
+    "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 18 + [_P]),
+    "amoe_conv2d_tc_supported": (_I, [_I] * 6),
+    "amoe_maxpool3x3s2_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "amoe_head1x1_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "amoe_upsample_bilinear_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "amoe_mean_hw_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "amoe_gate_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I] + [_P] * 7),
+    "amoe_policy_head_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "amoe_hungarian_cost_fwd": (_I, [_P] * 7 + [_I] * 5 + [_F] * 3 + [_P]),
+    "amoe_lsap_batched_host": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I]),
+}
+
+
+class AmoeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not LIB_PATH.exists():
+                    raise AmoeError(
+                        f"{LIB_PATH} not found: build it with `python self-driving-model_b200/build.py` "
+                        "(or __graft_entry__.build()); there is no fallback path")
+                l = C.CDLL(str(LIB_PATH))
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().amoe_last_error().decode("utf-8", "replace")
+        raise AmoeError(f"{what or 'amoe call'} failed ({rc}): {msg}")
+
+
+def ctx(device: torch.device | int | None = None) -> C.c_void_p:
+    """Per-device context handle (created lazily; needs a CUDA device of sm_100)."""
+    if device is None:
+        idx = torch.cuda.current_device()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise AmoeError(f"automoe_b200 kernels need a CUDA device, got {device}; there is no CPU path")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = _ctxs.get(idx)
+    if h is None:
+        with _lock:
+            h = _ctxs.get(idx)
+            if h is None:
+                torch.cuda.init()
+                out = _P()
+                with torch.cuda.device(idx):
+                    check(lib().amoe_create(idx, C.byref(out)), "amoe_create")
+                _ctxs[idx] = h = out
+    return h
+
+
+def stream_ptr(device=None) -> C.c_void_p:
+    return _P(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return _P(0) if t is None else _P(t.data_ptr())
+
+
+def launch_count(device=None) -> int:
+    return int(lib().amoe_launch_count(ctx(device)))
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise AmoeError(f"unsupported dtype {dt}")

@@ -1,0 +1,235 @@
+"""Tensor-level wrappers over the C-ABI (device pointers + current stream).
+
+Everything here launches sm_100a kernels from libautomoe_b200.so; torch is used only
+to own memory.  Activations are NHWC, stacked over experts on the batch axis.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import check, ctx, dtype_code, lib, ptr, stream_ptr
+
+
+def _al4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def flat_params(tensors: List[torch.Tensor], device) -> torch.Tensor:
+    """Concatenate fp32 tensors, each padded to a multiple of 4 floats (16-byte rows)."""
+    parts = []
+    for t in tensors:
+        f = t.detach().to(device=device, dtype=torch.float32).reshape(-1)
+        pad = _al4(f.numel()) - f.numel()
+        if pad:
+            f = torch.cat([f, f.new_zeros(pad)])
+        parts.append(f)
+    return torch.cat(parts).contiguous()
+
+
+def image_to_nhwc(img: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tensor:
+    """[B,C,H,W] fp32 NCHW -> [B,H,W,cp] (zero padded channels)."""
+    if img.dtype != torch.float32:
+        img = img.float()
+    img = img.contiguous()
+    B, Cc, H, W = img.shape
+    out = torch.empty((B, H, W, cp), device=img.device, dtype=dtype)
+    check(lib().amoe_image_nchw_to_nhwc(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp,
+                                        dtype_code(dtype), stream_ptr(img.device)), "image_nchw_to_nhwc")
+    return out
+
+
+@dataclass
+class PackedConv:
+    """Packed weights of G same-shape convolutions (+ folded BN) living on one device."""
+    w: torch.Tensor        # [G*Cout, KH, KW, Cin_k] (dtype)
+    scale: torch.Tensor    # [G*Cout] fp32
+    bias: torch.Tensor     # [G*Cout] fp32
+    G: int
+    cin: int               # channels the kernel sees (after padding / pairing)
+    cout: int
+    kh: int
+    kw: int
+    sh: int
+    sw: int
+    ph: int
+    pw: int
+    relu: bool
+    pair_w: bool = False   # input is read through the [N,H,W/2,2C] pixel-pair view
+    meta: dict = field(default_factory=dict)
+
+
+def pack_conv(convs, bns, dtype: torch.dtype, device, relu: bool, cin_pad: Optional[int] = None,
+              allow_pair: bool = True) -> PackedConv:
+    """Pack G nn.Conv2d (+ optional eval-mode nn.BatchNorm2d each) for amoe_conv2d_fwd.
+
+    BN (running stats) and the conv bias are folded into per-channel scale/bias applied
+    in the conv epilogue in fp32 (torchvision BasicBlock bn1/bn2; trajectory_head.py:8-24).
+    """
+    G = len(convs)
+    c0 = convs[0]
+    cout, cin, kh, kw = c0.weight.shape
+    sh, sw = c0.stride
+    ph, pw = c0.padding
+    st = stream_ptr(device)
+    h = ctx(device)
+    # 3x3/s2 convolutions with 32 input channels are re-expressed over pixel pairs so the
+    # implicit GEMM sees 64 contiguous channels per tap ("pair view").
+    pair = (allow_pair and dtype == torch.bfloat16 and cin == 32 and sw == 2 and kw == 3 and pw == 1)
+    if pair:
+        cin_k, kw_k, sw_k, pw_k = 64, 2, 1, 1
+    else:
+        cin_k, kw_k, sw_k, pw_k = (cin_pad or cin), kw, sw, pw
+    wbuf = torch.empty((G * cout, kh, kw_k, cin_k), device=device, dtype=dtype)
+    scale = torch.empty(G * cout, device=device, dtype=torch.float32)
+    bias = torch.empty(G * cout, device=device, dtype=torch.float32)
+    for g, conv in enumerate(convs):
+        w = conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+        if pair:
+            # w'[o, par*32+c, kh, j]: (j=0,par=1)=kw0, (j=1,par=0)=kw1, (j=1,par=1)=kw2, (j=0,par=0)=0
+            w2 = w.new_zeros((cout, 64, kh, 2))
+            w2[:, 32:, :, 0] = w[:, :, :, 0]
+            w2[:, :32, :, 1] = w[:, :, :, 1]
+            w2[:, 32:, :, 1] = w[:, :, :, 2]
+            w = w2.contiguous()
+        check(lib().amoe_pack_conv_weight(h, ptr(w), ptr(wbuf[g * cout:]), cout, w.shape[1], kh, kw_k, cin_k,
+                                          dtype_code(dtype), st), "pack_conv_weight")
+        cb = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous() if conv.bias is not None else None
+        bn = bns[g] if bns is not None else None
+        if bn is not None:
+            gmm = bn.weight.detach().float().contiguous()
+            bta = bn.bias.detach().float().contiguous()
+            mean = bn.running_mean.detach().float().contiguous()
+            var = bn.running_var.detach().float().contiguous()
+            check(lib().amoe_fold_bn(h, ptr(gmm), ptr(bta), ptr(mean), ptr(var), float(bn.eps), ptr(cb), cout,
+                                     ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
+        else:
+            check(lib().amoe_fold_bn(h, None, None, None, None, 0.0, ptr(cb), cout,
+                                     ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
+        # the temporaries above must outlive the async kernels that read them
+        torch.cuda.current_stream(device).synchronize()
+    return PackedConv(wbuf, scale, bias, G, cin_k, cout, kh, kw_k, sh, sw_k, ph, pw_k, relu, pair)
+
+
+def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Optional[torch.Tensor] = None,
+           x_shared: bool = False, impl: int = 0, relu: Optional[bool] = None) -> torch.Tensor:
+    """x: [G*B,H,W,Cin] NHWC (or [B,H,W,Cin] if x_shared) -> [G*B,Ho,Wo,Cout]."""
+    dtype = x.dtype
+    if pc.pair_w:
+        # output geometry of the original 3x3/s2/p1 conv; the kernel sees width W/2, KW=2, stride_w=1
+        Ho, Wo = (H + 2 * pc.ph - pc.kh) // pc.sh + 1, W // 2
+        Wk = W // 2
+    else:
+        Ho = (H + 2 * pc.ph - pc.kh) // pc.sh + 1
+        Wo = (W + 2 * pc.pw - pc.kw) // pc.sw + 1
+        Wk = W
+    y = torch.empty((pc.G * B, Ho, Wo, pc.cout), device=x.device, dtype=dtype)
+    check(lib().amoe_conv2d_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual), ptr(y),
+                                pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.sw,
+                                pc.ph, pc.pw, Ho, Wo, int(pc.relu if relu is None else relu), dtype_code(dtype),
+                                impl, stream_ptr(x.device)), "conv2d_fwd")
+    return y
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    NB, H, W, Cc = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((NB, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
+    check(lib().amoe_maxpool3x3s2_fwd(ctx(x.device), ptr(x), ptr(y), NB, H, W, Cc, dtype_code(x.dtype),
+                                      stream_ptr(x.device)), "maxpool3x3s2_fwd")
+    return y
+
+
+def head1x1_pool(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, pooled: torch.Tensor, pooled_off: int):
+    """x: [B,h,w,Cin]; w: [N,Cin] fp32; writes pooled[:, off:off+N]; returns low [B,h,w,N] fp32."""
+    B, h, wd, Cin = x.shape
+    N = w.shape[0]
+    low = torch.empty((B, h, wd, N), device=x.device, dtype=torch.float32)
+    pview = pooled[:, pooled_off:]
+    check(lib().amoe_head1x1_pool_fwd(ctx(x.device), ptr(x), ptr(w), ptr(b), ptr(low), ptr(pview), pooled.shape[1],
+                                      B, h * wd, Cin, N, dtype_code(x.dtype), stream_ptr(x.device)), "head1x1_pool_fwd")
+    return low
+
+
+def upsample_bilinear_nchw(low: torch.Tensor, H: int, W: int, dtype: torch.dtype) -> torch.Tensor:
+    B, h, w, Cc = low.shape
+    out = torch.empty((B, Cc, H, W), device=low.device, dtype=dtype)
+    check(lib().amoe_upsample_bilinear_nchw_fwd(ctx(low.device), ptr(low), ptr(out), B, h, w, Cc, H, W,
+                                                dtype_code(dtype), stream_ptr(low.device)), "upsample_bilinear_nchw_fwd")
+    return out
+
+
+def mean_hw_nchw(x: torch.Tensor) -> torch.Tensor:
+    B, Cc, H, W = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    check(lib().amoe_mean_hw_nchw_fwd(ctx(x.device), ptr(x), ptr(out), B, Cc, H * W, dtype_code(x.dtype),
+                                      stream_ptr(x.device)), "mean_hw_nchw_fwd")
+    return out
+
+
+def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0):
+    """Fused context extractor + expert extractors + gating network (gate.cu)."""
+    dev = state.device
+    B, E = state.shape[0], len(n_ch)
+    f32 = dict(device=dev, dtype=torch.float32)
+    context = torch.empty((B, ctx_dim), **f32)
+    weights = torch.empty((B, E), **f32)
+    logits = torch.empty((B, E), **f32)
+    if mode & 1:
+        features = processed = combined = None
+    else:
+        features = torch.empty((E, B, 256), **f32)
+        processed = torch.empty((E, B, 256), **f32)
+        combined = torch.empty((B, 256), **f32)
+    arr = (C.c_int * E)(*n_ch)
+    check(lib().amoe_gate_fwd(ctx(dev), ptr(state), ptr(pooled), ptr(params), params.numel(), B, E, arr, ctx_dim,
+                              hidden, float(temperature), mode, ptr(context), ptr(features), ptr(processed),
+                              ptr(logits), ptr(weights), ptr(combined), stream_ptr(dev)), "gate_fwd")
+    return dict(context=context, features=features, processed=processed, gate_logits=logits, weights=weights,
+                combined=combined)
+
+
+def policy_head(x, cvec, params, backbone_dim, ctx_dim, hidden, horizon):
+    """x: [B,h,w,Cf] conv4 output; cvec: [B,ctx_dim] fp32 or None."""
+    B, h, w, Cf = x.shape
+    dev = x.device
+    wp = torch.empty((B, 2 * horizon), device=dev, dtype=torch.float32)
+    spd = torch.empty((B, horizon), device=dev, dtype=torch.float32)
+    check(lib().amoe_policy_head_fwd(ctx(dev), ptr(x), ptr(cvec), ptr(params), params.numel(), B, h * w, Cf,
+                                     backbone_dim, ctx_dim, hidden, horizon, dtype_code(x.dtype), ptr(wp), ptr(spd),
+                                     stream_ptr(dev)), "policy_head_fwd")
+    return wp, spd
+
+
+def hungarian_cost(logits, boxes, tgt_boxes, tgt_labels, n_tgt, w_class, w_bbox, w_giou):
+    B, Q, Cc = logits.shape
+    D = boxes.shape[2]
+    Nmax = tgt_boxes.shape[1]
+    cost = torch.empty((B, Q, Nmax), device=logits.device, dtype=torch.float32)
+    check(lib().amoe_hungarian_cost_fwd(ctx(logits.device), ptr(logits), ptr(boxes), ptr(tgt_boxes), ptr(tgt_labels),
+                                        ptr(n_tgt), ptr(cost), B, Q, Cc, D, Nmax, float(w_class), float(w_bbox),
+                                        float(w_giou), stream_ptr(logits.device)), "hungarian_cost_fwd")
+    return cost
+
+
+def lsap_batched(cost_host: torch.Tensor, n_tgt_host: torch.Tensor, n_threads: int = 8):
+    """cost_host: [B,Q,Nmax] fp32 CPU tensor; returns (rows, cols, n_match) CPU tensors."""
+    B, Q, Nmax = cost_host.shape
+    K = min(Q, Nmax)
+    rows = torch.zeros((B, K), dtype=torch.int64)
+    cols = torch.zeros((B, K), dtype=torch.int64)
+    nm = torch.zeros((B,), dtype=torch.int32)
+    cost_host = cost_host.contiguous()
+    n_tgt_host = n_tgt_host.to(torch.int32).contiguous()
+    rc = lib().amoe_lsap_batched_host(ptr(cost_host), ptr(n_tgt_host), B, Q, Nmax, ptr(rows), ptr(cols), ptr(nm),
+                                      n_threads)
+    if rc == -2 or rc == -3:
+        # scipy.optimize.linear_sum_assignment raises ValueError for NaN/-inf or infeasible matrices
+        raise ValueError(lib().amoe_last_error().decode())
+    check(rc, "lsap_batched_host")
+    return rows, cols, nm

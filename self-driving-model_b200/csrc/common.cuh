@@ -1,0 +1,84 @@
+// Shared helpers for the AutoMoE sm_100a kernels (host + device).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/automoe_b200.h"
+
+struct amoe_ctx {
+  int device;
+  int sm_count;
+  std::atomic<int64_t> launches;
+  // cuTensorMapEncodeTiled resolved through the runtime (no -lcuda needed)
+  CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                           const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+};
+
+void amoe_set_error(const char* fmt, ...);
+
+#define AMOE_CHECK_CUDA(expr)                                                          \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      amoe_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -1;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define AMOE_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      amoe_set_error(__VA_ARGS__);   \
+      return -1;                     \
+    }                                \
+  } while (0)
+
+// launch-error check without synchronising
+#define AMOE_LAUNCH_OK(ctx)                                  \
+  do {                                                       \
+    (ctx)->launches.fetch_add(1, std::memory_order_relaxed); \
+    AMOE_CHECK_CUDA(cudaPeekAtLastError());                  \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- dtype-generic scalar load/store (device) ----
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}

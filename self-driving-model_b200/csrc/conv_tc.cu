@@ -1,0 +1,474 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a):
+//   tcgen05.mma (bf16 x bf16 -> fp32, accumulators in TMEM), operands staged in shared
+//   memory by TMA (cp.async.bulk.tensor, 128B swizzle), mbarrier producer/consumer
+//   pipeline, persistent CTAs, folded-BN scale/bias + residual + ReLU fused in the epilogue.
+//
+// GEMM view:  D[M, N] = sum over taps (kh,kw) and 64-channel chunks of  A_tap[M, 64] * W_tap[N, 64]^T
+//   M tile = 128 output pixels = a (nb x th x tw) patch (images x rows x cols), so the A
+//            operand of one tap is ONE TMA box of the NHWC input shifted by the tap offset;
+//            TMA zero-fills out-of-bounds coordinates = the convolution's zero padding.
+//   N tile = BLOCK_N output channels (64/128/256) = one TMA box of the packed weights
+//            [G*Cout][KH*KW*Cin] (K contiguous).
+//   Stride-2 convolutions read a "parity view" of the same memory: [N, H/2, 2, W/2, 2*C]
+//   so that every tap is again a dense box (no element strides needed).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> global).  Two TMEM
+// accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements per K chunk = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_TAPS = 49;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct Tap {
+  int c_off, dw, hp, dh;  // TMA start-coordinate offsets of this filter tap
+};
+
+struct Params {
+  int tw, th, nb;                   // M-tile patch: cols, rows, images (tw*th*nb == 128)
+  int tiles_w, tiles_h, tiles_b;    // patches per group
+  int n_tiles_n;                    // Cout / block_n
+  int G, B, Ho, Wo, Cout;
+  int block_n;
+  int num_taps, k_chunks;           // K iterations per tile = num_taps * k_chunks
+  int stages;
+  int relu, x_shared;
+  int total_tiles;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  Tap taps[MAX_TAPS];
+};
+
+// ------------------------------- PTX wrappers -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 B apart):
+// start address >>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct TileCoord {
+  int g, bt, ht, wt, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_tiles_n;
+  t /= p.n_tiles_n;
+  c.wt = t % p.tiles_w;
+  t /= p.tiles_w;
+  c.ht = t % p.tiles_h;
+  t /= p.tiles_h;
+  c.bt = t % p.tiles_b;
+  c.g = t / p.tiles_b;
+  return c;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B needs 1024 B alignment
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + (uint32_t)p.stages * A_STAGE_BYTES;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * MAX_STAGES + 2]);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  const int k_iters = p.num_taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, t);
+        const int n0 = (p.x_shared ? 0 : tc_.g * p.B) + tc_.bt * p.nb;
+        const int oh0 = tc_.ht * p.th, ow0 = tc_.wt * p.tw;
+        const int wrow0 = tc_.g * p.Cout + tc_.nt * p.block_n;
+        int kidx = 0;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const Tap tp = p.taps[tap];
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++kidx) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
+            tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
+                        tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW, bar_full + 8 * stage, kidx * BLOCK_K, wrow0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    const uint32_t idesc = make_idesc(p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);  // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_STRIDE);
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes have landed
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t a_desc = make_sw128_desc(smem_a + stage * A_STAGE_BYTES);
+          const uint64_t b_desc = make_sw128_desc(smem_b + stage * b_stage_bytes);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // advance 32 bytes (16 bf16) inside the 128B swizzle row: +2 in the >>4 address field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                      (uint32_t)((k | kk) != 0));
+          }
+          umma_commit(bar_empty + 8 * stage);                     // frees the smem slot
+          if (k == k_iters - 1) umma_commit(bar_tfull + 8 * as);  // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue ================================
+    const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    const int row = lg * 32 + lane;
+    const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const TileCoord tc_ = decode_tile(p, t);
+      const int nl = tc_.bt * p.nb + bi, oh = tc_.ht * p.th + hi, ow = tc_.wt * p.tw + wi;
+      const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
+      const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
+      const int64_t off = ((((int64_t)tc_.g * p.B + nl) * p.Ho + oh) * p.Wo + ow) * p.Cout + tc_.nt * p.block_n;
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (valid) {
+          const float* sc = p.scale + ch0 + c0;
+          const float* bs = p.bias + ch0 + c0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              f[j] = fmaf(__uint_as_float(acc[v * 8 + j]), __ldg(sc + v * 8 + j), __ldg(bs + v * 8 + j));
+            if (p.residual) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 rf = __bfloat1622float2(r2[j]);
+                f[2 * j] += rf.x;
+                f[2 * j + 1] += rf.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
+  if (Cin % 64 != 0 || Cout % 64 != 0) return false;
+  if (Cout > 256 && Cout % 256 != 0) return false;
+  if (sh != 1 && sh != 2) return false;
+  if (sw != 1 && sw != 2) return false;
+  if (sh == 2 && (H & 1)) return false;
+  if (sw == 2 && (W & 1)) return false;
+  return true;
+}
+
+}  // namespace tc
+
+int amoe_conv_tc_init(amoe_ctx* ctx) {
+  (void)ctx;
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tc::SMEM_BUDGET + 1024));
+  return 0;
+}
+
+int amoe_conv2d_simt(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
+                     const float* bias, const void* residual, void* y, int G, int x_shared, int B,
+                     int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw, int ph, int pw,
+                     int Ho, int Wo, int relu, int dtype, cudaStream_t st);
+
+static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
+                          const float* bias, const void* residual, void* y, int G, int x_shared,
+                          int B, int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw,
+                          int ph, int pw, int Ho, int Wo, int relu, cudaStream_t st) {
+  using namespace tc;
+  AMOE_REQUIRE(KH * KW <= MAX_TAPS, "conv_tc: %dx%d filter has more than %d taps", KH, KW, MAX_TAPS);
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+               "conv_tc: pointers must be 16-byte aligned");
+  Params p;
+  p.tw = std::min(128, pow2_ceil(Wo));
+  p.th = std::min(128 / p.tw, pow2_ceil(Ho));
+  p.nb = 128 / (p.tw * p.th);
+  p.tiles_w = ceil_div(Wo, p.tw);
+  p.tiles_h = ceil_div(Ho, p.th);
+  p.tiles_b = ceil_div(B, p.nb);
+  p.block_n = Cout >= 256 ? 256 : Cout;
+  p.n_tiles_n = Cout / p.block_n;
+  p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.num_taps = KH * KW;
+  p.k_chunks = Cin / BLOCK_K;
+  const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
+  p.stages = std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes);
+  p.relu = relu; p.x_shared = x_shared;
+  int64_t total = (int64_t)G * p.tiles_b * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  AMOE_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
+  p.total_tiles = (int)total;
+  p.scale = scale; p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.y = (__nv_bfloat16*)y;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      Tap& t = p.taps[kh * KW + kw];
+      int ho = kh - ph, wo = kw - pw;
+      if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
+      if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
+    }
+  if (total == 0) return 0;
+
+  // activation map: 5-D parity view (inner -> outer): Cv, Wv, P, Hv, N
+  const int NB = x_shared ? B : G * B;
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)(sw * Cin), (cuuint64_t)(W / sw), (cuuint64_t)sh, (cuuint64_t)(H / sh), (cuuint64_t)NB};
+    cuuint64_t strides[4] = {(cuuint64_t)sw * Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)sh * W * Cin * 2,
+                             (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.tw, 1u, (cuuint32_t)p.th, (cuuint32_t)p.nb};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = ctx->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+  }
+  {
+    const int Ktot = KH * KW * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)G * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  }
+  const int grid = std::min(p.total_tiles, ctx->sm_count);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" {
+
+int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w) {
+  return tc::supported(H, W, Cin, Cout, stride_h, stride_w) ? 1 : 0;
+}
+
+int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
+                    const float* bias, const void* residual, void* y, int G, int x_shared, int B,
+                    int H, int W, int Cin, int Cout, int KH, int KW, int stride_h, int stride_w,
+                    int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype, int impl, void* stream) {
+  AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv2d_fwd: NULL argument");
+  AMOE_REQUIRE(dtype == AMOE_F32 || dtype == AMOE_BF16, "amoe_conv2d_fwd: bad dtype %d", dtype);
+  AMOE_REQUIRE(G >= 1 && B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 &&
+                   stride_h > 0 && stride_w > 0 && Ho > 0 && Wo > 0,
+               "amoe_conv2d_fwd: bad shape");
+  // every tap of every output must stay within [-(K), H+K): padding is implicit zero
+  AMOE_REQUIRE((Ho - 1) * stride_h - pad_h < H && (Wo - 1) * stride_w - pad_w < W,
+               "amoe_conv2d_fwd: Ho/Wo inconsistent with input size");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = dtype == AMOE_BF16 && tc::supported(H, W, Cin, Cout, stride_h, stride_w);
+  if (impl == 2) AMOE_REQUIRE(tc_ok, "amoe_conv2d_fwd: tcgen05 path does not take this shape/dtype");
+  if (tc_ok && impl != 1)
+    return conv_tc_launch(ctx, x, w, scale, bias, residual, y, G, x_shared, B, H, W, Cin, Cout, KH, KW,
+                          stride_h, stride_w, pad_h, pad_w, Ho, Wo, relu, st);
+  return amoe_conv2d_simt(ctx, x, w, scale, bias, residual, y, G, x_shared, B, H, W, Cin, Cout, KH, KW,
+                          stride_h, stride_w, pad_h, pad_w, Ho, Wo, relu, dtype, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// Fused gate kernel: SimpleContextExtractor + expert extractors (MLP+LayerNorm on the
+// pooled expert logits) + GatingNetwork (context encoder, expert processors, gate MLP,
+// softmax, weighted combine, output projection) in ONE launch, fp32 throughout so the
+// top-1 routing matches the reference (SURVEY.md §7 "bit-exact top-1").
+//
+// One CTA owns FT frames; every weight row is streamed once per CTA with coalesced
+// 16-byte loads and reused for the FT frames; reductions are warp shuffles.
+//
+// Flat parameter layout (fp32; every tensor starts on a 4-float boundary, weights are
+// PyTorch [out,in] row-major) — must match models/automoe.py::_pack_gate_params:
+//   ctx.enc0.W[32,4] b[32] | ctx.enc3.W[ctx,32] b[ctx] | ctx.ln.g[ctx] b[ctx]
+//   per expert e: ext.W1[512,Ce] b1[512] | ext.W2[F,512] b2[F] | ext.ln.g[F] b[F]
+//   gate.ctxenc0.W[hid,ctx] b | gate.ctxenc3.W[hid,hid] b
+//   per expert e: proc.W0[P,F] b | proc.W3[P,P] b | proc.ln.g[P] b[P]
+//   gate.net0.W[hid,hid+P*E] b | gate.net3.W[E,hid] b | out_proj.W[P,P] b
+// with F = expert feature dim (256), P = processed dim (256).
+#include "common.cuh"
+#include "mlp.cuh"
+
+constexpr int GATE_MAX_E = 4;
+// mode bits (amoe_gate_fwd)
+constexpr int GATE_MODE_CTX_ONLY = 1;   // get_expert_weights: experts replaced by zeros, weights only
+constexpr int GATE_MODE_CTX_IN = 2;     // `state` holds an already-encoded context [B,ctx_dim]
+constexpr int GATE_MODE_FEAT_IN = 4;    // `pooled` holds expert features [E][B,F] (extractors skipped)
+constexpr int GATE_MODE_STOP_CTX = 8;   // stop after the context extractor
+constexpr int GATE_MODE_STOP_FEAT = 16; // stop after the expert extractors
+constexpr int EXT_HID = 512;     // expert_extractors.py:30,64,91
+
+struct GateDims {
+  int B, E, ctx_dim, hidden, F, P, sumC;
+  int n_ch[GATE_MAX_E];
+  float temperature;
+  int mode;
+};
+
+__global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
+    GateDims d, const float* __restrict__ state, const float* __restrict__ pooled,
+    const float* __restrict__ prm, float* __restrict__ context, float* __restrict__ features,
+    float* __restrict__ processed, float* __restrict__ gate_logits, float* __restrict__ weights,
+    float* __restrict__ combined) {
+  extern __shared__ __align__(16) float sm[];
+  const int f0 = blockIdx.x * GATE_FT;
+  const int gin = d.hidden + d.P * d.E;  // gate_network input width
+  // shared-memory carve-up (all row strides multiples of 4 floats)
+  const int ld_in = (int)al4(4 + d.sumC);
+  float* s_in = sm;                                   // [FT][ld_in]: state(4) | pooled(sumC)
+  float* s_ctx = s_in + GATE_FT * ld_in;              // [FT][ctx]
+  float* s_h = s_ctx + GATE_FT * (int)al4(d.ctx_dim); // [FT][512] scratch hidden
+  float* s_feat = s_h + GATE_FT * EXT_HID;            // [FT][F] current expert feature
+  float* s_gin = s_feat + GATE_FT * (int)al4(d.F);    // [FT][gin]  ctxenc | processed_0..E-1
+  float* s_t = s_gin + GATE_FT * (int)al4(gin);       // [FT][max(P,hid)] scratch
+  float* s_w = s_t + GATE_FT * (int)al4(max(d.P, d.hidden));  // [FT][E] logits then weights
+  const int ld_ctx = (int)al4(d.ctx_dim), ld_feat = (int)al4(d.F), ld_gin = (int)al4(gin),
+            ld_t = (int)al4(max(d.P, d.hidden));
+
+  const bool ctx_in = d.mode & GATE_MODE_CTX_IN, feat_in = d.mode & GATE_MODE_FEAT_IN;
+  const bool ctx_only = d.mode & GATE_MODE_CTX_ONLY;
+  for (int i = threadIdx.x; i < GATE_FT * ld_in; i += blockDim.x) {
+    int f = i / ld_in, c = i - f * ld_in;
+    float v = 0.f;
+    if (f0 + f < d.B) {
+      if (c < 4) v = ctx_in ? 0.f : state[(int64_t)(f0 + f) * 4 + c];
+      else if (c < 4 + d.sumC && !ctx_only && !feat_in && !(d.mode & GATE_MODE_STOP_CTX)) v = pooled[(int64_t)(f0 + f) * d.sumC + (c - 4)];
+    }
+    s_in[i] = v;
+  }
+  if (ctx_in) {
+    for (int i = threadIdx.x; i < GATE_FT * d.ctx_dim; i += blockDim.x) {
+      int f = i / d.ctx_dim, c = i - f * d.ctx_dim;
+      s_ctx[f * ld_ctx + c] = (f0 + f < d.B) ? state[(int64_t)(f0 + f) * d.ctx_dim + c] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- SimpleContextExtractor (context_features.py:143-165) ----
+  const float* p = prm;
+  {
+    const float* W0 = p; p += al4(32 * 4);
+    const float* b0 = p; p += al4(32);
+    const float* W3 = p; p += al4((int64_t)d.ctx_dim * 32);
+    const float* b3 = p; p += al4(d.ctx_dim);
+    const float* g = p; p += al4(d.ctx_dim);
+    const float* bb = p; p += al4(d.ctx_dim);
+    if (!ctx_in) {
+      linear_ft(W0, b0, s_in, ld_in, 4, s_h, EXT_HID, 32, true);
+      linear_ft(W3, b3, s_h, EXT_HID, 32, s_ctx, ld_ctx, d.ctx_dim, false);
+      layernorm_ft(s_ctx, ld_ctx, d.ctx_dim, g, bb);
+    }
+    if (context) store_rows(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
+    if (d.mode & GATE_MODE_STOP_CTX) return;
+  }
+
+  // ---- expert extractors (expert_extractors.py:27-35) -> features; kept in global, the
+  //      processors below re-read them from smem one expert at a time ----
+  const float* ext_prm[GATE_MAX_E];
+  for (int e = 0; e < d.E; ++e) {
+    ext_prm[e] = p;
+    p += al4((int64_t)EXT_HID * d.n_ch[e]) + al4(EXT_HID) + al4((int64_t)d.F * EXT_HID) + al4(d.F) + 2 * al4(d.F);
+  }
+  // gating context encoder (gating_network.py:12-20)
+  {
+    const float* W0 = p; p += al4((int64_t)d.hidden * d.ctx_dim);
+    const float* b0 = p; p += al4(d.hidden);
+    const float* W3 = p; p += al4((int64_t)d.hidden * d.hidden);
+    const float* b3 = p; p += al4(d.hidden);
+    if (!(d.mode & GATE_MODE_STOP_FEAT)) {
+      linear_ft(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true);
+      linear_ft(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true);
+    }
+  }
+  int ch_off = 4;
+  for (int e = 0; e < d.E; ++e) {
+    const float* q = ext_prm[e];
+    const float* W1 = q; q += al4((int64_t)EXT_HID * d.n_ch[e]);
+    const float* b1 = q; q += al4(EXT_HID);
+    const float* W2 = q; q += al4((int64_t)d.F * EXT_HID);
+    const float* b2 = q; q += al4(d.F);
+    const float* g = q; q += al4(d.F);
+    const float* bb = q;
+    const float* PW0 = p; p += al4((int64_t)d.P * d.F);
+    const float* Pb0 = p; p += al4(d.P);
+    const float* PW3 = p; p += al4((int64_t)d.P * d.P);
+    const float* Pb3 = p; p += al4(d.P);
+    const float* Pg = p; p += al4(d.P);
+    const float* Pbb = p; p += al4(d.P);
+    float* s_proc = s_gin + d.hidden + e * d.P;
+    if (!ctx_only) {
+      if (feat_in) {
+        for (int i = threadIdx.x; i < GATE_FT * d.F; i += blockDim.x) {
+          int f = i / d.F, c = i - f * d.F;
+          s_feat[f * ld_feat + c] = (f0 + f < d.B) ? pooled[((int64_t)e * d.B + f0 + f) * d.F + c] : 0.f;
+        }
+        __syncthreads();
+      } else {
+        linear_ft(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, EXT_HID, EXT_HID, true);
+        linear_ft(W2, b2, s_h, EXT_HID, EXT_HID, s_feat, ld_feat, d.F, false);
+        layernorm_ft(s_feat, ld_feat, d.F, g, bb);
+        if (features) store_rows(features + (int64_t)e * d.B * d.F, d.F, s_feat, ld_feat, d.F, f0, d.B);
+      }
+      if (!(d.mode & GATE_MODE_STOP_FEAT)) {
+        // ExpertOutputProcessor (gating_network.py:37-43)
+        linear_ft(PW0, Pb0, s_feat, ld_feat, d.F, s_t, ld_t, d.P, true);
+        linear_ft(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false);
+        layernorm_ft(s_proc, ld_gin, d.P, Pg, Pbb);
+        if (processed) store_rows(processed + (int64_t)e * d.B * d.P, d.P, s_proc, ld_gin, d.P, f0, d.B);
+      }
+    } else {
+      // get_expert_weights (gating_network.py:177-199): zeros stand in for the experts
+      for (int i = threadIdx.x; i < GATE_FT * d.P; i += blockDim.x) s_proc[(i / d.P) * ld_gin + (i % d.P)] = 0.f;
+      __syncthreads();
+    }
+    ch_off += d.n_ch[e];
+  }
+
+  if (d.mode & GATE_MODE_STOP_FEAT) return;
+
+  // ---- gate MLP + softmax (gating_network.py:94-99,141-160) ----
+  {
+    const float* W0 = p; p += al4((int64_t)d.hidden * gin);
+    const float* b0 = p; p += al4(d.hidden);
+    const float* W3 = p; p += al4((int64_t)d.E * d.hidden);
+    const float* b3 = p; p += al4(d.E);
+    linear_ft(W0, b0, s_gin, ld_gin, gin, s_t, ld_t, d.hidden, true);
+    linear_ft(W3, b3, s_t, ld_t, d.hidden, s_w, GATE_MAX_E, d.E, false);
+    if (threadIdx.x < GATE_FT) {
+      int f = threadIdx.x;
+      float* lg = s_w + f * GATE_MAX_E;
+      float mx = -INFINITY;
+      for (int e = 0; e < d.E; ++e) {
+        if (gate_logits && f0 + f < d.B) gate_logits[(int64_t)(f0 + f) * d.E + e] = lg[e];
+        lg[e] = lg[e] / d.temperature;
+        mx = fmaxf(mx, lg[e]);
+      }
+      float ssum = 0.f;
+      for (int e = 0; e < d.E; ++e) {
+        lg[e] = expf(lg[e] - mx);
+        ssum += lg[e];
+      }
+      for (int e = 0; e < d.E; ++e) {
+        lg[e] = lg[e] / ssum;
+        if (weights && f0 + f < d.B) weights[(int64_t)(f0 + f) * d.E + e] = lg[e];
+      }
+    }
+    __syncthreads();
+  }
+  if (ctx_only) return;
+
+  // ---- weighted combine + output projection (gating_network.py:162-168) ----
+  {
+    const float* W = p; p += al4((int64_t)d.P * d.P);
+    const float* b = p;
+    for (int i = threadIdx.x; i < GATE_FT * d.P; i += blockDim.x) {
+      int f = i / d.P, c = i - f * d.P;
+      float acc = 0.f;  // combined_output starts at zeros and adds w_e * processed_e in order
+      for (int e = 0; e < d.E; ++e) acc += s_w[f * GATE_MAX_E + e] * s_gin[f * ld_gin + d.hidden + e * d.P + c];
+      s_h[f * EXT_HID + c] = acc;
+    }
+    __syncthreads();
+    linear_ft(W, b, s_h, EXT_HID, d.P, s_t, ld_t, d.P, false);
+    if (combined) store_rows(combined, d.P, s_t, ld_t, d.P, f0, d.B);
+  }
+}
+
+static int64_t gate_param_count(const GateDims& d) {
+  int64_t n = al4(32 * 4) + al4(32) + al4((int64_t)d.ctx_dim * 32) + 3 * al4(d.ctx_dim);
+  for (int e = 0; e < d.E; ++e)
+    n += al4((int64_t)EXT_HID * d.n_ch[e]) + al4(EXT_HID) + al4((int64_t)d.F * EXT_HID) + 3 * al4(d.F);
+  n += al4((int64_t)d.hidden * d.ctx_dim) + al4(d.hidden) + al4((int64_t)d.hidden * d.hidden) + al4(d.hidden);
+  for (int e = 0; e < d.E; ++e)
+    n += al4((int64_t)d.P * d.F) + al4(d.P) + al4((int64_t)d.P * d.P) + 3 * al4(d.P);
+  int gin = d.hidden + d.P * d.E;
+  n += al4((int64_t)d.hidden * gin) + al4(d.hidden) + al4((int64_t)d.E * d.hidden) + al4(d.E);
+  n += al4((int64_t)d.P * d.P) + al4(d.P);
+  return n;
+}
+
+extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* pooled,
+                             const float* params, int64_t n_params, int B, int E,
+                             const int* n_ch_host, int ctx_dim, int hidden, float temperature,
+                             int mode, float* context, float* features, float* processed,
+                             float* gate_logits, float* weights, float* combined, void* stream) {
+  AMOE_REQUIRE(ctx && state && params && n_ch_host, "amoe_gate_fwd: NULL argument");
+  AMOE_REQUIRE(E >= 1 && E <= GATE_MAX_E, "amoe_gate_fwd: E=%d out of range [1,%d]", E, GATE_MAX_E);
+  AMOE_REQUIRE((mode & (GATE_MODE_CTX_ONLY | GATE_MODE_STOP_CTX)) || pooled, "amoe_gate_fwd: pooled is NULL");
+  AMOE_REQUIRE(temperature > 0.f, "amoe_gate_fwd: temperature must be > 0");
+  GateDims d;
+  d.B = B; d.E = E; d.ctx_dim = ctx_dim; d.hidden = hidden; d.F = 256; d.P = 256;
+  d.temperature = temperature; d.mode = mode; d.sumC = 0;
+  for (int e = 0; e < GATE_MAX_E; ++e) d.n_ch[e] = 0;
+  for (int e = 0; e < E; ++e) {
+    AMOE_REQUIRE(n_ch_host[e] >= 1, "amoe_gate_fwd: n_ch[%d]=%d", e, n_ch_host[e]);
+    d.n_ch[e] = n_ch_host[e];
+    d.sumC += n_ch_host[e];
+  }
+  AMOE_REQUIRE(hidden <= EXT_HID && ctx_dim <= EXT_HID && hidden >= 1 && ctx_dim >= 1,
+               "amoe_gate_fwd: hidden/ctx_dim must be in [1,512]");
+  int64_t need = gate_param_count(d);
+  AMOE_REQUIRE(n_params == need, "amoe_gate_fwd: params has %lld floats, layout needs %lld",
+               (long long)n_params, (long long)need);
+  if (B == 0) return 0;
+  int gin = hidden + d.P * E;
+  size_t smem = sizeof(float) * GATE_FT *
+                (al4(4 + d.sumC) + al4(ctx_dim) + EXT_HID + al4(d.F) + al4(gin) +
+                 al4(d.P > hidden ? d.P : hidden) + GATE_MAX_E);
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(gate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gate_fused_kernel<<<ceil_div(B, GATE_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
+      d, state, pooled, params, context, features, processed, gate_logits, weights, combined);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}

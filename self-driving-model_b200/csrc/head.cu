@@ -1,0 +1,167 @@
+// Expert heads: 1x1 classifier conv + global mean, bilinear up-sampling writer
+// (NHWC low-res fp32 -> NCHW full-res), and a plain NCHW spatial mean.
+#include "common.cuh"
+
+// ---- 1x1 conv + mean over pixels -------------------------------------------
+// One CTA per image.  Phase 1: low[b,p,n] = b[n] + sum_c x[b,p,c]*w[n,c] with one
+// warp per (pixel, n) pair group; phase 2: pooled[b,n] = mean_p low[b,p,n] summed in
+// a fixed order (deterministic, the gate's top-1 depends on it).
+template <typename T>
+__global__ __launch_bounds__(256) void head1x1_pool_kernel(const T* __restrict__ x,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ bias,
+                                                           float* __restrict__ low,
+                                                           float* __restrict__ pooled, int pooled_ld,
+                                                           int HW, int Cin, int N) {
+  extern __shared__ float sw[];  // [N][Cin] weights
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const T* xb = x + (int64_t)b * HW * Cin;
+  float* lb = low + (int64_t)b * HW * N;
+  for (int p = warp; p < HW; p += nwarp) {
+    const T* xp = xb + (int64_t)p * Cin;
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+      for (int c = lane; c < Cin; c += 32) s = fmaf(ld_as_float<T>(xp + c), sw[n * Cin + c], s);
+      s = warp_sum(s);
+      if (lane == 0) lb[(int64_t)p * N + n] = s + bias[n];
+    }
+  }
+  __syncthreads();  // low[] of this image is complete and visible to the block
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += lb[(int64_t)p * N + n];
+    pooled[(int64_t)b * pooled_ld + n] = s / (float)HW;
+  }
+}
+
+// ---- bilinear up-sampling writer ---------------------------------------------
+// out[b,c,y,x] = bilinear(low[b,:,:,c]) with PyTorch's align_corners=False rule
+// (aten upsample_bilinear2d: src = max(scale*(dst+0.5)-0.5, 0), scale = in/out).
+// One thread writes 8 consecutive x (16 B in bf16).  Grid: (W/8-chunks, H, B*C).
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+  float s = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)s, in_size - 1);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <typename T>
+__global__ __launch_bounds__(256) void upsample_bilinear_nchw_kernel(const float* __restrict__ low,
+                                                                     T* __restrict__ out, int h,
+                                                                     int w, int C, int H, int W,
+                                                                     float sh, float sw_, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int wc = (W + 7) >> 3;
+  int xc = (int)(i % wc);
+  int64_t r = i / wc;
+  int y = (int)(r % H);
+  r /= H;
+  int c = (int)(r % C);
+  int64_t b = r / C;
+  int y0, y1;
+  float ly;
+  src_index(sh, y, h, y0, y1, ly);
+  const float hy = 1.f - ly;
+  const float* l0 = low + ((b * h + y0) * w) * (int64_t)C + c;
+  const float* l1p = low + ((b * h + y1) * w) * (int64_t)C + c;
+  float v[8];
+  int x0 = xc * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int x = x0 + j;
+    int xa, xb;
+    float lx;
+    src_index(sw_, min(x, W - 1), w, xa, xb, lx);
+    float hx = 1.f - lx;
+    float v00 = __ldg(l0 + (int64_t)xa * C), v01 = __ldg(l0 + (int64_t)xb * C);
+    float v10 = __ldg(l1p + (int64_t)xa * C), v11 = __ldg(l1p + (int64_t)xb * C);
+    v[j] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  }
+  T* o = out + ((b * C + c) * (int64_t)H + y) * W + x0;
+  if (x0 + 8 <= W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+    if constexpr (sizeof(T) == 2) {
+      uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      __stcs(reinterpret_cast<uint4*>(o), pk);
+    } else {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+      __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+  } else {
+    for (int j = 0; j < 8 && x0 + j < W; ++j) st_from_float<T>(o + j, v[j]);
+  }
+}
+
+// ---- mean over H*W of NCHW: one warp per (b,c) --------------------------------
+template <typename T>
+__global__ void mean_hw_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t BC, int HW) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (wid >= BC) return;
+  const T* p = x + wid * HW;
+  float s = 0.f;
+  for (int i = lane; i < HW; i += 32) s += ld_as_float<T>(p + i);
+  s = warp_sum(s);
+  if (lane == 0) out[wid] = s / (float)HW;
+}
+
+extern "C" {
+
+int amoe_head1x1_pool_fwd(amoe_ctx* ctx, const void* x, const float* w, const float* b, float* low,
+                          float* pooled, int pooled_ld, int B, int HW, int Cin, int N, int x_dtype,
+                          void* stream) {
+  AMOE_REQUIRE(ctx && x && w && b && low && pooled, "amoe_head1x1_pool_fwd: NULL argument");
+  size_t smem = (size_t)N * Cin * sizeof(float);
+  AMOE_REQUIRE(smem <= 48 * 1024, "amoe_head1x1_pool_fwd: N*Cin=%d too large", N * Cin);
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == AMOE_BF16)
+    head1x1_pool_kernel<__nv_bfloat16><<<B, 256, smem, st>>>((const __nv_bfloat16*)x, w, b, low, pooled, pooled_ld, HW, Cin, N);
+  else if (x_dtype == AMOE_F32)
+    head1x1_pool_kernel<float><<<B, 256, smem, st>>>((const float*)x, w, b, low, pooled, pooled_ld, HW, Cin, N);
+  else
+    AMOE_REQUIRE(false, "amoe_head1x1_pool_fwd: bad dtype %d", x_dtype);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_upsample_bilinear_nchw_fwd(amoe_ctx* ctx, const float* low, void* out, int B, int h, int w,
+                                    int C, int H, int W, int out_dtype, void* stream) {
+  AMOE_REQUIRE(ctx && low && out, "amoe_upsample_bilinear_nchw_fwd: NULL argument");
+  int64_t total = (int64_t)B * C * H * ((W + 7) / 8);
+  if (total == 0) return 0;
+  float sh = (float)h / (float)H, sw_ = (float)w / (float)W;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (out_dtype == AMOE_BF16)
+    upsample_bilinear_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(low, (__nv_bfloat16*)out, h, w, C, H, W, sh, sw_, total);
+  else if (out_dtype == AMOE_F32)
+    upsample_bilinear_nchw_kernel<float><<<blocks, 256, 0, st>>>(low, (float*)out, h, w, C, H, W, sh, sw_, total);
+  else
+    AMOE_REQUIRE(false, "amoe_upsample_bilinear_nchw_fwd: bad dtype %d", out_dtype);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_mean_hw_nchw_fwd(amoe_ctx* ctx, const void* x, float* out, int B, int C, int HW, int dtype,
+                          void* stream) {
+  AMOE_REQUIRE(ctx && x && out, "amoe_mean_hw_nchw_fwd: NULL argument");
+  int64_t BC = (int64_t)B * C;
+  if (BC == 0) return 0;
+  unsigned blocks = (unsigned)((BC * 32 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == AMOE_BF16)
+    mean_hw_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, BC, HW);
+  else if (dtype == AMOE_F32)
+    mean_hw_nchw_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, out, BC, HW);
+  else
+    AMOE_REQUIRE(false, "amoe_mean_hw_nchw_fwd: bad dtype %d", dtype);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+"""AutoMoE composite model — drop-in for models/automoe.py (create_automoe_model,
+AutoMoE.forward / get_expert_weights / load_expert_checkpoints / freeze_experts /
+unfreeze_experts) with the same constructor config, attribute names, forward dict and
+state_dict keys; the forward runs on hand-written sm_100a kernels through the C-ABI.
+
+Forward schedule (reference automoe.py:189-233, re-designed):
+  image NCHW fp32 -> NHWC (one kernel, shared by experts and policy)
+  3 experts: grouped ResNet-18 trunks + heads (tcgen05 implicit-GEMM convs, BN folded),
+             1x1 classifier + pooled mean, bilinear x32 writer for the full-res logits
+  ONE fused kernel: context extractor + expert extractors + gating + softmax + combine
+  policy: 4 convs + fused pool/fc/MLP-heads kernel
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from .. import _ops
+from ._gatepack import pack_gate_params, require_eval
+from ._precision import resolve_dtype
+from .context.context_features import create_context_extractor
+from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
+from .experts._base import run_experts
+from .experts._trunk import params_stamp
+from .experts.expert_extractors import create_expert_extractors
+from .gating.gating_network import GatingNetwork
+from .policy.trajectory_head import TrajectoryPolicy
+
+
+class AutoMoE(nn.Module):
+    """Complete AutoMoE: Mixture of Experts Self-Driving Model"""
+
+    def __init__(self, expert_configs: List[Dict], gating_config: Dict, context_config: Dict,
+                 policy_config: Dict, device: str = 'cuda', precision: str = 'auto'):
+        super().__init__()
+        self.device = device
+        self.expert_configs = expert_configs
+        self.gating_config = gating_config
+        self.context_config = context_config
+        self.policy_config = policy_config
+        self.precision = precision
+
+        self.experts = self._create_experts()
+        self.expert_extractors = create_expert_extractors(expert_configs)
+        self.context_extractor = create_context_extractor(context_config)
+        self.gating_network = self._create_gating_network()
+        self.policy_head = self._create_policy_head()
+        self._expert_packs = {}
+        self._gate_flat = {}
+        self.to(device)
+
+    def _create_experts(self) -> nn.ModuleList:
+        experts = nn.ModuleList()
+        for config in self.expert_configs:
+            expert_type = config['type']
+            if expert_type == 'detection':
+                expert = BDDDetectionExpert(num_classes=config.get('num_classes', 10),
+                                            pretrained_backbone=config.get('pretrained_backbone', True))
+            elif expert_type == 'segmentation':
+                expert = BDDSegmentationExpert(num_classes=config.get('num_classes', 19),
+                                               pretrained_backbone=config.get('pretrained_backbone', True))
+            elif expert_type == 'drivable':
+                expert = BDDDrivableExpert(num_classes=config.get('num_classes', 3),
+                                           pretrained_backbone=config.get('pretrained_backbone', True))
+            elif expert_type == 'nuscenes':
+                raise NotImplementedError("the nuScenes expert is not part of the B200 hot path yet (SURVEY.md §8f)")
+            else:
+                raise ValueError(f"Unknown expert type: {expert_type}")
+            experts.append(expert)
+        return experts
+
+    def _create_gating_network(self) -> GatingNetwork:
+        num_experts = len(self.expert_configs)
+        expert_output_dims = [config.get('output_dim', 256) for config in self.expert_configs]
+        # top_k / noise_* / apply_topk_at_eval in the JSON are not forwarded (automoe.py:83-91)
+        return GatingNetwork(
+            num_experts=num_experts,
+            context_dim=self.context_config.get('context_dim', 64),
+            expert_output_dims=expert_output_dims,
+            processed_dim=self.gating_config.get('processed_dim', 256),
+            hidden_dim=self.gating_config.get('hidden_dim', 128),
+            temperature=self.gating_config.get('temperature', 1.0),
+            use_softmax=self.gating_config.get('use_softmax', True))
+
+    def _create_policy_head(self) -> TrajectoryPolicy:
+        return TrajectoryPolicy(
+            horizon=self.policy_config.get('num_waypoints', 10),
+            context_dim=self.gating_config.get('processed_dim', 256),
+            backbone_dim=self.policy_config.get('backbone_dim', 512))
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _last_col(t: torch.Tensor) -> torch.Tensor:
+        """[B,1] passes through; [B,H] -> last column; higher rank -> flattened last element
+        (automoe.py:108-134)."""
+        if t.dim() == 2 and t.size(1) > 1:
+            return t[:, -1:]
+        if t.dim() > 2:
+            return t.reshape(t.size(0), -1)[:, -1:]
+        return t
+
+    def _vehicle_state(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """[B,4] (speed, steering, throttle, brake) exactly as _extract_context_features builds it."""
+        if self.context_config.get('type', 'simple') != 'simple':
+            raise NotImplementedError("context type 'full' is dead code in the reference")
+        speed = batch['speed']
+        speed_in = speed[:, -1:] if (speed.dim() == 2 and speed.size(1) > 1) else speed
+        if all(k in batch for k in ('speed', 'steering', 'throttle', 'brake')):
+            cols = [speed_in] + [self._last_col(batch[k]) for k in ('steering', 'throttle', 'brake')]
+        else:
+            z = torch.zeros(speed_in.size(0), 1, device=speed_in.device)
+            cols = [speed_in, z, z, z]
+        return torch.cat([c.reshape(c.size(0), 1).float() for c in cols], dim=-1).contiguous()
+
+    def _gate_params(self, device, n_ch):
+        stamp = params_stamp([self.context_extractor, self.expert_extractors, self.gating_network])
+        key = device.index
+        g = self._gate_flat.get(key)
+        if g is None or g[0] != stamp:
+            flat = pack_gate_params(self.context_extractor, list(self.expert_extractors.extractors),
+                                    self.gating_network, n_ch, self.context_extractor.context_dim,
+                                    self.gating_network.hidden_dim, device)
+            g = (stamp, flat)
+            self._gate_flat[key] = g
+        return g[1]
+
+    def _extract_context_features(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        state = self._vehicle_state(batch)
+        return self.context_extractor(state[:, 0:1], state[:, 1:2], state[:, 2:3], state[:, 3:4])
+
+    def _run_experts(self, batch: Dict[str, torch.Tensor]) -> List:
+        """All experts on batch['image'] in grouped launches.  Unlike the reference
+        (automoe.py:181-185) an expert failure raises instead of being masked by zeros."""
+        outs, _ = run_experts(list(self.experts), batch['image'], resolve_dtype(self.precision), self._expert_packs)
+        return outs
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        require_eval(self, "AutoMoE")
+        image = batch['image']
+        if not image.is_cuda:
+            raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+        dtype = resolve_dtype(self.precision)
+        state = self._vehicle_state(batch).to(image.device)
+        x_nhwc = _ops.image_to_nhwc(image, 4, dtype)
+
+        expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc)
+
+        gn = self.gating_network
+        g = _ops.gate(state, aux['pooled'], self._gate_params(image.device, aux['n_ch']), aux['n_ch'],
+                      self.context_extractor.context_dim, gn.hidden_dim, gn.temperature)
+
+        policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype)
+        speed_seq = policy_output.get('speed')
+        speed_out = None
+        if speed_seq is not None and speed_seq.dim() == 2:
+            speed_out = speed_seq[:, -1:].contiguous()
+
+        return {
+            'waypoints': policy_output['waypoints'],
+            'speed': speed_out if speed_out is not None else speed_seq,
+            'speed_seq': speed_seq,
+            'expert_weights': g['weights'],
+            'expert_outputs': expert_outputs,
+            'context_features': g['context'],
+            'combined_features': g['combined'],
+            'gate_logits': g['gate_logits'],
+        }
+
+    def get_expert_weights(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Get expert weights without running experts (for analysis)"""
+        context_features = self._extract_context_features(batch)
+        return self.gating_network.get_expert_weights(context_features)
+
+    def load_expert_checkpoints(self, checkpoint_paths: List[str]):
+        """Load pre-trained expert checkpoints (automoe.py:240-267)"""
+        if len(checkpoint_paths) != len(self.experts):
+            raise ValueError(f"Expected {len(self.experts)} checkpoint paths, got {len(checkpoint_paths)}")
+        for i, (expert, checkpoint_path) in enumerate(zip(self.experts, checkpoint_paths)):
+            if checkpoint_path and checkpoint_path != '':
+                try:
+                    checkpoint = torch.load(checkpoint_path, map_location=self.device)
+                    state_dict = checkpoint.get('model_state_dict', checkpoint)
+                    expert.load_state_dict(state_dict)
+                    print(f"Loaded checkpoint for expert {i}: {checkpoint_path}")
+                except Exception as e:
+                    warnings.warn(f"Failed to load checkpoint for expert {i}: {str(e)}")
+
+    def freeze_experts(self):
+        """Freeze expert parameters during gating network training"""
+        for expert in self.experts:
+            for param in expert.parameters():
+                param.requires_grad = False
+
+    def unfreeze_experts(self):
+        """Unfreeze expert parameters for joint training"""
+        for expert in self.experts:
+            for param in expert.parameters():
+                param.requires_grad = True
+
+
+def create_automoe_model(config: Dict, device: str = 'cuda') -> AutoMoE:
+    """Create AutoMoE model from configuration (same schema as models/configs/automoe/model_config.json;
+    optional extra key "precision": "auto" | "bf16" | "fp32")."""
+    return AutoMoE(
+        expert_configs=config['experts'],
+        gating_config=config['gating'],
+        context_config=config['context'],
+        policy_config=config['policy'],
+        device=device,
+        precision=config.get('precision', 'auto'),
+    )

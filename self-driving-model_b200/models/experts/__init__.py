@@ -1,0 +1,5 @@
+from .bdd_detection_expert import BDDDetectionExpert
+from .bdd_drivable_expert import BDDDrivableExpert
+from .bdd_segmentation_expert import BDDSegmentationExpert
+
+__all__ = ["BDDDetectionExpert", "BDDDrivableExpert", "BDDSegmentationExpert"]

@@ -1,0 +1,73 @@
+"""Common forward of the three BDD perception experts (grouped or stand-alone)."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from ... import _ops
+from .._precision import resolve_dtype
+from ._trunk import TrunkPack, pack_trunks, params_stamp, run_trunks
+
+
+class BDDExpertBase(nn.Module):
+    """ResNet-18 trunk + 3x3/ReLU/1x1 head.  Sub-classes name the head attribute
+    (`head` / `decoder`) exactly as the reference does so state_dict keys match."""
+
+    head_attr = "head"
+    upsample_to_input = False
+
+    def __init__(self):
+        super().__init__()
+        self._packs = {}
+        self.precision = "auto"
+
+    def head_module(self):
+        return getattr(self, self.head_attr)
+
+    def out_channels(self) -> int:
+        return self.head_module()[2].weight.shape[0]
+
+    # -- reference forward signature: forward(x: [B,3,H,W]) --
+    def forward(self, x: torch.Tensor):
+        outs, _ = run_experts([self], x, resolve_dtype(self.precision), self._packs)
+        return outs[0]
+
+    def format_output(self, low: torch.Tensor, H: int, W: int, dtype: torch.dtype):
+        raise NotImplementedError
+
+
+def _check_eval(experts):
+    for e in experts:
+        if e.training:
+            raise NotImplementedError(
+                "automoe_b200 experts run eval-mode BatchNorm folded into the conv epilogue; "
+                "train-mode (batch-statistics) BatchNorm is not implemented yet - call .eval() on the experts")
+
+
+def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None):
+    """Run G experts on the same image batch in grouped launches.
+
+    Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
+    models/automoe.py:156-187 (_run_experts) + the pooled statistics the extractors need.
+    """
+    if not image.is_cuda:
+        raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+    _check_eval(experts)
+    stamp = params_stamp(experts)
+    key = (dtype, image.device.index)
+    pack: TrunkPack = cache.get(key)
+    if pack is None or pack.stamp != stamp:
+        pack = pack_trunks(experts, [e.head_module() for e in experts], dtype, image.device)
+        cache[key] = pack
+    B, _, H, W = image.shape
+    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc)
+    outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
+    # mean over the up-sampled map == mean over the low-res map only for integer scale factors
+    off = 0
+    for e, out, n in zip(experts, outs, pack.n_ch):
+        if e.upsample_to_input and (H % h != 0 or W % w != 0):
+            pooled[:, off:off + n] = _ops.mean_hw_nchw(out)
+        off += n
+    return outs, dict(pooled=pooled, n_ch=pack.n_ch)

@@ -1,0 +1,156 @@
+"""ResNet-18 trunk + 2-conv head shared by the three BDD experts, run through the
+sm_100a kernels for G experts at once ("grouped": activations stacked on the batch axis,
+weights on the Cout axis).
+
+Parameter holders reproduce the attribute names of torchvision.models.resnet18 sliced
+with children()[:-2] (reference: models/experts/bdd_detection_expert.py:9-10), so the
+state_dict keys are identical (experts.N.backbone.4.0.conv1.weight, ...).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import _ops
+
+
+class ParamHolder(nn.Sequential):
+    """Container that owns parameters but is never executed: the math lives in the kernels."""
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("parameter holder: call the owning expert/model, not this container")
+
+
+class BasicBlock(nn.Module):
+    """torchvision.models.resnet.BasicBlock attribute layout (conv1,bn1,relu,conv2,bn2,downsample)."""
+
+    def __init__(self, inplanes: int, planes: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = None
+        if stride != 1 or inplanes != planes:
+            self.downsample = ParamHolder(nn.Conv2d(inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+        self.stride = stride
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("parameter holder: call the owning expert/model, not this block")
+
+
+def make_resnet18_trunk(pretrained: bool = False) -> ParamHolder:
+    """children()[:-2] of resnet18: conv1, bn1, relu, maxpool, layer1..layer4 (indices 0..7)."""
+    layers = [nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+              nn.MaxPool2d(3, 2, 1)]
+    inplanes = 64
+    for planes, stride in ((64, 1), (128, 2), (256, 2), (512, 2)):
+        layers.append(ParamHolder(BasicBlock(inplanes, planes, stride), BasicBlock(planes, planes, 1)))
+        inplanes = planes
+    trunk = ParamHolder(*layers)
+    # torchvision init (resnet.py: kaiming_normal_ fan_out/relu for convs, BN weight 1 / bias 0)
+    for m in trunk.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+    if pretrained:
+        try:
+            import torchvision.models as tvm  # the reference's source of ImageNet weights
+            sd = tvm.resnet18(pretrained=True).state_dict()
+            names = ["conv1", "bn1", "relu", "maxpool", "layer1", "layer2", "layer3", "layer4"]
+            remap = {}
+            for k, v in sd.items():
+                head, _, rest = k.partition(".")
+                if head in names:
+                    remap[f"{names.index(head)}.{rest}"] = v
+            trunk.load_state_dict(remap)
+        except Exception as e:  # no network in most deployments; a checkpoint is loaded afterwards
+            import warnings
+            warnings.warn(f"pretrained_backbone=True but ImageNet weights are unavailable ({e}); using random init")
+    return trunk
+
+
+def make_head(out_channels: int) -> ParamHolder:
+    """nn.Sequential(Conv2d(512,256,3,padding=1), ReLU, Conv2d(256,out,1)) — bdd_*_expert.py:12-16."""
+    return ParamHolder(nn.Conv2d(512, 256, kernel_size=3, padding=1), nn.ReLU(), nn.Conv2d(256, out_channels, kernel_size=1))
+
+
+@dataclass
+class TrunkPack:
+    dtype: torch.dtype
+    G: int
+    stem: _ops.PackedConv
+    blocks: list            # [(conv1, conv2, down|None)]
+    head3: _ops.PackedConv  # 3x3 512->256 + bias + ReLU (grouped)
+    head1_w: List[torch.Tensor]  # per expert [N,256] fp32
+    head1_b: List[torch.Tensor]
+    n_ch: List[int]
+    stamp: tuple
+
+
+def params_stamp(modules) -> tuple:
+    """Cheap change detector for cached packs: in-place updates bump Tensor._version,
+    .to()/load swaps change data_ptr."""
+    v = 0
+    first = None
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            v += t._version
+            if first is None:
+                first = t.data_ptr()
+    return (v, first)
+
+
+def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
+    """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
+    G = len(experts)
+    bbs = [e.backbone for e in experts]
+    stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
+    blocks = []
+    for li in range(4, 8):
+        for bi in range(2):
+            blks = [bb[li][bi] for bb in bbs]
+            c1 = _ops.pack_conv([b.conv1 for b in blks], [b.bn1 for b in blks], dtype, device, relu=True)
+            c2 = _ops.pack_conv([b.conv2 for b in blks], [b.bn2 for b in blks], dtype, device, relu=True)
+            dn = None
+            if blks[0].downsample is not None:
+                dn = _ops.pack_conv([b.downsample[0] for b in blks], [b.downsample[1] for b in blks], dtype, device,
+                                    relu=False)
+            blocks.append((c1, c2, dn))
+    head3 = _ops.pack_conv([h[0] for h in heads], None, dtype, device, relu=True)
+    w1 = [h[2].weight.detach().to(device=device, dtype=torch.float32).reshape(h[2].weight.shape[0], -1).contiguous()
+          for h in heads]
+    b1 = [h[2].bias.detach().to(device=device, dtype=torch.float32).contiguous() for h in heads]
+    return TrunkPack(dtype, G, stem, blocks, head3, w1, b1, [w.shape[0] for w in w1],
+                     params_stamp(list(experts)))
+
+
+def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None):
+    """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
+
+    Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
+    (conv-bn-relu-conv-bn + identity/downsample, add, relu), then the expert head
+    (bdd_detection_expert.py:18-20).
+    """
+    B, _, H, W = image.shape
+    G = pack.G
+    if x_nhwc is None:
+        x_nhwc = _ops.image_to_nhwc(image, 4, pack.dtype)
+    y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)          # [G*B,H/2,W/2,64]
+    y = _ops.maxpool3x3s2(y)                                             # [G*B,H/4,W/4,64]
+    for (c1, c2, dn) in pack.blocks:
+        h_in, w_in = y.shape[1], y.shape[2]
+        out = _ops.conv2d(c1, y, B, h_in, w_in)
+        identity = y if dn is None else _ops.conv2d(dn, y, B, h_in, w_in)
+        y = _ops.conv2d(c2, out, B, out.shape[1], out.shape[2], residual=identity)
+    h, w = y.shape[1], y.shape[2]
+    hid = _ops.conv2d(pack.head3, y, B, h, w)                            # [G*B,h,w,256]
+    pooled = torch.empty((B, sum(pack.n_ch)), device=image.device, dtype=torch.float32)
+    lows, off = [], 0
+    for g in range(G):
+        lows.append(_ops.head1x1_pool(hid[g * B:(g + 1) * B], pack.head1_w[g], pack.head1_b[g], pooled, off))
+        off += pack.n_ch[g]
+    return lows, pooled, (h, w)

@@ -1,0 +1,18 @@
+"""BDDDrivableExpert — drop-in for models/experts/bdd_drivable_expert.py:5-23."""
+from ... import _ops
+from ._base import BDDExpertBase
+from ._trunk import make_head, make_resnet18_trunk
+
+
+class BDDDrivableExpert(BDDExpertBase):
+    head_attr = "decoder"
+    upsample_to_input = True
+
+    def __init__(self, num_classes=3, pretrained_backbone=True):
+        super().__init__()
+        self.num_classes = num_classes
+        self.backbone = make_resnet18_trunk(pretrained_backbone)
+        self.decoder = make_head(num_classes)
+
+    def format_output(self, low, H, W, dtype):
+        return _ops.upsample_bilinear_nchw(low, H, W, dtype)

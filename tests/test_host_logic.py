@@ -1,0 +1,84 @@
+"""CPU: host-side logic of the drop-in modules (no kernels run)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import automoe_oracle as O
+from oracle import synth
+
+
+@pytest.fixture(scope="module")
+def model():
+    from automoe_b200.models.automoe import create_automoe_model
+    return create_automoe_model(synth.CONFIG_3EXPERT, "cpu").eval()
+
+
+def test_state_dict_keys_match_reference(model, golden_dir):
+    keys = (golden_dir / "state_dict_keys.txt").read_text().split()
+    assert list(model.state_dict().keys()) == keys
+    assert len(keys) == 466
+    assert sum(p.numel() for p in model.parameters()) == 39_949_157
+
+
+def test_api_surface(model):
+    for attr in ("experts", "expert_extractors", "context_extractor", "gating_network", "policy_head",
+                 "forward", "get_expert_weights", "load_expert_checkpoints", "freeze_experts", "unfreeze_experts"):
+        assert hasattr(model, attr)
+    model.freeze_experts()
+    assert all(not p.requires_grad for e in model.experts for p in e.parameters())
+    assert all(p.requires_grad for p in model.gating_network.parameters())
+    model.unfreeze_experts()
+    assert all(p.requires_grad for e in model.experts for p in e.parameters())
+    trainable = sum(p.numel() for n, p in model.named_parameters() if not n.startswith("experts."))
+    assert trainable == 2_870_657  # extractors + context + gating + policy
+
+
+@pytest.mark.parametrize("speed_seq,controls", [(1, "col"), (5, "seq"), (3, "missing"), (4, "3d")])
+def test_vehicle_state_matches_oracle(model, speed_seq, controls):
+    B = 3
+    g = torch.Generator().manual_seed(0)
+    batch = {"speed": torch.rand(B, speed_seq, generator=g)}
+    if controls == "col":
+        for k in ("steering", "throttle", "brake"):
+            batch[k] = torch.rand(B, 1, generator=g)
+    elif controls == "seq":
+        for k in ("steering", "throttle", "brake"):
+            batch[k] = torch.rand(B, speed_seq, generator=g)
+    elif controls == "3d":
+        for k in ("steering", "throttle", "brake"):
+            batch[k] = torch.rand(B, 2, 2, generator=g)
+    assert torch.equal(model._vehicle_state(batch), O.vehicle_state(batch))
+
+
+def test_gate_param_layout_size(model):
+    """flat buffer length == what csrc/gate.cu derives from the dims (4-float aligned tensors)."""
+    from automoe_b200.models._gatepack import gate_param_tensors
+    n_ch = [14, 19, 3]
+    ts = gate_param_tensors(model.context_extractor, list(model.expert_extractors.extractors), model.gating_network,
+                            n_ch, 64, 128)
+    al4 = lambda n: (n + 3) & ~3
+    total = sum(al4(t.numel()) for t in ts)
+    raw = sum(t.numel() for t in ts)
+    assert raw == 2_400 + 415_488 + 602_115  # context + extractors + gating
+    assert total >= raw and total - raw < 4 * len(ts)
+
+
+def test_train_mode_is_rejected(model):
+    model.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            model({"image": torch.zeros(1, 3, 64, 64), "speed": torch.zeros(1, 1)})
+    finally:
+        model.eval()
+
+
+def test_unsupported_configs_fail_loudly():
+    from automoe_b200.models.automoe import create_automoe_model
+    cfg = {k: v for k, v in synth.CONFIG_3EXPERT.items()}
+    cfg["experts"] = list(cfg["experts"]) + [{"type": "nuscenes"}]
+    with pytest.raises(NotImplementedError):
+        create_automoe_model(cfg, "cpu")
+    cfg = dict(synth.CONFIG_3EXPERT)
+    cfg["context"] = {"type": "full"}
+    with pytest.raises(NotImplementedError):
+        create_automoe_model(cfg, "cpu")
