@@ -15,6 +15,10 @@ from . import _cabi
 from ._cabi import check, ctx, dtype_code, lib, ptr, stream_ptr
 
 
+# bench.py sets PROFILE to a list to get (kind, flops, start_event, end_event) per conv launch
+PROFILE = None
+
+
 def _al4(n: int) -> int:
     return (n + 3) & ~3
 
@@ -112,7 +116,8 @@ def pack_conv(convs, bns, dtype: torch.dtype, device, relu: bool, cin_pad: Optio
                                      ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
         # the temporaries above must outlive the async kernels that read them
         torch.cuda.current_stream(device).synchronize()
-    return PackedConv(wbuf, scale, bias, G, cin_k, cout, kh, kw_k, sh, sw_k, ph, pw_k, relu, pair)
+    return PackedConv(wbuf, scale, bias, G, cin_k, cout, kh, kw_k, sh, sw_k, ph, pw_k, relu, pair,
+                      meta={"true_k": cin * kh * kw})
 
 
 def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Optional[torch.Tensor] = None,
@@ -128,10 +133,19 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
         Wo = (W + 2 * pc.pw - pc.kw) // pc.sw + 1
         Wk = W
     y = torch.empty((pc.G * B, Ho, Wo, pc.cout), device=x.device, dtype=dtype)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().amoe_conv2d_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual), ptr(y),
                                 pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.sw,
                                 pc.ph, pc.pw, Ho, Wo, int(pc.relu if relu is None else relu), dtype_code(dtype),
                                 impl, stream_ptr(x.device)), "conv2d_fwd")
+    if prof is not None:
+        ev1.record()
+        tc = dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H, Wk, pc.cin, pc.cout, pc.sh, pc.sw)
+        macs = pc.meta.get("true_k", pc.kh * pc.kw * pc.cin) * pc.cout * pc.G * B * Ho * Wo
+        prof.append(("conv_tc" if tc else "conv_simt", 2.0 * macs, ev0, ev1))
     return y
 
 

