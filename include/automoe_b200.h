@@ -52,6 +52,10 @@ int64_t amoe_launch_count(amoe_ctx* ctx);
  * NHWC with C padded to Cp (zeros).  dst dtype f32 or bf16. */
 int amoe_image_nchw_to_nhwc(amoe_ctx*, const float* src, void* dst, int B, int C,
                             int H, int W, int Cp, int dst_dtype, void* stream);
+/* Same, into rows of Wpad pixels: `left` zero pixels, the W image pixels, zeros up to Wpad
+ * (the physically padded layout amoe_conv2d_rowwin_fwd reads).  dst: [B,H,Wpad,Cp]. */
+int amoe_image_nchw_to_nhwc_padded(amoe_ctx*, const float* src, void* dst, int B, int C, int H,
+                                   int W, int Cp, int left, int Wpad, int dst_dtype, void* stream);
 /* nn.Conv2d weight [Cout,Cin,KH,KW] fp32 -> packed [Cout][KH][KW][Cin_pad]
  * (dtype f32|bf16, zero-padded channels).  dst points at the first row of this
  * conv inside a (possibly grouped) packed buffer. */
@@ -84,6 +88,18 @@ int amoe_conv2d_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
                     int impl, void* stream);
 /* 1 if amoe_conv2d_fwd(impl=auto, dtype=bf16) would take the tcgen05 path. */
 int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w);
+/* "Row-window" convolution for tiny Cin (ResNet stem 7x7/s2 with Cin=3, policy conv1 5x5/s2)
+ * on the tensor cores.  x: [B,H,Wpad,Cp] bf16 with zero columns physically stored left/right
+ * (amoe_image_nchw_to_nhwc_padded).  For output column ow, filter row kh reads ONE contiguous
+ * window of 64/Cp pixels starting at padded column ow*stride_w of input row oh*stride_h-pad_h+kh
+ * (rows outside [0,H) are zero); the filter is packed as w: [Cout][KH][64] with zeros at window
+ * positions that are not filter taps.  Cout may be the concatenation of several convolutions
+ * that share the input (3 expert stems): channel ch goes to output tensor ch/split_c,
+ * y: [Cout/split_c][B,Ho,Wo,split_c] bf16. */
+int amoe_conv2d_rowwin_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
+                           const float* bias, void* y, int B, int H, int Wpad, int Cp, int Cout,
+                           int split_c, int KH, int stride_h, int stride_w, int pad_h, int Ho,
+                           int Wo, int relu, void* stream);
 /* nn.MaxPool2d(3, stride 2, pad 1) of the ResNet stem, NHWC. */
 int amoe_maxpool3x3s2_fwd(amoe_ctx*, const void* x, void* y, int NB, int H, int W, int C,
                           int dtype, void* stream);

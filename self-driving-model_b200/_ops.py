@@ -47,6 +47,100 @@ def image_to_nhwc(img: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tenso
     return out
 
 
+def image_to_nhwc_padded(img: torch.Tensor, cp: int, left: int, wpad: int, dtype: torch.dtype) -> torch.Tensor:
+    """[B,C,H,W] fp32 NCHW -> [B,H,wpad,cp]: `left` zero pixels, the image row, zeros up to wpad."""
+    if img.dtype != torch.float32:
+        img = img.float()
+    img = img.contiguous()
+    B, Cc, H, W = img.shape
+    out = torch.empty((B, H, wpad, cp), device=img.device, dtype=dtype)
+    check(lib().amoe_image_nchw_to_nhwc_padded(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp, left, wpad,
+                                               dtype_code(dtype), stream_ptr(img.device)), "image_nchw_to_nhwc_padded")
+    return out
+
+
+ROWWIN_LEFT = 4     # zero pixels stored left of every image row
+ROWWIN_CP = 4       # channels per pixel (3 padded to 4)
+ROWWIN_WIN = 16     # pixels per window = 64 bf16 = one 128-byte swizzle row
+
+
+def rowwin_wpad(W: int, sw: int = 2) -> int:
+    Wo = (W - 1) // sw + 1
+    need = max(ROWWIN_LEFT + W, (Wo - 1) * sw + ROWWIN_WIN)
+    return (need + 7) & ~7
+
+
+@dataclass
+class PackedRowwin:
+    """Several small-Cin, stride-2 convolutions that share one input, concatenated on Cout and packed
+    for amoe_conv2d_rowwin_fwd (each filter row = one 64-element window of the padded image row)."""
+    w: torch.Tensor       # [Cout_total, KH, 64] bf16
+    scale: torch.Tensor
+    bias: torch.Tensor
+    n_conv: int
+    cout: int             # per convolution (= split_c)
+    kh: int
+    kw: int
+    sh: int
+    sw: int
+    ph: int
+    pw: int
+    relu: bool
+    true_k: int
+
+
+def pack_rowwin(convs, bns, device, relu: bool) -> PackedRowwin:
+    c0 = convs[0]
+    cout, cin, kh, kw = c0.weight.shape
+    sh, sw = c0.stride
+    ph, pw = c0.padding
+    assert cin <= ROWWIN_CP and kw - pw + ROWWIN_LEFT <= ROWWIN_WIN and ROWWIN_LEFT - pw >= 0
+    n = len(convs)
+    st, h = stream_ptr(device), ctx(device)
+    wbuf = torch.empty((n * cout, kh, 64), device=device, dtype=torch.bfloat16)
+    scale = torch.empty(n * cout, device=device, dtype=torch.float32)
+    bias = torch.empty(n * cout, device=device, dtype=torch.float32)
+    for g, conv in enumerate(convs):
+        w = conv.weight.detach().to(device=device, dtype=torch.float32)
+        # window position j holds padded column sw*ow + j = original column sw*ow + j - LEFT  ->  kw = j - LEFT + pw
+        w2 = w.new_zeros((cout, ROWWIN_WIN, ROWWIN_CP, kh))
+        for k in range(kw):
+            w2[:, k - pw + ROWWIN_LEFT, :cin, :] = w[:, :, :, k]
+        w2 = w2.reshape(cout, 64, kh, 1).contiguous()
+        check(lib().amoe_pack_conv_weight(h, ptr(w2), ptr(wbuf[g * cout:]), cout, 64, kh, 1, 64, _cabi.BF16, st),
+              "pack_conv_weight")
+        cb = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous() if conv.bias is not None else None
+        bn = bns[g] if bns is not None else None
+        if bn is not None:
+            prm = [t.detach().float().contiguous() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+            check(lib().amoe_fold_bn(h, ptr(prm[0]), ptr(prm[1]), ptr(prm[2]), ptr(prm[3]), float(bn.eps), ptr(cb), cout,
+                                     ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
+        else:
+            check(lib().amoe_fold_bn(h, None, None, None, None, 0.0, ptr(cb), cout,
+                                     ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
+        torch.cuda.current_stream(device).synchronize()
+    return PackedRowwin(wbuf, scale, bias, n, cout, kh, kw, sh, sw, ph, pw, relu, cin * kh * kw)
+
+
+def conv2d_rowwin(pc: PackedRowwin, x_pad: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    """x_pad: [B,H,Wpad,4] bf16 from image_to_nhwc_padded -> [n_conv*B,Ho,Wo,cout] bf16."""
+    Wpad = x_pad.shape[2]
+    Ho = (H + 2 * pc.ph - pc.kh) // pc.sh + 1
+    Wo = (W + 2 * pc.pw - pc.kw) // pc.sw + 1
+    y = torch.empty((pc.n_conv * B, Ho, Wo, pc.cout), device=x_pad.device, dtype=torch.bfloat16)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().amoe_conv2d_rowwin_fwd(ctx(x_pad.device), ptr(x_pad), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(y),
+                                       B, H, Wpad, ROWWIN_CP, pc.n_conv * pc.cout, pc.cout, pc.kh, pc.sh, pc.sw, pc.ph,
+                                       Ho, Wo, int(pc.relu), stream_ptr(x_pad.device)), "conv2d_rowwin_fwd")
+    if prof is not None:
+        ev1.record()
+        prof.append(("conv_tc", 2.0 * pc.true_k * pc.cout * pc.n_conv * B * Ho * Wo, ev0, ev1))
+    return y
+
+
 @dataclass
 class PackedConv:
     """Packed weights of G same-shape convolutions (+ folded BN) living on one device."""

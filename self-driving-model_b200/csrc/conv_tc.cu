@@ -45,6 +45,8 @@ struct Params {
   int num_taps, k_chunks;           // K iterations per tile = num_taps * k_chunks
   int stages;
   int relu, x_shared;
+  int split_c;                      // output sub-tensor width: channel ch of group g goes to tensor
+                                    // (g*Cout/split_c + ch/split_c), channel ch%split_c (== Cout normally)
   int total_tiles;
   const float* scale;
   const float* bias;
@@ -290,7 +292,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nl = tc_.bt * p.nb + bi, oh = tc_.ht * p.th + hi, ow = tc_.wt * p.tw + wi;
       const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
       const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
-      const int64_t off = ((((int64_t)tc_.g * p.B + nl) * p.Ho + oh) * p.Wo + ow) * p.Cout + tc_.nt * p.block_n;
+      const int chn = tc_.nt * p.block_n;  // first channel of this tile inside its group
+      const int64_t pix = ((int64_t)nl * p.Ho + oh) * p.Wo + ow;
+      const int64_t sub_stride = (int64_t)p.B * p.Ho * p.Wo * p.split_c;
+      const int nsplit = p.Cout / p.split_c;
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
@@ -298,6 +303,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
+        // a 32-channel chunk never straddles output sub-tensors (split_c % 32 == 0)
+        const int ch = chn + c0;
+        const int64_t off = (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pix * p.split_c + ch % p.split_c - c0;
         if (valid) {
           const float* sc = p.scale + ch0 + c0;
           const float* bs = p.bias + ch0 + c0;
@@ -349,7 +357,7 @@ static int pow2_ceil(int v) {
 static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
-  if (Cin % 64 != 0 || Cout % 64 != 0) return false;
+  if (Cin % 64 != 0 || Cout % 32 != 0) return false;
   if (Cout > 256 && Cout % 256 != 0) return false;
   if (sh != 1 && sh != 2) return false;
   if (sw != 1 && sw != 2) return false;
@@ -372,15 +380,23 @@ int amoe_conv2d_simt(amoe_ctx* ctx, const void* x, const void* w, const float* s
                      int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw, int ph, int pw,
                      int Ho, int Wo, int relu, int dtype, cudaStream_t st);
 
-static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
-                          const float* bias, const void* residual, void* y, int G, int x_shared,
-                          int B, int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw,
-                          int ph, int pw, int Ho, int Wo, int relu, cudaStream_t st) {
+// How the kernel sees the input: a 5-D tensor (inner -> outer) {Cv, Wv, P, Hv, N} with byte
+// strides for dims 1..4 (dim 0 is contiguous bf16).
+struct AView {
+  uint64_t dims[5];
+  uint64_t strides[4];
+};
+
+static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const void* w, int Ktot,
+                          const float* scale, const float* bias, const void* residual, void* y, int G,
+                          int x_shared, int B, int Ho, int Wo, int Cout, int split_c, int num_taps,
+                          const tc::Tap* taps, int k_chunks, int relu, cudaStream_t st) {
   using namespace tc;
-  AMOE_REQUIRE(KH * KW <= MAX_TAPS, "conv_tc: %dx%d filter has more than %d taps", KH, KW, MAX_TAPS);
+  AMOE_REQUIRE(num_taps <= MAX_TAPS, "conv_tc: %d taps exceed the limit of %d", num_taps, MAX_TAPS);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                "conv_tc: pointers must be 16-byte aligned");
+  AMOE_REQUIRE(Cout % 32 == 0 && split_c % 32 == 0 && Cout % split_c == 0, "conv_tc: bad Cout/split_c %d/%d", Cout, split_c);
   Params p;
   p.tw = std::min(128, pow2_ceil(Wo));
   p.th = std::min(128 / p.tw, pow2_ceil(Ho));
@@ -389,10 +405,11 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
   p.tiles_h = ceil_div(Ho, p.th);
   p.tiles_b = ceil_div(B, p.nb);
   p.block_n = Cout >= 256 ? 256 : Cout;
+  AMOE_REQUIRE(Cout % p.block_n == 0 && p.block_n % 32 == 0, "conv_tc: unsupported channel tiling Cout=%d", Cout);
   p.n_tiles_n = Cout / p.block_n;
-  p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.num_taps = KH * KW;
-  p.k_chunks = Cin / BLOCK_K;
+  p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c;
+  p.num_taps = num_taps;
+  p.k_chunks = k_chunks;
   const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
   p.stages = std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes);
   p.relu = relu; p.x_shared = x_shared;
@@ -402,22 +419,14 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
   p.scale = scale; p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
-  for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) {
-      Tap& t = p.taps[kh * KW + kw];
-      int ho = kh - ph, wo = kw - pw;
-      if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
-      if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
-    }
+  for (int t = 0; t < num_taps; ++t) p.taps[t] = taps[t];
   if (total == 0) return 0;
 
-  // activation map: 5-D parity view (inner -> outer): Cv, Wv, P, Hv, N
-  const int NB = x_shared ? B : G * B;
   CUtensorMap tmA, tmW;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)(sw * Cin), (cuuint64_t)(W / sw), (cuuint64_t)sh, (cuuint64_t)(H / sh), (cuuint64_t)NB};
-    cuuint64_t strides[4] = {(cuuint64_t)sw * Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)sh * W * Cin * 2,
-                             (cuuint64_t)H * W * Cin * 2};
+    cuuint64_t dims[5], strides[4];
+    for (int i = 0; i < 5; ++i) dims[i] = av.dims[i];
+    for (int i = 0; i < 4; ++i) strides[i] = av.strides[i];
     cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.tw, 1u, (cuuint32_t)p.th, (cuuint32_t)p.nb};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = ctx->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
@@ -426,7 +435,6 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
   }
   {
-    const int Ktot = KH * KW * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)G * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
@@ -443,10 +451,66 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
   return 0;
 }
 
+static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
+                          const float* bias, const void* residual, void* y, int G, int x_shared,
+                          int B, int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw,
+                          int ph, int pw, int Ho, int Wo, int relu, cudaStream_t st) {
+  using namespace tc;
+  AMOE_REQUIRE(KH * KW <= MAX_TAPS, "conv_tc: %dx%d filter has more than %d taps", KH, KW, MAX_TAPS);
+  Tap taps[MAX_TAPS];
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      Tap& t = taps[kh * KW + kw];
+      int ho = kh - ph, wo = kw - pw;
+      if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
+      if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
+    }
+  // parity view (inner -> outer): Cv = sw*Cin, Wv = W/sw, P = sh, Hv = H/sh, N
+  const int NB = x_shared ? B : G * B;
+  AView av;
+  av.dims[0] = (uint64_t)sw * Cin; av.dims[1] = (uint64_t)(W / sw); av.dims[2] = (uint64_t)sh;
+  av.dims[3] = (uint64_t)(H / sh); av.dims[4] = (uint64_t)NB;
+  av.strides[0] = (uint64_t)sw * Cin * 2; av.strides[1] = (uint64_t)W * Cin * 2;
+  av.strides[2] = (uint64_t)sh * W * Cin * 2; av.strides[3] = (uint64_t)H * W * Cin * 2;
+  return launch_generic(ctx, x, av, w, KH * KW * Cin, scale, bias, residual, y, G, x_shared, B, Ho, Wo, Cout,
+                        Cout, KH * KW, taps, Cin / BLOCK_K, relu, st);
+}
+
 extern "C" {
 
 int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w) {
   return tc::supported(H, W, Cin, Cout, stride_h, stride_w) ? 1 : 0;
+}
+
+int amoe_conv2d_rowwin_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
+                           const float* bias, void* y, int B, int H, int Wpad, int Cp, int Cout,
+                           int split_c, int KH, int stride_h, int stride_w, int pad_h, int Ho, int Wo,
+                           int relu, void* stream) {
+  using namespace tc;
+  AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv2d_rowwin_fwd: NULL argument");
+  AMOE_REQUIRE(Cp > 0 && BLOCK_K % Cp == 0, "amoe_conv2d_rowwin_fwd: Cp=%d must divide %d", Cp, BLOCK_K);
+  const int win = BLOCK_K / Cp;  // pixels per window
+  AMOE_REQUIRE((stride_w * Cp * 2) % 16 == 0, "amoe_conv2d_rowwin_fwd: window stride must be a multiple of 16 bytes");
+  AMOE_REQUIRE((Wo - 1) * stride_w + win <= Wpad, "amoe_conv2d_rowwin_fwd: windows run past the padded row (Wpad=%d)", Wpad);
+  AMOE_REQUIRE((Wpad * Cp * 2) % 16 == 0, "amoe_conv2d_rowwin_fwd: padded row must be a multiple of 16 bytes");
+  AMOE_REQUIRE(stride_h == 1 || (stride_h == 2 && H % 2 == 0), "amoe_conv2d_rowwin_fwd: stride_h must be 1, or 2 with even H");
+  AMOE_REQUIRE(KH <= MAX_TAPS, "amoe_conv2d_rowwin_fwd: KH too large");
+  Tap taps[MAX_TAPS];
+  for (int kh = 0; kh < KH; ++kh) {
+    int ho = kh - pad_h;
+    taps[kh].c_off = 0;
+    taps[kh].dw = 0;
+    if (stride_h == 1) { taps[kh].dh = ho; taps[kh].hp = 0; } else { taps[kh].dh = floordiv2(ho); taps[kh].hp = ho - 2 * taps[kh].dh; }
+  }
+  // overlapping windows: dim0 = 64 contiguous elements (win pixels), dim1 = output column (stride_w pixels apart)
+  AView av;
+  const uint64_t row = (uint64_t)Wpad * Cp * 2;
+  av.dims[0] = BLOCK_K; av.dims[1] = (uint64_t)Wo; av.dims[2] = (uint64_t)stride_h;
+  av.dims[3] = (uint64_t)(H / stride_h); av.dims[4] = (uint64_t)B;
+  av.strides[0] = (uint64_t)stride_w * Cp * 2; av.strides[1] = row; av.strides[2] = (uint64_t)stride_h * row;
+  av.strides[3] = (uint64_t)H * row;
+  return launch_generic(ctx, x, av, w, KH * BLOCK_K, scale, bias, nullptr, y, 1, 0, B, Ho, Wo, Cout, split_c, KH,
+                        taps, 1, relu, (cudaStream_t)stream);
 }
 
 int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,

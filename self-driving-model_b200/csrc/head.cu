@@ -96,6 +96,53 @@ __global__ __launch_bounds__(256) void upsample_bilinear_nchw_kernel(const float
   }
 }
 
+// ---- fast path: integer scale factor S with S % 16 == 0 and w <= 32 (the x32 case) -------------
+// One CTA per (b,c) plane: the low-res plane sits in smem; each warp produces whole output rows.
+// Per row: lanes < w blend the two source rows (vertical lerp), every lane then needs only two of
+// those values (a lane's 8 consecutive pixels share one source cell because cell borders fall on
+// multiples of 8), fetched by shuffle, and writes one 16-byte (bf16) / two 16-byte (fp32) stores.
+template <typename T>
+__global__ __launch_bounds__(256) void upsample_intscale_nchw_kernel(const float* __restrict__ low,
+                                                                     T* __restrict__ out, int h, int w,
+                                                                     int C, int H, int W, float sh, float sw_) {
+  extern __shared__ float plane[];  // [h][w]
+  const int bc = blockIdx.x;
+  const int b = bc / C, c = bc - b * C;
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) plane[i] = __ldg(low + ((int64_t)b * h * w + i) * C + c);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  T* obase = out + (int64_t)bc * H * W;
+  for (int y = warp; y < H; y += nwarp) {
+    int y0, y1;
+    float ly;
+    src_index(sh, y, h, y0, y1, ly);
+    const float hy = 1.f - ly;
+    float vcol = 0.f;
+    if (lane < w) vcol = hy * plane[y0 * w + lane] + ly * plane[y1 * w + lane];
+    for (int x0 = lane * 8; x0 < W; x0 += 256) {
+      int xa, xb;
+      float lx0;
+      src_index(sw_, x0, w, xa, xb, lx0);
+      const float va = __shfl_sync(0xffffffffu, vcol, xa), vb = __shfl_sync(0xffffffffu, vcol, xb);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = fmaxf(sw_ * ((float)(x0 + j) + 0.5f) - 0.5f, 0.f);
+        float lx = s - (float)xa;
+        v[j] = (1.f - lx) * va + lx * vb;
+      }
+      T* o = obase + (int64_t)y * W + x0;
+      if constexpr (sizeof(T) == 2) {
+        __stcs(reinterpret_cast<uint4*>(o), make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+      } else {
+        __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
+      }
+    }
+  }
+}
+
 // ---- mean over H*W of NCHW: one warp per (b,c) --------------------------------
 template <typename T>
 __global__ void mean_hw_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t BC, int HW) {
@@ -136,6 +183,18 @@ int amoe_upsample_bilinear_nchw_fwd(amoe_ctx* ctx, const float* low, void* out, 
   if (total == 0) return 0;
   float sh = (float)h / (float)H, sw_ = (float)w / (float)W;
   cudaStream_t st = (cudaStream_t)stream;
+  // x32-style integer up-sampling: plane-per-CTA kernel (W % 256 == 0 keeps every lane's 8-pixel run
+  // inside the row and 16-byte aligned; S % 16 == 0 keeps a run inside one source cell)
+  if (W % w == 0 && (W / w) % 16 == 0 && w <= 32 && W % 256 == 0 && h * w * sizeof(float) <= 48 * 1024 &&
+      (out_dtype == AMOE_BF16 || out_dtype == AMOE_F32)) {
+    size_t smem = (size_t)h * w * sizeof(float);
+    if (out_dtype == AMOE_BF16)
+      upsample_intscale_nchw_kernel<__nv_bfloat16><<<B * C, 256, smem, st>>>(low, (__nv_bfloat16*)out, h, w, C, H, W, sh, sw_);
+    else
+      upsample_intscale_nchw_kernel<float><<<B * C, 256, smem, st>>>(low, (float*)out, h, w, C, H, W, sh, sw_);
+    AMOE_LAUNCH_OK(ctx);
+    return 0;
+  }
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (out_dtype == AMOE_BF16)
     upsample_bilinear_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(low, (__nv_bfloat16*)out, h, w, C, H, W, sh, sw_, total);

@@ -33,6 +33,26 @@ __global__ void image_nchw_to_nhwc4_bf16_kernel(const float* __restrict__ src,
   dst[i] = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
 }
 
+// physically padded rows: dst[b][h][wp][c], wp in [0,Wpad): image column wp-left or zero
+template <typename T>
+__global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, T* __restrict__ dst, int C,
+                                                 int H, int W, int Cp, int left, int Wpad, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int wp = (int)(i % Wpad);
+  int64_t r = i / Wpad;
+  int h = (int)(r % H);
+  int64_t b = r / H;
+  int w = wp - left;
+  const bool in = w >= 0 && w < W;
+  const float* s = src + (b * C * H + h) * (int64_t)W + w;
+  T* d = dst + i * Cp;
+  for (int c = 0; c < Cp; ++c) {
+    float v = (in && c < C) ? __ldg(s + (int64_t)c * H * W) : 0.f;
+    st_from_float<T>(d + c, v);
+  }
+}
+
 template <typename T>
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout,
                                         int Cin, int KH, int KW, int Cin_pad) {
@@ -88,6 +108,24 @@ int amoe_image_nchw_to_nhwc(amoe_ctx* ctx, const float* src, void* dst, int B, i
   } else {
     AMOE_REQUIRE(false, "amoe_image_nchw_to_nhwc: bad dtype %d", dst_dtype);
   }
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
+                                   int Cp, int left, int Wpad, int dst_dtype, void* stream) {
+  AMOE_REQUIRE(ctx && src && dst, "amoe_image_nchw_to_nhwc_padded: NULL argument");
+  AMOE_REQUIRE(Cp >= C && C >= 1 && left >= 0 && Wpad >= left + W, "amoe_image_nchw_to_nhwc_padded: bad geometry");
+  int64_t total = (int64_t)B * H * Wpad;
+  if (total == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dst_dtype == AMOE_BF16)
+    image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, total);
+  else if (dst_dtype == AMOE_F32)
+    image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, total);
+  else
+    AMOE_REQUIRE(false, "amoe_image_nchw_to_nhwc_padded: bad dtype %d", dst_dtype);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -24,7 +24,7 @@ from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
 from .experts._base import run_experts
-from .experts._trunk import params_stamp
+from .experts._trunk import params_stamp, stage_image
 from .experts.expert_extractors import create_expert_extractors
 from .gating.gating_network import GatingNetwork
 from .policy.trajectory_head import TrajectoryPolicy
@@ -145,7 +145,7 @@ class AutoMoE(nn.Module):
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
-        x_nhwc = _ops.image_to_nhwc(image, 4, dtype)
+        x_nhwc = stage_image(image, dtype)
 
         expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc)
 

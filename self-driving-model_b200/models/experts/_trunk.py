@@ -108,7 +108,10 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
     """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
     G = len(experts)
     bbs = [e.backbone for e in experts]
-    stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
+    if dtype == torch.bfloat16:   # Cin=3 stem on the tensor cores through row windows, 3 experts in one GEMM
+        stem = _ops.pack_rowwin([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
+    else:
+        stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
     blocks = []
     for li in range(4, 8):
         for bi in range(2):
@@ -128,6 +131,15 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
                      params_stamp(list(experts)))
 
 
+def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """NCHW fp32 frame -> the NHWC layout the first convolutions read: bf16 rows physically padded
+    for the row-window tensor-core stem, or plain [B,H,W,4] fp32 for the fp32 path."""
+    if dtype == torch.bfloat16:
+        W = image.shape[3]
+        return _ops.image_to_nhwc_padded(image, _ops.ROWWIN_CP, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), dtype)
+    return _ops.image_to_nhwc(image, 4, dtype)
+
+
 def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
 
@@ -138,8 +150,11 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     B, _, H, W = image.shape
     G = pack.G
     if x_nhwc is None:
-        x_nhwc = _ops.image_to_nhwc(image, 4, pack.dtype)
-    y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)          # [G*B,H/2,W/2,64]
+        x_nhwc = stage_image(image, pack.dtype)
+    if isinstance(pack.stem, _ops.PackedRowwin):
+        y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)               # [G*B,H/2,W/2,64]
+    else:
+        y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)
     y = _ops.maxpool3x3s2(y)                                             # [G*B,H/4,W/4,64]
     for (c1, c2, dn) in pack.blocks:
         h_in, w_in = y.shape[1], y.shape[2]

@@ -12,7 +12,7 @@ import torch.nn as nn
 from ... import _ops
 from .._gatepack import require_eval
 from .._precision import resolve_dtype
-from ..experts._trunk import ParamHolder, params_stamp
+from ..experts._trunk import ParamHolder, params_stamp, stage_image
 
 
 class EasyBackbone(nn.Module):
@@ -57,8 +57,10 @@ class TrajectoryPolicy(nn.Module):
         p = self._packs.get(key)
         if p is None or p["stamp"] != stamp:
             net = self.backbone.net
+            first = (_ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if dtype == torch.bfloat16 else
+                     _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4))
             convs = [
-                _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4),
+                first,
                 _ops.pack_conv([net[3]], [net[4]], dtype, device, relu=True),
                 _ops.pack_conv([net[6]], [net[7]], dtype, device, relu=True),
                 _ops.pack_conv([net[9]], [net[10]], dtype, device, relu=True),
@@ -78,10 +80,13 @@ class TrajectoryPolicy(nn.Module):
         dtype = _dtype or resolve_dtype(self.precision)
         p = self._pack(dtype, image.device)
         B, _, H, W = image.shape
-        x = _x_nhwc if _x_nhwc is not None else _ops.image_to_nhwc(image, 4, dtype)
+        x = _x_nhwc if _x_nhwc is not None else stage_image(image, dtype)
         h, w = H, W
         for pc in p["convs"]:
-            x = _ops.conv2d(pc, x, B, h, w)
+            if isinstance(pc, _ops.PackedRowwin):
+                x = _ops.conv2d_rowwin(pc, x, B, h, w)
+            else:
+                x = _ops.conv2d(pc, x, B, h, w)
             h, w = x.shape[1], x.shape[2]
         if context is not None:
             if self.context_dim == 0:

@@ -140,6 +140,46 @@ def test_conv_tc_bf16(shape):
     assert e < 8e-3 and l2 < 4e-3, (e, l2)
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [("stem", 3, 2, 64, 64), ("stem", 3, 3, 256, 256), ("stem", 1, 2, 224, 224),
+                                  ("policy", 1, 2, 64, 64), ("policy", 1, 3, 256, 256)])
+def test_conv_tc_rowwin(case):
+    """Cin=3 convolutions (ResNet stem 7x7/s2/p3, policy conv1 5x5/s2/p2) on the tensor cores through
+    row windows of the physically padded image; several convs sharing the input are one GEMM."""
+    from automoe_b200 import _ops
+    kind, n, B, H, W = case
+    g = torch.Generator().manual_seed(4)
+    if kind == "stem":
+        mk = lambda: nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+    else:
+        mk = lambda: nn.Conv2d(3, 32, 5, 2, 2, bias=True)
+    convs, bns = [], []
+    for _ in range(n):
+        c = mk()
+        cout = c.weight.shape[0]
+        with torch.no_grad():
+            c.weight.copy_((torch.randn(c.weight.shape, generator=g) * 0.1).bfloat16().float())
+            if c.bias is not None:
+                c.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+        b = nn.BatchNorm2d(cout)
+        with torch.no_grad():
+            b.weight.copy_(1 + 0.1 * torch.randn(cout, generator=g))
+            b.bias.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_mean.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_var.copy_(torch.rand(cout, generator=g) + 0.5)
+        convs.append(c.to(DEV))
+        bns.append(b.to(DEV).eval())
+    img = torch.randn((B, 3, H, W), generator=g).bfloat16().float().to(DEV)
+    with torch.no_grad():
+        ref = torch.cat([F.relu(bn(c(img))) for c, bn in zip(convs, bns)], 0)
+    pc = _ops.pack_rowwin(convs, bns, torch.device(DEV), relu=True)
+    xp = _ops.image_to_nhwc_padded(img, 4, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), torch.bfloat16)
+    assert torch.equal(xp[:, :, 4:4 + W, :3].float(), img.permute(0, 2, 3, 1)) and (xp[:, :, :4] == 0).all() and (xp[:, :, 4 + W:] == 0).all()
+    y = _ops.conv2d_rowwin(pc, xp, B, H, W).float().permute(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 8e-3 and rel_l2(y, ref) < 4e-3, (rel_err(y, ref), rel_l2(y, ref))
+
+
 def test_maxpool():
     from automoe_b200 import _ops
     for dtype in (torch.float32, torch.bfloat16):
