@@ -80,12 +80,15 @@ int amoe_fold_bn(amoe_ctx*, const float* gamma, const float* beta, const float* 
  *   caller can express asymmetric padding (nn.Conv2d: Ho=(H+2*pad-KH)/stride+1).
  * dtype selects activation+weight storage (f32: SIMT fp32 kernel; bf16: tcgen05
  * implicit GEMM when the shape qualifies, else the SIMT kernel with fp32 accum).
- * impl: 0 = auto, 1 = force SIMT, 2 = force tcgen05 (error if unsupported). */
+ * impl: 0 = auto, 1 = force SIMT, 2 = force tcgen05 (error if unsupported).
+ * in_pad / out_pad (tcgen05 path only): the input / the output+residual tensors are stored with a
+ * physical border of that many pixels ([N][H+2p][W+2p][C], H and W still name the interior);
+ * the input border must hold zeros, the output border is left untouched. */
 int amoe_conv2d_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
                     const float* bias, const void* residual, void* y, int G, int x_shared,
                     int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride_h,
                     int stride_w, int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype,
-                    int impl, void* stream);
+                    int impl, int in_pad, int out_pad, void* stream);
 /* 1 if amoe_conv2d_fwd(impl=auto, dtype=bf16) would take the tcgen05 path. */
 int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w);
 /* "Row-window" convolution for tiny Cin (ResNet stem 7x7/s2 with Cin=3, policy conv1 5x5/s2)
@@ -102,7 +105,16 @@ int amoe_conv2d_rowwin_fwd(amoe_ctx*, const void* x, const void* w, const float*
                            int Wo, int relu, void* stream);
 /* nn.MaxPool2d(3, stride 2, pad 1) of the ResNet stem, NHWC. */
 int amoe_maxpool3x3s2_fwd(amoe_ctx*, const void* x, void* y, int NB, int H, int W, int C,
-                          int dtype, void* stream);
+                          int dtype, int out_pad, void* stream);
+/* 3x3 / stride 1 / pad 1 convolution (+folded BN, residual, ReLU) on PHYSICALLY padded bf16
+ * activations: x [G*B][H+2][W+2][Cin] with a zero border -> y [G*B][H+2][W+2][Cout] with a zero
+ * border (residual: same layout as y).  "Flat-shift" halo reuse: one activation load per 256
+ * output positions and 64 channels serves all nine filter taps (csrc/conv_flat.cu).
+ * Cin % 64 == 0, Cout in {32..128}, W <= 118.  Same weights layout as amoe_conv2d_fwd. */
+int amoe_conv3x3_flat_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
+                          const float* bias, const void* residual, void* y, int G, int B, int H,
+                          int W, int Cin, int Cout, int relu, void* stream);
+int amoe_conv3x3_flat_supported(int H, int W, int Cin, int Cout);
 
 /* ---- expert heads ------------------------------------------------------ */
 /* 1x1 conv (head[2] / decoder[2]) + global mean over pixels.

@@ -37,9 +37,11 @@ SIGNATURES = {
     "amoe_conv2d_rowwin_fwd": (_I, [_P] * 6 + [_I] * 13 + [_P]),
     "amoe_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
-    "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 18 + [_P]),
+    "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 20 + [_P]),
+    "amoe_conv3x3_flat_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P]),
+    "amoe_conv3x3_flat_supported": (_I, [_I] * 4),
     "amoe_conv2d_tc_supported": (_I, [_I] * 6),
-    "amoe_maxpool3x3s2_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "amoe_maxpool3x3s2_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_head1x1_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_upsample_bilinear_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_mean_hw_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -59,6 +59,13 @@ def image_to_nhwc_padded(img: torch.Tensor, cp: int, left: int, wpad: int, dtype
     return out
 
 
+def use_rowwin(dtype: torch.dtype) -> bool:
+    """bf16 path: Cin=3 convolutions on the tensor cores (row windows).  AMOE_STEM=simt keeps them on
+    the CUDA-core kernel (debug / A-B switch)."""
+    import os
+    return dtype == torch.bfloat16 and os.environ.get("AMOE_STEM", "tc") != "simt"
+
+
 ROWWIN_LEFT = 4     # zero pixels stored left of every image row
 ROWWIN_CP = 4       # channels per pixel (3 padded to 4)
 ROWWIN_WIN = 16     # pixels per window = 64 bf16 = one 128-byte swizzle row
@@ -214,9 +221,18 @@ def pack_conv(convs, bns, dtype: torch.dtype, device, relu: bool, cin_pad: Optio
                       meta={"true_k": cin * kh * kw})
 
 
+def use_flat() -> bool:
+    """bf16 path: 3x3/s1 convolutions of the 64/128-channel stages through the halo-reuse kernel on
+    physically padded activations (csrc/conv_flat.cu).  AMOE_FLAT=0 keeps the per-tap TMA kernel."""
+    import os
+    return os.environ.get("AMOE_FLAT", "1") != "0"
+
+
 def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Optional[torch.Tensor] = None,
-           x_shared: bool = False, impl: int = 0, relu: Optional[bool] = None) -> torch.Tensor:
-    """x: [G*B,H,W,Cin] NHWC (or [B,H,W,Cin] if x_shared) -> [G*B,Ho,Wo,Cout]."""
+           x_shared: bool = False, impl: int = 0, relu: Optional[bool] = None, in_pad: int = 0, out_pad: int = 0,
+           zero_border: bool = False) -> torch.Tensor:
+    """x: [G*B,H(+2*in_pad),W(+2*in_pad),Cin] NHWC (or [B,...] if x_shared) -> [G*B,Ho(+2*out_pad),Wo(+2*out_pad),Cout].
+    H, W name the interior size.  zero_border: the padded output is allocated zero-filled."""
     dtype = x.dtype
     if pc.pair_w:
         # output geometry of the original 3x3/s2/p1 conv; the kernel sees width W/2, KW=2, stride_w=1
@@ -226,7 +242,8 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
         Ho = (H + 2 * pc.ph - pc.kh) // pc.sh + 1
         Wo = (W + 2 * pc.pw - pc.kw) // pc.sw + 1
         Wk = W
-    y = torch.empty((pc.G * B, Ho, Wo, pc.cout), device=x.device, dtype=dtype)
+    shape = (pc.G * B, Ho + 2 * out_pad, Wo + 2 * out_pad, pc.cout)
+    y = (torch.zeros if (zero_border and out_pad) else torch.empty)(shape, device=x.device, dtype=dtype)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,20 +251,42 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
     check(lib().amoe_conv2d_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual), ptr(y),
                                 pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.sw,
                                 pc.ph, pc.pw, Ho, Wo, int(pc.relu if relu is None else relu), dtype_code(dtype),
-                                impl, stream_ptr(x.device)), "conv2d_fwd")
+                                impl, in_pad, out_pad, stream_ptr(x.device)), "conv2d_fwd")
     if prof is not None:
         ev1.record()
-        tc = dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H, Wk, pc.cin, pc.cout, pc.sh, pc.sw)
+        tc = dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H + 2 * in_pad, Wk + 2 * in_pad, pc.cin, pc.cout, pc.sh, pc.sw)
         macs = pc.meta.get("true_k", pc.kh * pc.kw * pc.cin) * pc.cout * pc.G * B * Ho * Wo
         prof.append(("conv_tc" if tc else "conv_simt", 2.0 * macs, ev0, ev1))
     return y
 
 
-def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+def flat_supported(pc: PackedConv, H: int, W: int, dtype: torch.dtype) -> bool:
+    return (dtype == torch.bfloat16 and pc.kh == 3 and pc.kw == 3 and pc.sh == 1 and pc.sw == 1 and pc.ph == 1
+            and pc.pw == 1 and not pc.pair_w and bool(lib().amoe_conv3x3_flat_supported(H, W, pc.cin, pc.cout)))
+
+
+def conv3x3_flat(pc: PackedConv, x_pad: torch.Tensor, B: int, H: int, W: int,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x_pad: [G*B,H+2,W+2,Cin] bf16 with zero border -> [G*B,H+2,W+2,Cout] with zero border."""
+    y = torch.empty((pc.G * B, H + 2, W + 2, pc.cout), device=x_pad.device, dtype=x_pad.dtype)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().amoe_conv3x3_flat_fwd(ctx(x_pad.device), ptr(x_pad), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual),
+                                      ptr(y), pc.G, B, H, W, pc.cin, pc.cout, int(pc.relu), stream_ptr(x_pad.device)),
+          "conv3x3_flat_fwd")
+    if prof is not None:
+        ev1.record()
+        prof.append(("conv_tc", 2.0 * 9 * pc.cin * pc.cout * pc.G * B * H * W, ev0, ev1))
+    return y
+
+
+def maxpool3x3s2(x: torch.Tensor, out_pad: int = 0) -> torch.Tensor:
     NB, H, W, Cc = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    y = torch.empty((NB, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
-    check(lib().amoe_maxpool3x3s2_fwd(ctx(x.device), ptr(x), ptr(y), NB, H, W, Cc, dtype_code(x.dtype),
+    y = torch.empty((NB, Ho + 2 * out_pad, Wo + 2 * out_pad, Cc), device=x.device, dtype=x.dtype)
+    check(lib().amoe_maxpool3x3s2_fwd(ctx(x.device), ptr(x), ptr(y), NB, H, W, Cc, dtype_code(x.dtype), out_pad,
                                       stream_ptr(x.device)), "maxpool3x3s2_fwd")
     return y
 

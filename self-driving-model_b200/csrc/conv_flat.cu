@@ -1,0 +1,340 @@
+// "Flat-shift" 3x3 / stride-1 / pad-1 convolution on the tensor cores with halo reuse.
+//
+// Activations live in a PHYSICALLY padded NHWC layout [N][H+2][W+2][C] with a zero border.  With
+// P = (n*(H+2) + y)*(W+2) + x the flattened padded position, the input of filter tap (kh,kw) for
+// output position P is simply position P + (kh-1)*(W+2) + (kw-1): a pure ROW OFFSET in the
+// flattened [P][C] matrix.  So one M tile = 256 consecutive positions needs ONE load of
+// 256 + 2*(W+2) + 2 pixel rows per 64-channel chunk, and the nine taps are nine UMMA operand
+// descriptors that start at different rows of the same shared-memory buffer (a 128B-swizzled
+// K-major descriptor may start at any row: the swizzle is a function of the absolute smem
+// address; verified on B200 by tools/probe_umma.cu).  Compared with one TMA box per tap
+// (conv_tc.cu) the L2->SMEM activation traffic drops ~5x, which is what bounds the 64- and
+// 128-channel layers.  Border positions are computed too (2/(W+2) waste) and stored as zeros,
+// which keeps the output's zero border intact for the next convolution.
+//
+// Per CTA (192 threads, persistent over the tiles of one expert group):
+//   warp 0: TMA producer (activation halo buffers; weight tiles unless they are smem-resident)
+//   warp 1: TMEM allocator + single-thread tcgen05.mma issuer: per tile 2 M-halves x 9 taps x
+//           C/64 chunks x 4 K-steps, two 128xN fp32 accumulators, double buffered (4N <= 512 cols)
+//   warps 2-5: epilogue: tcgen05.ld -> scale/bias (+residual) -> ReLU -> zero at borders -> bf16
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace flat {
+
+using namespace tc;
+
+constexpr int TILE_P = 256;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int MAX_A_STAGES = 4;
+constexpr int MAX_W_STAGES = 8;
+constexpr int W_RESIDENT_MAX = 80 * 1024;
+
+struct Params {
+  int G, B, H, W, Hp, Wp, C, N;
+  int chunks;            // C / 64
+  int rows_pad;          // rows per activation buffer (multiple of 16, loaded as two TMA boxes)
+  int a_stages, w_stages, w_resident;
+  int tiles_per_group;   // ceil(B*Hp*Wp / TILE_P)
+  int group_positions;   // B*Hp*Wp
+  int relu;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 2 * MAX_W_STAGES + 4];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * 128u;
+  const uint32_t w_tile_bytes = (uint32_t)p.N * 128u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_w = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+  const uint32_t bar_afull = smem_u32(&bars[0]);
+  const uint32_t bar_aempty = smem_u32(&bars[MAX_A_STAGES]);
+  const uint32_t bar_wfull = smem_u32(&bars[2 * MAX_A_STAGES]);
+  const uint32_t bar_wempty = smem_u32(&bars[2 * MAX_A_STAGES + MAX_W_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_A_STAGES + 2 * MAX_W_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * MAX_A_STAGES + 2 * MAX_W_STAGES + 2]);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < MAX_A_STAGES; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int s = 0; s < MAX_W_STAGES; ++s) {
+      mbar_init(bar_wfull + 8 * s, 1);
+      mbar_init(bar_wempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const int group_row0 = g * p.group_positions;  // first flattened position of this expert group
+  const int wrow0 = g * p.N;                      // first weight row of this expert group
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      if (p.w_resident) {
+        // all chunks x taps weight tiles, once: tile j = chunk*9 + tap holds K columns tap*C + chunk*64 ...
+        mbar_arrive_expect_tx(bar_wfull, (uint32_t)(p.chunks * 9) * w_tile_bytes);
+        for (int j = 0; j < p.chunks * 9; ++j) {
+          const int chunk = j / 9, tap = j - chunk * 9;
+          tma_load_2d(smem_w + (uint32_t)j * w_tile_bytes, &tmW, bar_wfull, tap * p.C + chunk * BLOCK_K, wrow0);
+        }
+      }
+      int as = 0, ws = 0;
+      uint32_t aphase = 0, wphase = 0;
+      const int half_rows = p.rows_pad >> 1;
+      for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x) {
+        const int row_start = group_row0 + t * TILE_P - p.Wp - 1;  // may be negative: TMA zero-fills
+        for (int chunk = 0; chunk < p.chunks; ++chunk) {
+          mbar_wait(bar_aempty + 8 * as, aphase ^ 1u);
+          mbar_arrive_expect_tx(bar_afull + 8 * as, a_stage_bytes);
+          const uint32_t dst = smem_a + (uint32_t)as * a_stage_bytes;
+          tma_load_2d(dst, &tmA, bar_afull + 8 * as, chunk * BLOCK_K, row_start);
+          tma_load_2d(dst + (uint32_t)half_rows * 128u, &tmA, bar_afull + 8 * as, chunk * BLOCK_K, row_start + half_rows);
+          if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
+          if (!p.w_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bar_wempty + 8 * ws, wphase ^ 1u);
+              mbar_arrive_expect_tx(bar_wfull + 8 * ws, w_tile_bytes);
+              tma_load_2d(smem_w + (uint32_t)ws * w_tile_bytes, &tmW, bar_wfull + 8 * ws, tap * p.C + chunk * BLOCK_K, wrow0);
+              if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    const uint32_t idesc = make_idesc(p.N);
+    int as = 0, ws = 0, it = 0;
+    uint32_t aphase = 0, wphase = 0;
+    if (p.w_resident) {
+      mbar_wait(bar_wfull, 0);
+      tcgen05_fence_after();
+    }
+    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+      for (int chunk = 0; chunk < p.chunks; ++chunk) {
+        mbar_wait(bar_afull + 8 * as, aphase);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_a + (uint32_t)as * a_stage_bytes;
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t w_addr;
+          if (p.w_resident) {
+            w_addr = smem_w + (uint32_t)(chunk * 9 + tap) * w_tile_bytes;
+          } else {
+            mbar_wait(bar_wfull + 8 * ws, wphase);
+            tcgen05_fence_after();
+            w_addr = smem_w + (uint32_t)ws * w_tile_bytes;
+          }
+          if (lane == 0) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t a_tap = a_base + (uint32_t)(kh * p.Wp + kw) * 128u;  // row shift of this tap
+            const uint64_t b_desc = make_sw128_desc(w_addr);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint64_t a_desc = make_sw128_desc(a_tap + (uint32_t)half * (BLOCK_M * 128u));
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                umma_bf16(d_tmem + (uint32_t)(half * p.N), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                          (uint32_t)((chunk | tap | kk) != 0));
+            }
+            if (!p.w_resident) umma_commit(bar_wempty + 8 * ws);
+          }
+          __syncwarp();
+          if (!p.w_resident) {
+            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+          }
+        }
+        if (lane == 0) {
+          umma_commit(bar_aempty + 8 * as);
+          if (chunk == p.chunks - 1) umma_commit(bar_tfull + 8 * acc);
+        }
+        __syncwarp();
+        if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ============================ epilogue ================================
+    const int lg = warp & 3;
+    const int img = p.Hp * p.Wp;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tfull + 8 * acc, tphase);
+      tcgen05_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        const int q = t * TILE_P + half * BLOCK_M + lg * 32 + lane;  // position inside the group
+        const bool valid = q < p.group_positions;
+        const int rem = q % img;
+        const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
+        const bool interior = valid && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
+        const int64_t off = ((int64_t)group_row0 + q) * p.N;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * p.N);
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a);
+          tmem_ld_wait();
+          if (valid) {
+          const float* sc = p.scale + wrow0 + c0;
+          const float* bs = p.bias + wrow0 + c0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
+            if (interior) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                f[j] = fmaf(__uint_as_float(a[v * 8 + j]), __ldg(sc + v * 8 + j), __ldg(bs + v * 8 + j));
+              if (p.residual) {
+                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 rf = __bfloat1622float2(r2[j]);
+                  f[2 * j] += rf.x;
+                  f[2 * j + 1] += rf.y;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+            }
+            *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = o;
+          }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static bool supported(int H, int W, int C, int N) {
+  return C % 64 == 0 && N % 32 == 0 && N <= 128 && W + 2 <= 120 && H >= 1;
+}
+
+}  // namespace flat
+
+int amoe_conv_flat_init(amoe_ctx* ctx) {
+  (void)ctx;
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET + 1024));
+  return 0;
+}
+
+extern "C" {
+
+int amoe_conv3x3_flat_supported(int H, int W, int Cin, int Cout) { return flat::supported(H, W, Cin, Cout) ? 1 : 0; }
+
+int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias,
+                          const void* residual, void* y, int G, int B, int H, int W, int Cin, int Cout, int relu,
+                          void* stream) {
+  using namespace flat;
+  AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv3x3_flat_fwd: NULL argument");
+  AMOE_REQUIRE(flat::supported(H, W, Cin, Cout), "amoe_conv3x3_flat_fwd: unsupported shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+               "amoe_conv3x3_flat_fwd: pointers must be 16-byte aligned");
+  Params p;
+  p.G = G; p.B = B; p.H = H; p.W = W; p.Hp = H + 2; p.Wp = W + 2; p.C = Cin; p.N = Cout;
+  p.chunks = Cin / BLOCK_K;
+  p.rows_pad = (TILE_P + 2 * p.Wp + 2 + 15) & ~15;
+  const int64_t gp = (int64_t)B * p.Hp * p.Wp;
+  AMOE_REQUIRE(gp * G < (1ll << 31) - 4096, "amoe_conv3x3_flat_fwd: too many positions");
+  p.group_positions = (int)gp;
+  p.tiles_per_group = (int)((gp + TILE_P - 1) / TILE_P);
+  p.relu = relu;
+  p.scale = scale; p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.y = (__nv_bfloat16*)y;
+  const int a_stage = p.rows_pad * 128;
+  const int w_tile = Cout * 128;
+  const int w_all = p.chunks * 9 * w_tile;
+  p.w_resident = (w_all <= W_RESIDENT_MAX && SMEM_BUDGET - w_all >= 2 * a_stage) ? 1 : 0;
+  int w_bytes;
+  if (p.w_resident) {
+    p.w_stages = 0;
+    w_bytes = w_all;
+  } else {
+    p.w_stages = std::min(MAX_W_STAGES, std::max(2, (SMEM_BUDGET - 2 * a_stage) / w_tile));
+    // keep at least 2 (preferably 3) activation stages
+    while (p.w_stages > 3 && SMEM_BUDGET - p.w_stages * w_tile < 3 * a_stage) --p.w_stages;
+    w_bytes = p.w_stages * w_tile;
+  }
+  p.a_stages = std::min(MAX_A_STAGES, (SMEM_BUDGET - w_bytes) / a_stage);
+  AMOE_REQUIRE(p.a_stages >= 1, "amoe_conv3x3_flat_fwd: shared memory budget exceeded");
+  if (gp == 0) return 0;
+
+  CUtensorMap tmA, tmW;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)(gp * G)};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.rows_pad / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_flat_fwd: cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)G * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)Cout};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_flat_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  }
+  const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
+  const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + 1024;
+  conv3x3_flat_kernel<<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // extern "C"

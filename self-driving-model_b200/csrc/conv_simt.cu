@@ -133,41 +133,47 @@ int amoe_conv2d_simt(amoe_ctx* ctx, const void* x, const void* w, const float* s
   return 0;
 }
 
-// ---- MaxPool2d(3, stride 2, pad 1), NHWC; VEC channels per thread ----
+// ---- MaxPool2d(3, stride 2, pad 1), NHWC; VEC channels per thread.  out_pad > 0 writes into a
+// physically padded output [NB][Ho+2p][Wo+2p][C] and fills the border with zeros. ----
 template <typename T, int VEC>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C,
-                                    int Ho, int Wo, int64_t total) {
+                                    int Ho, int Wo, int out_pad, int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const int Hop = Ho + 2 * out_pad, Wop = Wo + 2 * out_pad;
   int cv = C / VEC;
   int c = (int)(i % cv) * VEC;
   int64_t r = i / cv;
-  int ow = (int)(r % Wo);
-  r /= Wo;
-  int oh = (int)(r % Ho);
-  int64_t n = r / Ho;
+  int owp = (int)(r % Wop);
+  r /= Wop;
+  int ohp = (int)(r % Hop);
+  int64_t n = r / Hop;
+  const int oh = ohp - out_pad, ow = owp - out_pad;
+  const bool border = oh < 0 || oh >= Ho || ow < 0 || ow >= Wo;
   float m[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) m[v] = -INFINITY;
-  for (int kh = 0; kh < 3; ++kh) {
-    int ih = oh * 2 - 1 + kh;
-    if (ih < 0 || ih >= H) continue;
-    for (int kw = 0; kw < 3; ++kw) {
-      int iw = ow * 2 - 1 + kw;
-      if (iw < 0 || iw >= W) continue;
-      const T* s = x + ((n * H + ih) * W + iw) * C + c;
-      if constexpr (sizeof(T) * VEC == 16) {
-        uint4 raw = *reinterpret_cast<const uint4*>(s);
-        const T* e = reinterpret_cast<const T*>(&raw);
+  for (int v = 0; v < VEC; ++v) m[v] = border ? 0.f : -INFINITY;
+  if (!border) {
+    for (int kh = 0; kh < 3; ++kh) {
+      int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        const T* s = x + ((n * H + ih) * W + iw) * C + c;
+        if constexpr (sizeof(T) * VEC == 16) {
+          uint4 raw = *reinterpret_cast<const uint4*>(s);
+          const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], ld_as_float<T>(e + v));
-      } else {
+          for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], ld_as_float<T>(e + v));
+        } else {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], ld_as_float<T>(s + v));
+          for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], ld_as_float<T>(s + v));
+        }
       }
     }
   }
-  T* d = y + ((n * Ho + oh) * Wo + ow) * C + c;
+  T* d = y + ((n * Hop + ohp) * Wop + owp) * C + c;
   if constexpr (sizeof(T) * VEC == 16) {
     uint4 raw;
     T* e = reinterpret_cast<T*>(&raw);
@@ -181,27 +187,29 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
 }
 
 extern "C" int amoe_maxpool3x3s2_fwd(amoe_ctx* ctx, const void* x, void* y, int NB, int H, int W,
-                                      int C, int dtype, void* stream) {
+                                      int C, int dtype, int out_pad, void* stream) {
   AMOE_REQUIRE(ctx && x && y, "amoe_maxpool3x3s2_fwd: NULL argument");
+  AMOE_REQUIRE(out_pad >= 0, "amoe_maxpool3x3s2_fwd: negative out_pad");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (NB == 0) return 0;
+  const int64_t pos = (int64_t)NB * (Ho + 2 * out_pad) * (Wo + 2 * out_pad);
   if (dtype == AMOE_BF16 && C % 8 == 0) {
-    int64_t total = (int64_t)NB * Ho * Wo * (C / 8);
+    int64_t total = pos * (C / 8);
     maxpool3x3s2_kernel<__nv_bfloat16, 8><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, Ho, Wo, total);
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, Ho, Wo, out_pad, total);
   } else if (dtype == AMOE_BF16) {
-    int64_t total = (int64_t)NB * Ho * Wo * C;
+    int64_t total = pos * C;
     maxpool3x3s2_kernel<__nv_bfloat16, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, Ho, Wo, total);
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, Ho, Wo, out_pad, total);
   } else if (dtype == AMOE_F32 && C % 4 == 0) {
-    int64_t total = (int64_t)NB * Ho * Wo * (C / 4);
+    int64_t total = pos * (C / 4);
     maxpool3x3s2_kernel<float, 4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const float*)x, (float*)y, H, W, C, Ho, Wo, total);
+        (const float*)x, (float*)y, H, W, C, Ho, Wo, out_pad, total);
   } else if (dtype == AMOE_F32) {
-    int64_t total = (int64_t)NB * Ho * Wo * C;
+    int64_t total = pos * C;
     maxpool3x3s2_kernel<float, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const float*)x, (float*)y, H, W, C, Ho, Wo, total);
+        (const float*)x, (float*)y, H, W, C, Ho, Wo, out_pad, total);
   } else {
     AMOE_REQUIRE(false, "amoe_maxpool3x3s2_fwd: bad dtype %d", dtype);
   }

@@ -18,12 +18,10 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tc {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // bf16 elements per K chunk = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_TAPS = 49;
@@ -45,6 +43,7 @@ struct Params {
   int num_taps, k_chunks;           // K iterations per tile = num_taps * k_chunks
   int stages;
   int relu, x_shared;
+  int out_pad;                      // output (and residual) tensors carry a physical border of out_pad pixels
   int split_c;                      // output sub-tensor width: channel ch of group g goes to tensor
                                     // (g*Cout/split_c + ch/split_c), channel ch%split_c (== Cout normally)
   int total_tiles;
@@ -54,115 +53,6 @@ struct Params {
   __nv_bfloat16* y;
   Tap taps[MAX_TAPS];
 };
-
-// ------------------------------- PTX wrappers -------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
-                                            int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
-                                            int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 B apart):
-// start address >>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 | SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
 
 struct TileCoord {
   int g, bt, ht, wt, nt;
@@ -293,8 +183,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
       const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
       const int chn = tc_.nt * p.block_n;  // first channel of this tile inside its group
-      const int64_t pix = ((int64_t)nl * p.Ho + oh) * p.Wo + ow;
-      const int64_t sub_stride = (int64_t)p.B * p.Ho * p.Wo * p.split_c;
+      const int Hop = p.Ho + 2 * p.out_pad, Wop = p.Wo + 2 * p.out_pad;
+      const int64_t pix = ((int64_t)nl * Hop + oh + p.out_pad) * Wop + ow + p.out_pad;
+      const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
       const int nsplit = p.Cout / p.split_c;
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
@@ -390,7 +281,7 @@ struct AView {
 static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const void* w, int Ktot,
                           const float* scale, const float* bias, const void* residual, void* y, int G,
                           int x_shared, int B, int Ho, int Wo, int Cout, int split_c, int num_taps,
-                          const tc::Tap* taps, int k_chunks, int relu, cudaStream_t st) {
+                          const tc::Tap* taps, int k_chunks, int relu, int out_pad, cudaStream_t st) {
   using namespace tc;
   AMOE_REQUIRE(num_taps <= MAX_TAPS, "conv_tc: %d taps exceed the limit of %d", num_taps, MAX_TAPS);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -407,7 +298,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   p.block_n = Cout >= 256 ? 256 : Cout;
   AMOE_REQUIRE(Cout % p.block_n == 0 && p.block_n % 32 == 0, "conv_tc: unsupported channel tiling Cout=%d", Cout);
   p.n_tiles_n = Cout / p.block_n;
-  p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c;
+  p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c; p.out_pad = out_pad;
   p.num_taps = num_taps;
   p.k_chunks = k_chunks;
   const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
@@ -454,8 +345,11 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
 static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
                           const float* bias, const void* residual, void* y, int G, int x_shared,
                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw,
-                          int ph, int pw, int Ho, int Wo, int relu, cudaStream_t st) {
+                          int ph, int pw, int Ho, int Wo, int relu, int in_pad, int out_pad, cudaStream_t st) {
   using namespace tc;
+  // a physically padded input [N][H+2*in_pad][W+2*in_pad][C] is just a bigger image whose
+  // filter taps start in_pad pixels further right/down
+  H += 2 * in_pad; W += 2 * in_pad; ph -= in_pad; pw -= in_pad;
   AMOE_REQUIRE(KH * KW <= MAX_TAPS, "conv_tc: %dx%d filter has more than %d taps", KH, KW, MAX_TAPS);
   Tap taps[MAX_TAPS];
   for (int kh = 0; kh < KH; ++kh)
@@ -473,7 +367,7 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
   av.strides[0] = (uint64_t)sw * Cin * 2; av.strides[1] = (uint64_t)W * Cin * 2;
   av.strides[2] = (uint64_t)sh * W * Cin * 2; av.strides[3] = (uint64_t)H * W * Cin * 2;
   return launch_generic(ctx, x, av, w, KH * KW * Cin, scale, bias, residual, y, G, x_shared, B, Ho, Wo, Cout,
-                        Cout, KH * KW, taps, Cin / BLOCK_K, relu, st);
+                        Cout, KH * KW, taps, Cin / BLOCK_K, relu, out_pad, st);
 }
 
 extern "C" {
@@ -510,13 +404,14 @@ int amoe_conv2d_rowwin_fwd(amoe_ctx* ctx, const void* x, const void* w, const fl
   av.strides[0] = (uint64_t)stride_w * Cp * 2; av.strides[1] = row; av.strides[2] = (uint64_t)stride_h * row;
   av.strides[3] = (uint64_t)H * row;
   return launch_generic(ctx, x, av, w, KH * BLOCK_K, scale, bias, nullptr, y, 1, 0, B, Ho, Wo, Cout, split_c, KH,
-                        taps, 1, relu, (cudaStream_t)stream);
+                        taps, 1, relu, 0, (cudaStream_t)stream);
 }
 
 int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
                     const float* bias, const void* residual, void* y, int G, int x_shared, int B,
                     int H, int W, int Cin, int Cout, int KH, int KW, int stride_h, int stride_w,
-                    int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype, int impl, void* stream) {
+                    int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype, int impl, int in_pad, int out_pad,
+                    void* stream) {
   AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv2d_fwd: NULL argument");
   AMOE_REQUIRE(dtype == AMOE_F32 || dtype == AMOE_BF16, "amoe_conv2d_fwd: bad dtype %d", dtype);
   AMOE_REQUIRE(G >= 1 && B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 &&
@@ -526,11 +421,14 @@ int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* sc
   AMOE_REQUIRE((Ho - 1) * stride_h - pad_h < H && (Wo - 1) * stride_w - pad_w < W,
                "amoe_conv2d_fwd: Ho/Wo inconsistent with input size");
   cudaStream_t st = (cudaStream_t)stream;
-  bool tc_ok = dtype == AMOE_BF16 && tc::supported(H, W, Cin, Cout, stride_h, stride_w);
+  AMOE_REQUIRE(in_pad >= 0 && out_pad >= 0, "amoe_conv2d_fwd: negative in_pad/out_pad");
+  bool tc_ok = dtype == AMOE_BF16 && tc::supported(H + 2 * in_pad, W + 2 * in_pad, Cin, Cout, stride_h, stride_w);
+  if (in_pad || out_pad)
+    AMOE_REQUIRE(tc_ok && impl != 1, "amoe_conv2d_fwd: padded layouts are only implemented by the tcgen05 path");
   if (impl == 2) AMOE_REQUIRE(tc_ok, "amoe_conv2d_fwd: tcgen05 path does not take this shape/dtype");
   if (tc_ok && impl != 1)
     return conv_tc_launch(ctx, x, w, scale, bias, residual, y, G, x_shared, B, H, W, Cin, Cout, KH, KW,
-                          stride_h, stride_w, pad_h, pad_w, Ho, Wo, relu, st);
+                          stride_h, stride_w, pad_h, pad_w, Ho, Wo, relu, in_pad, out_pad, st);
   return amoe_conv2d_simt(ctx, x, w, scale, bias, residual, y, G, x_shared, B, H, W, Cin, Cout, KH, KW,
                           stride_h, stride_w, pad_h, pad_w, Ho, Wo, relu, dtype, st);
 }

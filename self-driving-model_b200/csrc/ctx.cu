@@ -13,7 +13,8 @@ void amoe_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int amoe_conv_tc_init(amoe_ctx* ctx);  // conv_tc.cu
+int amoe_conv_tc_init(amoe_ctx* ctx);    // conv_tc.cu
+int amoe_conv_flat_init(amoe_ctx* ctx);  // conv_flat.cu
 
 extern "C" {
 
@@ -42,7 +43,7 @@ int amoe_create(int device, amoe_ctx** out) {
     return -1;
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
-  if (amoe_conv_tc_init(ctx) != 0) {
+  if (amoe_conv_tc_init(ctx) != 0 || amoe_conv_flat_init(ctx) != 0) {
     delete ctx;
     return -1;
   }

@@ -108,7 +108,7 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
     """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
     G = len(experts)
     bbs = [e.backbone for e in experts]
-    if dtype == torch.bfloat16:   # Cin=3 stem on the tensor cores through row windows, 3 experts in one GEMM
+    if _ops.use_rowwin(dtype):   # Cin=3 stem on the tensor cores through row windows, 3 experts in one GEMM
         stem = _ops.pack_rowwin([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
     else:
         stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
@@ -134,7 +134,7 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
 def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCHW fp32 frame -> the NHWC layout the first convolutions read: bf16 rows physically padded
     for the row-window tensor-core stem, or plain [B,H,W,4] fp32 for the fp32 path."""
-    if dtype == torch.bfloat16:
+    if _ops.use_rowwin(dtype):
         W = image.shape[3]
         return _ops.image_to_nhwc_padded(image, _ops.ROWWIN_CP, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), dtype)
     return _ops.image_to_nhwc(image, 4, dtype)
@@ -155,12 +155,27 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
         y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)               # [G*B,H/2,W/2,64]
     else:
         y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)
-    y = _ops.maxpool3x3s2(y)                                             # [G*B,H/4,W/4,64]
+    # Activations of the 64/128-channel stages live in a physically padded layout (zero border of one
+    # pixel) when their 3x3/s1 convolutions run through the halo-reuse kernel; `pad` tracks the layout.
+    flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()
+    h_cur, w_cur = (y.shape[1] - 1) // 2 + 1, (y.shape[2] - 1) // 2 + 1
+    pad = 1 if (flat_ok and _ops.flat_supported(pack.blocks[0][1], h_cur, w_cur, pack.dtype)) else 0
+    y = _ops.maxpool3x3s2(y, out_pad=pad)                                # [G*B,H/4(+2),W/4(+2),64]
     for (c1, c2, dn) in pack.blocks:
-        h_in, w_in = y.shape[1], y.shape[2]
-        out = _ops.conv2d(c1, y, B, h_in, w_in)
-        identity = y if dn is None else _ops.conv2d(dn, y, B, h_in, w_in)
-        y = _ops.conv2d(c2, out, B, out.shape[1], out.shape[2], residual=identity)
+        # geometry of this block's output and whether its stride-1 convs take the flat kernel
+        h_out = (h_cur + 2 * c1.ph - c1.kh) // c1.sh + 1
+        w_out = (w_cur + 2 * c1.pw - c1.kw) // c1.sw + 1
+        pad_out = 1 if (flat_ok and _ops.flat_supported(c2, h_out, w_out, pack.dtype)) else 0
+        if pad and pad_out and c1.sh == 1 and _ops.flat_supported(c1, h_cur, w_cur, pack.dtype):
+            out = _ops.conv3x3_flat(c1, y, B, h_cur, w_cur)
+        else:
+            out = _ops.conv2d(c1, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out, zero_border=True)
+        identity = y if dn is None else _ops.conv2d(dn, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out)
+        if pad_out:
+            y = _ops.conv3x3_flat(c2, out, B, h_out, w_out, residual=identity)
+        else:
+            y = _ops.conv2d(c2, out, B, h_out, w_out, residual=identity)
+        h_cur, w_cur, pad = h_out, w_out, pad_out
     h, w = y.shape[1], y.shape[2]
     hid = _ops.conv2d(pack.head3, y, B, h, w)                            # [G*B,h,w,256]
     pooled = torch.empty((B, sum(pack.n_ch)), device=image.device, dtype=torch.float32)

@@ -57,7 +57,7 @@ class TrajectoryPolicy(nn.Module):
         p = self._packs.get(key)
         if p is None or p["stamp"] != stamp:
             net = self.backbone.net
-            first = (_ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if dtype == torch.bfloat16 else
+            first = (_ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if _ops.use_rowwin(dtype) else
                      _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4))
             convs = [
                 first,

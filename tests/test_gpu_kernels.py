@@ -49,19 +49,6 @@ def _conv_case(G, B, H, W, Cin, Cout, k, s, p, dtype, residual, relu, bn=True, b
             res = res.bfloat16().float()
         for c in convs:
             c.weight.data = c.weight.data.bfloat16().float()
-    # reference
-    refs = []
-    with torch.no_grad():
-        for gi in range(G):
-            y = convs[gi](x[gi * B:(gi + 1) * B])
-            if bn:
-                y = bns[gi](y)
-            if res is not None:
-                y = y + res[gi * B:(gi + 1) * B]
-            if relu:
-                y = F.relu(y)
-            refs.append(y)
-    ref = torch.cat(refs, 0)
     # ours
     cin_pad = 4 if Cin == 3 else None
     pc = _ops.pack_conv(convs, bns if bn else None, dtype, torch.device(DEV), relu=relu, cin_pad=cin_pad)
@@ -72,6 +59,19 @@ def _conv_case(G, B, H, W, Cin, Cout, k, s, p, dtype, residual, relu, bn=True, b
     rn = res.permute(0, 2, 3, 1).contiguous().to(dtype) if res is not None else None
     y = _ops.conv2d(pc, xn, B, H, W, residual=rn, impl=impl)
     torch.cuda.synchronize()
+    # reference
+    refs = []
+    with torch.no_grad():
+        for gi in range(G):
+            r = convs[gi](x[gi * B:(gi + 1) * B])
+            if bn:
+                r = bns[gi](r)
+            if res is not None:
+                r = r + res[gi * B:(gi + 1) * B]
+            if relu:
+                r = F.relu(r)
+            refs.append(r)
+    ref = torch.cat(refs, 0)
     return y.float().permute(0, 3, 1, 2), ref
 
 
@@ -170,14 +170,99 @@ def test_conv_tc_rowwin(case):
         convs.append(c.to(DEV))
         bns.append(b.to(DEV).eval())
     img = torch.randn((B, 3, H, W), generator=g).bfloat16().float().to(DEV)
-    with torch.no_grad():
-        ref = torch.cat([F.relu(bn(c(img))) for c, bn in zip(convs, bns)], 0)
     pc = _ops.pack_rowwin(convs, bns, torch.device(DEV), relu=True)
     xp = _ops.image_to_nhwc_padded(img, 4, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), torch.bfloat16)
     assert torch.equal(xp[:, :, 4:4 + W, :3].float(), img.permute(0, 2, 3, 1)) and (xp[:, :, :4] == 0).all() and (xp[:, :, 4 + W:] == 0).all()
     y = _ops.conv2d_rowwin(pc, xp, B, H, W).float().permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = torch.cat([F.relu(bn(c(img))) for c, bn in zip(convs, bns)], 0)
     assert y.shape == ref.shape
     assert rel_err(y, ref) < 8e-3 and rel_l2(y, ref) < 4e-3, (rel_err(y, ref), rel_l2(y, ref))
+
+
+def _mk_conv_bn(Cin, Cout, k, s, p, g, n=1, bias=False):
+    convs, bns = [], []
+    for _ in range(n):
+        c = nn.Conv2d(Cin, Cout, k, s, p, bias=bias)
+        b = nn.BatchNorm2d(Cout)
+        with torch.no_grad():
+            c.weight.copy_((torch.randn(c.weight.shape, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).bfloat16().float())
+            b.weight.copy_(1 + 0.1 * torch.randn(Cout, generator=g))
+            b.bias.copy_(0.1 * torch.randn(Cout, generator=g))
+            b.running_mean.copy_(0.1 * torch.randn(Cout, generator=g))
+            b.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+        convs.append(c.to(DEV))
+        bns.append(b.to(DEV).eval())
+    return convs, bns
+
+
+def _pad_nhwc(x_nchw, dtype):
+    """NCHW fp32 -> physically padded NHWC [N,H+2,W+2,C] with a zero border."""
+    return F.pad(x_nchw.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).to(dtype).contiguous()
+
+
+FLAT_SHAPES = [
+    # G, B, H, W, C, N, residual
+    (1, 2, 16, 16, 64, 64, False),     # resident weights, 3 tiles
+    (1, 2, 16, 16, 64, 64, True),
+    (3, 2, 64, 64, 64, 64, True),      # layer1 geometry, grouped experts
+    (1, 3, 32, 32, 128, 128, True),    # layer2: 2 chunks, streamed weights
+    (2, 1, 56, 56, 64, 64, False),     # 224-px geometry
+    (1, 5, 14, 14, 128, 128, True),
+    (1, 40, 16, 16, 64, 64, False),    # many tiles per CTA: both accumulators, ring wrap-around
+    (1, 2, 8, 8, 64, 128, False),      # Cin != Cout
+]
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", FLAT_SHAPES)
+def test_conv_flat_bf16(shape):
+    """Halo-reuse 3x3/s1 kernel on physically padded activations (csrc/conv_flat.cu)."""
+    from automoe_b200 import _ops
+    G, B, H, W, C, N, residual = shape
+    g = torch.Generator().manual_seed(6)
+    convs, bns = _mk_conv_bn(C, N, 3, 1, 1, g, n=G)
+    x = torch.randn((G * B, C, H, W), generator=g).bfloat16().float().to(DEV)
+    res = torch.randn((G * B, N, H, W), generator=g).bfloat16().float().to(DEV) if residual else None
+    pc = _ops.pack_conv(convs, bns, torch.bfloat16, torch.device(DEV), relu=True)
+    assert _ops.flat_supported(pc, H, W, torch.bfloat16)
+    xp = _pad_nhwc(x, torch.bfloat16)
+    rp = _pad_nhwc(res, torch.bfloat16) if residual else None
+    y = _ops.conv3x3_flat(pc, xp, B, H, W, residual=rp)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = torch.cat([F.relu(bns[i](convs[i](x[i * B:(i + 1) * B])) + (res[i * B:(i + 1) * B] if residual else 0))
+                         for i in range(G)], 0)
+    yi = y[:, 1:-1, 1:-1, :].float().permute(0, 3, 1, 2)
+    assert (y[:, 0] == 0).all() and (y[:, -1] == 0).all() and (y[:, :, 0] == 0).all() and (y[:, :, -1] == 0).all()
+    assert rel_err(yi, ref) < 8e-3 and rel_l2(yi, ref) < 4e-3, (rel_err(yi, ref), rel_l2(yi, ref))
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [(64, 128, 3, 2, 1, 32, 32), (64, 128, 1, 2, 0, 32, 32), (128, 256, 3, 2, 1, 16, 16),
+                                  (64, 64, 3, 1, 1, 16, 16)])
+def test_conv_tc_padded_layouts(case):
+    """Per-tap tcgen05 kernel reading a physically padded input and/or writing a padded output."""
+    from automoe_b200 import _ops
+    Cin, Cout, k, s, p, H, W = case
+    B = 3
+    g = torch.Generator().manual_seed(8)
+    convs, bns = _mk_conv_bn(Cin, Cout, k, s, p, g)
+    x = torch.randn((B, Cin, H, W), generator=g).bfloat16().float().to(DEV)
+    pc = _ops.pack_conv(convs, bns, torch.bfloat16, torch.device(DEV), relu=True)
+    xp = _pad_nhwc(x, torch.bfloat16)
+    y_pp = _ops.conv2d(pc, xp, B, H, W, in_pad=1, out_pad=1, zero_border=True)
+    y_pu = _ops.conv2d(pc, xp, B, H, W, in_pad=1, out_pad=0)
+    y_up = _ops.conv2d(pc, x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous(), B, H, W, in_pad=0, out_pad=1, zero_border=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = F.relu(bns[0](convs[0](x)))
+    for y in (y_pp[:, 1:-1, 1:-1], y_pu, y_up[:, 1:-1, 1:-1]):
+        yy = y.float().permute(0, 3, 1, 2)
+        assert yy.shape == ref.shape
+        assert rel_err(yy, ref) < 8e-3, rel_err(yy, ref)
+    assert (y_pp[:, 0] == 0).all() and (y_pp[:, :, -1] == 0).all()
 
 
 def test_maxpool():
@@ -188,6 +273,9 @@ def test_maxpool():
             ref = F.max_pool2d(x.float(), 3, 2, 1)
             y = _ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2).float()
             assert torch.equal(y, ref)
+            yp = _ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous(), out_pad=1)
+            assert torch.equal(yp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float(), ref)
+            assert (yp[:, 0] == 0).all() and (yp[:, -1] == 0).all() and (yp[:, :, 0] == 0).all() and (yp[:, :, -1] == 0).all()
 
 
 def test_image_to_nhwc():
