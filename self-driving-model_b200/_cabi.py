@@ -19,7 +19,7 @@ LIB_PATH = _HERE / "lib" / "libautomoe_b200.so"
 F32, BF16 = 0, 1
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()  # re-entrant: ctx() loads the library while holding it
 _ctxs: dict[int, C.c_void_p] = {}
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -94,6 +94,7 @@ def ctx(device: torch.device | int | None = None) -> C.c_void_p:
         idx = device.index if device.index is not None else torch.cuda.current_device()
     h = _ctxs.get(idx)
     if h is None:
+        lib()
         with _lock:
             h = _ctxs.get(idx)
             if h is None:
