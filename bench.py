@@ -107,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -217,12 +217,12 @@ def run_b200(args):
             return model(b)
 
     # ---------------- device-resident throughput (value) ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # nvidia-smi needs ~100 ms to start: launch it before the warm-up
     for _ in range(max(args.warmup, 3)):
         out = step(batch)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     n0 = _cabi.launch_count(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -235,6 +235,13 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        # short timed regions end before nvidia-smi has produced samples: keep the same load running
+        # (untimed) until a handful of samples under load exist
+        t_wait = time.time()
+        while len(sampler.lines) < 8 and time.time() - t_wait < 3.0:
+            step(batch)
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms = ms.item()
     value = world * B * args.steps / (ms / 1e3)
@@ -286,8 +293,16 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        # raw host->device rate of this box for the same pinned buffer (context for the e2e number)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        slots[0]["image"].copy_(pinned[0]["image"], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = pinned[0]["image"].numel() * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
         e2e = {"value": world * B * args.steps / (ems.item() / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems.item() / args.steps}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems.item() / args.steps,
+               "h2d_gbs_measured": h2d_gbs}
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv), measured live ----------------
     pk = peaks()

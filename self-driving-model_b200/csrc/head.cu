@@ -3,9 +3,12 @@
 #include "common.cuh"
 
 // ---- 1x1 conv + mean over pixels -------------------------------------------
-// One CTA per image.  Phase 1: low[b,p,n] = b[n] + sum_c x[b,p,c]*w[n,c] with one
-// warp per (pixel, n) pair group; phase 2: pooled[b,n] = mean_p low[b,p,n] summed in
-// a fixed order (deterministic, the gate's top-1 depends on it).
+// One CTA per image.  Weights [N][Cin] and a chunk of HEAD_PX pixels live in shared memory (rows
+// padded to an odd stride -> conflict-free); one thread per (pixel, n) output does a Cin-long
+// dot product.  Phase 2: pooled[b,n] = mean_p low[b,p,n], summed in a fixed order (deterministic,
+// the gate's top-1 depends on it).
+constexpr int HEAD_PX = 16;
+
 template <typename T>
 __global__ __launch_bounds__(256) void head1x1_pool_kernel(const T* __restrict__ x,
                                                            const float* __restrict__ w,
@@ -13,20 +16,32 @@ __global__ __launch_bounds__(256) void head1x1_pool_kernel(const T* __restrict__
                                                            float* __restrict__ low,
                                                            float* __restrict__ pooled, int pooled_ld,
                                                            int HW, int Cin, int N) {
-  extern __shared__ float sw[];  // [N][Cin] weights
+  extern __shared__ float smh[];
+  const int ld = Cin | 1;              // odd row stride
+  float* sw = smh;                     // [N][ld]
+  float* sx = smh + N * ld;            // [HEAD_PX][ld]
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) sw[(i / Cin) * ld + (i % Cin)] = w[i];
   const T* xb = x + (int64_t)b * HW * Cin;
   float* lb = low + (int64_t)b * HW * N;
-  for (int p = warp; p < HW; p += nwarp) {
-    const T* xp = xb + (int64_t)p * Cin;
-    for (int n = 0; n < N; ++n) {
-      float s = 0.f;
-      for (int c = lane; c < Cin; c += 32) s = fmaf(ld_as_float<T>(xp + c), sw[n * Cin + c], s);
-      s = warp_sum(s);
-      if (lane == 0) lb[(int64_t)p * N + n] = s + bias[n];
+  for (int p0 = 0; p0 < HW; p0 += HEAD_PX) {
+    const int np = min(HEAD_PX, HW - p0);
+    __syncthreads();  // previous chunk consumed (also orders the weight fill before first use)
+    for (int i = threadIdx.x; i < np * Cin; i += blockDim.x)
+      sx[(i / Cin) * ld + (i % Cin)] = ld_as_float<T>(xb + (int64_t)p0 * Cin + i);
+    __syncthreads();
+    for (int o = threadIdx.x; o < np * N; o += blockDim.x) {
+      const int pl = o / N, n = o - pl * N;
+      const float* xr = sx + pl * ld;
+      const float* wr = sw + n * ld;
+      float s0 = 0.f, s1 = 0.f;
+      int c = 0;
+      for (; c + 1 < Cin; c += 2) {
+        s0 = fmaf(xr[c], wr[c], s0);
+        s1 = fmaf(xr[c + 1], wr[c + 1], s1);
+      }
+      if (c < Cin) s0 = fmaf(xr[c], wr[c], s0);
+      lb[(int64_t)(p0 + pl) * N + n] = (s0 + s1) + bias[n];
     }
   }
   __syncthreads();  // low[] of this image is complete and visible to the block
@@ -162,8 +177,8 @@ int amoe_head1x1_pool_fwd(amoe_ctx* ctx, const void* x, const float* w, const fl
                           float* pooled, int pooled_ld, int B, int HW, int Cin, int N, int x_dtype,
                           void* stream) {
   AMOE_REQUIRE(ctx && x && w && b && low && pooled, "amoe_head1x1_pool_fwd: NULL argument");
-  size_t smem = (size_t)N * Cin * sizeof(float);
-  AMOE_REQUIRE(smem <= 48 * 1024, "amoe_head1x1_pool_fwd: N*Cin=%d too large", N * Cin);
+  size_t smem = (size_t)(N + HEAD_PX) * (Cin | 1) * sizeof(float);
+  AMOE_REQUIRE(smem <= 48 * 1024, "amoe_head1x1_pool_fwd: (N+%d)*Cin too large for shared memory (N=%d Cin=%d)", HEAD_PX, N, Cin);
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == AMOE_BF16)

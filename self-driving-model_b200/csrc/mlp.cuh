@@ -9,45 +9,70 @@ constexpr int GATE_THREADS = 512;
 
 __host__ __device__ inline int64_t al4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
-// y[f][o] = act(b[o] + sum_i W[o][i] * x[f][i]),  x,y in shared memory
+// y[f][o] = act(b[o] + sum_i W[o][i] * x[f][i]),  x,y in shared memory.
+// A warp owns MLP_RPW output rows at a time so that MLP_RPW independent 16-byte weight loads per lane
+// are in flight (the kernel is bound by the L2->SM latency of streaming the weight rows).
+constexpr int MLP_RPW = 4;
+
 __device__ __forceinline__ void linear_ft(const float* __restrict__ Wg, const float* __restrict__ bg,
                                           const float* x, int x_ld, int in_dim, float* y, int y_ld,
                                           int out_dim, bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const bool vec = (in_dim & 3) == 0 && (x_ld & 3) == 0;
-  for (int o = warp; o < out_dim; o += nwarp) {
-    const float* wr = Wg + (int64_t)o * in_dim;
-    float acc[GATE_FT];
+  for (int o0 = warp * MLP_RPW; o0 < out_dim; o0 += nwarp * MLP_RPW) {
+    float acc[MLP_RPW][GATE_FT];
 #pragma unroll
-    for (int f = 0; f < GATE_FT; ++f) acc[f] = 0.f;
+    for (int r = 0; r < MLP_RPW; ++r)
+#pragma unroll
+      for (int f = 0; f < GATE_FT; ++f) acc[r][f] = 0.f;
     if (vec) {
       const int n4 = in_dim >> 2;
       for (int i = lane; i < n4; i += 32) {
-        float4 w4 = __ldg(reinterpret_cast<const float4*>(wr) + i);
+        float4 w4[MLP_RPW];
+#pragma unroll
+        for (int r = 0; r < MLP_RPW; ++r)
+          w4[r] = (o0 + r < out_dim) ? __ldg(reinterpret_cast<const float4*>(Wg + (int64_t)(o0 + r) * in_dim) + i)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int f = 0; f < GATE_FT; ++f) {
-          float4 x4 = *reinterpret_cast<const float4*>(x + f * x_ld + (i << 2));
-          acc[f] = fmaf(w4.x, x4.x, acc[f]);
-          acc[f] = fmaf(w4.y, x4.y, acc[f]);
-          acc[f] = fmaf(w4.z, x4.z, acc[f]);
-          acc[f] = fmaf(w4.w, x4.w, acc[f]);
+          const float4 x4 = *reinterpret_cast<const float4*>(x + f * x_ld + (i << 2));
+#pragma unroll
+          for (int r = 0; r < MLP_RPW; ++r) {
+            acc[r][f] = fmaf(w4[r].x, x4.x, acc[r][f]);
+            acc[r][f] = fmaf(w4[r].y, x4.y, acc[r][f]);
+            acc[r][f] = fmaf(w4[r].z, x4.z, acc[r][f]);
+            acc[r][f] = fmaf(w4[r].w, x4.w, acc[r][f]);
+          }
         }
       }
     } else {
       for (int i = lane; i < in_dim; i += 32) {
-        float wv = __ldg(wr + i);
+        float wv[MLP_RPW];
 #pragma unroll
-        for (int f = 0; f < GATE_FT; ++f) acc[f] = fmaf(wv, x[f * x_ld + i], acc[f]);
+        for (int r = 0; r < MLP_RPW; ++r) wv[r] = (o0 + r < out_dim) ? __ldg(Wg + (int64_t)(o0 + r) * in_dim + i) : 0.f;
+#pragma unroll
+        for (int f = 0; f < GATE_FT; ++f) {
+          const float xv = x[f * x_ld + i];
+#pragma unroll
+          for (int r = 0; r < MLP_RPW; ++r) acc[r][f] = fmaf(wv[r], xv, acc[r][f]);
+        }
       }
     }
 #pragma unroll
-    for (int f = 0; f < GATE_FT; ++f) acc[f] = warp_sum(acc[f]);
-    if (lane == 0) {
-      float bv = __ldg(bg + o);
+    for (int r = 0; r < MLP_RPW; ++r)
 #pragma unroll
-      for (int f = 0; f < GATE_FT; ++f) {
-        float v = acc[f] + bv;
-        y[f * y_ld + o] = relu ? fmaxf(v, 0.f) : v;
+      for (int f = 0; f < GATE_FT; ++f) acc[r][f] = warp_sum(acc[r][f]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < MLP_RPW; ++r) {
+        if (o0 + r < out_dim) {
+          const float bv = __ldg(bg + o0 + r);
+#pragma unroll
+          for (int f = 0; f < GATE_FT; ++f) {
+            float v = acc[r][f] + bv;
+            y[f * y_ld + o0 + r] = relu ? fmaxf(v, 0.f) : v;
+          }
+        }
       }
     }
   }
