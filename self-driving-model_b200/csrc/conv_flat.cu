@@ -49,6 +49,7 @@ struct Params {
   __nv_bfloat16* y;
 };
 
+template <int N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ Params p) {
@@ -60,9 +61,16 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int g = blockIdx.y;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * 128u;
-  const uint32_t w_tile_bytes = (uint32_t)p.N * 128u;
+  constexpr uint32_t w_tile_bytes = (uint32_t)N * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_w = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+  // folded-BN scale/bias of this expert group, staged once per CTA
+  __shared__ __align__(16) float s_scale[128];
+  __shared__ __align__(16) float s_bias[128];
+  for (int i = threadIdx.x; i < N; i += NUM_THREADS) {
+    s_scale[i] = __ldg(p.scale + blockIdx.y * N + i);
+    s_bias[i] = __ldg(p.bias + blockIdx.y * N + i);
+  }
   const uint32_t bar_afull = smem_u32(&bars[0]);
   const uint32_t bar_aempty = smem_u32(&bars[MAX_A_STAGES]);
   const uint32_t bar_wfull = smem_u32(&bars[2 * MAX_A_STAGES]);
@@ -93,7 +101,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
   const int group_row0 = g * p.group_positions;  // first flattened position of this expert group
-  const int wrow0 = g * p.N;                      // first weight row of this expert group
+  const int wrow0 = g * N;                        // first weight row of this expert group
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -131,7 +139,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    const uint32_t idesc = make_idesc(p.N);
+    const uint32_t idesc = make_idesc(N);
     int as = 0, ws = 0, it = 0;
     uint32_t aphase = 0, wphase = 0;
     if (p.w_resident) {
@@ -157,7 +165,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_after();
             w_addr = smem_w + (uint32_t)ws * w_tile_bytes;
           }
-          if (lane == 0) {
+          {
             const int kh = tap / 3, kw = tap - kh * 3;
             const uint32_t a_tap = a_base + (uint32_t)(kh * p.Wp + kw) * 128u;  // row shift of this tap
             const uint64_t b_desc = make_sw128_desc(w_addr);
@@ -166,21 +174,17 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint64_t a_desc = make_sw128_desc(a_tap + (uint32_t)half * (BLOCK_M * 128u));
 #pragma unroll
               for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                umma_bf16(d_tmem + (uint32_t)(half * p.N), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                umma_bf16(d_tmem + (uint32_t)(half * N), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
                           (uint32_t)((chunk | tap | kk) != 0));
             }
             if (!p.w_resident) umma_commit(bar_wempty + 8 * ws);
           }
-          __syncwarp();
           if (!p.w_resident) {
             if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
           }
         }
-        if (lane == 0) {
-          umma_commit(bar_aempty + 8 * as);
-          if (chunk == p.chunks - 1) umma_commit(bar_tfull + 8 * acc);
-        }
-        __syncwarp();
+        umma_commit(bar_aempty + 8 * as);
+        if (chunk == p.chunks - 1) umma_commit(bar_tfull + 8 * acc);
         if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
       }
     }
@@ -188,54 +192,81 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ============================ epilogue ================================
     const int lg = warp & 3;
     const int img = p.Hp * p.Wp;
+    constexpr int NV = N / 8;  // 16-byte pieces per output row
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tfull + 8 * acc, tphase);
-      tcgen05_fence_after();
+      // geometry of this thread's two rows; pull the residual rows towards L2 while the MMAs of
+      // this tile are still running
+      bool valid[2], interior[2];
+      int64_t off[2];
+#pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int q = t * TILE_P + half * BLOCK_M + lg * 32 + lane;  // position inside the group
-        const bool valid = q < p.group_positions;
+        valid[half] = q < p.group_positions;
         const int rem = q % img;
         const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
-        const bool interior = valid && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-        const int64_t off = ((int64_t)group_row0 + q) * p.N;
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * p.N);
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
+        interior[half] = valid[half] && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
+        off[half] = ((int64_t)group_row0 + q) * N;
+        if (p.residual && interior[half]) {
+#pragma unroll
+          for (int l = 0; l < N * 2 / 128; ++l)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off[half] + l * 64));
+        }
+      }
+      mbar_wait(bar_tfull + 8 * acc, tphase);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        // residual row of this half into registers before touching TMEM (loads overlap tcgen05.ld)
+        uint4 rr[NV];
+        const bool use_res = p.residual != nullptr && interior[half];
+        if (use_res) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(p.residual + off[half]) + v);
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * N);
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t a[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a);
           tmem_ld_wait();
-          if (valid) {
-          const float* sc = p.scale + wrow0 + c0;
-          const float* bs = p.bias + wrow0 + c0;
+          if (valid[half]) {
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+            const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
-            if (interior) {
-              float f[8];
+            for (int v = 0; v < 4; ++v) {
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
+              if (interior[half]) {
+                const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+                float f[8];
+                f[0] = fmaf(__uint_as_float(a[v * 8 + 0]), s0.x, b0.x);
+                f[1] = fmaf(__uint_as_float(a[v * 8 + 1]), s0.y, b0.y);
+                f[2] = fmaf(__uint_as_float(a[v * 8 + 2]), s0.z, b0.z);
+                f[3] = fmaf(__uint_as_float(a[v * 8 + 3]), s0.w, b0.w);
+                f[4] = fmaf(__uint_as_float(a[v * 8 + 4]), s1.x, b1.x);
+                f[5] = fmaf(__uint_as_float(a[v * 8 + 5]), s1.y, b1.y);
+                f[6] = fmaf(__uint_as_float(a[v * 8 + 6]), s1.z, b1.z);
+                f[7] = fmaf(__uint_as_float(a[v * 8 + 7]), s1.w, b1.w);
+                if (use_res) {
+                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[c0 / 8 + v]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[j] = fmaf(__uint_as_float(a[v * 8 + j]), __ldg(sc + v * 8 + j), __ldg(bs + v * 8 + j));
-              if (p.residual) {
-                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 rf = __bfloat1622float2(r2[j]);
-                  f[2 * j] += rf.x;
-                  f[2 * j + 1] += rf.y;
+                  for (int j = 0; j < 4; ++j) {
+                    float2 rf = __bfloat1622float2(r2[j]);
+                    f[2 * j] += rf.x;
+                    f[2 * j + 1] += rf.y;
+                  }
                 }
-              }
-              if (p.relu) {
+                if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
               }
-              o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(p.y + off[half] + c0 + v * 8) = o;
             }
-            *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = o;
-          }
           }
         }
       }
@@ -254,14 +285,16 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 static bool supported(int H, int W, int C, int N) {
-  return C % 64 == 0 && N % 32 == 0 && N <= 128 && W + 2 <= 120 && H >= 1;
+  return C % 64 == 0 && (N == 64 || N == 128) && W + 2 <= 120 && H >= 1;
 }
 
 }  // namespace flat
 
 int amoe_conv_flat_init(amoe_ctx* ctx) {
   (void)ctx;
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET + 1024));
   return 0;
 }
@@ -332,7 +365,10 @@ int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const flo
   }
   const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
   const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + 1024;
-  conv3x3_flat_kernel<<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+  if (Cout == 64)
+    conv3x3_flat_kernel<64><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+  else
+    conv3x3_flat_kernel<128><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

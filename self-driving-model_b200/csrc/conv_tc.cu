@@ -47,6 +47,7 @@ struct Params {
   int split_c;                      // output sub-tensor width: channel ch of group g goes to tensor
                                     // (g*Cout/split_c + ch/split_c), channel ch%split_c (== Cout normally)
   int total_tiles;
+  int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
   const float* scale;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -82,6 +83,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + (uint32_t)p.stages * A_STAGE_BYTES;
+  // folded-BN scale/bias of every group, staged once per CTA (the epilogue reads them with LDS.128)
+  float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
+                                            (size_t)p.stages * (A_STAGE_BYTES + b_stage_bytes));
+  float* s_bias = s_scale + p.n_ch_total;
+  for (int i = threadIdx.x; i < p.n_ch_total; i += NUM_THREADS) {
+    s_scale[i] = __ldg(p.scale + i);
+    s_bias[i] = __ldg(p.bias + i);
+  }
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_STAGES]);
@@ -150,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes have landed
         tcgen05_fence_after();
-        if (lane == 0) {
+        {
           const uint64_t a_desc = make_sw128_desc(smem_a + stage * A_STAGE_BYTES);
           const uint64_t b_desc = make_sw128_desc(smem_b + stage * b_stage_bytes);
 #pragma unroll
@@ -162,7 +171,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(bar_empty + 8 * stage);                     // frees the smem slot
           if (k == k_iters - 1) umma_commit(bar_tfull + 8 * as);  // accumulator ready
         }
-        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -187,28 +195,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t pix = ((int64_t)nl * Hop + oh + p.out_pad) * Wop + ow + p.out_pad;
       const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
       const int nsplit = p.Cout / p.split_c;
+      const bool use_res = p.residual != nullptr && valid;
+      if (use_res) {
+        // pull this row of the residual towards L2 while the MMAs of the tile are still running
+        // (a residual implies split_c == Cout: the row's block_n channels are contiguous)
+        const __nv_bfloat16* rrow = p.residual + (int64_t)tc_.g * sub_stride + pix * p.split_c + chn;
+        for (int l = 0; l < p.block_n * 2; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + l / 2));
+      }
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
-        tmem_ld_wait();
         // a 32-channel chunk never straddles output sub-tensors (split_c % 32 == 0)
         const int ch = chn + c0;
         const int64_t off = (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pix * p.split_c + ch % p.split_c - c0;
+        uint4 rr[4];
+        if (use_res) {  // issue the residual loads before the TMEM load so the latencies overlap
+#pragma unroll
+          for (int v = 0; v < 4; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
+        }
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
         if (valid) {
-          const float* sc = p.scale + ch0 + c0;
-          const float* bs = p.bias + ch0 + c0;
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch0 + c0);
+          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + ch0 + c0);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
+            const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = fmaf(__uint_as_float(acc[v * 8 + j]), __ldg(sc + v * 8 + j), __ldg(bs + v * 8 + j));
-            if (p.residual) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+            f[0] = fmaf(__uint_as_float(acc[v * 8 + 0]), s0.x, b0.x);
+            f[1] = fmaf(__uint_as_float(acc[v * 8 + 1]), s0.y, b0.y);
+            f[2] = fmaf(__uint_as_float(acc[v * 8 + 2]), s0.z, b0.z);
+            f[3] = fmaf(__uint_as_float(acc[v * 8 + 3]), s0.w, b0.w);
+            f[4] = fmaf(__uint_as_float(acc[v * 8 + 4]), s1.x, b1.x);
+            f[5] = fmaf(__uint_as_float(acc[v * 8 + 5]), s1.y, b1.y);
+            f[6] = fmaf(__uint_as_float(acc[v * 8 + 6]), s1.z, b1.z);
+            f[7] = fmaf(__uint_as_float(acc[v * 8 + 7]), s1.w, b1.w);
+            if (use_res) {
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[v]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float2 rf = __bfloat1622float2(r2[j]);
@@ -262,7 +287,7 @@ static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
 int amoe_conv_tc_init(amoe_ctx* ctx) {
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc::SMEM_BUDGET + 1024));
+                                       tc::SMEM_BUDGET + 1024 + 16 * 1024));
   return 0;
 }
 
@@ -308,6 +333,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   AMOE_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
   p.total_tiles = (int)total;
   p.scale = scale; p.bias = bias;
+  p.n_ch_total = G * Cout;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
   for (int t = 0; t < num_taps; ++t) p.taps[t] = taps[t];
@@ -336,7 +362,8 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
   const int grid = std::min(p.total_tiles, ctx->sm_count);
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)2 * p.n_ch_total * sizeof(float);
+  AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 16 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
   conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, p);
   AMOE_LAUNCH_OK(ctx);
   return 0;

@@ -70,21 +70,35 @@ __device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t cols) 
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
+// Executed by ALL lanes of the (converged) MMA warp with warp-uniform operands; one elected lane
+// issues the instruction.  Keeping the call site free of per-lane branches lets ptxas keep the
+// descriptors in uniform registers (a `if (lane == 0)` region makes it wrap every UTCHMMA in an
+// ELECT/R2UR waterfall loop that costs more cycles than an N=64 MMA takes to execute).
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, q;\n"
+      ".reg .b32 t;\n"
+      "elect.sync t|q, 0xffffffff;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
+// mbarrier arrives when all tcgen05.mma issued so far by the elected lane have completed
+// (same calling convention as umma_bf16: all lanes call, the elected lane issues)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .b32 t;\n"
+      "elect.sync t|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

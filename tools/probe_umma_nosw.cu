@@ -38,18 +38,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 }
 
 constexpr int NB = 64;        // N
-constexpr int NDATA = 2048;   // flat A data elements
+constexpr int NDATA = 2048;   // flat A data elements (Toeplitz variants)
+constexpr int ABYTES = 128 * 64 * 2;  // A region (canonical variants need 16 KB)
 
-__global__ void __launch_bounds__(128, 1) probe(float* out) {
+__global__ void __launch_bounds__(128, 1) probe(float* out, int variant) {
   extern __shared__ uint8_t raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t holder;
   const uint32_t base = (smem_u32(raw) + 127u) & ~127u;
   uint8_t* gen = raw + (base - smem_u32(raw));
   __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(gen);                  // flat data
-  __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(gen + NDATA * 2);     // [k/8][n][8]
+  __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(gen + ABYTES);        // [k/8][n][8]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < NDATA; i += 128) A[i] = __float2bfloat16((float)(i % 61));
+  if (variant < 2) {
+    // canonical no-swizzle A: [k/8][m][8]  with A[m][k] = (8*m + k) % 61 (same logical matrix as the Toeplitz view)
+    for (int i = tid; i < 128 * 64; i += 128) {
+      int m = i / 64, k = i % 64;
+      A[((k >> 3) * 128 + m) * 8 + (k & 7)] = __float2bfloat16((float)((8 * m + k) % 61));
+    }
+  } else {
+    for (int i = tid; i < NDATA; i += 128) A[i] = __float2bfloat16((float)(i % 61));
+  }
   for (int i = tid; i < 64 * NB; i += 128) {
     int k = i / NB, n = i % NB;  // identity: B[n][k] = (n == k)
     Bm[((k >> 3) * NB + n) * 8 + (k & 7)] = __float2bfloat16(n == k ? 1.f : 0.f);
@@ -69,17 +78,23 @@ __global__ void __launch_bounds__(128, 1) probe(float* out) {
   const uint32_t tmem = holder;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t phase = 0;
-  for (int variant = 0; variant < 2; ++variant) {
+  {
     if (tid == 0) {
-      const uint32_t a_addr = base, b_addr = base + NDATA * 2;
+      const uint32_t a_addr = base, b_addr = base + ABYTES;
       for (int ks = 0; ks < 4; ++ks) {  // K = 64 = 4 steps of 16
         uint64_t ad, bd;
-        if (variant == 0) {
-          ad = make_desc(a_addr + ks * 32, /*lbo*/ 16, /*sbo*/ 128);
-          bd = make_desc(b_addr + ks * 2 * NB * 16, /*lbo*/ NB * 16, /*sbo*/ 128);
-        } else {
-          ad = make_desc(a_addr + ks * 32, /*lbo*/ 128, /*sbo*/ 16);
-          bd = make_desc(b_addr + ks * 2 * NB * 16, /*lbo*/ 128, /*sbo*/ NB * 16);
+        if (variant == 0) {         // canonical A, roles: LBO = K-chunk stride, SBO = 8-row-group stride
+          ad = make_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+          bd = make_desc(b_addr + ks * 2 * NB * 16, NB * 16, 128);
+        } else if (variant == 1) {  // canonical A, roles swapped
+          ad = make_desc(a_addr + ks * 2 * 128 * 16, 128, 128 * 16);
+          bd = make_desc(b_addr + ks * 2 * NB * 16, 128, NB * 16);
+        } else if (variant == 2) {  // Toeplitz A (overlapping rows), roles as variant 0
+          ad = make_desc(a_addr + ks * 32, 16, 128);
+          bd = make_desc(b_addr + ks * 2 * NB * 16, NB * 16, 128);
+        } else {                    // Toeplitz A, roles as variant 1
+          ad = make_desc(a_addr + ks * 32, 128, 16);
+          bd = make_desc(b_addr + ks * 2 * NB * 16, 128, NB * 16);
         }
         umma_bf16(tmem, ad, bd, idesc, ks != 0);
       }
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) probe(float* out) {
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float* o = out + ((size_t)variant * 128 + warp * 32 + lane) * NB + c0;
+      float* o = out + ((size_t)(warp * 32 + lane)) * NB + c0;
       for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -110,30 +125,26 @@ __global__ void __launch_bounds__(128, 1) probe(float* out) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
 }
 
-int main() {
-  size_t n = (size_t)2 * 128 * NB;
+int main(int argc, char** argv) {
+  int variant = argc > 1 ? atoi(argv[1]) : 0;
+  size_t n = (size_t)128 * NB;
   float* d;
   cudaMalloc(&d, n * sizeof(float));
   cudaMemset(d, 0xff, n * sizeof(float));
-  size_t smem = NDATA * 2 + 64 * NB * 2 + 256;
-  probe<<<1, 128, smem>>>(d);
+  size_t smem = ABYTES + 64 * NB * 2 + 256;
+  probe<<<1, 128, smem>>>(d, variant);
   cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+  if (e != cudaSuccess) { printf("variant %d: CUDA error: %s\n", variant, cudaGetErrorString(e)); return 1; }
   float* h = (float*)malloc(n * sizeof(float));
   cudaMemcpy(h, d, n * sizeof(float), cudaMemcpyDeviceToHost);
-  for (int v = 0; v < 2; ++v) {
-    int bad = 0;
-    for (int m = 0; m < 128; ++m)
-      for (int c = 0; c < NB; ++c) {
-        float want = (float)((8 * m + c) % 61);
-        if (h[((size_t)v * 128 + m) * NB + c] != want) bad++;
-      }
-    printf("variant %d (%s): %s bad=%d  D[0][0..3]=%g %g %g %g  D[1][0..1]=%g %g  D[9][0]=%g D[0][8]=%g D[0][16]=%g\n", v,
-           v == 0 ? "A lbo=16 sbo=128, B lbo=N*16 sbo=128" : "lbo/sbo swapped", bad ? "MISMATCH" : "ok", bad,
-           h[(size_t)v * 128 * NB + 0], h[(size_t)v * 128 * NB + 1], h[(size_t)v * 128 * NB + 2], h[(size_t)v * 128 * NB + 3],
-           h[((size_t)v * 128 + 1) * NB + 0], h[((size_t)v * 128 + 1) * NB + 1], h[((size_t)v * 128 + 9) * NB + 0],
-           h[(size_t)v * 128 * NB + 8], h[(size_t)v * 128 * NB + 16]);
-  }
-  printf("expected: D[m][c] = (8*m + c) %% 61 -> D[0][0..3]=0 1 2 3  D[1][0..1]=8 9  D[9][0]=11 D[0][8]=8 D[0][16]=16\n");
+  int bad = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int c = 0; c < NB; ++c)
+      if (h[(size_t)m * NB + c] != (float)((8 * m + c) % 61)) bad++;
+  const char* names[4] = {"canonical A, LBO=K-chunk stride / SBO=8-row stride", "canonical A, roles swapped",
+                          "Toeplitz A (LBO=16,SBO=128)", "Toeplitz A, roles swapped"};
+  printf("variant %d (%s): %s bad=%d  D[0][0..3]=%g %g %g %g  D[1][0..1]=%g %g  D[9][0]=%g D[0][8]=%g D[0][16]=%g\n", variant,
+         names[variant & 3], bad ? "MISMATCH" : "ok", bad, h[0], h[1], h[2], h[3], h[NB], h[NB + 1], h[9 * NB], h[8], h[16]);
+  printf("expected D[m][c] = (8*m + c) %% 61: 0 1 2 3 | 8 9 | 11 | 8 | 16\n");
   return 0;
 }
