@@ -52,10 +52,22 @@ int64_t amoe_launch_count(amoe_ctx* ctx);
  * NHWC with C padded to Cp (zeros).  dst dtype f32 or bf16. */
 int amoe_image_nchw_to_nhwc(amoe_ctx*, const float* src, void* dst, int B, int C,
                             int H, int W, int Cp, int dst_dtype, void* stream);
-/* Same, into rows of Wpad pixels: `left` zero pixels, the W image pixels, zeros up to Wpad
- * (the physically padded layout amoe_conv2d_rowwin_fwd reads).  dst: [B,H,Wpad,Cp]. */
+/* Same, into a physically padded frame dst: [B,Hpad,Wpad,Cp]: image pixel (h,w) lands at
+ * (top+h, left+w), everything else is zero (the layout amoe_stem_fwd / amoe_conv2d_rowwin_fwd read). */
 int amoe_image_nchw_to_nhwc_padded(amoe_ctx*, const float* src, void* dst, int B, int C, int H,
-                                   int W, int Cp, int left, int Wpad, int dst_dtype, void* stream);
+                                   int W, int Cp, int left, int Wpad, int top, int Hpad,
+                                   int dst_dtype, void* stream);
+/* All first-layer convolutions of the frame (Cin=3, stride 2: the ResNet stems of the experts and
+ * the policy's conv1) as one tensor-core GEMM over the raw image rows (csrc/stem_tc.cu).
+ *   x_pad: [B,H+6,Wpad,4] bf16 from amoe_image_nchw_to_nhwc_padded(left=4, top=3), Wpad >= W+6
+ *   w_img: filters packed as [KH*4][n_total][8] bf16: K index = kh*32 + j*4 + c holds the weight of
+ *          padded pixel 2*ow+j, padded row 2*oh+kh, channel c (zero where no tap)
+ *   scale,bias: [n_total] folded BN;  output pixel (b,oh,ow), channels [32*i, 32*i+32) go to
+ *   dst[i] + ((b*Ho+oh)*Wo+ow)*dst_c[i]  (dst/dst_c: HOST arrays of n_total/32 device pointers /
+ *   channel counts).  H, W even, W/2 <= 128. */
+int amoe_stem_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* scale,
+                  const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
+                  void* const* dst_host, const int* dst_c_host, void* stream);
 /* nn.Conv2d weight [Cout,Cin,KH,KW] fp32 -> packed [Cout][KH][KW][Cin_pad]
  * (dtype f32|bf16, zero-padded channels).  dst points at the first row of this
  * conv inside a (possibly grouped) packed buffer. */

@@ -47,23 +47,145 @@ def image_to_nhwc(img: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tenso
     return out
 
 
-def image_to_nhwc_padded(img: torch.Tensor, cp: int, left: int, wpad: int, dtype: torch.dtype) -> torch.Tensor:
-    """[B,C,H,W] fp32 NCHW -> [B,H,wpad,cp]: `left` zero pixels, the image row, zeros up to wpad."""
+def image_to_nhwc_padded(img: torch.Tensor, cp: int, left: int, wpad: int, dtype: torch.dtype, top: int = 0,
+                         hpad: Optional[int] = None) -> torch.Tensor:
+    """[B,C,H,W] fp32 NCHW -> [B,hpad,wpad,cp]: image pixel (h,w) at (top+h, left+w), zeros elsewhere."""
     if img.dtype != torch.float32:
         img = img.float()
     img = img.contiguous()
     B, Cc, H, W = img.shape
-    out = torch.empty((B, H, wpad, cp), device=img.device, dtype=dtype)
-    check(lib().amoe_image_nchw_to_nhwc_padded(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp, left, wpad,
+    hpad = H if hpad is None else hpad
+    out = torch.empty((B, hpad, wpad, cp), device=img.device, dtype=dtype)
+    check(lib().amoe_image_nchw_to_nhwc_padded(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp, left, wpad, top, hpad,
                                                dtype_code(dtype), stream_ptr(img.device)), "image_nchw_to_nhwc_padded")
     return out
 
 
-def use_rowwin(dtype: torch.dtype) -> bool:
-    """bf16 path: Cin=3 convolutions on the tensor cores (row windows).  AMOE_STEM=simt keeps them on
-    the CUDA-core kernel (debug / A-B switch)."""
+# ---- first-layer GEMM over raw image rows (csrc/stem_tc.cu) ----
+STEM_LEFT, STEM_TOP, STEM_KH = 4, 3, 7
+
+
+def stem_supported(H: int, W: int) -> bool:
+    return H % 2 == 0 and W % 2 == 0 and W // 2 <= 128
+
+
+def stem_wpad(W: int) -> int:
+    return (W + 6 + 7) & ~7
+
+
+def stage_image_stem(img: torch.Tensor) -> torch.Tensor:
+    """Frame in the layout amoe_stem_fwd reads: [B,H+6,Wpad,4] bf16, 3 zero rows top/bottom, 4 zero px left."""
+    H, W = img.shape[2], img.shape[3]
+    return image_to_nhwc_padded(img, 4, STEM_LEFT, stem_wpad(W), torch.bfloat16, top=STEM_TOP, hpad=H + 6)
+
+
+@dataclass
+class PackedStem:
+    """First-layer filters of several convolutions sharing the frame, concatenated on N, in the
+    shared-memory image [KH*4][n_total][8] bf16 of stem_tc.cu."""
+    w: torch.Tensor
+    scale: torch.Tensor
+    bias: torch.Tensor
+    couts: List[int]       # output channels of each convolution (64 per expert stem, 32 for policy conv1)
+    n_total: int
+    relu: bool
+    true_macs_per_px: int  # sum over convs of cout*cin*kh*kw (algorithmic work per output pixel)
+
+
+def pack_stem(convs, bns, device, relu: bool = True) -> PackedStem:
+    """convs: stride-2 nn.Conv2d with Cin<=4 and kernel 7x7/p3 or 5x5/p2 (same output size)."""
+    st, h = stream_ptr(device), ctx(device)
+    couts = [int(c.weight.shape[0]) for c in convs]
+    n_total = sum(couts)
+    assert n_total % 32 == 0 and n_total <= 256 and all(co % 32 == 0 for co in couts)
+    wk = torch.zeros((n_total, STEM_KH, 8, 4), dtype=torch.float32, device=device)   # [n][kh][j][c]
+    scale = torch.empty(n_total, device=device, dtype=torch.float32)
+    bias = torch.empty(n_total, device=device, dtype=torch.float32)
+    n0, macs = 0, 0
+    for conv, bn in zip(convs, bns):
+        cout, cin, kh, kw = conv.weight.shape
+        (sh, sw), (ph, pw) = conv.stride, conv.padding
+        assert sh == 2 and sw == 2 and cin <= 4 and kh <= STEM_KH and STEM_TOP - ph >= 0 and STEM_LEFT - pw >= 0
+        assert kh - ph + STEM_TOP <= STEM_KH and kw - pw + STEM_LEFT <= 8
+        w = conv.weight.detach().to(device=device, dtype=torch.float32)
+        # tap (ih, iw) reads padded row 2*oh + ih - ph + TOP and padded pixel 2*ow + iw - pw + LEFT
+        for ih in range(kh):
+            for iw in range(kw):
+                wk[n0:n0 + cout, ih - ph + STEM_TOP, iw - pw + STEM_LEFT, :cin] = w[:, :, ih, iw]
+        cb = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous() if conv.bias is not None else None
+        if bn is not None:
+            prm = [t.detach().float().contiguous() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+            check(lib().amoe_fold_bn(h, ptr(prm[0]), ptr(prm[1]), ptr(prm[2]), ptr(prm[3]), float(bn.eps), ptr(cb), cout,
+                                     ptr(scale[n0:]), ptr(bias[n0:]), st), "fold_bn")
+        else:
+            check(lib().amoe_fold_bn(h, None, None, None, None, 0.0, ptr(cb), cout, ptr(scale[n0:]), ptr(bias[n0:]), st),
+                  "fold_bn")
+        torch.cuda.current_stream(device).synchronize()
+        n0 += cout
+        macs += cout * cin * kh * kw
+    # [n][k = kh*32 + j*4 + c] -> [k/8][n][8]
+    k_total = STEM_KH * 32
+    img = wk.reshape(n_total, k_total // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    return PackedStem(img, scale, bias, couts, n_total, relu, macs)
+
+
+def stem_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int,
+                 groups: Optional[List[int]] = None) -> List[torch.Tensor]:
+    """groups: how many consecutive packed convolutions share one stacked output tensor, e.g. [3, 1] for
+    three expert stems ([3B,H/2,W/2,64], the grouped activation layout) + policy conv1 ([B,H/2,W/2,32]).
+    Returns one tensor per group."""
+    Ho, Wo = H // 2, W // 2
+    dev = x_pad.device
+    groups = groups or [1] * len(ps.couts)
+    assert sum(groups) == len(ps.couts)
+    stacked, per_conv, i = [], [], 0
+    for n in groups:
+        co = ps.couts[i]
+        assert all(c == co for c in ps.couts[i:i + n])
+        t = torch.empty((n * B, Ho, Wo, co), device=dev, dtype=torch.bfloat16)
+        stacked.append(t)
+        per_conv += [t[j * B:(j + 1) * B] for j in range(n)]
+        i += n
+    _stem_launch(ps, x_pad, B, H, W, per_conv)
+    return stacked
+
+
+def _stem_launch(ps: PackedStem, x_pad, B, H, W, outs):
+    n_chunks = ps.n_total // 32
+    dst = (C.c_void_p * n_chunks)()
+    dst_c = (C.c_int * n_chunks)()
+    i = 0
+    for t, co in zip(outs, ps.couts):
+        for c0 in range(0, co, 32):
+            dst[i] = t.data_ptr() + c0 * 2
+            dst_c[i] = co
+            i += 1
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().amoe_stem_fwd(ctx(x_pad.device), ptr(x_pad), ptr(ps.w), ptr(ps.scale), ptr(ps.bias), B, H, W,
+                              x_pad.shape[2], STEM_KH, ps.n_total, int(ps.relu), dst, dst_c, stream_ptr(x_pad.device)),
+          "stem_fwd")
+    if prof is not None:
+        ev1.record()
+        prof.append(("conv_tc", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
+    return outs
+
+
+def stem_mode(dtype: torch.dtype) -> str:
+    """How the Cin=3 first-layer convolutions run: 'tc' (bf16 default: one GEMM over raw image rows,
+    stem_tc.cu), 'rowwin' (bf16: expanded row windows through conv_tc.cu) or 'simt' (CUDA cores; the only
+    choice in fp32 mode).  AMOE_STEM overrides the bf16 default (debug / A-B switch)."""
     import os
-    return dtype == torch.bfloat16 and os.environ.get("AMOE_STEM", "tc") != "simt"
+    if dtype != torch.bfloat16:
+        return "simt"
+    m = os.environ.get("AMOE_STEM", "tc")
+    return m if m in ("tc", "rowwin", "simt") else "tc"
+
+
+def use_rowwin(dtype: torch.dtype) -> bool:
+    return stem_mode(dtype) == "rowwin"
 
 
 ROWWIN_LEFT = 4     # zero pixels stored left of every image row

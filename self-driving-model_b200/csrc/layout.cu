@@ -33,18 +33,20 @@ __global__ void image_nchw_to_nhwc4_bf16_kernel(const float* __restrict__ src,
   dst[i] = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
 }
 
-// physically padded rows: dst[b][h][wp][c], wp in [0,Wpad): image column wp-left or zero
+// physically padded frame: dst[b][hp][wp][c], hp in [0,Hpad), wp in [0,Wpad): image pixel
+// (hp-top, wp-left) or zero
 template <typename T>
 __global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, T* __restrict__ dst, int C,
-                                                 int H, int W, int Cp, int left, int Wpad, int64_t total) {
+                                                 int H, int W, int Cp, int left, int Wpad, int top, int Hpad,
+                                                 int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int wp = (int)(i % Wpad);
   int64_t r = i / Wpad;
-  int h = (int)(r % H);
-  int64_t b = r / H;
-  int w = wp - left;
-  const bool in = w >= 0 && w < W;
+  int hp = (int)(r % Hpad);
+  int64_t b = r / Hpad;
+  int w = wp - left, h = hp - top;
+  const bool in = w >= 0 && w < W && h >= 0 && h < H;
   const float* s = src + (b * C * H + h) * (int64_t)W + w;
   T* d = dst + i * Cp;
   for (int c = 0; c < Cp; ++c) {
@@ -113,17 +115,18 @@ int amoe_image_nchw_to_nhwc(amoe_ctx* ctx, const float* src, void* dst, int B, i
 }
 
 int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
-                                   int Cp, int left, int Wpad, int dst_dtype, void* stream) {
+                                   int Cp, int left, int Wpad, int top, int Hpad, int dst_dtype, void* stream) {
   AMOE_REQUIRE(ctx && src && dst, "amoe_image_nchw_to_nhwc_padded: NULL argument");
-  AMOE_REQUIRE(Cp >= C && C >= 1 && left >= 0 && Wpad >= left + W, "amoe_image_nchw_to_nhwc_padded: bad geometry");
-  int64_t total = (int64_t)B * H * Wpad;
+  AMOE_REQUIRE(Cp >= C && C >= 1 && left >= 0 && Wpad >= left + W && top >= 0 && Hpad >= top + H,
+               "amoe_image_nchw_to_nhwc_padded: bad geometry");
+  int64_t total = (int64_t)B * Hpad * Wpad;
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (dst_dtype == AMOE_BF16)
-    image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, total);
+    image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
   else if (dst_dtype == AMOE_F32)
-    image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, total);
+    image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
   else
     AMOE_REQUIRE(false, "amoe_image_nchw_to_nhwc_padded: bad dtype %d", dst_dtype);
   AMOE_LAUNCH_OK(ctx);

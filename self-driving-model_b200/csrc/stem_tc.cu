@@ -1,0 +1,259 @@
+// First-layer convolutions (Cin = 3: ResNet stem 7x7/s2/p3 of every expert + policy conv1
+// 5x5/s2/p2) as ONE tensor-core GEMM that reads the raw image rows - no im2col copy anywhere.
+//
+// The frame is staged as [B][H+6][Wpad][4] bf16 (3 zero rows on top/bottom, 4 zero pixels left,
+// zeros right).  For output pixel (oh, ow) and filter row kh the needed input is the window of 8
+// pixels x 4 channels = 32 bf16 starting at padded pixel 2*ow of padded row 2*oh+kh, i.e.
+//     A[ow][k] = row[8*ow + k]        (byte address = row_base + 16*ow + 2*k)
+// - consecutive output pixels read OVERLAPPING windows.  A K-major SWIZZLE_NONE UMMA operand is
+// made of 8x16B core matrices with a programmable stride between 8-row groups (SBO) and between
+// the two 16-byte K chunks of one MMA (LBO); SBO = 128 B and LBO = 16 B make the tensor core read
+// exactly this Toeplitz matrix straight from the image row in shared memory (verified on B200 by
+// tools/probe_umma_nosw.cu).  So a tile (one output row, 128 pixels) needs 7 image rows = 15 KB of
+// shared memory instead of 7 x 16 KB of expanded windows, and K is 7*32 = 224 (147 useful).
+//
+// B operand: all filters of all convolutions sharing the frame, concatenated on N (3 experts x 64
+// + policy 32 = 224), resident in shared memory for the whole kernel in the no-swizzle layout
+// [K/8][N][8] (LBO = N*16 B, SBO = 128 B); filter taps sit at window position kw+1 (stem) /
+// kw+2, row kh+1 (policy), zeros elsewhere.
+//
+// Warp roles as in conv_tc.cu: warp 0 producer (bulk copies of 7 contiguous image rows), warp 1
+// MMA issuer (14 tcgen05.mma of N=n_total per tile), warps 2-5 epilogue (BN scale/bias + ReLU,
+// scatter of 32-channel chunks to their destination tensors).
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace stem {
+
+using namespace tc;
+
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+constexpr int A_STAGES = 4;
+constexpr int MAX_CHUNKS = 8;
+constexpr int WIN_K = 32;  // bf16 per filter row window (8 pixels x 4 channels)
+
+struct Params {
+  int B, Ho, Wo, Hpad, KH;
+  int row_bytes;       // Wpad * 8
+  int a_stage_bytes;   // KH * row_bytes + slack for the garbage rows ow >= Wo, multiple of 128
+  int n_total;         // multiple of 32, <= 256
+  int w_bytes;         // KH*4 * n_total * 16
+  int total_tiles;     // B * Ho
+  int relu;
+  const uint8_t* x;
+  const uint8_t* w;
+  const float* scale;
+  const float* bias;
+  __nv_bfloat16* dst[MAX_CHUNKS];  // per 32-channel chunk: destination (sub-tensor + channel offset applied)
+  int dst_c[MAX_CHUNKS];           // channels per pixel of that destination
+};
+
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout type 0 = SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) stem_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 5];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_scale[256];
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t smem_w = smem_base;
+  const uint32_t smem_a = smem_base + (uint32_t)((p.w_bytes + 127) & ~127);
+  const uint32_t bar_afull = smem_u32(&bars[0]);
+  const uint32_t bar_aempty = smem_u32(&bars[A_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * A_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * A_STAGES + 2]);
+  const uint32_t bar_w = smem_u32(&bars[2 * A_STAGES + 4]);
+
+  for (int i = threadIdx.x; i < p.n_total; i += NUM_THREADS) {
+    s_scale[i] = __ldg(p.scale + i);
+    s_bias[i] = __ldg(p.bias + i);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const uint32_t tile_bytes = (uint32_t)(p.KH * p.row_bytes);
+
+  if (warp == 0) {
+    // ============================ producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)p.w_bytes);
+      // weights: a few bulk copies (each <= 32 KB keeps the request size modest)
+      for (int o = 0; o < p.w_bytes; o += 32768)
+        bulk_g2s(smem_w + (uint32_t)o, p.w + o, (uint32_t)std::min(32768, p.w_bytes - o), bar_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int b = t / p.Ho, oh = t - b * p.Ho;
+        mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
+        mbar_arrive_expect_tx(bar_afull + 8 * stage, tile_bytes);
+        // KH contiguous padded rows starting at row 2*oh of image b
+        bulk_g2s(smem_a + (uint32_t)stage * p.a_stage_bytes, p.x + ((int64_t)b * p.Hpad + 2 * oh) * p.row_bytes,
+                 tile_bytes, bar_afull + 8 * stage);
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==========================
+    const uint32_t idesc = make_idesc(p.n_total);
+    const uint32_t lbo_b = (uint32_t)p.n_total * 16u;
+    mbar_wait(bar_w, 0);
+    tcgen05_fence_after();
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
+      mbar_wait(bar_afull + 8 * stage, phase);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+      const uint32_t a_base = smem_a + (uint32_t)stage * p.a_stage_bytes;
+      for (int kh = 0; kh < p.KH; ++kh) {
+#pragma unroll
+        for (int ks = 0; ks < WIN_K / UMMA_K; ++ks) {
+          const uint64_t a_desc = make_nosw_desc(a_base + (uint32_t)(kh * p.row_bytes + ks * 32), 16u, 128u);
+          const uint64_t b_desc = make_nosw_desc(smem_w + (uint32_t)(kh * 4 + ks * 2) * lbo_b, lbo_b, 128u);
+          umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)((kh | ks) != 0));
+        }
+      }
+      umma_commit(bar_aempty + 8 * stage);
+      umma_commit(bar_tfull + 8 * acc);
+      if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int lg = warp & 3;
+    const int ow = lg * 32 + lane;
+    const bool valid = ow < p.Wo;
+    const int n_chunks = p.n_total >> 5;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const int64_t pix = (int64_t)t * p.Wo + ow;  // (b*Ho + oh)*Wo + ow
+      mbar_wait(bar_tfull + 8 * acc, tphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+        tmem_ld_wait();
+        if (valid) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+          __nv_bfloat16* o = p.dst[c] + pix * p.dst_c[c];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+            float f[8];
+            f[0] = fmaf(__uint_as_float(a[v * 8 + 0]), s0.x, b0.x);
+            f[1] = fmaf(__uint_as_float(a[v * 8 + 1]), s0.y, b0.y);
+            f[2] = fmaf(__uint_as_float(a[v * 8 + 2]), s0.z, b0.z);
+            f[3] = fmaf(__uint_as_float(a[v * 8 + 3]), s0.w, b0.w);
+            f[4] = fmaf(__uint_as_float(a[v * 8 + 4]), s1.x, b1.x);
+            f[5] = fmaf(__uint_as_float(a[v * 8 + 5]), s1.y, b1.y);
+            f[6] = fmaf(__uint_as_float(a[v * 8 + 6]), s1.z, b1.z);
+            f[7] = fmaf(__uint_as_float(a[v * 8 + 7]), s1.w, b1.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(o + v * 8) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace stem
+
+int amoe_stem_init(amoe_ctx* ctx) {
+  (void)ctx;
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  return 0;
+}
+
+extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img, const float* scale,
+                             const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
+                             void* const* dst_host, const int* dst_c_host, void* stream) {
+  using namespace stem;
+  AMOE_REQUIRE(ctx && x_pad && w_img && scale && bias && dst_host && dst_c_host, "amoe_stem_fwd: NULL argument");
+  AMOE_REQUIRE(H % 2 == 0 && W % 2 == 0, "amoe_stem_fwd: H and W must be even (got %dx%d)", H, W);
+  AMOE_REQUIRE(n_total % 32 == 0 && n_total >= 32 && n_total <= 256, "amoe_stem_fwd: n_total=%d must be a multiple of 32 in [32,256]", n_total);
+  AMOE_REQUIRE(KH >= 1 && KH <= 7, "amoe_stem_fwd: KH=%d out of range", KH);
+  const int Ho = H / 2, Wo = W / 2;
+  AMOE_REQUIRE(Wo <= 128, "amoe_stem_fwd: output rows wider than 128 pixels are not tiled yet (Wo=%d)", Wo);
+  AMOE_REQUIRE(Wpad >= W + 6 && Wpad % 2 == 0, "amoe_stem_fwd: Wpad=%d too small/odd for W=%d", Wpad, W);
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_img) & 15) == 0,
+               "amoe_stem_fwd: pointers must be 16-byte aligned");
+  Params p;
+  p.B = B; p.Ho = Ho; p.Wo = Wo; p.Hpad = H + 6; p.KH = KH;
+  p.row_bytes = Wpad * 8;
+  // garbage rows (ow >= Wo) read up to byte 16*127 + 64 past the start of the last filter row
+  p.a_stage_bytes = (KH * p.row_bytes + 16 * 128 + 64 + 127) & ~127;
+  p.n_total = n_total;
+  p.w_bytes = KH * 4 * n_total * 16;
+  p.total_tiles = B * Ho;
+  p.relu = relu;
+  p.x = (const uint8_t*)x_pad;
+  p.w = (const uint8_t*)w_img;
+  p.scale = scale; p.bias = bias;
+  for (int c = 0; c < MAX_CHUNKS; ++c) { p.dst[c] = nullptr; p.dst_c[c] = 0; }
+  for (int c = 0; c < n_total / 32; ++c) {
+    AMOE_REQUIRE(dst_host[c] != nullptr && dst_c_host[c] % 8 == 0 && (reinterpret_cast<uintptr_t>(dst_host[c]) & 15) == 0,
+                 "amoe_stem_fwd: bad destination for chunk %d", c);
+    p.dst[c] = (__nv_bfloat16*)dst_host[c];
+    p.dst_c[c] = dst_c_host[c];
+  }
+  if (p.total_tiles == 0) return 0;
+  const size_t smem = ((size_t)p.w_bytes + 127) / 128 * 128 + (size_t)A_STAGES * p.a_stage_bytes + 256;
+  AMOE_REQUIRE(smem <= 220 * 1024, "amoe_stem_fwd: shared memory budget exceeded (%zu bytes)", smem);
+  const int grid = std::min(p.total_tiles, ctx->sm_count);
+  stem_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}

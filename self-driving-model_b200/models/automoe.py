@@ -127,6 +127,19 @@ class AutoMoE(nn.Module):
             self._gate_flat[key] = g
         return g[1]
 
+    def _fused_stem(self, device):
+        """PackedStem of [expert stems..., policy conv1] (cached; re-packed when any of them changes)."""
+        mods = [e.backbone[0] for e in self.experts] + [e.backbone[1] for e in self.experts] + \
+               [self.policy_head.backbone.net[0], self.policy_head.backbone.net[1]]
+        stamp = params_stamp(mods)
+        c = self._gate_flat.get(("stem", device.index))
+        if c is None or c[0] != stamp:
+            convs = [e.backbone[0] for e in self.experts] + [self.policy_head.backbone.net[0]]
+            bns = [e.backbone[1] for e in self.experts] + [self.policy_head.backbone.net[1]]
+            c = (stamp, _ops.pack_stem(convs, bns, device, relu=True))
+            self._gate_flat[("stem", device.index)] = c
+        return c[1]
+
     def _extract_context_features(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         state = self._vehicle_state(batch)
         return self.context_extractor(state[:, 0:1], state[:, 1:2], state[:, 2:3], state[:, 3:4])
@@ -146,14 +159,21 @@ class AutoMoE(nn.Module):
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
         x_nhwc = stage_image(image, dtype)
+        stem_out = pol1 = None
+        if _ops.stem_mode(dtype) == "tc":
+            # experts' stems + policy conv1 read the same frame: one GEMM with N = 3*64 + 32
+            fs = self._fused_stem(image.device)
+            stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, image.shape[0], image.shape[2], image.shape[3],
+                                               groups=[len(self.experts), 1])
 
-        expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc)
+        expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
+                                          stem_out=stem_out)
 
         gn = self.gating_network
         g = _ops.gate(state, aux['pooled'], self._gate_params(image.device, aux['n_ch']), aux['n_ch'],
                       self.context_extractor.context_dim, gn.hidden_dim, gn.temperature)
 
-        policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype)
+        policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)
         speed_seq = policy_output.get('speed')
         speed_out = None
         if speed_seq is not None and speed_seq.dim() == 2:

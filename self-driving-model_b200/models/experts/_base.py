@@ -46,7 +46,8 @@ def _check_eval(experts):
                 "train-mode (batch-statistics) BatchNorm is not implemented yet - call .eval() on the experts")
 
 
-def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None):
+def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None,
+                stem_out=None):
     """Run G experts on the same image batch in grouped launches.
 
     Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
@@ -62,7 +63,7 @@ def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.
         pack = pack_trunks(experts, [e.head_module() for e in experts], dtype, image.device)
         cache[key] = pack
     B, _, H, W = image.shape
-    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc)
+    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out)
     outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
     # mean over the up-sampled map == mean over the low-res map only for integer scale factors
     off = 0

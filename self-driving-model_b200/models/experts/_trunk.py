@@ -108,7 +108,10 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
     """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
     G = len(experts)
     bbs = [e.backbone for e in experts]
-    if _ops.use_rowwin(dtype):   # Cin=3 stem on the tensor cores through row windows, 3 experts in one GEMM
+    mode = _ops.stem_mode(dtype)
+    if mode == "tc":       # Cin=3 stems of all experts as one GEMM over the raw image rows
+        stem = _ops.pack_stem([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
+    elif mode == "rowwin":
         stem = _ops.pack_rowwin([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
     else:
         stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
@@ -132,15 +135,22 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
 
 
 def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """NCHW fp32 frame -> the NHWC layout the first convolutions read: bf16 rows physically padded
-    for the row-window tensor-core stem, or plain [B,H,W,4] fp32 for the fp32 path."""
-    if _ops.use_rowwin(dtype):
-        W = image.shape[3]
+    """NCHW fp32 frame -> the NHWC layout the first convolutions read (see _ops.stem_mode): the
+    physically padded bf16 frame of the tensor-core stem, padded rows for the row-window variant, or
+    plain [B,H,W,4] for the CUDA-core kernel."""
+    mode = _ops.stem_mode(dtype)
+    H, W = image.shape[2], image.shape[3]
+    if mode == "tc":
+        if not _ops.stem_supported(H, W):
+            raise NotImplementedError(f"tensor-core stem needs even H, W and W <= 256 (got {H}x{W}); set AMOE_STEM=rowwin")
+        return _ops.stage_image_stem(image)
+    if mode == "rowwin":
         return _ops.image_to_nhwc_padded(image, _ops.ROWWIN_CP, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), dtype)
     return _ops.image_to_nhwc(image, 4, dtype)
 
 
-def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None):
+def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None,
+               stem_out: Optional[torch.Tensor] = None):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
 
     Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
@@ -149,12 +159,17 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     """
     B, _, H, W = image.shape
     G = pack.G
-    if x_nhwc is None:
-        x_nhwc = stage_image(image, pack.dtype)
-    if isinstance(pack.stem, _ops.PackedRowwin):
-        y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)               # [G*B,H/2,W/2,64]
+    if stem_out is not None:
+        y = stem_out                                                     # computed by the caller (fused with policy conv1)
     else:
-        y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)
+        if x_nhwc is None:
+            x_nhwc = stage_image(image, pack.dtype)
+        if isinstance(pack.stem, _ops.PackedStem):
+            y = _ops.stem_forward(pack.stem, x_nhwc, B, H, W, groups=[G])[0]   # [G*B,H/2,W/2,64]
+        elif isinstance(pack.stem, _ops.PackedRowwin):
+            y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)
+        else:
+            y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)
     # Activations of the 64/128-channel stages live in a physically padded layout (zero border of one
     # pixel) when their 3x3/s1 convolutions run through the halo-reuse kernel; `pad` tracks the layout.
     flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()

@@ -57,7 +57,9 @@ class TrajectoryPolicy(nn.Module):
         p = self._packs.get(key)
         if p is None or p["stamp"] != stamp:
             net = self.backbone.net
-            first = (_ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if _ops.use_rowwin(dtype) else
+            mode = _ops.stem_mode(dtype)
+            first = (_ops.pack_stem([net[0]], [net[1]], device, relu=True) if mode == "tc" else
+                     _ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if mode == "rowwin" else
                      _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4))
             convs = [
                 first,
@@ -73,17 +75,24 @@ class TrajectoryPolicy(nn.Module):
         return p
 
     def forward(self, image: torch.Tensor, context: Optional[torch.Tensor] = None, _x_nhwc=None,
-                _dtype=None) -> Dict[str, torch.Tensor]:
+                _dtype=None, _conv1=None) -> Dict[str, torch.Tensor]:
         require_eval(self, "TrajectoryPolicy")
         if not image.is_cuda:
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
         dtype = _dtype or resolve_dtype(self.precision)
         p = self._pack(dtype, image.device)
         B, _, H, W = image.shape
-        x = _x_nhwc if _x_nhwc is not None else stage_image(image, dtype)
         h, w = H, W
-        for pc in p["convs"]:
-            if isinstance(pc, _ops.PackedRowwin):
+        convs = p["convs"]
+        if _conv1 is not None:       # conv1 already computed by the caller (fused into the experts' stem GEMM)
+            x, convs = _conv1, convs[1:]
+            h, w = x.shape[1], x.shape[2]
+        else:
+            x = _x_nhwc if _x_nhwc is not None else stage_image(image, dtype)
+        for pc in convs:
+            if isinstance(pc, _ops.PackedStem):
+                x = _ops.stem_forward(pc, x, B, h, w)[0]
+            elif isinstance(pc, _ops.PackedRowwin):
                 x = _ops.conv2d_rowwin(pc, x, B, h, w)
             else:
                 x = _ops.conv2d(pc, x, B, h, w)

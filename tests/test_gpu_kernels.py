@@ -181,6 +181,51 @@ def test_conv_tc_rowwin(case):
     assert rel_err(y, ref) < 8e-3 and rel_l2(y, ref) < 4e-3, (rel_err(y, ref), rel_l2(y, ref))
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [(3, True, 2, 64, 64), (3, True, 3, 256, 256), (1, False, 2, 224, 224), (0, True, 2, 64, 96),
+                                  (3, True, 1, 32, 32)])
+def test_stem_tc(case):
+    """All Cin=3 first-layer convolutions (expert stems 7x7/s2/p3 + policy conv1 5x5/s2/p2) as one GEMM over
+    the raw image rows (csrc/stem_tc.cu, Toeplitz no-swizzle A operand)."""
+    from automoe_b200 import _ops
+    n_exp, with_policy, B, H, W = case
+    g = torch.Generator().manual_seed(10)
+    convs, bns = [], []
+    for i in range(n_exp + int(with_policy)):
+        c = nn.Conv2d(3, 64, 7, 2, 3, bias=False) if i < n_exp else nn.Conv2d(3, 32, 5, 2, 2, bias=True)
+        cout = c.weight.shape[0]
+        b = nn.BatchNorm2d(cout)
+        with torch.no_grad():
+            c.weight.copy_((torch.randn(c.weight.shape, generator=g) * 0.1).bfloat16().float())
+            if c.bias is not None:
+                c.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+            b.weight.copy_(1 + 0.1 * torch.randn(cout, generator=g))
+            b.bias.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_mean.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_var.copy_(torch.rand(cout, generator=g) + 0.5)
+        convs.append(c.to(DEV))
+        bns.append(b.to(DEV).eval())
+    img = torch.randn((B, 3, H, W), generator=g).bfloat16().float().to(DEV)
+    ps = _ops.pack_stem(convs, bns, torch.device(DEV), relu=True)
+    xp = _ops.stage_image_stem(img)
+    assert torch.equal(xp[:, 3:3 + H, 4:4 + W, :3].float(), img.permute(0, 2, 3, 1))
+    assert (xp[:, :3] == 0).all() and (xp[:, 3 + H:] == 0).all() and (xp[:, :, :4] == 0).all() and (xp[:, :, 4 + W:] == 0).all()
+    groups = ([n_exp] if n_exp else []) + ([1] if with_policy else [])
+    outs = _ops.stem_forward(ps, xp, B, H, W, groups=groups)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        refs = [F.relu(bn(c(img))) for c, bn in zip(convs, bns)]
+    if n_exp:
+        ref = torch.cat(refs[:n_exp], 0)
+        y = outs[0].float().permute(0, 3, 1, 2)
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < 8e-3 and rel_l2(y, ref) < 4e-3, (rel_err(y, ref), rel_l2(y, ref))
+    if with_policy:
+        y = outs[-1].float().permute(0, 3, 1, 2)
+        assert y.shape == refs[-1].shape
+        assert rel_err(y, refs[-1]) < 8e-3 and rel_l2(y, refs[-1]) < 4e-3, (rel_err(y, refs[-1]), rel_l2(y, refs[-1]))
+
+
 def _mk_conv_bn(Cin, Cout, k, s, p, g, n=1, bias=False):
     convs, bns = [], []
     for _ in range(n):
