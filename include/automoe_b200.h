@@ -68,6 +68,15 @@ int amoe_image_nchw_to_nhwc_padded(amoe_ctx*, const float* src, void* dst, int B
 int amoe_stem_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* scale,
                   const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
                   void* const* dst_host, const int* dst_c_host, void* stream);
+/* Same GEMM with nn.MaxPool2d(3, stride 2, pad 1) fused behind the first n_pool_ch channels (the
+ * expert stems: resnet conv1+bn1+relu+maxpool in one kernel, the full-resolution stem output never
+ * reaches HBM).  pooled: [n_pool_ch/64 * B][H/4+2*out_pad][W/4+2*out_pad][64] bf16; with
+ * out_pad = 1 the zero border is written too.  Channels >= n_pool_ch go to dst/dst_c as above
+ * (entries below n_pool_ch/32 are ignored).  H, W multiples of 4. */
+int amoe_stem_pool_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* scale,
+                       const float* bias, int B, int H, int W, int Wpad, int KH, int n_total,
+                       int relu, int n_pool_ch, void* pooled, int out_pad, void* const* dst_host,
+                       const int* dst_c_host, void* stream);
 /* nn.Conv2d weight [Cout,Cin,KH,KW] fp32 -> packed [Cout][KH][KW][Cin_pad]
  * (dtype f32|bf16, zero-padded channels).  dst points at the first row of this
  * conv inside a (possibly grouped) packed buffer. */

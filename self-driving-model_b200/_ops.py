@@ -150,6 +150,41 @@ def stem_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int,
     return stacked
 
 
+def stem_pool_supported(H: int, W: int) -> bool:
+    import os
+    return H % 4 == 0 and W % 4 == 0 and W // 2 <= 128 and os.environ.get("AMOE_STEM_POOL", "1") != "0"
+
+
+def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int, n_pool: int, out_pad: int):
+    """First n_pool packed convolutions (64 channels each: expert stems) come back max-pooled as one
+    [n_pool*B, H/4+2p, W/4+2p, 64] tensor; the remaining convolutions at full resolution (list)."""
+    dev = x_pad.device
+    Hp, Wp = H // 4, W // 4
+    assert all(c == 64 for c in ps.couts[:n_pool])
+    pooled = torch.empty((n_pool * B, Hp + 2 * out_pad, Wp + 2 * out_pad, 64), device=dev, dtype=torch.bfloat16)
+    rest = [torch.empty((B, H // 2, W // 2, co), device=dev, dtype=torch.bfloat16) for co in ps.couts[n_pool:]]
+    n_chunks = ps.n_total // 32
+    dst = (C.c_void_p * n_chunks)()
+    dst_c = (C.c_int * n_chunks)()
+    i = n_pool * 2
+    for t, co in zip(rest, ps.couts[n_pool:]):
+        for c0 in range(0, co, 32):
+            dst[i] = t.data_ptr() + c0 * 2
+            dst_c[i] = co
+            i += 1
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().amoe_stem_pool_fwd(ctx(dev), ptr(x_pad), ptr(ps.w), ptr(ps.scale), ptr(ps.bias), B, H, W, x_pad.shape[2],
+                                   STEM_KH, ps.n_total, int(ps.relu), n_pool * 64, ptr(pooled), out_pad, dst, dst_c,
+                                   stream_ptr(dev)), "stem_pool_fwd")
+    if prof is not None:
+        ev1.record()
+        prof.append(("conv_tc", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
+    return pooled, rest
+
+
 def _stem_launch(ps: PackedStem, x_pad, B, H, W, outs):
     n_chunks = ps.n_total // 32
     dst = (C.c_void_p * n_chunks)()

@@ -3,11 +3,12 @@
 #include "common.cuh"
 
 // ---- 1x1 conv + mean over pixels -------------------------------------------
-// One CTA per image.  Weights [N][Cin] and a chunk of HEAD_PX pixels live in shared memory (rows
-// padded to an odd stride -> conflict-free); one thread per (pixel, n) output does a Cin-long
-// dot product.  Phase 2: pooled[b,n] = mean_p low[b,p,n], summed in a fixed order (deterministic,
-// the gate's top-1 depends on it).
-constexpr int HEAD_PX = 16;
+// One CTA per image.  Weights [N][Cin] (fp32) and a chunk of up to HEAD_PX pixels (activations as
+// fp32, filled with 16-byte global loads) live in shared memory, rows padded to an odd stride ->
+// conflict-free; one thread per (pixel, n) output does a Cin-long dot product.  Phase 2:
+// pooled[b,n] = mean_p low[b,p,n], summed in a fixed order (deterministic: the gate's top-1
+// routing depends on it).
+constexpr int HEAD_PX = 64;
 
 template <typename T>
 __global__ __launch_bounds__(256) void head1x1_pool_kernel(const T* __restrict__ x,
@@ -21,27 +22,43 @@ __global__ __launch_bounds__(256) void head1x1_pool_kernel(const T* __restrict__
   float* sw = smh;                     // [N][ld]
   float* sx = smh + N * ld;            // [HEAD_PX][ld]
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) sw[(i / Cin) * ld + (i % Cin)] = w[i];
+  for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) sw[(i / Cin) * ld + (i % Cin)] = __ldg(w + i);
   const T* xb = x + (int64_t)b * HW * Cin;
   float* lb = low + (int64_t)b * HW * N;
+  constexpr int VE = 16 / sizeof(T);   // elements per 16-byte load
+  const bool vec = (Cin % VE) == 0 && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
   for (int p0 = 0; p0 < HW; p0 += HEAD_PX) {
     const int np = min(HEAD_PX, HW - p0);
     __syncthreads();  // previous chunk consumed (also orders the weight fill before first use)
-    for (int i = threadIdx.x; i < np * Cin; i += blockDim.x)
-      sx[(i / Cin) * ld + (i % Cin)] = ld_as_float<T>(xb + (int64_t)p0 * Cin + i);
+    if (vec) {
+      const int nv = np * Cin / VE;
+      const uint4* src = reinterpret_cast<const uint4*>(xb + (int64_t)p0 * Cin);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const uint4 raw = __ldg(src + i);
+        const T* e = reinterpret_cast<const T*>(&raw);
+        const int el = i * VE, pl = el / Cin, c = el - pl * Cin;
+#pragma unroll
+        for (int k = 0; k < VE; ++k) sx[pl * ld + c + k] = ld_as_float<T>(e + k);
+      }
+    } else {
+      for (int i = threadIdx.x; i < np * Cin; i += blockDim.x)
+        sx[(i / Cin) * ld + (i % Cin)] = ld_as_float<T>(xb + (int64_t)p0 * Cin + i);
+    }
     __syncthreads();
     for (int o = threadIdx.x; o < np * N; o += blockDim.x) {
       const int pl = o / N, n = o - pl * N;
       const float* xr = sx + pl * ld;
       const float* wr = sw + n * ld;
-      float s0 = 0.f, s1 = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       int c = 0;
-      for (; c + 1 < Cin; c += 2) {
+      for (; c + 3 < Cin; c += 4) {
         s0 = fmaf(xr[c], wr[c], s0);
         s1 = fmaf(xr[c + 1], wr[c + 1], s1);
+        s2 = fmaf(xr[c + 2], wr[c + 2], s2);
+        s3 = fmaf(xr[c + 3], wr[c + 3], s3);
       }
-      if (c < Cin) s0 = fmaf(xr[c], wr[c], s0);
-      lb[(int64_t)(p0 + pl) * N + n] = (s0 + s1) + bias[n];
+      for (; c < Cin; ++c) s0 = fmaf(xr[c], wr[c], s0);
+      lb[(int64_t)(p0 + pl) * N + n] = ((s0 + s1) + (s2 + s3)) + bias[n];
     }
   }
   __syncthreads();  // low[] of this image is complete and visible to the block
@@ -178,7 +195,13 @@ int amoe_head1x1_pool_fwd(amoe_ctx* ctx, const void* x, const float* w, const fl
                           void* stream) {
   AMOE_REQUIRE(ctx && x && w && b && low && pooled, "amoe_head1x1_pool_fwd: NULL argument");
   size_t smem = (size_t)(N + HEAD_PX) * (Cin | 1) * sizeof(float);
-  AMOE_REQUIRE(smem <= 48 * 1024, "amoe_head1x1_pool_fwd: (N+%d)*Cin too large for shared memory (N=%d Cin=%d)", HEAD_PX, N, Cin);
+  AMOE_REQUIRE(smem <= 200 * 1024, "amoe_head1x1_pool_fwd: (N+%d)*Cin too large for shared memory (N=%d Cin=%d)", HEAD_PX, N, Cin);
+  if (smem > 48 * 1024) {
+    if (x_dtype == AMOE_BF16)
+      AMOE_CHECK_CUDA(cudaFuncSetAttribute(head1x1_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      AMOE_CHECK_CUDA(cudaFuncSetAttribute(head1x1_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == AMOE_BF16)

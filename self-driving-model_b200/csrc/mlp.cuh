@@ -10,69 +10,71 @@ constexpr int GATE_THREADS = 512;
 __host__ __device__ inline int64_t al4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
 // y[f][o] = act(b[o] + sum_i W[o][i] * x[f][i]),  x,y in shared memory.
-// A warp owns MLP_RPW output rows at a time so that MLP_RPW independent 16-byte weight loads per lane
-// are in flight (the kernel is bound by the L2->SM latency of streaming the weight rows).
-constexpr int MLP_RPW = 4;
+// The kernels built on this are bound by the L2->SM latency of streaming every weight row once per
+// CTA, so the mapping maximises independent loads in flight: 8 lanes share one output row (each
+// lane owns every 8th 16-byte piece -> a row is read as full 128-byte lines), a warp works on 4
+// rows at once, and a lane issues up to 8 independent 16-byte loads before the first FMA.
+constexpr int MLP_LPR = 8;             // lanes per output row
+constexpr int MLP_RPW = 32 / MLP_LPR;  // rows per warp pass
+constexpr int MLP_BATCH = 8;           // 16-byte weight loads in flight per lane
 
 __device__ __forceinline__ void linear_ft(const float* __restrict__ Wg, const float* __restrict__ bg,
                                           const float* x, int x_ld, int in_dim, float* y, int y_ld,
                                           int out_dim, bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int sub = lane / MLP_LPR, l = lane % MLP_LPR;
   const bool vec = (in_dim & 3) == 0 && (x_ld & 3) == 0;
   for (int o0 = warp * MLP_RPW; o0 < out_dim; o0 += nwarp * MLP_RPW) {
-    float acc[MLP_RPW][GATE_FT];
+    const int o = o0 + sub;
+    const bool row_ok = o < out_dim;
+    float acc[GATE_FT];
 #pragma unroll
-    for (int r = 0; r < MLP_RPW; ++r)
-#pragma unroll
-      for (int f = 0; f < GATE_FT; ++f) acc[r][f] = 0.f;
+    for (int f = 0; f < GATE_FT; ++f) acc[f] = 0.f;
     if (vec) {
       const int n4 = in_dim >> 2;
-      for (int i = lane; i < n4; i += 32) {
-        float4 w4[MLP_RPW];
+      const float4* wr = reinterpret_cast<const float4*>(Wg + (int64_t)(row_ok ? o : 0) * in_dim);
+      for (int j0 = l; j0 < n4; j0 += MLP_LPR * MLP_BATCH) {
+        float4 w4[MLP_BATCH];
 #pragma unroll
-        for (int r = 0; r < MLP_RPW; ++r)
-          w4[r] = (o0 + r < out_dim) ? __ldg(reinterpret_cast<const float4*>(Wg + (int64_t)(o0 + r) * in_dim) + i)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < MLP_BATCH; ++b) {
+          const int j = j0 + b * MLP_LPR;
+          w4[b] = (row_ok && j < n4) ? __ldg(wr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int f = 0; f < GATE_FT; ++f) {
-          const float4 x4 = *reinterpret_cast<const float4*>(x + f * x_ld + (i << 2));
+        for (int b = 0; b < MLP_BATCH; ++b) {
+          const int j = j0 + b * MLP_LPR;
+          if (j < n4) {
 #pragma unroll
-          for (int r = 0; r < MLP_RPW; ++r) {
-            acc[r][f] = fmaf(w4[r].x, x4.x, acc[r][f]);
-            acc[r][f] = fmaf(w4[r].y, x4.y, acc[r][f]);
-            acc[r][f] = fmaf(w4[r].z, x4.z, acc[r][f]);
-            acc[r][f] = fmaf(w4[r].w, x4.w, acc[r][f]);
+            for (int f = 0; f < GATE_FT; ++f) {
+              const float4 x4 = *reinterpret_cast<const float4*>(x + f * x_ld + (j << 2));
+              acc[f] = fmaf(w4[b].x, x4.x, acc[f]);
+              acc[f] = fmaf(w4[b].y, x4.y, acc[f]);
+              acc[f] = fmaf(w4[b].z, x4.z, acc[f]);
+              acc[f] = fmaf(w4[b].w, x4.w, acc[f]);
+            }
           }
         }
       }
     } else {
-      for (int i = lane; i < in_dim; i += 32) {
-        float wv[MLP_RPW];
+      const float* wr = Wg + (int64_t)(row_ok ? o : 0) * in_dim;
+      for (int i = l; i < in_dim; i += MLP_LPR) {
+        const float wv = row_ok ? __ldg(wr + i) : 0.f;
 #pragma unroll
-        for (int r = 0; r < MLP_RPW; ++r) wv[r] = (o0 + r < out_dim) ? __ldg(Wg + (int64_t)(o0 + r) * in_dim + i) : 0.f;
-#pragma unroll
-        for (int f = 0; f < GATE_FT; ++f) {
-          const float xv = x[f * x_ld + i];
-#pragma unroll
-          for (int r = 0; r < MLP_RPW; ++r) acc[r][f] = fmaf(wv[r], xv, acc[r][f]);
-        }
+        for (int f = 0; f < GATE_FT; ++f) acc[f] = fmaf(wv, x[f * x_ld + i], acc[f]);
       }
     }
+    // reduce over the 8 lanes of the row
 #pragma unroll
-    for (int r = 0; r < MLP_RPW; ++r)
+    for (int f = 0; f < GATE_FT; ++f) {
 #pragma unroll
-      for (int f = 0; f < GATE_FT; ++f) acc[r][f] = warp_sum(acc[r][f]);
-    if (lane == 0) {
+      for (int s = MLP_LPR / 2; s > 0; s >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], s);
+    }
+    if (l == 0 && row_ok) {
+      const float bv = __ldg(bg + o);
 #pragma unroll
-      for (int r = 0; r < MLP_RPW; ++r) {
-        if (o0 + r < out_dim) {
-          const float bv = __ldg(bg + o0 + r);
-#pragma unroll
-          for (int f = 0; f < GATE_FT; ++f) {
-            float v = acc[r][f] + bv;
-            y[f * y_ld + o0 + r] = relu ? fmaxf(v, 0.f) : v;
-          }
-        }
+      for (int f = 0; f < GATE_FT; ++f) {
+        float v = acc[f] + bv;
+        y[f * y_ld + o] = relu ? fmaxf(v, 0.f) : v;
       }
     }
   }

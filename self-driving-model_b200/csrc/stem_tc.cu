@@ -209,11 +209,297 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_tc_kernel(const __grid_co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Variant with the ResNet max-pool (3x3, stride 2, pad 1) fused behind the stem: the first
+// n_pool_ch channels (expert stems) never reach HBM at full resolution.  A CTA owns a contiguous
+// range of POOLED rows and walks the conv rows they need in order (2py-1 once as "carry", then
+// 2py and 2py+1 for every pooled row).  Per conv row the epilogue warps write the BN+ReLU'd bf16
+// row into shared memory, take the horizontal 3-max at even columns, fold it into a running
+// vertical max V (values are >= 0 after ReLU, so 0 is the identity that stands for the pool's
+// -inf padding) and emit pooled row py after conv row 2py+1.  Remaining channels (policy conv1)
+// are stored at full resolution as in the plain kernel.
+constexpr int POOL_A_STAGES = 3;
+constexpr int R_PITCH = 400;  // bytes per pixel row of the staging buffer (192 ch * 2 B + pad: conflict-free 16-byte stores)
+
+struct PoolParams {
+  Params base;
+  int n_pool_ch;          // leading channels that are max-pooled (multiple of 64)
+  int Hp, Wp, out_pad;    // pooled size, border of the pooled output tensor
+  __nv_bfloat16* pooled;  // [n_pool_ch/64 * B][Hp+2*out_pad][Wp+2*out_pad][64]
+};
+
+enum { ROLE_CARRY = 0, ROLE_EVEN = 1, ROLE_ODD = 2 };
+
+struct Seq {
+  int p_lo, p_hi, has_carry, n_tiles;
+};
+__device__ __forceinline__ Seq make_seq(int p_total, int Hp) {
+  Seq s;
+  s.p_lo = (int)((int64_t)blockIdx.x * p_total / gridDim.x);
+  s.p_hi = (int)((int64_t)(blockIdx.x + 1) * p_total / gridDim.x);
+  s.has_carry = (s.p_hi > s.p_lo && (s.p_lo % Hp) != 0) ? 1 : 0;
+  s.n_tiles = s.has_carry + 2 * (s.p_hi - s.p_lo);
+  return s;
+}
+__device__ __forceinline__ void tile_at(const Seq& s, int k, int Hp, int& b, int& py, int& oh, int& role) {
+  if (s.has_carry && k == 0) {
+    b = s.p_lo / Hp; py = s.p_lo - b * Hp; oh = 2 * py - 1; role = ROLE_CARRY;
+  } else {
+    const int kk = k - s.has_carry;
+    const int gp = s.p_lo + (kk >> 1);
+    b = gp / Hp; py = gp - b * Hp; oh = 2 * py + (kk & 1); role = (kk & 1) ? ROLE_ODD : ROLE_EVEN;
+  }
+}
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
+  const Params& p = pp.base;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * POOL_A_STAGES + 5];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_scale[256];
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_bytes_al = (uint32_t)((p.w_bytes + 127) & ~127);
+  const uint32_t smem_w = smem_base;
+  const uint32_t smem_a = smem_base + w_bytes_al;
+  uint8_t* sR = gen_base + w_bytes_al + (size_t)POOL_A_STAGES * p.a_stage_bytes;  // [128][R_PITCH]
+  uint8_t* sV = sR + 128 * R_PITCH;                                                // [Wp][n_pool_ch*2]
+  const uint32_t bar_afull = smem_u32(&bars[0]);
+  const uint32_t bar_aempty = smem_u32(&bars[POOL_A_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * POOL_A_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * POOL_A_STAGES + 2]);
+  const uint32_t bar_w = smem_u32(&bars[2 * POOL_A_STAGES + 4]);
+
+  for (int i = threadIdx.x; i < p.n_total; i += NUM_THREADS) {
+    s_scale[i] = __ldg(p.scale + i);
+    s_bias[i] = __ldg(p.bias + i);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < POOL_A_STAGES; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const uint32_t tile_bytes = (uint32_t)(p.KH * p.row_bytes);
+  const Seq seq = make_seq(p.B * pp.Hp, pp.Hp);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, (uint32_t)p.w_bytes);
+      for (int o = 0; o < p.w_bytes; o += 32768)
+        bulk_g2s(smem_w + (uint32_t)o, p.w + o, (uint32_t)std::min(32768, p.w_bytes - o), bar_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int k = 0; k < seq.n_tiles; ++k) {
+        int b, py, oh, role;
+        tile_at(seq, k, pp.Hp, b, py, oh, role);
+        mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
+        mbar_arrive_expect_tx(bar_afull + 8 * stage, tile_bytes);
+        bulk_g2s(smem_a + (uint32_t)stage * p.a_stage_bytes, p.x + ((int64_t)b * p.Hpad + 2 * oh) * p.row_bytes,
+                 tile_bytes, bar_afull + 8 * stage);
+        if (++stage == POOL_A_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(p.n_total);
+    const uint32_t lbo_b = (uint32_t)p.n_total * 16u;
+    mbar_wait(bar_w, 0);
+    tcgen05_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < seq.n_tiles; ++k) {
+      const int acc = k & 1;
+      const uint32_t tphase = (uint32_t)(k >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
+      mbar_wait(bar_afull + 8 * stage, phase);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+      const uint32_t a_base = smem_a + (uint32_t)stage * p.a_stage_bytes;
+      for (int kh = 0; kh < p.KH; ++kh) {
+#pragma unroll
+        for (int ks = 0; ks < WIN_K / UMMA_K; ++ks) {
+          const uint64_t a_desc = make_nosw_desc(a_base + (uint32_t)(kh * p.row_bytes + ks * 32), 16u, 128u);
+          const uint64_t b_desc = make_nosw_desc(smem_w + (uint32_t)(kh * 4 + ks * 2) * lbo_b, lbo_b, 128u);
+          umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)((kh | ks) != 0));
+        }
+      }
+      umma_commit(bar_aempty + 8 * stage);
+      umma_commit(bar_tfull + 8 * acc);
+      if (++stage == POOL_A_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================ epilogue + max-pool ============================
+    const int lg = warp & 3;
+    const int ow = lg * 32 + lane;
+    const bool valid = ow < p.Wo;
+    const int te = threadIdx.x - 64;            // 0..127 among the epilogue threads
+    const int n_chunks = p.n_total >> 5;
+    const int pool_chunks = pp.n_pool_ch >> 5;
+    const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
+    const int v_pitch = pp.n_pool_ch * 2;       // bytes per pixel of V
+    const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
+    for (int k = 0; k < seq.n_tiles; ++k) {
+      const int acc = k & 1;
+      const uint32_t tphase = (uint32_t)(k >> 1) & 1u;
+      int b, py, oh, role;
+      tile_at(seq, k, pp.Hp, b, py, oh, role);
+      const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
+      mbar_wait(bar_tfull + 8 * acc, tphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+        tmem_ld_wait();
+        if (valid && (c < pool_chunks || role != ROLE_CARRY)) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+            float f[8];
+            f[0] = fmaf(__uint_as_float(a[v * 8 + 0]), s0.x, b0.x);
+            f[1] = fmaf(__uint_as_float(a[v * 8 + 1]), s0.y, b0.y);
+            f[2] = fmaf(__uint_as_float(a[v * 8 + 2]), s0.z, b0.z);
+            f[3] = fmaf(__uint_as_float(a[v * 8 + 3]), s0.w, b0.w);
+            f[4] = fmaf(__uint_as_float(a[v * 8 + 4]), s1.x, b1.x);
+            f[5] = fmaf(__uint_as_float(a[v * 8 + 5]), s1.y, b1.y);
+            f[6] = fmaf(__uint_as_float(a[v * 8 + 6]), s1.z, b1.z);
+            f[7] = fmaf(__uint_as_float(a[v * 8 + 7]), s1.w, b1.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                       pack_bf16x2(f[6], f[7]));
+            if (c < pool_chunks)
+              *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = o;
+            else  // not pooled (policy conv1): full-resolution store; a carry row belongs to another CTA's range
+              *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // staged conv row complete
+      // horizontal 3-max at even columns, folded into the running vertical max
+      for (int item = te; item < pp.Wp * NV; item += 128) {
+        const int px = item / NV, v = item - px * NV;
+        const uint8_t* r0 = sR + (2 * px) * R_PITCH + v * 16;
+        uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
+        if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
+        uint4* vp = reinterpret_cast<uint4*>(sV + px * v_pitch + v * 16);
+        if (role == ROLE_CARRY || (role == ROLE_EVEN && py == 0)) {
+          *vp = m;                                  // first conv row of this pooled row (top padding above)
+        } else if (role == ROLE_EVEN) {
+          *vp = hmax8(*vp, m);
+        } else {
+          const uint4 out = hmax8(*vp, m);
+          *vp = m;                                  // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
+          const int e = v >> 3, cv = v & 7;
+          __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + pp.out_pad) * Wq + px + pp.out_pad) * 64 + cv * 8;
+          *reinterpret_cast<uint4*>(d) = out;
+        }
+      }
+      if (role == ROLE_ODD && pp.out_pad) {
+        // zero border of the padded pooled tensor: left/right pixel of this row, plus the rows above/below the image
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int item = te; item < 2 * NV; item += 128) {
+          const int side = item / NV, v = item - side * NV, e = v >> 3, cv = v & 7;
+          __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + 1) * Wq + (side ? Wq - 1 : 0)) * 64 + cv * 8;
+          *reinterpret_cast<uint4*>(d) = z;
+        }
+        if (py == 0 || py == pp.Hp - 1) {
+          const int row = (py == 0) ? 0 : Hq - 1;
+          for (int item = te; item < Wq * NV; item += 128) {
+            const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
+            __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + row) * Wq + x) * 64 + cv * 8;
+            *reinterpret_cast<uint4*>(d) = z;
+          }
+          if (pp.Hp == 1) {  // single pooled row: both borders
+            for (int item = te; item < Wq * NV; item += 128) {
+              const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
+              __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + Hq - 1) * Wq + x) * 64 + cv * 8;
+              *reinterpret_cast<uint4*>(d) = z;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer free for the next conv row
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace stem
 
 int amoe_stem_init(amoe_ctx* ctx) {
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  return 0;
+}
+
+static int stem_fill(stem::Params& p, const void* x_pad, const void* w_img, const float* scale, const float* bias,
+                     int B, int H, int W, int Wpad, int KH, int n_total, int relu, void* const* dst_host,
+                     const int* dst_c_host, int first_dst_chunk);
+
+extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img, const float* scale,
+                                  const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
+                                  int n_pool_ch, void* pooled, int out_pad, void* const* dst_host,
+                                  const int* dst_c_host, void* stream) {
+  using namespace stem;
+  AMOE_REQUIRE(ctx && pooled, "amoe_stem_pool_fwd: NULL argument");
+  AMOE_REQUIRE(n_pool_ch % 64 == 0 && n_pool_ch >= 64 && n_pool_ch <= 192 && n_pool_ch <= n_total,
+               "amoe_stem_pool_fwd: n_pool_ch=%d must be a multiple of 64 in [64,192]", n_pool_ch);
+  AMOE_REQUIRE(H % 4 == 0 && W % 4 == 0, "amoe_stem_pool_fwd: H and W must be multiples of 4 (got %dx%d)", H, W);
+  AMOE_REQUIRE(out_pad == 0 || out_pad == 1, "amoe_stem_pool_fwd: out_pad must be 0 or 1");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(pooled) & 15) == 0, "amoe_stem_pool_fwd: pooled must be 16-byte aligned");
+  PoolParams pp;
+  int rc = stem_fill(pp.base, x_pad, w_img, scale, bias, B, H, W, Wpad, KH, n_total, relu, dst_host, dst_c_host, n_pool_ch / 32);
+  if (rc) return rc;
+  pp.n_pool_ch = n_pool_ch;
+  pp.Hp = H / 4; pp.Wp = W / 4; pp.out_pad = out_pad;
+  pp.pooled = (__nv_bfloat16*)pooled;
+  const int p_total = B * pp.Hp;
+  if (p_total == 0) return 0;
+  const size_t smem = ((size_t)pp.base.w_bytes + 127) / 128 * 128 + (size_t)POOL_A_STAGES * pp.base.a_stage_bytes +
+                      (size_t)128 * R_PITCH + (size_t)pp.Wp * n_pool_ch * 2 + 256;
+  AMOE_REQUIRE(smem <= 226 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
+  const int grid = std::min(p_total, ctx->sm_count);
+  stem_pool_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(pp);
+  AMOE_LAUNCH_OK(ctx);
   return 0;
 }
 
@@ -221,7 +507,24 @@ extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img
                              const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
                              void* const* dst_host, const int* dst_c_host, void* stream) {
   using namespace stem;
-  AMOE_REQUIRE(ctx && x_pad && w_img && scale && bias && dst_host && dst_c_host, "amoe_stem_fwd: NULL argument");
+  AMOE_REQUIRE(ctx != nullptr, "amoe_stem_fwd: NULL ctx");
+  Params p;
+  int rc = stem_fill(p, x_pad, w_img, scale, bias, B, H, W, Wpad, KH, n_total, relu, dst_host, dst_c_host, 0);
+  if (rc) return rc;
+  if (p.total_tiles == 0) return 0;
+  const size_t smem = ((size_t)p.w_bytes + 127) / 128 * 128 + (size_t)A_STAGES * p.a_stage_bytes + 256;
+  AMOE_REQUIRE(smem <= 220 * 1024, "amoe_stem_fwd: shared memory budget exceeded (%zu bytes)", smem);
+  const int grid = std::min(p.total_tiles, ctx->sm_count);
+  stem_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+static int stem_fill(stem::Params& p, const void* x_pad, const void* w_img, const float* scale, const float* bias,
+                     int B, int H, int W, int Wpad, int KH, int n_total, int relu, void* const* dst_host,
+                     const int* dst_c_host, int first_dst_chunk) {
+  using namespace stem;
+  AMOE_REQUIRE(x_pad && w_img && scale && bias && dst_host && dst_c_host, "amoe_stem_fwd: NULL argument");
   AMOE_REQUIRE(H % 2 == 0 && W % 2 == 0, "amoe_stem_fwd: H and W must be even (got %dx%d)", H, W);
   AMOE_REQUIRE(n_total % 32 == 0 && n_total >= 32 && n_total <= 256, "amoe_stem_fwd: n_total=%d must be a multiple of 32 in [32,256]", n_total);
   AMOE_REQUIRE(KH >= 1 && KH <= 7, "amoe_stem_fwd: KH=%d out of range", KH);
@@ -230,7 +533,6 @@ extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img
   AMOE_REQUIRE(Wpad >= W + 6 && Wpad % 2 == 0, "amoe_stem_fwd: Wpad=%d too small/odd for W=%d", Wpad, W);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_img) & 15) == 0,
                "amoe_stem_fwd: pointers must be 16-byte aligned");
-  Params p;
   p.B = B; p.Ho = Ho; p.Wo = Wo; p.Hpad = H + 6; p.KH = KH;
   p.row_bytes = Wpad * 8;
   // garbage rows (ow >= Wo) read up to byte 16*127 + 64 past the start of the last filter row
@@ -243,17 +545,11 @@ extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img
   p.w = (const uint8_t*)w_img;
   p.scale = scale; p.bias = bias;
   for (int c = 0; c < MAX_CHUNKS; ++c) { p.dst[c] = nullptr; p.dst_c[c] = 0; }
-  for (int c = 0; c < n_total / 32; ++c) {
+  for (int c = first_dst_chunk; c < n_total / 32; ++c) {
     AMOE_REQUIRE(dst_host[c] != nullptr && dst_c_host[c] % 8 == 0 && (reinterpret_cast<uintptr_t>(dst_host[c]) & 15) == 0,
                  "amoe_stem_fwd: bad destination for chunk %d", c);
     p.dst[c] = (__nv_bfloat16*)dst_host[c];
     p.dst_c[c] = dst_c_host[c];
   }
-  if (p.total_tiles == 0) return 0;
-  const size_t smem = ((size_t)p.w_bytes + 127) / 128 * 128 + (size_t)A_STAGES * p.a_stage_bytes + 256;
-  AMOE_REQUIRE(smem <= 220 * 1024, "amoe_stem_fwd: shared memory budget exceeded (%zu bytes)", smem);
-  const int grid = std::min(p.total_tiles, ctx->sm_count);
-  stem_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
-  AMOE_LAUNCH_OK(ctx);
   return 0;
 }

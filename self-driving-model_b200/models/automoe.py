@@ -23,8 +23,8 @@ from ._gatepack import pack_gate_params, require_eval
 from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
-from .experts._base import run_experts
-from .experts._trunk import params_stamp, stage_image
+from .experts._base import get_trunk_pack, run_experts
+from .experts._trunk import params_stamp, stage_image, trunk_pool_pad
 from .experts.expert_extractors import create_expert_extractors
 from .gating.gating_network import GatingNetwork
 from .policy.trajectory_head import TrajectoryPolicy
@@ -159,15 +159,22 @@ class AutoMoE(nn.Module):
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
         x_nhwc = stage_image(image, dtype)
-        stem_out = pol1 = None
+        stem_out = pol1 = pooled = None
         if _ops.stem_mode(dtype) == "tc":
             # experts' stems + policy conv1 read the same frame: one GEMM with N = 3*64 + 32
+            # (+ the experts' max-pool fused behind it when the geometry allows)
             fs = self._fused_stem(image.device)
-            stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, image.shape[0], image.shape[2], image.shape[3],
-                                               groups=[len(self.experts), 1])
+            Bn, Hn, Wn = image.shape[0], image.shape[2], image.shape[3]
+            if _ops.stem_pool_supported(Hn, Wn):
+                tp = get_trunk_pack(list(self.experts), dtype, image.device, self._expert_packs)
+                pooled, rest = _ops.stem_pool_forward(fs, x_nhwc, Bn, Hn, Wn, len(self.experts),
+                                                      trunk_pool_pad(tp, Hn, Wn))
+                pol1 = rest[0]
+            else:
+                stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, Bn, Hn, Wn, groups=[len(self.experts), 1])
 
         expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
-                                          stem_out=stem_out)
+                                          stem_out=stem_out, stem_pooled=pooled)
 
         gn = self.gating_network
         g = _ops.gate(state, aux['pooled'], self._gate_params(image.device, aux['n_ch']), aux['n_ch'],

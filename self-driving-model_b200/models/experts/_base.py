@@ -46,8 +46,18 @@ def _check_eval(experts):
                 "train-mode (batch-statistics) BatchNorm is not implemented yet - call .eval() on the experts")
 
 
+def get_trunk_pack(experts, dtype, device, cache: dict) -> TrunkPack:
+    stamp = params_stamp(experts)
+    key = (dtype, device.index)
+    pack: TrunkPack = cache.get(key)
+    if pack is None or pack.stamp != stamp:
+        pack = pack_trunks(experts, [e.head_module() for e in experts], dtype, device)
+        cache[key] = pack
+    return pack
+
+
 def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None,
-                stem_out=None):
+                stem_out=None, stem_pooled=None):
     """Run G experts on the same image batch in grouped launches.
 
     Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
@@ -56,14 +66,9 @@ def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.
     if not image.is_cuda:
         raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
     _check_eval(experts)
-    stamp = params_stamp(experts)
-    key = (dtype, image.device.index)
-    pack: TrunkPack = cache.get(key)
-    if pack is None or pack.stamp != stamp:
-        pack = pack_trunks(experts, [e.head_module() for e in experts], dtype, image.device)
-        cache[key] = pack
+    pack = get_trunk_pack(experts, dtype, image.device, cache)
     B, _, H, W = image.shape
-    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out)
+    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled)
     outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
     # mean over the up-sampled map == mean over the low-res map only for integer scale factors
     off = 0

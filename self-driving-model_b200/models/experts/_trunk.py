@@ -149,8 +149,17 @@ def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return _ops.image_to_nhwc(image, 4, dtype)
 
 
+def trunk_pool_pad(pack: TrunkPack, H: int, W: int) -> int:
+    """1 if the max-pooled stem output must be stored with a zero border (its consumers are the
+    halo-reuse 3x3 kernels), else 0."""
+    flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()
+    h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+    return 1 if (flat_ok and _ops.flat_supported(pack.blocks[0][1], h4, w4, pack.dtype)) else 0
+
+
 def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None,
-               stem_out: Optional[torch.Tensor] = None):
+               stem_out: Optional[torch.Tensor] = None, stem_pooled: Optional[torch.Tensor] = None):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
 
     Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
@@ -159,12 +168,18 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     """
     B, _, H, W = image.shape
     G = pack.G
-    if stem_out is not None:
+    pad = trunk_pool_pad(pack, H, W)
+    if stem_pooled is not None:
+        y = None                                                         # stem + max-pool done by the caller
+    elif stem_out is not None:
         y = stem_out                                                     # computed by the caller (fused with policy conv1)
     else:
         if x_nhwc is None:
             x_nhwc = stage_image(image, pack.dtype)
-        if isinstance(pack.stem, _ops.PackedStem):
+        if isinstance(pack.stem, _ops.PackedStem) and _ops.stem_pool_supported(H, W):
+            stem_pooled = _ops.stem_pool_forward(pack.stem, x_nhwc, B, H, W, G, pad)[0]
+            y = None
+        elif isinstance(pack.stem, _ops.PackedStem):
             y = _ops.stem_forward(pack.stem, x_nhwc, B, H, W, groups=[G])[0]   # [G*B,H/2,W/2,64]
         elif isinstance(pack.stem, _ops.PackedRowwin):
             y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)
@@ -173,9 +188,12 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     # Activations of the 64/128-channel stages live in a physically padded layout (zero border of one
     # pixel) when their 3x3/s1 convolutions run through the halo-reuse kernel; `pad` tracks the layout.
     flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()
-    h_cur, w_cur = (y.shape[1] - 1) // 2 + 1, (y.shape[2] - 1) // 2 + 1
-    pad = 1 if (flat_ok and _ops.flat_supported(pack.blocks[0][1], h_cur, w_cur, pack.dtype)) else 0
-    y = _ops.maxpool3x3s2(y, out_pad=pad)                                # [G*B,H/4(+2),W/4(+2),64]
+    h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    h_cur, w_cur = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+    if stem_pooled is not None:
+        y = stem_pooled                                                  # [G*B,H/4(+2),W/4(+2),64]
+    else:
+        y = _ops.maxpool3x3s2(y, out_pad=pad)
     for (c1, c2, dn) in pack.blocks:
         # geometry of this block's output and whether its stride-1 convs take the flat kernel
         h_out = (h_cur + 2 * c1.ph - c1.kh) // c1.sh + 1

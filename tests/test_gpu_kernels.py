@@ -226,6 +226,52 @@ def test_stem_tc(case):
         assert rel_err(y, refs[-1]) < 8e-3 and rel_l2(y, refs[-1]) < 4e-3, (rel_err(y, refs[-1]), rel_l2(y, refs[-1]))
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [(3, True, 2, 64, 64, 1), (3, True, 3, 256, 256, 1), (1, False, 2, 224, 224, 0),
+                                  (3, True, 5, 32, 32, 1), (1, True, 150, 16, 16, 0), (3, True, 2, 256, 128, 1)])
+def test_stem_pool_fused(case):
+    """Stem GEMM with the ResNet max-pool fused behind the expert channels (policy conv1 stays full-res)."""
+    from automoe_b200 import _ops
+    n_exp, with_policy, B, H, W, out_pad = case
+    g = torch.Generator().manual_seed(12)
+    convs, bns = [], []
+    for i in range(n_exp + int(with_policy)):
+        c = nn.Conv2d(3, 64, 7, 2, 3, bias=False) if i < n_exp else nn.Conv2d(3, 32, 5, 2, 2, bias=True)
+        cout = c.weight.shape[0]
+        b = nn.BatchNorm2d(cout)
+        with torch.no_grad():
+            c.weight.copy_((torch.randn(c.weight.shape, generator=g) * 0.1).bfloat16().float())
+            if c.bias is not None:
+                c.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+            b.weight.copy_(1 + 0.1 * torch.randn(cout, generator=g))
+            b.bias.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_mean.copy_(0.1 * torch.randn(cout, generator=g))
+            b.running_var.copy_(torch.rand(cout, generator=g) + 0.5)
+        convs.append(c.to(DEV))
+        bns.append(b.to(DEV).eval())
+    img = torch.randn((B, 3, H, W), generator=g).bfloat16().float().to(DEV)
+    ps = _ops.pack_stem(convs, bns, torch.device(DEV), relu=True)
+    xp = _ops.stage_image_stem(img)
+    assert _ops.stem_pool_supported(H, W)
+    pooled, rest = _ops.stem_pool_forward(ps, xp, B, H, W, n_exp, out_pad)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        # the reference pools bf16-rounded activations (autocast); max commutes with the rounding
+        refs = [F.relu(bn(c(img))) for c, bn in zip(convs, bns)]
+        ref_pool = torch.cat([F.max_pool2d(r, 3, 2, 1) for r in refs[:n_exp]], 0)
+    y = pooled
+    if out_pad:
+        assert (y[:, 0] == 0).all() and (y[:, -1] == 0).all() and (y[:, :, 0] == 0).all() and (y[:, :, -1] == 0).all()
+        y = y[:, 1:-1, 1:-1]
+    y = y.float().permute(0, 3, 1, 2)
+    assert y.shape == ref_pool.shape
+    assert rel_err(y, ref_pool) < 8e-3 and rel_l2(y, ref_pool) < 4e-3, (rel_err(y, ref_pool), rel_l2(y, ref_pool))
+    if with_policy:
+        yp = rest[0].float().permute(0, 3, 1, 2)
+        assert yp.shape == refs[-1].shape
+        assert rel_err(yp, refs[-1]) < 8e-3, rel_err(yp, refs[-1])
+
+
 def _mk_conv_bn(Cin, Cout, k, s, p, g, n=1, bias=False):
     convs, bns = [], []
     for _ in range(n):
