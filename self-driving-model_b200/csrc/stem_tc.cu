@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
 int amoe_stem_init(amoe_ctx* ctx) {
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return 0;
 }
 
@@ -496,7 +496,7 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
   if (p_total == 0) return 0;
   const size_t smem = ((size_t)pp.base.w_bytes + 127) / 128 * 128 + (size_t)POOL_A_STAGES * pp.base.a_stage_bytes +
                       (size_t)128 * R_PITCH + (size_t)pp.Wp * n_pool_ch * 2 + 256;
-  AMOE_REQUIRE(smem <= 226 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
+  AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
   stem_pool_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(pp);
   AMOE_LAUNCH_OK(ctx);
