@@ -362,6 +362,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
     const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
     const int v_pitch = pp.n_pool_ch * 2;       // bytes per pixel of V
     const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
+    // the (pooled pixel, channel vector) items of this thread never change: hoist their index math
+    constexpr int MAX_ITEMS = 12;  // Wp*NV / 128 <= 64*24/128
+    int r_off[MAX_ITEMS], v_off[MAX_ITEMS];
+    int64_t g_off[MAX_ITEMS];
+    const int n_items = pp.Wp * NV;
+#pragma unroll
+    for (int i = 0; i < MAX_ITEMS; ++i) {
+      const int item = te + 128 * i;
+      const int px = item / NV, v = item - px * NV, e = v >> 3, cv = v & 7;
+      r_off[i] = (2 * px) * R_PITCH + v * 16;
+      v_off[i] = px * v_pitch + v * 16;
+      g_off[i] = ((int64_t)e * p.B * Hq * Wq + px + pp.out_pad) * 64 + cv * 8;
+    }
     for (int k = 0; k < seq.n_tiles; ++k) {
       const int acc = k & 1;
       const uint32_t tphase = (uint32_t)(k >> 1) & 1u;
@@ -408,22 +421,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
       asm volatile("bar.sync 1, 128;" ::: "memory");       // staged conv row complete
       // horizontal 3-max at even columns, folded into the running vertical max
-      for (int item = te; item < pp.Wp * NV; item += 128) {
-        const int px = item / NV, v = item - px * NV;
-        const uint8_t* r0 = sR + (2 * px) * R_PITCH + v * 16;
-        uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
-        if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
-        uint4* vp = reinterpret_cast<uint4*>(sV + px * v_pitch + v * 16);
-        if (role == ROLE_CARRY || (role == ROLE_EVEN && py == 0)) {
-          *vp = m;                                  // first conv row of this pooled row (top padding above)
-        } else if (role == ROLE_EVEN) {
-          *vp = hmax8(*vp, m);
-        } else {
-          const uint4 out = hmax8(*vp, m);
-          *vp = m;                                  // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
-          const int e = v >> 3, cv = v & 7;
-          __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + pp.out_pad) * Wq + px + pp.out_pad) * 64 + cv * 8;
-          *reinterpret_cast<uint4*>(d) = out;
+      const int64_t g_row = ((int64_t)b * Hq + py + pp.out_pad) * Wq * 64;
+      const bool first_row = role == ROLE_CARRY || (role == ROLE_EVEN && py == 0);
+#pragma unroll
+      for (int i = 0; i < MAX_ITEMS; ++i) {
+        if (te + 128 * i < n_items) {
+          const uint8_t* r0 = sR + r_off[i];
+          uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
+          if (r_off[i] >= 2 * R_PITCH) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));   // px > 0
+          uint4* vp = reinterpret_cast<uint4*>(sV + v_off[i]);
+          if (first_row) {
+            *vp = m;                                  // first conv row of this pooled row (top padding above)
+          } else if (role == ROLE_EVEN) {
+            *vp = hmax8(*vp, m);
+          } else {
+            const uint4 out = hmax8(*vp, m);
+            *vp = m;                                  // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
+            *reinterpret_cast<uint4*>(pp.pooled + g_row + g_off[i]) = out;
+          }
         }
       }
       if (role == ROLE_ODD && pp.out_pad) {
