@@ -135,6 +135,14 @@ int amoe_maxpool3x3s2_fwd(amoe_ctx*, const void* x, void* y, int NB, int H, int 
 int amoe_conv3x3_flat_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
                           const float* bias, const void* residual, void* y, int G, int B, int H,
                           int W, int Cin, int Cout, int relu, void* stream);
+/* Same, for a sub-batch of a larger grouped tensor: expert group g of y (of the residual) starts
+ * y_group_images (res_group_images) images after group g-1 instead of B (0 = B).  Lets a caller walk
+ * the batch in L2-sized chunks while the last layer of the chunked region writes straight into the
+ * full [G*B_total,...] tensor (y points at the chunk's first image inside group 0). */
+int amoe_conv3x3_flat_fwd_strided(amoe_ctx*, const void* x, const void* w, const float* scale,
+                                  const float* bias, const void* residual, void* y, int G, int B,
+                                  int H, int W, int Cin, int Cout, int relu,
+                                  int64_t y_group_images, int64_t res_group_images, void* stream);
 int amoe_conv3x3_flat_supported(int H, int W, int Cin, int Cout);
 
 /* ---- expert heads ------------------------------------------------------ */
@@ -211,6 +219,100 @@ int amoe_hungarian_cost_fwd(amoe_ctx*, const float* logits, const float* boxes,
 int amoe_lsap_batched_host(const float* cost_host, const int32_t* n_tgt_host, int B, int Q,
                            int Nmax, int64_t* rows_host, int64_t* cols_host,
                            int32_t* n_match_host, int n_threads);
+
+/* ---- training step of the gating / policy part -------------------------------
+ * Replaces, for training/train_gating_network.py:76-117 (train_one_epoch), the autograd graph torch
+ * builds over the trainable 2.87 M parameters (context extractor, expert extractors, GatingNetwork,
+ * TrajectoryPolicy) - experts are frozen and run through the inference entry points above.  All fp32,
+ * row-major [B, features]; every function is one or a few launches on `stream`, allocates nothing. */
+/* y = Dropout_p(ReLU?(x W^T + b));  x [B,in] (row stride ldx), W [out,in], y [B,out] (row stride ldy).
+ * Dropout is the inverted form nn.Dropout uses (kept units scaled by 1/(1-p)), keyed by (seed, b*out+o). */
+int amoe_linear_fwd(amoe_ctx*, const float* x, int ldx, const float* W, const float* b, float* y,
+                    int ldy, int B, int in_dim, int out_dim, int relu, float drop_p, uint64_t seed,
+                    void* stream);
+/* Gradients of the above.  With relu!=0 the mask of ReLU and Dropout together is y > 0 (g_tmp [B,out]
+ * receives dy*[y>0]/(1-p)).  Any of dx/dW/db may be NULL.  dW [out,in], db [out]: overwritten. */
+int amoe_linear_bwd(amoe_ctx*, const float* dy, int lddy, const float* y, int ldy, const float* x,
+                    int ldx, const float* W, float* g_tmp, float* dx, int lddx, float* dW, float* db,
+                    int B, int in_dim, int out_dim, int relu, float drop_p, void* stream);
+/* nn.LayerNorm over the last dim (biased variance); mean/rstd [B] are saved for the backward. */
+int amoe_layernorm_fwd(amoe_ctx*, const float* x, const float* gamma, const float* beta, float* y,
+                       float* mean, float* rstd, int B, int D, float eps, void* stream);
+int amoe_layernorm_bwd(amoe_ctx*, const float* dy, const float* x, const float* gamma,
+                       const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta,
+                       int B, int D, void* stream);
+/* weights = softmax(logits/T) [B,E]; combined[b] = sum_e weights[b,e] * processed_e[b]
+ * (models/gating/gating_network.py:157-165).  processed_e = processed + e*expert_stride, rows ld_p apart. */
+int amoe_gate_combine_fwd(amoe_ctx*, const float* logits, const float* processed,
+                          int64_t expert_stride, int ld_p, float temperature, float* weights,
+                          float* combined, int B, int E, int P, void* stream);
+/* dcombined [B,P] and/or dweights [B,E] (direct gradient on the gate weights: load-balancing and
+ * entropy losses) -> dlogits [B,E], dprocessed_e = dprocessed + e*dexpert_stride ([B,P] each). */
+int amoe_gate_combine_bwd(amoe_ctx*, const float* dcombined, const float* dweights,
+                          const float* weights, const float* processed, int64_t expert_stride,
+                          int ld_p, float temperature, float* dlogits, float* dprocessed,
+                          int64_t dexpert_stride, int B, int E, int P, void* stream);
+/* compute_gating_losses (training/train_gating_network.py:21-74): every loss term and the gradient of
+ * total_loss w.r.t. the predictions, one launch.
+ *   waypoints/tgt_waypoints [B,H,2]; speed [B,*] rows speed_ld apart, tgt_speed rows tgt_speed_ld apart
+ *   speed_mode 0: no speed term; 1: L1 over the [B,H] sequences; 2: last step only
+ *   coef_host[6] = ade, fde, speed, smoothness, load_balancing, entropy weights (HOST pointer)
+ *   losses[7] (device) = total, ade, fde, speed, smoothness, load_balancing, entropy_loss
+ *   d_waypoints [B,H,2], d_speed [B,H], d_weights [B,E]: d total / d prediction (may be NULL). */
+int amoe_gating_loss_fwd_bwd(amoe_ctx*, const float* waypoints, const float* speed, int speed_ld,
+                             const float* expert_weights, const float* tgt_waypoints,
+                             const float* tgt_speed, int tgt_speed_ld, int B, int H, int E,
+                             int speed_mode, const float* coef_host, int use_lb, int use_entropy,
+                             float* losses, float* d_waypoints, float* d_speed, float* d_weights,
+                             void* stream);
+/* out2[0] = sum g^2, out2[1] = sqrt of it, over a flat fp32 buffer (clip_grad_norm_'s total norm);
+ * partial_ws: ws_floats >= 1 scratch floats (more = more CTAs, up to 4 per SM). */
+int amoe_sq_norm(amoe_ctx*, const float* g, int64_t n, float* partial_ws, int ws_floats,
+                 float* out2, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.AdamW.step() on flat buffers, one launch:
+ * g' = g * grad_scale * min(1, max_norm / (norm2[1]*grad_scale + 1e-6)); decoupled weight decay;
+ * bias-corrected moments with `step` counting from 1.  norm2 from amoe_sq_norm (device, NULL or
+ * max_norm <= 0: no clipping).  grad_scale = 1/world_size after a SUM all-reduce. */
+int amoe_fused_clip_adamw(amoe_ctx*, float* params, const float* grads, float* exp_avg,
+                          float* exp_avg_sq, int64_t n, const float* norm2, float grad_scale,
+                          float max_norm, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, void* stream);
+/* nn.BatchNorm2d in training mode on NHWC fp32 x [M = N*H*W, C]: batch statistics (biased variance for
+ * the normalisation, unbiased for running_var), running stats updated in place with `momentum`
+ * (NULL: not tracked), y = ReLU?(gamma * xhat + beta).  save_mean/save_rstd [C] feed the backward.
+ * workspace: amoe_colreduce_workspace_floats(M, C) floats. */
+int64_t amoe_colreduce_workspace_floats(int64_t M, int C);
+int amoe_bn_train_fwd(amoe_ctx*, const float* x, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* y,
+                      float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
+                      int relu, void* stream);
+/* y = ReLU?(gamma*(x-mean)*rstd + beta) with given statistics (eval-mode BN kept differentiable). */
+int amoe_bn_apply_fwd(amoe_ctx*, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, float* y, int64_t M, int C, int relu,
+                      void* stream);
+/* Backward of either: y_relu != NULL masks dy with y > 0 first.  batch_stats=1: statistics were taken
+ * from this batch (train mode); 0: constants (eval mode).  dgamma/dbeta [C] always written. */
+int amoe_bn_bwd(amoe_ctx*, const float* dy, const float* x, const float* y_relu, const float* gamma,
+                const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta,
+                float* workspace, int64_t M, int C, int batch_stats, void* stream);
+/* out[c] = scale * sum_m x[m,c]  (conv bias gradient; deterministic two-stage reduction). */
+int amoe_colsum(amoe_ctx*, const float* x, float* out, float* workspace, int64_t M, int C,
+                float scale, void* stream);
+/* Convolution backward, NHWC fp32 (EasyBackbone convs): dx from dy and the packed weights
+ * [Cout][KH][KW][Cin]; dw in the same packed layout from dy and x (K split over output pixels, summed
+ * in a fixed order; workspace size from amoe_conv2d_bwd_weight_workspace_floats). */
+int amoe_conv2d_bwd_data(amoe_ctx*, const float* dy, const float* w, float* dx, int B, int H, int W,
+                         int Cin, int Cout, int KH, int KW, int stride_h, int stride_w, int pad_h,
+                         int pad_w, int Ho, int Wo, void* stream);
+int64_t amoe_conv2d_bwd_weight_workspace_floats(amoe_ctx*, int B, int Cin, int Cout, int KH, int KW,
+                                                int Ho, int Wo);
+int amoe_conv2d_bwd_weight(amoe_ctx*, const float* dy, const float* x, float* dw, float* workspace,
+                           int64_t workspace_floats, int B, int H, int W, int Cin, int Cout, int KH,
+                           int KW, int stride_h, int stride_w, int pad_h, int pad_w, int Ho, int Wo,
+                           void* stream);
+/* nn.AdaptiveAvgPool2d(1) on NHWC fp32: x [B,HW,C] -> out [B,C]; backward broadcasts dy/HW. */
+int amoe_gap_fwd(amoe_ctx*, const float* x, float* out, int B, int HW, int C, void* stream);
+int amoe_gap_bwd(amoe_ctx*, const float* dy, float* dx, int B, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ SIGNATURES = {
     "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
     "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 20 + [_P]),
     "amoe_conv3x3_flat_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P]),
+    "amoe_conv3x3_flat_fwd_strided": (_I, [_P] * 7 + [_I] * 7 + [C.c_int64, C.c_int64, _P]),
     "amoe_conv3x3_flat_supported": (_I, [_I] * 4),
     "amoe_conv2d_tc_supported": (_I, [_I] * 6),
     "amoe_maxpool3x3s2_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -51,6 +52,26 @@ SIGNATURES = {
     "amoe_policy_head_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "amoe_hungarian_cost_fwd": (_I, [_P] * 7 + [_I] * 5 + [_F] * 3 + [_P]),
     "amoe_lsap_batched_host": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I]),
+    # training step (gating + policy)
+    "amoe_linear_fwd": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, C.c_uint64, _P]),
+    "amoe_linear_bwd": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "amoe_layernorm_fwd": (_I, [_P] * 7 + [_I, _I, _F, _P]),
+    "amoe_layernorm_bwd": (_I, [_P] * 9 + [_I, _I, _P]),
+    "amoe_gate_combine_fwd": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _I, _I, _I, _P]),
+    "amoe_gate_combine_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P, _P, _L, _I, _I, _I, _P]),
+    "amoe_gating_loss_fwd_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, C.POINTER(_F), _I, _I, _P, _P, _P, _P, _P]),
+    "amoe_sq_norm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
+    "amoe_fused_clip_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P] + [_F] * 7 + [_I, _P]),
+    "amoe_colreduce_workspace_floats": (_L, [_L, _I]),
+    "amoe_bn_train_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "amoe_bn_apply_fwd": (_I, [_P] * 7 + [_L, _I, _I, _P]),
+    "amoe_bn_bwd": (_I, [_P] * 11 + [_L, _I, _I, _P]),
+    "amoe_colsum": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
+    "amoe_conv2d_bwd_data": (_I, [_P] * 4 + [_I] * 13 + [_P]),
+    "amoe_conv2d_bwd_weight_workspace_floats": (_L, [_P] + [_I] * 7),
+    "amoe_conv2d_bwd_weight": (_I, [_P] * 5 + [_L] + [_I] * 13 + [_P]),
+    "amoe_gap_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "amoe_gap_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 

@@ -155,14 +155,18 @@ def stem_pool_supported(H: int, W: int) -> bool:
     return H % 4 == 0 and W % 4 == 0 and W // 2 <= 128 and os.environ.get("AMOE_STEM_POOL", "1") != "0"
 
 
-def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int, n_pool: int, out_pad: int):
+def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int, n_pool: int, out_pad: int,
+                      pooled: Optional[torch.Tensor] = None, rest: Optional[List[torch.Tensor]] = None):
     """First n_pool packed convolutions (64 channels each: expert stems) come back max-pooled as one
-    [n_pool*B, H/4+2p, W/4+2p, 64] tensor; the remaining convolutions at full resolution (list)."""
+    [n_pool*B, H/4+2p, W/4+2p, 64] tensor; the remaining convolutions at full resolution (list).
+    `pooled` / `rest` may be preallocated destinations (sub-batch walks reuse them / write into slices)."""
     dev = x_pad.device
     Hp, Wp = H // 4, W // 4
     assert all(c == 64 for c in ps.couts[:n_pool])
-    pooled = torch.empty((n_pool * B, Hp + 2 * out_pad, Wp + 2 * out_pad, 64), device=dev, dtype=torch.bfloat16)
-    rest = [torch.empty((B, H // 2, W // 2, co), device=dev, dtype=torch.bfloat16) for co in ps.couts[n_pool:]]
+    if pooled is None:
+        pooled = torch.empty((n_pool * B, Hp + 2 * out_pad, Wp + 2 * out_pad, 64), device=dev, dtype=torch.bfloat16)
+    if rest is None:
+        rest = [torch.empty((B, H // 2, W // 2, co), device=dev, dtype=torch.bfloat16) for co in ps.couts[n_pool:]]
     n_chunks = ps.n_total // 32
     dst = (C.c_void_p * n_chunks)()
     dst_c = (C.c_int * n_chunks)()
@@ -217,6 +221,22 @@ def stem_mode(dtype: torch.dtype) -> str:
         return "simt"
     m = os.environ.get("AMOE_STEM", "tc")
     return m if m in ("tc", "rowwin", "simt") else "tc"
+
+
+def l2_chunk_images() -> int:
+    """Sub-batch (images per expert) for the L2-resident walk through stem + layer1; 0 disables.
+    Off by default: measured on B200 at batch 256 (CUDA-graph replay) chunks of 16/32/64 images gave
+    47.5k/48.2k/49.0k frames/s against 50.3k unchunked - the layer1 kernels are bound by shared-memory
+    bandwidth, not HBM, so L2 residency buys nothing and the shorter launches pay more tail.
+    AMOE_L2_CHUNK=<n> turns it on (kept for larger-L2 / lower-HBM parts and as a tested path)."""
+    import os
+    return int(os.environ.get("AMOE_L2_CHUNK", "0"))
+
+
+def overlap_outputs() -> bool:
+    """Fork the full-resolution logit writers onto a side stream (AMOE_OVERLAP=0 keeps one stream)."""
+    import os
+    return os.environ.get("AMOE_OVERLAP", "1") != "0"
 
 
 def use_rowwin(dtype: torch.dtype) -> bool:
@@ -423,15 +443,19 @@ def flat_supported(pc: PackedConv, H: int, W: int, dtype: torch.dtype) -> bool:
 
 
 def conv3x3_flat(pc: PackedConv, x_pad: torch.Tensor, B: int, H: int, W: int,
-                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x_pad: [G*B,H+2,W+2,Cin] bf16 with zero border -> [G*B,H+2,W+2,Cout] with zero border."""
-    y = torch.empty((pc.G * B, H + 2, W + 2, pc.cout), device=x_pad.device, dtype=x_pad.dtype)
+                 residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                 out_group_images: int = 0) -> torch.Tensor:
+    """x_pad: [G*B,H+2,W+2,Cin] bf16 with zero border -> [G*B,H+2,W+2,Cout] with zero border.
+    `out` (+ out_group_images): write the B images of every expert group into a larger grouped tensor
+    whose groups are out_group_images apart; `out` starts at this sub-batch's first image of group 0."""
+    y = out if out is not None else torch.empty((pc.G * B, H + 2, W + 2, pc.cout), device=x_pad.device, dtype=x_pad.dtype)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().amoe_conv3x3_flat_fwd(ctx(x_pad.device), ptr(x_pad), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual),
-                                      ptr(y), pc.G, B, H, W, pc.cin, pc.cout, int(pc.relu), stream_ptr(x_pad.device)),
+    check(lib().amoe_conv3x3_flat_fwd_strided(ctx(x_pad.device), ptr(x_pad), ptr(pc.w), ptr(pc.scale), ptr(pc.bias),
+                                              ptr(residual), ptr(y), pc.G, B, H, W, pc.cin, pc.cout, int(pc.relu),
+                                              int(out_group_images), 0, stream_ptr(x_pad.device)),
           "conv3x3_flat_fwd")
     if prof is not None:
         ev1.record()

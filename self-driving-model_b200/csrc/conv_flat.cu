@@ -14,9 +14,11 @@
 //
 // Per CTA (192 threads, persistent over the tiles of one expert group):
 //   warp 0: TMA producer (activation halo buffers; weight tiles unless they are smem-resident)
-//   warp 1: TMEM allocator + single-thread tcgen05.mma issuer: per tile 2 M-halves x 9 taps x
-//           C/64 chunks x 4 K-steps, two 128xN fp32 accumulators, double buffered (4N <= 512 cols)
-//   warps 2-5: epilogue: tcgen05.ld -> scale/bias (+residual) -> ReLU -> zero at borders -> bf16
+//   warps 1-2: tcgen05.mma issuers, one per M-half (warp 1 also owns the TMEM allocation): per tile
+//           9 taps x C/64 chunks x 4 K-steps each, two 128xN fp32 accumulators per half, double
+//           buffered (4N <= 512 cols)
+//   warps 3-6: epilogue: tcgen05.ld -> scale/bias (+residual) -> ReLU -> zero at borders -> bf16,
+//           transposed through swizzled staging rows to coalesced 16-byte stores
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,10 +29,10 @@ namespace flat {
 using namespace tc;
 
 constexpr int TILE_P = 256;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;  // warp 0 producer, warps 1-2 MMA issuers (one per M-half), warps 3-6 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;  // activation + weight stages (the epilogue staging rows come on top)
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_W_STAGES = 8;
 constexpr int W_RESIDENT_MAX = 80 * 1024;
@@ -40,14 +42,20 @@ struct Params {
   int chunks;            // C / 64
   int rows_pad;          // rows per activation buffer (multiple of 16, loaded as two TMA boxes)
   int a_stages, w_stages, w_resident;
+  uint32_t stg_off;      // byte offset of the epilogue staging rows behind the aligned smem base
   int tiles_per_group;   // ceil(B*Hp*Wp / TILE_P)
   int group_positions;   // B*Hp*Wp
   int relu;
+  int64_t y_group_elems, res_group_elems;  // element distance between the expert groups of y / residual
   const float* scale;
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
 };
+
+template <int N>
+__host__ __device__ constexpr int STG_BUFS() { return N == 64 ? 2 : 1; }
+constexpr int STG_BYTES = 4 * 32 * 128 * 2;  // 4 epilogue warps x 32 rows x 256 B (N=64: two 128-byte buffers)
 
 template <int N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -83,14 +91,14 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmW);
     for (int s = 0; s < MAX_A_STAGES; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
-      mbar_init(bar_aempty + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 2);   // both MMA issuers commit
     }
     for (int s = 0; s < MAX_W_STAGES; ++s) {
       mbar_init(bar_wfull + 8 * s, 1);
-      mbar_init(bar_wempty + 8 * s, 1);
+      mbar_init(bar_wempty + 8 * s, 2);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tfull + 8 * a, 2);
       mbar_init(bar_tempty + 8 * a, 4);
     }
     fence_barrier_init();
@@ -137,8 +145,15 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
+  } else if (warp <= 2) {
+    // ============================ MMA issuers =============================
+    // An N=64 MMA occupies the tensor pipe for 32 cycles, but computing its descriptors and moving
+    // them to uniform registers costs one warp ~19 issue slots, so the two M-halves of a tile are
+    // issued by two warps on different SM sub-partitions; each commits to the shared barriers itself.
+    // (Measured on B200: what then bounds the N=64 layers is shared-memory bandwidth - every
+    // 128x64x16 MMA reads 4 KB of A and 2 KB of B from smem, 432 KB per 256-position tile, ~4300
+    // cycles at 128 B/clk against 2304 cycles of tensor time; row-unaligned tap shifts cost nothing.)
+    const int half = warp - 1;
     const uint32_t idesc = make_idesc(N);
     int as = 0, ws = 0, it = 0;
     uint32_t aphase = 0, wphase = 0;
@@ -146,16 +161,18 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(bar_wfull, 0);
       tcgen05_fence_after();
     }
+    const uint32_t wp128 = (uint32_t)p.Wp * 128u;
     for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
       tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE + half * N);
       for (int chunk = 0; chunk < p.chunks; ++chunk) {
         mbar_wait(bar_afull + 8 * as, aphase);
         tcgen05_fence_after();
-        const uint32_t a_base = smem_a + (uint32_t)as * a_stage_bytes;
+        const uint32_t a_half = smem_a + (uint32_t)as * a_stage_bytes + (uint32_t)half * (BLOCK_M * 128u);
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           uint32_t w_addr;
           if (p.w_resident) {
@@ -165,21 +182,14 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_after();
             w_addr = smem_w + (uint32_t)ws * w_tile_bytes;
           }
-          {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t a_tap = a_base + (uint32_t)(kh * p.Wp + kw) * 128u;  // row shift of this tap
-            const uint64_t b_desc = make_sw128_desc(w_addr);
+          const uint64_t a_desc = make_sw128_desc(a_half + (uint32_t)(tap / 3) * wp128 + (uint32_t)(tap % 3) * 128u);  // row shift of this tap
+          const uint64_t b_desc = make_sw128_desc(w_addr);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint64_t a_desc = make_sw128_desc(a_tap + (uint32_t)half * (BLOCK_M * 128u));
-#pragma unroll
-              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                umma_bf16(d_tmem + (uint32_t)(half * N), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                          (uint32_t)((chunk | tap | kk) != 0));
-            }
-            if (!p.w_resident) umma_commit(bar_wempty + 8 * ws);
-          }
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                      (uint32_t)((chunk | tap | kk) != 0));
           if (!p.w_resident) {
+            umma_commit(bar_wempty + 8 * ws);
             if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
           }
         }
@@ -190,89 +200,135 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ============================ epilogue ================================
+    // TMEM hands every thread one output ROW (32 rows per warp); written straight to global that is
+    // 32 different 128-byte lines per store instruction, which costs more L1 cycles than the MMAs of
+    // an N=64 tile take.  So each warp transposes through its own swizzled staging rows in shared
+    // memory: residual rows arrive there by cp.async (issued before the accumulator is ready),
+    // every thread updates its row in place, and the warp then streams the 32 x N block - which is
+    // contiguous in the flattened [P][N] output - with fully coalesced 16-byte stores.
     const int lg = warp & 3;
     const int img = p.Hp * p.Wp;
-    constexpr int NV = N / 8;  // 16-byte pieces per output row
+    constexpr int NV = N / 8;            // 16-byte pieces per output row
+    constexpr int ROWB = N * 2;          // bytes per staged row
+    constexpr int BUFS = STG_BUFS<N>();  // staging buffers per warp (one per M-half when they fit)
+    uint8_t* stg_warp = smem_raw + (smem_base - smem_u32(smem_raw)) + p.stg_off + (uint32_t)(lg * BUFS) * (32u * ROWB);
+    const uint32_t stg_warp_s = smem_base + p.stg_off + (uint32_t)(lg * BUFS) * (32u * ROWB);
+    const bool has_res = p.residual != nullptr;
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      // geometry of this thread's two rows; pull the residual rows towards L2 while the MMAs of
-      // this tile are still running
-      bool valid[2], interior[2];
-      int64_t off[2];
+      bool interior[2];
+      int rows_valid[2];
+      int64_t off0[2], roff0[2];   // element offset of the warp's first row in y / in the residual
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int q = t * TILE_P + half * BLOCK_M + lg * 32 + lane;  // position inside the group
-        valid[half] = q < p.group_positions;
+        const int q0 = t * TILE_P + half * BLOCK_M + lg * 32;  // first position of this warp inside the group
+        const int q = q0 + lane;
+        rows_valid[half] = min(32, max(0, p.group_positions - q0));
         const int rem = q % img;
         const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
-        interior[half] = valid[half] && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-        off[half] = ((int64_t)group_row0 + q) * N;
-        if (p.residual && interior[half]) {
+        interior[half] = q < p.group_positions && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
+        off0[half] = (int64_t)g * p.y_group_elems + (int64_t)q0 * N;
+        roff0[half] = (int64_t)g * p.res_group_elems + (int64_t)q0 * N;
+      }
+      auto fetch_residual = [&](int half, int buf) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + roff0[half]);
 #pragma unroll
-          for (int l = 0; l < N * 2 / 128; ++l)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off[half] + l * 64));
+        for (int i = 0; i < NV; ++i) {
+          const int m = i * 32 + lane, row = m / NV, j = m - row * NV;
+          if (row < rows_valid[half]) {
+            const uint32_t dst = stg_warp_s + (uint32_t)buf * (32u * ROWB) + (uint32_t)row * ROWB +
+                                 (uint32_t)(((j & ~7) | ((j ^ row) & 7)) * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)m * 16) : "memory");
+          }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (has_res) {
+        fetch_residual(0, 0);
+        if (BUFS == 2) fetch_residual(1, 1);
       }
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        // residual row of this half into registers before touching TMEM (loads overlap tcgen05.ld)
-        uint4 rr[NV];
-        const bool use_res = p.residual != nullptr && interior[half];
-        if (use_res) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(p.residual + off[half]) + v);
+        const int buf = (BUFS == 2) ? half : 0;
+        uint8_t* my_row = stg_warp + (size_t)buf * (32u * ROWB) + (size_t)lane * ROWB;
+        if (has_res) {
+          if (BUFS == 1 && half == 1) fetch_residual(1, 0);
+          if (BUFS == 2 && half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * N);
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t a[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a);
+        for (int c0 = 0; c0 < N; c0 += 64) {
+          uint32_t a[2][32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a[0]);
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 32), a[1]);
           tmem_ld_wait();
-          if (valid[half]) {
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
-            const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + h * 32);
+            const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c0 + h * 32);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
+              const int j = (c0 >> 3) + h * 4 + v;   // logical 16-byte piece of the row
+              uint4* slot = reinterpret_cast<uint4*>(my_row + (((j & ~7) | ((j ^ lane) & 7)) * 16));
               uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
               if (interior[half]) {
                 const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
                 float f[8];
-                f[0] = fmaf(__uint_as_float(a[v * 8 + 0]), s0.x, b0.x);
-                f[1] = fmaf(__uint_as_float(a[v * 8 + 1]), s0.y, b0.y);
-                f[2] = fmaf(__uint_as_float(a[v * 8 + 2]), s0.z, b0.z);
-                f[3] = fmaf(__uint_as_float(a[v * 8 + 3]), s0.w, b0.w);
-                f[4] = fmaf(__uint_as_float(a[v * 8 + 4]), s1.x, b1.x);
-                f[5] = fmaf(__uint_as_float(a[v * 8 + 5]), s1.y, b1.y);
-                f[6] = fmaf(__uint_as_float(a[v * 8 + 6]), s1.z, b1.z);
-                f[7] = fmaf(__uint_as_float(a[v * 8 + 7]), s1.w, b1.w);
-                if (use_res) {
-                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[c0 / 8 + v]);
+                f[0] = fmaf(__uint_as_float(a[h][v * 8 + 0]), s0.x, b0.x);
+                f[1] = fmaf(__uint_as_float(a[h][v * 8 + 1]), s0.y, b0.y);
+                f[2] = fmaf(__uint_as_float(a[h][v * 8 + 2]), s0.z, b0.z);
+                f[3] = fmaf(__uint_as_float(a[h][v * 8 + 3]), s0.w, b0.w);
+                f[4] = fmaf(__uint_as_float(a[h][v * 8 + 4]), s1.x, b1.x);
+                f[5] = fmaf(__uint_as_float(a[h][v * 8 + 5]), s1.y, b1.y);
+                f[6] = fmaf(__uint_as_float(a[h][v * 8 + 6]), s1.z, b1.z);
+                f[7] = fmaf(__uint_as_float(a[h][v * 8 + 7]), s1.w, b1.w);
+                if (has_res) {
+                  const uint4 rr = *slot;
+                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 rf = __bfloat1622float2(r2[j]);
-                    f[2 * j] += rf.x;
-                    f[2 * j + 1] += rf.y;
+                  for (int jj = 0; jj < 4; ++jj) {
+                    float2 rf = __bfloat1622float2(r2[jj]);
+                    f[2 * jj] += rf.x;
+                    f[2 * jj + 1] += rf.y;
                   }
                 }
                 if (p.relu) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                  for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
                 }
                 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                                pack_bf16x2(f[6], f[7]));
               }
-              *reinterpret_cast<uint4*>(p.y + off[half] + c0 + v * 8) = o;
+              *slot = o;
             }
           }
         }
+        if (half == 1) {
+          // both halves of this accumulator are in registers/smem now: hand it back before the stores
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        } else {
+          __syncwarp();
+        }
+        // coalesced write-out of the warp's 32 x N block
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.y + off0[half]);
+        const uint8_t* blk = stg_warp + (size_t)buf * (32u * ROWB);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int m = i * 32 + lane, row = m / NV, j = m - row * NV;
+          if (row < rows_valid[half])
+            *reinterpret_cast<uint4*>(dst + (size_t)m * 16) =
+                *reinterpret_cast<const uint4*>(blk + (size_t)row * ROWB + (((j & ~7) | ((j ^ row) & 7)) * 16));
+        }
+        __syncwarp();   // staging rows may be overwritten (next half / next tile's residual)
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
     }
   }
 
@@ -293,9 +349,9 @@ static bool supported(int H, int W, int C, int N) {
 int amoe_conv_flat_init(amoe_ctx* ctx) {
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       flat::SMEM_BUDGET + 1024));
+                                       flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       flat::SMEM_BUDGET + 1024));
+                                       flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
   return 0;
 }
 
@@ -306,6 +362,12 @@ int amoe_conv3x3_flat_supported(int H, int W, int Cin, int Cout) { return flat::
 int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias,
                           const void* residual, void* y, int G, int B, int H, int W, int Cin, int Cout, int relu,
                           void* stream) {
+  return amoe_conv3x3_flat_fwd_strided(ctx, x, w, scale, bias, residual, y, G, B, H, W, Cin, Cout, relu, 0, 0, stream);
+}
+
+int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias,
+                                  const void* residual, void* y, int G, int B, int H, int W, int Cin, int Cout, int relu,
+                                  int64_t y_group_images, int64_t res_group_images, void* stream) {
   using namespace flat;
   AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv3x3_flat_fwd: NULL argument");
   AMOE_REQUIRE(flat::supported(H, W, Cin, Cout), "amoe_conv3x3_flat_fwd: unsupported shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
@@ -321,6 +383,8 @@ int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const flo
   p.group_positions = (int)gp;
   p.tiles_per_group = (int)((gp + TILE_P - 1) / TILE_P);
   p.relu = relu;
+  p.y_group_elems = (y_group_images > 0 ? y_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
+  p.res_group_elems = (res_group_images > 0 ? res_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
   p.scale = scale; p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
@@ -364,7 +428,8 @@ int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const flo
     AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_flat_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
   const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
-  const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + 1024;
+  p.stg_off = (uint32_t)(p.a_stages * a_stage + w_bytes);
+  const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + STG_BYTES + 1024;
   if (Cout == 64)
     conv3x3_flat_kernel<64><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
   else

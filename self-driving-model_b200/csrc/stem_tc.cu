@@ -214,12 +214,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_tc_kernel(const __grid_co
 // Variant with the ResNet max-pool (3x3, stride 2, pad 1) fused behind the stem: the first
 // n_pool_ch channels (expert stems) never reach HBM at full resolution.  A CTA owns a contiguous
 // range of POOLED rows and walks the conv rows they need in order (2py-1 once as "carry", then
-// 2py and 2py+1 for every pooled row).  Per conv row the epilogue warps write the BN+ReLU'd bf16
-// row into shared memory, take the horizontal 3-max at even columns, fold it into a running
-// vertical max V (values are >= 0 after ReLU, so 0 is the identity that stands for the pool's
-// -inf padding) and emit pooled row py after conv row 2py+1.  Remaining channels (policy conv1)
-// are stored at full resolution as in the plain kernel.
-constexpr int POOL_A_STAGES = 3;
+// 2py and 2py+1 for every pooled row); the pooling itself is described at the kernel.  Remaining
+// channels (policy conv1) are stored at full resolution as in the plain kernel.
+constexpr int POOL_A_STAGES = 4;
+constexpr int POOL_THREADS = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue + pooling
+constexpr int POOL_EPI_THREADS = 256;
 constexpr int R_PITCH = 400;  // bytes per pixel row of the staging buffer (192 ch * 2 B + pad: conflict-free 16-byte stores)
 
 struct PoolParams {
@@ -260,8 +259,48 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
   for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
   return r;
 }
+// two fp32 FMAs in one instruction (Blackwell fma.rn.f32x2; per-element IEEE, same bits as fmaf)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, uint32_t a0, uint32_t a1, float s0, float s1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 ra, rs, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rs, {%4, %5};\n"
+      "mov.b64 rb, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rs, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "r"(a0), "r"(a1), "f"(s0), "f"(s1), "f"(b0), "f"(b1));
+}
+// folded BN (+ optional ReLU) of 32 accumulator columns -> 4 x 8 packed bf16
+template <bool RELU>
+__device__ __forceinline__ void bn_pack32(const uint32_t (&a)[32], const float* s_scale, const float* s_bias, uint4 (&q)[4]) {
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+  const float4* bs4 = reinterpret_cast<const float4*>(s_bias);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+    float f[8];
+    ffma2(f[0], f[1], a[v * 8 + 0], a[v * 8 + 1], s0.x, s0.y, b0.x, b0.y);
+    ffma2(f[2], f[3], a[v * 8 + 2], a[v * 8 + 3], s0.z, s0.w, b0.z, b0.w);
+    ffma2(f[4], f[5], a[v * 8 + 4], a[v * 8 + 5], s1.x, s1.y, b1.x, b1.y);
+    ffma2(f[6], f[7], a[v * 8 + 6], a[v * 8 + 7], s1.z, s1.w, b1.z, b1.w);
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    q[v] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
+// Epilogue organisation: the eight epilogue warps form two groups; warps g*4+lq of both groups read
+// TMEM lane quarter lq (output pixels 32*lq..+31) and split the 32-channel chunks between them
+// (group 0: first half of the pooled chunks; group 1: second half + the full-resolution chunks).
+// The vertical 3-max runs first and entirely in registers: V (one packed bf16 row segment per owned
+// chunk) carries conv row 2py-1 into pooled row py, conv row 2py folds in, and conv row 2py+1 both
+// completes the pooled row and becomes the next carry.  Only the completed vertical max goes through
+// shared memory, once per POOLED row, for the horizontal 3-max at even columns.
+__global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
   const Params& p = pp.base;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * POOL_A_STAGES + 5];
@@ -276,14 +315,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
   const uint32_t smem_w = smem_base;
   const uint32_t smem_a = smem_base + w_bytes_al;
   uint8_t* sR = gen_base + w_bytes_al + (size_t)POOL_A_STAGES * p.a_stage_bytes;  // [128][R_PITCH]
-  uint8_t* sV = sR + 128 * R_PITCH;                                                // [Wp][n_pool_ch*2]
   const uint32_t bar_afull = smem_u32(&bars[0]);
   const uint32_t bar_aempty = smem_u32(&bars[POOL_A_STAGES]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * POOL_A_STAGES]);
   const uint32_t bar_tempty = smem_u32(&bars[2 * POOL_A_STAGES + 2]);
   const uint32_t bar_w = smem_u32(&bars[2 * POOL_A_STAGES + 4]);
 
-  for (int i = threadIdx.x; i < p.n_total; i += NUM_THREADS) {
+  for (int i = threadIdx.x; i < p.n_total; i += POOL_THREADS) {
     s_scale[i] = __ldg(p.scale + i);
     s_bias[i] = __ldg(p.bias + i);
   }
@@ -294,7 +332,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, 8);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -353,111 +391,116 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
     }
   } else {
     // ============================ epilogue + max-pool ============================
-    const int lg = warp & 3;
-    const int ow = lg * 32 + lane;
+    const int lq = warp & 3;                    // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;            // chunk group
+    const int ow = lq * 32 + lane;
     const bool valid = ow < p.Wo;
-    const int te = threadIdx.x - 64;            // 0..127 among the epilogue threads
+    const int te = threadIdx.x - 64;            // 0..255 among the epilogue threads
     const int n_chunks = p.n_total >> 5;
-    const int pool_chunks = pp.n_pool_ch >> 5;
+    const int pool_chunks = pp.n_pool_ch >> 5;  // <= 6
+    const int h0 = (pool_chunks + 1) >> 1;
+    const int c_begin = grp ? h0 : 0;
+    const int c_cnt = grp ? pool_chunks - h0 : h0;  // <= 3 pooled chunks owned by this warp
     const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
-    const int v_pitch = pp.n_pool_ch * 2;       // bytes per pixel of V
     const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
-    // the (pooled pixel, channel vector) items of this thread never change: hoist their index math
-    constexpr int MAX_ITEMS = 12;  // Wp*NV / 128 <= 64*24/128
-    int r_off[MAX_ITEMS], v_off[MAX_ITEMS];
-    int64_t g_off[MAX_ITEMS];
-    const int n_items = pp.Wp * NV;
+    // horizontal pass mapping: thread -> (pixel lane, channel vector v); a pass covers px_per_pass pooled
+    // pixels, so the per-pass offsets are plain multiples (no per-item tables, no spills)
+    const int px_per_pass = POOL_EPI_THREADS / NV;          // 32 / 16 / 10 for 1 / 2 / 3 experts
+    const int h_px0 = te / NV, h_v = te - h_px0 * NV;
+    const bool h_active = h_px0 < px_per_pass;
+    const int h_r0 = (2 * h_px0) * R_PITCH + h_v * 16;
+    const int64_t h_g0 = ((int64_t)(h_v >> 3) * p.B * Hq * Wq + h_px0 + pp.out_pad) * 64 + (h_v & 7) * 8;
+    const int h_rstep = 2 * px_per_pass * R_PITCH, h_gstep = px_per_pass * 64;
+    uint4 V[3][4];  // running vertical max of the owned chunks (registers)
 #pragma unroll
-    for (int i = 0; i < MAX_ITEMS; ++i) {
-      const int item = te + 128 * i;
-      const int px = item / NV, v = item - px * NV, e = v >> 3, cv = v & 7;
-      r_off[i] = (2 * px) * R_PITCH + v * 16;
-      v_off[i] = px * v_pitch + v * 16;
-      g_off[i] = ((int64_t)e * p.B * Hq * Wq + px + pp.out_pad) * 64 + cv * 8;
-    }
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) V[ci][v] = make_uint4(0u, 0u, 0u, 0u);
+
     for (int k = 0; k < seq.n_tiles; ++k) {
       const int acc = k & 1;
       const uint32_t tphase = (uint32_t)(k >> 1) & 1u;
       int b, py, oh, role;
       tile_at(seq, k, pp.Hp, b, py, oh, role);
-      const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
+      const bool fresh = role == ROLE_CARRY || (role == ROLE_EVEN && py == 0);  // nothing above: top padding / range start
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t a[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
-        tmem_ld_wait();
-        if (valid && (c < pool_chunks || role != ROLE_CARRY)) {
-          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
-          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      if (role == ROLE_ODD) asm volatile("bar.sync 1, 256;" ::: "memory");  // previous horizontal pass has left sR
+      uint32_t a[32];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
-            float f[8];
-            f[0] = fmaf(__uint_as_float(a[v * 8 + 0]), s0.x, b0.x);
-            f[1] = fmaf(__uint_as_float(a[v * 8 + 1]), s0.y, b0.y);
-            f[2] = fmaf(__uint_as_float(a[v * 8 + 2]), s0.z, b0.z);
-            f[3] = fmaf(__uint_as_float(a[v * 8 + 3]), s0.w, b0.w);
-            f[4] = fmaf(__uint_as_float(a[v * 8 + 4]), s1.x, b1.x);
-            f[5] = fmaf(__uint_as_float(a[v * 8 + 5]), s1.y, b1.y);
-            f[6] = fmaf(__uint_as_float(a[v * 8 + 6]), s1.z, b1.z);
-            f[7] = fmaf(__uint_as_float(a[v * 8 + 7]), s1.w, b1.w);
-            if (p.relu) {
+      for (int ci = 0; ci < 3; ++ci) {
+        if (ci < c_cnt) {
+          const int c = c_begin + ci;
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+          tmem_ld_wait();
+          uint4 q[4];
+          bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);   // ReLU commutes with max: applied once after pooling
+          if (fresh) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int v = 0; v < 4; ++v) V[ci][v] = q[v];
+          } else if (role == ROLE_EVEN) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) V[ci][v] = hmax8(V[ci][v], q[v]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q[v]);
+              V[ci][v] = q[v];   // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
             }
-            const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                       pack_bf16x2(f[6], f[7]));
-            if (c < pool_chunks)
-              *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = o;
-            else  // not pooled (policy conv1): full-resolution store; a carry row belongs to another CTA's range
-              *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = o;
+          }
+        }
+      }
+      if (grp == 1) {
+        // not pooled (policy conv1): full-resolution store; a carry row belongs to another CTA's range
+        const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
+        for (int c = pool_chunks; c < n_chunks; ++c) {
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+          tmem_ld_wait();
+          if (valid && role != ROLE_CARRY) {
+            uint4 q[4];
+            if (p.relu) bn_pack32<true>(a, s_scale + c * 32, s_bias + c * 32, q);
+            else bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = q[v];
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // staged conv row complete
-      // horizontal 3-max at even columns, folded into the running vertical max
-      const int64_t g_row = ((int64_t)b * Hq + py + pp.out_pad) * Wq * 64;
-      const bool first_row = role == ROLE_CARRY || (role == ROLE_EVEN && py == 0);
-#pragma unroll
-      for (int i = 0; i < MAX_ITEMS; ++i) {
-        if (te + 128 * i < n_items) {
-          const uint8_t* r0 = sR + r_off[i];
+      if (role != ROLE_ODD) continue;
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // vertical max of pooled row py staged
+      // horizontal 3-max at even columns, then the ReLU (max with 0 on the packed bf16 pairs)
+      if (h_active) {
+        __nv_bfloat16* g = pp.pooled + ((int64_t)b * Hq + py + pp.out_pad) * Wq * 64 + h_g0;
+        const uint8_t* r0 = sR + h_r0;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 2
+        for (int px = h_px0; px < pp.Wp; px += px_per_pass, r0 += h_rstep, g += h_gstep) {
           uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
-          if (r_off[i] >= 2 * R_PITCH) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));   // px > 0
-          uint4* vp = reinterpret_cast<uint4*>(sV + v_off[i]);
-          if (first_row) {
-            *vp = m;                                  // first conv row of this pooled row (top padding above)
-          } else if (role == ROLE_EVEN) {
-            *vp = hmax8(*vp, m);
-          } else {
-            const uint4 out = hmax8(*vp, m);
-            *vp = m;                                  // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
-            *reinterpret_cast<uint4*>(pp.pooled + g_row + g_off[i]) = out;
-          }
+          if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
+          if (p.relu) m = hmax8(m, zero);
+          *reinterpret_cast<uint4*>(g) = m;
         }
       }
-      if (role == ROLE_ODD && pp.out_pad) {
+      if (pp.out_pad) {
         // zero border of the padded pooled tensor: left/right pixel of this row, plus the rows above/below the image
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int item = te; item < 2 * NV; item += 128) {
+        for (int item = te; item < 2 * NV; item += POOL_EPI_THREADS) {
           const int side = item / NV, v = item - side * NV, e = v >> 3, cv = v & 7;
           __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + 1) * Wq + (side ? Wq - 1 : 0)) * 64 + cv * 8;
           *reinterpret_cast<uint4*>(d) = z;
         }
         if (py == 0 || py == pp.Hp - 1) {
           const int row = (py == 0) ? 0 : Hq - 1;
-          for (int item = te; item < Wq * NV; item += 128) {
+          for (int item = te; item < Wq * NV; item += POOL_EPI_THREADS) {
             const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
             __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + row) * Wq + x) * 64 + cv * 8;
             *reinterpret_cast<uint4*>(d) = z;
           }
           if (pp.Hp == 1) {  // single pooled row: both borders
-            for (int item = te; item < Wq * NV; item += 128) {
+            for (int item = te; item < Wq * NV; item += POOL_EPI_THREADS) {
               const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
               __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + Hq - 1) * Wq + x) * 64 + cv * 8;
               *reinterpret_cast<uint4*>(d) = z;
@@ -465,7 +508,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_pool_kernel(const __grid_
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer free for the next conv row
     }
   }
 
@@ -510,10 +552,10 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
   const int p_total = B * pp.Hp;
   if (p_total == 0) return 0;
   const size_t smem = ((size_t)pp.base.w_bytes + 127) / 128 * 128 + (size_t)POOL_A_STAGES * pp.base.a_stage_bytes +
-                      (size_t)128 * R_PITCH + (size_t)pp.Wp * n_pool_ch * 2 + 256;
+                      (size_t)128 * R_PITCH + 256;
   AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
-  stem_pool_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(pp);
+  stem_pool_kernel<<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -1,0 +1,486 @@
+// Training-step kernels of the policy backbone (EasyBackbone, models/policy/trajectory_head.py:5-33):
+// train-mode BatchNorm2d (batch statistics, running-stat update) forward/backward, convolution
+// backward (data and weight gradients) and global-average-pool forward/backward.  fp32, NHWC, CUDA
+// cores: four small stride-2 convolutions at a per-GPU batch of 32; the forward
+// convolution itself is amoe_conv2d_fwd(dtype = f32).
+//
+// All reductions are two-stage with a fixed summation order, so a training step is bit-reproducible.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RED_THREADS = 256;
+constexpr int RED_ROWS = 1024;  // rows of [M, C] per CTA of the column reductions
+
+// Column sums of up to two per-element quantities over the rows of an [M, C] fp32 matrix.
+//   MODE 0: s0 = sum x,           s1 = sum x*x                       (BatchNorm statistics)
+//   MODE 1: s0 = sum g,           s1 = sum g * (x - mean) * rstd      (BatchNorm backward)
+//           with g = dy * [y > 0] when y != nullptr (ReLU fused behind the norm) else dy
+//   MODE 2: s0 = sum x                                                (bias gradient / pooling)
+// partial: [gridDim.x][2][C]
+template <int MODE>
+__global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ dy,
+                                                                        const float* __restrict__ y,
+                                                                        const float* __restrict__ mean,
+                                                                        const float* __restrict__ rstd, int64_t M, int C,
+                                                                        float* __restrict__ partial) {
+  __shared__ float sh0[RED_THREADS], sh1[RED_THREADS];
+  const int cb = min(C, RED_THREADS);          // channels handled per pass (C is a multiple of cb or < 256)
+  const int rl = threadIdx.x / cb, nrl = RED_THREADS / cb;
+  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS, r1 = min(M, r0 + RED_ROWS);
+  for (int c0 = 0; c0 < C; c0 += cb) {
+    const int c = c0 + threadIdx.x % cb;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C && rl < nrl) {
+      const float mu = MODE == 1 ? mean[c] : 0.f, rs = MODE == 1 ? rstd[c] : 0.f;
+      for (int64_t r = r0 + rl; r < r1; r += nrl) {
+        const int64_t i = r * C + c;
+        if (MODE == 0) {
+          const float v = x[i];
+          s0 += v;
+          s1 = fmaf(v, v, s1);
+        } else if (MODE == 1) {
+          float g = dy[i];
+          if (y && !(y[i] > 0.f)) g = 0.f;
+          s0 += g;
+          s1 = fmaf(g, (x[i] - mu) * rs, s1);
+        } else {
+          s0 += x[i];
+        }
+      }
+    }
+    sh0[threadIdx.x] = s0;
+    sh1[threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < cb && c < C) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int j = 0; j < nrl; ++j) {      // fixed order
+        t0 += sh0[j * cb + threadIdx.x];
+        t1 += sh1[j * cb + threadIdx.x];
+      }
+      partial[((int64_t)blockIdx.x * 2 + 0) * C + c] = t0;
+      partial[((int64_t)blockIdx.x * 2 + 1) * C + c] = t1;
+    }
+    __syncthreads();
+  }
+}
+
+// BatchNorm statistics from the partial sums: mean, rstd (biased variance), running-stat update
+// (momentum; running_var gets the unbiased variance, as nn.BatchNorm2d does).
+__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int64_t M, int C, float eps,
+                                      float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
+    ss += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  const double mu = s / (double)M;
+  double var = ss / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+// out0[c] = sum of partial s0, out1[c] = sum of partial s1 (either may be NULL); scale applied
+__global__ void colreduce_final_kernel(const float* __restrict__ partial, int nblk, int C, float scale,
+                                       float* __restrict__ out0, float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, t = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
+    t += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  if (out0) out0[c] = (float)s * scale;
+  if (out1) out1[c] = (float)t * scale;
+}
+
+// y = act((x - mean[c]) * rstd[c] * gamma[c] + beta[c])
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                                int64_t n4, int C, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % C);
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[j] = (o[j] - mean[c + j]) * rstd[c + j] * gamma[c + j] + beta[c + j];
+    if (relu) o[j] = fmaxf(o[j], 0.f);
+  }
+  reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+// train: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M);  eval (batch_stats = 0): dx = gamma*rstd*g
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sum_g,
+                                    const float* __restrict__ sum_gx, float* __restrict__ dx, int64_t n4, int C,
+                                    float inv_M, int batch_stats) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % C);
+  const float4 d4 = reinterpret_cast<const float4*>(dy)[i];
+  const float4 x4 = reinterpret_cast<const float4*>(x)[i];
+  float g[4] = {d4.x, d4.y, d4.z, d4.w};
+  const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+  if (y) {
+    const float4 y4 = reinterpret_cast<const float4*>(y)[i];
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (!(yv[j] > 0.f)) g[j] = 0.f;
+  }
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float k = gamma[c + j] * rstd[c + j];
+    if (batch_stats) {
+      const float xh = (xv[j] - mean[c + j]) * rstd[c + j];
+      o[j] = k * (g[j] - sum_g[c + j] * inv_M - xh * sum_gx[c + j] * inv_M);
+    } else {
+      o[j] = k * g[j];
+    }
+  }
+  reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Convolution backward, NHWC fp32, implicit GEMMs on 64x64x16 tiles (4x4 outputs per thread).
+struct ConvBwdParams {
+  const float* dy;   // [B,Ho,Wo,Cout]
+  const float* x;    // [B,H,W,Cin]            (weight gradient)
+  const float* w;    // [Cout][KH][KW][Cin]     (data gradient)
+  float* out;        // dx [B,H,W,Cin]  or  partial dW [S][Cout][KH*KW*Cin]
+  int B, H, W, Cin, Cout, KH, KW, sh, sw, ph, pw, Ho, Wo;
+  int rows_per_slice;  // weight gradient: output pixels per K slice
+};
+constexpr int TBM = 64, TBN = 64, TBK = 16;
+
+// dx[m=(n,ih,iw), ci] = sum_{kh,kw,co} dy[n, (ih+ph-kh)/sh, (iw+pw-kw)/sw, co] * w[co,kh,kw,ci]
+__global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
+  __shared__ float As[TBK][TBM + 4];
+  __shared__ float Bs[TBK][TBN + 4];
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int Ktot = p.KH * p.KW * p.Cout;   // reduction index k = tap*Cout + co
+  const int Kw = p.KH * p.KW * p.Cin;      // row length of the packed weights
+  const int64_t m0 = (int64_t)blockIdx.x * TBM;
+  const int n0 = blockIdx.y * TBN;
+  const int tid = threadIdx.x, lrow = tid >> 2, lk = (tid & 3) << 2, ty = tid >> 4, tx = tid & 15;
+  const int64_t m = m0 + lrow;
+  const bool m_ok = m < M;
+  int n_img = 0, ih = 0, iw = 0;
+  if (m_ok) {
+    n_img = (int)(m / ((int64_t)p.H * p.W));
+    const int r = (int)(m - (int64_t)n_img * p.H * p.W);
+    ih = r / p.W;
+    iw = r - ih * p.W;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < Ktot; k0 += TBK) {
+    // A: this thread's pixel, 4 consecutive k (same tap: Cout % 4 == 0)
+    {
+      const int k = k0 + lk;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m_ok && k < Ktot) {
+        const int tap = k / p.Cout, co = k - tap * p.Cout;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        const int th = ih + p.ph - kh, tw = iw + p.pw - kw;
+        if (th >= 0 && tw >= 0 && th % p.sh == 0 && tw % p.sw == 0) {
+          const int oh = th / p.sh, ow = tw / p.sw;
+          if (oh < p.Ho && ow < p.Wo)
+            a = *reinterpret_cast<const float4*>(p.dy + (((int64_t)n_img * p.Ho + oh) * p.Wo + ow) * p.Cout + co);
+        }
+      }
+      As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
+    }
+    // B: 16 k x 64 ci; element (k, ci) = w[co][tap][ci]; consecutive threads walk ci
+    for (int e = tid; e < TBK * TBN; e += 256) {
+      const int kk = e / TBN, c = e - kk * TBN;
+      const int k = k0 + kk, ci = n0 + c;
+      float v = 0.f;
+      if (k < Ktot && ci < p.Cin) {
+        const int tap = k / p.Cout, co = k - tap * p.Cout;
+        v = p.w[(int64_t)co * Kw + tap * p.Cin + ci];
+      }
+      Bs[kk][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = n0 + tx * 4 + j;
+      if (ci < p.Cin) p.out[mm * p.Cin + ci] = acc[i][j];
+    }
+  }
+}
+
+// partial dW[s][co][k=(kh,kw,ci)] = sum over the output pixels of slice s of dy[pix,co] * x[window(pix,k)]
+__global__ __launch_bounds__(256) void conv_bwd_weight_kernel(ConvBwdParams p) {
+  __shared__ float As[TBK][TBM + 4];   // [pixel][co]
+  __shared__ float Bs[TBK][TBN + 4];   // [pixel][k]
+  const int Kw = p.KH * p.KW * p.Cin;
+  const int64_t Mg = (int64_t)p.B * p.Ho * p.Wo;
+  const int co0 = blockIdx.x * TBM, k0 = blockIdx.y * TBN, s = blockIdx.z;
+  const int64_t r0 = (int64_t)s * p.rows_per_slice, r1 = min(Mg, r0 + p.rows_per_slice);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += TBK) {
+    for (int e = tid; e < TBK * TBM; e += 256) {
+      const int rr = e / TBM, c = e - rr * TBM;
+      const int64_t r = rb + rr;
+      const int co = co0 + c;
+      As[rr][c] = (r < r1 && co < p.Cout) ? p.dy[r * p.Cout + co] : 0.f;
+    }
+    for (int e = tid; e < TBK * TBN; e += 256) {
+      const int rr = e / TBN, c = e - rr * TBN;
+      const int64_t r = rb + rr;
+      const int k = k0 + c;
+      float v = 0.f;
+      if (r < r1 && k < Kw) {
+        const int n_img = (int)(r / ((int64_t)p.Ho * p.Wo));
+        const int rem = (int)(r - (int64_t)n_img * p.Ho * p.Wo);
+        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        const int ih = oh * p.sh - p.ph + kh, iw = ow * p.sw - p.pw + kw;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[(((int64_t)n_img * p.H + ih) * p.W + iw) * p.Cin + ci];
+      }
+      Bs[rr][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = p.out + (int64_t)s * p.Cout * Kw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < Kw) out[(int64_t)co * Kw + k] = acc[i][j];
+    }
+  }
+}
+__global__ void slice_sum_kernel(const float* __restrict__ partial, int S, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+// global average pool over HW: x [B,HW,C] -> out [B,C]; backward broadcasts dy/HW
+__global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < HW; ++i) s += x[((int64_t)b * HW + i) * C + c];
+    out[(int64_t)b * C + c] = s / (float)HW;
+  }
+}
+__global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int HW, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const int64_t b = i / ((int64_t)HW * C);
+  dx[i] = dy[b * C + c] / (float)HW;
+}
+
+int wgrad_slices(int sm_count, int Cout, int Kw, int64_t Mg, int* rows_per_slice) {
+  const int tiles = ceil_div(Cout, TBM) * ceil_div(Kw, TBN);
+  int S = std::max(1, (4 * sm_count) / tiles);
+  const int64_t max_s = std::max<int64_t>(1, Mg / 256);   // at least 256 pixels per slice
+  S = (int)std::min<int64_t>(S, max_s);
+  int rps = (int)((Mg + S - 1) / S);
+  rps = (rps + TBK - 1) / TBK * TBK;
+  S = (int)((Mg + rps - 1) / rps);
+  *rows_per_slice = rps;
+  return S;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { return ((M + RED_ROWS - 1) / RED_ROWS) * 2 * (int64_t)C; }
+
+int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float momentum, float eps, float* y, float* save_mean, float* save_rstd,
+                      float* workspace, int64_t M, int C, int relu, void* stream) {
+  AMOE_REQUIRE(ctx && x && gamma && beta && y && save_mean && save_rstd && workspace, "amoe_bn_train_fwd: NULL argument");
+  AMOE_REQUIRE(C % 4 == 0 && (C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0),
+               "amoe_bn_train_fwd: C=%d must divide or be a multiple of 256 (and of 4)", C);
+  AMOE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "amoe_bn_train_fwd: running stats come together");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
+  colreduce_partial_kernel<0><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, workspace);
+  AMOE_LAUNCH_OK(ctx);
+  bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, M, C, eps, momentum, save_mean, save_rstd,
+                                                        running_mean, running_var);
+  AMOE_LAUNCH_OK(ctx);
+  const int64_t n4 = M * C / 4;
+  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, save_mean, save_rstd, gamma, beta, y, n4, C, relu);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_bn_apply_fwd(amoe_ctx* ctx, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, float* y, int64_t M, int C, int relu, void* stream) {
+  AMOE_REQUIRE(ctx && x && mean && rstd && gamma && beta && y, "amoe_bn_apply_fwd: NULL argument");
+  AMOE_REQUIRE(C % 4 == 0, "amoe_bn_apply_fwd: C=%d must be a multiple of 4", C);
+  if (M == 0) return 0;
+  const int64_t n4 = M * C / 4;
+  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, gamma, beta, y, n4, C, relu);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_relu, const float* gamma, const float* mean,
+                const float* rstd, float* dx, float* dgamma, float* dbeta, float* workspace, int64_t M, int C,
+                int batch_stats, void* stream) {
+  AMOE_REQUIRE(ctx && dy && x && gamma && mean && rstd && dgamma && dbeta && workspace, "amoe_bn_bwd: NULL argument");
+  AMOE_REQUIRE(C % 4 == 0 && (C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0),
+               "amoe_bn_bwd: C=%d must divide or be a multiple of 256 (and of 4)", C);
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
+  colreduce_partial_kernel<1><<<nblk, RED_THREADS, 0, st>>>(x, dy, y_relu, mean, rstd, M, C, workspace);
+  AMOE_LAUNCH_OK(ctx);
+  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, C, 1.f, dbeta, dgamma);
+  AMOE_LAUNCH_OK(ctx);
+  if (dx) {
+    const int64_t n4 = M * C / 4;
+    bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dy, x, y_relu, mean, rstd, gamma, dbeta, dgamma, dx, n4,
+                                                                    C, 1.f / (float)M, batch_stats);
+    AMOE_LAUNCH_OK(ctx);
+  }
+  return 0;
+}
+
+int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int64_t M, int C, float scale, void* stream) {
+  AMOE_REQUIRE(ctx && x && out && workspace, "amoe_colsum: NULL argument");
+  AMOE_REQUIRE(C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0, "amoe_colsum: C=%d must divide or be a multiple of 256", C);
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
+  colreduce_partial_kernel<2><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, workspace);
+  AMOE_LAUNCH_OK(ctx);
+  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, C, scale, out, nullptr);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_conv2d_bwd_data(amoe_ctx* ctx, const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
+                         int KH, int KW, int stride_h, int stride_w, int pad_h, int pad_w, int Ho, int Wo, void* stream) {
+  AMOE_REQUIRE(ctx && dy && w && dx, "amoe_conv2d_bwd_data: NULL argument");
+  AMOE_REQUIRE(Cout % 4 == 0, "amoe_conv2d_bwd_data: Cout=%d must be a multiple of 4", Cout);
+  if (B == 0) return 0;
+  ConvBwdParams p;
+  p.dy = dy; p.x = nullptr; p.w = w; p.out = dx;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.sh = stride_h; p.sw = stride_w;
+  p.ph = pad_h; p.pw = pad_w; p.Ho = Ho; p.Wo = Wo; p.rows_per_slice = 0;
+  const int64_t M = (int64_t)B * H * W;
+  dim3 grid((unsigned)((M + TBM - 1) / TBM), ceil_div(Cin, TBN));
+  conv_bwd_data_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int64_t amoe_conv2d_bwd_weight_workspace_floats(amoe_ctx* ctx, int B, int Cin, int Cout, int KH, int KW, int Ho, int Wo) {
+  if (!ctx) return -1;
+  int rps;
+  const int S = wgrad_slices(ctx->sm_count, Cout, KH * KW * Cin, (int64_t)B * Ho * Wo, &rps);
+  return (int64_t)S * Cout * KH * KW * Cin;
+}
+
+int amoe_conv2d_bwd_weight(amoe_ctx* ctx, const float* dy, const float* x, float* dw, float* workspace,
+                           int64_t workspace_floats, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride_h,
+                           int stride_w, int pad_h, int pad_w, int Ho, int Wo, void* stream) {
+  AMOE_REQUIRE(ctx && dy && x && dw && workspace, "amoe_conv2d_bwd_weight: NULL argument");
+  if (B == 0) return 0;
+  ConvBwdParams p;
+  p.dy = dy; p.x = x; p.w = nullptr; p.out = workspace;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.sh = stride_h; p.sw = stride_w;
+  p.ph = pad_h; p.pw = pad_w; p.Ho = Ho; p.Wo = Wo;
+  const int Kw = KH * KW * Cin;
+  const int S = wgrad_slices(ctx->sm_count, Cout, Kw, (int64_t)B * Ho * Wo, &p.rows_per_slice);
+  AMOE_REQUIRE(workspace_floats >= (int64_t)S * Cout * Kw, "amoe_conv2d_bwd_weight: workspace holds %lld floats, %lld needed",
+               (long long)workspace_floats, (long long)S * Cout * Kw);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(ceil_div(Cout, TBM), ceil_div(Kw, TBN), S);
+  conv_bwd_weight_kernel<<<grid, 256, 0, st>>>(p);
+  AMOE_LAUNCH_OK(ctx);
+  const int64_t n = (int64_t)Cout * Kw;
+  slice_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, S, n, dw);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_gap_fwd(amoe_ctx* ctx, const float* x, float* out, int B, int HW, int C, void* stream) {
+  AMOE_REQUIRE(ctx && x && out, "amoe_gap_fwd: NULL argument");
+  if (B == 0) return 0;
+  gap_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, HW, C);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_gap_bwd(amoe_ctx* ctx, const float* dy, float* dx, int B, int HW, int C, void* stream) {
+  AMOE_REQUIRE(ctx && dy && dx, "amoe_gap_bwd: NULL argument");
+  if (B == 0) return 0;
+  const int64_t n = (int64_t)B * HW * C;
+  gap_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, n, HW, C);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // extern "C"

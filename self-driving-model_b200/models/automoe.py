@@ -24,7 +24,8 @@ from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
 from .experts._base import get_trunk_pack, run_experts
-from .experts._trunk import params_stamp, stage_image, trunk_pool_pad
+from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, stage_image,
+                             trunk_pool_pad)
 from .experts.expert_extractors import create_expert_extractors
 from .gating.gating_network import GatingNetwork
 from .policy.trajectory_head import TrajectoryPolicy
@@ -159,14 +160,18 @@ class AutoMoE(nn.Module):
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
         x_nhwc = stage_image(image, dtype)
-        stem_out = pol1 = pooled = None
+        stem_out = pol1 = pooled = layer1 = None
         if _ops.stem_mode(dtype) == "tc":
             # experts' stems + policy conv1 read the same frame: one GEMM with N = 3*64 + 32
             # (+ the experts' max-pool fused behind it when the geometry allows)
             fs = self._fused_stem(image.device)
             Bn, Hn, Wn = image.shape[0], image.shape[2], image.shape[3]
-            if _ops.stem_pool_supported(Hn, Wn):
-                tp = get_trunk_pack(list(self.experts), dtype, image.device, self._expert_packs)
+            tp = get_trunk_pack(list(self.experts), dtype, image.device, self._expert_packs)
+            if chunked_stem_layer1_supported(tp, Bn, Hn, Wn):
+                # stem+pool and layer1 walk the batch in L2-resident chunks (policy conv1 rides along)
+                pol1 = torch.empty((Bn, Hn // 2, Wn // 2, fs.couts[-1]), device=image.device, dtype=torch.bfloat16)
+                layer1 = run_stem_layer1_chunked(tp, fs, x_nhwc, Bn, Hn, Wn, rest_out=[pol1])
+            elif _ops.stem_pool_supported(Hn, Wn):
                 pooled, rest = _ops.stem_pool_forward(fs, x_nhwc, Bn, Hn, Wn, len(self.experts),
                                                       trunk_pool_pad(tp, Hn, Wn))
                 pol1 = rest[0]
@@ -174,13 +179,16 @@ class AutoMoE(nn.Module):
                 stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, Bn, Hn, Wn, groups=[len(self.experts), 1])
 
         expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
-                                          stem_out=stem_out, stem_pooled=pooled)
+                                          stem_out=stem_out, stem_pooled=pooled, layer1_out=layer1,
+                                          overlap_outputs=_ops.overlap_outputs())
 
         gn = self.gating_network
         g = _ops.gate(state, aux['pooled'], self._gate_params(image.device, aux['n_ch']), aux['n_ch'],
                       self.context_extractor.context_dim, gn.hidden_dim, gn.temperature)
 
         policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)
+        if aux.get('join') is not None:      # full-resolution logits were written on the side stream
+            torch.cuda.current_stream(image.device).wait_stream(aux['join'])
         speed_seq = policy_output.get('speed')
         speed_out = None
         if speed_seq is not None and speed_seq.dim() == 2:
@@ -196,6 +204,18 @@ class AutoMoE(nn.Module):
             'combined_features': g['combined'],
             'gate_logits': g['gate_logits'],
         }
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, batch: Dict[str, torch.Tensor], autocast_dtype=torch.bfloat16,
+                clone_inputs: bool = True) -> "GraphedForward":
+        """Capture forward(batch) into a CUDA graph on static copies of the inputs (fixed shapes).
+
+        The forward is ~35 launches at batch 256 and ~70 when stem+layer1 walk the batch in L2-sized
+        chunks; replaying a graph removes the per-launch host cost (ctypes + allocator), so short
+        kernels queue back to back.  Weights are baked in as packed at capture time: re-capture after
+        an optimizer step / load_state_dict.  clone_inputs=False captures on the given tensors
+        themselves: the caller refills those buffers in place and calls the result without arguments."""
+        return GraphedForward(self, batch, autocast_dtype, clone_inputs)
 
     def get_expert_weights(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Get expert weights without running experts (for analysis)"""
@@ -227,6 +247,43 @@ class AutoMoE(nn.Module):
         for expert in self.experts:
             for param in expert.parameters():
                 param.requires_grad = True
+
+
+class GraphedForward:
+    """Replayable CUDA graph of AutoMoE.forward on fixed input shapes (see AutoMoE.capture)."""
+
+    def __init__(self, model: AutoMoE, batch: Dict[str, torch.Tensor], autocast_dtype=torch.bfloat16,
+                 clone_inputs: bool = True):
+        from .. import _cabi
+        dev = batch['image'].device
+        self.static_in = {k: (v.clone() if clone_inputs else v) for k, v in batch.items() if torch.is_tensor(v)}
+        self.autocast_dtype = autocast_dtype
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm), torch.no_grad():      # packs + allocator warm before capture
+            for _ in range(2):
+                self._run(model)
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _cabi.launch_count(dev)
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = self._run(model)
+        self.launches_per_replay = _cabi.launch_count(dev) - n0
+
+    def _run(self, model):
+        if self.autocast_dtype is None:
+            return model(self.static_in)
+        with torch.autocast("cuda", dtype=self.autocast_dtype):
+            return model(self.static_in)
+
+    def __call__(self, batch: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Copy `batch` into the static inputs (if given), replay, return the static outputs."""
+        if batch is not None:
+            for k, v in self.static_in.items():
+                v.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
 
 def create_automoe_model(config: Dict, device: str = 'cuda') -> AutoMoE:

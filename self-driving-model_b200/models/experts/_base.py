@@ -56,24 +56,63 @@ def get_trunk_pack(experts, dtype, device, cache: dict) -> TrunkPack:
     return pack
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that overlaps the gate/policy tail of the forward."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = s
+    return s
+
+
+def _tensors_of(out):
+    if isinstance(out, dict):
+        return [t for t in out.values() if torch.is_tensor(t)]
+    return [out] if torch.is_tensor(out) else []
+
+
 def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None,
-                stem_out=None, stem_pooled=None):
+                stem_out=None, stem_pooled=None, layer1_out=None, overlap_outputs: bool = False):
     """Run G experts on the same image batch in grouped launches.
 
     Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
     models/automoe.py:156-187 (_run_experts) + the pooled statistics the extractors need.
+
+    overlap_outputs: the x32 bilinear writers of the segmentation/drivable logits (HBM-bound, nothing
+    downstream inside the forward reads them) are forked onto a side stream so the latency-bound gate and
+    policy-head kernels run beside them; the caller must join with aux['join'] (main.wait_stream) before
+    returning the outputs.
     """
     if not image.is_cuda:
         raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
     _check_eval(experts)
     pack = get_trunk_pack(experts, dtype, image.device, cache)
     B, _, H, W = image.shape
-    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled)
-    outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
+    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled, layer1_out)
+    exact_pool = all((not e.upsample_to_input) or (H % h == 0 and W % w == 0) for e in experts)
+    join = None
+    if overlap_outputs and exact_pool:
+        main = torch.cuda.current_stream(image.device)
+        side = side_stream(image.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
+        for low in lows:
+            low.record_stream(side)
+        for out in outs:
+            for t in _tensors_of(out):
+                t.record_stream(main)
+        join = side
+    else:
+        outs = [e.format_output(low, H, W, dtype) for e, low in zip(experts, lows)]
     # mean over the up-sampled map == mean over the low-res map only for integer scale factors
     off = 0
     for e, out, n in zip(experts, outs, pack.n_ch):
         if e.upsample_to_input and (H % h != 0 or W % w != 0):
             pooled[:, off:off + n] = _ops.mean_hw_nchw(out)
         off += n
-    return outs, dict(pooled=pooled, n_ch=pack.n_ch)
+    return outs, dict(pooled=pooled, n_ch=pack.n_ch, join=join)

@@ -158,8 +158,53 @@ def trunk_pool_pad(pack: TrunkPack, H: int, W: int) -> int:
     return 1 if (flat_ok and _ops.flat_supported(pack.blocks[0][1], h4, w4, pack.dtype)) else 0
 
 
+def chunked_stem_layer1_supported(pack: TrunkPack, B: int, H: int, W: int) -> bool:
+    """True when stem+max-pool and the four layer1 convolutions can walk the batch in L2-sized chunks."""
+    chunk = _ops.l2_chunk_images()
+    if chunk <= 0 or B <= chunk or pack.dtype != torch.bfloat16 or not _ops.use_flat():
+        return False
+    if _ops.stem_mode(pack.dtype) != "tc" or not _ops.stem_pool_supported(H, W) or not trunk_pool_pad(pack, H, W):
+        return False
+    (c1a, c2a, dna), (c1b, c2b, dnb) = pack.blocks[0], pack.blocks[1]
+    if dna is not None or dnb is not None or c1a.sh != 1 or c1b.sh != 1:
+        return False
+    return all(_ops.flat_supported(c, H // 4, W // 4, pack.dtype) for c in (c1a, c2a, c1b, c2b))
+
+
+def run_stem_layer1_chunked(pack: TrunkPack, fused_stem, x_nhwc: torch.Tensor, B: int, H: int, W: int,
+                            rest_out: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+    """conv1+bn1+relu+maxpool and layer1 (two BasicBlocks) of all experts, one sub-batch at a time.
+
+    Every layer1 convolution moves ~3.3 MB per frame (read + write, 3 experts) for 0.9 GFLOP, so at full
+    batch the stage runs at HBM speed.  Walking the batch in chunks whose activations fit the 126 MB L2
+    lets each convolution read what the previous launch just wrote from L2; only the stage's final
+    output goes to HBM, written straight into the full [G*B,...] tensor (strided expert groups).
+    fused_stem: PackedStem whose first G convolutions are the expert stems (more may follow: their
+    full-resolution outputs go to rest_out, sliced per chunk)."""
+    G = pack.G
+    chunk = _ops.l2_chunk_images()
+    h4, w4 = H // 4, W // 4
+    (c1a, c2a, _), (c1b, c2b, _) = pack.blocks[0], pack.blocks[1]
+    dev = x_nhwc.device
+    y_full = torch.empty((G * B, h4 + 2, w4 + 2, c2b.cout), device=dev, dtype=torch.bfloat16)
+    bufs = {}
+    for b0 in range(0, B, chunk):
+        bc = min(chunk, B - b0)
+        if bc not in bufs:   # the last chunk may be shorter
+            bufs[bc] = [torch.empty((G * bc, h4 + 2, w4 + 2, 64), device=dev, dtype=torch.bfloat16) for _ in range(4)]
+        p0, t1, t2, t3 = bufs[bc]
+        rest = [r[b0:b0 + bc] for r in rest_out] if rest_out is not None else None
+        _ops.stem_pool_forward(fused_stem, x_nhwc[b0:b0 + bc], bc, H, W, G, 1, pooled=p0, rest=rest)
+        _ops.conv3x3_flat(c1a, p0, bc, h4, w4, out=t1)
+        _ops.conv3x3_flat(c2a, t1, bc, h4, w4, residual=p0, out=t2)
+        _ops.conv3x3_flat(c1b, t2, bc, h4, w4, out=t3)
+        _ops.conv3x3_flat(c2b, t3, bc, h4, w4, residual=t2, out=y_full[b0:], out_group_images=B)
+    return y_full
+
+
 def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None,
-               stem_out: Optional[torch.Tensor] = None, stem_pooled: Optional[torch.Tensor] = None):
+               stem_out: Optional[torch.Tensor] = None, stem_pooled: Optional[torch.Tensor] = None,
+               layer1_out: Optional[torch.Tensor] = None):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
 
     Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
@@ -169,8 +214,13 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     B, _, H, W = image.shape
     G = pack.G
     pad = trunk_pool_pad(pack, H, W)
-    if stem_pooled is not None:
-        y = None                                                         # stem + max-pool done by the caller
+    if layer1_out is None and stem_pooled is None and stem_out is None and isinstance(pack.stem, _ops.PackedStem) \
+            and chunked_stem_layer1_supported(pack, B, H, W):
+        if x_nhwc is None:
+            x_nhwc = stage_image(image, pack.dtype)
+        layer1_out = run_stem_layer1_chunked(pack, pack.stem, x_nhwc, B, H, W)
+    if layer1_out is not None or stem_pooled is not None:
+        y = None                                                         # stem + max-pool (+ layer1) already done
     elif stem_out is not None:
         y = stem_out                                                     # computed by the caller (fused with policy conv1)
     else:
@@ -190,11 +240,14 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()
     h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     h_cur, w_cur = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
-    if stem_pooled is not None:
+    blocks = pack.blocks
+    if layer1_out is not None:
+        y, blocks, pad = layer1_out, pack.blocks[2:], 1                  # [G*B,H/4+2,W/4+2,64], layer1 done
+    elif stem_pooled is not None:
         y = stem_pooled                                                  # [G*B,H/4(+2),W/4(+2),64]
     else:
         y = _ops.maxpool3x3s2(y, out_pad=pad)
-    for (c1, c2, dn) in pack.blocks:
+    for (c1, c2, dn) in blocks:
         # geometry of this block's output and whether its stride-1 convs take the flat kernel
         h_out = (h_cur + 2 * c1.ph - c1.kh) // c1.sh + 1
         w_out = (w_cur + 2 * c1.pw - c1.kw) // c1.sw + 1

@@ -1,0 +1,304 @@
+"""Differentiable building blocks of the gating / policy training step.
+
+Each torch.autograd.Function below is a thin shim over the C-ABI training kernels
+(include/automoe_b200.h, csrc/train_mlp.cu, csrc/train_conv.cu): forward and backward both run
+hand-written sm_100a kernels in fp32; torch only owns the buffers and strings the graph together,
+so `loss.backward()`, `clip_grad_norm_`, `AdamW` and `DistributedDataParallel` of the reference's
+trainer (training/train_gating_network.py:76-117) work unchanged on the drop-in modules.
+
+There is no torch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi
+from .._cabi import check, ctx, lib
+from .._ops import ptr, stream_ptr
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("automoe_b200 has no CPU path: training tensors must live on a CUDA (sm_100a) device")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def next_seed() -> int:
+    """Dropout seed drawn from torch's CPU generator: reproducible under torch.manual_seed, no device sync."""
+    return int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFFFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = Dropout_p(ReLU?(x W^T + b)) — nn.Linear [+ nn.ReLU [+ nn.Dropout]] fused."""
+
+    @staticmethod
+    def forward(ctx_, x, W, b, relu: bool, drop_p: float, seed: int):
+        x2, W2 = _f32c(x), _f32c(W)
+        b2 = _f32c(b) if b is not None else None
+        B, in_dim = x2.shape
+        out_dim = W2.shape[0]
+        y = torch.empty((B, out_dim), device=x2.device, dtype=torch.float32)
+        check(lib().amoe_linear_fwd(ctx(x2.device), ptr(x2), in_dim, ptr(W2), ptr(b2), ptr(y), out_dim, B, in_dim, out_dim,
+                                    int(relu), float(drop_p), seed, stream_ptr(x2.device)), "linear_fwd")
+        ctx_.save_for_backward(x2, W2, y if relu else None)
+        ctx_.cfg = (relu, float(drop_p), b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        x2, W2, y = ctx_.saved_tensors
+        relu, drop_p, has_b = ctx_.cfg
+        dy = _f32c(dy)
+        B, in_dim = x2.shape
+        out_dim = W2.shape[0]
+        need_x, need_W, need_b = ctx_.needs_input_grad[0], ctx_.needs_input_grad[1], has_b and ctx_.needs_input_grad[2]
+        dev = x2.device
+        dx = torch.empty_like(x2) if need_x else None
+        dW = torch.empty_like(W2) if need_W else None
+        db = torch.empty(out_dim, device=dev, dtype=torch.float32) if need_b else None
+        g_tmp = torch.empty((B, out_dim), device=dev, dtype=torch.float32) if relu else None
+        check(lib().amoe_linear_bwd(ctx(dev), ptr(dy), out_dim, ptr(y), out_dim, ptr(x2), in_dim, ptr(W2), ptr(g_tmp),
+                                    ptr(dx), in_dim, ptr(dW), ptr(db), B, in_dim, out_dim, int(relu), drop_p,
+                                    stream_ptr(dev)), "linear_bwd")
+        return dx, dW, db, None, None, None
+
+
+def linear(x, lin: nn.Linear, relu: bool = False, drop_p: float = 0.0) -> torch.Tensor:
+    seed = next_seed() if drop_p > 0.0 else 0
+    return _Linear.apply(x, lin.weight, lin.bias, relu, drop_p, seed)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx_, x, gamma, beta, eps: float):
+        x2, g2, b2 = _f32c(x), _f32c(gamma), _f32c(beta)
+        B, D = x2.shape
+        dev = x2.device
+        y = torch.empty_like(x2)
+        mean = torch.empty(B, device=dev, dtype=torch.float32)
+        rstd = torch.empty(B, device=dev, dtype=torch.float32)
+        check(lib().amoe_layernorm_fwd(ctx(dev), ptr(x2), ptr(g2), ptr(b2), ptr(y), ptr(mean), ptr(rstd), B, D, float(eps),
+                                       stream_ptr(dev)), "layernorm_fwd")
+        ctx_.save_for_backward(x2, g2, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        x2, g2, mean, rstd = ctx_.saved_tensors
+        dy = _f32c(dy)
+        B, D = x2.shape
+        dev = x2.device
+        dx = torch.empty_like(x2) if ctx_.needs_input_grad[0] else None
+        need_p = ctx_.needs_input_grad[1] or ctx_.needs_input_grad[2]
+        dg = torch.empty(D, device=dev, dtype=torch.float32) if need_p else None
+        db = torch.empty(D, device=dev, dtype=torch.float32) if need_p else None
+        check(lib().amoe_layernorm_bwd(ctx(dev), ptr(dy), ptr(x2), ptr(g2), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
+                                       B, D, stream_ptr(dev)), "layernorm_bwd")
+        return dx, dg, db, None
+
+
+def layer_norm(x, ln: nn.LayerNorm) -> torch.Tensor:
+    return _LayerNorm.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+class _GateCombine(torch.autograd.Function):
+    """(logits [B,E], processed [E,B,P]) -> (weights [B,E], combined [B,P])  — gating_network.py:157-165."""
+
+    @staticmethod
+    def forward(ctx_, logits, processed, temperature: float):
+        lg, pr = _f32c(logits), _f32c(processed)
+        E, B, P = pr.shape
+        dev = lg.device
+        weights = torch.empty((B, E), device=dev, dtype=torch.float32)
+        combined = torch.empty((B, P), device=dev, dtype=torch.float32)
+        check(lib().amoe_gate_combine_fwd(ctx(dev), ptr(lg), ptr(pr), B * P, P, float(temperature), ptr(weights),
+                                          ptr(combined), B, E, P, stream_ptr(dev)), "gate_combine_fwd")
+        ctx_.save_for_backward(weights, pr)
+        ctx_.T = float(temperature)
+        return weights, combined
+
+    @staticmethod
+    def backward(ctx_, dweights, dcombined):
+        weights, pr = ctx_.saved_tensors
+        E, B, P = pr.shape
+        dev = pr.device
+        dw = _f32c(dweights) if dweights is not None else None
+        dc = _f32c(dcombined) if dcombined is not None else None
+        dlogits = torch.empty((B, E), device=dev, dtype=torch.float32)
+        dproc = torch.empty_like(pr)
+        check(lib().amoe_gate_combine_bwd(ctx(dev), ptr(dc), ptr(dw), ptr(weights), ptr(pr), B * P, P, ctx_.T, ptr(dlogits),
+                                          ptr(dproc), B * P, B, E, P, stream_ptr(dev)), "gate_combine_bwd")
+        return dlogits, dproc, None
+
+
+def gate_combine(logits, processed: List[torch.Tensor], temperature: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _GateCombine.apply(logits, torch.stack(processed, dim=0), temperature)
+
+
+# ------------------------------------------------------------------------------------------------
+def _pack_w(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,Cin,KH,KW] -> packed [Cout,KH,KW,cin_pad] fp32 (kernel layout)."""
+    Cout, Cin, KH, KW = weight.shape
+    w = _f32c(weight)
+    out = torch.empty((Cout, KH, KW, cin_pad), device=w.device, dtype=torch.float32)
+    check(lib().amoe_pack_conv_weight(ctx(w.device), ptr(w), ptr(out), Cout, Cin, KH, KW, cin_pad, _cabi.F32,
+                                      stream_ptr(w.device)), "pack_conv_weight")
+    return out
+
+
+class _ConvBNReLU(torch.autograd.Function):
+    """nn.Conv2d(stride, padding, bias) -> nn.BatchNorm2d -> nn.ReLU on NHWC fp32 activations.
+
+    batch_stats=True is train-mode BatchNorm (statistics of this batch, running stats updated in
+    place); False normalises with the running statistics (eval mode) and stays differentiable."""
+
+    @staticmethod
+    def forward(ctx_, x, weight, bias, gamma, beta, running_mean, running_var, stride: int, padding: int,
+                momentum: float, eps: float, batch_stats: bool):
+        x2 = _f32c(x)                                    # [B,H,W,Cx]  (Cx >= Cin: zero-padded channels)
+        B, H, W, Cx = x2.shape
+        Cout, Cin, KH, KW = weight.shape
+        dev = x2.device
+        h, st = ctx(dev), stream_ptr(dev)
+        wp = _pack_w(weight, Cx)
+        Ho, Wo = (H + 2 * padding - KH) // stride + 1, (W + 2 * padding - KW) // stride + 1
+        ones = torch.ones(Cout, device=dev, dtype=torch.float32)
+        cb = _f32c(bias) if bias is not None else torch.zeros(Cout, device=dev, dtype=torch.float32)
+        conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
+        check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
+                                    stride, stride, padding, padding, Ho, Wo, 0, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
+        M = B * Ho * Wo
+        g2, b2 = _f32c(gamma), _f32c(beta)
+        y = torch.empty_like(conv)
+        ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
+        if batch_stats:
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            rstd = torch.empty(Cout, device=dev, dtype=torch.float32)
+            check(lib().amoe_bn_train_fwd(h, ptr(conv), ptr(g2), ptr(b2), ptr(running_mean), ptr(running_var),
+                                          float(momentum), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(ws), M, Cout, 1,
+                                          st), "bn_train_fwd")
+        else:
+            mean = _f32c(running_mean)
+            rstd = torch.rsqrt(_f32c(running_var) + eps)   # C values: parameter preparation, not activation math
+            check(lib().amoe_bn_apply_fwd(h, ptr(conv), ptr(mean), ptr(rstd), ptr(g2), ptr(b2), ptr(y), M, Cout, 1, st),
+                  "bn_apply_fwd")
+        ctx_.save_for_backward(x2, wp, conv, y, g2, mean, rstd)
+        ctx_.cfg = (stride, padding, batch_stats, Cin, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        x2, wp, conv, y, g2, mean, rstd = ctx_.saved_tensors
+        stride, padding, batch_stats, Cin, has_bias = ctx_.cfg
+        dy = _f32c(dy)
+        B, H, W, Cx = x2.shape
+        _, Ho, Wo, Cout = conv.shape
+        KH, KW = wp.shape[1], wp.shape[2]
+        dev = x2.device
+        h, st = ctx(dev), stream_ptr(dev)
+        M = B * Ho * Wo
+        ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
+        dconv = torch.empty_like(conv)
+        dgamma = torch.empty(Cout, device=dev, dtype=torch.float32)
+        dbeta = torch.empty(Cout, device=dev, dtype=torch.float32)
+        check(lib().amoe_bn_bwd(h, ptr(dy), ptr(conv), ptr(y), ptr(g2), ptr(mean), ptr(rstd), ptr(dconv), ptr(dgamma),
+                                ptr(dbeta), ptr(ws), M, Cout, int(batch_stats), st), "bn_bwd")
+        dbias = None
+        if has_bias and ctx_.needs_input_grad[2]:
+            dbias = torch.empty(Cout, device=dev, dtype=torch.float32)
+            check(lib().amoe_colsum(h, ptr(dconv), ptr(dbias), ptr(ws), M, Cout, 1.0, st), "colsum")
+        dw = None
+        if ctx_.needs_input_grad[1]:
+            n_ws = lib().amoe_conv2d_bwd_weight_workspace_floats(h, B, Cx, Cout, KH, KW, Ho, Wo)
+            ws2 = torch.empty(max(1, n_ws), device=dev, dtype=torch.float32)
+            dwp = torch.empty_like(wp)
+            check(lib().amoe_conv2d_bwd_weight(h, ptr(dconv), ptr(x2), ptr(dwp), ptr(ws2), n_ws, B, H, W, Cx, Cout, KH, KW,
+                                               stride, stride, padding, padding, Ho, Wo, st), "conv2d_bwd_weight")
+            dw = dwp[..., :Cin].permute(0, 3, 1, 2).contiguous()   # packed [Cout,KH,KW,Cin] -> OIHW
+        dx = None
+        if ctx_.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
+                                             padding, padding, Ho, Wo, st), "conv2d_bwd_data")
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def conv_bn_relu(x_nhwc, conv: nn.Conv2d, bn: nn.BatchNorm2d, batch_stats: bool) -> torch.Tensor:
+    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:
+        raise NotImplementedError("training conv kernels take square stride/padding")
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if batch_stats and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    rm, rv = bn.running_mean, bn.running_var
+    return _ConvBNReLU.apply(x_nhwc, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, conv.stride[0], conv.padding[0],
+                             momentum, bn.eps, batch_stats)
+
+
+class _GlobalAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx_, x):
+        x2 = _f32c(x)
+        B, H, W, Cc = x2.shape
+        out = torch.empty((B, Cc), device=x2.device, dtype=torch.float32)
+        check(lib().amoe_gap_fwd(ctx(x2.device), ptr(x2), ptr(out), B, H * W, Cc, stream_ptr(x2.device)), "gap_fwd")
+        ctx_.shape = (B, H, W, Cc)
+        return out
+
+    @staticmethod
+    def backward(ctx_, dy):
+        B, H, W, Cc = ctx_.shape
+        dy = _f32c(dy)
+        dx = torch.empty((B, H, W, Cc), device=dy.device, dtype=torch.float32)
+        check(lib().amoe_gap_bwd(ctx(dy.device), ptr(dy), ptr(dx), B, H * W, Cc, stream_ptr(dy.device)), "gap_bwd")
+        return dx
+
+
+def global_avg_pool(x_nhwc) -> torch.Tensor:
+    return _GlobalAvgPool.apply(x_nhwc)
+
+
+# ------------------------------------------------------------------------------------------------
+LOSS_NAMES = ("total_loss", "ade", "fde", "speed", "smoothness", "load_balancing", "entropy")
+
+
+class _GatingLoss(torch.autograd.Function):
+    """All seven terms of compute_gating_losses in one launch; the gradient of total_loss w.r.t. the
+    predictions is produced by the same launch and handed to autograd in backward."""
+
+    @staticmethod
+    def forward(ctx_, waypoints, speed, expert_weights, tgt_wp, tgt_spd, speed_mode: int, coef, use_lb: bool, use_ent: bool):
+        wp, ew, twp = _f32c(waypoints), _f32c(expert_weights), _f32c(tgt_wp)
+        B, H, _ = wp.shape
+        E = ew.shape[1]
+        dev = wp.device
+        spd = _f32c(speed) if speed is not None else None
+        tspd = _f32c(tgt_spd) if tgt_spd is not None else None
+        losses = torch.empty(7, device=dev, dtype=torch.float32)
+        dwp = torch.empty_like(wp)
+        dspd = torch.zeros((B, spd.shape[1]), device=dev, dtype=torch.float32) if spd is not None else None
+        dew = torch.empty_like(ew)
+        if spd is not None and spd.shape[1] != H and speed_mode == 1:
+            raise ValueError("speed sequence length differs from the waypoint horizon")
+        coef_c = (C.c_float * 6)(*[float(c) for c in coef])
+        Hs = spd.shape[1] if spd is not None else 0
+        d_spd_arg = dspd if (spd is not None and Hs == H) else None
+        check(lib().amoe_gating_loss_fwd_bwd(ctx(dev), ptr(wp), ptr(spd), Hs, ptr(ew), ptr(twp), ptr(tspd),
+                                             tspd.shape[1] if tspd is not None else 0, B, H, E, int(speed_mode), coef_c,
+                                             int(use_lb), int(use_ent), ptr(losses), ptr(dwp), ptr(d_spd_arg), ptr(dew),
+                                             stream_ptr(dev)), "gating_loss_fwd_bwd")
+        ctx_.save_for_backward(dwp, dspd, dew)
+        ctx_.mark_non_differentiable()
+        return losses
+
+    @staticmethod
+    def backward(ctx_, dlosses):
+        dwp, dspd, dew = ctx_.saved_tensors
+        # the reference back-propagates total_loss only; gradients arriving at the other six entries (a caller
+        # differentiating e.g. `ade` alone) are not supported by the fused kernel
+        s = dlosses[0]
+        return dwp * s, (dspd * s if dspd is not None else None), dew * s, None, None, None, None, None, None

@@ -115,3 +115,21 @@ def test_weight_update_invalidates_pack(model_sd):
         b = m(batch)["waypoints"]
         m.policy_head.head_wp[4].bias.sub_(1.0)
     assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+def test_l2_chunked_stem_layer1_is_bit_identical(model_sd, monkeypatch):
+    """Walking stem+layer1 in sub-batches (L2-resident chunks, ragged last chunk, strided write into the
+    full grouped tensor) must not change a single bit of the forward."""
+    m, sd = model_sd
+    batch = _to(synth.synth_batch(16, 256, 256, seed=7), DEV)
+    outs = {}
+    for chunk in ("0", "6"):
+        monkeypatch.setenv("AMOE_L2_CHUNK", chunk)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            outs[chunk] = m(batch)
+    for k in SMALL:
+        assert torch.equal(outs["0"][k], outs["6"][k]), k
+    for i in (1, 2):
+        assert torch.equal(outs["0"]["expert_outputs"][i], outs["6"]["expert_outputs"][i])
+    for k in ("class_logits", "bbox_deltas"):
+        assert torch.equal(outs["0"]["expert_outputs"][0][k], outs["6"]["expert_outputs"][0][k])
