@@ -258,7 +258,8 @@ int amoe_gate_combine_bwd(amoe_ctx*, const float* dcombined, const float* dweigh
  *   speed_mode 0: no speed term; 1: L1 over the [B,H] sequences; 2: last step only
  *   coef_host[6] = ade, fde, speed, smoothness, load_balancing, entropy weights (HOST pointer)
  *   losses[7] (device) = total, ade, fde, speed, smoothness, load_balancing, entropy_loss
- *   d_waypoints [B,H,2], d_speed [B,H], d_weights [B,E]: d total / d prediction (may be NULL). */
+ *   d_waypoints [B,H,2], d_speed [B,speed_ld] (zero-filled by the caller; mode 2 writes the last column),
+ *   d_weights [B,E]: d total / d prediction (may be NULL). */
 int amoe_gating_loss_fwd_bwd(amoe_ctx*, const float* waypoints, const float* speed, int speed_ld,
                              const float* expert_weights, const float* tgt_waypoints,
                              const float* tgt_speed, int tgt_speed_ld, int B, int H, int E,

@@ -91,7 +91,7 @@ def extractor(expert_output, sd, p, cfg):
     AdaptiveAvgPool2d(1) -> Flatten -> Linear -> ReLU -> Dropout(eval: id) -> Linear -> LayerNorm."""
     if cfg["type"] == "detection":
         expert_output = torch.cat([expert_output["class_logits"], expert_output["bbox_deltas"]], dim=1)
-    v = expert_output.float().mean(dim=(2, 3))
+    v = expert_output.to(sd[p + ".feature_extractor.2.weight"].dtype).mean(dim=(2, 3))   # fp32 (fp64 in accuracy studies)
     v = F.relu(_linear(v, sd, p + ".feature_extractor.2"))
     v = _linear(v, sd, p + ".feature_extractor.5")
     return _ln(v, sd, p + ".feature_extractor.6")
@@ -118,7 +118,7 @@ def vehicle_state(batch):
 
 def context_extractor(state, sd, p="context_extractor"):
     """SimpleContextExtractor.forward (context_features.py:151-165)."""
-    v = F.relu(_linear(state, sd, p + ".encoder.0"))
+    v = F.relu(_linear(state.to(sd[p + ".encoder.0.weight"].dtype), sd, p + ".encoder.0"))
     v = _linear(v, sd, p + ".encoder.3")
     return _ln(v, sd, p + ".encoder.4")
 

@@ -26,29 +26,32 @@ __global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const fl
                                                                         const float* __restrict__ y,
                                                                         const float* __restrict__ mean,
                                                                         const float* __restrict__ rstd, int64_t M, int C,
-                                                                        float* __restrict__ partial) {
-  __shared__ float sh0[RED_THREADS], sh1[RED_THREADS];
+                                                                        double* __restrict__ partial) {
+  __shared__ double sh0[RED_THREADS], sh1[RED_THREADS];
   const int cb = min(C, RED_THREADS);          // channels handled per pass (C is a multiple of cb or < 256)
   const int rl = threadIdx.x / cb, nrl = RED_THREADS / cb;
   const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS, r1 = min(M, r0 + RED_ROWS);
   for (int c0 = 0; c0 < C; c0 += cb) {
     const int c = c0 + threadIdx.x % cb;
-    float s0 = 0.f, s1 = 0.f;
+    // double accumulators: these sums feed differences (variance; g - mean(g) in the BatchNorm backward,
+    // where the pooled policy gradient is almost constant over a channel), so fp32 rounding would be
+    // amplified by the cancellation.  The reductions are memory-bound; the fp64 adds are free.
+    double s0 = 0.0, s1 = 0.0;
     if (c < C && rl < nrl) {
       const float mu = MODE == 1 ? mean[c] : 0.f, rs = MODE == 1 ? rstd[c] : 0.f;
       for (int64_t r = r0 + rl; r < r1; r += nrl) {
         const int64_t i = r * C + c;
         if (MODE == 0) {
-          const float v = x[i];
+          const double v = (double)x[i];
           s0 += v;
-          s1 = fmaf(v, v, s1);
+          s1 += v * v;
         } else if (MODE == 1) {
           float g = dy[i];
           if (y && !(y[i] > 0.f)) g = 0.f;
-          s0 += g;
-          s1 = fmaf(g, (x[i] - mu) * rs, s1);
+          s0 += (double)g;
+          s1 += (double)g * (double)((x[i] - mu) * rs);
         } else {
-          s0 += x[i];
+          s0 += (double)x[i];
         }
       }
     }
@@ -56,7 +59,7 @@ __global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const fl
     sh1[threadIdx.x] = s1;
     __syncthreads();
     if (threadIdx.x < cb && c < C) {
-      float t0 = 0.f, t1 = 0.f;
+      double t0 = 0.0, t1 = 0.0;
       for (int j = 0; j < nrl; ++j) {      // fixed order
         t0 += sh0[j * cb + threadIdx.x];
         t1 += sh1[j * cb + threadIdx.x];
@@ -70,15 +73,15 @@ __global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const fl
 
 // BatchNorm statistics from the partial sums: mean, rstd (biased variance), running-stat update
 // (momentum; running_var gets the unbiased variance, as nn.BatchNorm2d does).
-__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int64_t M, int C, float eps,
+__global__ void bn_stats_final_kernel(const double* __restrict__ partial, int nblk, int64_t M, int C, float eps,
                                       float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                                       float* __restrict__ running_mean, float* __restrict__ running_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, ss = 0.0;
   for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
-    ss += (double)partial[((int64_t)b * 2 + 1) * C + c];
+    s += partial[((int64_t)b * 2 + 0) * C + c];
+    ss += partial[((int64_t)b * 2 + 1) * C + c];
   }
   const double mu = s / (double)M;
   double var = ss / (double)M - mu * mu;
@@ -92,17 +95,17 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nbl
   }
 }
 // out0[c] = sum of partial s0, out1[c] = sum of partial s1 (either may be NULL); scale applied
-__global__ void colreduce_final_kernel(const float* __restrict__ partial, int nblk, int C, float scale,
+__global__ void colreduce_final_kernel(const double* __restrict__ partial, int nblk, int C, float scale,
                                        float* __restrict__ out0, float* __restrict__ out1) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, t = 0.0;
   for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
-    t += (double)partial[((int64_t)b * 2 + 1) * C + c];
+    s += partial[((int64_t)b * 2 + 0) * C + c];
+    t += partial[((int64_t)b * 2 + 1) * C + c];
   }
-  if (out0) out0[c] = (float)s * scale;
-  if (out1) out1[c] = (float)t * scale;
+  if (out0) out0[c] = (float)(s * (double)scale);
+  if (out1) out1[c] = (float)(t * (double)scale);
 }
 
 // y = act((x - mean[c]) * rstd[c] * gamma[c] + beta[c])
@@ -313,9 +316,9 @@ __global__ __launch_bounds__(256) void conv_bwd_weight_kernel(ConvBwdParams p) {
 __global__ void slice_sum_kernel(const float* __restrict__ partial, int S, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(int64_t)k * n + i];
-  out[i] = s;
+  double s = 0.0;   // a few hundred partials of mixed sign: the final sum in double costs nothing
+  for (int k = 0; k < S; ++k) s += (double)partial[(int64_t)k * n + i];
+  out[i] = (float)s;
 }
 
 // global average pool over HW: x [B,HW,C] -> out [B,C]; backward broadcasts dy/HW
@@ -335,6 +338,8 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__
   dx[i] = dy[b * C + c] / (float)HW;
 }
 
+inline double* ws64(float* ws) { return reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 7) & ~(uintptr_t)7); }
+
 int wgrad_slices(int sm_count, int Cout, int Kw, int64_t Mg, int* rows_per_slice) {
   const int tiles = ceil_div(Cout, TBM) * ceil_div(Kw, TBN);
   int S = std::max(1, (4 * sm_count) / tiles);
@@ -351,7 +356,8 @@ int wgrad_slices(int sm_count, int Cout, int Kw, int64_t Mg, int* rows_per_slice
 
 extern "C" {
 
-int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { return ((M + RED_ROWS - 1) / RED_ROWS) * 2 * (int64_t)C; }
+// partial sums are doubles: 2 floats each, +2 so the caller's float buffer can be aligned up to 8 bytes
+int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { return ((M + RED_ROWS - 1) / RED_ROWS) * 4 * (int64_t)C + 2; }
 
 int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float momentum, float eps, float* y, float* save_mean, float* save_rstd,
@@ -363,9 +369,9 @@ int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const f
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<0><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, workspace);
+  colreduce_partial_kernel<0><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace));
   AMOE_LAUNCH_OK(ctx);
-  bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, M, C, eps, momentum, save_mean, save_rstd,
+  bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, M, C, eps, momentum, save_mean, save_rstd,
                                                         running_mean, running_var);
   AMOE_LAUNCH_OK(ctx);
   const int64_t n4 = M * C / 4;
@@ -394,9 +400,9 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<1><<<nblk, RED_THREADS, 0, st>>>(x, dy, y_relu, mean, rstd, M, C, workspace);
+  colreduce_partial_kernel<1><<<nblk, RED_THREADS, 0, st>>>(x, dy, y_relu, mean, rstd, M, C, ws64(workspace));
   AMOE_LAUNCH_OK(ctx);
-  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, C, 1.f, dbeta, dgamma);
+  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, C, 1.f, dbeta, dgamma);
   AMOE_LAUNCH_OK(ctx);
   if (dx) {
     const int64_t n4 = M * C / 4;
@@ -413,9 +419,9 @@ int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<2><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, workspace);
+  colreduce_partial_kernel<2><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace));
   AMOE_LAUNCH_OK(ctx);
-  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, nblk, C, scale, out, nullptr);
+  colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, C, scale, out, nullptr);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

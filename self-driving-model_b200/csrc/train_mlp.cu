@@ -345,14 +345,18 @@ __global__ __launch_bounds__(1024) void gating_loss_kernel(LossArgs a) {
       a.dwp[i] = g;
     }
   }
-  if (a.dspd) {
+  if (a.dspd) {   // [B, spd_ld], zero-filled by the caller
     const float k = n_spd ? a.coef[2] / (float)n_spd : 0.f;
-    for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
-      const int b = i / H, t = i - b * H;
-      float g = 0.f;
-      if (a.speed_mode == 1) g = k * sgnf(a.spd[b * a.spd_ld + t] - a.tspd[b * a.tspd_ld + t]);
-      else if (a.speed_mode == 2 && t == H - 1) g = k * sgnf(a.spd[b * a.spd_ld + t] - a.tspd[b * a.tspd_ld + a.tspd_ld - 1]);
-      a.dspd[i] = g;
+    if (a.speed_mode == 1) {
+      for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
+        const int b = i / H, t = i - b * H;
+        a.dspd[b * a.spd_ld + t] = k * sgnf(a.spd[b * a.spd_ld + t] - a.tspd[b * a.tspd_ld + t]);
+      }
+    } else if (a.speed_mode == 2) {
+      for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int j = b * a.spd_ld + a.spd_ld - 1;
+        a.dspd[j] = k * sgnf(a.spd[j] - a.tspd[b * a.tspd_ld + a.tspd_ld - 1]);
+      }
     }
   }
   if (a.dew) {

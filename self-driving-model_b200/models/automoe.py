@@ -152,8 +152,52 @@ class AutoMoE(nn.Module):
         return outs
 
     # ------------------------------------------------------------------ forward
+    def _trainable_part(self):
+        return [self.context_extractor, self.expert_extractors, self.gating_network, self.policy_head]
+
+    def _forward_train(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Forward that records an autograd graph over the gating / policy parameters
+        (training/train_gating_network.py:96-100).  Experts must be frozen (freeze_experts()): they run
+        through the inference kernels under no_grad with their BatchNorm running statistics - the
+        reference's model.train() would silently switch the frozen experts to batch statistics and keep
+        mutating their running stats; call model.experts.eval() on the reference for the same numbers."""
+        from ._train_forward import context_extractor_forward, extractor_forward, gating_forward, policy_forward
+        if any(p.requires_grad for p in self.experts.parameters()):
+            raise NotImplementedError("joint training of the experts (unfreeze_experts) is not implemented: "
+                                      "call freeze_experts() - only the gating/policy part back-propagates")
+        image = batch['image']
+        if not image.is_cuda:
+            raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+        dtype = resolve_dtype(self.precision)
+        state = self._vehicle_state(batch).to(image.device)
+        with torch.no_grad():
+            expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, frozen_eval=True)
+        ctx = context_extractor_forward(self.context_extractor, state)
+        feats, off = [], 0
+        for ext, n in zip(self.expert_extractors.extractors, aux['n_ch']):
+            feats.append(extractor_forward(ext, aux['pooled'][:, off:off + n].contiguous()))
+            off += n
+        g = gating_forward(self.gating_network, feats, ctx)
+        pol = policy_forward(self.policy_head, image, g['combined_output'])
+        speed_seq = pol['speed']
+        return {
+            'waypoints': pol['waypoints'],
+            'speed': speed_seq[:, -1:].contiguous(),
+            'speed_seq': speed_seq,
+            'expert_weights': g['expert_weights'],
+            'expert_outputs': expert_outputs,
+            'context_features': ctx,
+            'combined_features': g['combined_output'],
+            'gate_logits': g['gate_logits'],
+        }
+
     def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        require_eval(self, "AutoMoE")
+        from ._train_forward import wants_grad
+        if self.training:
+            return self._forward_train(batch)
+        if torch.is_grad_enabled() and any(wants_grad(m) for m in self._trainable_part()) and \
+                not any(p.requires_grad for p in self.experts.parameters()):
+            return self._forward_train(batch)      # eval semantics, differentiable (frozen experts)
         image = batch['image']
         if not image.is_cuda:
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")

@@ -76,7 +76,8 @@ def _tensors_of(out):
 
 
 def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None,
-                stem_out=None, stem_pooled=None, layer1_out=None, overlap_outputs: bool = False):
+                stem_out=None, stem_pooled=None, layer1_out=None, overlap_outputs: bool = False,
+                frozen_eval: bool = False):
     """Run G experts on the same image batch in grouped launches.
 
     Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
@@ -89,7 +90,8 @@ def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.
     """
     if not image.is_cuda:
         raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
-    _check_eval(experts)
+    if not frozen_eval:      # frozen_eval: caller runs frozen experts inside a training step (eval BatchNorm)
+        _check_eval(experts)
     pack = get_trunk_pack(experts, dtype, image.device, cache)
     B, _, H, W = image.shape
     lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled, layer1_out)

@@ -41,9 +41,11 @@ class ExpertOutputExtractor(nn.Module):
         return expert_output
 
     def forward(self, expert_output) -> torch.Tensor:
-        require_eval(self, type(self).__name__)
         x = self._as_map(expert_output)
         pooled = _ops.mean_hw_nchw(x)  # AdaptiveAvgPool2d((1,1)) + Flatten
+        from .._train_forward import extractor_forward, wants_grad
+        if wants_grad(self):   # experts are frozen upstream: the pooled logits are constants of the graph
+            return extractor_forward(self, pooled)
         n_ch = [self.in_channels()]
         stamp = (params_stamp([self]), x.device)
         if self._flat is None or self._flat[0] != stamp:

@@ -81,7 +81,9 @@ class GatingNetwork(nn.Module):
         return self._flat[1]
 
     def forward(self, expert_outputs: List[torch.Tensor], context: torch.Tensor) -> Dict[str, torch.Tensor]:
-        require_eval(self, "GatingNetwork")
+        from .._train_forward import gating_forward, wants_grad
+        if wants_grad(self):
+            return gating_forward(self, [t.float() for t in expert_outputs], context.float())
         E = self.num_experts
         feats = torch.stack([t.float() for t in expert_outputs], dim=0).contiguous()  # [E,B,256]
         context = context.float().contiguous()

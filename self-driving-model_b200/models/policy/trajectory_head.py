@@ -76,7 +76,9 @@ class TrajectoryPolicy(nn.Module):
 
     def forward(self, image: torch.Tensor, context: Optional[torch.Tensor] = None, _x_nhwc=None,
                 _dtype=None, _conv1=None) -> Dict[str, torch.Tensor]:
-        require_eval(self, "TrajectoryPolicy")
+        from .._train_forward import policy_forward, wants_grad
+        if wants_grad(self):
+            return policy_forward(self, image, context)
         if not image.is_cuda:
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
         dtype = _dtype or resolve_dtype(self.precision)

@@ -235,8 +235,13 @@ def conv_bn_relu(x_nhwc, conv: nn.Conv2d, bn: nn.BatchNorm2d, batch_stats: bool)
     if batch_stats and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     rm, rv = bn.running_mean, bn.running_var
-    return _ConvBNReLU.apply(x_nhwc, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, conv.stride[0], conv.padding[0],
-                             momentum, bn.eps, batch_stats)
+    if batch_stats and (rm is None or rv is None):
+        raise NotImplementedError("BatchNorm2d(track_running_stats=False) is not supported by the training kernels")
+    y = _ConvBNReLU.apply(x_nhwc, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, conv.stride[0], conv.padding[0],
+                          momentum, bn.eps, batch_stats)
+    if batch_stats:   # the kernel updated the running statistics through raw pointers: bump Tensor._version
+        torch.autograd.graph.increment_version([rm, rv])
+    return y
 
 
 class _GlobalAvgPool(torch.autograd.Function):
@@ -286,7 +291,7 @@ class _GatingLoss(torch.autograd.Function):
             raise ValueError("speed sequence length differs from the waypoint horizon")
         coef_c = (C.c_float * 6)(*[float(c) for c in coef])
         Hs = spd.shape[1] if spd is not None else 0
-        d_spd_arg = dspd if (spd is not None and Hs == H) else None
+        d_spd_arg = dspd if (spd is not None and speed_mode in (1, 2)) else None
         check(lib().amoe_gating_loss_fwd_bwd(ctx(dev), ptr(wp), ptr(spd), Hs, ptr(ew), ptr(twp), ptr(tspd),
                                              tspd.shape[1] if tspd is not None else 0, B, H, E, int(speed_mode), coef_c,
                                              int(use_lb), int(use_ent), ptr(losses), ptr(dwp), ptr(d_spd_arg), ptr(dew),

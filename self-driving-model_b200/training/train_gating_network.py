@@ -1,0 +1,142 @@
+"""Gating / policy training step — drop-in for the hot part of training/train_gating_network.py
+(compute_gating_losses :21-74, the body of train_one_epoch :93-105) on the sm_100a kernels.
+
+Two ways to use it:
+
+* the reference's trainer unchanged: `pred = model(batch)` (train mode, experts frozen) records the
+  autograd graph over the kernels of training/functional.py; `compute_gating_losses` here returns the
+  same dict from ONE fused kernel; `loss.backward()`, `clip_grad_norm_`, `torch.optim.AdamW` and
+  `DistributedDataParallel` then work as they do on the reference;
+* `FlatAdamW`: parameters, gradients and both Adam moments live in four flat fp32 buffers, so the
+  data-parallel exchange is ONE NCCL all-reduce (SUM) of 11.5 MB over NVLink, and global-norm clip +
+  AdamW is one reduction + one update kernel (amoe_sq_norm, amoe_fused_clip_adamw).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .._cabi import check, ctx, lib
+from .._ops import ptr, stream_ptr
+from .functional import LOSS_NAMES, _GatingLoss
+
+
+def compute_gating_losses(pred: Dict[str, torch.Tensor], target_wp: torch.Tensor, target_spd: torch.Tensor,
+                          config: Dict) -> Dict[str, torch.Tensor]:
+    """Same signature, keys and values as the reference's compute_gating_losses."""
+    wp = pred["waypoints"]
+    pred_spd = pred.get("speed_seq", pred.get("speed"))
+    # speed term selection as train_gating_network.py:28-37
+    if pred_spd is not None and pred_spd.dim() == 2 and target_spd.dim() == 2 and pred_spd.size(1) == target_spd.size(1):
+        mode, spd = 1, pred_spd
+    else:
+        pred_last = pred.get("speed")
+        if pred_last is not None and pred_last.dim() == 2 and pred_last.size(1) == 1:
+            mode, spd = 2, pred_last
+        else:
+            mode, spd = 0, None
+    coef = [config.get('ade_weight', 1.0), config.get('fde_weight', 2.0), config.get('speed_weight', 0.2),
+            config.get('smoothness_weight', 0.1), config.get('load_balancing_weight', 0.01),
+            config.get('entropy_weight', 0.001)]
+    tspd = target_spd if target_spd.dim() == 2 else target_spd.reshape(target_spd.size(0), -1)
+    losses = _GatingLoss.apply(wp, spd, pred["expert_weights"], target_wp, tspd if mode else None, mode, coef,
+                               bool(config.get('use_load_balancing', True)), bool(config.get('use_entropy_loss', True)))
+    return {name: losses[i] for i, name in enumerate(LOSS_NAMES)}
+
+
+def allreduce_flat_(flat_grad: torch.Tensor, group=None) -> float:
+    """SUM all-reduce of the flat gradient buffer across data-parallel ranks (NCCL over NVLink on GPUs, any
+    torch.distributed backend otherwise).  Returns the scale (1/world) the optimizer applies."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
+    return 1.0
+
+
+class FlatAdamW:
+    """torch.optim.AdamW(params, lr, betas, eps, weight_decay) + clip_grad_norm_(max_norm) on flat buffers.
+
+    The trainable parameters are re-pointed at slices of one flat fp32 buffer (their values are kept),
+    `.grad` of every parameter is a slice of a second one, so autograd accumulates straight into the
+    buffer that is all-reduced.  step() = all-reduce -> squared-norm reduction -> fused clip+AdamW.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, max_norm: Optional[float] = 1.0, group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdamW got no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("automoe_b200 has no CPU path: FlatAdamW needs parameters on a CUDA (sm_100a) device")
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm, self.group = lr, betas, eps, weight_decay, max_norm, group
+        self.offsets, n = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatAdamW takes fp32 parameters on one device")
+            self.offsets.append(n)
+            n += (p.numel() + 3) & ~3          # 16-byte aligned slices
+        self.n = n
+        self.flat_param = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat_param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+        self._ws = torch.empty(4 * 148, device=dev, dtype=torch.float32)
+        self._norm = torch.zeros(2, device=dev, dtype=torch.float32)
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+        for p, off in zip(self.params, self.offsets):      # autograd may have replaced .grad (e.g. after set_to_none)
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+
+    def total_norm(self) -> torch.Tensor:
+        """Gradient norm of the last step() before clipping (after the all-reduce average)."""
+        return self._norm[1]
+
+    @torch.no_grad()
+    def step(self):
+        dev = self.flat_param.device
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
+                self.flat_grad[off:off + p.numel()].view_as(p).copy_(p.grad)      # foreign .grad: fold it in
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+        scale = allreduce_flat_(self.flat_grad, self.group)
+        h, st = ctx(dev), stream_ptr(dev)
+        self.step_count += 1
+        clip = self.max_norm is not None and self.max_norm > 0
+        check(lib().amoe_sq_norm(h, ptr(self.flat_grad), self.n, ptr(self._ws), self._ws.numel(), ptr(self._norm), st), "sq_norm")
+        check(lib().amoe_fused_clip_adamw(h, ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                          self.n, ptr(self._norm), scale, float(self.max_norm) if clip else 0.0, self.lr,
+                                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, st),
+              "fused_clip_adamw")
+        # the kernel wrote through raw pointers: tell torch (cached weight packs key on Tensor._version)
+        torch.autograd.graph.increment_version(self.params)
+
+
+def freeze_for_gating_training(model) -> List[torch.nn.Parameter]:
+    """model.freeze_experts() + the list of parameters the gating trainer optimises (2,870,657 for the
+    3-expert configuration)."""
+    model.freeze_experts()
+    return [p for p in model.parameters() if p.requires_grad]
+
+
+def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, config: Dict) -> Dict[str, torch.Tensor]:
+    """One iteration of train_one_epoch (train_gating_network.py:93-105): zero_grad, forward, losses,
+    backward, (all-reduce,) clip 1.0, AdamW.  Returns the loss dict (device tensors; no host sync)."""
+    optimizer.zero_grad()
+    pred = model(batch)
+    losses = compute_gating_losses(pred, batch["waypoints"], batch["speed"], config)
+    losses["total_loss"].backward()
+    optimizer.step()
+    return {k: v.detach() for k, v in losses.items()}

@@ -70,3 +70,41 @@ def test_shard_range_properties():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    from automoe_b200.training.train_gating_network import allreduce_flat_
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)        # rank 0: i, rank 1: 2i
+        scale = allreduce_flat_(flat)
+        q.put((rank, flat.tolist(), scale))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    """The training step's one exchange: SUM all-reduce of the flat gradient buffer, averaged by 1/world
+    inside the fused optimizer kernel (here: the host logic over gloo)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, flat, scale in res:
+        assert flat == [3.0 * i for i in range(10)] and scale == 0.5
+
+
+def test_allreduce_flat_single_process_is_identity():
+    from automoe_b200.training.train_gating_network import allreduce_flat_
+    t = torch.ones(4)
+    assert allreduce_flat_(t) == 1.0 and t.tolist() == [1.0] * 4
