@@ -315,6 +315,31 @@ int amoe_conv2d_bwd_weight(amoe_ctx*, const float* dy, const float* x, float* dw
 int amoe_gap_fwd(amoe_ctx*, const float* x, float* out, int B, int HW, int C, void* stream);
 int amoe_gap_bwd(amoe_ctx*, const float* dy, float* dx, int B, int HW, int C, void* stream);
 
+/* ---- detection-expert training step (training/train_bdd100k_ddp.py:117-186) -----
+ * The trunk/head forward+backward reuse the fp32 conv / BatchNorm entry points above; these add the
+ * pieces only a full expert needs. */
+/* backward of nn.MaxPool2d(3, stride 2, pad 1), NHWC fp32: x [NB,H,W,C], dy [NB,Ho,Wo,C] -> dx like x.
+ * Arg-max rule of torch (first strictly greater element in kh-major scan order). */
+int amoe_maxpool3x3s2_bwd(amoe_ctx*, const float* x, const float* dy, float* dx, int NB, int H,
+                          int W, int C, void* stream);
+/* BasicBlock tail: y = relu(a + b) (n % 4 == 0); g = dy * [y > 0] (the gradient of both addends). */
+int amoe_add_relu_fwd(amoe_ctx*, const float* a, const float* b, float* y, int64_t n, void* stream);
+int amoe_relu_bwd(amoe_ctx*, const float* dy, const float* y, float* g, int64_t n, void* stream);
+/* Scatter of the Hungarian assignment (train_bdd100k_ddp.py:167-170) for the whole batch in one launch:
+ * for matched pair m of image batch_of[m]: target_classes[batch_of[m]*Q + pred_idx[m]] = labels[m],
+ * target_boxes[...] = boxes[m] (cxcywh).  The caller pre-fills classes with num_classes, boxes with 0. */
+int amoe_det_targets(amoe_ctx*, const int64_t* pred_idx, const int32_t* batch_of,
+                     const int64_t* labels, const float* boxes, int n_match, int Q,
+                     int64_t* target_classes, float* target_boxes, void* stream);
+/* nn.CrossEntropyLoss(ignore_index) + bbox_weight * nn.SmoothL1Loss(mean) over the matched rows
+ * (train_bdd100k_ddp.py:172-185) and d(total)/d(logits), d(total)/d(boxes), one launch.
+ *   logits [rows, ld_logits] (C classes), boxes [rows, ld_boxes] (4), target_classes [rows] int64,
+ *   target_boxes [rows,4]; losses4 = total, class_loss, bbox_loss, #matched rows. */
+int amoe_det_loss_fwd_bwd(amoe_ctx*, const float* logits, int ld_logits, const float* boxes,
+                          int ld_boxes, const int64_t* target_classes, const float* target_boxes,
+                          int64_t rows, int C, int ignore_index, float bbox_weight, float* losses4,
+                          float* dlogits, int ld_dlogits, float* dboxes, int ld_dboxes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

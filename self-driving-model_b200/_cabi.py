@@ -72,6 +72,12 @@ SIGNATURES = {
     "amoe_conv2d_bwd_weight": (_I, [_P] * 5 + [_L] + [_I] * 13 + [_P]),
     "amoe_gap_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "amoe_gap_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    # detection-expert training step
+    "amoe_maxpool3x3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "amoe_add_relu_fwd": (_I, [_P, _P, _P, _P, _L, _P]),
+    "amoe_relu_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
+    "amoe_det_targets": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "amoe_det_loss_fwd_bwd": (_I, [_P, _P, _I, _P, _I, _P, _P, _L, _I, _I, _F, _P, _P, _I, _P, _I, _P]),
 }
 
 

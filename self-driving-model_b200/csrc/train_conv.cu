@@ -195,8 +195,8 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < Ktot; k0 += TBK) {
-    // A: this thread's pixel, 4 consecutive k (same tap: Cout % 4 == 0)
-    {
+    // A: this thread's pixel, 4 consecutive k (one 16-byte load when Cout % 4 == 0: same tap, aligned)
+    if ((p.Cout & 3) == 0) {
       const int k = k0 + lk;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m_ok && k < Ktot) {
@@ -210,6 +210,22 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
         }
       }
       As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + lk + j;
+        float a = 0.f;
+        if (m_ok && k < Ktot) {
+          const int tap = k / p.Cout, co = k - tap * p.Cout;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          const int th = ih + p.ph - kh, tw = iw + p.pw - kw;
+          if (th >= 0 && tw >= 0 && th % p.sh == 0 && tw % p.sw == 0) {
+            const int oh = th / p.sh, ow = tw / p.sw;
+            if (oh < p.Ho && ow < p.Wo) a = p.dy[(((int64_t)n_img * p.Ho + oh) * p.Wo + ow) * p.Cout + co];
+          }
+        }
+        As[lk + j][lrow] = a;
+      }
     }
     // B: 16 k x 64 ci; element (k, ci) = w[co][tap][ci]; consecutive threads walk ci
     for (int e = tid; e < TBK * TBN; e += 256) {
@@ -363,8 +379,7 @@ int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const f
                       float* running_var, float momentum, float eps, float* y, float* save_mean, float* save_rstd,
                       float* workspace, int64_t M, int C, int relu, void* stream) {
   AMOE_REQUIRE(ctx && x && gamma && beta && y && save_mean && save_rstd && workspace, "amoe_bn_train_fwd: NULL argument");
-  AMOE_REQUIRE(C % 4 == 0 && (C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0),
-               "amoe_bn_train_fwd: C=%d must divide or be a multiple of 256 (and of 4)", C);
+  AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_train_fwd: C=%d must be a multiple of 4", C);
   AMOE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "amoe_bn_train_fwd: running stats come together");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -395,8 +410,7 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
                 const float* rstd, float* dx, float* dgamma, float* dbeta, float* workspace, int64_t M, int C,
                 int batch_stats, void* stream) {
   AMOE_REQUIRE(ctx && dy && x && gamma && mean && rstd && dgamma && dbeta && workspace, "amoe_bn_bwd: NULL argument");
-  AMOE_REQUIRE(C % 4 == 0 && (C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0),
-               "amoe_bn_bwd: C=%d must divide or be a multiple of 256 (and of 4)", C);
+  AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_bwd: C=%d must be a multiple of 4", C);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
@@ -415,7 +429,7 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
 
 int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int64_t M, int C, float scale, void* stream) {
   AMOE_REQUIRE(ctx && x && out && workspace, "amoe_colsum: NULL argument");
-  AMOE_REQUIRE(C <= RED_THREADS ? RED_THREADS % C == 0 : C % RED_THREADS == 0, "amoe_colsum: C=%d must divide or be a multiple of 256", C);
+  AMOE_REQUIRE(C >= 1, "amoe_colsum: C=%d", C);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
@@ -429,7 +443,6 @@ int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int
 int amoe_conv2d_bwd_data(amoe_ctx* ctx, const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
                          int KH, int KW, int stride_h, int stride_w, int pad_h, int pad_w, int Ho, int Wo, void* stream) {
   AMOE_REQUIRE(ctx && dy && w && dx, "amoe_conv2d_bwd_data: NULL argument");
-  AMOE_REQUIRE(Cout % 4 == 0, "amoe_conv2d_bwd_data: Cout=%d must be a multiple of 4", Cout);
   if (B == 0) return 0;
   ConvBwdParams p;
   p.dy = dy; p.x = nullptr; p.w = w; p.out = dx;

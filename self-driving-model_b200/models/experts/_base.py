@@ -31,8 +31,23 @@ class BDDExpertBase(nn.Module):
 
     # -- reference forward signature: forward(x: [B,3,H,W]) --
     def forward(self, x: torch.Tensor):
+        from .._train_forward import wants_grad
+        if wants_grad(self):
+            return self.forward_train(x)
         outs, _ = run_experts([self], x, resolve_dtype(self.precision), self._packs)
         return outs[0]
+
+    def forward_train(self, x: torch.Tensor):
+        """Differentiable forward (expert training): see _trunk.run_trunk_train."""
+        from ._trunk import run_trunk_train
+        if self.upsample_to_input:
+            raise NotImplementedError("training of the up-sampling experts (segmentation / drivable) needs the bilinear "
+                                      "backward, which is not implemented yet; the detection expert trains (SURVEY 8 a12)")
+        low = run_trunk_train(self, x)                      # [B,h,w,N] NHWC fp32
+        return self.format_output_train(low)
+
+    def format_output_train(self, low: torch.Tensor):
+        raise NotImplementedError
 
     def format_output(self, low: torch.Tensor, H: int, W: int, dtype: torch.dtype):
         raise NotImplementedError

@@ -134,6 +134,31 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
                      params_stamp(list(experts)))
 
 
+def run_trunk_train(expert, image: torch.Tensor) -> torch.Tensor:
+    """Differentiable forward of ONE expert (ResNet-18 trunk + 2-conv head) for expert training
+    (training/train_bdd100k_ddp.py:117-186): fp32 NHWC, every layer an autograd shim over
+    the sm_100a training kernels (training/functional.py).  BatchNorm follows module.training (batch
+    statistics + running-stat update in train mode).  Returns the head output [B,h,w,N] (NHWC).
+
+    torchvision ResNet._forward_impl / BasicBlock.forward (resnet.py:89-105,266-278), bdd_*_expert.py:12-24."""
+    from ...training import functional as TF
+    if not image.is_cuda:
+        raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+    bb = expert.backbone
+    x = _ops.image_to_nhwc(image, 4, torch.float32)
+    y = TF.conv_bn_act(x, bb[0], bb[1], relu=True)
+    y = TF.max_pool3x3s2(y)
+    for li in range(4, 8):
+        for blk in bb[li]:
+            out = TF.conv_bn_act(y, blk.conv1, blk.bn1, relu=True)
+            out = TF.conv_bn_act(out, blk.conv2, blk.bn2, relu=False)
+            idn = y if blk.downsample is None else TF.conv_bn_act(y, blk.downsample[0], blk.downsample[1], relu=False)
+            y = TF.add_relu(out, idn)
+    head = expert.head_module()
+    h = TF.conv_bn_act(y, head[0], None, relu=True)
+    return TF.conv_bn_act(h, head[2], None, relu=False)
+
+
 def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCHW fp32 frame -> the NHWC layout the first convolutions read (see _ops.stem_mode): the
     physically padded bf16 frame of the tensor-core stem, padded rows for the row-window variant, or

@@ -26,6 +26,14 @@ class BDDDetectionExpert(BDDExpertBase):
             "bbox_deltas": out[:, self.num_classes:, :, :],
         }
 
+    def format_output_train(self, low):
+        out = low.permute(0, 3, 1, 2)       # NCHW view of the NHWC head output (no copy)
+        return {
+            "class_logits": out[:, :self.num_classes, :, :],
+            "bbox_deltas": out[:, self.num_classes:, :, :],
+            "_head_nhwc": low,              # extra key: lets the fused detection loss skip the permutes
+        }
+
     def predict(self, x):
         output = self.forward(x)
         return {

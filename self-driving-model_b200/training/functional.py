@@ -151,15 +151,18 @@ def _pack_w(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
     return out
 
 
-class _ConvBNReLU(torch.autograd.Function):
-    """nn.Conv2d(stride, padding, bias) -> nn.BatchNorm2d -> nn.ReLU on NHWC fp32 activations.
+BN_NONE, BN_BATCH, BN_RUNNING = 0, 1, 2
 
-    batch_stats=True is train-mode BatchNorm (statistics of this batch, running stats updated in
-    place); False normalises with the running statistics (eval mode) and stays differentiable."""
+
+class _ConvBNAct(torch.autograd.Function):
+    """nn.Conv2d(stride, padding, bias?) [-> nn.BatchNorm2d] [-> nn.ReLU] on NHWC fp32 activations.
+
+    bn_mode: BN_NONE (plain convolution + bias), BN_BATCH (train-mode BatchNorm: statistics of this batch,
+    running stats updated in place), BN_RUNNING (eval-mode BatchNorm, kept differentiable)."""
 
     @staticmethod
     def forward(ctx_, x, weight, bias, gamma, beta, running_mean, running_var, stride: int, padding: int,
-                momentum: float, eps: float, batch_stats: bool):
+                momentum: float, eps: float, bn_mode: int, relu: bool):
         x2 = _f32c(x)                                    # [B,H,W,Cx]  (Cx >= Cin: zero-padded channels)
         B, H, W, Cx = x2.shape
         Cout, Cin, KH, KW = weight.shape
@@ -170,44 +173,62 @@ class _ConvBNReLU(torch.autograd.Function):
         ones = torch.ones(Cout, device=dev, dtype=torch.float32)
         cb = _f32c(bias) if bias is not None else torch.zeros(Cout, device=dev, dtype=torch.float32)
         conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
+        fuse_relu = int(relu and bn_mode == BN_NONE)
         check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
-                                    stride, stride, padding, padding, Ho, Wo, 0, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
+                                    stride, stride, padding, padding, Ho, Wo, fuse_relu, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
+        ctx_.cfg = (stride, padding, bn_mode, relu, Cin, bias is not None)
+        if bn_mode == BN_NONE:
+            ctx_.save_for_backward(x2, wp, conv if relu else None)
+            return conv
         M = B * Ho * Wo
         g2, b2 = _f32c(gamma), _f32c(beta)
         y = torch.empty_like(conv)
-        ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
-        if batch_stats:
+        if bn_mode == BN_BATCH:
+            ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
             mean = torch.empty(Cout, device=dev, dtype=torch.float32)
             rstd = torch.empty(Cout, device=dev, dtype=torch.float32)
             check(lib().amoe_bn_train_fwd(h, ptr(conv), ptr(g2), ptr(b2), ptr(running_mean), ptr(running_var),
-                                          float(momentum), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(ws), M, Cout, 1,
-                                          st), "bn_train_fwd")
+                                          float(momentum), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(ws), M, Cout,
+                                          int(relu), st), "bn_train_fwd")
         else:
             mean = _f32c(running_mean)
             rstd = torch.rsqrt(_f32c(running_var) + eps)   # C values: parameter preparation, not activation math
-            check(lib().amoe_bn_apply_fwd(h, ptr(conv), ptr(mean), ptr(rstd), ptr(g2), ptr(b2), ptr(y), M, Cout, 1, st),
+            check(lib().amoe_bn_apply_fwd(h, ptr(conv), ptr(mean), ptr(rstd), ptr(g2), ptr(b2), ptr(y), M, Cout, int(relu), st),
                   "bn_apply_fwd")
-        ctx_.save_for_backward(x2, wp, conv, y, g2, mean, rstd)
-        ctx_.cfg = (stride, padding, batch_stats, Cin, bias is not None)
+        ctx_.save_for_backward(x2, wp, conv, y if relu else None, g2, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx_, dy):
-        x2, wp, conv, y, g2, mean, rstd = ctx_.saved_tensors
-        stride, padding, batch_stats, Cin, has_bias = ctx_.cfg
+        stride, padding, bn_mode, relu, Cin, has_bias = ctx_.cfg
         dy = _f32c(dy)
+        dgamma = dbeta = None
+        if bn_mode == BN_NONE:
+            x2, wp, y = ctx_.saved_tensors
+            dev = x2.device
+            h, st = ctx(dev), stream_ptr(dev)
+            if relu:
+                dconv = torch.empty_like(dy)
+                check(lib().amoe_relu_bwd(h, ptr(dy), ptr(y), ptr(dconv), dy.numel(), st), "relu_bwd")
+            else:
+                dconv = dy
+            B, Ho, Wo, Cout = dconv.shape
+            M = B * Ho * Wo
+            ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
+        else:
+            x2, wp, conv, y, g2, mean, rstd = ctx_.saved_tensors
+            dev = x2.device
+            h, st = ctx(dev), stream_ptr(dev)
+            B, Ho, Wo, Cout = conv.shape
+            M = B * Ho * Wo
+            ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
+            dconv = torch.empty_like(conv)
+            dgamma = torch.empty(Cout, device=dev, dtype=torch.float32)
+            dbeta = torch.empty(Cout, device=dev, dtype=torch.float32)
+            check(lib().amoe_bn_bwd(h, ptr(dy), ptr(conv), ptr(y), ptr(g2), ptr(mean), ptr(rstd), ptr(dconv), ptr(dgamma),
+                                    ptr(dbeta), ptr(ws), M, Cout, int(bn_mode == BN_BATCH), st), "bn_bwd")
         B, H, W, Cx = x2.shape
-        _, Ho, Wo, Cout = conv.shape
         KH, KW = wp.shape[1], wp.shape[2]
-        dev = x2.device
-        h, st = ctx(dev), stream_ptr(dev)
-        M = B * Ho * Wo
-        ws = torch.empty(max(1, lib().amoe_colreduce_workspace_floats(M, Cout)), device=dev, dtype=torch.float32)
-        dconv = torch.empty_like(conv)
-        dgamma = torch.empty(Cout, device=dev, dtype=torch.float32)
-        dbeta = torch.empty(Cout, device=dev, dtype=torch.float32)
-        check(lib().amoe_bn_bwd(h, ptr(dy), ptr(conv), ptr(y), ptr(g2), ptr(mean), ptr(rstd), ptr(dconv), ptr(dgamma),
-                                ptr(dbeta), ptr(ws), M, Cout, int(batch_stats), st), "bn_bwd")
         dbias = None
         if has_bias and ctx_.needs_input_grad[2]:
             dbias = torch.empty(Cout, device=dev, dtype=torch.float32)
@@ -225,23 +246,111 @@ class _ConvBNReLU(torch.autograd.Function):
             dx = torch.empty_like(x2)
             check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
                                              padding, padding, Ho, Wo, st), "conv2d_bwd_data")
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
-def conv_bn_relu(x_nhwc, conv: nn.Conv2d, bn: nn.BatchNorm2d, batch_stats: bool) -> torch.Tensor:
+def conv_bn_act(x_nhwc, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], relu: bool, batch_stats: Optional[bool] = None):
+    """conv [+ BatchNorm] [+ ReLU].  batch_stats defaults to bn.training."""
     if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:
         raise NotImplementedError("training conv kernels take square stride/padding")
+    if bn is None:
+        return _ConvBNAct.apply(x_nhwc, conv.weight, conv.bias, None, None, None, None, conv.stride[0], conv.padding[0],
+                                0.0, 0.0, BN_NONE, relu)
+    if batch_stats is None:
+        batch_stats = bn.training
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    if batch_stats and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
     rm, rv = bn.running_mean, bn.running_var
-    if batch_stats and (rm is None or rv is None):
+    if rm is None or rv is None:
         raise NotImplementedError("BatchNorm2d(track_running_stats=False) is not supported by the training kernels")
-    y = _ConvBNReLU.apply(x_nhwc, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, conv.stride[0], conv.padding[0],
-                          momentum, bn.eps, batch_stats)
+    if batch_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    y = _ConvBNAct.apply(x_nhwc, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, conv.stride[0], conv.padding[0],
+                         momentum, bn.eps, BN_BATCH if batch_stats else BN_RUNNING, relu)
     if batch_stats:   # the kernel updated the running statistics through raw pointers: bump Tensor._version
         torch.autograd.graph.increment_version([rm, rv])
     return y
+
+
+def conv_bn_relu(x_nhwc, conv: nn.Conv2d, bn: nn.BatchNorm2d, batch_stats: bool) -> torch.Tensor:
+    return conv_bn_act(x_nhwc, conv, bn, relu=True, batch_stats=batch_stats)
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    """nn.MaxPool2d(3, stride 2, padding 1) on NHWC fp32."""
+
+    @staticmethod
+    def forward(ctx_, x):
+        x2 = _f32c(x)
+        B, H, W, Cc = x2.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, Ho, Wo, Cc), device=x2.device, dtype=torch.float32)
+        check(lib().amoe_maxpool3x3s2_fwd(ctx(x2.device), ptr(x2), ptr(y), B, H, W, Cc, _cabi.F32, 0, stream_ptr(x2.device)),
+              "maxpool3x3s2_fwd")
+        ctx_.save_for_backward(x2)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        (x2,) = ctx_.saved_tensors
+        dy = _f32c(dy)
+        B, H, W, Cc = x2.shape
+        dx = torch.empty_like(x2)
+        check(lib().amoe_maxpool3x3s2_bwd(ctx(x2.device), ptr(x2), ptr(dy), ptr(dx), B, H, W, Cc, stream_ptr(x2.device)),
+              "maxpool3x3s2_bwd")
+        return dx
+
+
+def max_pool3x3s2(x_nhwc) -> torch.Tensor:
+    return _MaxPool3x3s2.apply(x_nhwc)
+
+
+class _AddReLU(torch.autograd.Function):
+    """BasicBlock tail: relu(main + identity)."""
+
+    @staticmethod
+    def forward(ctx_, a, b):
+        a2, b2 = _f32c(a), _f32c(b)
+        y = torch.empty_like(a2)
+        check(lib().amoe_add_relu_fwd(ctx(a2.device), ptr(a2), ptr(b2), ptr(y), a2.numel(), stream_ptr(a2.device)), "add_relu_fwd")
+        ctx_.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        (y,) = ctx_.saved_tensors
+        dy = _f32c(dy)
+        g = torch.empty_like(y)
+        check(lib().amoe_relu_bwd(ctx(y.device), ptr(dy), ptr(y), ptr(g), y.numel(), stream_ptr(y.device)), "relu_bwd")
+        return g, g
+
+
+def add_relu(a, b) -> torch.Tensor:
+    return _AddReLU.apply(a, b)
+
+
+class _DetLoss(torch.autograd.Function):
+    """CrossEntropy(ignore_index=num_classes) + w * SmoothL1 over the matched queries; `head_out` is the
+    NHWC head output [B,h,w,C+4] (class logits then box deltas in the channel axis)."""
+
+    @staticmethod
+    def forward(ctx_, head_out, target_classes, target_boxes, num_classes: int, bbox_weight: float):
+        ho = _f32c(head_out)
+        B, h, w, Ct = ho.shape
+        rows = B * h * w
+        dev = ho.device
+        losses = torch.empty(4, device=dev, dtype=torch.float32)
+        dho = torch.empty_like(ho)
+        base = ho.data_ptr()
+        check(lib().amoe_det_loss_fwd_bwd(ctx(dev), base, Ct, base + 4 * num_classes, Ct, ptr(target_classes), ptr(target_boxes),
+                                          rows, num_classes, num_classes, float(bbox_weight), ptr(losses), dho.data_ptr(), Ct,
+                                          dho.data_ptr() + 4 * num_classes, Ct, stream_ptr(dev)), "det_loss_fwd_bwd")
+        ctx_.save_for_backward(dho)
+        return losses
+
+    @staticmethod
+    def backward(ctx_, dlosses):
+        (dho,) = ctx_.saved_tensors
+        return dho * dlosses[0], None, None, None, None
 
 
 class _GlobalAvgPool(torch.autograd.Function):

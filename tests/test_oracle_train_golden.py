@@ -49,3 +49,30 @@ def test_training_oracle_matches_reference(name, golden_dir):
     for key in g.files:
         if key.startswith("full__"):
             assert rel_err(sd[key[6:]].grad, g[key]) < 2e-4, key
+
+
+def _det_expert_sd():
+    from automoe_b200.models.automoe import create_automoe_model
+    full = synth.synth_state_dict(create_automoe_model(synth.CONFIG_3EXPERT, "cpu").state_dict(), 0)
+    return {k[len("experts.0."):]: v for k, v in full.items() if k.startswith("experts.0.")}
+
+
+def test_detection_training_oracle_matches_reference(golden_dir):
+    """oracle/detection_train_oracle.py against the reference's BDDDetectionExpert + _train_detection_batch."""
+    from oracle import detection_train_oracle as DO
+    g = np.load(golden_dir / "det_train_b3_128x160.npz")
+    sd = {k: v.clone() for k, v in _det_expert_sd().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    batch = DO.synth_detection_batch(int(g["B"]), int(g["H"]), int(g["W"]), int(g["n_max"]), int(g["seed"]))
+    out = DO.detection_forward_train(batch["image"], sd)
+    losses = DO.detection_loss(out, batch["bboxes"], batch["labels"])
+    losses["total_loss"].backward()
+    assert abs(losses["total_loss"].item() - float(g["total_loss"])) < 2e-5 * float(g["total_loss"])
+    for n, norm in zip([str(x) for x in g["grad_names"]], g["grad_norms"]):
+        got = sd[n].grad.double().norm().item()
+        assert abs(got - norm) <= 1e-3 * max(norm, 1e-4) + 1e-7, (n, got, norm)
+    for key in g.files:
+        if key.startswith("full__") and float(np.abs(g[key]).max()) > 1e-6:
+            assert rel_err(sd[key[6:]].grad, g[key]) < 1e-3, key
