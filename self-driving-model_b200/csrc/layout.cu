@@ -55,6 +55,29 @@ __global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, 
   }
 }
 
+// bf16, Cp == 4, even W / left / Wpad: one thread converts TWO neighbouring padded pixels - three 8-byte
+// plane loads, one 16-byte store (the generic kernel issues four 2-byte stores per pixel)
+__global__ void image_nchw_to_nhwc4_padded_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C,
+                                                       int H, int W, int left, int Wpad2, int top, int Hpad,
+                                                       int64_t total2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total2) return;
+  const int wp = (int)(i % Wpad2) * 2;
+  const int64_t r = i / Wpad2;
+  const int hp = (int)(r % Hpad);
+  const int64_t b = r / Hpad;
+  const int w = wp - left, h = hp - top;
+  float2 v[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  if (w >= 0 && w < W && h >= 0 && h < H) {     // w even and W even: the pair is inside or outside together
+    const float* s = src + (b * C * H + h) * (int64_t)W + w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c < C) v[c] = __ldg(reinterpret_cast<const float2*>(s + (int64_t)c * H * W));
+  }
+  dst[i] = make_uint4(pack_bf16x2(v[0].x, v[1].x), pack_bf16x2(v[2].x, 0.f), pack_bf16x2(v[0].y, v[1].y),
+                      pack_bf16x2(v[2].y, 0.f));
+}
+
 template <typename T>
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout,
                                         int Cin, int KH, int KW, int Cin_pad) {
@@ -123,7 +146,12 @@ int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, i
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned blocks = (unsigned)((total + 255) / 256);
-  if (dst_dtype == AMOE_BF16)
+  if (dst_dtype == AMOE_BF16 && Cp == 4 && C <= 3 && W % 2 == 0 && left % 2 == 0 && Wpad % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t total2 = total / 2;
+    image_nchw_to_nhwc4_padded_bf16_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
+        src, (uint4*)dst, C, H, W, left, Wpad / 2, top, Hpad, total2);
+  } else if (dst_dtype == AMOE_BF16)
     image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
   else if (dst_dtype == AMOE_F32)
     image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
