@@ -57,6 +57,11 @@ int amoe_image_nchw_to_nhwc(amoe_ctx*, const float* src, void* dst, int B, int C
 int amoe_image_nchw_to_nhwc_padded(amoe_ctx*, const float* src, void* dst, int B, int C, int H,
                                    int W, int Cp, int left, int Wpad, int top, int Hpad,
                                    int dst_dtype, void* stream);
+/* Same with the padding channels (c >= C) set to pad_channel_value at EVERY position of the frame, the
+ * zero border included (1.0 lets the stem GEMM add folded biases through that channel). */
+int amoe_image_nchw_to_nhwc_padded_v(amoe_ctx*, const float* src, void* dst, int B, int C, int H,
+                                     int W, int Cp, int left, int Wpad, int top, int Hpad,
+                                     int dst_dtype, float pad_channel_value, void* stream);
 /* All first-layer convolutions of the frame (Cin=3, stride 2: the ResNet stems of the experts and
  * the policy's conv1) as one tensor-core GEMM over the raw image rows (csrc/stem_tc.cu).
  *   x_pad: [B,H+6,Wpad,4] bf16 from amoe_image_nchw_to_nhwc_padded(left=4, top=3), Wpad >= W+6
@@ -72,7 +77,11 @@ int amoe_stem_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* 
  * expert stems: resnet conv1+bn1+relu+maxpool in one kernel, the full-resolution stem output never
  * reaches HBM).  pooled: [n_pool_ch/64 * B][H/4+2*out_pad][W/4+2*out_pad][64] bf16; with
  * out_pad = 1 the zero border is written too.  Channels >= n_pool_ch go to dst/dst_c as above
- * (entries below n_pool_ch/32 are ignored).  H, W multiples of 4. */
+ * (entries below n_pool_ch/32 are ignored).  H, W multiples of 4.
+ * scale == bias == NULL selects FOLDED filters: w_img holds bf16(w * scale) and the bias split into two
+ * bf16 parts at K slots (kh=0, j=0, c=3) and (kh=0, j=1, c=3); the frame must be staged with
+ * pad_channel_value = 1 (amoe_image_nchw_to_nhwc_padded_v).  The epilogue then only packs, pools and
+ * applies the ReLU (the scale/bias epilogue costs more issue slots than the N=224 MMAs take). */
 int amoe_stem_pool_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* scale,
                        const float* bias, int B, int H, int W, int Wpad, int KH, int n_total,
                        int relu, int n_pool_ch, void* pooled, int out_pad, void* const* dst_host,

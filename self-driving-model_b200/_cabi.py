@@ -34,6 +34,7 @@ SIGNATURES = {
     "amoe_launch_count": (_L, [_P]),
     "amoe_image_nchw_to_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_image_nchw_to_nhwc_padded": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "amoe_image_nchw_to_nhwc_padded_v": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "amoe_stem_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, C.POINTER(_P), C.POINTER(_I), _P]),
     "amoe_stem_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_P), C.POINTER(_I), _P]),
     "amoe_conv2d_rowwin_fwd": (_I, [_P] * 6 + [_I] * 13 + [_P]),

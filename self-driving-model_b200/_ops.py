@@ -48,16 +48,18 @@ def image_to_nhwc(img: torch.Tensor, cp: int, dtype: torch.dtype) -> torch.Tenso
 
 
 def image_to_nhwc_padded(img: torch.Tensor, cp: int, left: int, wpad: int, dtype: torch.dtype, top: int = 0,
-                         hpad: Optional[int] = None) -> torch.Tensor:
-    """[B,C,H,W] fp32 NCHW -> [B,hpad,wpad,cp]: image pixel (h,w) at (top+h, left+w), zeros elsewhere."""
+                         hpad: Optional[int] = None, pad_value: float = 0.0) -> torch.Tensor:
+    """[B,C,H,W] fp32 NCHW -> [B,hpad,wpad,cp]: image pixel (h,w) at (top+h, left+w), zeros elsewhere;
+    the padding channels (c >= C) hold pad_value at every position."""
     if img.dtype != torch.float32:
         img = img.float()
     img = img.contiguous()
     B, Cc, H, W = img.shape
     hpad = H if hpad is None else hpad
     out = torch.empty((B, hpad, wpad, cp), device=img.device, dtype=dtype)
-    check(lib().amoe_image_nchw_to_nhwc_padded(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp, left, wpad, top, hpad,
-                                               dtype_code(dtype), stream_ptr(img.device)), "image_nchw_to_nhwc_padded")
+    check(lib().amoe_image_nchw_to_nhwc_padded_v(ctx(img.device), ptr(img), ptr(out), B, Cc, H, W, cp, left, wpad, top, hpad,
+                                                 dtype_code(dtype), float(pad_value), stream_ptr(img.device)),
+          "image_nchw_to_nhwc_padded")
     return out
 
 
@@ -74,9 +76,18 @@ def stem_wpad(W: int) -> int:
 
 
 def stage_image_stem(img: torch.Tensor) -> torch.Tensor:
-    """Frame in the layout amoe_stem_fwd reads: [B,H+6,Wpad,4] bf16, 3 zero rows top/bottom, 4 zero px left."""
+    """Frame in the layout amoe_stem_fwd reads: [B,H+6,Wpad,4] bf16, 3 zero rows top/bottom, 4 zero px left.
+    The 4th (padding) channel is 1.0 everywhere: the folded stem filters add their bias through it; the
+    unfolded filters have zeros there, so it is inert for them."""
     H, W = img.shape[2], img.shape[3]
-    return image_to_nhwc_padded(img, 4, STEM_LEFT, stem_wpad(W), torch.bfloat16, top=STEM_TOP, hpad=H + 6)
+    return image_to_nhwc_padded(img, 4, STEM_LEFT, stem_wpad(W), torch.bfloat16, top=STEM_TOP, hpad=H + 6, pad_value=1.0)
+
+
+def stem_fold() -> bool:
+    """Fused stem+pool kernel with BatchNorm folded into the filters / bias on the padding channel
+    (AMOE_STEM_FOLD=0: scale/bias applied in fp32 in the epilogue, weights rounded exactly like autocast's)."""
+    import os
+    return os.environ.get("AMOE_STEM_FOLD", "1") != "0"
 
 
 @dataclass
@@ -90,6 +101,7 @@ class PackedStem:
     n_total: int
     relu: bool
     true_macs_per_px: int  # sum over convs of cout*cin*kh*kw (algorithmic work per output pixel)
+    w_folded: Optional[torch.Tensor] = None   # same image with scale folded in and the bias on channel 3 (see stem_tc.cu)
 
 
 def pack_stem(convs, bns, device, relu: bool = True) -> PackedStem:
@@ -126,7 +138,17 @@ def pack_stem(convs, bns, device, relu: bool = True) -> PackedStem:
     # [n][k = kh*32 + j*4 + c] -> [k/8][n][8]
     k_total = STEM_KH * 32
     img = wk.reshape(n_total, k_total // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
-    return PackedStem(img, scale, bias, couts, n_total, relu, macs)
+    folded = None
+    if all(c.weight.shape[1] <= 3 for c in convs):
+        # scale folded into the filters; bias = hi + lo (two bf16 values) on the frame's padding channel, which
+        # stage_image_stem fills with ones: slots (kh=0, j=0, c=3) and (kh=0, j=1, c=3) are never filter taps
+        wf = wk * scale.view(-1, 1, 1, 1)
+        assert float(wf[:, 0, 0:2, 3].abs().max()) == 0.0
+        hi = bias.to(torch.bfloat16).float()
+        wf[:, 0, 0, 3] = hi
+        wf[:, 0, 1, 3] = bias - hi
+        folded = wf.reshape(n_total, k_total // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    return PackedStem(img, scale, bias, couts, n_total, relu, macs, folded)
 
 
 def stem_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: int,
@@ -180,7 +202,9 @@ def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: in
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().amoe_stem_pool_fwd(ctx(dev), ptr(x_pad), ptr(ps.w), ptr(ps.scale), ptr(ps.bias), B, H, W, x_pad.shape[2],
+    fold = ps.w_folded is not None and stem_fold()
+    check(lib().amoe_stem_pool_fwd(ctx(dev), ptr(x_pad), ptr(ps.w_folded if fold else ps.w), None if fold else ptr(ps.scale),
+                                   None if fold else ptr(ps.bias), B, H, W, x_pad.shape[2],
                                    STEM_KH, ps.n_total, int(ps.relu), n_pool * 64, ptr(pooled), out_pad, dst, dst_c,
                                    stream_ptr(dev)), "stem_pool_fwd")
     if prof is not None:

@@ -38,7 +38,7 @@ __global__ void image_nchw_to_nhwc4_bf16_kernel(const float* __restrict__ src,
 template <typename T>
 __global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, T* __restrict__ dst, int C,
                                                  int H, int W, int Cp, int left, int Wpad, int top, int Hpad,
-                                                 int64_t total) {
+                                                 float pad_ch, int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int wp = (int)(i % Wpad);
@@ -50,7 +50,7 @@ __global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, 
   const float* s = src + (b * C * H + h) * (int64_t)W + w;
   T* d = dst + i * Cp;
   for (int c = 0; c < Cp; ++c) {
-    float v = (in && c < C) ? __ldg(s + (int64_t)c * H * W) : 0.f;
+    float v = c < C ? (in ? __ldg(s + (int64_t)c * H * W) : 0.f) : pad_ch;
     st_from_float<T>(d + c, v);
   }
 }
@@ -59,7 +59,7 @@ __global__ void image_nchw_to_nhwc_padded_kernel(const float* __restrict__ src, 
 // plane loads, one 16-byte store (the generic kernel issues four 2-byte stores per pixel)
 __global__ void image_nchw_to_nhwc4_padded_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C,
                                                        int H, int W, int left, int Wpad2, int top, int Hpad,
-                                                       int64_t total2) {
+                                                       float pad_ch, int64_t total2) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total2) return;
   const int wp = (int)(i % Wpad2) * 2;
@@ -74,8 +74,9 @@ __global__ void image_nchw_to_nhwc4_padded_bf16_kernel(const float* __restrict__
     for (int c = 0; c < 3; ++c)
       if (c < C) v[c] = __ldg(reinterpret_cast<const float2*>(s + (int64_t)c * H * W));
   }
-  dst[i] = make_uint4(pack_bf16x2(v[0].x, v[1].x), pack_bf16x2(v[2].x, 0.f), pack_bf16x2(v[0].y, v[1].y),
-                      pack_bf16x2(v[2].y, 0.f));
+  // channel 3 is padding: pad_ch everywhere (also outside the image) - 0, or 1 when it carries folded biases
+  dst[i] = make_uint4(pack_bf16x2(v[0].x, v[1].x), pack_bf16x2(v[2].x, pad_ch), pack_bf16x2(v[0].y, v[1].y),
+                      pack_bf16x2(v[2].y, pad_ch));
 }
 
 template <typename T>
@@ -139,6 +140,12 @@ int amoe_image_nchw_to_nhwc(amoe_ctx* ctx, const float* src, void* dst, int B, i
 
 int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
                                    int Cp, int left, int Wpad, int top, int Hpad, int dst_dtype, void* stream) {
+  return amoe_image_nchw_to_nhwc_padded_v(ctx, src, dst, B, C, H, W, Cp, left, Wpad, top, Hpad, dst_dtype, 0.f, stream);
+}
+
+int amoe_image_nchw_to_nhwc_padded_v(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
+                                     int Cp, int left, int Wpad, int top, int Hpad, int dst_dtype, float pad_channel_value,
+                                     void* stream) {
   AMOE_REQUIRE(ctx && src && dst, "amoe_image_nchw_to_nhwc_padded: NULL argument");
   AMOE_REQUIRE(Cp >= C && C >= 1 && left >= 0 && Wpad >= left + W && top >= 0 && Hpad >= top + H,
                "amoe_image_nchw_to_nhwc_padded: bad geometry");
@@ -150,11 +157,11 @@ int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, i
       (reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int64_t total2 = total / 2;
     image_nchw_to_nhwc4_padded_bf16_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
-        src, (uint4*)dst, C, H, W, left, Wpad / 2, top, Hpad, total2);
+        src, (uint4*)dst, C, H, W, left, Wpad / 2, top, Hpad, pad_channel_value, total2);
   } else if (dst_dtype == AMOE_BF16)
-    image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
+    image_nchw_to_nhwc_padded_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, C, H, W, Cp, left, Wpad, top, Hpad, pad_channel_value, total);
   else if (dst_dtype == AMOE_F32)
-    image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, top, Hpad, total);
+    image_nchw_to_nhwc_padded_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, C, H, W, Cp, left, Wpad, top, Hpad, pad_channel_value, total);
   else
     AMOE_REQUIRE(false, "amoe_image_nchw_to_nhwc_padded: bad dtype %d", dst_dtype);
   AMOE_LAUNCH_OK(ctx);

@@ -293,6 +293,16 @@ __device__ __forceinline__ void bn_pack32(const uint32_t (&a)[32], const float* 
   }
 }
 
+// 32 accumulator columns -> 4 x 8 packed bf16 (folded mode: nothing left to apply)
+__device__ __forceinline__ void pack32(const uint32_t (&a)[32], uint4 (&q)[4]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    q[v] = make_uint4(pack_bf16x2(__uint_as_float(a[v * 8 + 0]), __uint_as_float(a[v * 8 + 1])),
+                      pack_bf16x2(__uint_as_float(a[v * 8 + 2]), __uint_as_float(a[v * 8 + 3])),
+                      pack_bf16x2(__uint_as_float(a[v * 8 + 4]), __uint_as_float(a[v * 8 + 5])),
+                      pack_bf16x2(__uint_as_float(a[v * 8 + 6]), __uint_as_float(a[v * 8 + 7])));
+}
+
 // Epilogue organisation: the eight epilogue warps form two groups; warps g*4+lq of both groups read
 // TMEM lane quarter lq (output pixels 32*lq..+31) and split the 32-channel chunks between them
 // (group 0: first half of the pooled chunks; group 1: second half + the full-resolution chunks).
@@ -300,6 +310,10 @@ __device__ __forceinline__ void bn_pack32(const uint32_t (&a)[32], const float* 
 // chunk) carries conv row 2py-1 into pooled row py, conv row 2py folds in, and conv row 2py+1 both
 // completes the pooled row and becomes the next carry.  Only the completed vertical max goes through
 // shared memory, once per POOLED row, for the horizontal 3-max at even columns.
+// FOLDED: the BatchNorm scale is folded into the packed filters and the bias rides on the frame's padding
+// channel (staged as 1.0; filter slots (kh=0, j=0/1, c=3) hold the bias split into two bf16 parts), so the
+// accumulator already is scale*conv+bias and the epilogue only packs, pools and applies the ReLU.
+template <bool FOLDED>
 __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
   const Params& p = pp.base;
   extern __shared__ uint8_t smem_raw[];
@@ -321,9 +335,11 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
   const uint32_t bar_tempty = smem_u32(&bars[2 * POOL_A_STAGES + 2]);
   const uint32_t bar_w = smem_u32(&bars[2 * POOL_A_STAGES + 4]);
 
-  for (int i = threadIdx.x; i < p.n_total; i += POOL_THREADS) {
-    s_scale[i] = __ldg(p.scale + i);
-    s_bias[i] = __ldg(p.bias + i);
+  if (!FOLDED) {
+    for (int i = threadIdx.x; i < p.n_total; i += POOL_THREADS) {
+      s_scale[i] = __ldg(p.scale + i);
+      s_bias[i] = __ldg(p.bias + i);
+    }
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < POOL_A_STAGES; ++s) {
@@ -403,14 +419,6 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
     const int c_cnt = grp ? pool_chunks - h0 : h0;  // <= 3 pooled chunks owned by this warp
     const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
     const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
-    // horizontal pass mapping: thread -> (pixel lane, channel vector v); a pass covers px_per_pass pooled
-    // pixels, so the per-pass offsets are plain multiples (no per-item tables, no spills)
-    const int px_per_pass = POOL_EPI_THREADS / NV;          // 32 / 16 / 10 for 1 / 2 / 3 experts
-    const int h_px0 = te / NV, h_v = te - h_px0 * NV;
-    const bool h_active = h_px0 < px_per_pass;
-    const int h_r0 = (2 * h_px0) * R_PITCH + h_v * 16;
-    const int64_t h_g0 = ((int64_t)(h_v >> 3) * p.B * Hq * Wq + h_px0 + pp.out_pad) * 64 + (h_v & 7) * 8;
-    const int h_rstep = 2 * px_per_pass * R_PITCH, h_gstep = px_per_pass * 64;
     uint4 V[3][4];  // running vertical max of the owned chunks (registers)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
@@ -428,25 +436,58 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
       if (role == ROLE_ODD) asm volatile("bar.sync 1, 256;" ::: "memory");  // previous horizontal pass has left sR
       uint32_t a[32];
+      if (FOLDED) {
+        // 16-column TMEM loads, one always in flight behind the half-chunk being packed (same 32 registers as
+        // one 32-column load; a second 32-column buffer would spill)
+        uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&a[0]);
+        uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&a[16]);
+        if (c_cnt > 0) tmem_ld_32x32b_x16(taddr + (uint32_t)(c_begin * 32), lo);
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        if (ci < c_cnt) {
-          const int c = c_begin + ci;
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
-          tmem_ld_wait();
-          uint4 q[4];
-          bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);   // ReLU commutes with max: applied once after pooling
-          if (fresh) {
+        for (int hc = 0; hc < 6; ++hc) {
+          if (hc < 2 * c_cnt) {
+            const int ci = hc >> 1, c = c_begin + ci, half = hc & 1;
+            tmem_ld_wait();
+            if (hc + 1 < 2 * c_cnt) tmem_ld_32x32b_x16(taddr + (uint32_t)(c_begin * 32 + (hc + 1) * 16), half ? lo : hi);
+            const uint32_t (&cur)[16] = half ? hi : lo;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) V[ci][v] = q[v];
-          } else if (role == ROLE_EVEN) {
+            for (int vv = 0; vv < 2; ++vv) {
+              const int v = half * 2 + vv;
+              const uint4 q = make_uint4(pack_bf16x2(__uint_as_float(cur[vv * 8 + 0]), __uint_as_float(cur[vv * 8 + 1])),
+                                         pack_bf16x2(__uint_as_float(cur[vv * 8 + 2]), __uint_as_float(cur[vv * 8 + 3])),
+                                         pack_bf16x2(__uint_as_float(cur[vv * 8 + 4]), __uint_as_float(cur[vv * 8 + 5])),
+                                         pack_bf16x2(__uint_as_float(cur[vv * 8 + 6]), __uint_as_float(cur[vv * 8 + 7])));
+              if (fresh) {
+                V[ci][v] = q;
+              } else if (role == ROLE_EVEN) {
+                V[ci][v] = hmax8(V[ci][v], q);
+              } else {
+                *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q);
+                V[ci][v] = q;   // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) V[ci][v] = hmax8(V[ci][v], q[v]);
-          } else {
+        for (int ci = 0; ci < 3; ++ci) {
+          if (ci < c_cnt) {
+            const int c = c_begin + ci;
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+            tmem_ld_wait();
+            uint4 q[4];
+            bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);   // ReLU commutes with max: applied once after pooling
+            if (fresh) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q[v]);
-              V[ci][v] = q[v];   // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
+              for (int v = 0; v < 4; ++v) V[ci][v] = q[v];
+            } else if (role == ROLE_EVEN) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) V[ci][v] = hmax8(V[ci][v], q[v]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q[v]);
+                V[ci][v] = q[v];   // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
+              }
             }
           }
         }
@@ -459,8 +500,18 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
           tmem_ld_wait();
           if (valid && role != ROLE_CARRY) {
             uint4 q[4];
-            if (p.relu) bn_pack32<true>(a, s_scale + c * 32, s_bias + c * 32, q);
-            else bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
+            if (FOLDED) {
+              pack32(a, q);
+              if (p.relu) {
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) q[v] = hmax8(q[v], zero);
+              }
+            } else if (p.relu) {
+              bn_pack32<true>(a, s_scale + c * 32, s_bias + c * 32, q);
+            } else {
+              bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
+            }
 #pragma unroll
             for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = q[v];
           }
@@ -471,17 +522,26 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
       if (role != ROLE_ODD) continue;
       asm volatile("bar.sync 1, 256;" ::: "memory");       // vertical max of pooled row py staged
-      // horizontal 3-max at even columns, then the ReLU (max with 0 on the packed bf16 pairs)
-      if (h_active) {
-        __nv_bfloat16* g = pp.pooled + ((int64_t)b * Hq + py + pp.out_pad) * Wq * 64 + h_g0;
-        const uint8_t* r0 = sR + h_r0;
-        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      // horizontal 3-max at even columns, then the ReLU (max with 0 on the packed bf16 pairs).
+      // mapping: thread -> (pixel lane, channel vector v); a pass covers px_per_pass pooled pixels.  The index
+      // math is redone per pooled row on purpose: hoisting it out of the tile loop made ptxas spill it to local
+      // memory, and those reloads (L1 misses under the streaming stores) cost more than the divisions.
+      {
+        const int px_per_pass = POOL_EPI_THREADS / NV;          // 32 / 16 / 10 for 1 / 2 / 3 experts
+        const int h_px0 = te / NV, h_v = te - h_px0 * NV;
+        if (h_px0 < px_per_pass) {
+          __nv_bfloat16* g = pp.pooled + (((int64_t)(h_v >> 3) * p.B + b) * Hq + py + pp.out_pad) * (int64_t)Wq * 64 +
+                             (h_px0 + pp.out_pad) * 64 + (h_v & 7) * 8;
+          const uint8_t* r0 = sR + (2 * h_px0) * R_PITCH + h_v * 16;
+          const int h_rstep = 2 * px_per_pass * R_PITCH, h_gstep = px_per_pass * 64;
+          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 2
-        for (int px = h_px0; px < pp.Wp; px += px_per_pass, r0 += h_rstep, g += h_gstep) {
-          uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
-          if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
-          if (p.relu) m = hmax8(m, zero);
-          *reinterpret_cast<uint4*>(g) = m;
+          for (int px = h_px0; px < pp.Wp; px += px_per_pass, r0 += h_rstep, g += h_gstep) {
+            uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
+            if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
+            if (p.relu) m = hmax8(m, zero);
+            *reinterpret_cast<uint4*>(g) = m;
+          }
         }
       }
       if (pp.out_pad) {
@@ -524,7 +584,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
 int amoe_stem_init(amoe_ctx* ctx) {
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return 0;
 }
 
@@ -555,7 +616,10 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
                       (size_t)128 * R_PITCH + 256;
   AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
-  stem_pool_kernel<<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
+  if (scale == nullptr)
+    stem_pool_kernel<true><<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
+  else
+    stem_pool_kernel<false><<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
@@ -565,6 +629,7 @@ extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img
                              void* const* dst_host, const int* dst_c_host, void* stream) {
   using namespace stem;
   AMOE_REQUIRE(ctx != nullptr, "amoe_stem_fwd: NULL ctx");
+  AMOE_REQUIRE(scale != nullptr, "amoe_stem_fwd: folded filters (scale == NULL) are only taken by amoe_stem_pool_fwd");
   Params p;
   int rc = stem_fill(p, x_pad, w_img, scale, bias, B, H, W, Wpad, KH, n_total, relu, dst_host, dst_c_host, 0);
   if (rc) return rc;
@@ -581,7 +646,8 @@ static int stem_fill(stem::Params& p, const void* x_pad, const void* w_img, cons
                      int B, int H, int W, int Wpad, int KH, int n_total, int relu, void* const* dst_host,
                      const int* dst_c_host, int first_dst_chunk) {
   using namespace stem;
-  AMOE_REQUIRE(x_pad && w_img && scale && bias && dst_host && dst_c_host, "amoe_stem_fwd: NULL argument");
+  AMOE_REQUIRE(x_pad && w_img && dst_host && dst_c_host, "amoe_stem_fwd: NULL argument");
+  AMOE_REQUIRE((scale == nullptr) == (bias == nullptr), "amoe_stem_fwd: scale and bias come together");
   AMOE_REQUIRE(H % 2 == 0 && W % 2 == 0, "amoe_stem_fwd: H and W must be even (got %dx%d)", H, W);
   AMOE_REQUIRE(n_total % 32 == 0 && n_total >= 32 && n_total <= 256, "amoe_stem_fwd: n_total=%d must be a multiple of 32 in [32,256]", n_total);
   AMOE_REQUIRE(KH >= 1 && KH <= 7, "amoe_stem_fwd: KH=%d out of range", KH);

@@ -209,7 +209,9 @@ def test_stem_tc(case):
     ps = _ops.pack_stem(convs, bns, torch.device(DEV), relu=True)
     xp = _ops.stage_image_stem(img)
     assert torch.equal(xp[:, 3:3 + H, 4:4 + W, :3].float(), img.permute(0, 2, 3, 1))
-    assert (xp[:, :3] == 0).all() and (xp[:, 3 + H:] == 0).all() and (xp[:, :, :4] == 0).all() and (xp[:, :, 4 + W:] == 0).all()
+    rgb = xp[..., :3]   # the image channels have a zero border; the padding channel is 1.0 everywhere (folded-bias carrier)
+    assert (rgb[:, :3] == 0).all() and (rgb[:, 3 + H:] == 0).all() and (rgb[:, :, :4] == 0).all() and (rgb[:, :, 4 + W:] == 0).all()
+    assert (xp[..., 3] == 1).all()
     groups = ([n_exp] if n_exp else []) + ([1] if with_policy else [])
     outs = _ops.stem_forward(ps, xp, B, H, W, groups=groups)
     torch.cuda.synchronize()
@@ -229,9 +231,12 @@ def test_stem_tc(case):
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("case", [(3, True, 2, 64, 64, 1), (3, True, 3, 256, 256, 1), (1, False, 2, 224, 224, 0),
                                   (3, True, 5, 32, 32, 1), (1, True, 150, 16, 16, 0), (3, True, 2, 256, 128, 1)])
-def test_stem_pool_fused(case):
-    """Stem GEMM with the ResNet max-pool fused behind the expert channels (policy conv1 stays full-res)."""
+@pytest.mark.parametrize("fold", ["1", "0"])
+def test_stem_pool_fused(case, fold, monkeypatch):
+    """fold=1: BatchNorm scale folded into the bf16 filters, bias carried by the frame's padding channel;
+    fold=0: fp32 scale/bias epilogue.  Stem GEMM with the ResNet max-pool fused behind the expert channels (policy conv1 stays full-res)."""
     from automoe_b200 import _ops
+    monkeypatch.setenv("AMOE_STEM_FOLD", fold)
     n_exp, with_policy, B, H, W, out_pad = case
     g = torch.Generator().manual_seed(12)
     convs, bns = [], []
