@@ -62,6 +62,18 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def conv_traffic(launches_per_step):
+    """DRAM bytes per launch of the tensor-core conv launches, from the committed ncu pass (tools/summarize_launches.py);
+    None when the capture is missing or was taken with a different launch count."""
+    p = ROOT / "profiles" / "conv_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    if d.get("conv_launches") != launches_per_step:
+        return None
+    return d["dram_bytes_per_launch"]
+
+
 def model_config():
     return {
         "experts": [
@@ -340,7 +352,8 @@ def run_b200(args):
         ach = f / (t / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all layers)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "peak_source": f"{pk['src']} (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                "traffic": conv_traffic(n // 2), "peak_source": f"{pk['src']} (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                "achieved_per_launch_gflop": f / n / 1e9, "algorithmic_dram_bytes_per_launch": 43e6 * B / (n // 2),
                 "launches_per_step": n // 2, "ms_per_step": t / 2,
                 "share_of_step": (t / 2) / (ms / args.steps),
                 "whole_forward_frac": (value / world) * GFLOP_PER_FRAME * 1e9 / 1e12 / pk["tf_sustained"]}

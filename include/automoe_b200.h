@@ -334,6 +334,10 @@ int amoe_maxpool3x3s2_bwd(amoe_ctx*, const float* x, const float* dy, float* dx,
 /* BasicBlock tail: y = relu(a + b) (n % 4 == 0); g = dy * [y > 0] (the gradient of both addends). */
 int amoe_add_relu_fwd(amoe_ctx*, const float* a, const float* b, float* y, int64_t n, void* stream);
 int amoe_relu_bwd(amoe_ctx*, const float* dy, const float* y, float* g, int64_t n, void* stream);
+/* Backward of amoe_upsample_bilinear_nchw_fwd (segmentation / drivable expert training,
+ * train_bdd100k_ddp.py:188-194): dy [B,C,H,W] fp32 -> dlow [B,h,w,C] fp32. */
+int amoe_upsample_bilinear_nchw_bwd(amoe_ctx*, const float* dy, float* dlow, int B, int h, int w,
+                                    int C, int H, int W, void* stream);
 /* Scatter of the Hungarian assignment (train_bdd100k_ddp.py:167-170) for the whole batch in one launch:
  * for matched pair m of image batch_of[m]: target_classes[batch_of[m]*Q + pred_idx[m]] = labels[m],
  * target_boxes[...] = boxes[m] (cxcywh).  The caller pre-fills classes with num_classes, boxes with 0. */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "amoe_maxpool3x3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_add_relu_fwd": (_I, [_P, _P, _P, _P, _L, _P]),
     "amoe_relu_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
+    "amoe_upsample_bilinear_nchw_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_det_targets": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "amoe_det_loss_fwd_bwd": (_I, [_P, _P, _I, _P, _I, _P, _P, _L, _I, _I, _F, _P, _P, _I, _P, _I, _P]),
 }

@@ -61,6 +61,59 @@ __global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __r
   g[i] = make_float4(v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f);
 }
 
+// Adjoint of F.interpolate(low, size=(H,W), mode="bilinear", align_corners=False) + the NHWC->NCHW transpose:
+// dlow[b,y,x,c] = sum over output pixels (Y,X) of dy[b,c,Y,X] * wy(Y,y) * wx(X,x), with the forward's index rule
+// (aten upsample_bilinear2d: src = max(scale*(dst+0.5)-0.5, 0)).  One warp per (b,c,y,x): lanes walk X of the
+// window of output pixels that can touch the cell (coalesced rows of dy), fixed summation order.
+__device__ __forceinline__ void up_src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+  float s = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)s, in_size - 1);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+__global__ void upsample_bilinear_nchw_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dlow, int h, int w, int C,
+                                                  int H, int W, float sh, float sw_, int64_t n_cells) {
+  const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (cell >= n_cells) return;
+  const int c = (int)(cell % C);
+  int64_t r = cell / C;
+  const int x = (int)(r % w);
+  r /= w;
+  const int y = (int)(r % h);
+  const int64_t b = r / h;
+  // output rows/cols whose source interval [i0, i1] can contain this cell (generous bounds, exact test inside)
+  const float inv_sh = 1.f / sh, inv_sw = 1.f / sw_;
+  const int Y0 = max(0, (int)floorf(((float)y - 1.f + 0.5f) * inv_sh - 0.5f) - 1);
+  const int Y1 = min(H - 1, (int)ceilf(((float)y + 1.f + 0.5f) * inv_sh - 0.5f) + 1);
+  const int X0 = max(0, (int)floorf(((float)x - 1.f + 0.5f) * inv_sw - 0.5f) - 1);
+  const int X1 = min(W - 1, (int)ceilf(((float)x + 1.f + 0.5f) * inv_sw - 0.5f) + 1);
+  const float* plane = dy + (b * C + c) * (int64_t)H * W;
+  float acc = 0.f;
+  for (int Y = Y0; Y <= Y1; ++Y) {
+    int y0, y1;
+    float ly;
+    up_src_index(sh, Y, h, y0, y1, ly);
+    float wy = 0.f;
+    if (y0 == y) wy += 1.f - ly;
+    if (y1 == y) wy += ly;
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int X = X0 + lane; X <= X1; X += 32) {
+      int xa, xb;
+      float lx;
+      up_src_index(sw_, X, w, xa, xb, lx);
+      float wx = 0.f;
+      if (xa == x) wx += 1.f - lx;
+      if (xb == x) wx += lx;
+      if (wx != 0.f) row = fmaf(plane[(int64_t)Y * W + X], wx, row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dlow[((b * h + y) * w + x) * (int64_t)C + c] = acc;
+}
+
 // target_classes[b*Q + pred_idx[m]] = labels[m]; target_boxes[...] = boxes[m]  for the matched pairs m of
 // image b = batch_of[m] (everything else: class = num_classes (ignored), box = 0; filled by the caller)
 __global__ void det_targets_kernel(const int64_t* __restrict__ pred_idx, const int32_t* __restrict__ batch_of,
@@ -179,6 +232,18 @@ int amoe_relu_bwd(amoe_ctx* ctx, const float* dy, const float* y, float* g, int6
   if (n == 0) return 0;
   relu_bwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)y,
                                                                                      (float4*)g, n / 4);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_upsample_bilinear_nchw_bwd(amoe_ctx* ctx, const float* dy, float* dlow, int B, int h, int w, int C, int H, int W,
+                                    void* stream) {
+  AMOE_REQUIRE(ctx && dy && dlow, "amoe_upsample_bilinear_nchw_bwd: NULL argument");
+  const int64_t cells = (int64_t)B * h * w * C;
+  if (cells == 0) return 0;
+  const float sh = (float)h / (float)H, sw_ = (float)w / (float)W;
+  upsample_bilinear_nchw_bwd_kernel<<<(unsigned)((cells * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dy, dlow, h, w, C, H, W,
+                                                                                                         sh, sw_, cells);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -40,14 +40,13 @@ class BDDExpertBase(nn.Module):
     def forward_train(self, x: torch.Tensor):
         """Differentiable forward (expert training): see _trunk.run_trunk_train."""
         from ._trunk import run_trunk_train
-        if self.upsample_to_input:
-            raise NotImplementedError("training of the up-sampling experts (segmentation / drivable) needs the bilinear "
-                                      "backward, which is not implemented yet; the detection expert trains (SURVEY 8 a12)")
         low = run_trunk_train(self, x)                      # [B,h,w,N] NHWC fp32
-        return self.format_output_train(low)
+        return self.format_output_train(low, x.shape[2], x.shape[3])
 
-    def format_output_train(self, low: torch.Tensor):
-        raise NotImplementedError
+    def format_output_train(self, low: torch.Tensor, H: int, W: int):
+        """Default (segmentation / drivable): differentiable x32 bilinear up-sampling to NCHW logits."""
+        from ...training import functional as TF
+        return TF.upsample_bilinear_nchw(low, H, W)
 
     def format_output(self, low: torch.Tensor, H: int, W: int, dtype: torch.dtype):
         raise NotImplementedError

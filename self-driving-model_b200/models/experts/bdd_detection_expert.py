@@ -26,7 +26,7 @@ class BDDDetectionExpert(BDDExpertBase):
             "bbox_deltas": out[:, self.num_classes:, :, :],
         }
 
-    def format_output_train(self, low):
+    def format_output_train(self, low, H=None, W=None):
         out = low.permute(0, 3, 1, 2)       # NCHW view of the NHWC head output (no copy)
         return {
             "class_logits": out[:, :self.num_classes, :, :],

@@ -328,6 +328,34 @@ def add_relu(a, b) -> torch.Tensor:
     return _AddReLU.apply(a, b)
 
 
+class _UpsampleBilinearNCHW(torch.autograd.Function):
+    """F.interpolate(low, size=(H,W), mode="bilinear", align_corners=False) from the NHWC head output to the
+    NCHW logits the segmentation / drivable experts return."""
+
+    @staticmethod
+    def forward(ctx_, low, H: int, W: int):
+        lo = _f32c(low)
+        B, h, w, Cc = lo.shape
+        out = torch.empty((B, Cc, H, W), device=lo.device, dtype=torch.float32)
+        check(lib().amoe_upsample_bilinear_nchw_fwd(ctx(lo.device), ptr(lo), ptr(out), B, h, w, Cc, H, W, _cabi.F32,
+                                                    stream_ptr(lo.device)), "upsample_bilinear_nchw_fwd")
+        ctx_.shape = (B, h, w, Cc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx_, dy):
+        B, h, w, Cc, H, W = ctx_.shape
+        dy = _f32c(dy)
+        dlow = torch.empty((B, h, w, Cc), device=dy.device, dtype=torch.float32)
+        check(lib().amoe_upsample_bilinear_nchw_bwd(ctx(dy.device), ptr(dy), ptr(dlow), B, h, w, Cc, H, W, stream_ptr(dy.device)),
+              "upsample_bilinear_nchw_bwd")
+        return dlow, None, None
+
+
+def upsample_bilinear_nchw(low_nhwc, H: int, W: int) -> torch.Tensor:
+    return _UpsampleBilinearNCHW.apply(low_nhwc, H, W)
+
+
 class _DetLoss(torch.autograd.Function):
     """CrossEntropy(ignore_index=num_classes) + w * SmoothL1 over the matched queries; `head_out` is the
     NHWC head output [B,h,w,C+4] (class logits then box deltas in the channel axis)."""

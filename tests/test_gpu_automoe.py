@@ -133,3 +133,26 @@ def test_l2_chunked_stem_layer1_is_bit_identical(model_sd, monkeypatch):
         assert torch.equal(outs["0"]["expert_outputs"][i], outs["6"]["expert_outputs"][i])
     for k in ("class_logits", "bbox_deltas"):
         assert torch.equal(outs["0"]["expert_outputs"][0][k], outs["6"]["expert_outputs"][0][k])
+
+
+def test_cuda_graph_capture_replays_the_eager_forward(model_sd):
+    """AutoMoE.capture(): replaying the captured graph on new inputs gives bit-identical outputs to the eager
+    call (same kernels, same order; side-stream logit writers joined inside the graph)."""
+    m, sd = model_sd
+    b1 = _to(synth.synth_batch(8, 256, 256, seed=31), DEV)
+    b2 = _to(synth.synth_batch(8, 256, 256, seed=32), DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        eager2 = m(b2)
+    g = m.capture(b1)
+    assert g.launches_per_replay >= 25
+    out = g(b2)
+    torch.cuda.synchronize()
+    for k in SMALL:
+        assert torch.equal(out[k], eager2[k]), k
+    for i in (1, 2):
+        assert torch.equal(out["expert_outputs"][i], eager2["expert_outputs"][i])
+    out1 = {k: v.clone() for k, v in g(b1).items() if torch.is_tensor(v)}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        eager1 = m(b1)
+    for k in SMALL:
+        assert torch.equal(out1[k], eager1[k]), k

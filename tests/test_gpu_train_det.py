@@ -178,8 +178,52 @@ def test_detection_training_step_matches_oracle_and_assignment_bit_exact():
         assert rel_l2(ours, ref) < 2e-2 and rel_err(ours, ref) < 5e-2, (k, rel_l2(ours, ref), rel_err(ours, ref))
 
 
-def test_seg_expert_training_raises_not_silently_wrong():
+@pytest.mark.parametrize("shape", [(2, 4, 5, 19, 128, 160), (1, 8, 8, 3, 256, 256), (2, 3, 3, 4, 50, 70)])
+def test_upsample_bilinear_fwd_bwd(shape):
+    """x32 (and non-integer scale) bilinear up-sampling NHWC -> NCHW against F.interpolate, forward and adjoint."""
+    from automoe_b200.training import functional as TF
+    B, h, w, C, H, W = shape
+    low = torch.randn((B, h, w, C), generator=_gen(8)).to(DEV).requires_grad_(True)
+    dy = torch.randn((B, C, H, W), generator=_gen(9)).to(DEV)
+    y = TF.upsample_bilinear_nchw(low, H, W)
+    y.backward(dy)
+    lr = low.detach().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yr = F.interpolate(lr, size=(H, W), mode="bilinear", align_corners=False)
+    yr.backward(dy)
+    assert rel_err(y.detach(), yr.detach()) < 1e-5
+    assert rel_err(low.grad.permute(0, 3, 1, 2), lr.grad) < 1e-5, rel_err(low.grad.permute(0, 3, 1, 2), lr.grad)
+
+
+def test_segmentation_expert_training_step_matches_oracle():
+    """BDDTrainer._train_segmentation_batch (train_bdd100k_ddp.py:188-194): expert forward in train mode +
+    nn.CrossEntropyLoss(ignore_index=255) (the reference's own torch loss on our differentiable output)."""
+    from automoe_b200.models.automoe import create_automoe_model
     from automoe_b200.models.experts import BDDSegmentationExpert
-    m = BDDSegmentationExpert(num_classes=19, pretrained_backbone=False).to(DEV).train()
-    with pytest.raises(NotImplementedError, match="bilinear"):
-        m(torch.randn(1, 3, 64, 64, device=DEV))
+    from oracle import automoe_oracle as O
+    full = synth.synth_state_dict(create_automoe_model(synth.CONFIG_3EXPERT, "cpu").state_dict(), 0)
+    sd = {k[len("experts.1."):]: v for k, v in full.items() if k.startswith("experts.1.")}
+    m = BDDSegmentationExpert(num_classes=19, pretrained_backbone=False)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    g = _gen(13)
+    x = torch.randn((2, 3, 64, 96), generator=g).to(DEV)
+    mask = torch.randint(0, 19, (2, 64, 96), generator=g)
+    mask[torch.rand((2, 64, 96), generator=g) < 0.1] = 255
+    mask = mask.to(DEV)
+    out = m(x)
+    assert out.shape == (2, 19, 64, 96) and out.requires_grad
+    loss = F.cross_entropy(out, mask, ignore_index=255)
+    loss.backward()
+    sdd = {k: v.to(DEV).clone() for k, v in sd.items()}
+    for k, v in sdd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    low = O.expert_head(DO.trunk_train(x, sdd, "backbone"), sdd, "decoder")
+    ref = F.interpolate(low, size=x.shape[-2:], mode="bilinear", align_corners=False)
+    lref = F.cross_entropy(ref, mask, ignore_index=255)
+    lref.backward()
+    assert rel_err(out.detach(), ref.detach()) < TOL
+    assert abs(loss.item() - lref.item()) < 1e-4 * abs(lref.item())
+    params = dict(m.named_parameters())
+    for k in ("decoder.2.weight", "decoder.2.bias", "decoder.0.weight", "backbone.7.1.conv2.weight", "backbone.0.weight"):
+        assert rel_l2(params[k].grad, sdd[k].grad) < 5e-3, (k, rel_l2(params[k].grad, sdd[k].grad))
