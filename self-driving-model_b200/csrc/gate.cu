@@ -33,29 +33,30 @@ struct GateDims {
   int mode;
 };
 
+template <int FT, bool CL>
 __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     GateDims d, const float* __restrict__ state, const float* __restrict__ pooled,
     const float* __restrict__ prm, float* __restrict__ context, float* __restrict__ features,
     float* __restrict__ processed, float* __restrict__ gate_logits, float* __restrict__ weights,
     float* __restrict__ combined) {
   extern __shared__ __align__(16) float sm[];
-  const int f0 = blockIdx.x * GATE_FT;
+  const int f0 = (CL ? blockIdx.x / CL_RANKS : blockIdx.x) * FT;
   const int gin = d.hidden + d.P * d.E;  // gate_network input width
   // shared-memory carve-up (all row strides multiples of 4 floats)
   const int ld_in = (int)al4(4 + d.sumC);
   float* s_in = sm;                                   // [FT][ld_in]: state(4) | pooled(sumC)
-  float* s_ctx = s_in + GATE_FT * ld_in;              // [FT][ctx]
-  float* s_h = s_ctx + GATE_FT * (int)al4(d.ctx_dim); // [FT][512] scratch hidden
-  float* s_feat = s_h + GATE_FT * EXT_HID;            // [FT][F] current expert feature
-  float* s_gin = s_feat + GATE_FT * (int)al4(d.F);    // [FT][gin]  ctxenc | processed_0..E-1
-  float* s_t = s_gin + GATE_FT * (int)al4(gin);       // [FT][max(P,hid)] scratch
-  float* s_w = s_t + GATE_FT * (int)al4(max(d.P, d.hidden));  // [FT][E] logits then weights
+  float* s_ctx = s_in + FT * ld_in;              // [FT][ctx]
+  float* s_h = s_ctx + FT * (int)al4(d.ctx_dim); // [FT][512] scratch hidden
+  float* s_feat = s_h + FT * EXT_HID;            // [FT][F] current expert feature
+  float* s_gin = s_feat + FT * (int)al4(d.F);    // [FT][gin]  ctxenc | processed_0..E-1
+  float* s_t = s_gin + FT * (int)al4(gin);       // [FT][max(P,hid)] scratch
+  float* s_w = s_t + FT * (int)al4(max(d.P, d.hidden));  // [FT][E] logits then weights
   const int ld_ctx = (int)al4(d.ctx_dim), ld_feat = (int)al4(d.F), ld_gin = (int)al4(gin),
             ld_t = (int)al4(max(d.P, d.hidden));
 
   const bool ctx_in = d.mode & GATE_MODE_CTX_IN, feat_in = d.mode & GATE_MODE_FEAT_IN;
   const bool ctx_only = d.mode & GATE_MODE_CTX_ONLY;
-  for (int i = threadIdx.x; i < GATE_FT * ld_in; i += blockDim.x) {
+  for (int i = threadIdx.x; i < FT * ld_in; i += blockDim.x) {
     int f = i / ld_in, c = i - f * ld_in;
     float v = 0.f;
     if (f0 + f < d.B) {
@@ -65,12 +66,12 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     s_in[i] = v;
   }
   if (ctx_in) {
-    for (int i = threadIdx.x; i < GATE_FT * d.ctx_dim; i += blockDim.x) {
+    for (int i = threadIdx.x; i < FT * d.ctx_dim; i += blockDim.x) {
       int f = i / d.ctx_dim, c = i - f * d.ctx_dim;
       s_ctx[f * ld_ctx + c] = (f0 + f < d.B) ? state[(int64_t)(f0 + f) * d.ctx_dim + c] : 0.f;
     }
   }
-  __syncthreads();
+  __syncthreads();   // CTA-local phase (every rank works on its own copy)
 
   // ---- SimpleContextExtractor (context_features.py:143-165) ----
   const float* p = prm;
@@ -82,11 +83,11 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* g = p; p += al4(d.ctx_dim);
     const float* bb = p; p += al4(d.ctx_dim);
     if (!ctx_in) {
-      linear_ft(W0, b0, s_in, ld_in, 4, s_h, EXT_HID, 32, true);
-      linear_ft(W3, b3, s_h, EXT_HID, 32, s_ctx, ld_ctx, d.ctx_dim, false);
-      layernorm_ft(s_ctx, ld_ctx, d.ctx_dim, g, bb);
+      linear_ft<FT, CL>(W0, b0, s_in, ld_in, 4, s_h, EXT_HID, 32, true);
+      linear_ft<FT, CL>(W3, b3, s_h, EXT_HID, 32, s_ctx, ld_ctx, d.ctx_dim, false);
+      layernorm_ft<FT, CL>(s_ctx, ld_ctx, d.ctx_dim, g, bb);
     }
-    if (context) store_rows(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
+    if (context) store_rows<FT, CL>(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
     if (d.mode & GATE_MODE_STOP_CTX) return;
   }
 
@@ -104,8 +105,8 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* W3 = p; p += al4((int64_t)d.hidden * d.hidden);
     const float* b3 = p; p += al4(d.hidden);
     if (!(d.mode & GATE_MODE_STOP_FEAT)) {
-      linear_ft(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true);
-      linear_ft(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true);
+      linear_ft<FT, CL>(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true);
+      linear_ft<FT, CL>(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true);
     }
   }
   int ch_off = 4;
@@ -126,28 +127,28 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     float* s_proc = s_gin + d.hidden + e * d.P;
     if (!ctx_only) {
       if (feat_in) {
-        for (int i = threadIdx.x; i < GATE_FT * d.F; i += blockDim.x) {
+        for (int i = threadIdx.x; i < FT * d.F; i += blockDim.x) {
           int f = i / d.F, c = i - f * d.F;
           s_feat[f * ld_feat + c] = (f0 + f < d.B) ? pooled[((int64_t)e * d.B + f0 + f) * d.F + c] : 0.f;
         }
-        __syncthreads();
+        __syncthreads();   // CTA-local phase (every rank works on its own copy)
       } else {
-        linear_ft(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, EXT_HID, EXT_HID, true);
-        linear_ft(W2, b2, s_h, EXT_HID, EXT_HID, s_feat, ld_feat, d.F, false);
-        layernorm_ft(s_feat, ld_feat, d.F, g, bb);
-        if (features) store_rows(features + (int64_t)e * d.B * d.F, d.F, s_feat, ld_feat, d.F, f0, d.B);
+        linear_ft<FT, CL>(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, EXT_HID, EXT_HID, true);
+        linear_ft<FT, CL>(W2, b2, s_h, EXT_HID, EXT_HID, s_feat, ld_feat, d.F, false);
+        layernorm_ft<FT, CL>(s_feat, ld_feat, d.F, g, bb);
+        if (features) store_rows<FT, CL>(features + (int64_t)e * d.B * d.F, d.F, s_feat, ld_feat, d.F, f0, d.B);
       }
       if (!(d.mode & GATE_MODE_STOP_FEAT)) {
         // ExpertOutputProcessor (gating_network.py:37-43)
-        linear_ft(PW0, Pb0, s_feat, ld_feat, d.F, s_t, ld_t, d.P, true);
-        linear_ft(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false);
-        layernorm_ft(s_proc, ld_gin, d.P, Pg, Pbb);
-        if (processed) store_rows(processed + (int64_t)e * d.B * d.P, d.P, s_proc, ld_gin, d.P, f0, d.B);
+        linear_ft<FT, CL>(PW0, Pb0, s_feat, ld_feat, d.F, s_t, ld_t, d.P, true);
+        linear_ft<FT, CL>(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false);
+        layernorm_ft<FT, CL>(s_proc, ld_gin, d.P, Pg, Pbb);
+        if (processed) store_rows<FT, CL>(processed + (int64_t)e * d.B * d.P, d.P, s_proc, ld_gin, d.P, f0, d.B);
       }
     } else {
       // get_expert_weights (gating_network.py:177-199): zeros stand in for the experts
-      for (int i = threadIdx.x; i < GATE_FT * d.P; i += blockDim.x) s_proc[(i / d.P) * ld_gin + (i % d.P)] = 0.f;
-      __syncthreads();
+      for (int i = threadIdx.x; i < FT * d.P; i += blockDim.x) s_proc[(i / d.P) * ld_gin + (i % d.P)] = 0.f;
+      __syncthreads();   // CTA-local phase (every rank works on its own copy)
     }
     ch_off += d.n_ch[e];
   }
@@ -160,9 +161,9 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* b0 = p; p += al4(d.hidden);
     const float* W3 = p; p += al4((int64_t)d.E * d.hidden);
     const float* b3 = p; p += al4(d.E);
-    linear_ft(W0, b0, s_gin, ld_gin, gin, s_t, ld_t, d.hidden, true);
-    linear_ft(W3, b3, s_t, ld_t, d.hidden, s_w, GATE_MAX_E, d.E, false);
-    if (threadIdx.x < GATE_FT) {
+    linear_ft<FT, CL>(W0, b0, s_gin, ld_gin, gin, s_t, ld_t, d.hidden, true);
+    linear_ft<FT, CL>(W3, b3, s_t, ld_t, d.hidden, s_w, GATE_MAX_E, d.E, false);
+    if (threadIdx.x < FT) {
       int f = threadIdx.x;
       float* lg = s_w + f * GATE_MAX_E;
       float mx = -INFINITY;
@@ -181,7 +182,7 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
         if (weights && f0 + f < d.B) weights[(int64_t)(f0 + f) * d.E + e] = lg[e];
       }
     }
-    __syncthreads();
+    __syncthreads();   // CTA-local phase (every rank works on its own copy)
   }
   if (ctx_only) return;
 
@@ -189,15 +190,15 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
   {
     const float* W = p; p += al4((int64_t)d.P * d.P);
     const float* b = p;
-    for (int i = threadIdx.x; i < GATE_FT * d.P; i += blockDim.x) {
+    for (int i = threadIdx.x; i < FT * d.P; i += blockDim.x) {
       int f = i / d.P, c = i - f * d.P;
       float acc = 0.f;  // combined_output starts at zeros and adds w_e * processed_e in order
       for (int e = 0; e < d.E; ++e) acc += s_w[f * GATE_MAX_E + e] * s_gin[f * ld_gin + d.hidden + e * d.P + c];
       s_h[f * EXT_HID + c] = acc;
     }
-    __syncthreads();
-    linear_ft(W, b, s_h, EXT_HID, d.P, s_t, ld_t, d.P, false);
-    if (combined) store_rows(combined, d.P, s_t, ld_t, d.P, f0, d.B);
+    __syncthreads();   // CTA-local phase (every rank works on its own copy)
+    linear_ft<FT, CL>(W, b, s_h, EXT_HID, d.P, s_t, ld_t, d.P, false);
+    if (combined) store_rows<FT, CL>(combined, d.P, s_t, ld_t, d.P, f0, d.B);
   }
 }
 
@@ -239,11 +240,32 @@ extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* poo
                (long long)n_params, (long long)need);
   if (B == 0) return 0;
   int gin = hidden + d.P * E;
-  size_t smem = sizeof(float) * GATE_FT *
-                (al4(4 + d.sumC) + al4(ctx_dim) + EXT_HID + al4(d.F) + al4(gin) +
-                 al4(d.P > hidden ? d.P : hidden) + GATE_MAX_E);
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(gate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gate_fused_kernel<<<ceil_div(B, GATE_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
+  const size_t per_frame = sizeof(float) * (al4(4 + d.sumC) + al4(ctx_dim) + EXT_HID + al4(d.F) + al4(gin) +
+                                           al4(d.P > hidden ? d.P : hidden) + GATE_MAX_E);
+  if (mlp_use_cluster(B) && per_frame * CL_FT <= 200 * 1024) {
+    // large batch: clusters of 8 CTAs split every layer's output rows (each CTA streams 1/8 of the weights)
+    const size_t smem = per_frame * CL_FT;
+    auto kern = gate_fused_kernel<CL_FT, true>;
+    AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(B, CL_FT) * CL_RANKS);
+    cfg.blockDim = dim3(GATE_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL_RANKS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, context, features, processed, gate_logits,
+                                       weights, combined));
+    AMOE_LAUNCH_OK(ctx);
+    return 0;
+  }
+  const size_t smem = per_frame * GATE_FT;
+  auto kern = gate_fused_kernel<GATE_FT, false>;
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(B, GATE_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
       d, state, pooled, params, context, features, processed, gate_logits, weights, combined);
   AMOE_LAUNCH_OK(ctx);
   return 0;

@@ -486,3 +486,34 @@ def test_policy_head_vs_oracle():
         outb = m.policy_head(img, context=ctx)
         m.policy_head.precision = "auto"
         assert rel_err(outb["waypoints"], ref["waypoints"]) < 2e-2
+
+
+@pytest.mark.parametrize("B", [64, 100, 256])
+def test_mlp_cluster_kernels_match_single_cta(B, monkeypatch):
+    """Large batches run the gate / policy-head MLPs on clusters of 8 CTAs (output rows split across the
+    cluster, activations all-gathered through distributed shared memory).  Same fp32 arithmetic with a
+    different summation order: equal to the single-CTA kernels to rounding, identical top-1 routing
+    (ragged last cluster included)."""
+    from automoe_b200 import _ops
+    m, _ = _small_model()
+    g = torch.Generator().manual_seed(17)
+    pooled = (torch.randn((B, 36), generator=g) * 3).to(DEV)
+    state = torch.cat([torch.rand((B, 1), generator=g) * 30, torch.rand((B, 3), generator=g) - 0.5], 1).to(DEV)
+    n_ch = [14, 19, 3]
+    prm = m._gate_params(torch.device(DEV), n_ch)
+    x = torch.randn((B, 4, 4, 256), generator=g).to(DEV)
+    cvec = torch.randn((B, 256), generator=g).to(DEV)
+    pp = m.policy_head._pack(torch.float32, torch.device(DEV))["flat"]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AMOE_MLP_CLUSTER", mode)
+        gate = _ops.gate(state, pooled, prm, n_ch, 64, 128, 1.0)
+        wp32, sp32 = _ops.policy_head(x, cvec, pp, 512, 256, 512, 10)
+        wp16, sp16 = _ops.policy_head(x.bfloat16(), cvec, pp, 512, 256, 512, 10)
+        torch.cuda.synchronize()
+        res[mode] = (gate, wp32, sp32, wp16, sp16)
+    for k in ("context", "features", "processed", "gate_logits", "weights", "combined"):
+        assert rel_err(res["1"][0][k], res["0"][0][k]) < 5e-6, (k, rel_err(res["1"][0][k], res["0"][0][k]))
+    assert torch.equal(res["1"][0]["weights"].argmax(1), res["0"][0]["weights"].argmax(1))
+    for i in range(1, 5):
+        assert rel_err(res["1"][i], res["0"][i]) < 5e-6, i
