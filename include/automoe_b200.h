@@ -197,6 +197,16 @@ int amoe_gate_fwd(amoe_ctx*, const float* state, const float* pooled, const floa
                   float* processed, float* gate_logits, float* weights, float* combined,
                   void* stream);
 
+/* Same with an optional bf16 copy of the parameter buffer (same element offsets, 16-byte aligned):
+ * params_bf16 != NULL and B >= 16 selects the bf16-inference variant - 16 frames per CTA, every layer with
+ * K % 32 == 0 on mma.sync TF32 (bf16 weights, fp32 activations truncated to TF32, fp32 accumulation; the
+ * K = 4 / C_e input layers, biases, LayerNorm and softmax stay fp32). */
+int amoe_gate_fwd_ex(amoe_ctx*, const float* state, const float* pooled, const float* params,
+                     const void* params_bf16, int64_t n_params, int B, int E, const int* n_ch_host,
+                     int ctx_dim, int hidden, float temperature, int mode, float* context,
+                     float* features, float* processed, float* gate_logits, float* weights,
+                     float* combined, void* stream);
+
 /* ---- policy head ------------------------------------------------------- */
 /* EasyBackbone pool+fc and both TrajectoryPolicy MLP heads
  * (trajectory_head.py:25-33,44-63) after the 4 convs:
@@ -207,6 +217,19 @@ int amoe_policy_head_fwd(amoe_ctx*, const void* x, const float* ctx, const float
                          int64_t n_params, int B, int HW, int Cf, int backbone_dim,
                          int ctx_dim, int hidden, int horizon, int x_dtype,
                          float* waypoints, float* speed, void* stream);
+
+/* Same with an optional bf16 copy of the parameter buffer (same element offsets as `params`, 16-byte aligned).
+ * params_bf16 != NULL and B >= 16 selects the bf16-inference variant: 16 frames per CTA, every layer with
+ * K % 32 == 0 on mma.sync TF32 (bf16 weights, fp32 activations truncated to TF32, fp32 accumulation; biases
+ * stay fp32).  x may be the pre-pooled feature [B,1,Cf] fp32 (HW = 1). */
+int amoe_policy_head_fwd_ex(amoe_ctx*, const void* x, const float* ctx, const float* params,
+                            int64_t n_params, int B, int HW, int Cf, int backbone_dim,
+                            int ctx_dim, int hidden, int horizon, int x_dtype, const void* params_bf16,
+                            float* waypoints, float* speed, void* stream);
+/* AdaptiveAvgPool2d(1) of an NHWC bf16 tensor (EasyBackbone.pool, trajectory_head.py:30):
+ *   x [B,HW,C] bf16 (C % 8 == 0) -> out [B,C] fp32, fixed summation order */
+int amoe_mean_hw_nhwc_fwd(amoe_ctx*, const void* x, float* out, int B, int HW, int C, int dtype,
+                          void* stream);
 
 /* ---- Hungarian matcher ------------------------------------------------- */
 /* Batched cost matrix of HungarianMatcher.forward (training/hungarian_matcher.py:34-76):

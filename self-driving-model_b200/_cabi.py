@@ -50,7 +50,10 @@ SIGNATURES = {
     "amoe_upsample_bilinear_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_mean_hw_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_gate_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I] + [_P] * 7),
+    "amoe_gate_fwd_ex": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I] + [_P] * 7),
     "amoe_policy_head_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "amoe_policy_head_fwd_ex": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "amoe_mean_hw_nhwc_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_hungarian_cost_fwd": (_I, [_P] * 7 + [_I] * 5 + [_F] * 3 + [_P]),
     "amoe_lsap_batched_host": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I]),
     # training step (gating + policy)

@@ -6,6 +6,7 @@ to own memory.  Activations are NHWC, stacked over experts on the batch axis.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -19,16 +20,16 @@ from ._cabi import check, ctx, dtype_code, lib, ptr, stream_ptr
 PROFILE = None
 
 
-def _al4(n: int) -> int:
-    return (n + 3) & ~3
+def _al8(n: int) -> int:
+    return (n + 7) & ~7
 
 
 def flat_params(tensors: List[torch.Tensor], device) -> torch.Tensor:
-    """Concatenate fp32 tensors, each padded to a multiple of 4 floats (16-byte rows)."""
+    """Concatenate fp32 tensors, each padded to a multiple of 8 floats (tensors stay 16-byte aligned in a bf16 copy)."""
     parts = []
     for t in tensors:
         f = t.detach().to(device=device, dtype=torch.float32).reshape(-1)
-        pad = _al4(f.numel()) - f.numel()
+        pad = _al8(f.numel()) - f.numel()
         if pad:
             f = torch.cat([f, f.new_zeros(pad)])
         parts.append(f)
@@ -524,8 +525,9 @@ def mean_hw_nchw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0):
-    """Fused context extractor + expert extractors + gating network (gate.cu)."""
+def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0, params_bf16=None):
+    """Fused context extractor + expert extractors + gating network (gate.cu).
+    params_bf16: bf16 copy of `params` -> tensor-core (TF32) variant for bf16 inference at B >= 16."""
     dev = state.device
     B, E = state.shape[0], len(n_ch)
     f32 = dict(device=dev, dtype=torch.float32)
@@ -539,22 +541,48 @@ def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0):
         processed = torch.empty((E, B, 256), **f32)
         combined = torch.empty((B, 256), **f32)
     arr = (C.c_int * E)(*n_ch)
-    check(lib().amoe_gate_fwd(ctx(dev), ptr(state), ptr(pooled), ptr(params), params.numel(), B, E, arr, ctx_dim,
-                              hidden, float(temperature), mode, ptr(context), ptr(features), ptr(processed),
-                              ptr(logits), ptr(weights), ptr(combined), stream_ptr(dev)), "gate_fwd")
+    if params_bf16 is not None:
+        assert params_bf16.dtype == torch.bfloat16 and params_bf16.numel() == params.numel()
+    check(lib().amoe_gate_fwd_ex(ctx(dev), ptr(state), ptr(pooled), ptr(params), ptr(params_bf16), params.numel(), B, E,
+                                 arr, ctx_dim, hidden, float(temperature), mode, ptr(context), ptr(features),
+                                 ptr(processed), ptr(logits), ptr(weights), ptr(combined), stream_ptr(dev)), "gate_fwd")
     return dict(context=context, features=features, processed=processed, gate_logits=logits, weights=weights,
                 combined=combined)
 
 
-def policy_head(x, cvec, params, backbone_dim, ctx_dim, hidden, horizon):
-    """x: [B,h,w,Cf] conv4 output; cvec: [B,ctx_dim] fp32 or None."""
+def mlp_tc(dtype: torch.dtype) -> bool:
+    """bf16 inference mode runs the gate / policy-head MLPs 16 frames per CTA on mma.sync TF32 with bf16
+    weights (AMOE_MLP_TC=0 keeps the fp32 CUDA-core kernels; fp32 mode always uses those)."""
+    return dtype == torch.bfloat16 and os.environ.get("AMOE_MLP_TC", "1") != "0"
+
+
+def mean_hw_nhwc(x):
+    """[B,h,w,C] bf16 -> [B,C] fp32 mean over the pixels (deterministic order)."""
+    B, h, w, Cc = x.shape
+    out = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    check(lib().amoe_mean_hw_nhwc_fwd(ctx(x.device), ptr(x), ptr(out), B, h * w, Cc, dtype_code(x.dtype),
+                                      stream_ptr(x.device)), "mean_hw_nhwc_fwd")
+    return out
+
+
+def policy_head(x, cvec, params, backbone_dim, ctx_dim, hidden, horizon, params_bf16=None):
+    """x: [B,h,w,Cf] conv4 output; cvec: [B,ctx_dim] fp32 or None.
+    params_bf16: bf16 copy of `params` -> tensor-core (TF32) variant for bf16 inference at B >= 16; the
+    pooling then runs as its own grid-wide kernel (one CTA per frame) instead of inside the head's 16 CTAs."""
     B, h, w, Cf = x.shape
     dev = x.device
     wp = torch.empty((B, 2 * horizon), device=dev, dtype=torch.float32)
     spd = torch.empty((B, horizon), device=dev, dtype=torch.float32)
-    check(lib().amoe_policy_head_fwd(ctx(dev), ptr(x), ptr(cvec), ptr(params), params.numel(), B, h * w, Cf,
-                                     backbone_dim, ctx_dim, hidden, horizon, dtype_code(x.dtype), ptr(wp), ptr(spd),
-                                     stream_ptr(dev)), "policy_head_fwd")
+    if params_bf16 is not None and B >= 16:
+        assert params_bf16.dtype == torch.bfloat16 and params_bf16.numel() == params.numel()
+        if x.dtype == torch.bfloat16 and Cf % 8 == 0:
+            x = mean_hw_nhwc(x).view(B, 1, 1, Cf)
+            h = w = 1
+    else:
+        params_bf16 = None
+    check(lib().amoe_policy_head_fwd_ex(ctx(dev), ptr(x), ptr(cvec), ptr(params), params.numel(), B, h * w, Cf,
+                                        backbone_dim, ctx_dim, hidden, horizon, dtype_code(x.dtype), ptr(params_bf16),
+                                        ptr(wp), ptr(spd), stream_ptr(dev)), "policy_head_fwd")
     return wp, spd
 
 

@@ -6,7 +6,7 @@
 // One CTA owns FT frames; every weight row is streamed once per CTA with coalesced
 // 16-byte loads and reused for the FT frames; reductions are warp shuffles.
 //
-// Flat parameter layout (fp32; every tensor starts on a 4-float boundary, weights are
+// Flat parameter layout (fp32; every tensor starts on an 8-float boundary, weights are
 // PyTorch [out,in] row-major) — must match models/automoe.py::_pack_gate_params:
 //   ctx.enc0.W[32,4] b[32] | ctx.enc3.W[ctx,32] b[ctx] | ctx.ln.g[ctx] b[ctx]
 //   per expert e: ext.W1[512,Ce] b1[512] | ext.W2[F,512] b2[F] | ext.ln.g[F] b[F]
@@ -33,26 +33,46 @@ struct GateDims {
   int mode;
 };
 
-template <int FT, bool CL>
+// shared-memory row strides (floats) of the per-CTA activation buffers; the tensor-core variant pads every row to
+// 16 mod 32 floats so its 16-byte fragment loads are bank-conflict free
+struct GateLds {
+  int in, ctx, h, feat, gin, t;
+  __host__ __device__ int64_t per_frame() const { return (int64_t)in + ctx + h + feat + gin + t + GATE_MAX_E; }
+};
+__host__ __device__ inline GateLds gate_lds(int sumC, int ctx_dim, int hidden, int F, int P, int E, bool tc) {
+  GateLds l;
+  const int gin = hidden + P * E, t = P > hidden ? P : hidden;
+  l.in = (int)al8(4 + sumC);
+  l.ctx = tc ? ld_tc(ctx_dim) : (int)al8(ctx_dim);
+  l.h = tc ? ld_tc(EXT_HID) : EXT_HID;
+  l.feat = tc ? ld_tc(F) : (int)al8(F);
+  l.gin = tc ? ld_tc(gin) : (int)al8(gin);
+  l.t = tc ? ld_tc(t) : (int)al8(t);
+  return l;
+}
+
+template <int FT, bool CL, bool TC>
 __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     GateDims d, const float* __restrict__ state, const float* __restrict__ pooled,
-    const float* __restrict__ prm, float* __restrict__ context, float* __restrict__ features,
+    const float* __restrict__ prm, const __nv_bfloat16* __restrict__ prm16, float* __restrict__ context,
+    float* __restrict__ features,
     float* __restrict__ processed, float* __restrict__ gate_logits, float* __restrict__ weights,
     float* __restrict__ combined) {
   extern __shared__ __align__(16) float sm[];
   const int f0 = (CL ? blockIdx.x / CL_RANKS : blockIdx.x) * FT;
   const int gin = d.hidden + d.P * d.E;  // gate_network input width
   // shared-memory carve-up (all row strides multiples of 4 floats)
-  const int ld_in = (int)al4(4 + d.sumC);
-  float* s_in = sm;                                   // [FT][ld_in]: state(4) | pooled(sumC)
-  float* s_ctx = s_in + FT * ld_in;              // [FT][ctx]
-  float* s_h = s_ctx + FT * (int)al4(d.ctx_dim); // [FT][512] scratch hidden
-  float* s_feat = s_h + FT * EXT_HID;            // [FT][F] current expert feature
-  float* s_gin = s_feat + FT * (int)al4(d.F);    // [FT][gin]  ctxenc | processed_0..E-1
-  float* s_t = s_gin + FT * (int)al4(gin);       // [FT][max(P,hid)] scratch
-  float* s_w = s_t + FT * (int)al4(max(d.P, d.hidden));  // [FT][E] logits then weights
-  const int ld_ctx = (int)al4(d.ctx_dim), ld_feat = (int)al4(d.F), ld_gin = (int)al4(gin),
-            ld_t = (int)al4(max(d.P, d.hidden));
+  const GateLds L = gate_lds(d.sumC, d.ctx_dim, d.hidden, d.F, d.P, d.E, TC);
+  const int ld_in = L.in, ld_ctx = L.ctx, ld_h = L.h, ld_feat = L.feat, ld_gin = L.gin, ld_t = L.t;
+  float* s_in = sm;                      // [FT][ld_in]: state(4) | pooled(sumC)
+  float* s_ctx = s_in + FT * ld_in;      // [FT][ctx]
+  float* s_h = s_ctx + FT * ld_ctx;      // [FT][512] scratch hidden
+  float* s_feat = s_h + FT * ld_h;       // [FT][F] current expert feature
+  float* s_gin = s_feat + FT * ld_feat;  // [FT][gin]  ctxenc | processed_0..E-1
+  float* s_t = s_gin + FT * ld_gin;      // [FT][max(P,hid)] scratch
+  float* s_w = s_t + FT * ld_t;          // [FT][E] logits then weights
+  // tensor-core variant: the bf16 copy of the parameter buffer has the same element offsets
+  auto w16 = [&](const float* W) -> const __nv_bfloat16* { return (TC && prm16) ? prm16 + (W - prm) : nullptr; };
 
   const bool ctx_in = d.mode & GATE_MODE_CTX_IN, feat_in = d.mode & GATE_MODE_FEAT_IN;
   const bool ctx_only = d.mode & GATE_MODE_CTX_ONLY;
@@ -76,15 +96,15 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
   // ---- SimpleContextExtractor (context_features.py:143-165) ----
   const float* p = prm;
   {
-    const float* W0 = p; p += al4(32 * 4);
-    const float* b0 = p; p += al4(32);
-    const float* W3 = p; p += al4((int64_t)d.ctx_dim * 32);
-    const float* b3 = p; p += al4(d.ctx_dim);
-    const float* g = p; p += al4(d.ctx_dim);
-    const float* bb = p; p += al4(d.ctx_dim);
+    const float* W0 = p; p += al8(32 * 4);
+    const float* b0 = p; p += al8(32);
+    const float* W3 = p; p += al8((int64_t)d.ctx_dim * 32);
+    const float* b3 = p; p += al8(d.ctx_dim);
+    const float* g = p; p += al8(d.ctx_dim);
+    const float* bb = p; p += al8(d.ctx_dim);
     if (!ctx_in) {
-      linear_ft<FT, CL>(W0, b0, s_in, ld_in, 4, s_h, EXT_HID, 32, true);
-      linear_ft<FT, CL>(W3, b3, s_h, EXT_HID, 32, s_ctx, ld_ctx, d.ctx_dim, false);
+      linear_ft<FT, CL, TC>(W0, b0, s_in, ld_in, 4, s_h, ld_h, 32, true, w16(W0));
+      linear_ft<FT, CL, TC>(W3, b3, s_h, ld_h, 32, s_ctx, ld_ctx, d.ctx_dim, false, w16(W3));
       layernorm_ft<FT, CL>(s_ctx, ld_ctx, d.ctx_dim, g, bb);
     }
     if (context) store_rows<FT, CL>(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
@@ -96,34 +116,34 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
   const float* ext_prm[GATE_MAX_E];
   for (int e = 0; e < d.E; ++e) {
     ext_prm[e] = p;
-    p += al4((int64_t)EXT_HID * d.n_ch[e]) + al4(EXT_HID) + al4((int64_t)d.F * EXT_HID) + al4(d.F) + 2 * al4(d.F);
+    p += al8((int64_t)EXT_HID * d.n_ch[e]) + al8(EXT_HID) + al8((int64_t)d.F * EXT_HID) + al8(d.F) + 2 * al8(d.F);
   }
   // gating context encoder (gating_network.py:12-20)
   {
-    const float* W0 = p; p += al4((int64_t)d.hidden * d.ctx_dim);
-    const float* b0 = p; p += al4(d.hidden);
-    const float* W3 = p; p += al4((int64_t)d.hidden * d.hidden);
-    const float* b3 = p; p += al4(d.hidden);
+    const float* W0 = p; p += al8((int64_t)d.hidden * d.ctx_dim);
+    const float* b0 = p; p += al8(d.hidden);
+    const float* W3 = p; p += al8((int64_t)d.hidden * d.hidden);
+    const float* b3 = p; p += al8(d.hidden);
     if (!(d.mode & GATE_MODE_STOP_FEAT)) {
-      linear_ft<FT, CL>(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true);
-      linear_ft<FT, CL>(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true);
+      linear_ft<FT, CL, TC>(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true, w16(W0));
+      linear_ft<FT, CL, TC>(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true, w16(W3));
     }
   }
   int ch_off = 4;
   for (int e = 0; e < d.E; ++e) {
     const float* q = ext_prm[e];
-    const float* W1 = q; q += al4((int64_t)EXT_HID * d.n_ch[e]);
-    const float* b1 = q; q += al4(EXT_HID);
-    const float* W2 = q; q += al4((int64_t)d.F * EXT_HID);
-    const float* b2 = q; q += al4(d.F);
-    const float* g = q; q += al4(d.F);
+    const float* W1 = q; q += al8((int64_t)EXT_HID * d.n_ch[e]);
+    const float* b1 = q; q += al8(EXT_HID);
+    const float* W2 = q; q += al8((int64_t)d.F * EXT_HID);
+    const float* b2 = q; q += al8(d.F);
+    const float* g = q; q += al8(d.F);
     const float* bb = q;
-    const float* PW0 = p; p += al4((int64_t)d.P * d.F);
-    const float* Pb0 = p; p += al4(d.P);
-    const float* PW3 = p; p += al4((int64_t)d.P * d.P);
-    const float* Pb3 = p; p += al4(d.P);
-    const float* Pg = p; p += al4(d.P);
-    const float* Pbb = p; p += al4(d.P);
+    const float* PW0 = p; p += al8((int64_t)d.P * d.F);
+    const float* Pb0 = p; p += al8(d.P);
+    const float* PW3 = p; p += al8((int64_t)d.P * d.P);
+    const float* Pb3 = p; p += al8(d.P);
+    const float* Pg = p; p += al8(d.P);
+    const float* Pbb = p; p += al8(d.P);
     float* s_proc = s_gin + d.hidden + e * d.P;
     if (!ctx_only) {
       if (feat_in) {
@@ -133,15 +153,15 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
         }
         __syncthreads();   // CTA-local phase (every rank works on its own copy)
       } else {
-        linear_ft<FT, CL>(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, EXT_HID, EXT_HID, true);
-        linear_ft<FT, CL>(W2, b2, s_h, EXT_HID, EXT_HID, s_feat, ld_feat, d.F, false);
+        linear_ft<FT, CL, TC>(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, ld_h, EXT_HID, true, w16(W1));
+        linear_ft<FT, CL, TC>(W2, b2, s_h, ld_h, EXT_HID, s_feat, ld_feat, d.F, false, w16(W2));
         layernorm_ft<FT, CL>(s_feat, ld_feat, d.F, g, bb);
         if (features) store_rows<FT, CL>(features + (int64_t)e * d.B * d.F, d.F, s_feat, ld_feat, d.F, f0, d.B);
       }
       if (!(d.mode & GATE_MODE_STOP_FEAT)) {
         // ExpertOutputProcessor (gating_network.py:37-43)
-        linear_ft<FT, CL>(PW0, Pb0, s_feat, ld_feat, d.F, s_t, ld_t, d.P, true);
-        linear_ft<FT, CL>(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false);
+        linear_ft<FT, CL, TC>(PW0, Pb0, s_feat, ld_feat, d.F, s_t, ld_t, d.P, true, w16(PW0));
+        linear_ft<FT, CL, TC>(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false, w16(PW3));
         layernorm_ft<FT, CL>(s_proc, ld_gin, d.P, Pg, Pbb);
         if (processed) store_rows<FT, CL>(processed + (int64_t)e * d.B * d.P, d.P, s_proc, ld_gin, d.P, f0, d.B);
       }
@@ -157,12 +177,12 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
 
   // ---- gate MLP + softmax (gating_network.py:94-99,141-160) ----
   {
-    const float* W0 = p; p += al4((int64_t)d.hidden * gin);
-    const float* b0 = p; p += al4(d.hidden);
-    const float* W3 = p; p += al4((int64_t)d.E * d.hidden);
-    const float* b3 = p; p += al4(d.E);
-    linear_ft<FT, CL>(W0, b0, s_gin, ld_gin, gin, s_t, ld_t, d.hidden, true);
-    linear_ft<FT, CL>(W3, b3, s_t, ld_t, d.hidden, s_w, GATE_MAX_E, d.E, false);
+    const float* W0 = p; p += al8((int64_t)d.hidden * gin);
+    const float* b0 = p; p += al8(d.hidden);
+    const float* W3 = p; p += al8((int64_t)d.E * d.hidden);
+    const float* b3 = p; p += al8(d.E);
+    linear_ft<FT, CL, TC>(W0, b0, s_gin, ld_gin, gin, s_t, ld_t, d.hidden, true, w16(W0));
+    linear_ft<FT, CL, TC>(W3, b3, s_t, ld_t, d.hidden, s_w, GATE_MAX_E, d.E, false, w16(W3));
     if (threadIdx.x < FT) {
       int f = threadIdx.x;
       float* lg = s_w + f * GATE_MAX_E;
@@ -188,35 +208,35 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
 
   // ---- weighted combine + output projection (gating_network.py:162-168) ----
   {
-    const float* W = p; p += al4((int64_t)d.P * d.P);
+    const float* W = p; p += al8((int64_t)d.P * d.P);
     const float* b = p;
     for (int i = threadIdx.x; i < FT * d.P; i += blockDim.x) {
       int f = i / d.P, c = i - f * d.P;
       float acc = 0.f;  // combined_output starts at zeros and adds w_e * processed_e in order
       for (int e = 0; e < d.E; ++e) acc += s_w[f * GATE_MAX_E + e] * s_gin[f * ld_gin + d.hidden + e * d.P + c];
-      s_h[f * EXT_HID + c] = acc;
+      s_h[f * ld_h + c] = acc;
     }
     __syncthreads();   // CTA-local phase (every rank works on its own copy)
-    linear_ft<FT, CL>(W, b, s_h, EXT_HID, d.P, s_t, ld_t, d.P, false);
+    linear_ft<FT, CL, TC>(W, b, s_h, ld_h, d.P, s_t, ld_t, d.P, false, w16(W));
     if (combined) store_rows<FT, CL>(combined, d.P, s_t, ld_t, d.P, f0, d.B);
   }
 }
 
 static int64_t gate_param_count(const GateDims& d) {
-  int64_t n = al4(32 * 4) + al4(32) + al4((int64_t)d.ctx_dim * 32) + 3 * al4(d.ctx_dim);
+  int64_t n = al8(32 * 4) + al8(32) + al8((int64_t)d.ctx_dim * 32) + 3 * al8(d.ctx_dim);
   for (int e = 0; e < d.E; ++e)
-    n += al4((int64_t)EXT_HID * d.n_ch[e]) + al4(EXT_HID) + al4((int64_t)d.F * EXT_HID) + 3 * al4(d.F);
-  n += al4((int64_t)d.hidden * d.ctx_dim) + al4(d.hidden) + al4((int64_t)d.hidden * d.hidden) + al4(d.hidden);
+    n += al8((int64_t)EXT_HID * d.n_ch[e]) + al8(EXT_HID) + al8((int64_t)d.F * EXT_HID) + 3 * al8(d.F);
+  n += al8((int64_t)d.hidden * d.ctx_dim) + al8(d.hidden) + al8((int64_t)d.hidden * d.hidden) + al8(d.hidden);
   for (int e = 0; e < d.E; ++e)
-    n += al4((int64_t)d.P * d.F) + al4(d.P) + al4((int64_t)d.P * d.P) + 3 * al4(d.P);
+    n += al8((int64_t)d.P * d.F) + al8(d.P) + al8((int64_t)d.P * d.P) + 3 * al8(d.P);
   int gin = d.hidden + d.P * d.E;
-  n += al4((int64_t)d.hidden * gin) + al4(d.hidden) + al4((int64_t)d.E * d.hidden) + al4(d.E);
-  n += al4((int64_t)d.P * d.P) + al4(d.P);
+  n += al8((int64_t)d.hidden * gin) + al8(d.hidden) + al8((int64_t)d.E * d.hidden) + al8(d.E);
+  n += al8((int64_t)d.P * d.P) + al8(d.P);
   return n;
 }
 
-extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* pooled,
-                             const float* params, int64_t n_params, int B, int E,
+extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* pooled,
+                                const float* params, const void* params_bf16, int64_t n_params, int B, int E,
                              const int* n_ch_host, int ctx_dim, int hidden, float temperature,
                              int mode, float* context, float* features, float* processed,
                              float* gate_logits, float* weights, float* combined, void* stream) {
@@ -239,13 +259,24 @@ extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* poo
   AMOE_REQUIRE(n_params == need, "amoe_gate_fwd: params has %lld floats, layout needs %lld",
                (long long)n_params, (long long)need);
   if (B == 0) return 0;
-  int gin = hidden + d.P * E;
-  const size_t per_frame = sizeof(float) * (al4(4 + d.sumC) + al4(ctx_dim) + EXT_HID + al4(d.F) + al4(gin) +
-                                           al4(d.P > hidden ? d.P : hidden) + GATE_MAX_E);
+  const __nv_bfloat16* p16 = (const __nv_bfloat16*)params_bf16;
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(params_bf16) & 15) == 0, "amoe_gate_fwd: params_bf16 must be 16-byte aligned");
+  if (p16 && B >= MMA_FT) {
+    // bf16 inference mode: 16 frames per CTA, layers with K % 32 == 0 run on mma.sync TF32 (mlp.cuh)
+    const size_t smem = sizeof(float) * (size_t)gate_lds(d.sumC, ctx_dim, hidden, d.F, d.P, E, true).per_frame() * MMA_FT;
+    AMOE_REQUIRE(smem <= 226 * 1024, "amoe_gate_fwd: dims too large for shared memory");
+    auto kern = gate_fused_kernel<MMA_FT, false, true>;
+    AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ceil_div(B, MMA_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
+        d, state, pooled, params, p16, context, features, processed, gate_logits, weights, combined);
+    AMOE_LAUNCH_OK(ctx);
+    return 0;
+  }
+  const size_t per_frame = sizeof(float) * (size_t)gate_lds(d.sumC, ctx_dim, hidden, d.F, d.P, E, false).per_frame();
   if (mlp_use_cluster(B) && per_frame * CL_FT <= 200 * 1024) {
     // large batch: clusters of 8 CTAs split every layer's output rows (each CTA streams 1/8 of the weights)
     const size_t smem = per_frame * CL_FT;
-    auto kern = gate_fused_kernel<CL_FT, true>;
+    auto kern = gate_fused_kernel<CL_FT, true, false>;
     AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ceil_div(B, CL_FT) * CL_RANKS);
@@ -257,16 +288,25 @@ extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* poo
     attr[0].val.clusterDim.x = CL_RANKS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, context, features, processed, gate_logits,
+    AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, (const __nv_bfloat16*)nullptr, context, features, processed, gate_logits,
                                        weights, combined));
     AMOE_LAUNCH_OK(ctx);
     return 0;
   }
   const size_t smem = per_frame * GATE_FT;
-  auto kern = gate_fused_kernel<GATE_FT, false>;
+  auto kern = gate_fused_kernel<GATE_FT, false, false>;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<ceil_div(B, GATE_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
-      d, state, pooled, params, context, features, processed, gate_logits, weights, combined);
+      d, state, pooled, params, (const __nv_bfloat16*)nullptr, context, features, processed, gate_logits, weights, combined);
   AMOE_LAUNCH_OK(ctx);
   return 0;
+}
+
+extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* pooled,
+                             const float* params, int64_t n_params, int B, int E,
+                             const int* n_ch_host, int ctx_dim, int hidden, float temperature,
+                             int mode, float* context, float* features, float* processed,
+                             float* gate_logits, float* weights, float* combined, void* stream) {
+  return amoe_gate_fwd_ex(ctx, state, pooled, params, nullptr, n_params, B, E, n_ch_host, ctx_dim, hidden, temperature, mode,
+                          context, features, processed, gate_logits, weights, combined, stream);
 }

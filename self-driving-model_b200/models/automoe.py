@@ -116,7 +116,9 @@ class AutoMoE(nn.Module):
             cols = [speed_in, z, z, z]
         return torch.cat([c.reshape(c.size(0), 1).float() for c in cols], dim=-1).contiguous()
 
-    def _gate_params(self, device, n_ch):
+    def _gate_params(self, device, n_ch, bf16_copy=False):
+        """Flat fp32 parameter buffer of the fused gate kernel (cached; re-packed when a parameter changes).
+        bf16_copy=True returns (flat, flat.bfloat16()) for the tensor-core variant of bf16 inference."""
         stamp = params_stamp([self.context_extractor, self.expert_extractors, self.gating_network])
         key = device.index
         g = self._gate_flat.get(key)
@@ -124,9 +126,9 @@ class AutoMoE(nn.Module):
             flat = pack_gate_params(self.context_extractor, list(self.expert_extractors.extractors),
                                     self.gating_network, n_ch, self.context_extractor.context_dim,
                                     self.gating_network.hidden_dim, device)
-            g = (stamp, flat)
+            g = (stamp, flat, flat.to(torch.bfloat16))
             self._gate_flat[key] = g
-        return g[1]
+        return (g[1], g[2]) if bf16_copy else g[1]
 
     def _fused_stem(self, device):
         """PackedStem of [expert stems..., policy conv1] (cached; re-packed when any of them changes)."""
@@ -227,8 +229,10 @@ class AutoMoE(nn.Module):
                                           overlap_outputs=_ops.overlap_outputs())
 
         gn = self.gating_network
-        g = _ops.gate(state, aux['pooled'], self._gate_params(image.device, aux['n_ch']), aux['n_ch'],
-                      self.context_extractor.context_dim, gn.hidden_dim, gn.temperature)
+        gflat, gflat16 = self._gate_params(image.device, aux['n_ch'], bf16_copy=True)
+        g = _ops.gate(state, aux['pooled'], gflat, aux['n_ch'],
+                      self.context_extractor.context_dim, gn.hidden_dim, gn.temperature,
+                      params_bf16=gflat16 if _ops.mlp_tc(dtype) else None)
 
         policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)
         if aux.get('join') is not None:      # full-resolution logits were written on the side stream

@@ -70,7 +70,7 @@ class TrajectoryPolicy(nn.Module):
             lin = [self.backbone.fc, self.head_wp[0], self.head_wp[2], self.head_wp[4],
                    self.head_spd[0], self.head_spd[2], self.head_spd[4]]
             flat = _ops.flat_params([t for l in lin for t in (l.weight, l.bias)], device)
-            p = dict(stamp=stamp, convs=convs, flat=flat)
+            p = dict(stamp=stamp, convs=convs, flat=flat, flat16=flat.to(torch.bfloat16))
             self._packs[key] = p
         return p
 
@@ -108,5 +108,6 @@ class TrajectoryPolicy(nn.Module):
             if self.context_dim != 0:
                 raise ValueError("TrajectoryPolicy expects a context of dim %d" % self.context_dim)
             cvec, cdim = None, 0
-        wp, spd = _ops.policy_head(x, cvec, p["flat"], self.backbone_dim, cdim, self.hidden, self.horizon)
+        wp, spd = _ops.policy_head(x, cvec, p["flat"], self.backbone_dim, cdim, self.hidden, self.horizon,
+                                   params_bf16=p["flat16"] if _ops.mlp_tc(dtype) else None)
         return {"waypoints": wp.view(-1, self.horizon, 2), "speed": spd.view(-1, self.horizon)}

@@ -517,3 +517,52 @@ def test_mlp_cluster_kernels_match_single_cta(B, monkeypatch):
     assert torch.equal(res["1"][0]["weights"].argmax(1), res["0"][0]["weights"].argmax(1))
     for i in range(1, 5):
         assert rel_err(res["1"][i], res["0"][i]) < 5e-6, i
+
+
+@pytest.mark.parametrize("B", [16, 37, 256])
+def test_mlp_tf32_kernels_vs_fp32_kernels(B):
+    """bf16 inference mode runs the gate / policy-head layers 16 frames per CTA on mma.sync TF32 (bf16 weights,
+    fp32 activations truncated to TF32, fp32 accumulate).  Against the fp32 CUDA-core kernels fed the SAME
+    bf16-rounded weights: every output within 2e-3 relative (activation truncation only); against the fp32
+    weights: within 1e-2 (the bf16 tolerance - this is the weight rounding the reference's autocast applies too);
+    softmax weights sum to one, identical top-1 routing wherever the fp32 logit gap exceeds that noise; ragged
+    last CTA included.  The grid-wide NHWC mean kernel that feeds the head is checked against torch."""
+    from automoe_b200 import _ops
+    m, _ = _small_model()
+    g = torch.Generator().manual_seed(23)
+    pooled = (torch.randn((B, 36), generator=g) * 3).to(DEV)
+    state = torch.cat([torch.rand((B, 1), generator=g) * 30, torch.rand((B, 3), generator=g) - 0.5], 1).to(DEV)
+    n_ch = [14, 19, 3]
+    prm, prm16 = m._gate_params(torch.device(DEV), n_ch, bf16_copy=True)
+    ref = _ops.gate(state, pooled, prm, n_ch, 64, 128, 1.0)
+    ref16 = _ops.gate(state, pooled, prm16.float(), n_ch, 64, 128, 1.0)     # fp32 kernel, bf16-rounded parameters
+    out = _ops.gate(state, pooled, prm, n_ch, 64, 128, 1.0, params_bf16=prm16)
+    for k in ("context", "features", "processed", "gate_logits", "weights", "combined"):
+        assert rel_err(out[k], ref[k]) < 1e-2, (k, rel_err(out[k], ref[k]))
+    # weights of the MMA layers are the bf16 copy, biases / LayerNorm / tiny layers the fp32 buffer: compare the
+    # end of the chain with both references
+    assert min(rel_err(out["combined"], ref16["combined"]), rel_err(out["combined"], ref["combined"])) < 5e-3
+    assert torch.allclose(out["weights"].sum(1), torch.ones(B, device=DEV), atol=1e-6)
+    top2 = ref["gate_logits"].topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2e-2 * ref["gate_logits"].abs().max()
+    assert safe.float().mean() > 0.5
+    assert torch.equal(out["weights"].argmax(1)[safe], ref["weights"].argmax(1)[safe])
+
+    x = torch.randn((B, 4, 4, 256), generator=g).to(DEV).bfloat16()
+    cvec = torch.randn((B, 256), generator=g).to(DEV)
+    pk = m.policy_head._pack(torch.float32, torch.device(DEV))
+    pp, pp16 = pk["flat"], pk["flat16"]
+    pooled_x = _ops.mean_hw_nhwc(x)
+    assert rel_err(pooled_x, x.float().mean(dim=(1, 2))) < 1e-6
+    wp_ref, sp_ref = _ops.policy_head(x, cvec, pp, 512, 256, 512, 10)
+    wp, sp = _ops.policy_head(x, cvec, pp, 512, 256, 512, 10, params_bf16=pp16)
+    assert rel_err(wp, wp_ref) < 1e-2, rel_err(wp, wp_ref)
+    assert rel_err(sp, sp_ref) < 1e-2, rel_err(sp, sp_ref)
+    # same bf16-rounded weights through the fp32 kernel: only the TF32 truncation of the activations differs
+    # (biases differ by their bf16 rounding there, hence not tighter than 3e-3)
+    wp_r16, sp_r16 = _ops.policy_head(x, cvec, pp16.float(), 512, 256, 512, 10)
+    assert rel_err(wp, wp_r16) < 3e-3, rel_err(wp, wp_r16)
+    assert rel_err(sp, sp_r16) < 3e-3, rel_err(sp, sp_r16)
+    # fp32 feature map through the tensor-core head (pooling inside the kernel)
+    wp32, sp32 = _ops.policy_head(x.float(), cvec, pp, 512, 256, 512, 10, params_bf16=pp16)
+    assert rel_err(wp32, wp) < 1e-3 and rel_err(sp32, sp) < 1e-3
