@@ -20,6 +20,7 @@
 //   warps 3-6: epilogue: tcgen05.ld -> scale/bias (+residual) -> ReLU -> zero at borders -> bf16,
 //           transposed through swizzled staging rows to coalesced 16-byte stores
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -340,6 +341,337 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+}  // namespace flat
+
+// ---------------------------------------------------------------------------------------------------------
+// 64 -> 64 channels (ResNet layer1): two horizontal taps of a filter row in ONE MMA.
+//
+// With N = 64 every 128x64x16 MMA reads 4 KB of activations and 2 KB of weights from shared memory for 32 cycles
+// of tensor time - 192 B/clk against the ~128 B/clk the operand path delivers, which is what holds the kernel above
+// at 41-52 % tensor-busy.  The A operands of the taps (kh,0) and (kh,1) are the same activation window shifted by
+// one position, so here the window of tap (kh,1) is multiplied by both weight tiles at once
+// (B = [W(kh,0); W(kh,1)], N = 128: adjacent in the resident weight buffer) into two 64-column accumulators
+//     D0[P] = sum_kh X[P + (kh-1)*Wp] * W(kh,0)^T         D1[P] = sum_kh X[P + (kh-1)*Wp] * W(kh,1)^T
+// and tap (kh,2) stays an N = 64 MMA on the window shifted by +1 that accumulates straight into D1.  Then
+//     out[Q] = D0[Q-1] + D1[Q]
+// Operand traffic per filter row and K step: 8 KB / 64 cycles + 6 KB / 32 cycles = 146 B/clk instead of 192.
+// (All three taps in one N = 192 MMA - 107 B/clk - was measured first: it needs a second shuffle and add per
+// output in the epilogue, and ~500 instructions per epilogue warp and 128-row sub-tile do not fit into the
+// 1152 cycles its MMAs take; it ran at 30 % tensor-busy.)  Accumulator rows are TMEM lanes, so the one-row shift
+// of D0 is a warp shuffle; lane 0 of every warp takes it from the previous lane quarter's warp through a 128-byte
+// shared-memory exchange, and row 0 of every 128-row MMA is halo: a sub-tile yields 127 outputs, a tile = two
+// sub-tiles = 254 consecutive positions sharing one activation buffer.
+//   warp 0: TMA producer   warp 1: MMA issuer (+TMEM owner)   warp 2: idle   warps 3-18: epilogue
+namespace flat {
+
+constexpr int KW3_STATIC = 3072;         // its static shared memory (row exchange) comes out of the dynamic budget
+constexpr int KW3_THREADS = 11 * 32;     // warp 0 producer, warps 1-2 MMA issuers (one per sub-tile), warps 3-10 epilogue
+constexpr int KW3_SUB = 127;             // outputs per 128-row sub-tile
+constexpr int KW3_TILE = 2 * KW3_SUB;    // positions per tile
+
+// n / d for 0 <= n < 2^31 with a precomputed multiplier (host: fastdiv_init)
+struct FastDiv { uint32_t mul, shift, d; };
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.mul) + n) >> f.shift; }
+static FastDiv fastdiv_init(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((1ull << s) - d) << 32) / d + 1);
+  return f;
+}
+
+struct Kw3Params {
+  Params p;
+  FastDiv div_img, div_wp;
+};
+
+// (a0 + a1) * s + b on two fp32 lanes per instruction (Blackwell add/fma.rn.f32x2: per-element IEEE)
+__device__ __forceinline__ void add_scale2(float& h0, float& h1, uint32_t u0, uint32_t u1, uint32_t c0, uint32_t c1,
+                                           float s0, float s1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 ru, rc, rs, rb, rd;\n"
+      "mov.b64 ru, {%2, %3};\n"
+      "mov.b64 rc, {%4, %5};\n"
+      "mov.b64 rs, {%6, %7};\n"
+      "mov.b64 rb, {%8, %9};\n"
+      "add.rn.f32x2 rd, ru, rc;\n"
+      "fma.rn.f32x2 rd, rd, rs, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(h0), "=f"(h1)
+      : "r"(u0), "r"(u1), "r"(c0), "r"(c1), "f"(s0), "f"(s1), "f"(b0), "f"(b1));
+}
+
+__global__ void __launch_bounds__(KW3_THREADS, 1)
+conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                        const __grid_constant__ Kw3Params kp) {
+  constexpr int N = 64;
+  const Params& p = kp.p;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 1 + 4];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_scale[N];
+  __shared__ __align__(16) float s_bias[N];
+  __shared__ __align__(16) float xch[2][2][4][32];   // [toggle][channel half][lane quarter][channel]: D0 row of lane 31
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * 128u;
+  constexpr uint32_t w_tile_bytes = (uint32_t)N * 128u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_w = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+  for (int i = threadIdx.x; i < N; i += KW3_THREADS) {
+    s_scale[i] = __ldg(p.scale + blockIdx.y * N + i);
+    s_bias[i] = __ldg(p.bias + blockIdx.y * N + i);
+  }
+  const uint32_t bar_afull = smem_u32(&bars[0]);
+  const uint32_t bar_aempty = smem_u32(&bars[MAX_A_STAGES]);
+  const uint32_t bar_wfull = smem_u32(&bars[2 * MAX_A_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_A_STAGES + 1]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * MAX_A_STAGES + 3]);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < MAX_A_STAGES; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 2);    // both MMA issuers commit
+    }
+    mbar_init(bar_wfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 8);    // one arrive per epilogue warp of the sub-tile
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const int group_row0 = g * p.group_positions;
+  const int wrow0 = g * N;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_wfull, 9u * w_tile_bytes);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d(smem_w + (uint32_t)tap * w_tile_bytes, &tmW, bar_wfull, tap * p.C, wrow0);
+      int as = 0;
+      uint32_t aphase = 0;
+      const int half_rows = p.rows_pad >> 1;
+      for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x) {
+        const int row_start = group_row0 + t * KW3_TILE - 1 - p.Wp;   // may be negative: TMA zero-fills
+        mbar_wait(bar_aempty + 8 * as, aphase ^ 1u);
+        mbar_arrive_expect_tx(bar_afull + 8 * as, a_stage_bytes);
+        const uint32_t dst = smem_a + (uint32_t)as * a_stage_bytes;
+        tma_load_2d(dst, &tmA, bar_afull + 8 * as, 0, row_start);
+        tma_load_2d(dst + (uint32_t)half_rows * 128u, &tmA, bar_afull + 8 * as, 0, row_start + half_rows);
+        if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp <= 2) {
+    // ============================ MMA issuers =============================
+    // One warp per sub-tile (disjoint accumulators): computing the descriptors of an MMA and moving them to uniform
+    // registers costs a warp ~20 dependent issue slots, more than an N=64 MMA occupies the tensor pipe.
+    const int sub = warp - 1;
+    const uint32_t idesc2 = make_idesc(2 * N), idesc1 = make_idesc(N);
+    int as = 0, it = 0;
+    uint32_t aphase = 0;
+    mbar_wait(bar_wfull, 0);
+    tcgen05_fence_after();
+    const uint32_t wp128 = (uint32_t)p.Wp * 128u;
+    const uint32_t d_tmem = tmem_base + (uint32_t)(sub * ACC_STRIDE);
+    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+      const uint32_t tphase = (uint32_t)it & 1u;
+      mbar_wait(bar_afull + 8 * as, aphase);
+      mbar_wait(bar_tempty + 8 * sub, tphase ^ 1u);
+      tcgen05_fence_after();
+      // buffer row 0 is position (tile base - 1 - Wp); MMA row r of this sub-tile is position base + sub*127 - 1 + r
+      const uint32_t a_base = smem_a + (uint32_t)as * a_stage_bytes + (uint32_t)(sub * KW3_SUB) * 128u;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const uint64_t a_desc = make_sw128_desc(a_base + (uint32_t)kh * wp128);
+        const uint64_t a_desc1 = make_sw128_desc(a_base + 128u + (uint32_t)kh * wp128);
+        const uint64_t b_desc01 = make_sw128_desc(smem_w + (uint32_t)(kh * 3) * w_tile_bytes);
+        const uint64_t b_desc2 = make_sw128_desc(smem_w + (uint32_t)(kh * 3 + 2) * w_tile_bytes);
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc01 + (uint64_t)(kk * 2), idesc2, (uint32_t)((kh | kk) != 0));
+          umma_bf16(d_tmem + (uint32_t)N, a_desc1 + (uint64_t)(kk * 2), b_desc2 + (uint64_t)(kk * 2), idesc1, 1u);
+        }
+      }
+      umma_commit(bar_tfull + 8 * sub);
+      umma_commit(bar_aempty + 8 * as);
+      if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 3) {
+    // ============================ epilogue ================================
+    // Eight warps: warp (c, lg) owns TMEM lane quarter lg (MMA rows [32*lg, 32*lg+32)) and output channels
+    // [32c, 32c+32) of both sub-tiles; two warps per SM sub-partition hide each other's latencies.  (Sixteen warps,
+    // one set per sub-tile, were measured slower.)
+    const int lg = warp & 3, c = (warp - 3) >> 2;
+    constexpr int HV = 4, HROWB = 64;     // 16-byte pieces / bytes of a staged half row (32 channels)
+    const uint32_t stg_off_w = p.stg_off + (uint32_t)(c * 4 + lg) * 2 * (32u * HROWB);
+    uint8_t* stg_warp = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off_w;
+    const uint32_t stg_warp_s = smem_base + stg_off_w;
+    const bool has_res = p.residual != nullptr;
+    const int r = lg * 32 + lane;         // MMA row of this thread
+    const int row_lo = lg == 0 ? 1 : 0;   // MMA row 0 is halo
+    const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);   // folded BatchNorm of this warp's channels
+    const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+    const int up = (lane + 31) & 31;
+    // Residual half rows of the warp's block of sub-tile (tt, ss) -> staging buffer ss (swizzled).  Issued one
+    // sub-tile AHEAD: the epilogue, not the MMA, sets the pace of this kernel, so a fetch issued when its sub-tile
+    // starts would expose one HBM latency per sub-tile (measured: ~1 us of ~1.7).  One cp.async group per call.
+    auto fetch_residual = [&](int tt, int ss) {
+      if (tt < p.tiles_per_group) {
+        const int q0 = tt * KW3_TILE + ss * KW3_SUB - 1 + lg * 32;
+        const int row_hi = max(row_lo, min(32, p.group_positions - q0));
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0 * N + c * 32);
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+          const int m = i * 32 + lane, row = m / HV, j = m - row * HV;
+          if (row >= row_lo && row < row_hi) {
+            const uint32_t dst = stg_warp_s + (uint32_t)ss * (32u * HROWB) + (uint32_t)row * HROWB + (uint32_t)(((j ^ (row >> 1)) & 3) * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (int64_t)row * (N * 2) + j * 16) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (has_res) fetch_residual(blockIdx.x, 0);
+    int it = 0, xi = 0;
+    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+      const uint32_t tphase = (uint32_t)it & 1u;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t stg_sub = (uint32_t)sub * (32u * HROWB);   // staging buffer of this sub-tile
+        // output position of this thread's row / of the warp's row 0, inside the group
+        const int q0 = t * KW3_TILE + sub * KW3_SUB - 1 + lg * 32;
+        const int q = q0 + lane;
+        const int row_hi = max(row_lo, min(32, p.group_positions - q0));
+        const uint32_t qq = (uint32_t)(q < 0 ? 0 : q);
+        const uint32_t rem = qq - fdiv(qq, kp.div_img) * kp.div_img.d;
+        const uint32_t yy = fdiv(rem, kp.div_wp), xx = rem - yy * kp.div_wp.d;
+        const bool interior = r >= 1 && q < p.group_positions && yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W;
+        // element offset of the warp's row 0, channel 32c (may point one row before the group: never dereferenced there)
+        const int64_t off0 = (int64_t)g * p.y_group_elems + (int64_t)q0 * N + c * 32;
+        uint8_t* my_row = stg_warp + stg_sub + (size_t)lane * HROWB;
+        // the other staging buffer was written out one sub-tile ago: fill it with the next sub-tile's residual
+        if (has_res) fetch_residual(sub == 0 ? t : t + (int)gridDim.x, sub ^ 1);
+        mbar_wait(bar_tfull + 8 * sub, tphase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(sub * ACC_STRIDE + c * 32);
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32b_x32(taddr, a0);
+        tmem_ld_32x32b_x32(taddr + (uint32_t)N, a1);
+        tmem_ld_wait();
+        // hand the accumulator back as soon as it is in registers
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * sub);
+        // Row at the upper edge of the lane quarter: lane 31 publishes its D0 row for the next warp.  Nobody inside
+        // the warp needs lane 31's D0, so after the barrier that register takes the PREVIOUS warp's row and the
+        // one-row shift becomes a plain rotate (lane 0 receives D0[r-1] from lane 31).  MMA row 0 is halo.
+        if (lane == 31) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(&xch[xi][c][lg][v * 4]) = make_uint4(a0[v * 4], a0[v * 4 + 1], a0[v * 4 + 2], a0[v * 4 + 3]);
+        }
+        // the four lane-quarter warps of this channel half
+        if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (lane == 31) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const uint4 t4 = *reinterpret_cast<const uint4*>(&xch[xi][c][(lg + 3) & 3][v * 4]);
+            a0[v * 4] = t4.x; a0[v * 4 + 1] = t4.y; a0[v * 4 + 2] = t4.z; a0[v * 4 + 3] = t4.w;
+          }
+        }
+        xi ^= 1;
+        if (has_res) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");   // this sub-tile's residual landed (the next one may be in flight)
+          __syncwarp();
+        }
+#pragma unroll
+        for (int v = 0; v < HV; ++v) {
+          float h[8];
+          const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+          const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float bsv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 2) {
+            const int i = v * 8 + jj;
+            const uint32_t u0 = __shfl_sync(0xffffffffu, a0[i], up), u1 = __shfl_sync(0xffffffffu, a0[i + 1], up);
+            add_scale2(h[jj], h[jj + 1], u0, u1, a1[i], a1[i + 1], scv[jj], scv[jj + 1], bsv[jj], bsv[jj + 1]);
+          }
+          uint4* slot = reinterpret_cast<uint4*>(my_row + (((v ^ (lane >> 1)) & 3) * 16));
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border / halo positions stay zero
+          if (interior) {
+            if (has_res) {
+              const uint4 rr = *slot;
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float2 rf = __bfloat1622float2(r2[jj]);
+                h[2 * jj] += rf.x;
+                h[2 * jj + 1] += rf.y;
+              }
+            }
+            o = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+            if (p.relu) {   // max(bf16(x), 0) == bf16(max(x, 0))
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+              const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) o2[jj] = __hmax2(o2[jj], z);
+            }
+          }
+          *slot = o;
+        }
+        __syncwarp();
+        // write-out of the warp's half rows [row_lo, row_hi): 64 contiguous bytes per row
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.y + off0);
+        const uint8_t* blk = stg_warp + stg_sub;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+          const int m = i * 32 + lane, row = m / HV, j = m - row * HV;
+          if (row >= row_lo && row < row_hi)
+            *reinterpret_cast<uint4*>(dst + (int64_t)row * (N * 2) + j * 16) =
+                *reinterpret_cast<const uint4*>(blk + (size_t)row * HROWB + (((j ^ (row >> 1)) & 3) * 16));
+        }
+        __syncwarp();   // staging rows of this sub-tile are rewritten by the next tile's residual fetch
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Opt-in (AMOE_FLAT_KW3=1).  Measured on B200 at batch 256 (layer1, 3 experts): correct, but 308 / 369 us per
+// convolution (without / with residual) against 249 / 302 us of conv3x3_flat_kernel<64>.  Timing the parts alone:
+// loads + MMAs + TMEM drain 171 us - the operand-bandwidth argument above holds - but the epilogue alone 270 us:
+// the shift-add makes it ~400 instructions per warp and 128-row sub-tile (8 warps -> ~3200 issue slots per
+// sub-tile against ~1300 cycles of MMA time), and neither more epilogue warps (16, one set per sub-tile), a second
+// MMA issuer, a residual prefetched one sub-tile ahead, nor dropping the row-exchange barrier or the shuffles
+// changed the time: it is bound by instruction issue of the epilogue as a whole, not by one step of it.
+static bool kw3_enabled() {
+  const char* e = getenv("AMOE_FLAT_KW3");
+  return e != nullptr && atoi(e) != 0;
+}
+
+}  // namespace flat
+
+namespace flat {
 static bool supported(int H, int W, int C, int N) {
   return C % 64 == 0 && (N == 64 || N == 128) && W + 2 <= 120 && H >= 1;
 }
@@ -352,6 +684,8 @@ int amoe_conv_flat_init(amoe_ctx* ctx) {
                                        flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kw3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET - flat::KW3_STATIC + flat::STG_BYTES + 1024));
   return 0;
 }
 
@@ -377,11 +711,14 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   Params p;
   p.G = G; p.B = B; p.H = H; p.W = W; p.Hp = H + 2; p.Wp = W + 2; p.C = Cin; p.N = Cout;
   p.chunks = Cin / BLOCK_K;
-  p.rows_pad = (TILE_P + 2 * p.Wp + 2 + 15) & ~15;
+  // 64 -> 64 channels: the kw-fused kernel (three horizontal taps per MMA, 252-position tiles with a one-row halo)
+  const bool kw3 = Cin == 64 && Cout == 64 && kw3_enabled();
+  const int tile_p = kw3 ? KW3_TILE : TILE_P;
+  p.rows_pad = ((kw3 ? KW3_TILE + 2 : TILE_P + 2) + 2 * p.Wp + 15) & ~15;   // kw3: + halo row before, + 1 for the shifted tap
   const int64_t gp = (int64_t)B * p.Hp * p.Wp;
   AMOE_REQUIRE(gp * G < (1ll << 31) - 4096, "amoe_conv3x3_flat_fwd: too many positions");
   p.group_positions = (int)gp;
-  p.tiles_per_group = (int)((gp + TILE_P - 1) / TILE_P);
+  p.tiles_per_group = (int)((gp + tile_p - 1) / tile_p);
   p.relu = relu;
   p.y_group_elems = (y_group_images > 0 ? y_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
   p.res_group_elems = (res_group_images > 0 ? res_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
@@ -402,7 +739,7 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
     while (p.w_stages > 3 && SMEM_BUDGET - p.w_stages * w_tile < 3 * a_stage) --p.w_stages;
     w_bytes = p.w_stages * w_tile;
   }
-  p.a_stages = std::min(MAX_A_STAGES, (SMEM_BUDGET - w_bytes) / a_stage);
+  p.a_stages = std::min(MAX_A_STAGES, (SMEM_BUDGET - (kw3 ? KW3_STATIC : 0) - w_bytes) / a_stage);
   AMOE_REQUIRE(p.a_stages >= 1, "amoe_conv3x3_flat_fwd: shared memory budget exceeded");
   if (gp == 0) return 0;
 
@@ -430,7 +767,14 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
   p.stg_off = (uint32_t)(p.a_stages * a_stage + w_bytes);
   const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + STG_BYTES + 1024;
-  if (Cout == 64)
+  if (kw3) {
+    AMOE_REQUIRE(p.w_resident && p.a_stages >= 1, "amoe_conv3x3_flat_fwd: kw-fused kernel needs resident weights");
+    Kw3Params kp;
+    kp.p = p;
+    kp.div_img = fastdiv_init((uint32_t)(p.Hp * p.Wp));
+    kp.div_wp = fastdiv_init((uint32_t)p.Wp);
+    conv3x3_flat_kw3_kernel<<<dim3(ctas, G), KW3_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, kp);
+  } else if (Cout == 64)
     conv3x3_flat_kernel<64><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
   else
     conv3x3_flat_kernel<128><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);

@@ -308,15 +308,22 @@ FLAT_SHAPES = [
     (1, 5, 14, 14, 128, 128, True),
     (1, 40, 16, 16, 64, 64, False),    # many tiles per CTA: both accumulators, ring wrap-around
     (1, 2, 8, 8, 64, 128, False),      # Cin != Cout
+    (2, 3, 13, 11, 64, 64, True),      # odd sizes: ragged last tile, group boundary inside a kw-fused sub-tile
+    (1, 1, 4, 4, 64, 64, False),       # a single partial tile
 ]
 
 
 @pytest.mark.timeout(180)
+@pytest.mark.parametrize("kw3", ["0", "1"])
 @pytest.mark.parametrize("shape", FLAT_SHAPES)
-def test_conv_flat_bf16(shape):
-    """Halo-reuse 3x3/s1 kernel on physically padded activations (csrc/conv_flat.cu)."""
+def test_conv_flat_bf16(shape, kw3, monkeypatch):
+    """Halo-reuse 3x3/s1 kernel on physically padded activations (csrc/conv_flat.cu).  kw3=1: the opt-in
+    64->64 variant that multiplies two horizontal taps per MMA and shifts rows in the epilogue."""
     from automoe_b200 import _ops
     G, B, H, W, C, N, residual = shape
+    if kw3 == "1" and (C != 64 or N != 64):
+        pytest.skip("kw-fused kernel is 64 -> 64 channels only")
+    monkeypatch.setenv("AMOE_FLAT_KW3", kw3)
     g = torch.Generator().manual_seed(6)
     convs, bns = _mk_conv_bn(C, N, 3, 1, 1, g, n=G)
     x = torch.randn((G * B, C, H, W), generator=g).bfloat16().float().to(DEV)
