@@ -513,34 +513,39 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // ============================ epilogue ================================
     // Eight warps: warp (c, lg) owns TMEM lane quarter lg (MMA rows [32*lg, 32*lg+32)) and output channels
     // [32c, 32c+32) of both sub-tiles; two warps per SM sub-partition hide each other's latencies.  (Sixteen warps,
-    // one set per sub-tile, were measured slower.)
+    // one set per sub-tile, were measured slower.)  This epilogue is what bounds the kernel, so everything that does
+    // not depend on the sub-tile is a per-thread constant: a thread moves the same four 16-byte pieces (row
+    // 8i + lane/4, piece lane%4) of every staged 32-row x 64-byte block, between fixed staging addresses and
+    // base + i*1024 bytes in global memory.
     const int lg = warp & 3, c = (warp - 3) >> 2;
-    constexpr int HV = 4, HROWB = 64;     // 16-byte pieces / bytes of a staged half row (32 channels)
-    const uint32_t stg_off_w = p.stg_off + (uint32_t)(c * 4 + lg) * 2 * (32u * HROWB);
-    uint8_t* stg_warp = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off_w;
-    const uint32_t stg_warp_s = smem_base + stg_off_w;
+    constexpr int HROWB = 64;             // bytes of a staged half row (32 channels)
+    const uint32_t stg_warp_s = smem_base + p.stg_off + (uint32_t)(c * 4 + lg) * 2 * (32u * HROWB);
     const bool has_res = p.residual != nullptr;
     const int r = lg * 32 + lane;         // MMA row of this thread
-    const int row_lo = lg == 0 ? 1 : 0;   // MMA row 0 is halo
+    const int rl = lane >> 2;             // row (mod 8) of the pieces this thread moves
+    // staging address / global byte offset of piece i = 0 (pieces of odd row pairs are swizzled: (j ^ row/2) & 3)
+    const uint32_t piece_s = stg_warp_s + (uint32_t)rl * HROWB + (uint32_t)((((lane & 3) ^ (lane >> 3)) & 3) * 16);
+    const int piece_g = rl * (N * 2) + (lane & 3) * 16;
+    const int i0_lo = (lg == 0 && rl == 0) ? 1 : 0;     // MMA row 0 is halo: lanes 0-3 of lane quarter 0 skip piece 0
+    const uint32_t my_row_s = stg_warp_s + (uint32_t)lane * HROWB;
+    const uint32_t my_sw = (uint32_t)(lane >> 1);
     const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);   // folded BatchNorm of this warp's channels
     const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
     const int up = (lane + 31) & 31;
-    // Residual half rows of the warp's block of sub-tile (tt, ss) -> staging buffer ss (swizzled).  Issued one
-    // sub-tile AHEAD: the epilogue, not the MMA, sets the pace of this kernel, so a fetch issued when its sub-tile
-    // starts would expose one HBM latency per sub-tile (measured: ~1 us of ~1.7).  One cp.async group per call.
+    const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual) + ((int64_t)g * p.res_group_elems + c * 32) * 2 + piece_g;
+    uint8_t* y_base = reinterpret_cast<uint8_t*>(p.y) + ((int64_t)g * p.y_group_elems + c * 32) * 2 + piece_g;
+    // Residual half rows of the warp's block of sub-tile (tt, ss) -> staging buffer ss.  Issued one sub-tile AHEAD:
+    // the epilogue, not the MMA, sets the pace of this kernel.  One cp.async group per call.
     auto fetch_residual = [&](int tt, int ss) {
       if (tt < p.tiles_per_group) {
         const int q0 = tt * KW3_TILE + ss * KW3_SUB - 1 + lg * 32;
-        const int row_hi = max(row_lo, min(32, p.group_positions - q0));
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0 * N + c * 32);
+        const int rows = p.group_positions - q0 - rl;     // piece i is inside the group iff 8i < rows
+        const uint8_t* src = res_base + (int64_t)q0 * (N * 2);
+        const uint32_t dst = piece_s + (uint32_t)ss * (32u * HROWB);
 #pragma unroll
-        for (int i = 0; i < HV; ++i) {
-          const int m = i * 32 + lane, row = m / HV, j = m - row * HV;
-          if (row >= row_lo && row < row_hi) {
-            const uint32_t dst = stg_warp_s + (uint32_t)ss * (32u * HROWB) + (uint32_t)row * HROWB + (uint32_t)(((j ^ (row >> 1)) & 3) * 16);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (int64_t)row * (N * 2) + j * 16) : "memory");
-          }
-        }
+        for (int i = 0; i < 4; ++i)
+          if (i >= i0_lo && 8 * i < rows)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 8 * HROWB), "l"(src + i * 8 * (N * 2)) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -551,17 +556,13 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const uint32_t stg_sub = (uint32_t)sub * (32u * HROWB);   // staging buffer of this sub-tile
-        // output position of this thread's row / of the warp's row 0, inside the group
+        // output position of the warp's row 0 / of this thread's row, inside the group
         const int q0 = t * KW3_TILE + sub * KW3_SUB - 1 + lg * 32;
         const int q = q0 + lane;
-        const int row_hi = max(row_lo, min(32, p.group_positions - q0));
-        const uint32_t qq = (uint32_t)(q < 0 ? 0 : q);
+        const uint32_t qq = (uint32_t)max(q, 0);
         const uint32_t rem = qq - fdiv(qq, kp.div_img) * kp.div_img.d;
         const uint32_t yy = fdiv(rem, kp.div_wp), xx = rem - yy * kp.div_wp.d;
-        const bool interior = r >= 1 && q < p.group_positions && yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W;
-        // element offset of the warp's row 0, channel 32c (may point one row before the group: never dereferenced there)
-        const int64_t off0 = (int64_t)g * p.y_group_elems + (int64_t)q0 * N + c * 32;
-        uint8_t* my_row = stg_warp + stg_sub + (size_t)lane * HROWB;
+        const bool interior = r >= 1 && q < p.group_positions && yy - 1u < (uint32_t)p.H && xx - 1u < (uint32_t)p.W;
         // the other staging buffer was written out one sub-tile ago: fill it with the next sub-tile's residual
         if (has_res) fetch_residual(sub == 0 ? t : t + (int)gridDim.x, sub ^ 1);
         mbar_wait(bar_tfull + 8 * sub, tphase);
@@ -599,7 +600,7 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           __syncwarp();
         }
 #pragma unroll
-        for (int v = 0; v < HV; ++v) {
+        for (int v = 0; v < 4; ++v) {
           float h[8];
           const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
           const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -610,39 +611,41 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint32_t u0 = __shfl_sync(0xffffffffu, a0[i], up), u1 = __shfl_sync(0xffffffffu, a0[i + 1], up);
             add_scale2(h[jj], h[jj + 1], u0, u1, a1[i], a1[i + 1], scv[jj], scv[jj + 1], bsv[jj], bsv[jj + 1]);
           }
-          uint4* slot = reinterpret_cast<uint4*>(my_row + (((v ^ (lane >> 1)) & 3) * 16));
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border / halo positions stay zero
-          if (interior) {
-            if (has_res) {
-              const uint4 rr = *slot;
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+          const uint32_t slot = my_row_s + stg_sub + (((uint32_t)v ^ my_sw) & 3u) * 16u;
+          if (has_res) {
+            uint4 rr;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(slot) : "memory");
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float2 rf = __bfloat1622float2(r2[jj]);
-                h[2 * jj] += rf.x;
-                h[2 * jj + 1] += rf.y;
-              }
-            }
-            o = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-            if (p.relu) {   // max(bf16(x), 0) == bf16(max(x, 0))
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-              const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) o2[jj] = __hmax2(o2[jj], z);
+            for (int jj = 0; jj < 4; ++jj) {   // bf16 pair -> two fp32: low half << 16, high half masked
+              h[2 * jj] += __uint_as_float(rw[jj] << 16);
+              h[2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
             }
           }
-          *slot = o;
+          uint4 o = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          if (p.relu) {   // max(bf16(x), 0) == bf16(max(x, 0))
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) o2[jj] = __hmax2(o2[jj], z);
+          }
+          if (!interior) o = make_uint4(0u, 0u, 0u, 0u);   // border / halo positions stay zero
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(slot), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
         __syncwarp();
-        // write-out of the warp's half rows [row_lo, row_hi): 64 contiguous bytes per row
-        uint8_t* dst = reinterpret_cast<uint8_t*>(p.y + off0);
-        const uint8_t* blk = stg_warp + stg_sub;
+        // write-out: piece i of this thread = row 8i + lane/4 of the block, 16 bytes at byte 16*(lane%4) of its 64
+        {
+          uint8_t* dst = y_base + (int64_t)q0 * (N * 2);
+          const int rows = p.group_positions - q0 - rl;
+          const uint32_t src = piece_s + stg_sub;
 #pragma unroll
-        for (int i = 0; i < HV; ++i) {
-          const int m = i * 32 + lane, row = m / HV, j = m - row * HV;
-          if (row >= row_lo && row < row_hi)
-            *reinterpret_cast<uint4*>(dst + (int64_t)row * (N * 2) + j * 16) =
-                *reinterpret_cast<const uint4*>(blk + (size_t)row * HROWB + (((j ^ (row >> 1)) & 3) * 16));
+          for (int i = 0; i < 4; ++i) {
+            if (i >= i0_lo && 8 * i < rows) {
+              uint4 v4;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "r"(src + i * 8 * HROWB) : "memory");
+              *reinterpret_cast<uint4*>(dst + i * 8 * (N * 2)) = v4;
+            }
+          }
         }
         __syncwarp();   // staging rows of this sub-tile are rewritten by the next tile's residual fetch
       }
@@ -657,13 +660,16 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
 }
 
-// Opt-in (AMOE_FLAT_KW3=1).  Measured on B200 at batch 256 (layer1, 3 experts): correct, but 308 / 369 us per
-// convolution (without / with residual) against 249 / 302 us of conv3x3_flat_kernel<64>.  Timing the parts alone:
-// loads + MMAs + TMEM drain 171 us - the operand-bandwidth argument above holds - but the epilogue alone 270 us:
-// the shift-add makes it ~400 instructions per warp and 128-row sub-tile (8 warps -> ~3200 issue slots per
-// sub-tile against ~1300 cycles of MMA time), and neither more epilogue warps (16, one set per sub-tile), a second
-// MMA issuer, a residual prefetched one sub-tile ahead, nor dropping the row-exchange barrier or the shuffles
-// changed the time: it is bound by instruction issue of the epilogue as a whole, not by one step of it.
+// Opt-in (AMOE_FLAT_KW3=1).  Measured on B200 at batch 256 (layer1, 3 experts, four convolutions per forward): correct,
+// but the whole forward is 0.08-0.19 ms slower with it (4.56-4.69 ms against 4.48-4.50 ms on the same box).  First
+// version: 308 / 369 us per convolution (without / with residual) against 249 / 302 us of conv3x3_flat_kernel<64>.
+// Timing the parts alone: loads + MMAs + TMEM drain 171 us - the operand-bandwidth argument above holds - but the
+// epilogue alone 270 us: ~400 instructions per warp and 128-row sub-tile (8 warps -> ~3200 issue slots per sub-tile
+// against ~1300 cycles of MMA time).  More epilogue warps (16, one set per sub-tile), a second MMA issuer, the
+// residual prefetched one sub-tile ahead, dropping the row-exchange barrier or the shuffles: each within noise - the
+// epilogue is bound by instruction issue as a whole.  Making everything sub-tile-independent a per-thread constant
+// (this version, ~250 instructions) recovered two thirds of the gap.  What is left is inherent to the shift
+// (32 shuffles, the exchange and its barrier, eight warps' fixed overhead); the 171 us bound stays the target.
 static bool kw3_enabled() {
   const char* e = getenv("AMOE_FLAT_KW3");
   return e != nullptr && atoi(e) != 0;
