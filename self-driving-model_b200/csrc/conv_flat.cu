@@ -47,6 +47,7 @@ struct Params {
   int tiles_per_group;   // ceil(B*Hp*Wp / TILE_P)
   int group_positions;   // B*Hp*Wp
   int relu;
+  int res_prefetch;      // epilogue prefetches the next tile's residual rows into L2 (AMOE_FLAT_RES_PREFETCH=0 disables)
   int64_t y_group_elems, res_group_elems;  // element distance between the expert groups of y / residual
   const float* scale;
   const float* bias;
@@ -249,6 +250,20 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (has_res) {
         fetch_residual(0, 0);
         if (BUFS == 2) fetch_residual(1, 1);
+        // The residual was last touched a whole convolution ago (long evicted from L2), so the cp.async above pays an
+        // HBM round trip that the ~1.4 us of MMAs per tile only partly cover: ask L2 for the NEXT tile's rows now.
+        if (p.res_prefetch) {
+          const int tn = t + (int)gridDim.x;
+          if (tn < p.tiles_per_group) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int q0n = tn * TILE_P + half * BLOCK_M + lg * 32;
+              const int bytes = min(32, max(0, p.group_positions - q0n)) * ROWB;
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0n * N);
+              for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+            }
+          }
+        }
       }
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
@@ -726,6 +741,7 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   p.group_positions = (int)gp;
   p.tiles_per_group = (int)((gp + tile_p - 1) / tile_p);
   p.relu = relu;
+  { const char* e = getenv("AMOE_FLAT_RES_PREFETCH"); p.res_prefetch = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
   p.y_group_elems = (y_group_images > 0 ? y_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
   p.res_group_elems = (res_group_images > 0 ? res_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
   p.scale = scale; p.bias = bias;
