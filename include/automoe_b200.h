@@ -200,7 +200,8 @@ int amoe_gate_fwd(amoe_ctx*, const float* state, const float* pooled, const floa
 /* Same with an optional bf16 copy of the parameter buffer (same element offsets, 16-byte aligned):
  * params_bf16 != NULL and B >= 16 selects the bf16-inference variant - 16 frames per CTA, every layer with
  * K % 32 == 0 on mma.sync TF32 (bf16 weights, fp32 activations truncated to TF32, fp32 accumulation; the
- * K = 4 / C_e input layers, biases, LayerNorm and softmax stay fp32). */
+ * K = 4 / C_e input layers, biases, LayerNorm and softmax stay fp32).  With mode == 0 it launches clusters of
+ * E+1 CTAs per 16 frames (one expert chain per CTA, gate input gathered through distributed shared memory). */
 int amoe_gate_fwd_ex(amoe_ctx*, const float* state, const float* pooled, const float* params,
                      const void* params_bf16, int64_t n_params, int B, int E, const int* n_ch_host,
                      int ctx_dim, int hidden, float temperature, int mode, float* context,

@@ -14,6 +14,8 @@
 //   per expert e: proc.W0[P,F] b | proc.W3[P,P] b | proc.ln.g[P] b[P]
 //   gate.net0.W[hid,hid+P*E] b | gate.net3.W[E,hid] b | out_proj.W[P,P] b
 // with F = expert feature dim (256), P = processed dim (256).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mlp.cuh"
 
@@ -31,6 +33,7 @@ struct GateDims {
   int n_ch[GATE_MAX_E];
   float temperature;
   int mode;
+  int split;   // tensor-core variant launched as clusters of E+1 CTAs per 16 frames (see gate_fused_kernel)
 };
 
 // shared-memory row strides (floats) of the per-CTA activation buffers; the tensor-core variant pads every row to
@@ -59,7 +62,17 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     float* __restrict__ processed, float* __restrict__ gate_logits, float* __restrict__ weights,
     float* __restrict__ combined) {
   extern __shared__ __align__(16) float sm[];
-  const int f0 = (CL ? blockIdx.x / CL_RANKS : blockIdx.x) * FT;
+  // Tensor-core variant, d.split: the weight stream per CTA bounds this kernel and the E expert chains (extractor +
+  // processor, 3/4 of the parameters) are independent, so a cluster of E+1 CTAs owns the 16 frames: rank e < E runs
+  // expert e, rank E the context path; each writes its block of the gate input into rank 0's shared memory
+  // (distributed shared memory), and after one cluster barrier rank 0 runs the gate MLP, softmax, combine and
+  // projection.  Per-CTA weight stream: 1.03 M -> 0.26 M + 0.18 M parameters on the critical path.
+  const bool split = TC && d.split;
+  const int R = d.E + 1;
+  const int rank = split ? (int)cg::this_cluster().block_rank() : 0;
+  const int f0 = (CL ? blockIdx.x / CL_RANKS : (split ? blockIdx.x / R : blockIdx.x)) * FT;
+  const bool do_ctx = !split || rank == d.E;      // context extractor + gating context encoder
+  if (split) cg::this_cluster().sync();           // every CTA of the cluster is running before anyone writes into rank 0
   const int gin = d.hidden + d.P * d.E;  // gate_network input width
   // shared-memory carve-up (all row strides multiples of 4 floats)
   const GateLds L = gate_lds(d.sumC, d.ctx_dim, d.hidden, d.F, d.P, d.E, TC);
@@ -102,12 +115,12 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* b3 = p; p += al8(d.ctx_dim);
     const float* g = p; p += al8(d.ctx_dim);
     const float* bb = p; p += al8(d.ctx_dim);
-    if (!ctx_in) {
+    if (!ctx_in && do_ctx) {
       linear_ft<FT, CL, TC>(W0, b0, s_in, ld_in, 4, s_h, ld_h, 32, true, w16(W0));
       linear_ft<FT, CL, TC>(W3, b3, s_h, ld_h, 32, s_ctx, ld_ctx, d.ctx_dim, false, w16(W3));
       layernorm_ft<FT, CL>(s_ctx, ld_ctx, d.ctx_dim, g, bb);
     }
-    if (context) store_rows<FT, CL>(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
+    if (context && do_ctx) store_rows<FT, CL>(context, d.ctx_dim, s_ctx, ld_ctx, d.ctx_dim, f0, d.B);
     if (d.mode & GATE_MODE_STOP_CTX) return;
   }
 
@@ -124,9 +137,17 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* b0 = p; p += al8(d.hidden);
     const float* W3 = p; p += al8((int64_t)d.hidden * d.hidden);
     const float* b3 = p; p += al8(d.hidden);
-    if (!(d.mode & GATE_MODE_STOP_FEAT)) {
+    if (!(d.mode & GATE_MODE_STOP_FEAT) && do_ctx) {
       linear_ft<FT, CL, TC>(W0, b0, s_ctx, ld_ctx, d.ctx_dim, s_t, ld_t, d.hidden, true, w16(W0));
       linear_ft<FT, CL, TC>(W3, b3, s_t, ld_t, d.hidden, s_gin, ld_gin, d.hidden, true, w16(W3));
+      if (split) {   // encoded context -> rank 0's gate input, columns [0, hidden)
+        float* dst = cg::this_cluster().map_shared_rank(s_gin, 0);
+        const int n4 = d.hidden >> 2;
+        for (int i = threadIdx.x; i < FT * n4; i += blockDim.x) {
+          const int f = i / n4, c4 = i - f * n4;
+          *reinterpret_cast<float4*>(dst + f * ld_gin + (c4 << 2)) = *reinterpret_cast<const float4*>(s_gin + f * ld_gin + (c4 << 2));
+        }
+      }
     }
   }
   int ch_off = 4;
@@ -145,6 +166,10 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* Pg = p; p += al8(d.P);
     const float* Pbb = p; p += al8(d.P);
     float* s_proc = s_gin + d.hidden + e * d.P;
+    if (split && rank != e) {   // another rank's expert (split implies mode == 0)
+      ch_off += d.n_ch[e];
+      continue;
+    }
     if (!ctx_only) {
       if (feat_in) {
         for (int i = threadIdx.x; i < FT * d.F; i += blockDim.x) {
@@ -164,6 +189,14 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
         linear_ft<FT, CL, TC>(PW3, Pb3, s_t, ld_t, d.P, s_proc, ld_gin, d.P, false, w16(PW3));
         layernorm_ft<FT, CL>(s_proc, ld_gin, d.P, Pg, Pbb);
         if (processed) store_rows<FT, CL>(processed + (int64_t)e * d.B * d.P, d.P, s_proc, ld_gin, d.P, f0, d.B);
+        if (split && rank != 0) {   // processed_e -> rank 0's gate input, columns [hidden + e*P, hidden + (e+1)*P)
+          float* dst = cg::this_cluster().map_shared_rank(s_gin, 0) + d.hidden + e * d.P;
+          const int n4 = d.P >> 2;
+          for (int i = threadIdx.x; i < FT * n4; i += blockDim.x) {
+            const int f = i / n4, c4 = i - f * n4;
+            *reinterpret_cast<float4*>(dst + f * ld_gin + (c4 << 2)) = *reinterpret_cast<const float4*>(s_proc + f * ld_gin + (c4 << 2));
+          }
+        }
       }
     } else {
       // get_expert_weights (gating_network.py:177-199): zeros stand in for the experts
@@ -174,6 +207,10 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
   }
 
   if (d.mode & GATE_MODE_STOP_FEAT) return;
+  if (split) {
+    cg::this_cluster().sync();   // every rank's block of the gate input has landed in rank 0's shared memory
+    if (rank != 0) return;
+  }
 
   // ---- gate MLP + softmax (gating_network.py:94-99,141-160) ----
   {
@@ -246,7 +283,7 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
   AMOE_REQUIRE(temperature > 0.f, "amoe_gate_fwd: temperature must be > 0");
   GateDims d;
   d.B = B; d.E = E; d.ctx_dim = ctx_dim; d.hidden = hidden; d.F = 256; d.P = 256;
-  d.temperature = temperature; d.mode = mode; d.sumC = 0;
+  d.temperature = temperature; d.mode = mode; d.sumC = 0; d.split = 0;
   for (int e = 0; e < GATE_MAX_E; ++e) d.n_ch[e] = 0;
   for (int e = 0; e < E; ++e) {
     AMOE_REQUIRE(n_ch_host[e] >= 1, "amoe_gate_fwd: n_ch[%d]=%d", e, n_ch_host[e]);
@@ -267,8 +304,26 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
     AMOE_REQUIRE(smem <= 226 * 1024, "amoe_gate_fwd: dims too large for shared memory");
     auto kern = gate_fused_kernel<MMA_FT, false, true>;
     AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ceil_div(B, MMA_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
-        d, state, pooled, params, p16, context, features, processed, gate_logits, weights, combined);
+    const char* e = getenv("AMOE_GATE_SPLIT");
+    d.split = (mode == 0 && hidden % 4 == 0 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
+    if (d.split) {
+      // the forward of AutoMoE: clusters of E+1 CTAs per 16 frames (expert chains and the context path in parallel)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(ceil_div(B, MMA_FT) * (E + 1));
+      cfg.blockDim = dim3(GATE_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = E + 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, p16, context, features, processed, gate_logits,
+                                         weights, combined));
+    } else {
+      kern<<<ceil_div(B, MMA_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
+          d, state, pooled, params, p16, context, features, processed, gate_logits, weights, combined);
+    }
     AMOE_LAUNCH_OK(ctx);
     return 0;
   }
