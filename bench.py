@@ -362,6 +362,35 @@ def run_b200(args):
             roof["simt_conv_ms_per_step"] = ts / 2
             roof["simt_conv_tflops"] = fs / (ts / 1e3) / 1e12
 
+    # ---------------- the HBM-bound kernel of the path: the x32 full-resolution logit writer, timed alone ----------------
+    # (22 classes x 65536 pixels x 2 B per frame; in the forward it runs on the side stream beside the
+    # gate / policy tail, so it is timed here on its own: algorithmic bytes written / CUDA-event time)
+    if roof is not None:
+        from automoe_b200._cabi import check, ctx as _ctx, dtype_code, lib, ptr, stream_ptr
+        low = torch.randn((B, 8, 8, 19), device=dev, dtype=torch.float32)
+        up = torch.empty((B, 19, 256, 256), device=dev, dtype=torch.bfloat16)      # written in place by every launch
+
+        def writer():
+            check(lib().amoe_upsample_bilinear_nchw_fwd(_ctx(dev), ptr(low), ptr(up), B, 8, 8, 19, 256, 256,
+                                                        dtype_code(torch.bfloat16), stream_ptr(dev)), "upsample")
+        for _ in range(3):
+            writer()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 10                              # back to back: 6.4 GB written, the 126 MB L2 cannot absorb it
+        ev[0].record()
+        for _ in range(reps):
+            writer()
+        ev[1].record()
+        torch.cuda.synchronize()
+        wbytes = up.numel() * 2
+        gbs = wbytes * reps / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9
+        roof["hbm_kernel"] = {"kernel": "upsample_intscale_nchw_kernel (x32 bilinear logit writer, 19 classes)", "bound": "hbm",
+                              "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                              "algorithmic_bytes_per_launch": wbytes, "us_per_launch": ev[0].elapsed_time(ev[1]) * 1e3 / reps,
+                              "how": "10 launches back to back on a preallocated output, CUDA events; the peak is the measured COPY "
+                                     "bandwidth (read+write mix) - a pure write stream can exceed it (HBM3e nominal ~7.7 TB/s)"}
+        del up, low
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
