@@ -91,14 +91,14 @@ static int64_t policy_param_count(const PolicyDims& d) {
 }
 
 // AdaptiveAvgPool2d(1) of an NHWC tensor: out[b][c] = mean over the HW pixels, summed in a fixed order
-// (4 pixel quarters per CTA, each accumulated front to back, then quarter 0+1+2+3) -> deterministic.
+// (8 pixel slices per CTA, each accumulated front to back, then slice 0+1+...+7) -> deterministic.
 // One CTA per frame, a lane owns 8 channels (one 16-byte load per pixel), so a warp reads whole 512-byte
 // pixel rows; this spreads the 33 MB read over all SMs instead of the 16 CTAs of the tensor-core head.
-__global__ __launch_bounds__(128) void mean_hw_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+__global__ __launch_bounds__(256) void mean_hw_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                                  int HW, int C) {
-  __shared__ float part[4][8 * 32 + 8];
+  __shared__ float part[8][8 * 32 + 8];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = (HW + 3) >> 2, p0 = warp * per, p1 = min(HW, p0 + per);
+  const int per = (HW + 7) >> 3, p0 = warp * per, p1 = min(HW, p0 + per);
   for (int cb = 0; cb < C; cb += 256) {          // CTA-uniform trip count
     const int c0 = cb + lane * 8;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -123,7 +123,10 @@ __global__ __launch_bounds__(128) void mean_hw_nhwc_bf16_kernel(const __nv_bfloa
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = lane * 8 + j;
-        out[(int64_t)b * C + c0 + j] = (((part[0][i] + part[1][i]) + part[2][i]) + part[3][i]) / (float)HW;
+        float t = part[0][i];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part[q][i];
+        out[(int64_t)b * C + c0 + j] = t / (float)HW;
       }
     }
     __syncthreads();
@@ -136,7 +139,7 @@ extern "C" int amoe_mean_hw_nhwc_fwd(amoe_ctx* ctx, const void* x, float* out, i
   AMOE_REQUIRE(dtype == AMOE_BF16 && C % 8 == 0 && HW >= 1, "amoe_mean_hw_nhwc_fwd: bf16 input with C %% 8 == 0 only (C=%d)", C);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "amoe_mean_hw_nhwc_fwd: x must be 16-byte aligned");
   if (B == 0) return 0;
-  mean_hw_nhwc_bf16_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, HW, C);
+  mean_hw_nhwc_bf16_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, HW, C);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
