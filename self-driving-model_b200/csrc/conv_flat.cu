@@ -30,10 +30,10 @@ namespace flat {
 using namespace tc;
 
 constexpr int TILE_P = 256;
-constexpr int NUM_THREADS = 224;  // warp 0 producer, warps 1-2 MMA issuers (one per M-half), warps 3-6 epilogue
+constexpr int NUM_THREADS = 352;  // warp 0 producer, warps 1-2 MMA issuers (one per M-half), warps 3-10 epilogue (four per M-half)
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int SMEM_BUDGET = 192 * 1024;  // activation + weight stages (the epilogue staging rows come on top)
+constexpr int SMEM_BUDGET = 192 * 1024;  // activation + weight stages of the N=64 kernels (their staging rows, 32 KB, come on top)
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_W_STAGES = 8;
 constexpr int W_RESIDENT_MAX = 80 * 1024;
@@ -55,9 +55,9 @@ struct Params {
   __nv_bfloat16* y;
 };
 
-template <int N>
-__host__ __device__ constexpr int STG_BUFS() { return N == 64 ? 2 : 1; }
-constexpr int STG_BYTES = 4 * 32 * 128 * 2;  // 4 epilogue warps x 32 rows x 256 B (N=64: two 128-byte buffers)
+constexpr int STG_BYTES = 8 * 32 * 64 * 2;   // N=64: 8 epilogue warps x 32 rows x 128 B
+constexpr int STG_BYTES_128 = 8 * 32 * 128 * 2;   // N=128: 8 epilogue warps x 32 rows x 256 B
+constexpr int SMEM_BUDGET_128 = 160 * 1024;       // operand stages of the N=128 kernel (224 KB with its staging rows)
 
 template <int N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -101,7 +101,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 2);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, 8);    // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -208,143 +208,124 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // memory: residual rows arrive there by cp.async (issued before the accumulator is ready),
     // every thread updates its row in place, and the warp then streams the 32 x N block - which is
     // contiguous in the flattened [P][N] output - with fully coalesced 16-byte stores.
-    const int lg = warp & 3;
+    // Eight warps: warp (lg, hs) owns TMEM lane quarter lg of M-half hs.  (Measured with the epilogue body removed:
+    // the N=128 kernel runs at 90 % tensor-busy, 156-166 us per layer2 convolution, against 70-76 % / 189-214 us with
+    // four warps draining both halves one after the other - it was bound by this epilogue, not by its MMAs.)
+    const int lg = warp & 3, hs = (warp - 3) >> 2;
     const int img = p.Hp * p.Wp;
     constexpr int NV = N / 8;            // 16-byte pieces per output row
     constexpr int ROWB = N * 2;          // bytes per staged row
-    constexpr int BUFS = STG_BUFS<N>();  // staging buffers per warp (one per M-half when they fit)
-    uint8_t* stg_warp = smem_raw + (smem_base - smem_u32(smem_raw)) + p.stg_off + (uint32_t)(lg * BUFS) * (32u * ROWB);
-    const uint32_t stg_warp_s = smem_base + p.stg_off + (uint32_t)(lg * BUFS) * (32u * ROWB);
+    const uint32_t stg_off_w = p.stg_off + (uint32_t)(lg * 2 + hs) * (32u * ROWB);
+    uint8_t* stg_warp = smem_raw + (smem_base - smem_u32(smem_raw)) + stg_off_w;
+    const uint32_t stg_warp_s = smem_base + stg_off_w;
     const bool has_res = p.residual != nullptr;
+    uint8_t* my_row = stg_warp + (size_t)lane * ROWB;
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      bool interior[2];
-      int rows_valid[2];
-      int64_t off0[2], roff0[2];   // element offset of the warp's first row in y / in the residual
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int q0 = t * TILE_P + half * BLOCK_M + lg * 32;  // first position of this warp inside the group
-        const int q = q0 + lane;
-        rows_valid[half] = min(32, max(0, p.group_positions - q0));
-        const int rem = q % img;
-        const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
-        interior[half] = q < p.group_positions && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-        off0[half] = (int64_t)g * p.y_group_elems + (int64_t)q0 * N;
-        roff0[half] = (int64_t)g * p.res_group_elems + (int64_t)q0 * N;
-      }
-      auto fetch_residual = [&](int half, int buf) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + roff0[half]);
+      const int q0 = t * TILE_P + hs * BLOCK_M + lg * 32;  // first position of this warp inside the group
+      const int q = q0 + lane;
+      const int rows_valid = min(32, max(0, p.group_positions - q0));
+      const int rem = q % img;
+      const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
+      const bool interior = q < p.group_positions && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
+      const int64_t off0 = (int64_t)g * p.y_group_elems + (int64_t)q0 * N;      // element offset of the warp's first row in y
+      const int64_t roff0 = (int64_t)g * p.res_group_elems + (int64_t)q0 * N;   // ... and in the residual
+      if (has_res) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + roff0);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int m = i * 32 + lane, row = m / NV, j = m - row * NV;
-          if (row < rows_valid[half]) {
-            const uint32_t dst = stg_warp_s + (uint32_t)buf * (32u * ROWB) + (uint32_t)row * ROWB +
-                                 (uint32_t)(((j & ~7) | ((j ^ row) & 7)) * 16);
+          if (row < rows_valid) {
+            const uint32_t dst = stg_warp_s + (uint32_t)row * ROWB + (uint32_t)(((j & ~7) | ((j ^ row) & 7)) * 16);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)m * 16) : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      if (has_res) {
-        fetch_residual(0, 0);
-        if (BUFS == 2) fetch_residual(1, 1);
         // The residual was last touched a whole convolution ago (long evicted from L2), so the cp.async above pays an
         // HBM round trip that the ~1.4 us of MMAs per tile only partly cover: ask L2 for the NEXT tile's rows now.
         if (p.res_prefetch) {
           const int tn = t + (int)gridDim.x;
           if (tn < p.tiles_per_group) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int q0n = tn * TILE_P + half * BLOCK_M + lg * 32;
-              const int bytes = min(32, max(0, p.group_positions - q0n)) * ROWB;
-              const uint8_t* src = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0n * N);
-              for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
-            }
+            const int q0n = tn * TILE_P + hs * BLOCK_M + lg * 32;
+            const int bytes = min(32, max(0, p.group_positions - q0n)) * ROWB;
+            const uint8_t* srcn = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0n * N);
+            for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcn + o));
           }
         }
       }
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
+      if (has_res) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + hs * N);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int buf = (BUFS == 2) ? half : 0;
-        uint8_t* my_row = stg_warp + (size_t)buf * (32u * ROWB) + (size_t)lane * ROWB;
-        if (has_res) {
-          if (BUFS == 1 && half == 1) fetch_residual(1, 0);
-          if (BUFS == 2 && half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
-          else asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * N);
-#pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 64) {
-          uint32_t a[2][32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a[0]);
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 32), a[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + h * 32);
-            const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c0 + h * 32);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const int j = (c0 >> 3) + h * 4 + v;   // logical 16-byte piece of the row
-              uint4* slot = reinterpret_cast<uint4*>(my_row + (((j & ~7) | ((j ^ lane) & 7)) * 16));
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
-              if (interior[half]) {
-                const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
-                float f[8];
-                f[0] = fmaf(__uint_as_float(a[h][v * 8 + 0]), s0.x, b0.x);
-                f[1] = fmaf(__uint_as_float(a[h][v * 8 + 1]), s0.y, b0.y);
-                f[2] = fmaf(__uint_as_float(a[h][v * 8 + 2]), s0.z, b0.z);
-                f[3] = fmaf(__uint_as_float(a[h][v * 8 + 3]), s0.w, b0.w);
-                f[4] = fmaf(__uint_as_float(a[h][v * 8 + 4]), s1.x, b1.x);
-                f[5] = fmaf(__uint_as_float(a[h][v * 8 + 5]), s1.y, b1.y);
-                f[6] = fmaf(__uint_as_float(a[h][v * 8 + 6]), s1.z, b1.z);
-                f[7] = fmaf(__uint_as_float(a[h][v * 8 + 7]), s1.w, b1.w);
-                if (has_res) {
-                  const uint4 rr = *slot;
-                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                  for (int jj = 0; jj < 4; ++jj) {
-                    float2 rf = __bfloat1622float2(r2[jj]);
-                    f[2 * jj] += rf.x;
-                    f[2 * jj + 1] += rf.y;
-                  }
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
-                }
-                o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
-              }
-              *slot = o;
-            }
-          }
-        }
-        if (half == 1) {
-          // both halves of this accumulator are in registers/smem now: hand it back before the stores
+      for (int c0 = 0; c0 < N; c0 += 64) {
+        uint32_t a[2][32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, a[0]);
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 32), a[1]);
+        tmem_ld_wait();
+        if (c0 + 64 >= N) {
+          // this warp's part of the accumulator is in registers now: hand it back before the math and the stores
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        } else {
-          __syncwarp();
         }
-        // coalesced write-out of the warp's 32 x N block
-        uint8_t* dst = reinterpret_cast<uint8_t*>(p.y + off0[half]);
-        const uint8_t* blk = stg_warp + (size_t)buf * (32u * ROWB);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int m = i * 32 + lane, row = m / NV, j = m - row * NV;
-          if (row < rows_valid[half])
-            *reinterpret_cast<uint4*>(dst + (size_t)m * 16) =
-                *reinterpret_cast<const uint4*>(blk + (size_t)row * ROWB + (((j & ~7) | ((j ^ row) & 7)) * 16));
+        for (int h = 0; h < 2; ++h) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + h * 32);
+          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c0 + h * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int j = (c0 >> 3) + h * 4 + v;   // logical 16-byte piece of the row
+            uint4* slot = reinterpret_cast<uint4*>(my_row + (((j & ~7) | ((j ^ lane) & 7)) * 16));
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
+            if (interior) {
+              const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+              float f[8];
+              f[0] = fmaf(__uint_as_float(a[h][v * 8 + 0]), s0.x, b0.x);
+              f[1] = fmaf(__uint_as_float(a[h][v * 8 + 1]), s0.y, b0.y);
+              f[2] = fmaf(__uint_as_float(a[h][v * 8 + 2]), s0.z, b0.z);
+              f[3] = fmaf(__uint_as_float(a[h][v * 8 + 3]), s0.w, b0.w);
+              f[4] = fmaf(__uint_as_float(a[h][v * 8 + 4]), s1.x, b1.x);
+              f[5] = fmaf(__uint_as_float(a[h][v * 8 + 5]), s1.y, b1.y);
+              f[6] = fmaf(__uint_as_float(a[h][v * 8 + 6]), s1.z, b1.z);
+              f[7] = fmaf(__uint_as_float(a[h][v * 8 + 7]), s1.w, b1.w);
+              if (has_res) {
+                const uint4 rr = *slot;
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  float2 rf = __bfloat1622float2(r2[jj]);
+                  f[2 * jj] += rf.x;
+                  f[2 * jj + 1] += rf.y;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+              }
+              o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+            }
+            *slot = o;
+          }
         }
-        __syncwarp();   // staging rows may be overwritten (next half / next tile's residual)
       }
+      __syncwarp();
+      // coalesced write-out of the warp's 32 x N block
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p.y + off0);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int m = i * 32 + lane, row = m / NV, j = m - row * NV;
+        if (row < rows_valid)
+          *reinterpret_cast<uint4*>(dst + (size_t)m * 16) =
+              *reinterpret_cast<const uint4*>(stg_warp + (size_t)row * ROWB + (((j & ~7) | ((j ^ row) & 7)) * 16));
+      }
+      __syncwarp();   // staging rows are overwritten by the next tile's residual
     }
   }
 
@@ -704,7 +685,7 @@ int amoe_conv_flat_init(amoe_ctx* ctx) {
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
+                                       flat::SMEM_BUDGET_128 + flat::STG_BYTES_128 + 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kw3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET - flat::KW3_STATIC + flat::STG_BYTES + 1024));
   return 0;
@@ -750,18 +731,20 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   const int a_stage = p.rows_pad * 128;
   const int w_tile = Cout * 128;
   const int w_all = p.chunks * 9 * w_tile;
-  p.w_resident = (w_all <= W_RESIDENT_MAX && SMEM_BUDGET - w_all >= 2 * a_stage) ? 1 : 0;
+  const int budget = Cout == 128 ? SMEM_BUDGET_128 : SMEM_BUDGET;     // operand stages; the staging rows come on top
+  const int stg_bytes = Cout == 128 ? STG_BYTES_128 : STG_BYTES;
+  p.w_resident = (w_all <= W_RESIDENT_MAX && budget - w_all >= 2 * a_stage) ? 1 : 0;
   int w_bytes;
   if (p.w_resident) {
     p.w_stages = 0;
     w_bytes = w_all;
   } else {
-    p.w_stages = std::min(MAX_W_STAGES, std::max(2, (SMEM_BUDGET - 2 * a_stage) / w_tile));
+    p.w_stages = std::min(MAX_W_STAGES, std::max(2, (budget - 2 * a_stage) / w_tile));
     // keep at least 2 (preferably 3) activation stages
-    while (p.w_stages > 3 && SMEM_BUDGET - p.w_stages * w_tile < 3 * a_stage) --p.w_stages;
+    while (p.w_stages > 3 && budget - p.w_stages * w_tile < 3 * a_stage) --p.w_stages;
     w_bytes = p.w_stages * w_tile;
   }
-  p.a_stages = std::min(MAX_A_STAGES, (SMEM_BUDGET - (kw3 ? KW3_STATIC : 0) - w_bytes) / a_stage);
+  p.a_stages = std::min(MAX_A_STAGES, (budget - (kw3 ? KW3_STATIC : 0) - w_bytes) / a_stage);
   AMOE_REQUIRE(p.a_stages >= 1, "amoe_conv3x3_flat_fwd: shared memory budget exceeded");
   if (gp == 0) return 0;
 
@@ -788,7 +771,7 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   }
   const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
   p.stg_off = (uint32_t)(p.a_stages * a_stage + w_bytes);
-  const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + STG_BYTES + 1024;
+  const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + stg_bytes + 1024;
   if (kw3) {
     AMOE_REQUIRE(p.w_resident && p.a_stages >= 1, "amoe_conv3x3_flat_fwd: kw-fused kernel needs resident weights");
     Kw3Params kp;
