@@ -51,16 +51,27 @@ def test_vehicle_state_matches_oracle(model, speed_seq, controls):
 
 
 def test_gate_param_layout_size(model):
-    """flat buffer length == what csrc/gate.cu derives from the dims (4-float aligned tensors)."""
+    """flat buffer length == what csrc/gate.cu derives from the dims: every tensor starts on an 8-element
+    boundary, so it is 32-byte aligned in fp32 and 16-byte aligned in the bf16 copy the tensor-core variant reads."""
+    from automoe_b200 import _ops
     from automoe_b200.models._gatepack import gate_param_tensors
     n_ch = [14, 19, 3]
     ts = gate_param_tensors(model.context_extractor, list(model.expert_extractors.extractors), model.gating_network,
                             n_ch, 64, 128)
-    al4 = lambda n: (n + 3) & ~3
-    total = sum(al4(t.numel()) for t in ts)
+    al8 = lambda n: (n + 7) & ~7
+    total = sum(al8(t.numel()) for t in ts)
     raw = sum(t.numel() for t in ts)
     assert raw == 2_400 + 415_488 + 602_115  # context + extractors + gating (SURVEY.md §2.2)
-    assert total >= raw and total - raw < 4 * len(ts)
+    assert total >= raw and total - raw < 8 * len(ts)
+    flat = _ops.flat_params(ts, "cpu")
+    assert flat.numel() == total and flat.dtype == torch.float32
+    off = 0
+    for t in ts:                                      # tensors sit at their aligned offsets, padding is zero
+        assert off % 8 == 0
+        assert torch.equal(flat[off:off + t.numel()], t.detach().float().reshape(-1))
+        assert (flat[off + t.numel():off + al8(t.numel())] == 0).all()
+        off += al8(t.numel())
+    assert _ops.mlp_tc(torch.bfloat16) and not _ops.mlp_tc(torch.float32)   # fp32 mode never takes the TF32 kernels
 
 
 def test_train_mode_is_rejected(model):
