@@ -1,28 +1,33 @@
 #!/usr/bin/env python
 """bench.py — AutoMoE batched forward, frames/s (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode infer|train_gating|train_detection]
     torchrun --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one forward pass of the AutoMoE hot path (3 experts + gating + policy) over one
-batch of 256 synthetic 3x256x256 frames per GPU (BASELINE.json configs[1]); weights are
-random-init (seeded), BatchNorm statistics perturbed.  Frames are independent, so N GPUs
-run N independent shards with no data-path collective (weak scaling).
+One "step" (--mode infer, the headline) = one forward pass of the AutoMoE hot path (3 experts + gating + policy)
+over one batch of 256 synthetic 3x256x256 frames per GPU (BASELINE.json configs[1]); weights are random-init
+(seeded), BatchNorm statistics perturbed.  Frames are independent, so N GPUs run N independent shards with no
+data-path collective (weak scaling).
 
-  value  : whole-job frames/s with inputs resident in HBM (device-timed, max over ranks)
-  e2e    : frames/s through the public module API with HOST (pinned) inputs: every step
-           uploads its fp32 frames + vehicle state and downloads waypoints/speed/weights
-  roofline: tensor bound; achieved = algorithmic conv FLOPs of the tcgen05 conv launches /
-           their CUDA-event time, measured live after the timed region
-  cpu_baseline / --impl reference: the oracle port of the reference (pure torch CPU fp32,
-           all host threads) on a bounded sample of the same workload.
+  value    : whole-job frames/s with inputs resident in HBM (device-timed, max over ranks), measured AFTER a
+             >= 3 s untimed pre-heat of the same graph replays, clocks/power sampled through NVML during the timed steps
+  e2e      : frames/s through the public module API with HOST (pinned) inputs: every step uploads its camera
+             frames as uint8 HWC (what inference/run_automoe.py receives from the camera; normalisation and
+             layout staging run on the device) + vehicle state and downloads waypoints/speed/expert weights
+  roofline : tensor bound; achieved = algorithmic conv FLOPs of the tcgen05 conv launches / their CUDA-event
+             time, measured live after the timed region; per-kernel split in roofline.kernels; HBM legs
+             (x32 logit writer, gate kernel at B=256 and B=65536, matcher cost matrix) beside it
+  gpu_reference : the reference forward (oracle port: stock torch ops = cuDNN/cuBLAS) on the same GPU, bf16
+             autocast, channels_last, cudnn.benchmark - the "stock library on the same box" row of SURVEY 8(d)
+  cpu_baseline / --impl reference: the oracle port of the reference (pure torch CPU fp32, all host threads) on a
+             bounded sample of the same workload; B=1 latency and B=64 throughput reported beside it.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
+import statistics
 import sys
 import threading
 import time
@@ -37,19 +42,25 @@ GFLOP_PER_FRAME = 15.203  # SURVEY.md §8 / BASELINE.md §3 (2*MAC over conv+lin
 METRIC = "automoe_forward_frames_per_sec"
 UNIT = "frames/s"
 WORKLOAD = "AutoMoE batched inference bf16, batch=256 synthetic 3x256x256 frames per GPU (BASELINE.json configs[1])"
+PREHEAT_S = 3.0
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train_gating", "train_detection"])
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (infer 256, train_gating 32, train_detection 64)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames per step of the CPU baseline sample")
+    ap.add_argument("--preheat", type=float, default=PREHEAT_S, help="seconds of untimed replays before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the HBM legs (gate / cost matrix / logit writer)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying AutoMoE.capture()")
+    ap.add_argument("--det-hw", default="720x1280", help="train_detection image size HxW")
     return ap.parse_args()
 
 
@@ -99,74 +110,114 @@ def randomize_norm_stats(model, seed=0):
                 m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
 
 
-def host_batch(B, seed):
+def host_batch(B, seed, H=256, W=256):
     g = torch.Generator().manual_seed(seed)
     return {
-        "image": torch.randn((B, 3, 256, 256), generator=g),
+        "image": torch.randn((B, 3, H, W), generator=g),
         "speed": torch.rand((B, 1), generator=g) * 30.0,
         "steering": torch.zeros(B, 1), "throttle": torch.zeros(B, 1), "brake": torch.zeros(B, 1),
     }
 
 
+def host_batch_u8(B, seed, H=256, W=256):
+    """Camera bytes: uint8 HWC RGB frames (what inference/run_automoe.py:95-97 hands to model_infer)."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "image": torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8),
+        "speed": torch.rand((B, 1), generator=g) * 30.0,
+        "steering": torch.zeros(B, 1), "throttle": torch.zeros(B, 1), "brake": torch.zeros(B, 1),
+    }
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this rank (and the pinned host buffers it first-touches) on the CPUs local to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"bound": True, "cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:  # containers with a restricted cpuset, no NVML
+        return {"bound": False, "why": str(e)[:80]}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled through NVML every ~5 ms in a thread; `mark()` brackets the
+    timed region so the reported median is taken from samples inside it."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread, self.h = index, [], False, None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:
+            self.h, self.err = None, str(e)[:80]
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        used = inside if len(inside) >= 3 else self.samples[-8:]
+        sm = sorted(s[1] for s in used)
+        reasons = set()
+        for s in used:
+            for n, bit in self.REASONS.items():
+                if s[3] & bit:
                     reasons.add(n)
-        sm.sort()
-        # median over the upper half = samples taken under load
-        load = sm[len(sm) // 2:] if sm else []
-        med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_median": statistics.median(s[2] for s in used) if used else None,
+                "power_w_max": max((s[2] for s in used), default=None), "reasons": sorted(reasons),
+                "samples_in_timed_region": len(inside), "samples": len(self.samples), "source": "nvml, 4 ms period"}
+
+
+# ------------------------------------------------------------------ CPU / reference arms
+def _oracle_setup():
+    from oracle import automoe_oracle as O
+    from oracle import synth
+    from automoe_b200.models.automoe import create_automoe_model
+    cfg = model_config()
+    template = create_automoe_model(cfg, "cpu").state_dict()
+    return O, synth.synth_state_dict(template, 0), cfg
 
 
 def cpu_reference_throughput(sample, steps, warmup):
     """The oracle port of the reference forward on the host cores (fp32, all threads)."""
-    from oracle import automoe_oracle as O
-    from oracle import synth
-    from automoe_b200.models.automoe import create_automoe_model
+    O, sd, cfg = _oracle_setup()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = model_config()
-    template = create_automoe_model(cfg, "cpu").state_dict()
-    sd = synth.synth_state_dict(template, 0)
     batch = host_batch(sample, 1)
     times = []
     with torch.no_grad():
@@ -180,10 +231,60 @@ def cpu_reference_throughput(sample, steps, warmup):
     return sample * len(times) / total, cores, total / len(times)
 
 
+def cpu_reference_points():
+    """B=1 latency (median of 5 after 2 warm-ups) and B=64 throughput (median of 3 after 1)."""
+    O, sd, cfg = _oracle_setup()
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {}
+    with torch.no_grad():
+        for B, warm, reps in ((1, 2, 5), (64, 1, 3)):
+            batch = host_batch(B, 1)
+            ts = []
+            for i in range(warm + reps):
+                t0 = time.perf_counter()
+                O.automoe_forward(sd, batch, cfg)
+                if i >= warm:
+                    ts.append(time.perf_counter() - t0)
+            med = statistics.median(ts)
+            out[f"b{B}"] = {"latency_ms": med * 1e3, "frames_per_s": B / med, "runs": reps}
+    return out
+
+
+def gpu_reference(dev, B, steps=5, warmup=3):
+    """The reference forward with stock libraries on this GPU: oracle port (F.conv2d / batch_norm / linear = cuDNN +
+    cuBLAS) under bf16 autocast, channels_last input and filters, cudnn.benchmark=True."""
+    O, sd, cfg = _oracle_setup()
+    torch.backends.cudnn.benchmark = True
+    sdd = {}
+    for k, v in sd.items():
+        v = v.to(dev)
+        sdd[k] = v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
+    batch = {k: v.to(dev) for k, v in host_batch(B, 1).items()}
+    batch["image"] = batch["image"].contiguous(memory_format=torch.channels_last)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(warmup):
+            O.automoe_forward(sdd, batch, cfg)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(steps):
+            O.automoe_forward(sdd, batch, cfg)
+        ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    torch.backends.cudnn.benchmark = False
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps,
+            "what": "reference forward (oracle port, stock torch ops: cuDNN/cuBLAS) eager on the same GPU, bf16 autocast, "
+                    "channels_last, cudnn.benchmark=True"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.mode != "infer":
+        from bench_train import run_reference_train
+        return run_reference_train(args)
     fps, cores, per_step = cpu_reference_throughput(args.cpu_sample, args.steps, args.warmup)
     sample = f"{args.cpu_sample} frames of 3x256x256 per step, fp32, oracle port of the reference forward (torch CPU ops)"
     line = {
@@ -198,15 +299,97 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ HBM legs
+def _time_launches(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) * 1e3 / reps     # us per launch
+
+
+def hbm_legs(model, dev, B, pk):
+    """The HBM-bound kernels north_star names, each timed alone: algorithmic bytes / CUDA-event time vs the measured copy peak."""
+    from automoe_b200 import _ops
+    from automoe_b200._cabi import check, ctx as _ctx, dtype_code, lib, ptr, stream_ptr
+    legs = {}
+    # (1) x32 full-resolution logit writer (SURVEY 8d: 22 classes x 65536 px x 2 B per frame; 19-class launch timed)
+    low = torch.randn((B, 8, 8, 19), device=dev, dtype=torch.float32)
+    up = torch.empty((B, 19, 256, 256), device=dev, dtype=torch.bfloat16)
+
+    def writer():
+        check(lib().amoe_upsample_bilinear_nchw_fwd(_ctx(dev), ptr(low), ptr(up), B, 8, 8, 19, 256, 256,
+                                                    dtype_code(torch.bfloat16), stream_ptr(dev)), "upsample")
+    us = _time_launches(writer, 10)     # back to back: 6.4 GB written, the 126 MB L2 cannot absorb it
+    wbytes = up.numel() * 2
+    legs["logit_writer"] = {"kernel": "upsample_intscale_nchw_kernel (x32 bilinear logit writer, 19 classes)", "bound": "hbm",
+                            "achieved": wbytes / us / 1e3, "peak": pk["hbm"], "unit": "GB/s", "frac": wbytes / us / 1e3 / pk["hbm"],
+                            "algorithmic_bytes_per_launch": wbytes, "us_per_launch": us,
+                            "how": "10 launches back to back on a preallocated output, CUDA events; the peak is the measured COPY "
+                                   "bandwidth (read+write mix) - a pure write stream can exceed it (HBM3e nominal ~7.7 TB/s)"}
+    del up, low
+    # (2) fused gate kernel (context + extractors + gating + softmax + combine) at the bench batch and at B=65536
+    gn = model.gating_network
+    n_ch = [14, 19, 3]
+    gflat, gflat16 = model._gate_params(dev, n_ch, bf16_copy=True)
+    for gb in (B, 65536):
+        state = torch.rand((gb, 4), device=dev)
+        pooled = torch.randn((gb, sum(n_ch)), device=dev)
+        f = lambda: _ops.gate(state, pooled, gflat, n_ch, model.context_extractor.context_dim, gn.hidden_dim, gn.temperature,
+                              params_bf16=gflat16)
+        us = _time_launches(f, 5)
+        alg = gb * (160 + 7448) + gflat.numel() * 2          # per frame in/out (SURVEY 8d) + one pass over the bf16 parameters
+        legs[f"gate_b{gb}"] = {"kernel": "gate_fused_kernel (tensor-core variant, bf16 parameters)", "bound": "hbm", "batch": gb,
+                               "achieved": alg / us / 1e3, "peak": pk["hbm"], "unit": "GB/s", "frac": alg / us / 1e3 / pk["hbm"],
+                               "algorithmic_bytes_per_launch": alg, "us_per_launch": us,
+                               "note": "includes the host-side output allocation of _ops.gate; at B=256 the launch moves ~3 MB "
+                                       "(<1 us at peak): latency-bound by construction (SURVEY 8d), the B=65536 point is the bandwidth one"}
+        del state, pooled
+    # (3) Hungarian cost matrix: B=64 images, Q=920 queries (BDD 720x1280 -> 23x40 cells), Ni ~ U{1..60} targets, C=10, D=4
+    g = torch.Generator().manual_seed(5)
+    for mb in (64, 4096):
+        Q, Cc, D = 920, 10, 4
+        n = torch.randint(1, 61, (mb,), generator=g)
+        Nmax = int(n.max())
+        logits = torch.randn((mb, Q, Cc), device=dev)
+        boxes = torch.rand((mb, Q, D), device=dev) * 0.5 + 0.1
+        tb = torch.rand((mb, Nmax, D), device=dev) * 0.5 + 0.1
+        tl = torch.randint(0, Cc, (mb, Nmax), device=dev)
+        nt = n.to(device=dev, dtype=torch.int32)
+        cost = torch.empty((mb, Q, Nmax), device=dev, dtype=torch.float32)
+
+        def costk():
+            check(lib().amoe_hungarian_cost_fwd(_ctx(dev), ptr(logits), ptr(boxes), ptr(tb), ptr(tl), ptr(nt), ptr(cost), mb, Q, Cc, D,
+                                                Nmax, 1.0, 5.0, 2.0, stream_ptr(dev)), "hungarian_cost")
+        us = _time_launches(costk, 10)
+        nsum = int(n.sum())
+        alg = mb * Q * (Cc + D) * 4 + nsum * (D + 1) * 4 + Q * nsum * 4       # SURVEY 8d: read Q(C+D)4 + Ni(D+1)4, write Q*Ni*4
+        legs[f"cost_matrix_b{mb}"] = {"kernel": "hungarian_cost_kernel", "bound": "hbm", "images": mb, "queries": Q, "targets_total": nsum,
+                                      "achieved": alg / us / 1e3, "peak": pk["hbm"], "unit": "GB/s", "frac": alg / us / 1e3 / pk["hbm"],
+                                      "algorithmic_bytes_per_launch": alg, "us_per_launch": us,
+                                      "note": "config 5 is B=64 (~10 MB, a few us: launch-latency-bound); B=4096 shows the kernel's bandwidth"}
+        del logits, boxes, tb, tl, cost
+    return legs
+
+
+# ------------------------------------------------------------------ the headline arm
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local)          # before CUDA/NCCL threads exist: they inherit the affinity
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    if args.mode != "infer":
+        from bench_train import run_train
+        return run_train(args, dev, world, rank, numa)
 
     from automoe_b200 import _cabi, _ops
     from automoe_b200.models.automoe import create_automoe_model
@@ -216,7 +399,7 @@ def run_b200(args):
     randomize_norm_stats(model)
     model = model.to(dev).eval()
     model.device = dev
-    B = args.batch
+    B = args.batch or 256
     hb = host_batch(B, 1 + rank)
     batch = {k: v.to(dev) for k, v in hb.items()}
 
@@ -244,20 +427,47 @@ def run_b200(args):
             g = graphs[id(b)] = model.capture(b, clone_inputs=False)
         return g()
 
+    # ---------------- the replayed graph must be the eager computation (checked before anything is timed) ----------------
+    small = ("waypoints", "speed", "speed_seq", "expert_weights", "gate_logits", "combined_features", "context_features")
+    ref_out = eager_step(batch)
+    ref_keep = {k: ref_out[k].clone() for k in small}
+    ref_seg_sum = ref_out["expert_outputs"][1].float().abs().sum().item()
+    out = step(batch)
+    torch.cuda.synchronize()
+    replay_checked = all(torch.equal(out[k], ref_keep[k]) for k in small) and \
+        out["expert_outputs"][1].float().abs().sum().item() == ref_seg_sum
+    if not replay_checked:
+        raise SystemExit("bench.py: the replayed CUDA graph does not reproduce the eager forward - refusing to time it")
+    finite = all(torch.isfinite(ref_keep[k]).all().item() for k in small)
+    if not finite:
+        raise SystemExit("bench.py: non-finite outputs")
+    del ref_out
+
     # ---------------- device-resident throughput (value) ----------------
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()       # nvidia-smi needs ~100 ms to start: launch it before the warm-up
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step(batch)
+    torch.cuda.synchronize()
+    # pre-heat: the same load, untimed, until clocks and power have settled (the sustained state the peak was measured in)
+    t_heat = time.perf_counter()
+    heat_steps = 0
+    while time.perf_counter() - t_heat < args.preheat:
+        for _ in range(10):
+            step(batch)
+        torch.cuda.synchronize()
+        heat_steps += 10
     barrier()
     n0 = _cabi.launch_count(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         out = step(batch)
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     launches = _cabi.launch_count(dev) - n0
     if use_graph:
         launches = graphs[id(batch)].launches_per_replay * args.steps
@@ -265,21 +475,14 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        # short timed regions end before nvidia-smi has produced samples: keep the same load running
-        # (untimed) until a handful of samples under load exist
-        t_wait = time.time()
-        while len(sampler.lines) < 8 and time.time() - t_wait < 3.0:
-            step(batch)
-            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms = ms.item()
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---------------- end-to-end through the module API with host buffers ----------------
+    # ---------------- end-to-end through the module API with host buffers (uint8 camera frames) ----------------
     e2e = None
     if not args.no_e2e:
-        pinned = [{k: v.pin_memory() for k, v in host_batch(B, 100 + rank * 7 + i).items()} for i in range(2)]
+        pinned = [{k: v.pin_memory() for k, v in host_batch_u8(B, 100 + rank * 7 + i).items()} for i in range(2)]
         h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
         res_host = [torch.empty((B, 10, 2)).pin_memory(), torch.empty((B, 1)).pin_memory(), torch.empty((B, 3)).pin_memory()]
         d2h = sum(t.numel() * t.element_size() for t in res_host)
@@ -294,7 +497,7 @@ def run_b200(args):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[s])
                 for k, v in pinned[s].items():
-                    slots[s][k].copy_(v, non_blocking=True)
+                    slots[s][k].copy_(v, non_blocking=True)     # one cudaMemcpyAsync per buffer
                 ready[s].record(copy_stream)
 
         def e2e_loop(n):
@@ -312,7 +515,7 @@ def run_b200(args):
                 res_host[2].copy_(o["expert_weights"], non_blocking=True)
                 freed[s].record(main)
 
-        e2e_loop(2)
+        e2e_loop(4)
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -329,16 +532,23 @@ def run_b200(args):
         slots[0]["image"].copy_(pinned[0]["image"], non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
-        h2d_gbs = pinned[0]["image"].numel() * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
+        h2d_gbs = pinned[0]["image"].numel() / (c0.elapsed_time(c1) / 1e3) / 1e9
         e2e = {"value": world * B * args.steps / (ems.item() / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems.item() / args.steps,
-               "h2d_gbs_measured": h2d_gbs}
+               "h2d_gbs_measured": h2d_gbs,
+               "input": "uint8 HWC camera frames [B,256,256,3] in pinned host memory (the frame inference/run_automoe.py gets from "
+                        "the camera); ToTensor+Normalize+layout staging run on the device (amoe_stage_u8_hwc_fwd)",
+               "d2h_subset": "waypoints, speed, expert_weights - what the reference's control loop reads (run_automoe.py:253); the "
+                             "737 MB of full-resolution logits are produced every step and stay on the device",
+               "numa": numa}
+        del pinned, slots
 
-    # ---------------- roofline of the dominant kernel (tcgen05 conv), measured live ----------------
+    # ---------------- roofline of the dominant kernels (tcgen05 convs), measured live ----------------
     pk = peaks()
     roof = None
     _ops.PROFILE = []
-    for _ in range(2):
+    n_prof = 3
+    for _ in range(n_prof):
         eager_step(batch)                      # per-kernel events need the eager launches
     torch.cuda.synchronize()
     rec = _ops.PROFILE
@@ -347,56 +557,51 @@ def run_b200(args):
     for kind, flops, a, b in rec:
         t, f, n = agg.get(kind, (0.0, 0.0, 0))
         agg[kind] = (t + a.elapsed_time(b), f + flops, n + 1)
-    if "conv_tc" in agg:
-        t, f, n = agg["conv_tc"]
+    tc_kinds = [k for k in agg if k != "conv2d_simt_kernel"]
+    if tc_kinds:
+        t = sum(agg[k][0] for k in tc_kinds)
+        f = sum(agg[k][1] for k in tc_kinds)
+        n = sum(agg[k][2] for k in tc_kinds)
         ach = f / (t / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all layers)",
+        kernels = {}
+        for k in sorted(tc_kinds):
+            tk, fk, nk = agg[k]
+            kernels[k] = {"launches_per_step": nk // n_prof, "gflop_per_step": fk / n_prof / 1e9, "us_per_step": tk / n_prof * 1e3,
+                          "tflops": fk / (tk / 1e3) / 1e12, "frac_of_sustained": fk / (tk / 1e3) / 1e12 / pk["tf_sustained"],
+                          "frac_of_burst": fk / (tk / 1e3) / 1e12 / pk["tf_burst"]}
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions: " + " + ".join(sorted(tc_kinds)),
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": conv_traffic(n // 2), "peak_source": f"{pk['src']} (MEASURED_PEAKS.json bf16_tflops_sustained)",
-                "achieved_per_launch_gflop": f / n / 1e9, "algorithmic_dram_bytes_per_launch": 43e6 * B / (n // 2),
-                "launches_per_step": n // 2, "ms_per_step": t / 2,
-                "share_of_step": (t / 2) / (ms / args.steps),
-                "whole_forward_frac": (value / world) * GFLOP_PER_FRAME * 1e9 / 1e12 / pk["tf_sustained"]}
-        if "conv_simt" in agg:
-            ts, fs, ns = agg["conv_simt"]
-            roof["simt_conv_ms_per_step"] = ts / 2
+                "frac_of_burst_peak": ach / pk["tf_burst"],
+                "traffic": conv_traffic(n // n_prof), "peak_source": f"{pk['src']} (MEASURED_PEAKS.json bf16_tflops_sustained; "
+                "the timed region follows a >= 3 s pre-heat, clocks/power in `clocks`)",
+                "achieved_per_launch_gflop": f / n / 1e9, "algorithmic_dram_bytes_per_launch": 43e6 * B / (n // n_prof),
+                "launches_per_step": n // n_prof, "ms_per_step": t / n_prof,
+                "share_of_step": (t / n_prof) / (ms / args.steps),
+                "whole_forward_frac": (value / world) * GFLOP_PER_FRAME * 1e9 / 1e12 / pk["tf_sustained"],
+                "whole_forward_frac_of_burst": (value / world) * GFLOP_PER_FRAME * 1e9 / 1e12 / pk["tf_burst"],
+                "kernels": kernels}
+        if "conv2d_simt_kernel" in agg:
+            ts, fs, ns = agg["conv2d_simt_kernel"]
+            roof["simt_conv_ms_per_step"] = ts / n_prof
             roof["simt_conv_tflops"] = fs / (ts / 1e3) / 1e12
+    if roof is not None and not args.no_legs and rank == 0:
+        legs = hbm_legs(model, dev, B, pk)
+        roof["hbm_kernel"] = legs.pop("logit_writer")
+        roof["gate"] = {k: v for k, v in legs.items() if k.startswith("gate_")}
+        roof["cost_matrix"] = {k: v for k, v in legs.items() if k.startswith("cost_matrix_")}
 
-    # ---------------- the HBM-bound kernel of the path: the x32 full-resolution logit writer, timed alone ----------------
-    # (22 classes x 65536 pixels x 2 B per frame; in the forward it runs on the side stream beside the
-    # gate / policy tail, so it is timed here on its own: algorithmic bytes written / CUDA-event time)
-    if roof is not None:
-        from automoe_b200._cabi import check, ctx as _ctx, dtype_code, lib, ptr, stream_ptr
-        low = torch.randn((B, 8, 8, 19), device=dev, dtype=torch.float32)
-        up = torch.empty((B, 19, 256, 256), device=dev, dtype=torch.bfloat16)      # written in place by every launch
-
-        def writer():
-            check(lib().amoe_upsample_bilinear_nchw_fwd(_ctx(dev), ptr(low), ptr(up), B, 8, 8, 19, 256, 256,
-                                                        dtype_code(torch.bfloat16), stream_ptr(dev)), "upsample")
-        for _ in range(3):
-            writer()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        reps = 10                              # back to back: 6.4 GB written, the 126 MB L2 cannot absorb it
-        ev[0].record()
-        for _ in range(reps):
-            writer()
-        ev[1].record()
-        torch.cuda.synchronize()
-        wbytes = up.numel() * 2
-        gbs = wbytes * reps / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9
-        roof["hbm_kernel"] = {"kernel": "upsample_intscale_nchw_kernel (x32 bilinear logit writer, 19 classes)", "bound": "hbm",
-                              "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                              "algorithmic_bytes_per_launch": wbytes, "us_per_launch": ev[0].elapsed_time(ev[1]) * 1e3 / reps,
-                              "how": "10 launches back to back on a preallocated output, CUDA events; the peak is the measured COPY "
-                                     "bandwidth (read+write mix) - a pure write stream can exceed it (HBM3e nominal ~7.7 TB/s)"}
-        del up, low
-
-    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
-    cpu = None
+    # ---------------- stock libraries on the same GPU, CPU baseline (rank 0, N=1 only) ----------------
+    gref = cpu = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        del graphs
+        torch.cuda.empty_cache()
+        gref = gpu_reference(dev, B)
+        gref["ours_over_gpu_reference"] = value / gref["value"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, cores, per = cpu_reference_throughput(args.cpu_sample, 3, 1)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"3 steps of {args.cpu_sample} frames 3x256x256, fp32 oracle port, {per:.2f} s/step"}
+        cpu.update(cpu_reference_points())
 
     if rank == 0:
         line = {
@@ -407,8 +612,9 @@ def run_b200(args):
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2_policy": "inputs (201 MB fp32 frames per step) and activations exceed the 126 MB L2",
                        "launch_mode": "cuda_graph replay of AutoMoE.capture()" if use_graph else "eager (one ctypes launch per kernel)",
+                       "preheat_s": args.preheat, "preheat_steps": heat_steps, "replay_equals_eager_checked": replay_checked,
                        "l2_chunk_images": _ops.l2_chunk_images(), "side_stream_outputs": _ops.overlap_outputs()},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gref,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -62,6 +62,25 @@ int amoe_image_nchw_to_nhwc_padded(amoe_ctx*, const float* src, void* dst, int B
 int amoe_image_nchw_to_nhwc_padded_v(amoe_ctx*, const float* src, void* dst, int B, int C, int H,
                                      int W, int Cp, int left, int Wpad, int top, int Hpad,
                                      int dst_dtype, float pad_channel_value, void* stream);
+/* ---- input staging from camera bytes ------------------- */
+/* uint8 HWC RGB frames [B,H,W,3] -> normalised (u/255 - mean)/std, the transform of
+ * inference/run_automoe.py:25-31 (ToTensor + Normalize; IEEE fp32 op order, bit-exact), written as the
+ * physically padded bf16 NHWC4 frame [B,Hpad,Wpad,4] that amoe_stem_fwd / amoe_stem_pool_fwd read (same
+ * geometry arguments as amoe_image_nchw_to_nhwc_padded_v).  mean/std: HOST arrays of 3 floats. */
+int amoe_stage_u8_hwc_fwd(amoe_ctx*, const void* src_u8, void* dst, int B, int H, int W, int left,
+                          int Wpad, int top, int Hpad, const float* mean3_host,
+                          const float* std3_host, float pad_channel_value, void* stream);
+/* Same arithmetic into the reference's own tensor: [B,3,H,W] fp32 NCHW (fp32 mode / non-tensor-core stems). */
+int amoe_normalize_u8_hwc_to_nchw_fwd(amoe_ctx*, const void* src_u8, float* dst, int B, int H, int W,
+                                      const float* mean3_host, const float* std3_host, void* stream);
+/* One separable pass of Pillow's 8-bit bilinear/antialias resize (what T.Resize does on the PIL image at
+ * run_automoe.py:27; Pillow src/libImaging/Resample.c ImagingResampleHorizontal_8bpc / Vertical_8bpc):
+ * src viewed as [outer][in_size][inner] u8 -> dst [outer][out_size][inner] u8;
+ * bounds: DEVICE int[2*out_size] (first input index, tap count), coeffs: DEVICE int[out_size*ksize]
+ * fixed-point weights (22 fractional bits) prepared as precompute_coeffs + normalize_coeffs_8bpc do. */
+int amoe_resample_u8_fwd(amoe_ctx*, const void* src_u8, void* dst_u8, const int* bounds,
+                         const int* coeffs, int ksize, int64_t outer, int in_size, int out_size,
+                         int inner, void* stream);
 /* All first-layer convolutions of the frame (Cin=3, stride 2: the ResNet stems of the experts and
  * the policy's conv1) as one tensor-core GEMM over the raw image rows (csrc/stem_tc.cu).
  *   x_pad: [B,H+6,Wpad,4] bf16 from amoe_image_nchw_to_nhwc_padded(left=4, top=3), Wpad >= W+6
@@ -186,7 +205,8 @@ int amoe_mean_hw_nchw_fwd(amoe_ctx*, const void* x, float* out, int B, int C, in
  *   outputs (all fp32): context [B,ctx_dim], features [E][B,256],
  *            processed [E][B,256], gate_logits [B,E], weights [B,E],
  *            combined [B,256] (after output_projection)
- * mode bits: 1 = context-only path of get_expert_weights (zeros for experts, weights only);
+ * mode bits: 32 = sigmoid gate (use_softmax=False, gating_network.py:159-160; temperature unused);
+ *            1 = context-only path of get_expert_weights (zeros for experts, weights only);
  *   2 = `state` holds an encoded context [B,ctx_dim] (context extractor skipped);
  *   4 = `pooled` holds expert features [E][B,256] (extractors skipped);
  *   8 = stop after the context extractor; 16 = stop after the expert extractors.
@@ -279,12 +299,23 @@ int amoe_layernorm_bwd(amoe_ctx*, const float* dy, const float* x, const float* 
 int amoe_gate_combine_fwd(amoe_ctx*, const float* logits, const float* processed,
                           int64_t expert_stride, int ld_p, float temperature, float* weights,
                           float* combined, int B, int E, int P, void* stream);
+/* use_softmax = 0: weights = sigmoid(logits) / (sum_e sigmoid(logits) + 1e-8), temperature unused
+ * (gating_network.py:159-160). */
+int amoe_gate_combine_fwd_ex(amoe_ctx*, const float* logits, const float* processed,
+                             int64_t expert_stride, int ld_p, float temperature, int use_softmax,
+                             float* weights, float* combined, int B, int E, int P, void* stream);
 /* dcombined [B,P] and/or dweights [B,E] (direct gradient on the gate weights: load-balancing and
  * entropy losses) -> dlogits [B,E], dprocessed_e = dprocessed + e*dexpert_stride ([B,P] each). */
 int amoe_gate_combine_bwd(amoe_ctx*, const float* dcombined, const float* dweights,
                           const float* weights, const float* processed, int64_t expert_stride,
                           int ld_p, float temperature, float* dlogits, float* dprocessed,
                           int64_t dexpert_stride, int B, int E, int P, void* stream);
+/* logits_if_sigmoid != NULL selects the backward of the sigmoid gate (needs the forward's logits). */
+int amoe_gate_combine_bwd_ex(amoe_ctx*, const float* dcombined, const float* dweights,
+                             const float* weights, const float* processed, int64_t expert_stride,
+                             int ld_p, float temperature, const float* logits_if_sigmoid,
+                             float* dlogits, float* dprocessed, int64_t dexpert_stride, int B, int E,
+                             int P, void* stream);
 /* compute_gating_losses (training/train_gating_network.py:21-74): every loss term and the gradient of
  * total_loss w.r.t. the predictions, one launch.
  *   waypoints/tgt_waypoints [B,H,2]; speed [B,*] rows speed_ld apart, tgt_speed rows tgt_speed_ld apart

@@ -123,9 +123,10 @@ def context_extractor(state, sd, p="context_extractor"):
     return _ln(v, sd, p + ".encoder.4")
 
 
-def gating_network(features: List[torch.Tensor], context, sd, p="gating_network", temperature=1.0, context_only=False):
-    """GatingNetwork.forward (gating_network.py:122-175), eval mode, softmax gate, top_k=0
-    (the only configuration reachable through AutoMoE, automoe.py:83-91);
+def gating_network(features: List[torch.Tensor], context, sd, p="gating_network", temperature=1.0, context_only=False,
+                   use_softmax=True):
+    """GatingNetwork.forward (gating_network.py:122-175), eval mode, top_k=0 (all that is reachable through
+    AutoMoE, automoe.py:83-91); softmax gate or, with use_softmax=False, the sigmoid gate of :159-160;
     context_only=True restates get_expert_weights (gating_network.py:177-199)."""
     c = F.relu(_linear(context, sd, p + ".context_encoder.context_encoder.0"))
     c = F.relu(_linear(c, sd, p + ".context_encoder.context_encoder.3"))
@@ -142,7 +143,11 @@ def gating_network(features: List[torch.Tensor], context, sd, p="gating_network"
     gate_in = torch.cat([c] + processed, dim=1)
     g = F.relu(_linear(gate_in, sd, p + ".gate_network.0"))
     logits = _linear(g, sd, p + ".gate_network.3")
-    weights = F.softmax(logits / temperature, dim=1)
+    if use_softmax:
+        weights = F.softmax(logits / temperature, dim=1)
+    else:
+        weights = torch.sigmoid(logits)
+        weights = weights / (weights.sum(dim=1, keepdim=True) + 1e-8)
     combined = torch.zeros_like(processed[0])
     for i in range(E):
         combined = combined + weights[:, i:i + 1] * processed[i]
@@ -174,7 +179,8 @@ def automoe_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor],
     expert_outputs = [run_expert(image, sd, f"experts.{i}", c) for i, c in enumerate(config["experts"])]
     feats = [extractor(o, sd, f"expert_extractors.extractors.{i}", c)
              for i, (o, c) in enumerate(zip(expert_outputs, config["experts"]))]
-    g = gating_network(feats, ctx, sd, temperature=config["gating"].get("temperature", 1.0))
+    g = gating_network(feats, ctx, sd, temperature=config["gating"].get("temperature", 1.0),
+                       use_softmax=config["gating"].get("use_softmax", True))
     horizon = config["policy"].get("num_waypoints", 10)
     pol = policy_head(image, g["combined_output"], sd, horizon=horizon)
     speed_seq = pol["speed"]
@@ -198,4 +204,4 @@ def get_expert_weights(sd, batch, config):
     ctx = context_extractor(vehicle_state(batch), sd)
     E = len(config["experts"])
     return gating_network([None] * E, ctx, sd, temperature=config["gating"].get("temperature", 1.0),
-                          context_only=True)["expert_weights"]
+                          context_only=True, use_softmax=config["gating"].get("use_softmax", True))["expert_weights"]

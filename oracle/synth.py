@@ -85,3 +85,15 @@ def synth_matcher_case(B: int, Q: int, C: int, D: int, n_min: int, n_max: int, s
         tl = torch.randint(0, C, (n,), generator=g)
         targets.append({"boxes": tb, "labels": tl})
     return {"pred_logits": logits, "pred_boxes": boxes}, targets
+
+
+def synth_u8_frame(h, w, seed):
+    """Seeded uint8 HWC frame: smooth gradient + noise + saturated patches (exercises clipping and flat areas)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255.0 / max(w - 1, 1)), (yy * 255.0 / max(h - 1, 1)), ((xx + yy) % 256)], -1)
+    img = base + rng.randint(-60, 61, size=(h, w, 3))
+    img[: h // 4, : w // 4] = 255
+    img[-(h // 5):, -(w // 5):] = 0
+    return np.clip(img, 0, 255).astype(np.uint8)

@@ -35,6 +35,9 @@ SIGNATURES = {
     "amoe_image_nchw_to_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_image_nchw_to_nhwc_padded": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_image_nchw_to_nhwc_padded_v": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "amoe_stage_u8_hwc_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _F, _P]),
+    "amoe_normalize_u8_hwc_to_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P]),
+    "amoe_resample_u8_fwd": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P]),
     "amoe_stem_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, C.POINTER(_P), C.POINTER(_I), _P]),
     "amoe_stem_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_P), C.POINTER(_I), _P]),
     "amoe_conv2d_rowwin_fwd": (_I, [_P] * 6 + [_I] * 13 + [_P]),
@@ -62,6 +65,8 @@ SIGNATURES = {
     "amoe_layernorm_fwd": (_I, [_P] * 7 + [_I, _I, _F, _P]),
     "amoe_layernorm_bwd": (_I, [_P] * 9 + [_I, _I, _P]),
     "amoe_gate_combine_fwd": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _I, _I, _I, _P]),
+    "amoe_gate_combine_fwd_ex": (_I, [_P, _P, _P, _L, _I, _F, _I, _P, _P, _I, _I, _I, _P]),
+    "amoe_gate_combine_bwd_ex": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P, _P, _P, _L, _I, _I, _I, _P]),
     "amoe_gate_combine_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _P, _P, _L, _I, _I, _I, _P]),
     "amoe_gating_loss_fwd_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, C.POINTER(_F), _I, _I, _P, _P, _P, _P, _P]),
     "amoe_sq_norm": (_I, [_P, _P, _L, _P, _I, _P, _P]),

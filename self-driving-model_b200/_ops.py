@@ -16,7 +16,7 @@ from . import _cabi
 from ._cabi import check, ctx, dtype_code, lib, ptr, stream_ptr
 
 
-# bench.py sets PROFILE to a list to get (kind, flops, start_event, end_event) per conv launch
+# bench.py sets PROFILE to a list to get (kernel name, flops, start_event, end_event) per conv launch
 PROFILE = None
 
 
@@ -210,7 +210,7 @@ def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: in
                                    stream_ptr(dev)), "stem_pool_fwd")
     if prof is not None:
         ev1.record()
-        prof.append(("conv_tc", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
+        prof.append(("stem_pool_kernel", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
     return pooled, rest
 
 
@@ -233,19 +233,23 @@ def _stem_launch(ps: PackedStem, x_pad, B, H, W, outs):
           "stem_fwd")
     if prof is not None:
         ev1.record()
-        prof.append(("conv_tc", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
+        prof.append(("stem_kernel", 2.0 * ps.true_macs_per_px * B * (H // 2) * (W // 2), ev0, ev1))
     return outs
 
 
-def stem_mode(dtype: torch.dtype) -> str:
+def stem_mode(dtype: torch.dtype, H: Optional[int] = None, W: Optional[int] = None) -> str:
     """How the Cin=3 first-layer convolutions run: 'tc' (bf16 default: one GEMM over raw image rows,
-    stem_tc.cu), 'rowwin' (bf16: expanded row windows through conv_tc.cu) or 'simt' (CUDA cores; the only
-    choice in fp32 mode).  AMOE_STEM overrides the bf16 default (debug / A-B switch)."""
-    import os
+    stem_tc.cu; needs even H, W and W <= 256), 'rowwin' (bf16: expanded row windows through conv_tc.cu - picked
+    automatically for frames the 'tc' kernel does not take, e.g. BDD's native 720x1280) or 'simt' (CUDA cores;
+    the only choice in fp32 mode).  AMOE_STEM overrides the bf16 choice (debug / A-B switch)."""
     if dtype != torch.bfloat16:
         return "simt"
-    m = os.environ.get("AMOE_STEM", "tc")
-    return m if m in ("tc", "rowwin", "simt") else "tc"
+    m = os.environ.get("AMOE_STEM", "")
+    if m in ("tc", "rowwin", "simt"):
+        return m
+    if H is not None and W is not None and not stem_supported(H, W):
+        return "rowwin"
+    return "tc"
 
 
 def l2_chunk_images() -> int:
@@ -262,10 +266,6 @@ def overlap_outputs() -> bool:
     """Fork the full-resolution logit writers onto a side stream (AMOE_OVERLAP=0 keeps one stream)."""
     import os
     return os.environ.get("AMOE_OVERLAP", "1") != "0"
-
-
-def use_rowwin(dtype: torch.dtype) -> bool:
-    return stem_mode(dtype) == "rowwin"
 
 
 ROWWIN_LEFT = 4     # zero pixels stored left of every image row
@@ -346,7 +346,7 @@ def conv2d_rowwin(pc: PackedRowwin, x_pad: torch.Tensor, B: int, H: int, W: int)
                                        Ho, Wo, int(pc.relu), stream_ptr(x_pad.device)), "conv2d_rowwin_fwd")
     if prof is not None:
         ev1.record()
-        prof.append(("conv_tc", 2.0 * pc.true_k * pc.cout * pc.n_conv * B * Ho * Wo, ev0, ev1))
+        prof.append(("conv_tc_kernel", 2.0 * pc.true_k * pc.cout * pc.n_conv * B * Ho * Wo, ev0, ev1))
     return y
 
 
@@ -458,7 +458,7 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
         ev1.record()
         tc = dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H + 2 * in_pad, Wk + 2 * in_pad, pc.cin, pc.cout, pc.sh, pc.sw)
         macs = pc.meta.get("true_k", pc.kh * pc.kw * pc.cin) * pc.cout * pc.G * B * Ho * Wo
-        prof.append(("conv_tc" if tc else "conv_simt", 2.0 * macs, ev0, ev1))
+        prof.append(("conv_tc_kernel" if tc else "conv2d_simt_kernel", 2.0 * macs, ev0, ev1))
     return y
 
 
@@ -484,7 +484,7 @@ def conv3x3_flat(pc: PackedConv, x_pad: torch.Tensor, B: int, H: int, W: int,
           "conv3x3_flat_fwd")
     if prof is not None:
         ev1.record()
-        prof.append(("conv_tc", 2.0 * 9 * pc.cin * pc.cout * pc.G * B * H * W, ev0, ev1))
+        prof.append((f"conv3x3_flat_kernel<{pc.cout}>", 2.0 * 9 * pc.cin * pc.cout * pc.G * B * H * W, ev0, ev1))
     return y
 
 
@@ -613,3 +613,111 @@ def lsap_batched(cost_host: torch.Tensor, n_tgt_host: torch.Tensor, n_threads: i
         raise ValueError(lib().amoe_last_error().decode())
     check(rc, "lsap_batched_host")
     return rows, cols, nm
+
+
+# ---- input staging from camera bytes (csrc/stage_u8.cu; reference inference/run_automoe.py:25-31) ----
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def _f3(v):
+    a = torch.as_tensor(v, dtype=torch.float32).reshape(3)      # the fp32 rounding T.Normalize applies to mean/std
+    return (C.c_float * 3)(*[float(x) for x in a])
+
+
+def _check_u8_hwc(img: torch.Tensor):
+    if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[3] != 3:
+        raise ValueError(f"expected uint8 frames [B,H,W,3] (HWC RGB), got {img.dtype} {tuple(img.shape)}")
+    if not img.is_cuda:
+        raise RuntimeError("automoe_b200 has no CPU path: move the frames to a CUDA (sm_100a) device")
+
+
+def stage_u8_stem(img_u8: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 [B,H,W,3] -> the frame amoe_stem_fwd reads ([B,H+6,Wpad,4] bf16, normalised, 4th channel 1.0):
+    ToTensor + Normalize + stage_image_stem as one kernel."""
+    _check_u8_hwc(img_u8)
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, H + 6, stem_wpad(W), 4), device=img_u8.device, dtype=torch.bfloat16)
+    check(lib().amoe_stage_u8_hwc_fwd(ctx(img_u8.device), ptr(img_u8), ptr(out), B, H, W, STEM_LEFT, out.shape[2], STEM_TOP,
+                                      H + 6, _f3(mean), _f3(std), 1.0, stream_ptr(img_u8.device)), "stage_u8_hwc_fwd")
+    return out
+
+
+def normalize_u8_nchw(img_u8: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 [B,H,W,3] -> fp32 [B,3,H,W], bit-identical to T.ToTensor() + T.Normalize(mean, std)."""
+    _check_u8_hwc(img_u8)
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, 3, H, W), device=img_u8.device, dtype=torch.float32)
+    check(lib().amoe_normalize_u8_hwc_to_nchw_fwd(ctx(img_u8.device), ptr(img_u8), ptr(out), B, H, W, _f3(mean), _f3(std),
+                                                  stream_ptr(img_u8.device)), "normalize_u8_hwc_to_nchw_fwd")
+    return out
+
+
+_PIL_PRECISION_BITS = 32 - 8 - 2
+_resize_tables: dict = {}
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Fixed-point taps of Pillow's 8-bit bilinear resize along one axis (Pillow src/libImaging/Resample.c:
+    precompute_coeffs with the bilinear filter (support 1, widened by the scale when shrinking = antialias) and
+    normalize_coeffs_8bpc).  Returns (bounds int32 [out,2], coeffs int32 [out,ksize], ksize).  Python floats are
+    the C doubles of the original; int() truncates like the C cast."""
+    import math
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = torch.zeros((out_size, 2), dtype=torch.int32)
+    coeffs = torch.zeros((out_size, ksize), dtype=torch.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = []
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            k.append(1.0 - a if a < 1.0 else 0.0)
+        ww = 0.0                        # accumulated left to right in double, like the C loop
+        for w in k:
+            ww += w
+        for x in range(xmax):
+            v = k[x] / ww if ww != 0.0 else k[x]
+            coeffs[xx, x] = int(-0.5 + v * (1 << _PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PIL_PRECISION_BITS))
+        bounds[xx, 0], bounds[xx, 1] = xmin, xmax
+    return bounds, coeffs, ksize
+
+
+def resize_u8_bilinear(img_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """uint8 [B,H,W,3] -> uint8 [B,out_h,out_w,3]: Pillow's Image.resize(BILINEAR) (horizontal pass, then vertical pass,
+    8-bit rounding after each), the T.Resize of inference/run_automoe.py:27.  Same size returns the input (Pillow copies)."""
+    _check_u8_hwc(img_u8)
+    B, H, W, _ = img_u8.shape
+    if (H, W) == (out_h, out_w):
+        return img_u8
+    dev = img_u8.device
+    x = img_u8.contiguous()
+
+    def table(n_in, n_out):
+        key = (n_in, n_out, dev.index)
+        t = _resize_tables.get(key)
+        if t is None:
+            b, c, ks = pil_bilinear_coeffs(n_in, n_out)
+            t = _resize_tables[key] = (b.to(dev), c.to(dev), ks)
+        return t
+
+    if W != out_w:
+        b, c, ks = table(W, out_w)
+        y = torch.empty((B, H, out_w, 3), device=dev, dtype=torch.uint8)
+        check(lib().amoe_resample_u8_fwd(ctx(dev), ptr(x), ptr(y), ptr(b), ptr(c), ks, B * H, W, out_w, 3, stream_ptr(dev)),
+              "resample_u8_fwd(horizontal)")
+        x = y
+    if H != out_h:
+        b, c, ks = table(H, out_h)
+        y = torch.empty((B, out_h, out_w, 3), device=dev, dtype=torch.uint8)
+        check(lib().amoe_resample_u8_fwd(ctx(dev), ptr(x), ptr(y), ptr(b), ptr(c), ks, B, H, out_h, out_w * 3, stream_ptr(dev)),
+              "resample_u8_fwd(vertical)")
+        x = y
+    return x

@@ -47,6 +47,23 @@ void amoe_set_error(const char* fmt, ...);
     AMOE_CHECK_CUDA(cudaPeekAtLastError());                  \
   } while (0)
 
+// Every entry point that launches work runs on the context's device, whatever the calling thread's
+// current device is (a model on cuda:1 driven from a thread whose current device is 0), and restores it.
+struct amoe_device_scope {
+  int prev = -1;
+  explicit amoe_device_scope(const amoe_ctx* ctx) {
+    if (ctx == nullptr) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) prev = cur;
+  }
+  ~amoe_device_scope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  amoe_device_scope(const amoe_device_scope&) = delete;
+  amoe_device_scope& operator=(const amoe_device_scope&) = delete;
+};
+#define AMOE_ENTER(ctx) amoe_device_scope _amoe_dev_scope(ctx)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- dtype-generic scalar load/store (device) ----

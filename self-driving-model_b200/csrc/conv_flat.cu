@@ -681,6 +681,7 @@ static bool supported(int H, int W, int C, int N) {
 }  // namespace flat
 
 int amoe_conv_flat_init(amoe_ctx* ctx) {
+  AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
@@ -698,12 +699,14 @@ int amoe_conv3x3_flat_supported(int H, int W, int Cin, int Cout) { return flat::
 int amoe_conv3x3_flat_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias,
                           const void* residual, void* y, int G, int B, int H, int W, int Cin, int Cout, int relu,
                           void* stream) {
+  AMOE_ENTER(ctx);
   return amoe_conv3x3_flat_fwd_strided(ctx, x, w, scale, bias, residual, y, G, B, H, W, Cin, Cout, relu, 0, 0, stream);
 }
 
 int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias,
                                   const void* residual, void* y, int G, int B, int H, int W, int Cin, int Cout, int relu,
                                   int64_t y_group_images, int64_t res_group_images, void* stream) {
+  AMOE_ENTER(ctx);
   using namespace flat;
   AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv3x3_flat_fwd: NULL argument");
   AMOE_REQUIRE(flat::supported(H, W, Cin, Cout), "amoe_conv3x3_flat_fwd: unsupported shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);

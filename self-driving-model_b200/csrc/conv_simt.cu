@@ -115,6 +115,7 @@ int amoe_conv2d_simt(amoe_ctx* ctx, const void* x, const void* w, const float* s
                      const float* bias, const void* residual, void* y, int G, int x_shared, int B,
                      int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw, int ph, int pw,
                      int Ho, int Wo, int relu, int dtype, cudaStream_t st) {
+  AMOE_ENTER(ctx);
   ConvSimtParams p;
   p.x = x; p.w = w; p.scale = scale; p.bias = bias; p.residual = residual; p.y = y;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW;

@@ -285,6 +285,7 @@ static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
 }  // namespace tc
 
 int amoe_conv_tc_init(amoe_ctx* ctx) {
+  AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        tc::SMEM_BUDGET + 1024 + 16 * 1024));
@@ -407,6 +408,7 @@ int amoe_conv2d_rowwin_fwd(amoe_ctx* ctx, const void* x, const void* w, const fl
                            const float* bias, void* y, int B, int H, int Wpad, int Cp, int Cout,
                            int split_c, int KH, int stride_h, int stride_w, int pad_h, int Ho, int Wo,
                            int relu, void* stream) {
+  AMOE_ENTER(ctx);
   using namespace tc;
   AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv2d_rowwin_fwd: NULL argument");
   AMOE_REQUIRE(Cp > 0 && BLOCK_K % Cp == 0, "amoe_conv2d_rowwin_fwd: Cp=%d must divide %d", Cp, BLOCK_K);
@@ -439,6 +441,7 @@ int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* sc
                     int H, int W, int Cin, int Cout, int KH, int KW, int stride_h, int stride_w,
                     int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype, int impl, int in_pad, int out_pad,
                     void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && w && scale && bias && y, "amoe_conv2d_fwd: NULL argument");
   AMOE_REQUIRE(dtype == AMOE_F32 || dtype == AMOE_BF16, "amoe_conv2d_fwd: bad dtype %d", dtype);
   AMOE_REQUIRE(G >= 1 && B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 &&

@@ -26,6 +26,7 @@ constexpr int GATE_MODE_CTX_IN = 2;     // `state` holds an already-encoded cont
 constexpr int GATE_MODE_FEAT_IN = 4;    // `pooled` holds expert features [E][B,F] (extractors skipped)
 constexpr int GATE_MODE_STOP_CTX = 8;   // stop after the context extractor
 constexpr int GATE_MODE_STOP_FEAT = 16; // stop after the expert extractors
+constexpr int GATE_MODE_SIGMOID = 32;   // use_softmax=False: sigmoid(logits) / (sum + 1e-8), gating_network.py:159-160
 constexpr int EXT_HID = 512;     // expert_extractors.py:30,64,91
 
 struct GateDims {
@@ -224,16 +225,18 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
       int f = threadIdx.x;
       float* lg = s_w + f * GATE_MAX_E;
       float mx = -INFINITY;
+      const bool sig = d.mode & GATE_MODE_SIGMOID;
       for (int e = 0; e < d.E; ++e) {
         if (gate_logits && f0 + f < d.B) gate_logits[(int64_t)(f0 + f) * d.E + e] = lg[e];
-        lg[e] = lg[e] / d.temperature;
+        if (!sig) lg[e] = lg[e] / d.temperature;
         mx = fmaxf(mx, lg[e]);
       }
       float ssum = 0.f;
       for (int e = 0; e < d.E; ++e) {
-        lg[e] = expf(lg[e] - mx);
+        lg[e] = sig ? 1.f / (1.f + expf(-lg[e])) : expf(lg[e] - mx);
         ssum += lg[e];
       }
+      if (sig) ssum += 1e-8f;
       for (int e = 0; e < d.E; ++e) {
         lg[e] = lg[e] / ssum;
         if (weights && f0 + f < d.B) weights[(int64_t)(f0 + f) * d.E + e] = lg[e];
@@ -305,7 +308,7 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
     auto kern = gate_fused_kernel<MMA_FT, false, true>;
     AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char* e = getenv("AMOE_GATE_SPLIT");
-    d.split = (mode == 0 && hidden % 4 == 0 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
+    d.split = ((mode & ~GATE_MODE_SIGMOID) == 0 && hidden % 4 == 0 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
     if (d.split) {
       // the forward of AutoMoE: clusters of E+1 CTAs per 16 frames (expert chains and the context path in parallel)
       cudaLaunchConfig_t cfg = {};

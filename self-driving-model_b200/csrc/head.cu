@@ -284,6 +284,7 @@ extern "C" {
 int amoe_head1x1_pool_fwd(amoe_ctx* ctx, const void* x, const float* w, const float* b, float* low,
                           float* pooled, int pooled_ld, int B, int HW, int Cin, int N, int x_dtype,
                           void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && w && b && low && pooled, "amoe_head1x1_pool_fwd: NULL argument");
   AMOE_REQUIRE(N >= 1 && N <= 256, "amoe_head1x1_pool_fwd: N=%d out of range [1,256]", N);
   size_t smem = ((size_t)N * ((Cin + 3) & ~3) + (size_t)Cin * HEAD_PX + (size_t)HEAD_PX * N) * sizeof(float);
@@ -317,6 +318,7 @@ int amoe_head1x1_pool_fwd(amoe_ctx* ctx, const void* x, const float* w, const fl
 
 int amoe_upsample_bilinear_nchw_fwd(amoe_ctx* ctx, const float* low, void* out, int B, int h, int w,
                                     int C, int H, int W, int out_dtype, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && low && out, "amoe_upsample_bilinear_nchw_fwd: NULL argument");
   int64_t total = (int64_t)B * C * H * ((W + 7) / 8);
   if (total == 0) return 0;
@@ -347,6 +349,7 @@ int amoe_upsample_bilinear_nchw_fwd(amoe_ctx* ctx, const float* low, void* out, 
 
 int amoe_mean_hw_nchw_fwd(amoe_ctx* ctx, const void* x, float* out, int B, int C, int HW, int dtype,
                           void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && out, "amoe_mean_hw_nchw_fwd: NULL argument");
   int64_t BC = (int64_t)B * C;
   if (BC == 0) return 0;

@@ -117,6 +117,7 @@ extern "C" {
 
 int amoe_image_nchw_to_nhwc(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
                             int Cp, int dst_dtype, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && src && dst, "amoe_image_nchw_to_nhwc: NULL argument");
   AMOE_REQUIRE(Cp >= C && C >= 1, "amoe_image_nchw_to_nhwc: need Cp >= C >= 1 (C=%d Cp=%d)", C, Cp);
   cudaStream_t st = (cudaStream_t)stream;
@@ -140,12 +141,14 @@ int amoe_image_nchw_to_nhwc(amoe_ctx* ctx, const float* src, void* dst, int B, i
 
 int amoe_image_nchw_to_nhwc_padded(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
                                    int Cp, int left, int Wpad, int top, int Hpad, int dst_dtype, void* stream) {
+  AMOE_ENTER(ctx);
   return amoe_image_nchw_to_nhwc_padded_v(ctx, src, dst, B, C, H, W, Cp, left, Wpad, top, Hpad, dst_dtype, 0.f, stream);
 }
 
 int amoe_image_nchw_to_nhwc_padded_v(amoe_ctx* ctx, const float* src, void* dst, int B, int C, int H, int W,
                                      int Cp, int left, int Wpad, int top, int Hpad, int dst_dtype, float pad_channel_value,
                                      void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && src && dst, "amoe_image_nchw_to_nhwc_padded: NULL argument");
   AMOE_REQUIRE(Cp >= C && C >= 1 && left >= 0 && Wpad >= left + W && top >= 0 && Hpad >= top + H,
                "amoe_image_nchw_to_nhwc_padded: bad geometry");
@@ -170,6 +173,7 @@ int amoe_image_nchw_to_nhwc_padded_v(amoe_ctx* ctx, const float* src, void* dst,
 
 int amoe_pack_conv_weight(amoe_ctx* ctx, const float* w_oihw, void* dst, int Cout, int Cin, int KH,
                           int KW, int Cin_pad, int dst_dtype, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && w_oihw && dst, "amoe_pack_conv_weight: NULL argument");
   AMOE_REQUIRE(Cin_pad >= Cin, "amoe_pack_conv_weight: Cin_pad < Cin");
   cudaStream_t st = (cudaStream_t)stream;
@@ -189,6 +193,7 @@ int amoe_pack_conv_weight(amoe_ctx* ctx, const float* w_oihw, void* dst, int Cou
 int amoe_fold_bn(amoe_ctx* ctx, const float* gamma, const float* beta, const float* mean,
                  const float* var, float eps, const float* conv_bias, int C, float* scale,
                  float* bias, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && scale && bias, "amoe_fold_bn: NULL argument");
   AMOE_REQUIRE(gamma == nullptr || (beta && mean && var), "amoe_fold_bn: incomplete BN parameters");
   fold_bn_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, conv_bias, C, scale, bias);

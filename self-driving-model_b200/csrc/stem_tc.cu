@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
 }  // namespace stem
 
 int amoe_stem_init(amoe_ctx* ctx) {
+  AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

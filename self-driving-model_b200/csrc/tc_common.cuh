@@ -139,9 +139,4 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-
-__device__ __forceinline__ void tma_load_2d_raw(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
-  tma_load_2d(dst, m, bar, c0, c1);
-}
-
 }  // namespace tc

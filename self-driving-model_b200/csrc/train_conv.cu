@@ -378,6 +378,7 @@ int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { return ((M + RED_ROW
 int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float momentum, float eps, float* y, float* save_mean, float* save_rstd,
                       float* workspace, int64_t M, int C, int relu, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && gamma && beta && y && save_mean && save_rstd && workspace, "amoe_bn_train_fwd: NULL argument");
   AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_train_fwd: C=%d must be a multiple of 4", C);
   AMOE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "amoe_bn_train_fwd: running stats come together");
@@ -397,6 +398,7 @@ int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const f
 
 int amoe_bn_apply_fwd(amoe_ctx* ctx, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, float* y, int64_t M, int C, int relu, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && mean && rstd && gamma && beta && y, "amoe_bn_apply_fwd: NULL argument");
   AMOE_REQUIRE(C % 4 == 0, "amoe_bn_apply_fwd: C=%d must be a multiple of 4", C);
   if (M == 0) return 0;
@@ -409,6 +411,7 @@ int amoe_bn_apply_fwd(amoe_ctx* ctx, const float* x, const float* mean, const fl
 int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_relu, const float* gamma, const float* mean,
                 const float* rstd, float* dx, float* dgamma, float* dbeta, float* workspace, int64_t M, int C,
                 int batch_stats, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && x && gamma && mean && rstd && dgamma && dbeta && workspace, "amoe_bn_bwd: NULL argument");
   AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_bwd: C=%d must be a multiple of 4", C);
   if (M == 0) return 0;
@@ -428,6 +431,7 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
 }
 
 int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int64_t M, int C, float scale, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && out && workspace, "amoe_colsum: NULL argument");
   AMOE_REQUIRE(C >= 1, "amoe_colsum: C=%d", C);
   if (M == 0) return 0;
@@ -442,6 +446,7 @@ int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int
 
 int amoe_conv2d_bwd_data(amoe_ctx* ctx, const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
                          int KH, int KW, int stride_h, int stride_w, int pad_h, int pad_w, int Ho, int Wo, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && w && dx, "amoe_conv2d_bwd_data: NULL argument");
   if (B == 0) return 0;
   ConvBwdParams p;
@@ -456,6 +461,7 @@ int amoe_conv2d_bwd_data(amoe_ctx* ctx, const float* dy, const float* w, float* 
 }
 
 int64_t amoe_conv2d_bwd_weight_workspace_floats(amoe_ctx* ctx, int B, int Cin, int Cout, int KH, int KW, int Ho, int Wo) {
+  AMOE_ENTER(ctx);
   if (!ctx) return -1;
   int rps;
   const int S = wgrad_slices(ctx->sm_count, Cout, KH * KW * Cin, (int64_t)B * Ho * Wo, &rps);
@@ -465,6 +471,7 @@ int64_t amoe_conv2d_bwd_weight_workspace_floats(amoe_ctx* ctx, int B, int Cin, i
 int amoe_conv2d_bwd_weight(amoe_ctx* ctx, const float* dy, const float* x, float* dw, float* workspace,
                            int64_t workspace_floats, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride_h,
                            int stride_w, int pad_h, int pad_w, int Ho, int Wo, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && x && dw && workspace, "amoe_conv2d_bwd_weight: NULL argument");
   if (B == 0) return 0;
   ConvBwdParams p;
@@ -486,6 +493,7 @@ int amoe_conv2d_bwd_weight(amoe_ctx* ctx, const float* dy, const float* x, float
 }
 
 int amoe_gap_fwd(amoe_ctx* ctx, const float* x, float* out, int B, int HW, int C, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && out, "amoe_gap_fwd: NULL argument");
   if (B == 0) return 0;
   gap_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, HW, C);
@@ -494,6 +502,7 @@ int amoe_gap_fwd(amoe_ctx* ctx, const float* x, float* out, int B, int HW, int C
 }
 
 int amoe_gap_bwd(amoe_ctx* ctx, const float* dy, float* dx, int B, int HW, int C, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && dx, "amoe_gap_bwd: NULL argument");
   if (B == 0) return 0;
   const int64_t n = (int64_t)B * HW * C;

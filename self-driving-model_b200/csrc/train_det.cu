@@ -207,6 +207,7 @@ __global__ __launch_bounds__(1024) void det_loss_kernel(const float* __restrict_
 extern "C" {
 
 int amoe_maxpool3x3s2_bwd(amoe_ctx* ctx, const float* x, const float* dy, float* dx, int NB, int H, int W, int C, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && dy && dx, "amoe_maxpool3x3s2_bwd: NULL argument");
   if (NB == 0) return 0;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
@@ -217,6 +218,7 @@ int amoe_maxpool3x3s2_bwd(amoe_ctx* ctx, const float* x, const float* dy, float*
 }
 
 int amoe_add_relu_fwd(amoe_ctx* ctx, const float* a, const float* b, float* y, int64_t n, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && a && b && y, "amoe_add_relu_fwd: NULL argument");
   AMOE_REQUIRE(n % 4 == 0, "amoe_add_relu_fwd: element count must be a multiple of 4");
   if (n == 0) return 0;
@@ -227,6 +229,7 @@ int amoe_add_relu_fwd(amoe_ctx* ctx, const float* a, const float* b, float* y, i
 }
 
 int amoe_relu_bwd(amoe_ctx* ctx, const float* dy, const float* y, float* g, int64_t n, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && y && g, "amoe_relu_bwd: NULL argument");
   AMOE_REQUIRE(n % 4 == 0, "amoe_relu_bwd: element count must be a multiple of 4");
   if (n == 0) return 0;
@@ -238,6 +241,7 @@ int amoe_relu_bwd(amoe_ctx* ctx, const float* dy, const float* y, float* g, int6
 
 int amoe_upsample_bilinear_nchw_bwd(amoe_ctx* ctx, const float* dy, float* dlow, int B, int h, int w, int C, int H, int W,
                                     void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && dlow, "amoe_upsample_bilinear_nchw_bwd: NULL argument");
   const int64_t cells = (int64_t)B * h * w * C;
   if (cells == 0) return 0;
@@ -250,6 +254,7 @@ int amoe_upsample_bilinear_nchw_bwd(amoe_ctx* ctx, const float* dy, float* dlow,
 
 int amoe_det_targets(amoe_ctx* ctx, const int64_t* pred_idx, const int32_t* batch_of, const int64_t* labels,
                      const float* boxes, int n_match, int Q, int64_t* target_classes, float* target_boxes, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && target_classes && target_boxes, "amoe_det_targets: NULL argument");
   if (n_match == 0) return 0;
   AMOE_REQUIRE(pred_idx && batch_of && labels && boxes, "amoe_det_targets: NULL argument");
@@ -263,6 +268,7 @@ int amoe_det_loss_fwd_bwd(amoe_ctx* ctx, const float* logits, int ld_logits, con
                           const int64_t* target_classes, const float* target_boxes, int64_t rows, int C, int ignore_index,
                           float bbox_weight, float* losses4, float* dlogits, int ld_dlogits, float* dboxes, int ld_dboxes,
                           void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && logits && boxes && target_classes && target_boxes && losses4, "amoe_det_loss_fwd_bwd: NULL argument");
   AMOE_REQUIRE(C >= 1 && ld_logits >= C && ld_boxes >= 4, "amoe_det_loss_fwd_bwd: bad sizes");
   det_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, ld_logits, boxes, ld_boxes, target_classes, target_boxes, rows,

@@ -178,18 +178,26 @@ __global__ void layernorm_bwd_param_kernel(const float* __restrict__ dy, const f
 constexpr int MAX_E = 4;
 __global__ void gate_combine_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ processed,
                                         int64_t e_stride, int ld_p, float inv_T, float* __restrict__ weights,
-                                        float* __restrict__ combined, int B, int E, int P) {
+                                        float* __restrict__ combined, int B, int E, int P, int sigmoid_gate) {
   const int b = blockIdx.x;
   __shared__ float w[MAX_E];
   if (threadIdx.x == 0) {
     float mx = -INFINITY, z[MAX_E], s = 0.f;
-    for (int e = 0; e < E; ++e) {
-      z[e] = logits[(int64_t)b * E + e] * inv_T;
-      mx = fmaxf(mx, z[e]);
-    }
-    for (int e = 0; e < E; ++e) {
-      z[e] = expf(z[e] - mx);
-      s += z[e];
+    if (sigmoid_gate) {   // gating_network.py:159-160: sigmoid(logits) / (sum + 1e-8), no temperature
+      for (int e = 0; e < E; ++e) {
+        z[e] = 1.f / (1.f + expf(-logits[(int64_t)b * E + e]));
+        s += z[e];
+      }
+      s += 1e-8f;
+    } else {
+      for (int e = 0; e < E; ++e) {
+        z[e] = logits[(int64_t)b * E + e] * inv_T;
+        mx = fmaxf(mx, z[e]);
+      }
+      for (int e = 0; e < E; ++e) {
+        z[e] = expf(z[e] - mx);
+        s += z[e];
+      }
     }
     for (int e = 0; e < E; ++e) {
       w[e] = z[e] / s;
@@ -204,11 +212,13 @@ __global__ void gate_combine_fwd_kernel(const float* __restrict__ logits, const 
   }
 }
 // dprocessed_e = w_e * dcombined; dw_e = <dcombined, processed_e> + dweights_e;
-// dlogits = inv_T * w * (dw - sum_e w_e dw_e)
+// dlogits = inv_T * w * (dw - sum_e w_e dw_e)            (softmax gate)
+// dlogits = s(1-s) * (dw - sum_e w_e dw_e) / (sum s + 1e-8)  (sigmoid gate, s = sigmoid(logits))
 __global__ void gate_combine_bwd_kernel(const float* __restrict__ dcombined, const float* __restrict__ dweights,
                                         const float* __restrict__ weights, const float* __restrict__ processed,
                                         int64_t e_stride, int ld_p, float inv_T, float* __restrict__ dlogits,
-                                        float* __restrict__ dprocessed, int64_t de_stride, int B, int E, int P) {
+                                        float* __restrict__ dprocessed, int64_t de_stride, int B, int E, int P,
+                                        const float* __restrict__ logits) {
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   __shared__ float part[MAX_E][8];
   float dot[MAX_E];
@@ -238,7 +248,17 @@ __global__ void gate_combine_bwd_kernel(const float* __restrict__ dcombined, con
       dw[e] = s + (dweights ? dweights[(int64_t)b * E + e] : 0.f);
       mix = fmaf(weights[(int64_t)b * E + e], dw[e], mix);
     }
-    for (int e = 0; e < E; ++e) dlogits[(int64_t)b * E + e] = inv_T * weights[(int64_t)b * E + e] * (dw[e] - mix);
+    if (logits != nullptr) {
+      float sg[MAX_E], S = 0.f;
+      for (int e = 0; e < E; ++e) {
+        sg[e] = 1.f / (1.f + expf(-logits[(int64_t)b * E + e]));
+        S += sg[e];
+      }
+      S += 1e-8f;
+      for (int e = 0; e < E; ++e) dlogits[(int64_t)b * E + e] = sg[e] * (1.f - sg[e]) * (dw[e] - mix) / S;
+    } else {
+      for (int e = 0; e < E; ++e) dlogits[(int64_t)b * E + e] = inv_T * weights[(int64_t)b * E + e] * (dw[e] - mix);
+    }
   }
 }
 
@@ -439,6 +459,7 @@ extern "C" {
 
 int amoe_linear_fwd(amoe_ctx* ctx, const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int B,
                     int in_dim, int out_dim, int relu, float drop_p, uint64_t seed, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && W && y, "amoe_linear_fwd: NULL argument");
   AMOE_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "amoe_linear_fwd: dropout p=%f out of [0,1)", drop_p);
   AMOE_REQUIRE(ldx >= in_dim && ldy >= out_dim, "amoe_linear_fwd: leading dimension too small");
@@ -451,6 +472,7 @@ int amoe_linear_fwd(amoe_ctx* ctx, const float* x, int ldx, const float* W, cons
 int amoe_linear_bwd(amoe_ctx* ctx, const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
                     const float* W, float* g_tmp, float* dx, int lddx, float* dW, float* db, int B, int in_dim,
                     int out_dim, int relu, float drop_p, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && W, "amoe_linear_bwd: NULL argument");
   AMOE_REQUIRE(!relu || (y && g_tmp), "amoe_linear_bwd: y and g_tmp are required behind a ReLU");
   AMOE_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "amoe_linear_bwd: dropout p=%f out of [0,1)", drop_p);
@@ -485,6 +507,7 @@ int amoe_linear_bwd(amoe_ctx* ctx, const float* dy, int lddy, const float* y, in
 
 int amoe_layernorm_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, float* mean,
                        float* rstd, int B, int D, float eps, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && gamma && beta && y && mean && rstd, "amoe_layernorm_fwd: NULL argument");
   if (B == 0) return 0;
   layernorm_fwd_kernel<<<ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, rstd, B, D, eps);
@@ -494,6 +517,7 @@ int amoe_layernorm_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const 
 
 int amoe_layernorm_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* gamma, const float* mean,
                        const float* rstd, float* dx, float* dgamma, float* dbeta, int B, int D, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && dy && x && gamma && mean && rstd, "amoe_layernorm_bwd: NULL argument");
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -509,13 +533,35 @@ int amoe_layernorm_bwd(amoe_ctx* ctx, const float* dy, const float* x, const flo
   return 0;
 }
 
-int amoe_gate_combine_fwd(amoe_ctx* ctx, const float* logits, const float* processed, int64_t expert_stride, int ld_p,
-                          float temperature, float* weights, float* combined, int B, int E, int P, void* stream) {
+int amoe_gate_combine_fwd_ex(amoe_ctx* ctx, const float* logits, const float* processed, int64_t expert_stride, int ld_p,
+                             float temperature, int use_softmax, float* weights, float* combined, int B, int E, int P,
+                             void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && logits && processed && weights && combined, "amoe_gate_combine_fwd: NULL argument");
   AMOE_REQUIRE(E >= 1 && E <= MAX_E && temperature > 0.f, "amoe_gate_combine_fwd: E=%d / temperature out of range", E);
   if (B == 0) return 0;
   gate_combine_fwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(logits, processed, expert_stride, ld_p, 1.f / temperature,
-                                                             weights, combined, B, E, P);
+                                                             weights, combined, B, E, P, use_softmax ? 0 : 1);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_gate_combine_fwd(amoe_ctx* ctx, const float* logits, const float* processed, int64_t expert_stride, int ld_p,
+                          float temperature, float* weights, float* combined, int B, int E, int P, void* stream) {
+  return amoe_gate_combine_fwd_ex(ctx, logits, processed, expert_stride, ld_p, temperature, 1, weights, combined, B, E, P, stream);
+}
+
+int amoe_gate_combine_bwd_ex(amoe_ctx* ctx, const float* dcombined, const float* dweights, const float* weights,
+                             const float* processed, int64_t expert_stride, int ld_p, float temperature,
+                             const float* logits_if_sigmoid, float* dlogits, float* dprocessed, int64_t dexpert_stride, int B,
+                             int E, int P, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && weights && processed && dlogits && dprocessed, "amoe_gate_combine_bwd: NULL argument");
+  AMOE_REQUIRE(E >= 1 && E <= MAX_E && temperature > 0.f, "amoe_gate_combine_bwd: E=%d / temperature out of range", E);
+  if (B == 0) return 0;
+  gate_combine_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dcombined, dweights, weights, processed, expert_stride, ld_p,
+                                                             1.f / temperature, dlogits, dprocessed, dexpert_stride, B, E, P,
+                                                             logits_if_sigmoid);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
@@ -523,13 +569,8 @@ int amoe_gate_combine_fwd(amoe_ctx* ctx, const float* logits, const float* proce
 int amoe_gate_combine_bwd(amoe_ctx* ctx, const float* dcombined, const float* dweights, const float* weights,
                           const float* processed, int64_t expert_stride, int ld_p, float temperature, float* dlogits,
                           float* dprocessed, int64_t dexpert_stride, int B, int E, int P, void* stream) {
-  AMOE_REQUIRE(ctx && weights && processed && dlogits && dprocessed, "amoe_gate_combine_bwd: NULL argument");
-  AMOE_REQUIRE(E >= 1 && E <= MAX_E && temperature > 0.f, "amoe_gate_combine_bwd: E=%d / temperature out of range", E);
-  if (B == 0) return 0;
-  gate_combine_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dcombined, dweights, weights, processed, expert_stride, ld_p,
-                                                             1.f / temperature, dlogits, dprocessed, dexpert_stride, B, E, P);
-  AMOE_LAUNCH_OK(ctx);
-  return 0;
+  return amoe_gate_combine_bwd_ex(ctx, dcombined, dweights, weights, processed, expert_stride, ld_p, temperature, nullptr,
+                                  dlogits, dprocessed, dexpert_stride, B, E, P, stream);
 }
 
 int amoe_gating_loss_fwd_bwd(amoe_ctx* ctx, const float* waypoints, const float* speed, int speed_ld,
@@ -537,6 +578,7 @@ int amoe_gating_loss_fwd_bwd(amoe_ctx* ctx, const float* waypoints, const float*
                              int tgt_speed_ld, int B, int H, int E, int speed_mode, const float* coef_host, int use_lb,
                              int use_entropy, float* losses, float* d_waypoints, float* d_speed, float* d_weights,
                              void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && waypoints && expert_weights && tgt_waypoints && coef_host && losses,
                "amoe_gating_loss_fwd_bwd: NULL argument");
   AMOE_REQUIRE(speed_mode == 0 || (speed && tgt_speed), "amoe_gating_loss_fwd_bwd: speed tensors missing");
@@ -553,6 +595,7 @@ int amoe_gating_loss_fwd_bwd(amoe_ctx* ctx, const float* waypoints, const float*
 }
 
 int amoe_sq_norm(amoe_ctx* ctx, const float* g, int64_t n, float* partial_ws, int ws_floats, float* out2, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && g && partial_ws && out2, "amoe_sq_norm: NULL argument");
   AMOE_REQUIRE(ws_floats >= 1, "amoe_sq_norm: workspace too small");
   const int blocks = (int)std::min<int64_t>(std::min(ws_floats, 4 * ctx->sm_count), std::max<int64_t>(1, (n + 1023) / 1024));
@@ -566,6 +609,7 @@ int amoe_sq_norm(amoe_ctx* ctx, const float* g, int64_t n, float* partial_ws, in
 int amoe_fused_clip_adamw(amoe_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                           const float* norm2, float grad_scale, float max_norm, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq, "amoe_fused_clip_adamw: NULL argument");
   AMOE_REQUIRE(step >= 1, "amoe_fused_clip_adamw: step counts from 1");
   if (n == 0) return 0;

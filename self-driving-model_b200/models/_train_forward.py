@@ -62,7 +62,7 @@ def gating_forward(gn, features: List[torch.Tensor], context: torch.Tensor) -> D
     gate_in = torch.cat([c] + processed, dim=1)                       # plumbing: one copy
     g = TF.linear(gate_in, gn.gate_network[0], relu=True, drop_p=_p(gn.gate_network[2], tr))
     logits = TF.linear(g, gn.gate_network[3])
-    weights, combined = TF.gate_combine(logits, processed, gn.temperature)
+    weights, combined = TF.gate_combine(logits, processed, gn.temperature, gn.use_softmax)
     final = TF.linear(combined, gn.output_projection)
     return {'combined_output': final, 'expert_weights': weights, 'processed_expert_outputs': processed,
             'gate_logits': logits}

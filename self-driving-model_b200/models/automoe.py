@@ -143,6 +143,21 @@ class AutoMoE(nn.Module):
             self._gate_flat[("stem", device.index)] = c
         return c[1]
 
+    input_mean = _ops.IMAGENET_MEAN      # T.Normalize constants of inference/run_automoe.py:30
+    input_std = _ops.IMAGENET_STD
+
+    def _stage_u8(self, frames: torch.Tensor, dtype: torch.dtype):
+        """uint8 HWC frames -> (image, x_nhwc).  bf16 tensor-core stem: one kernel writes the normalised, padded NHWC4
+        frame directly and `image` is only a [B,3,H,W] shape carrier (a permuted view of the bytes, never read);
+        otherwise the fp32 NCHW tensor of the reference transform is materialised and staged as usual."""
+        if frames.dim() != 4 or frames.shape[3] != 3:
+            raise ValueError(f"uint8 frames must be [B,H,W,3] (HWC RGB), got {tuple(frames.shape)}")
+        H, W = frames.shape[1], frames.shape[2]
+        if _ops.stem_mode(dtype, H, W) == "tc":
+            return frames.permute(0, 3, 1, 2), _ops.stage_u8_stem(frames, self.input_mean, self.input_std)
+        image = _ops.normalize_u8_nchw(frames, self.input_mean, self.input_std)
+        return image, stage_image(image, dtype)
+
     def _extract_context_features(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         state = self._vehicle_state(batch)
         return self.context_extractor(state[:, 0:1], state[:, 1:2], state[:, 2:3], state[:, 3:4])
@@ -205,9 +220,14 @@ class AutoMoE(nn.Module):
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
-        x_nhwc = stage_image(image, dtype)
+        if image.dtype == torch.uint8:
+            # camera bytes [B,H,W,3]: ToTensor + Normalize (+ the stem's layout) happen on the device
+            # (inference/run_automoe.py:25-31,41 does them per frame on the CPU and uploads fp32)
+            image, x_nhwc = self._stage_u8(image, dtype)
+        else:
+            x_nhwc = stage_image(image, dtype)
         stem_out = pol1 = pooled = layer1 = None
-        if _ops.stem_mode(dtype) == "tc":
+        if _ops.stem_mode(dtype, image.shape[2], image.shape[3]) == "tc":
             # experts' stems + policy conv1 read the same frame: one GEMM with N = 3*64 + 32
             # (+ the experts' max-pool fused behind it when the geometry allows)
             fs = self._fused_stem(image.device)
@@ -231,7 +251,7 @@ class AutoMoE(nn.Module):
         gn = self.gating_network
         gflat, gflat16 = self._gate_params(image.device, aux['n_ch'], bf16_copy=True)
         g = _ops.gate(state, aux['pooled'], gflat, aux['n_ch'],
-                      self.context_extractor.context_dim, gn.hidden_dim, gn.temperature,
+                      self.context_extractor.context_dim, gn.hidden_dim, gn.temperature, mode=gn._gate_kind(),
                       params_bf16=gflat16 if _ops.mlp_tc(dtype) else None)
 
         policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)

@@ -82,7 +82,8 @@ def make_head(out_channels: int) -> ParamHolder:
 class TrunkPack:
     dtype: torch.dtype
     G: int
-    stem: _ops.PackedConv
+    stems: dict             # stem mode ('tc' | 'rowwin' | 'simt') -> packed first-layer filters (filled on demand)
+    stem_src: tuple         # (convs, bns, device) the stems are packed from
     blocks: list            # [(conv1, conv2, down|None)]
     head3: _ops.PackedConv  # 3x3 512->256 + bias + ReLU (grouped)
     head1_w: List[torch.Tensor]  # per expert [N,256] fp32
@@ -108,13 +109,6 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
     """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
     G = len(experts)
     bbs = [e.backbone for e in experts]
-    mode = _ops.stem_mode(dtype)
-    if mode == "tc":       # Cin=3 stems of all experts as one GEMM over the raw image rows
-        stem = _ops.pack_stem([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
-    elif mode == "rowwin":
-        stem = _ops.pack_rowwin([bb[0] for bb in bbs], [bb[1] for bb in bbs], device, relu=True)
-    else:
-        stem = _ops.pack_conv([bb[0] for bb in bbs], [bb[1] for bb in bbs], dtype, device, relu=True, cin_pad=4)
     blocks = []
     for li in range(4, 8):
         for bi in range(2):
@@ -130,8 +124,23 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
     w1 = [h[2].weight.detach().to(device=device, dtype=torch.float32).reshape(h[2].weight.shape[0], -1).contiguous()
           for h in heads]
     b1 = [h[2].bias.detach().to(device=device, dtype=torch.float32).contiguous() for h in heads]
-    return TrunkPack(dtype, G, stem, blocks, head3, w1, b1, [w.shape[0] for w in w1],
-                     params_stamp(list(experts)))
+    return TrunkPack(dtype, G, {}, ([bb[0] for bb in bbs], [bb[1] for bb in bbs], device), blocks, head3, w1, b1,
+                     [w.shape[0] for w in w1], params_stamp(list(experts)))
+
+
+def stem_pack(pack: TrunkPack, mode: str):
+    """First-layer filters of all experts packed for `mode` (cached inside the TrunkPack)."""
+    st = pack.stems.get(mode)
+    if st is None:
+        convs, bns, device = pack.stem_src
+        if mode == "tc":       # Cin=3 stems of all experts as one GEMM over the raw image rows
+            st = _ops.pack_stem(convs, bns, device, relu=True)
+        elif mode == "rowwin":
+            st = _ops.pack_rowwin(convs, bns, device, relu=True)
+        else:
+            st = _ops.pack_conv(convs, bns, pack.dtype, device, relu=True, cin_pad=4)
+        pack.stems[mode] = st
+    return st
 
 
 def run_trunk_train(expert, image: torch.Tensor) -> torch.Tensor:
@@ -163,11 +172,11 @@ def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCHW fp32 frame -> the NHWC layout the first convolutions read (see _ops.stem_mode): the
     physically padded bf16 frame of the tensor-core stem, padded rows for the row-window variant, or
     plain [B,H,W,4] for the CUDA-core kernel."""
-    mode = _ops.stem_mode(dtype)
     H, W = image.shape[2], image.shape[3]
+    mode = _ops.stem_mode(dtype, H, W)
     if mode == "tc":
         if not _ops.stem_supported(H, W):
-            raise NotImplementedError(f"tensor-core stem needs even H, W and W <= 256 (got {H}x{W}); set AMOE_STEM=rowwin")
+            raise NotImplementedError(f"AMOE_STEM=tc needs even H, W and W <= 256 (got {H}x{W})")
         return _ops.stage_image_stem(image)
     if mode == "rowwin":
         return _ops.image_to_nhwc_padded(image, _ops.ROWWIN_CP, _ops.ROWWIN_LEFT, _ops.rowwin_wpad(W), dtype)
@@ -188,7 +197,7 @@ def chunked_stem_layer1_supported(pack: TrunkPack, B: int, H: int, W: int) -> bo
     chunk = _ops.l2_chunk_images()
     if chunk <= 0 or B <= chunk or pack.dtype != torch.bfloat16 or not _ops.use_flat():
         return False
-    if _ops.stem_mode(pack.dtype) != "tc" or not _ops.stem_pool_supported(H, W) or not trunk_pool_pad(pack, H, W):
+    if _ops.stem_mode(pack.dtype, H, W) != "tc" or not _ops.stem_pool_supported(H, W) or not trunk_pool_pad(pack, H, W):
         return False
     (c1a, c2a, dna), (c1b, c2b, dnb) = pack.blocks[0], pack.blocks[1]
     if dna is not None or dnb is not None or c1a.sh != 1 or c1b.sh != 1:
@@ -239,11 +248,12 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     B, _, H, W = image.shape
     G = pack.G
     pad = trunk_pool_pad(pack, H, W)
-    if layer1_out is None and stem_pooled is None and stem_out is None and isinstance(pack.stem, _ops.PackedStem) \
+    stem = stem_pack(pack, _ops.stem_mode(pack.dtype, H, W))
+    if layer1_out is None and stem_pooled is None and stem_out is None and isinstance(stem, _ops.PackedStem) \
             and chunked_stem_layer1_supported(pack, B, H, W):
         if x_nhwc is None:
             x_nhwc = stage_image(image, pack.dtype)
-        layer1_out = run_stem_layer1_chunked(pack, pack.stem, x_nhwc, B, H, W)
+        layer1_out = run_stem_layer1_chunked(pack, stem, x_nhwc, B, H, W)
     if layer1_out is not None or stem_pooled is not None:
         y = None                                                         # stem + max-pool (+ layer1) already done
     elif stem_out is not None:
@@ -251,15 +261,15 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     else:
         if x_nhwc is None:
             x_nhwc = stage_image(image, pack.dtype)
-        if isinstance(pack.stem, _ops.PackedStem) and _ops.stem_pool_supported(H, W):
-            stem_pooled = _ops.stem_pool_forward(pack.stem, x_nhwc, B, H, W, G, pad)[0]
+        if isinstance(stem, _ops.PackedStem) and _ops.stem_pool_supported(H, W):
+            stem_pooled = _ops.stem_pool_forward(stem, x_nhwc, B, H, W, G, pad)[0]
             y = None
-        elif isinstance(pack.stem, _ops.PackedStem):
-            y = _ops.stem_forward(pack.stem, x_nhwc, B, H, W, groups=[G])[0]   # [G*B,H/2,W/2,64]
-        elif isinstance(pack.stem, _ops.PackedRowwin):
-            y = _ops.conv2d_rowwin(pack.stem, x_nhwc, B, H, W)
+        elif isinstance(stem, _ops.PackedStem):
+            y = _ops.stem_forward(stem, x_nhwc, B, H, W, groups=[G])[0]   # [G*B,H/2,W/2,64]
+        elif isinstance(stem, _ops.PackedRowwin):
+            y = _ops.conv2d_rowwin(stem, x_nhwc, B, H, W)
         else:
-            y = _ops.conv2d(pack.stem, x_nhwc, B, H, W, x_shared=True)
+            y = _ops.conv2d(stem, x_nhwc, B, H, W, x_shared=True)
     # Activations of the 64/128-channel stages live in a physically padded layout (zero border of one
     # pixel) when their 3x3/s1 convolutions run through the halo-reuse kernel; `pad` tracks the layout.
     flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()

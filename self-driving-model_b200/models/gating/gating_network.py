@@ -60,8 +60,6 @@ class GatingNetwork(nn.Module):
         self.apply_topk_at_eval = bool(apply_topk_at_eval)
         if self.top_k > 0:
             raise NotImplementedError("noisy top-k gating is unreachable through AutoMoE and not implemented")
-        if not use_softmax:
-            raise NotImplementedError("sigmoid gating (use_softmax=False) is not implemented in the fused kernel")
         if expert_output_dims is None:
             expert_output_dims = [256] * num_experts
         self.context_encoder = ContextEncoder(context_dim, hidden_dim)
@@ -72,6 +70,10 @@ class GatingNetwork(nn.Module):
         )
         self.output_projection = nn.Linear(processed_dim, processed_dim)
         self._flat = None
+
+    def _gate_kind(self) -> int:
+        """Mode bit of the fused kernel: 32 = sigmoid gate (use_softmax=False, reference gating_network.py:159-160)."""
+        return 0 if self.use_softmax else 32
 
     def _params(self, device):
         stamp = (params_stamp([self]), device)
@@ -88,7 +90,7 @@ class GatingNetwork(nn.Module):
         feats = torch.stack([t.float() for t in expert_outputs], dim=0).contiguous()  # [E,B,256]
         context = context.float().contiguous()
         out = _ops.gate(context, feats, self._params(context.device), [1] * E, self.context_dim, self.hidden_dim,
-                        self.temperature, mode=2 | 4)
+                        self.temperature, mode=2 | 4 | self._gate_kind())
         return {
             'combined_output': out['combined'],
             'expert_weights': out['weights'],
@@ -100,7 +102,7 @@ class GatingNetwork(nn.Module):
         require_eval(self, "GatingNetwork")
         context = context.float().contiguous()
         return _ops.gate(context, None, self._params(context.device), [1] * self.num_experts, self.context_dim,
-                         self.hidden_dim, self.temperature, mode=1 | 2)
+                         self.hidden_dim, self.temperature, mode=1 | 2 | self._gate_kind())
 
     def get_expert_weights(self, context: torch.Tensor) -> torch.Tensor:
         """Expert weights from the context alone (gating_network.py:177-199)."""

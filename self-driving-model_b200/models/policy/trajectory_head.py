@@ -57,12 +57,8 @@ class TrajectoryPolicy(nn.Module):
         p = self._packs.get(key)
         if p is None or p["stamp"] != stamp:
             net = self.backbone.net
-            mode = _ops.stem_mode(dtype)
-            first = (_ops.pack_stem([net[0]], [net[1]], device, relu=True) if mode == "tc" else
-                     _ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if mode == "rowwin" else
-                     _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4))
             convs = [
-                first,
+                {},      # conv1 (Cin=3), packed on demand per stem mode (see _first)
                 _ops.pack_conv([net[3]], [net[4]], dtype, device, relu=True),
                 _ops.pack_conv([net[6]], [net[7]], dtype, device, relu=True),
                 _ops.pack_conv([net[9]], [net[10]], dtype, device, relu=True),
@@ -73,6 +69,16 @@ class TrajectoryPolicy(nn.Module):
             p = dict(stamp=stamp, convs=convs, flat=flat, flat16=flat.to(torch.bfloat16))
             self._packs[key] = p
         return p
+
+    def _first(self, p, mode: str, dtype, device):
+        first = p["convs"][0].get(mode)
+        if first is None:
+            net = self.backbone.net
+            first = (_ops.pack_stem([net[0]], [net[1]], device, relu=True) if mode == "tc" else
+                     _ops.pack_rowwin([net[0]], [net[1]], device, relu=True) if mode == "rowwin" else
+                     _ops.pack_conv([net[0]], [net[1]], dtype, device, relu=True, cin_pad=4))
+            p["convs"][0][mode] = first
+        return first
 
     def forward(self, image: torch.Tensor, context: Optional[torch.Tensor] = None, _x_nhwc=None,
                 _dtype=None, _conv1=None) -> Dict[str, torch.Tensor]:
@@ -85,12 +91,12 @@ class TrajectoryPolicy(nn.Module):
         p = self._pack(dtype, image.device)
         B, _, H, W = image.shape
         h, w = H, W
-        convs = p["convs"]
         if _conv1 is not None:       # conv1 already computed by the caller (fused into the experts' stem GEMM)
-            x, convs = _conv1, convs[1:]
+            x, convs = _conv1, p["convs"][1:]
             h, w = x.shape[1], x.shape[2]
         else:
             x = _x_nhwc if _x_nhwc is not None else stage_image(image, dtype)
+            convs = [self._first(p, _ops.stem_mode(dtype, H, W), dtype, image.device)] + p["convs"][1:]
         for pc in convs:
             if isinstance(pc, _ops.PackedStem):
                 x = _ops.stem_forward(pc, x, B, h, w)[0]

@@ -110,34 +110,37 @@ class _GateCombine(torch.autograd.Function):
     """(logits [B,E], processed [E,B,P]) -> (weights [B,E], combined [B,P])  — gating_network.py:157-165."""
 
     @staticmethod
-    def forward(ctx_, logits, processed, temperature: float):
+    def forward(ctx_, logits, processed, temperature: float, use_softmax: bool = True):
         lg, pr = _f32c(logits), _f32c(processed)
         E, B, P = pr.shape
         dev = lg.device
         weights = torch.empty((B, E), device=dev, dtype=torch.float32)
         combined = torch.empty((B, P), device=dev, dtype=torch.float32)
-        check(lib().amoe_gate_combine_fwd(ctx(dev), ptr(lg), ptr(pr), B * P, P, float(temperature), ptr(weights),
-                                          ptr(combined), B, E, P, stream_ptr(dev)), "gate_combine_fwd")
-        ctx_.save_for_backward(weights, pr)
+        check(lib().amoe_gate_combine_fwd_ex(ctx(dev), ptr(lg), ptr(pr), B * P, P, float(temperature), int(bool(use_softmax)),
+                                             ptr(weights), ptr(combined), B, E, P, stream_ptr(dev)), "gate_combine_fwd")
+        ctx_.save_for_backward(weights, pr, lg)
         ctx_.T = float(temperature)
+        ctx_.use_softmax = bool(use_softmax)
         return weights, combined
 
     @staticmethod
     def backward(ctx_, dweights, dcombined):
-        weights, pr = ctx_.saved_tensors
+        weights, pr, lg = ctx_.saved_tensors
         E, B, P = pr.shape
         dev = pr.device
         dw = _f32c(dweights) if dweights is not None else None
         dc = _f32c(dcombined) if dcombined is not None else None
         dlogits = torch.empty((B, E), device=dev, dtype=torch.float32)
         dproc = torch.empty_like(pr)
-        check(lib().amoe_gate_combine_bwd(ctx(dev), ptr(dc), ptr(dw), ptr(weights), ptr(pr), B * P, P, ctx_.T, ptr(dlogits),
-                                          ptr(dproc), B * P, B, E, P, stream_ptr(dev)), "gate_combine_bwd")
-        return dlogits, dproc, None
+        check(lib().amoe_gate_combine_bwd_ex(ctx(dev), ptr(dc), ptr(dw), ptr(weights), ptr(pr), B * P, P, ctx_.T,
+                                             None if ctx_.use_softmax else ptr(lg), ptr(dlogits), ptr(dproc), B * P, B, E, P,
+                                             stream_ptr(dev)), "gate_combine_bwd")
+        return dlogits, dproc, None, None
 
 
-def gate_combine(logits, processed: List[torch.Tensor], temperature: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    return _GateCombine.apply(logits, torch.stack(processed, dim=0), temperature)
+def gate_combine(logits, processed: List[torch.Tensor], temperature: float,
+                 use_softmax: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _GateCombine.apply(logits, torch.stack(processed, dim=0), temperature, use_softmax)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -27,6 +27,25 @@ class HungarianMatcher(nn.Module):
         assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0
         self.lsap_threads = 8
 
+    @staticmethod
+    def pack_targets(targets, counts, Nmax: int, D: int, dev):
+        """Ragged per-image targets -> padded [B,Nmax,D] fp32 boxes / [B,Nmax] int64 labels (-1 padding) with ONE
+        concatenation and ONE indexed scatter per tensor (no per-image copies)."""
+        B = len(targets)
+        tb = torch.zeros((B, Nmax, D), device=dev, dtype=torch.float32)
+        tl = torch.full((B, Nmax), -1, device=dev, dtype=torch.int64)
+        total = sum(counts)
+        if total:
+            boxes = torch.cat([t['boxes'].reshape(-1, D) for t in targets], dim=0).to(device=dev, dtype=torch.float32)
+            labels = torch.cat([t['labels'].reshape(-1) for t in targets], dim=0).to(device=dev, dtype=torch.int64)
+            cnt = torch.tensor(counts, dtype=torch.int64)
+            img = torch.repeat_interleave(torch.arange(B), cnt)
+            slot = torch.arange(total) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+            flat = (img * Nmax + slot).to(dev)
+            tb.view(B * Nmax, D)[flat] = boxes
+            tl.view(B * Nmax)[flat] = labels
+        return tb, tl
+
     @torch.no_grad()
     def cost_matrices(self, outputs, targets):
         """Padded cost tensor [B,Q,Nmax] (device) and per-image target counts (CPU int32)."""
@@ -42,13 +61,7 @@ class HungarianMatcher(nn.Module):
         n_tgt_host = torch.tensor(counts, dtype=torch.int32)
         if Nmax == 0:
             return torch.zeros((B, Q, 0), device=dev), n_tgt_host
-        tb = torch.zeros((B, Nmax, D), device=dev, dtype=torch.float32)
-        tl = torch.full((B, Nmax), -1, device=dev, dtype=torch.int64)
-        for b, t in enumerate(targets):
-            n = counts[b]
-            if n:
-                tb[b, :n] = t['boxes'].to(device=dev, dtype=torch.float32)
-                tl[b, :n] = t['labels'].to(device=dev, dtype=torch.int64)
+        tb, tl = self.pack_targets(targets, counts, Nmax, D, dev)
         cost = _ops.hungarian_cost(pred_logits.float().contiguous(), pred_boxes.float().contiguous(), tb, tl,
                                    n_tgt_host.to(dev), self.cost_class, self.cost_bbox, self.cost_giou)
         return cost, n_tgt_host

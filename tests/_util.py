@@ -18,9 +18,17 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def build_b200_model(device, precision="auto", seed=0):
-    from automoe_b200.models.automoe import create_automoe_model
+def golden_config(g):
+    """Model config of a golden automoe case (the sigmoid-gate case stores use_softmax=False)."""
     cfg = dict(synth.CONFIG_3EXPERT)
+    if "use_softmax" in g.files:
+        cfg["gating"] = dict(cfg["gating"], use_softmax=bool(g["use_softmax"]))
+    return cfg
+
+
+def build_b200_model(device, precision="auto", seed=0, config=None):
+    from automoe_b200.models.automoe import create_automoe_model
+    cfg = dict(config or synth.CONFIG_3EXPERT)
     cfg["precision"] = precision
     m = create_automoe_model(cfg, "cpu")
     sd = synth.synth_state_dict(m.state_dict(), seed)

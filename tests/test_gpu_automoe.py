@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import build_b200_model, golden_batch, rel_err, rel_l2
+from _util import build_b200_model, golden_batch, golden_config, rel_err, rel_l2
 from oracle import automoe_oracle as O
 from oracle import synth
 
@@ -45,6 +45,46 @@ def test_fp32_matches_reference_golden(name, golden_dir, model_sd):
     assert np.array_equal(out["expert_weights"].argmax(1).cpu().numpy(), g["expert_weights"].argmax(1))
     assert out["expert_outputs"][1].shape == (int(g["B"]), 19, int(g["H"]), int(g["W"]))
     assert rel_err(m.get_expert_weights(batch).cpu(), g["ctx_only_weights"]) < 1e-4
+
+
+def test_sigmoid_gate_matches_reference_golden(golden_dir):
+    """use_softmax=False (gating_network.py:159-160), reachable through AutoMoE's gating config: fp32 vs the reference's
+    golden outputs, bf16 (tensor-core gate variant at B >= 16) vs the oracle, and the training combine's gradients."""
+    g = np.load(golden_dir / "automoe_b2_64_sigmoid.npz")
+    cfg = golden_config(g)
+    m, sd = build_b200_model(DEV, "auto", config=cfg)
+    batch = _to(golden_batch(g), DEV)
+    with torch.no_grad():
+        out = m(batch)
+    for k in SMALL:
+        assert rel_err(out[k].cpu(), g[{"speed_seq": "speed_seq_out"}.get(k, k)]) < 1e-4, k
+    assert rel_err(m.get_expert_weights(batch).cpu(), g["ctx_only_weights"]) < 1e-4
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    big = _to(synth.synth_batch(32, 64, 64, seed=9), DEV)
+    with torch.no_grad():
+        ref = O.automoe_forward(sdd, big, cfg)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o16 = m(big)
+    assert rel_err(o16["expert_weights"], ref["expert_weights"]) < 1e-2
+    assert rel_err(o16["combined_features"], ref["combined_features"]) < 2e-2
+    # differentiable combine (training path): gradients of the sigmoid gate against torch autograd
+    from automoe_b200.training import functional as TF
+    gen = torch.Generator().manual_seed(4)
+    lg = torch.randn((6, 3), generator=gen).to(DEV).requires_grad_(True)
+    pr = [torch.randn((6, 256), generator=gen).to(DEV).requires_grad_(True) for _ in range(3)]
+    w, c = TF.gate_combine(lg, pr, 1.0, use_softmax=False)
+    lg2 = lg.detach().clone().requires_grad_(True)
+    pr2 = [p.detach().clone().requires_grad_(True) for p in pr]
+    w2 = torch.sigmoid(lg2)
+    w2 = w2 / (w2.sum(dim=1, keepdim=True) + 1e-8)
+    c2 = sum(w2[:, i:i + 1] * pr2[i] for i in range(3))
+    gw, gc = torch.randn_like(w), torch.randn_like(c)
+    ((w * gw).sum() + (c * gc).sum()).backward()
+    ((w2 * gw).sum() + (c2 * gc).sum()).backward()
+    assert rel_err(w, w2) < 1e-6 and rel_err(c, c2) < 1e-6
+    assert rel_err(lg.grad, lg2.grad) < 1e-5
+    for a, b in zip(pr, pr2):
+        assert rel_err(a.grad, b.grad) < 1e-6
 
 
 def test_fp32_matches_oracle_batch(model_sd):

@@ -93,3 +93,31 @@ def test_unsupported_configs_fail_loudly():
     cfg["context"] = {"type": "full"}
     with pytest.raises(NotImplementedError):
         create_automoe_model(cfg, "cpu")
+
+
+def test_matcher_pack_targets_is_one_padded_pack():
+    """Ragged targets -> padded [B,Nmax,D] / [B,Nmax] (-1) without per-image copies; empty images stay padding."""
+    import torch
+    from automoe_b200.training.hungarian_matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(0)
+    counts = [3, 0, 5, 1]
+    targets = [{"boxes": torch.rand(n, 4, generator=g), "labels": torch.randint(0, 10, (n,), generator=g)} for n in counts]
+    tb, tl = HungarianMatcher.pack_targets(targets, counts, 5, 4, "cpu")
+    for b, t in enumerate(targets):
+        n = counts[b]
+        assert torch.equal(tb[b, :n], t["boxes"]) and torch.equal(tl[b, :n], t["labels"])
+        assert (tl[b, n:] == -1).all() and (tb[b, n:] == 0).all()
+
+
+def test_stem_mode_follows_geometry(monkeypatch):
+    """bf16: the tensor-core stem for frames it takes (even H/W, W <= 256), the row-window variant otherwise
+    (BDD's native 720x1280) - chosen by the module, no environment switch needed; fp32 always CUDA cores."""
+    import torch
+    from automoe_b200 import _ops
+    monkeypatch.delenv("AMOE_STEM", raising=False)
+    assert _ops.stem_mode(torch.bfloat16, 256, 256) == "tc"
+    assert _ops.stem_mode(torch.bfloat16, 720, 1280) == "rowwin"
+    assert _ops.stem_mode(torch.bfloat16, 255, 256) == "rowwin"
+    assert _ops.stem_mode(torch.float32, 256, 256) == "simt"
+    monkeypatch.setenv("AMOE_STEM", "rowwin")
+    assert _ops.stem_mode(torch.bfloat16, 256, 256) == "rowwin"
