@@ -74,17 +74,33 @@ def policy_head_batchstats(image, context, sd, p="policy_head", horizon=10):
     return {"waypoints": outs[0].view(-1, horizon, 2), "speed": outs[1].view(-1, horizon)}
 
 
-def training_forward(sd, batch, config, policy_batch_stats: bool = False):
-    """AutoMoE.forward as train_one_epoch sees it, Dropout off, experts frozen with eval BatchNorm:
-    gradients flow into the TRAINABLE_PREFIXES parameters only."""
+def run_expert_batchstats(x, sd, p, cfg):
+    """An expert inside model.train() (train_gating_network.py:85): torchvision BasicBlocks with BATCH statistics
+    (running statistics are updated as a side effect in the reference; the outputs do not depend on them)."""
+    from .detection_train_oracle import trunk_train
+    feat = trunk_train(x, sd, p + ".backbone", batch_stats=True)
+    if cfg["type"] == "detection":
+        nc = cfg.get("num_classes", 10)
+        out = O.expert_head(feat, sd, p + ".head")
+        return {"class_logits": out[:, :nc], "bbox_deltas": out[:, nc:]}
+    low = O.expert_head(feat, sd, p + ".decoder")
+    return F.interpolate(low, size=x.shape[-2:], mode="bilinear", align_corners=False)
+
+
+def training_forward(sd, batch, config, policy_batch_stats: bool = False, expert_batch_stats: bool = False):
+    """AutoMoE.forward as train_one_epoch sees it, Dropout off, experts frozen; gradients flow into the
+    TRAINABLE_PREFIXES parameters only.  expert_batch_stats=True is the reference's actual state after model.train()
+    (frozen experts' BatchNorm on batch statistics); False = after model.experts.eval() (running statistics)."""
     image = batch["image"]
     ctx = O.context_extractor(O.vehicle_state(batch), sd)
+    run = run_expert_batchstats if expert_batch_stats else O.run_expert
     with torch.no_grad():
-        expert_outputs = [O.run_expert(image, sd, f"experts.{i}", c) for i, c in enumerate(config["experts"])]
+        expert_outputs = [run(image, sd, f"experts.{i}", c) for i, c in enumerate(config["experts"])]
     feats = [O.extractor(o, sd, f"expert_extractors.extractors.{i}", c)
              for i, (o, c) in enumerate(zip(expert_outputs, config["experts"]))]
     g = O.gating_network(feats, ctx, sd, temperature=config["gating"].get("temperature", 1.0))
     horizon = config["policy"].get("num_waypoints", 10)
     pol = (policy_head_batchstats if policy_batch_stats else O.policy_head)(image, g["combined_output"], sd, horizon=horizon)
     return {"waypoints": pol["waypoints"], "speed": pol["speed"][:, -1:].contiguous(), "speed_seq": pol["speed"],
-            "expert_weights": g["expert_weights"], "gate_logits": g["gate_logits"], "combined_features": g["combined_output"]}
+            "expert_weights": g["expert_weights"], "gate_logits": g["gate_logits"], "combined_features": g["combined_output"],
+            "expert_outputs": expert_outputs}

@@ -189,6 +189,7 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
 
 extern "C" int amoe_maxpool3x3s2_fwd(amoe_ctx* ctx, const void* x, void* y, int NB, int H, int W,
                                       int C, int dtype, int out_pad, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && y, "amoe_maxpool3x3s2_fwd: NULL argument");
   AMOE_REQUIRE(out_pad >= 0, "amoe_maxpool3x3s2_fwd: negative out_pad");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;

@@ -280,6 +280,7 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
                              const int* n_ch_host, int ctx_dim, int hidden, float temperature,
                              int mode, float* context, float* features, float* processed,
                              float* gate_logits, float* weights, float* combined, void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && state && params && n_ch_host, "amoe_gate_fwd: NULL argument");
   AMOE_REQUIRE(E >= 1 && E <= GATE_MAX_E, "amoe_gate_fwd: E=%d out of range [1,%d]", E, GATE_MAX_E);
   AMOE_REQUIRE((mode & (GATE_MODE_CTX_ONLY | GATE_MODE_STOP_CTX)) || pooled, "amoe_gate_fwd: pooled is NULL");
@@ -365,6 +366,7 @@ extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* poo
                              const int* n_ch_host, int ctx_dim, int hidden, float temperature,
                              int mode, float* context, float* features, float* processed,
                              float* gate_logits, float* weights, float* combined, void* stream) {
+  AMOE_ENTER(ctx);
   return amoe_gate_fwd_ex(ctx, state, pooled, params, nullptr, n_params, B, E, n_ch_host, ctx_dim, hidden, temperature, mode,
                           context, features, processed, gate_logits, weights, combined, stream);
 }

@@ -30,15 +30,59 @@ __device__ __forceinline__ void box_corners(const float* b, int D, float& x1, fl
   y2 = fadd(cy, hh);
 }
 
+// One CTA = 32 queries of one image.  Everything a (query, target) pair needs is staged in shared memory first
+// (class probabilities of the 32 queries; per-box corners and areas, computed ONCE per box instead of once per
+// pair), then warp w sweeps rows w, w+8, ... with its lanes along the target axis: conflict-free shared-memory
+// reads, no integer division, and every store instruction writes one contiguous run of the padded cost row.
+// The arithmetic per pair is the same rounded fp32 op sequence as before (= torch's eager ops).
+struct BoxPre { float x1, y1, x2, y2, area; };
+
+__device__ __forceinline__ BoxPre box_pre(const float* b, int D) {
+  BoxPre r;
+  box_corners(b, D, r.x1, r.y1, r.x2, r.y2);
+  r.area = fmul(fsub(r.x2, r.x1), fsub(r.y2, r.y1));
+  return r;
+}
+
 __global__ __launch_bounds__(256) void hungarian_cost_kernel(
     const float* __restrict__ logits, const float* __restrict__ boxes,
     const float* __restrict__ tgt_boxes, const int64_t* __restrict__ tgt_labels,
     const int32_t* __restrict__ n_tgt, float* __restrict__ cost, int Q, int C, int D, int Nmax,
     float w_class, float w_bbox, float w_giou) {
-  extern __shared__ float sprob[];  // [MQ_TILE][C]
+  extern __shared__ float sm[];
   const int b = blockIdx.y;
   const int q0 = blockIdx.x * MQ_TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = min(n_tgt[b], Nmax);
+  const bool giou_on = (w_giou > 0.f) && (D == 4 || D == 7);
+  // shared-memory carve-up (floats): probabilities [32][C] | query boxes [32][D] | query pre [5][32] |
+  //                                  target boxes [D][Nmax] | target pre [5][Nmax] | target label [Nmax] (int)
+  float* sprob = sm;
+  float* sqb = sprob + MQ_TILE * C;
+  float* sqp = sqb + MQ_TILE * D;
+  float* stb = sqp + 5 * MQ_TILE;
+  float* stp = stb + D * Nmax;
+  int* slab = reinterpret_cast<int*>(stp + 5 * Nmax);
+  for (int n = threadIdx.x; n < nt; n += blockDim.x) {
+    const float* tb = tgt_boxes + ((int64_t)b * Nmax + n) * D;
+    for (int k = 0; k < D; ++k) stb[k * Nmax + n] = tb[k];
+    if (giou_on) {
+      const BoxPre r = box_pre(tb, D);
+      stp[n] = r.x1; stp[Nmax + n] = r.y1; stp[2 * Nmax + n] = r.x2; stp[3 * Nmax + n] = r.y2; stp[4 * Nmax + n] = r.area;
+    }
+    int64_t lab = tgt_labels[(int64_t)b * Nmax + n];
+    if (lab < 0) lab += C;  // torch negative indexing
+    slab[n] = (lab >= 0 && lab < C) ? (int)lab : -1;
+  }
+  if (threadIdx.x < MQ_TILE && q0 + threadIdx.x < Q) {
+    const int r = threadIdx.x;
+    const float* pb = boxes + ((int64_t)b * Q + q0 + r) * D;
+    for (int k = 0; k < D; ++k) sqb[r * D + k] = pb[k];
+    if (giou_on) {
+      const BoxPre v = box_pre(pb, D);
+      sqp[r] = v.x1; sqp[32 + r] = v.y1; sqp[64 + r] = v.x2; sqp[96 + r] = v.y2; sqp[128 + r] = v.area;
+    }
+  }
   // softmax over classes, one warp per query row
   for (int r = warp; r < MQ_TILE; r += (blockDim.x >> 5)) {
     int q = q0 + r;
@@ -57,42 +101,37 @@ __global__ __launch_bounds__(256) void hungarian_cost_kernel(
     for (int c = lane; c < C; c += 32) sprob[r * C + c] = sprob[r * C + c] / s;
   }
   __syncthreads();
-  const int nt = n_tgt[b];
-  const bool giou_on = (w_giou > 0.f) && (D == 4 || D == 7);
-  for (int i = threadIdx.x; i < MQ_TILE * Nmax; i += blockDim.x) {
-    int r = i / Nmax, n = i - r * Nmax;
-    int q = q0 + r;
+  for (int r = warp; r < MQ_TILE; r += (blockDim.x >> 5)) {
+    const int q = q0 + r;
     if (q >= Q) break;
-    float out = 0.f;
-    if (n < nt) {
-      const float* pb = boxes + ((int64_t)b * Q + q) * D;
-      const float* tb = tgt_boxes + ((int64_t)b * Nmax + n) * D;
-      int64_t lab = tgt_labels[(int64_t)b * Nmax + n];
-      if (lab < 0) lab += C;  // torch negative indexing
-      float p = (lab >= 0 && lab < C) ? sprob[r * C + (int)lab] : __int_as_float(0x7fc00000);
-      float l1 = 0.f;
-      for (int k = 0; k < D; ++k) l1 = fadd(l1, fabsf(fsub(pb[k], tb[k])));
-      float g = 0.f;
-      if (giou_on) {
-        float ax1, ay1, ax2, ay2, bx1, by1, bx2, by2;
-        box_corners(pb, D, ax1, ay1, ax2, ay2);
-        box_corners(tb, D, bx1, by1, bx2, by2);
-        float area1 = fmul(fsub(ax2, ax1), fsub(ay2, ay1));
-        float area2 = fmul(fsub(bx2, bx1), fsub(by2, by1));
-        float iw = fmaxf(fsub(fminf(ax2, bx2), fmaxf(ax1, bx1)), 0.f);
-        float ih = fmaxf(fsub(fminf(ay2, by2), fmaxf(ay1, by1)), 0.f);
-        float inter = fmul(iw, ih);
-        float uni = fsub(fadd(area1, area2), inter);
-        float iou = __fdiv_rn(inter, uni);
-        float cw = fmaxf(fsub(fmaxf(ax2, bx2), fminf(ax1, bx1)), 0.f);
-        float ch = fmaxf(fsub(fmaxf(ay2, by2), fminf(ay1, by1)), 0.f);
-        float areai = fmul(cw, ch);
-        g = fsub(iou, __fdiv_rn(fsub(areai, uni), areai));
+    float* crow = cost + ((int64_t)b * Q + q) * Nmax;
+    float ax1 = 0.f, ay1 = 0.f, ax2 = 0.f, ay2 = 0.f, area1 = 0.f;
+    if (giou_on) { ax1 = sqp[r]; ay1 = sqp[32 + r]; ax2 = sqp[64 + r]; ay2 = sqp[96 + r]; area1 = sqp[128 + r]; }
+    for (int n = lane; n < Nmax; n += 32) {
+      float out = 0.f;
+      if (n < nt) {
+        const int lab = slab[n];
+        const float p = lab >= 0 ? sprob[r * C + lab] : __int_as_float(0x7fc00000);
+        float l1 = 0.f;
+        for (int k = 0; k < D; ++k) l1 = fadd(l1, fabsf(fsub(sqb[r * D + k], stb[k * Nmax + n])));
+        float g = 0.f;
+        if (giou_on) {
+          const float bx1 = stp[n], by1 = stp[Nmax + n], bx2 = stp[2 * Nmax + n], by2 = stp[3 * Nmax + n], area2 = stp[4 * Nmax + n];
+          float iw = fmaxf(fsub(fminf(ax2, bx2), fmaxf(ax1, bx1)), 0.f);
+          float ih = fmaxf(fsub(fminf(ay2, by2), fmaxf(ay1, by1)), 0.f);
+          float inter = fmul(iw, ih);
+          float uni = fsub(fadd(area1, area2), inter);
+          float iou = __fdiv_rn(inter, uni);
+          float cw = fmaxf(fsub(fmaxf(ax2, bx2), fminf(ax1, bx1)), 0.f);
+          float ch = fmaxf(fsub(fmaxf(ay2, by2), fminf(ay1, by1)), 0.f);
+          float areai = fmul(cw, ch);
+          g = fsub(iou, __fdiv_rn(fsub(areai, uni), areai));
+        }
+        // C = w_bbox*cost_bbox + w_class*(-prob) + w_giou*(-giou)   (hungarian_matcher.py:73-75)
+        out = fadd(fadd(fmul(w_bbox, l1), fmul(w_class, -p)), fmul(w_giou, -g));
       }
-      // C = w_bbox*cost_bbox + w_class*(-prob) + w_giou*(-giou)   (hungarian_matcher.py:73-75)
-      out = fadd(fadd(fmul(w_bbox, l1), fmul(w_class, -p)), fmul(w_giou, -g));
+      crow[n] = out;
     }
-    cost[((int64_t)b * Q + q) * Nmax + n] = out;
   }
 }
 
@@ -101,11 +140,15 @@ extern "C" int amoe_hungarian_cost_fwd(amoe_ctx* ctx, const float* logits, const
                                        const int32_t* n_tgt, float* cost, int B, int Q, int C, int D,
                                        int Nmax, float w_class, float w_bbox, float w_giou,
                                        void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && logits && boxes && n_tgt && cost, "amoe_hungarian_cost_fwd: NULL argument");
   AMOE_REQUIRE(Nmax == 0 || (tgt_boxes && tgt_labels), "amoe_hungarian_cost_fwd: NULL targets");
+  AMOE_REQUIRE(D >= 1 && D <= 16, "amoe_hungarian_cost_fwd: box dimension %d out of range", D);
   if (B == 0 || Q == 0 || Nmax == 0) return 0;
-  size_t smem = (size_t)MQ_TILE * C * sizeof(float);
-  AMOE_REQUIRE(smem <= 48 * 1024, "amoe_hungarian_cost_fwd: too many classes (%d)", C);
+  size_t smem = ((size_t)MQ_TILE * (C + D + 5) + (size_t)Nmax * (D + 6)) * sizeof(float);
+  AMOE_REQUIRE(smem <= 200 * 1024, "amoe_hungarian_cost_fwd: %d classes x %d targets do not fit in shared memory", C, Nmax);
+  if (smem > 48 * 1024)
+    AMOE_CHECK_CUDA(cudaFuncSetAttribute(hungarian_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(Q, MQ_TILE), B);
   hungarian_cost_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
       logits, boxes, tgt_boxes, tgt_labels, n_tgt, cost, Q, C, D, Nmax, w_class, w_bbox, w_giou);

@@ -135,6 +135,7 @@ __global__ __launch_bounds__(256) void mean_hw_nhwc_bf16_kernel(const __nv_bfloa
 
 extern "C" int amoe_mean_hw_nhwc_fwd(amoe_ctx* ctx, const void* x, float* out, int B, int HW, int C, int dtype,
                                      void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && out, "amoe_mean_hw_nhwc_fwd: NULL argument");
   AMOE_REQUIRE(dtype == AMOE_BF16 && C % 8 == 0 && HW >= 1, "amoe_mean_hw_nhwc_fwd: bf16 input with C %% 8 == 0 only (C=%d)", C);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "amoe_mean_hw_nhwc_fwd: x must be 16-byte aligned");
@@ -149,6 +150,7 @@ extern "C" int amoe_policy_head_fwd_ex(amoe_ctx* ctx, const void* x, const float
                                        int backbone_dim, int ctx_dim, int hidden, int horizon,
                                        int x_dtype, const void* params_bf16, float* waypoints, float* speed,
                                        void* stream) {
+  AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && x && params && waypoints && speed, "amoe_policy_head_fwd: NULL argument");
   AMOE_REQUIRE(ctx_dim == 0 || cvec, "amoe_policy_head_fwd: ctx is NULL but ctx_dim=%d", ctx_dim);
   PolicyDims d;
@@ -221,6 +223,7 @@ extern "C" int amoe_policy_head_fwd(amoe_ctx* ctx, const void* x, const float* c
                                     const float* params, int64_t n_params, int B, int HW, int Cf,
                                     int backbone_dim, int ctx_dim, int hidden, int horizon,
                                     int x_dtype, float* waypoints, float* speed, void* stream) {
+  AMOE_ENTER(ctx);
   return amoe_policy_head_fwd_ex(ctx, x, cvec, params, n_params, B, HW, Cf, backbone_dim, ctx_dim, hidden, horizon,
                                  x_dtype, nullptr, waypoints, speed, stream);
 }

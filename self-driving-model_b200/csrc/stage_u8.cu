@@ -139,7 +139,7 @@ extern "C" {
 int amoe_stage_u8_hwc_fwd(amoe_ctx* ctx, const void* src_u8, void* dst, int B, int H, int W, int left, int Wpad, int top,
                           int Hpad, const float* mean3_host, const float* std3_host, float pad_channel_value, void* stream) {
   AMOE_ENTER(ctx);
-  AMOE_REQUIRE(ctx && src_u8 && dst && mean3_host && std3_host, "amoe_stage_u8_hwc_fwd: NULL argument");
+  AMOE_REQUIRE(ctx && mean3_host && std3_host && (B == 0 || (src_u8 && dst)), "amoe_stage_u8_hwc_fwd: NULL argument");
   AMOE_REQUIRE(left >= 0 && Wpad >= left + W && top >= 0 && Hpad >= top + H && B >= 0 && H > 0 && W > 0,
                "amoe_stage_u8_hwc_fwd: bad geometry");
   for (int c = 0; c < 3; ++c) AMOE_REQUIRE(std3_host[c] != 0.f, "amoe_stage_u8_hwc_fwd: std[%d] is zero", c);
@@ -166,7 +166,7 @@ int amoe_stage_u8_hwc_fwd(amoe_ctx* ctx, const void* src_u8, void* dst, int B, i
 int amoe_normalize_u8_hwc_to_nchw_fwd(amoe_ctx* ctx, const void* src_u8, float* dst, int B, int H, int W,
                                       const float* mean3_host, const float* std3_host, void* stream) {
   AMOE_ENTER(ctx);
-  AMOE_REQUIRE(ctx && src_u8 && dst && mean3_host && std3_host, "amoe_normalize_u8_hwc_to_nchw_fwd: NULL argument");
+  AMOE_REQUIRE(ctx && mean3_host && std3_host && (B == 0 || (src_u8 && dst)), "amoe_normalize_u8_hwc_to_nchw_fwd: NULL argument");
   for (int c = 0; c < 3; ++c) AMOE_REQUIRE(std3_host[c] != 0.f, "amoe_normalize_u8_hwc_to_nchw_fwd: std[%d] is zero", c);
   const int64_t total = (int64_t)B * H * W;
   if (total == 0) return 0;
@@ -181,7 +181,7 @@ int amoe_normalize_u8_hwc_to_nchw_fwd(amoe_ctx* ctx, const void* src_u8, float* 
 int amoe_resample_u8_fwd(amoe_ctx* ctx, const void* src_u8, void* dst_u8, const int* bounds, const int* coeffs, int ksize,
                          int64_t outer, int in_size, int out_size, int inner, void* stream) {
   AMOE_ENTER(ctx);
-  AMOE_REQUIRE(ctx && src_u8 && dst_u8 && bounds && coeffs, "amoe_resample_u8_fwd: NULL argument");
+  AMOE_REQUIRE(ctx && bounds && coeffs && (outer == 0 || (src_u8 && dst_u8)), "amoe_resample_u8_fwd: NULL argument");
   AMOE_REQUIRE(ksize > 0 && in_size > 0 && out_size > 0 && inner > 0 && outer >= 0, "amoe_resample_u8_fwd: bad geometry");
   const int64_t total = outer * out_size * inner;
   if (total == 0) return 0;

@@ -598,6 +598,7 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
                                   const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
                                   int n_pool_ch, void* pooled, int out_pad, void* const* dst_host,
                                   const int* dst_c_host, void* stream) {
+  AMOE_ENTER(ctx);
   using namespace stem;
   AMOE_REQUIRE(ctx && pooled, "amoe_stem_pool_fwd: NULL argument");
   AMOE_REQUIRE(n_pool_ch % 64 == 0 && n_pool_ch >= 64 && n_pool_ch <= 192 && n_pool_ch <= n_total,
@@ -628,6 +629,7 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
 extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img, const float* scale,
                              const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
                              void* const* dst_host, const int* dst_c_host, void* stream) {
+  AMOE_ENTER(ctx);
   using namespace stem;
   AMOE_REQUIRE(ctx != nullptr, "amoe_stem_fwd: NULL ctx");
   AMOE_REQUIRE(scale != nullptr, "amoe_stem_fwd: folded filters (scale == NULL) are only taken by amoe_stem_pool_fwd");

@@ -24,8 +24,8 @@ from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
 from .experts._base import get_trunk_pack, run_experts
-from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, stage_image,
-                             trunk_pool_pad)
+from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, run_trunk_train,
+                             stage_image, trunk_pool_pad)
 from .experts.expert_extractors import create_expert_extractors
 from .gating.gating_network import GatingNetwork
 from .policy.trajectory_head import TrajectoryPolicy
@@ -172,12 +172,36 @@ class AutoMoE(nn.Module):
     def _trainable_part(self):
         return [self.context_extractor, self.expert_extractors, self.gating_network, self.policy_head]
 
+    # Reference train-mode semantics (training/train_gating_network.py:85 calls model.train() on the whole model):
+    # the frozen experts' BatchNorm layers then normalise with BATCH statistics and keep updating their running
+    # statistics, and every Dropout is active.  That is the default here too.  frozen_experts_eval = True is the
+    # explicit opt-out: frozen experts keep their running statistics and run through the (much faster) inference
+    # kernels - the numbers the reference gives after `model.experts.eval()`.
+    frozen_experts_eval = False
+
+    def _run_experts_train_mode(self, image: torch.Tensor):
+        """Frozen experts exactly as the reference runs them inside model.train(): batch-statistics BatchNorm with
+        running-stat updates (fp32 training kernels, no autograd graph).  Returns (expert_outputs, pooled, n_ch)."""
+        outs, pooled = [], []
+        H, W = image.shape[2], image.shape[3]
+        with torch.no_grad():
+            for e in self.experts:
+                low = run_trunk_train(e, image)                          # [B,h,w,N] NHWC fp32
+                out = e.format_output_train(low, H, W)
+                outs.append({k: v for k, v in out.items() if not k.startswith('_')} if isinstance(out, dict) else out)
+                h, w = low.shape[1], low.shape[2]
+                if e.upsample_to_input and (H % h != 0 or W % w != 0):
+                    pooled.append(_ops.mean_hw_nchw(out))                # non-integer scale: pool the full-resolution map
+                else:
+                    pooled.append(low.mean(dim=(1, 2)))                  # == mean of the x32 bilinear map (integer scale)
+        n_ch = [int(t.shape[1]) for t in pooled]
+        return outs, torch.cat(pooled, dim=1).contiguous(), n_ch
+
     def _forward_train(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Forward that records an autograd graph over the gating / policy parameters
-        (training/train_gating_network.py:96-100).  Experts must be frozen (freeze_experts()): they run
-        through the inference kernels under no_grad with their BatchNorm running statistics - the
-        reference's model.train() would silently switch the frozen experts to batch statistics and keep
-        mutating their running stats; call model.experts.eval() on the reference for the same numbers."""
+        (training/train_gating_network.py:96-100).  Experts must be frozen (freeze_experts()).  Experts in train
+        mode (what model.train() gives) follow the reference: batch-statistics BatchNorm + running-stat updates;
+        experts in eval mode, or frozen_experts_eval = True, run through the inference kernels with running statistics."""
         from ._train_forward import context_extractor_forward, extractor_forward, gating_forward, policy_forward
         if any(p.requires_grad for p in self.experts.parameters()):
             raise NotImplementedError("joint training of the experts (unfreeze_experts) is not implemented: "
@@ -185,14 +209,20 @@ class AutoMoE(nn.Module):
         image = batch['image']
         if not image.is_cuda:
             raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+        if image.dtype == torch.uint8:
+            image = _ops.normalize_u8_nchw(image, self.input_mean, self.input_std)
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
-        with torch.no_grad():
-            expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, frozen_eval=True)
+        if any(e.training for e in self.experts) and not self.frozen_experts_eval:
+            expert_outputs, pooled, n_ch = self._run_experts_train_mode(image)
+        else:
+            with torch.no_grad():
+                expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, frozen_eval=True)
+            pooled, n_ch = aux['pooled'], aux['n_ch']
         ctx = context_extractor_forward(self.context_extractor, state)
         feats, off = [], 0
-        for ext, n in zip(self.expert_extractors.extractors, aux['n_ch']):
-            feats.append(extractor_forward(ext, aux['pooled'][:, off:off + n].contiguous()))
+        for ext, n in zip(self.expert_extractors.extractors, n_ch):
+            feats.append(extractor_forward(ext, pooled[:, off:off + n].contiguous()))
             off += n
         g = gating_forward(self.gating_network, feats, ctx)
         pol = policy_forward(self.policy_head, image, g['combined_output'])

@@ -8,8 +8,10 @@ The reference model (models/automoe.py) and the reference's own compute_gating_l
 imports need tensorboard/dataloaders that are not part of the path) run one forward/backward on seeded
 synthetic weights, inputs and targets.  Stored: the seven loss values and, for EVERY trainable
 parameter, the gradient's L2 norm and its first 8 elements; full gradients of a few small tensors.
-Two cases: eval-mode semantics (Dropout off, BatchNorm running statistics) and train mode with
-Dropout p forced to 0 and the frozen experts kept in eval() (policy BatchNorm on batch statistics).
+Three cases: eval-mode semantics (Dropout off, BatchNorm running statistics); train mode with Dropout p forced
+to 0 and the frozen experts kept in eval() (policy BatchNorm on batch statistics); and the reference's actual
+train_one_epoch state - model.train() on everything, so the frozen experts' BatchNorm layers also run on batch
+statistics and update their running statistics (Dropout p forced to 0: its random stream is torch's own).
 """
 import ast
 import sys
@@ -48,14 +50,17 @@ def targets(B, horizon, seed):
     return torch.randn((B, horizon, 2), generator=g) * 5.0, torch.rand((B, horizon), generator=g) * 30.0
 
 
-def case(name, B, H, train_mode):
+def case(name, B, H, train_mode, experts_eval=True):
     torch.manual_seed(0)
     ref = ref_create(synth.CONFIG_3EXPERT, "cpu")
     ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), 0), strict=True)
     ref.freeze_experts()
     if train_mode:
         ref.train()
-        ref.experts.eval()                       # frozen experts: running statistics (see AutoMoE._forward_train)
+        if experts_eval:
+            ref.experts.eval()                   # frozen experts on running statistics (AutoMoE.frozen_experts_eval = True)
+        # else: the reference's actual train_one_epoch state (train_gating_network.py:85): the frozen experts'
+        # BatchNorm layers use batch statistics and update their running statistics
         for m in ref.modules():
             if isinstance(m, nn.Dropout):
                 m.p = 0.0
@@ -68,7 +73,7 @@ def case(name, B, H, train_mode):
     pred = ref(batch)
     losses = loss_fn(pred, wp, spd, cfg)
     losses["total_loss"].backward()
-    d = dict(versions=VERS, B=B, H=H, train_mode=train_mode,
+    d = dict(versions=VERS, B=B, H=H, train_mode=train_mode, experts_eval=experts_eval,
              losses=np.array([losses[k].item() for k in ("total_loss", "ade", "fde", "speed", "smoothness", "load_balancing", "entropy")],
                              dtype=np.float64),
              waypoints=pred["waypoints"].detach().numpy(), expert_weights=pred["expert_weights"].detach().numpy())
@@ -94,6 +99,14 @@ def case(name, B, H, train_mode):
         bn = ref.policy_head.backbone.net[1]
         d["bn1_running_mean"] = bn.running_mean.numpy()
         d["bn1_running_var"] = bn.running_var.numpy()
+        if not experts_eval:
+            sdr = ref.state_dict()
+            for k in ("experts.0.backbone.1.running_mean", "experts.0.backbone.1.running_var", "experts.1.backbone.5.0.downsample.1.running_var",
+                      "experts.2.backbone.7.1.bn2.running_mean", "experts.2.backbone.7.1.bn2.running_var"):
+                d["stat__" + k] = sdr[k].numpy()
+            d["expert_nbt"] = sdr["experts.1.backbone.4.0.bn1.num_batches_tracked"].numpy()
+            d["seg_mean"] = pred["expert_outputs"][1].detach().mean(dim=(2, 3)).numpy()
+            d["det_class_logits"] = pred["expert_outputs"][0]["class_logits"].detach().numpy()
     np.savez_compressed(OUT / f"{name}.npz", **d)
     print(name, "losses", d["losses"].round(5).tolist(), "n_trainable", len(names),
           "n_params", sum(p.numel() for p in ref.parameters() if p.requires_grad))
@@ -102,3 +115,4 @@ def case(name, B, H, train_mode):
 if __name__ == "__main__":
     case("train_eval_b4_64", 4, 64, False)
     case("train_trainmode_b4_64", 4, 64, True)
+    case("train_refmode_b4_128", 4, 128, True, experts_eval=False)     # model.train() exactly as train_one_epoch leaves it

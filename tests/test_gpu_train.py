@@ -217,25 +217,28 @@ def _targets(B, horizon, seed):
     return torch.randn((B, horizon, 2), generator=g) * 5.0, torch.rand((B, horizon), generator=g) * 30.0
 
 
-def _model_for_training(train_mode):
+def _model_for_training(train_mode, experts_eval=True):
     m, sd = build_b200_model(DEV, "fp32")
     m.freeze_experts()
     if train_mode:
         m.train()
+        if experts_eval:
+            m.experts.eval()      # what the reference gives after model.experts.eval(); model.train() alone = reference semantics
         for mod in m.modules():
             if isinstance(mod, nn.Dropout):
                 mod.p = 0.0
     return m, sd
 
 
-@pytest.mark.parametrize("name", ["train_eval_b4_64", "train_trainmode_b4_64"])
+@pytest.mark.parametrize("name", ["train_eval_b4_64", "train_trainmode_b4_64", "train_refmode_b4_128"])
 def test_training_step_matches_reference_golden(name, golden_dir):
     """loss values + gradients of all 82 trainable tensors (2,870,657 parameters) against the unmodified
     reference (eval semantics; train mode with Dropout p=0 and batch-statistics BatchNorm in the policy)."""
     from automoe_b200.training.train_gating_network import compute_gating_losses
     g = np.load(golden_dir / f"{name}.npz")
     B, H, train_mode = int(g["B"]), int(g["H"]), bool(g["train_mode"])
-    m, sd = _model_for_training(train_mode)
+    experts_eval = bool(g["experts_eval"]) if "experts_eval" in g.files else True
+    m, sd = _model_for_training(train_mode, experts_eval)
     batch = {k: v.to(DEV) for k, v in synth.synth_batch(B, H, H, seed=3, speed_seq=1).items()}
     wp, spd = _targets(B, 10, 4)
     pred = m(batch)
@@ -265,6 +268,15 @@ def test_training_step_matches_reference_golden(name, golden_dir):
     if train_mode:
         bn = m.policy_head.backbone.net[1]
         assert rel_err(bn.running_mean.cpu(), g["bn1_running_mean"]) < TOL and rel_err(bn.running_var.cpu(), g["bn1_running_var"]) < TOL
+    if not experts_eval:
+        # reference train-mode semantics: the frozen experts ran on batch statistics and updated their running statistics
+        sdm = m.state_dict()
+        for key in g.files:
+            if key.startswith("stat__"):
+                assert rel_err(sdm[key[6:]].cpu(), g[key]) < TOL, (key, rel_err(sdm[key[6:]].cpu(), g[key]))
+        assert int(sdm["experts.1.backbone.4.0.bn1.num_batches_tracked"]) == int(g["expert_nbt"])
+        assert rel_err(pred["expert_outputs"][1].mean(dim=(2, 3)).cpu(), g["seg_mean"]) < TOL
+        assert rel_err(pred["expert_outputs"][0]["class_logits"].cpu(), g["det_class_logits"]) < TOL
     print(name, "worst relative grad-norm error", worst)
 
 

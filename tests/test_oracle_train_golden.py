@@ -14,18 +14,19 @@ def _targets(B, horizon, seed):
     return torch.randn((B, horizon, 2), generator=g) * 5.0, torch.rand((B, horizon), generator=g) * 30.0
 
 
-def oracle_step(sd, batch, wp, spd, policy_batch_stats):
+def oracle_step(sd, batch, wp, spd, policy_batch_stats, expert_batch_stats=False):
     sd = {k: v.clone() for k, v in sd.items()}
     for k, v in sd.items():
         if GT.is_trainable_key(k) and v.is_floating_point():
             v.requires_grad_(True)
-    pred = GT.training_forward(sd, batch, synth.CONFIG_3EXPERT, policy_batch_stats=policy_batch_stats)
+    pred = GT.training_forward(sd, batch, synth.CONFIG_3EXPERT, policy_batch_stats=policy_batch_stats,
+                               expert_batch_stats=expert_batch_stats)
     losses = GT.compute_gating_losses(pred, wp, spd, {})
     losses["total_loss"].backward()
     return sd, pred, losses
 
 
-@pytest.mark.parametrize("name", ["train_eval_b4_64", "train_trainmode_b4_64"])
+@pytest.mark.parametrize("name", ["train_eval_b4_64", "train_trainmode_b4_64", "train_refmode_b4_128"])
 def test_training_oracle_matches_reference(name, golden_dir):
     from automoe_b200.models.automoe import create_automoe_model
     g = np.load(golden_dir / f"{name}.npz")
@@ -34,7 +35,11 @@ def test_training_oracle_matches_reference(name, golden_dir):
     sd0 = synth.synth_state_dict(template, 0)
     batch = synth.synth_batch(B, H, H, seed=3, speed_seq=1)
     wp, spd = _targets(B, 10, 4)
-    sd, pred, losses = oracle_step(sd0, batch, wp, spd, train_mode)
+    experts_eval = bool(g["experts_eval"]) if "experts_eval" in g.files else True
+    sd, pred, losses = oracle_step(sd0, batch, wp, spd, train_mode, expert_batch_stats=not experts_eval)
+    if not experts_eval:
+        assert rel_err(pred["expert_outputs"][1].mean(dim=(2, 3)), g["seg_mean"]) < 1e-5
+        assert rel_err(pred["expert_outputs"][0]["class_logits"], g["det_class_logits"]) < 1e-5
     got = np.array([losses[k].item() for k in ("total_loss", "ade", "fde", "speed", "smoothness", "load_balancing", "entropy")])
     assert np.allclose(got, g["losses"], rtol=2e-6, atol=1e-7), (got, g["losses"])
     assert rel_err(pred["waypoints"].detach(), g["waypoints"]) < 1e-5
