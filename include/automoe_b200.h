@@ -227,6 +227,19 @@ int amoe_gate_fwd_ex(amoe_ctx*, const float* state, const float* pooled, const f
                      int ctx_dim, int hidden, float temperature, int mode, float* context,
                      float* features, float* processed, float* gate_logits, float* weights,
                      float* combined, void* stream);
+/* Same with features computed OUTSIDE the kernel for the experts whose n_ch_host[e] == 0: ext_features [E][B][256] fp32
+ * (only the blocks of those experts are read).  Used for extractors whose input vector does not fit the kernel's
+ * shared-memory rows - NuScenesExpertExtractor, Linear(Q*(C+D), 512) on the flattened queries
+ * (models/experts/expert_extractors.py:108-137); their slot of the parameter layout holds a zero-width first layer. */
+int amoe_gate_fwd_ex2(amoe_ctx*, const float* state, const float* pooled, const float* params,
+                      const void* params_bf16, int64_t n_params, int B, int E, const int* n_ch_host,
+                      int ctx_dim, int hidden, float temperature, int mode, const float* ext_features,
+                      float* context, float* features, float* processed, float* gate_logits,
+                      float* weights, float* combined, void* stream);
+/* y[b][q][:] = max(a[b][:] + c[q][:], 0), fp32, D % 4 == 0 (first decoder layer of the nuScenes multi-query head,
+ * models/experts/nuscenes_expert.py:172-180, split into its per-frame and per-query halves). */
+int amoe_bcast_add_relu(amoe_ctx*, const float* a, const float* c, float* y, int B, int Q, int D,
+                        void* stream);
 
 /* ---- policy head ------------------------------------------------------- */
 /* EasyBackbone pool+fc and both TrajectoryPolicy MLP heads

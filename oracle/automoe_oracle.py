@@ -86,6 +86,26 @@ def run_expert(x, sd, p, cfg):
     return F.interpolate(low, size=x.shape[-2:], mode="bilinear", align_corners=False)
 
 
+def nuscenes_expert(image, sd, p, cfg):
+    """NuScenesExpert.forward, image-only (models/experts/nuscenes_expert.py:150-190): resnet18 children()[:-1]
+    (trunk + AdaptiveAvgPool2d(1)) -> Linear(512,256) -> + query_embed -> decoder (eval: Dropout = identity) -> heads."""
+    feat = resnet18_trunk(image, sd, p + ".image_backbone").mean(dim=(2, 3))
+    img = _linear(feat.to(sd[p + ".image_projection.weight"].dtype), sd, p + ".image_projection")      # [B,256]
+    x = img.unsqueeze(1) + sd[p + ".query_embed.weight"].unsqueeze(0)                                   # [B,Q,256]
+    x = F.relu(_linear(x, sd, p + ".decoder.0"))
+    x = F.relu(_linear(x, sd, p + ".decoder.3"))
+    return {"class_logits": _linear(x, sd, p + ".class_head"), "bbox_preds": _linear(x, sd, p + ".bbox_head")}
+
+
+def nuscenes_extractor(expert_output, sd, p):
+    """NuScenesExpertExtractor.forward (expert_extractors.py:125-137)."""
+    flat = torch.cat([expert_output["class_logits"], expert_output["bbox_preds"]], dim=-1)
+    flat = flat.reshape(flat.size(0), -1).to(sd[p + ".feature_extractor.0.weight"].dtype)
+    v = F.relu(_linear(flat, sd, p + ".feature_extractor.0"))
+    v = _linear(v, sd, p + ".feature_extractor.3")
+    return _ln(v, sd, p + ".feature_extractor.4")
+
+
 def extractor(expert_output, sd, p, cfg):
     """Detection/Segmentation/DrivableExpertExtractor.forward (expert_extractors.py:37-52,71-79,98-106):
     AdaptiveAvgPool2d(1) -> Flatten -> Linear -> ReLU -> Dropout(eval: id) -> Linear -> LayerNorm."""
@@ -173,11 +193,13 @@ def policy_head(image, context, sd, p="policy_head", horizon=10):
 
 
 def automoe_forward(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], config: Dict) -> Dict:
-    """AutoMoE.forward (automoe.py:189-233) for the 3-expert configuration."""
+    """AutoMoE.forward (automoe.py:189-233); experts of type detection / segmentation / drivable / nuscenes (image-only)."""
     image = batch["image"]
     ctx = context_extractor(vehicle_state(batch), sd)
-    expert_outputs = [run_expert(image, sd, f"experts.{i}", c) for i, c in enumerate(config["experts"])]
-    feats = [extractor(o, sd, f"expert_extractors.extractors.{i}", c)
+    expert_outputs = [(nuscenes_expert if c["type"] == "nuscenes" else run_expert)(image, sd, f"experts.{i}", c)
+                      for i, c in enumerate(config["experts"])]
+    feats = [nuscenes_extractor(o, sd, f"expert_extractors.extractors.{i}") if c["type"] == "nuscenes"
+             else extractor(o, sd, f"expert_extractors.extractors.{i}", c)
              for i, (o, c) in enumerate(zip(expert_outputs, config["experts"]))]
     g = gating_network(feats, ctx, sd, temperature=config["gating"].get("temperature", 1.0),
                        use_softmax=config["gating"].get("use_softmax", True))

@@ -19,6 +19,19 @@ CONFIG_3EXPERT = {
 }
 
 
+# the shipped models/configs/automoe/model_config.json: the three BDD experts + the image-only nuScenes expert
+# (pretrained_backbone false: no network; gating keys top_k / noise_* are not forwarded by AutoMoE, automoe.py:83-91)
+CONFIG_4EXPERT = {
+    "experts": CONFIG_3EXPERT["experts"] + [
+        {"type": "nuscenes", "num_queries": 196, "num_classes": 10, "output_dim": 256, "fusion": "sum", "use_lidar": False,
+         "use_tnet": False, "bbox_dim": 4, "pretrained_backbone": False},
+    ],
+    "gating": dict(CONFIG_3EXPERT["gating"], top_k=2, noise_type="gumbel", noise_scale=0.0, apply_topk_at_eval=True),
+    "context": CONFIG_3EXPERT["context"],
+    "policy": CONFIG_3EXPERT["policy"],
+}
+
+
 def synth_state_dict(template: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, torch.Tensor]:
     """Fill a state_dict (shapes/keys taken from `template`) deterministically, key by key:
     conv: N(0, sqrt(2/fan_out)); linear weight: U(+-1/sqrt(fan_in)); biases: N(0,0.05);

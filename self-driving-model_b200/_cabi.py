@@ -54,6 +54,8 @@ SIGNATURES = {
     "amoe_mean_hw_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_gate_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I] + [_P] * 7),
     "amoe_gate_fwd_ex": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I] + [_P] * 7),
+    "amoe_gate_fwd_ex2": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, C.POINTER(_I), _I, _I, _F, _I, _P] + [_P] * 7),
+    "amoe_bcast_add_relu": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "amoe_policy_head_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "amoe_policy_head_fwd_ex": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "amoe_mean_hw_nhwc_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

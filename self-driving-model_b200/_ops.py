@@ -525,9 +525,10 @@ def mean_hw_nchw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0, params_bf16=None):
+def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0, params_bf16=None, ext_features=None):
     """Fused context extractor + expert extractors + gating network (gate.cu).
-    params_bf16: bf16 copy of `params` -> tensor-core (TF32) variant for bf16 inference at B >= 16."""
+    params_bf16: bf16 copy of `params` -> tensor-core (TF32) variant for bf16 inference at B >= 16.
+    ext_features: [E,B,256] fp32 - features computed outside the kernel for the experts whose n_ch entry is 0."""
     dev = state.device
     B, E = state.shape[0], len(n_ch)
     f32 = dict(device=dev, dtype=torch.float32)
@@ -543,9 +544,11 @@ def gate(state, pooled, params, n_ch, ctx_dim, hidden, temperature, mode=0, para
     arr = (C.c_int * E)(*n_ch)
     if params_bf16 is not None:
         assert params_bf16.dtype == torch.bfloat16 and params_bf16.numel() == params.numel()
-    check(lib().amoe_gate_fwd_ex(ctx(dev), ptr(state), ptr(pooled), ptr(params), ptr(params_bf16), params.numel(), B, E,
-                                 arr, ctx_dim, hidden, float(temperature), mode, ptr(context), ptr(features),
-                                 ptr(processed), ptr(logits), ptr(weights), ptr(combined), stream_ptr(dev)), "gate_fwd")
+    if ext_features is not None:
+        assert ext_features.dtype == torch.float32 and tuple(ext_features.shape) == (E, B, 256) and ext_features.is_contiguous()
+    check(lib().amoe_gate_fwd_ex2(ctx(dev), ptr(state), ptr(pooled), ptr(params), ptr(params_bf16), params.numel(), B, E,
+                                  arr, ctx_dim, hidden, float(temperature), mode, ptr(ext_features), ptr(context), ptr(features),
+                                  ptr(processed), ptr(logits), ptr(weights), ptr(combined), stream_ptr(dev)), "gate_fwd")
     return dict(context=context, features=features, processed=processed, gate_logits=logits, weights=weights,
                 combined=combined)
 

@@ -61,7 +61,7 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
     const float* __restrict__ prm, const __nv_bfloat16* __restrict__ prm16, float* __restrict__ context,
     float* __restrict__ features,
     float* __restrict__ processed, float* __restrict__ gate_logits, float* __restrict__ weights,
-    float* __restrict__ combined) {
+    float* __restrict__ combined, const float* __restrict__ ext_feat) {
   extern __shared__ __align__(16) float sm[];
   // Tensor-core variant, d.split: the weight stream per CTA bounds this kernel and the E expert chains (extractor +
   // processor, 3/4 of the parameters) are independent, so a cluster of E+1 CTAs owns the 16 frames: rank e < E runs
@@ -172,12 +172,16 @@ __global__ __launch_bounds__(GATE_THREADS) void gate_fused_kernel(
       continue;
     }
     if (!ctx_only) {
-      if (feat_in) {
+      if (feat_in || d.n_ch[e] == 0) {
+        // feature of this expert computed outside (all of them: GATE_MODE_FEAT_IN; or this one only: n_ch[e] == 0, an
+        // extractor whose input does not fit this kernel's shared-memory rows, e.g. the nuScenes expert's Q*(C+D) vector)
+        const float* src = feat_in ? pooled : ext_feat;
         for (int i = threadIdx.x; i < FT * d.F; i += blockDim.x) {
           int f = i / d.F, c = i - f * d.F;
-          s_feat[f * ld_feat + c] = (f0 + f < d.B) ? pooled[((int64_t)e * d.B + f0 + f) * d.F + c] : 0.f;
+          s_feat[f * ld_feat + c] = (f0 + f < d.B) ? src[((int64_t)e * d.B + f0 + f) * d.F + c] : 0.f;
         }
         __syncthreads();   // CTA-local phase (every rank works on its own copy)
+        if (!feat_in && features) store_rows<FT, CL>(features + (int64_t)e * d.B * d.F, d.F, s_feat, ld_feat, d.F, f0, d.B);
       } else {
         linear_ft<FT, CL, TC>(W1, b1, s_in + ch_off, ld_in, d.n_ch[e], s_h, ld_h, EXT_HID, true, w16(W1));
         linear_ft<FT, CL, TC>(W2, b2, s_h, ld_h, EXT_HID, s_feat, ld_feat, d.F, false, w16(W2));
@@ -275,11 +279,11 @@ static int64_t gate_param_count(const GateDims& d) {
   return n;
 }
 
-extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* pooled,
-                                const float* params, const void* params_bf16, int64_t n_params, int B, int E,
-                             const int* n_ch_host, int ctx_dim, int hidden, float temperature,
-                             int mode, float* context, float* features, float* processed,
-                             float* gate_logits, float* weights, float* combined, void* stream) {
+extern "C" int amoe_gate_fwd_ex2(amoe_ctx* ctx, const float* state, const float* pooled,
+                                 const float* params, const void* params_bf16, int64_t n_params, int B, int E,
+                                 const int* n_ch_host, int ctx_dim, int hidden, float temperature,
+                                 int mode, const float* ext_features, float* context, float* features, float* processed,
+                                 float* gate_logits, float* weights, float* combined, void* stream) {
   AMOE_ENTER(ctx);
   AMOE_REQUIRE(ctx && state && params && n_ch_host, "amoe_gate_fwd: NULL argument");
   AMOE_REQUIRE(E >= 1 && E <= GATE_MAX_E, "amoe_gate_fwd: E=%d out of range [1,%d]", E, GATE_MAX_E);
@@ -290,7 +294,8 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
   d.temperature = temperature; d.mode = mode; d.sumC = 0; d.split = 0;
   for (int e = 0; e < GATE_MAX_E; ++e) d.n_ch[e] = 0;
   for (int e = 0; e < E; ++e) {
-    AMOE_REQUIRE(n_ch_host[e] >= 1, "amoe_gate_fwd: n_ch[%d]=%d", e, n_ch_host[e]);
+    AMOE_REQUIRE(n_ch_host[e] >= 1 || (n_ch_host[e] == 0 && ext_features != nullptr),
+                 "amoe_gate_fwd: n_ch[%d]=%d (0 = feature supplied in ext_features)", e, n_ch_host[e]);
     d.n_ch[e] = n_ch_host[e];
     d.sumC += n_ch_host[e];
   }
@@ -309,7 +314,7 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
     auto kern = gate_fused_kernel<MMA_FT, false, true>;
     AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char* e = getenv("AMOE_GATE_SPLIT");
-    d.split = ((mode & ~GATE_MODE_SIGMOID) == 0 && hidden % 4 == 0 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
+    d.split = ((mode & ~GATE_MODE_SIGMOID) == 0 && E <= 3 && hidden % 4 == 0 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
     if (d.split) {
       // the forward of AutoMoE: clusters of E+1 CTAs per 16 frames (expert chains and the context path in parallel)
       cudaLaunchConfig_t cfg = {};
@@ -323,10 +328,10 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, p16, context, features, processed, gate_logits,
-                                         weights, combined));
+                                         weights, combined, ext_features));
     } else {
       kern<<<ceil_div(B, MMA_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
-          d, state, pooled, params, p16, context, features, processed, gate_logits, weights, combined);
+          d, state, pooled, params, p16, context, features, processed, gate_logits, weights, combined, ext_features);
     }
     AMOE_LAUNCH_OK(ctx);
     return 0;
@@ -348,7 +353,7 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     AMOE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, state, pooled, params, (const __nv_bfloat16*)nullptr, context, features, processed, gate_logits,
-                                       weights, combined));
+                                       weights, combined, ext_features));
     AMOE_LAUNCH_OK(ctx);
     return 0;
   }
@@ -356,9 +361,18 @@ extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* 
   auto kern = gate_fused_kernel<GATE_FT, false, false>;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<ceil_div(B, GATE_FT), GATE_THREADS, smem, (cudaStream_t)stream>>>(
-      d, state, pooled, params, (const __nv_bfloat16*)nullptr, context, features, processed, gate_logits, weights, combined);
+      d, state, pooled, params, (const __nv_bfloat16*)nullptr, context, features, processed, gate_logits, weights, combined, ext_features);
   AMOE_LAUNCH_OK(ctx);
   return 0;
+}
+
+extern "C" int amoe_gate_fwd_ex(amoe_ctx* ctx, const float* state, const float* pooled,
+                                const float* params, const void* params_bf16, int64_t n_params, int B, int E,
+                                const int* n_ch_host, int ctx_dim, int hidden, float temperature,
+                                int mode, float* context, float* features, float* processed,
+                                float* gate_logits, float* weights, float* combined, void* stream) {
+  return amoe_gate_fwd_ex2(ctx, state, pooled, params, params_bf16, n_params, B, E, n_ch_host, ctx_dim, hidden, temperature, mode,
+                           nullptr, context, features, processed, gate_logits, weights, combined, stream);
 }
 
 extern "C" int amoe_gate_fwd(amoe_ctx* ctx, const float* state, const float* pooled,

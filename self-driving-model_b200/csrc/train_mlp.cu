@@ -453,9 +453,37 @@ int launch_sgemm(amoe_ctx* ctx, const float* A, const float* B, float* C, int M,
   return 0;
 }
 
+// y[b][q][:] = max(a[b][:] + c[q][:], 0): first decoder layer of the nuScenes multi-query head - Linear(h0[b] + E[q])
+// split into W h0[b] (per frame) + (W E[q] + bias) (per query, constant), models/experts/nuscenes_expert.py:172-180
+__global__ void bcast_add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ c, float4* __restrict__ y, int Q,
+                                      int D4, int64_t total4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D4);
+    const int64_t r = i / D4;
+    const int q = (int)(r % Q);
+    const int64_t b = r / Q;
+    const float4 u = __ldg(a + b * D4 + d), v = __ldg(c + (int64_t)q * D4 + d);
+    y[i] = make_float4(fmaxf(u.x + v.x, 0.f), fmaxf(u.y + v.y, 0.f), fmaxf(u.z + v.z, 0.f), fmaxf(u.w + v.w, 0.f));
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int amoe_bcast_add_relu(amoe_ctx* ctx, const float* a, const float* c, float* y, int B, int Q, int D, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && a && c && y, "amoe_bcast_add_relu: NULL argument");
+  AMOE_REQUIRE(D % 4 == 0 && D > 0 && Q > 0 && B >= 0, "amoe_bcast_add_relu: D must be a positive multiple of 4");
+  const int64_t total4 = (int64_t)B * Q * (D / 4);
+  if (total4 == 0) return 0;
+  const int64_t want = (total4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < (int64_t)ctx->sm_count * 16 ? want : (int64_t)ctx->sm_count * 16);
+  bcast_add_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)c, (float4*)y, Q, D / 4, total4);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
 
 int amoe_linear_fwd(amoe_ctx* ctx, const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int B,
                     int in_dim, int out_dim, int relu, float drop_p, uint64_t seed, void* stream) {

@@ -26,7 +26,10 @@ def gate_param_tensors(context_extractor, extractors: Optional[list], gating, n_
     else:
         t += [_z(32, 4), _z(32), _z(ctx_dim, 32), _z(ctx_dim), _z(ctx_dim), _z(ctx_dim)]
     for e in range(E):
-        if extractors is not None:
+        if n_ch[e] == 0:
+            # feature supplied from outside the kernel (amoe_gate_fwd_ex2): zero-width first layer, the rest unused
+            t += [_z(EXT_HID, 0), _z(EXT_HID), _z(FEAT, EXT_HID), _z(FEAT), _z(FEAT), _z(FEAT)]
+        elif extractors is not None:
             lin = [m for m in extractors[e].feature_extractor if isinstance(m, torch.nn.Linear)]
             ln = [m for m in extractors[e].feature_extractor if isinstance(m, torch.nn.LayerNorm)][0]
             if lin[0].weight.shape != (EXT_HID, n_ch[e]) or lin[1].weight.shape != (FEAT, EXT_HID):

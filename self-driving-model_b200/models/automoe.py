@@ -22,8 +22,8 @@ from .. import _ops
 from ._gatepack import pack_gate_params, require_eval
 from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
-from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert
-from .experts._base import get_trunk_pack, run_experts
+from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert, NuScenesExpert
+from .experts._base import BDDExpertBase, get_trunk_pack, run_experts
 from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, run_trunk_train,
                              stage_image, trunk_pool_pad)
 from .experts.expert_extractors import create_expert_extractors
@@ -67,7 +67,10 @@ class AutoMoE(nn.Module):
                 expert = BDDDrivableExpert(num_classes=config.get('num_classes', 3),
                                            pretrained_backbone=config.get('pretrained_backbone', True))
             elif expert_type == 'nuscenes':
-                raise NotImplementedError("the nuScenes expert is not part of the B200 hot path yet (SURVEY.md §8f)")
+                expert = NuScenesExpert(num_queries=config.get('num_queries', 100), fusion=config.get('fusion', 'concat'),
+                                        use_lidar=config.get('use_lidar', False), use_tnet=config.get('use_tnet', False),
+                                        bbox_dim=config.get('bbox_dim', 7),
+                                        pretrained_backbone=config.get('pretrained_backbone', True))
             else:
                 raise ValueError(f"Unknown expert type: {expert_type}")
             experts.append(expert)
@@ -132,13 +135,14 @@ class AutoMoE(nn.Module):
 
     def _fused_stem(self, device):
         """PackedStem of [expert stems..., policy conv1] (cached; re-packed when any of them changes)."""
-        mods = [e.backbone[0] for e in self.experts] + [e.backbone[1] for e in self.experts] + \
+        bdd = self._bdd_experts()
+        mods = [e.backbone[0] for e in bdd] + [e.backbone[1] for e in bdd] + \
                [self.policy_head.backbone.net[0], self.policy_head.backbone.net[1]]
         stamp = params_stamp(mods)
         c = self._gate_flat.get(("stem", device.index))
         if c is None or c[0] != stamp:
-            convs = [e.backbone[0] for e in self.experts] + [self.policy_head.backbone.net[0]]
-            bns = [e.backbone[1] for e in self.experts] + [self.policy_head.backbone.net[1]]
+            convs = [e.backbone[0] for e in bdd] + [self.policy_head.backbone.net[0]]
+            bns = [e.backbone[1] for e in bdd] + [self.policy_head.backbone.net[1]]
             c = (stamp, _ops.pack_stem(convs, bns, device, relu=True))
             self._gate_flat[("stem", device.index)] = c
         return c[1]
@@ -158,6 +162,31 @@ class AutoMoE(nn.Module):
         image = _ops.normalize_u8_nchw(frames, self.input_mean, self.input_std)
         return image, stage_image(image, dtype)
 
+    def _bdd_experts(self):
+        """The experts that share the grouped ResNet-18 + 2-conv-head launches (detection / segmentation / drivable)."""
+        return [e for e in self.experts if isinstance(e, BDDExpertBase)]
+
+    def _other_expert_features(self, image, dtype, x_nhwc, expert_outputs, n_ch_bdd):
+        """Experts outside the grouped launches (nuScenes): run them, return (expert_outputs in config order, n_ch per expert
+        with 0 for externally extracted features, ext_features [E,B,256] or None)."""
+        E = len(self.experts)
+        if len(expert_outputs) == E:
+            return expert_outputs, n_ch_bdd, None
+        outs, n_ch, bdd_i = [], [], 0
+        ext = torch.zeros((E, image.shape[0], 256), device=image.device, dtype=torch.float32)
+        for i, e in enumerate(self.experts):
+            if isinstance(e, BDDExpertBase):
+                outs.append(expert_outputs[bdd_i])
+                n_ch.append(n_ch_bdd[bdd_i])
+                bdd_i += 1
+            else:
+                out = e({'image': image}, _x_nhwc=x_nhwc, _dtype=dtype)
+                with torch.no_grad():
+                    ext[i] = self.expert_extractors.extractors[i](out)
+                outs.append({k: v for k, v in out.items() if not k.startswith('_')})
+                n_ch.append(0)
+        return outs, n_ch, ext
+
     def _extract_context_features(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         state = self._vehicle_state(batch)
         return self.context_extractor(state[:, 0:1], state[:, 1:2], state[:, 2:3], state[:, 3:4])
@@ -165,8 +194,9 @@ class AutoMoE(nn.Module):
     def _run_experts(self, batch: Dict[str, torch.Tensor]) -> List:
         """All experts on batch['image'] in grouped launches.  Unlike the reference
         (automoe.py:181-185) an expert failure raises instead of being masked by zeros."""
-        outs, _ = run_experts(list(self.experts), batch['image'], resolve_dtype(self.precision), self._expert_packs)
-        return outs
+        dtype = resolve_dtype(self.precision)
+        outs, aux = run_experts(self._bdd_experts(), batch['image'], dtype, self._expert_packs)
+        return self._other_expert_features(batch['image'], dtype, None, outs, aux['n_ch'])[0]
 
     # ------------------------------------------------------------------ forward
     def _trainable_part(self):
@@ -185,7 +215,7 @@ class AutoMoE(nn.Module):
         outs, pooled = [], []
         H, W = image.shape[2], image.shape[3]
         with torch.no_grad():
-            for e in self.experts:
+            for e in self._bdd_experts():
                 low = run_trunk_train(e, image)                          # [B,h,w,N] NHWC fp32
                 out = e.format_output_train(low, H, W)
                 outs.append({k: v for k, v in out.items() if not k.startswith('_')} if isinstance(out, dict) else out)
@@ -213,17 +243,34 @@ class AutoMoE(nn.Module):
             image = _ops.normalize_u8_nchw(image, self.input_mean, self.input_std)
         dtype = resolve_dtype(self.precision)
         state = self._vehicle_state(batch).to(image.device)
-        if any(e.training for e in self.experts) and not self.frozen_experts_eval:
+        ref_mode = any(e.training for e in self.experts) and not self.frozen_experts_eval
+        if ref_mode:
             expert_outputs, pooled, n_ch = self._run_experts_train_mode(image)
         else:
             with torch.no_grad():
-                expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, frozen_eval=True)
+                expert_outputs, aux = run_experts(self._bdd_experts(), image, dtype, self._expert_packs, frozen_eval=True)
             pooled, n_ch = aux['pooled'], aux['n_ch']
         ctx = context_extractor_forward(self.context_extractor, state)
-        feats, off = [], 0
-        for ext, n in zip(self.expert_extractors.extractors, n_ch):
-            feats.append(extractor_forward(ext, pooled[:, off:off + n].contiguous()))
-            off += n
+        feats, off, bdd_i, outs_all = [], 0, 0, []
+        for e, ext in zip(self.experts, self.expert_extractors.extractors):
+            if isinstance(e, BDDExpertBase):
+                n = n_ch[bdd_i]
+                feats.append(extractor_forward(ext, pooled[:, off:off + n].contiguous()))
+                outs_all.append(expert_outputs[bdd_i])
+                off += n
+                bdd_i += 1
+            else:
+                # nuScenes expert: frozen; in train mode it follows the reference (batch-statistics BatchNorm, active Dropout)
+                was = e.training
+                if not ref_mode:
+                    e.eval()
+                try:
+                    out = e({'image': image}, _dtype=dtype)
+                finally:
+                    e.train(was)
+                feats.append(ext(out))                    # differentiable extractor (training/functional.py shims)
+                outs_all.append({k: v for k, v in out.items() if not k.startswith('_')})
+        expert_outputs = outs_all
         g = gating_forward(self.gating_network, feats, ctx)
         pol = policy_forward(self.policy_head, image, g['combined_output'])
         speed_seq = pol['speed']
@@ -262,27 +309,29 @@ class AutoMoE(nn.Module):
             # (+ the experts' max-pool fused behind it when the geometry allows)
             fs = self._fused_stem(image.device)
             Bn, Hn, Wn = image.shape[0], image.shape[2], image.shape[3]
-            tp = get_trunk_pack(list(self.experts), dtype, image.device, self._expert_packs)
+            bdd = self._bdd_experts()
+            tp = get_trunk_pack(bdd, dtype, image.device, self._expert_packs)
             if chunked_stem_layer1_supported(tp, Bn, Hn, Wn):
                 # stem+pool and layer1 walk the batch in L2-resident chunks (policy conv1 rides along)
                 pol1 = torch.empty((Bn, Hn // 2, Wn // 2, fs.couts[-1]), device=image.device, dtype=torch.bfloat16)
                 layer1 = run_stem_layer1_chunked(tp, fs, x_nhwc, Bn, Hn, Wn, rest_out=[pol1])
             elif _ops.stem_pool_supported(Hn, Wn):
-                pooled, rest = _ops.stem_pool_forward(fs, x_nhwc, Bn, Hn, Wn, len(self.experts),
+                pooled, rest = _ops.stem_pool_forward(fs, x_nhwc, Bn, Hn, Wn, len(bdd),
                                                       trunk_pool_pad(tp, Hn, Wn))
                 pol1 = rest[0]
             else:
-                stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, Bn, Hn, Wn, groups=[len(self.experts), 1])
+                stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, Bn, Hn, Wn, groups=[len(bdd), 1])
 
-        expert_outputs, aux = run_experts(list(self.experts), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
+        expert_outputs, aux = run_experts(self._bdd_experts(), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
                                           stem_out=stem_out, stem_pooled=pooled, layer1_out=layer1,
                                           overlap_outputs=_ops.overlap_outputs())
+        expert_outputs, n_ch, ext = self._other_expert_features(image, dtype, x_nhwc, expert_outputs, aux['n_ch'])
 
         gn = self.gating_network
-        gflat, gflat16 = self._gate_params(image.device, aux['n_ch'], bf16_copy=True)
-        g = _ops.gate(state, aux['pooled'], gflat, aux['n_ch'],
+        gflat, gflat16 = self._gate_params(image.device, n_ch, bf16_copy=True)
+        g = _ops.gate(state, aux['pooled'], gflat, n_ch,
                       self.context_extractor.context_dim, gn.hidden_dim, gn.temperature, mode=gn._gate_kind(),
-                      params_bf16=gflat16 if _ops.mlp_tc(dtype) else None)
+                      params_bf16=gflat16 if _ops.mlp_tc(dtype) else None, ext_features=ext)
 
         policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)
         if aux.get('join') is not None:      # full-resolution logits were written on the side stream

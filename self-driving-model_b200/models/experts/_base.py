@@ -60,12 +60,12 @@ def _check_eval(experts):
                 "train-mode (batch-statistics) BatchNorm is not implemented yet - call .eval() on the experts")
 
 
-def get_trunk_pack(experts, dtype, device, cache: dict) -> TrunkPack:
+def get_trunk_pack(experts, dtype, device, cache: dict, with_head: bool = True) -> TrunkPack:
     stamp = params_stamp(experts)
     key = (dtype, device.index)
     pack: TrunkPack = cache.get(key)
     if pack is None or pack.stamp != stamp:
-        pack = pack_trunks(experts, [e.head_module() for e in experts], dtype, device)
+        pack = pack_trunks(experts, [e.head_module() for e in experts] if with_head else None, dtype, device)
         cache[key] = pack
     return pack
 

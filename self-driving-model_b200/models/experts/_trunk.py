@@ -106,7 +106,8 @@ def params_stamp(modules) -> tuple:
 
 
 def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
-    """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads."""
+    """experts: list of modules with .backbone (ParamHolder trunk); heads: their 2-conv heads, or None for a
+    trunk-only pack (the nuScenes expert pools the trunk output instead)."""
     G = len(experts)
     bbs = [e.backbone for e in experts]
     blocks = []
@@ -120,6 +121,9 @@ def pack_trunks(experts, heads, dtype: torch.dtype, device) -> TrunkPack:
                 dn = _ops.pack_conv([b.downsample[0] for b in blks], [b.downsample[1] for b in blks], dtype, device,
                                     relu=False)
             blocks.append((c1, c2, dn))
+    if heads is None:
+        return TrunkPack(dtype, G, {}, ([bb[0] for bb in bbs], [bb[1] for bb in bbs], device), blocks, None, [], [], [],
+                         params_stamp(list(experts)))
     head3 = _ops.pack_conv([h[0] for h in heads], None, dtype, device, relu=True)
     w1 = [h[2].weight.detach().to(device=device, dtype=torch.float32).reshape(h[2].weight.shape[0], -1).contiguous()
           for h in heads]
@@ -143,7 +147,7 @@ def stem_pack(pack: TrunkPack, mode: str):
     return st
 
 
-def run_trunk_train(expert, image: torch.Tensor) -> torch.Tensor:
+def run_trunk_train(expert, image: torch.Tensor, with_head: bool = True) -> torch.Tensor:
     """Differentiable forward of ONE expert (ResNet-18 trunk + 2-conv head) for expert training
     (training/train_bdd100k_ddp.py:117-186): fp32 NHWC, every layer an autograd shim over
     the sm_100a training kernels (training/functional.py).  BatchNorm follows module.training (batch
@@ -163,6 +167,8 @@ def run_trunk_train(expert, image: torch.Tensor) -> torch.Tensor:
             out = TF.conv_bn_act(out, blk.conv2, blk.bn2, relu=False)
             idn = y if blk.downsample is None else TF.conv_bn_act(y, blk.downsample[0], blk.downsample[1], relu=False)
             y = TF.add_relu(out, idn)
+    if not with_head:
+        return y                                                          # [B,h,w,512] trunk output
     head = expert.head_module()
     h = TF.conv_bn_act(y, head[0], None, relu=True)
     return TF.conv_bn_act(h, head[2], None, relu=False)
@@ -238,7 +244,7 @@ def run_stem_layer1_chunked(pack: TrunkPack, fused_stem, x_nhwc: torch.Tensor, B
 
 def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None,
                stem_out: Optional[torch.Tensor] = None, stem_pooled: Optional[torch.Tensor] = None,
-               layer1_out: Optional[torch.Tensor] = None):
+               layer1_out: Optional[torch.Tensor] = None, features_only: bool = False):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
 
     Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
@@ -298,6 +304,8 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
             y = _ops.conv2d(c2, out, B, h_out, w_out, residual=identity)
         h_cur, w_cur, pad = h_out, w_out, pad_out
     h, w = y.shape[1], y.shape[2]
+    if features_only:
+        return y                                                         # [G*B,h,w,512] (layer4 is never stored padded)
     hid = _ops.conv2d(pack.head3, y, B, h, w)                            # [G*B,h,w,256]
     pooled = torch.empty((B, sum(pack.n_ch)), device=image.device, dtype=torch.float32)
     lows, off = [], 0

@@ -86,6 +86,43 @@ class DrivableExpertExtractor(ExpertOutputExtractor):
         self.feature_extractor = self._make_mlp(num_classes, output_dim)
 
 
+class NuScenesExpertExtractor(ExpertOutputExtractor):
+    """Extracts features from nuScenes expert outputs (expert_extractors.py:108-137): cat(class_logits, bbox_preds) ->
+    flatten [B, Q*(C+bbox_dim)] -> Linear(.,512)+ReLU+Dropout -> Linear(512,out) -> LayerNorm.  The 2,744-wide input does not
+    fit the fused gate kernel's shared-memory rows, so this extractor runs as two GEMM launches + one LayerNorm launch and
+    hands its feature to the gate kernel (amoe_gate_fwd_ex2, n_ch = 0)."""
+
+    def __init__(self, output_dim: int = 256, num_queries: int = 100, num_classes: int = 10, bbox_dim: int = 7):
+        super().__init__(output_dim)
+        self.num_queries = num_queries
+        self.num_classes = num_classes
+        self.bbox_dim = bbox_dim
+        self.feature_extractor = nn.Sequential(
+            nn.Linear(num_queries * (num_classes + self.bbox_dim), 512),
+            nn.ReLU(),
+            nn.Dropout(0.1),
+            nn.Linear(512, output_dim),
+            nn.LayerNorm(output_dim),
+        )
+
+    def in_channels(self) -> int:
+        return 0            # not a pooled-channel extractor: its feature reaches the gate kernel ready-made
+
+    def forward(self, expert_output: Dict[str, torch.Tensor]) -> torch.Tensor:
+        from ...training import functional as TF
+        flat = expert_output.get('_flat')
+        if flat is None:
+            flat = torch.cat([expert_output['class_logits'], expert_output['bbox_preds']], dim=-1)
+        flat = flat.reshape(flat.size(0), -1).float()
+        if not flat.is_cuda:
+            raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+        fe = self.feature_extractor
+        p = float(fe[2].p) if self.training else 0.0
+        h = TF.linear(flat, fe[0], relu=True, drop_p=p)
+        h = TF.linear(h, fe[3])
+        return TF.layer_norm(h, fe[4])
+
+
 class ExpertOutputManager(nn.Module):
     """Manages multiple expert output extractors as a registered module (expert_extractors.py:139-157)"""
 
@@ -98,7 +135,7 @@ class ExpertOutputManager(nn.Module):
 
 
 def create_expert_extractors(expert_configs: List[Dict]) -> ExpertOutputManager:
-    """Same factory as expert_extractors.py:159-200 (nuScenes expert: see DESIGN.md, out of scope)."""
+    """Same factory as expert_extractors.py:159-200."""
     extractors = []
     for config in expert_configs:
         expert_type = config['type']
@@ -112,7 +149,10 @@ def create_expert_extractors(expert_configs: List[Dict]) -> ExpertOutputManager:
             extractor = DrivableExpertExtractor(output_dim=config.get('output_dim', 256),
                                                 num_classes=config.get('num_classes', 3))
         elif expert_type == 'nuscenes':
-            raise NotImplementedError("the nuScenes expert is not part of the B200 hot path yet (SURVEY.md §8f)")
+            extractor = NuScenesExpertExtractor(output_dim=config.get('output_dim', 256),
+                                                num_queries=config.get('num_queries', 100),
+                                                num_classes=config.get('num_classes', 10),
+                                                bbox_dim=config.get('bbox_dim', 7))
         else:
             raise ValueError(f"Unknown expert type: {expert_type}")
         extractors.append(extractor)

@@ -20,7 +20,7 @@ def rel_l2(a, b):
 
 def golden_config(g):
     """Model config of a golden automoe case (the sigmoid-gate case stores use_softmax=False)."""
-    cfg = dict(synth.CONFIG_3EXPERT)
+    cfg = dict(synth.CONFIG_4EXPERT if ("four_experts" in g.files and bool(g["four_experts"])) else synth.CONFIG_3EXPERT)
     if "use_softmax" in g.files:
         cfg["gating"] = dict(cfg["gating"], use_softmax=bool(g["use_softmax"]))
     return cfg

@@ -28,10 +28,16 @@ OUT = Path(__file__).resolve().parent
 VERS = np.array([f"torch {torch.__version__}", f"torchvision {torchvision.__version__}", f"scipy {scipy.__version__}"])
 
 
-def automoe_case(name, B, H, W, sub, speed_seq=1, controls_seq=False, use_softmax=True):
+def automoe_case(name, B, H, W, sub, speed_seq=1, controls_seq=False, use_softmax=True, four_experts=False):
     torch.manual_seed(0)
-    cfg = dict(synth.CONFIG_3EXPERT)
+    cfg = dict(synth.CONFIG_4EXPERT if four_experts else synth.CONFIG_3EXPERT)
     cfg["gating"] = dict(cfg["gating"], use_softmax=use_softmax)
+    if four_experts:
+        # NuScenesExpert.__init__ always asks torchvision for ImageNet weights (nuscenes_expert.py:108); there is no network
+        # here and every weight is overwritten by the synthetic state_dict below, so resnet18 is asked for random weights
+        import torchvision.models as tvm
+        orig = tvm.resnet18
+        tvm.resnet18 = lambda pretrained=False, **k: orig(weights=None)
     ref = ref_create(cfg, "cpu").eval()
     ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), 0), strict=True)
     batch = synth.synth_batch(B, H, W, seed=1, speed_seq=speed_seq)
@@ -53,7 +59,9 @@ def automoe_case(name, B, H, W, sub, speed_seq=1, controls_seq=False, use_softma
         seg_sub=seg[:, :, ::sub, ::sub].numpy(), drv_sub=drv[:, :, ::sub, ::sub].numpy(),
         seg_mean=seg.mean(dim=(2, 3)).numpy(), drv_mean=drv.mean(dim=(2, 3)).numpy(),
         seg_abs_sum=np.float64(seg.double().abs().sum().item()), drv_abs_sum=np.float64(drv.double().abs().sum().item()),
-        ctx_only_weights=w_ctx.numpy(), use_softmax=use_softmax,
+        ctx_only_weights=w_ctx.numpy(), use_softmax=use_softmax, four_experts=four_experts,
+        **({"nus_class_logits": r["expert_outputs"][3]["class_logits"].numpy(),
+            "nus_bbox_preds": r["expert_outputs"][3]["bbox_preds"].numpy()} if four_experts else {}),
     )
     print(name, "weights", r["expert_weights"].numpy().round(4).tolist())
 
@@ -99,6 +107,7 @@ if __name__ == "__main__":
     automoe_case("automoe_b1_256", B=1, H=256, W=256, sub=16)                 # BASELINE.json configs[0]
     automoe_case("automoe_b3_96_seq", B=3, H=96, W=96, sub=8, speed_seq=5, controls_seq=True)
     automoe_case("automoe_b2_64_sigmoid", B=2, H=64, W=64, sub=4, use_softmax=False)     # gating_network.py:159-160
+    automoe_case("automoe4_b2_96", B=2, H=96, W=96, sub=8, four_experts=True)            # shipped model_config.json (4 experts)
     matcher_case("matcher_d4_q64", B=4, Q=64, C=10, D=4, n_min=1, n_max=20, seed=0)
     matcher_case("matcher_d4_tall", B=3, Q=16, C=10, D=4, n_min=17, n_max=30, seed=1)   # more targets than queries
     matcher_case("matcher_d7_q50", B=2, Q=50, C=10, D=7, n_min=1, n_max=12, seed=2)

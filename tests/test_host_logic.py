@@ -86,13 +86,28 @@ def test_train_mode_is_rejected(model):
 def test_unsupported_configs_fail_loudly():
     from automoe_b200.models.automoe import create_automoe_model
     cfg = {k: v for k, v in synth.CONFIG_3EXPERT.items()}
-    cfg["experts"] = list(cfg["experts"]) + [{"type": "nuscenes"}]
-    with pytest.raises(NotImplementedError):
+    cfg["experts"] = list(cfg["experts"]) + [{"type": "nuscenes", "use_lidar": True, "pretrained_backbone": False}]
+    with pytest.raises(NotImplementedError, match="use_lidar"):      # PointNet branch: outside the hot path, named in the error
         create_automoe_model(cfg, "cpu")
     cfg = dict(synth.CONFIG_3EXPERT)
     cfg["context"] = {"type": "full"}
     with pytest.raises(NotImplementedError):
         create_automoe_model(cfg, "cpu")
+
+
+def test_shipped_four_expert_config_builds_with_reference_keys():
+    """models/configs/automoe/model_config.json (3 BDD experts + image-only nuScenes expert, sigmoid/softmax gate keys that
+    AutoMoE does not forward) builds; nuScenes sub-modules carry the reference's parameter names and shapes."""
+    from automoe_b200.models.automoe import create_automoe_model
+    m = create_automoe_model(synth.CONFIG_4EXPERT, "cpu")
+    sd = m.state_dict()
+    assert len(sd) == 609
+    assert sd["experts.3.image_backbone.7.1.bn2.running_var"].shape == (512,)
+    assert sd["experts.3.query_embed.weight"].shape == (196, 256)
+    assert sd["experts.3.bbox_head.weight"].shape == (4, 128)
+    assert sd["expert_extractors.extractors.3.feature_extractor.0.weight"].shape == (512, 196 * 14)
+    assert sd["gating_network.gate_network.0.weight"].shape == (128, 128 + 4 * 256)
+
 
 
 def test_matcher_pack_targets_is_one_padded_pack():
