@@ -138,6 +138,16 @@ int amoe_conv2d_fwd(amoe_ctx*, const void* x, const void* w, const float* scale,
                     int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride_h,
                     int stride_w, int pad_h, int pad_w, int Ho, int Wo, int relu, int dtype,
                     int impl, int in_pad, int out_pad, void* stream);
+/* A ResNet stage entry in ONE launch: the KHxKW/stride/pad convolution (conv1 + bn1 + ReLU -> y) and the 1x1/stride/pad-0
+ * downsample convolution of the same block (downsample.0 + downsample.1 -> y2) over the same input
+ * (torchvision BasicBlock.forward, resnet.py:92-103).  bf16 tcgen05 path only; x, y, y2 layouts as amoe_conv2d_fwd
+ * (in_pad / out_pad physical borders); w_1x1: [G*Cout][Cin] bf16.  Every output patch is computed as two consecutive
+ * tiles of the persistent kernel (the 1x1 tile re-reads the centre-tap box that conv1 just pulled through L2). */
+int amoe_conv2d_dual_fwd(amoe_ctx*, const void* x, const void* w, const float* scale, const float* bias,
+                         void* y, const void* w_1x1, const float* scale2, const float* bias2, void* y2,
+                         int G, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                         int pad, int Ho, int Wo, int relu, int relu2, int in_pad, int out_pad,
+                         void* stream);
 /* 1 if amoe_conv2d_fwd(impl=auto, dtype=bf16) would take the tcgen05 path. */
 int amoe_conv2d_tc_supported(int H, int W, int Cin, int Cout, int stride_h, int stride_w);
 /* "Row-window" convolution for tiny Cin (ResNet stem 7x7/s2 with Cin=3, policy conv1 5x5/s2)

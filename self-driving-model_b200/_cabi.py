@@ -44,6 +44,7 @@ SIGNATURES = {
     "amoe_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
     "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 20 + [_P]),
+    "amoe_conv2d_dual_fwd": (_I, [_P] * 10 + [_I] * 16 + [_P]),
     "amoe_conv3x3_flat_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P]),
     "amoe_conv3x3_flat_fwd_strided": (_I, [_P] * 7 + [_I] * 7 + [C.c_int64, C.c_int64, _P]),
     "amoe_conv3x3_flat_supported": (_I, [_I] * 4),

@@ -462,6 +462,42 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
     return y
 
 
+def dual_entry() -> bool:
+    """Stage-entry conv1 (3x3/s2) and the block's 1x1/s2 downsample as one dual launch (AMOE_DUAL=0: two launches)."""
+    return os.environ.get("AMOE_DUAL", "1") != "0"
+
+
+def conv2d_dual(pc: PackedConv, pd: PackedConv, x: torch.Tensor, B: int, H: int, W: int, in_pad: int = 0, out_pad: int = 0):
+    """conv (pc: KxK/stride s/pad p, + BN + ReLU) and the 1x1/stride s/pad 0 convolution pd (+ BN) over the same input in
+    one launch -> (y, y2), both [G*B,Ho(+2*out_pad),Wo(+2*out_pad),Cout] with a zero border when out_pad."""
+    assert x.dtype == torch.bfloat16 and pc.sh == pc.sw == pd.sh == pd.sw and pc.ph == pc.pw and not pc.pair_w
+    assert pd.kh == pd.kw == 1 and pd.ph == pd.pw == 0 and pd.cout == pc.cout and pd.cin == pc.cin and pd.G == pc.G
+    Ho = (H + 2 * pc.ph - pc.kh) // pc.sh + 1
+    Wo = (W + 2 * pc.pw - pc.kw) // pc.sw + 1
+    assert Ho == (H - 1) // pd.sh + 1 and Wo == (W - 1) // pd.sw + 1
+    shape = (pc.G * B, Ho + 2 * out_pad, Wo + 2 * out_pad, pc.cout)
+    alloc = torch.zeros if out_pad else torch.empty
+    y, y2 = alloc(shape, device=x.device, dtype=x.dtype), alloc(shape, device=x.device, dtype=x.dtype)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().amoe_conv2d_dual_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(y), ptr(pd.w), ptr(pd.scale),
+                                     ptr(pd.bias), ptr(y2), pc.G, B, H, W, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.ph, Ho, Wo,
+                                     int(pc.relu), int(pd.relu), in_pad, out_pad, stream_ptr(x.device)), "conv2d_dual_fwd")
+    if prof is not None:
+        ev1.record()
+        macs = (pc.kh * pc.kw + 1) * pc.cin * pc.cout * pc.G * B * Ho * Wo
+        prof.append(("conv_tc_kernel", 2.0 * macs, ev0, ev1))
+    return y, y2
+
+
+def dual_supported(pc: PackedConv, pd: Optional[PackedConv], H: int, W: int, in_pad: int, dtype: torch.dtype) -> bool:
+    return (pd is not None and dtype == torch.bfloat16 and dual_entry() and not pc.pair_w and pc.sh == pc.sw and pc.ph == pc.pw
+            and pd.kh == 1 and pd.kw == 1 and pd.sh == pc.sh and pd.sw == pc.sw and pd.ph == 0 and pd.pw == 0
+            and bool(lib().amoe_conv2d_tc_supported(H + 2 * in_pad, W + 2 * in_pad, pc.cin, pc.cout, pc.sh, pc.sw)))
+
+
 def flat_supported(pc: PackedConv, H: int, W: int, dtype: torch.dtype) -> bool:
     return (dtype == torch.bfloat16 and pc.kh == 3 and pc.kw == 3 and pc.sh == 1 and pc.sw == 1 and pc.ph == 1
             and pc.pw == 1 and not pc.pair_w and bool(lib().amoe_conv3x3_flat_supported(H, W, pc.cin, pc.cout)))

@@ -52,6 +52,16 @@ struct Params {
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
+  // Optional SECOND convolution over the same input, output geometry and Cout, run as a second tile behind every tile of
+  // the first one (nprob == 2): the 1x1/stride-2 downsample of a ResNet stage entry next to its 3x3/stride-2 conv1.
+  // Its single tap is the centre tap of conv1, so the activation box it loads was loaded a moment ago (L2 hit), and the
+  // short-K tile rides in the same persistent pipeline instead of paying a launch, a prologue and an L2-cold sweep.
+  int nprob;
+  int relu2;
+  Tap tap2;
+  const float* scale2;
+  const float* bias2;
+  __nv_bfloat16* y2;
   Tap taps[MAX_TAPS];
 };
 
@@ -73,7 +83,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4];
   __shared__ uint32_t tmem_holder;
@@ -91,6 +101,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_scale[i] = __ldg(p.scale + i);
     s_bias[i] = __ldg(p.bias + i);
   }
+  float* s_scale2 = s_bias + p.n_ch_total;      // second problem (nprob == 2)
+  float* s_bias2 = s_scale2 + p.n_ch_total;
+  if (p.nprob == 2) {
+    for (int i = threadIdx.x; i < p.n_ch_total; i += NUM_THREADS) {
+      s_scale2[i] = __ldg(p.scale2 + i);
+      s_bias2[i] = __ldg(p.bias2 + i);
+    }
+  }
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_STAGES]);
@@ -99,6 +117,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
+    if (p.nprob == 2) prefetch_tmap(&tmW2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -115,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
 
-  const int k_iters = p.num_taps * p.k_chunks;
+  const int k_iters1 = p.num_taps * p.k_chunks;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -142,6 +161,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (p.nprob == 2) {   // the second convolution's tile for the same output patch: one tap, k_chunks chunks
+          const Tap tp = p.tap2;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
+            tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
+                        tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW2, bar_full + 8 * stage, kc * BLOCK_K, wrow0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -150,12 +183,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+    for (int prob = 0; prob < p.nprob; ++prob, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);  // epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_STRIDE);
+      const int k_iters = prob ? p.k_chunks : k_iters1;
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes have landed
         tcgen05_fence_after();
@@ -183,10 +218,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = lg * 32 + lane;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+    for (int prob = 0; prob < p.nprob; ++prob, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const TileCoord tc_ = decode_tile(p, t);
+      const float* e_scale = prob ? s_scale2 : s_scale;
+      const float* e_bias = prob ? s_bias2 : s_bias;
+      __nv_bfloat16* e_y = prob ? p.y2 : p.y;
+      const int e_relu = prob ? p.relu2 : p.relu;
       const int nl = tc_.bt * p.nb + bi, oh = tc_.ht * p.th + hi, ow = tc_.wt * p.tw + wi;
       const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
       const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
@@ -195,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t pix = ((int64_t)nl * Hop + oh + p.out_pad) * Wop + ow + p.out_pad;
       const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
       const int nsplit = p.Cout / p.split_c;
-      const bool use_res = p.residual != nullptr && valid;
+      const bool use_res = p.residual != nullptr && valid && prob == 0;
       if (use_res) {
         // pull this row of the residual towards L2 while the MMAs of the tile are still running
         // (a residual implies split_c == Cout: the row's block_n channels are contiguous)
@@ -218,8 +258,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
         if (valid) {
-          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch0 + c0);
-          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + ch0 + c0);
+          const float4* sc4 = reinterpret_cast<const float4*>(e_scale + ch0 + c0);
+          const float4* bs4 = reinterpret_cast<const float4*>(e_bias + ch0 + c0);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
@@ -241,13 +281,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[2 * j + 1] += rf.y;
               }
             }
-            if (p.relu) {
+            if (e_relu) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
             }
             uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = o;
+            *reinterpret_cast<uint4*>(e_y + off + c0 + v * 8) = o;
           }
         }
       }
@@ -288,7 +328,7 @@ int amoe_conv_tc_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc::SMEM_BUDGET + 1024 + 16 * 1024));
+                                       tc::SMEM_BUDGET + 1024 + 24 * 1024));
   return 0;
 }
 
@@ -304,10 +344,21 @@ struct AView {
   uint64_t strides[4];
 };
 
+// second convolution of a dual launch (see Params::nprob): 1x1 weights [G*Cout][Cin], its folded BatchNorm and output
+struct Second {
+  const void* w = nullptr;
+  const float* scale = nullptr;
+  const float* bias = nullptr;
+  void* y = nullptr;
+  int relu = 0;
+  tc::Tap tap;
+};
+
 static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const void* w, int Ktot,
                           const float* scale, const float* bias, const void* residual, void* y, int G,
                           int x_shared, int B, int Ho, int Wo, int Cout, int split_c, int num_taps,
-                          const tc::Tap* taps, int k_chunks, int relu, int out_pad, cudaStream_t st) {
+                          const tc::Tap* taps, int k_chunks, int relu, int out_pad, cudaStream_t st,
+                          const Second* second = nullptr) {
   using namespace tc;
   AMOE_REQUIRE(num_taps <= MAX_TAPS, "conv_tc: %d taps exceed the limit of %d", num_taps, MAX_TAPS);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -338,6 +389,15 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
   for (int t = 0; t < num_taps; ++t) p.taps[t] = taps[t];
+  p.nprob = 1; p.relu2 = 0; p.tap2 = taps[0]; p.scale2 = nullptr; p.bias2 = nullptr; p.y2 = nullptr;
+  if (second != nullptr) {
+    AMOE_REQUIRE(second->w && second->scale && second->bias && second->y && split_c == Cout,
+                 "conv_tc: incomplete second convolution of a dual launch");
+    AMOE_REQUIRE((reinterpret_cast<uintptr_t>(second->w) & 15) == 0 && (reinterpret_cast<uintptr_t>(second->y) & 15) == 0,
+                 "conv_tc: pointers must be 16-byte aligned");
+    p.nprob = 2; p.relu2 = second->relu; p.tap2 = second->tap; p.scale2 = second->scale; p.bias2 = second->bias;
+    p.y2 = (__nv_bfloat16*)second->y;
+  }
   if (total == 0) return 0;
 
   CUtensorMap tmA, tmW;
@@ -362,10 +422,22 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
+  CUtensorMap tmW2 = tmW;
+  if (second != nullptr) {
+    const int K2 = k_chunks * BLOCK_K;          // 1x1 filter: K = Cin
+    cuuint64_t dims[2] = {(cuuint64_t)K2, (cuuint64_t)G * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K2 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(second->w), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(second weights) failed with %d", (int)r);
+  }
   const int grid = std::min(p.total_tiles, ctx->sm_count);
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)2 * p.n_ch_total * sizeof(float);
-  AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 16 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
-  conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, p);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
+  AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
+  conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, tmW2, p);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
@@ -373,7 +445,8 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
 static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const float* scale,
                           const float* bias, const void* residual, void* y, int G, int x_shared,
                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int sh, int sw,
-                          int ph, int pw, int Ho, int Wo, int relu, int in_pad, int out_pad, cudaStream_t st) {
+                          int ph, int pw, int Ho, int Wo, int relu, int in_pad, int out_pad, cudaStream_t st,
+                          Second* second = nullptr) {
   using namespace tc;
   // a physically padded input [N][H+2*in_pad][W+2*in_pad][C] is just a bigger image whose
   // filter taps start in_pad pixels further right/down
@@ -394,8 +467,15 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
   av.dims[3] = (uint64_t)(H / sh); av.dims[4] = (uint64_t)NB;
   av.strides[0] = (uint64_t)sw * Cin * 2; av.strides[1] = (uint64_t)W * Cin * 2;
   av.strides[2] = (uint64_t)sh * W * Cin * 2; av.strides[3] = (uint64_t)H * W * Cin * 2;
+  if (second != nullptr) {
+    // 1x1 / same stride / no padding over the (physically padded) input: the tap at offset (in_pad, in_pad)
+    Tap& t = second->tap;
+    const int ho = in_pad, wo = in_pad;      // ph, pw were shifted by in_pad above; a 1x1/p0 filter reads pixel (s*oh, s*ow)
+    if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
+    if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
+  }
   return launch_generic(ctx, x, av, w, KH * KW * Cin, scale, bias, residual, y, G, x_shared, B, Ho, Wo, Cout,
-                        Cout, KH * KW, taps, Cin / BLOCK_K, relu, out_pad, st);
+                        Cout, KH * KW, taps, Cin / BLOCK_K, relu, out_pad, st, second);
 }
 
 extern "C" {
@@ -434,6 +514,24 @@ int amoe_conv2d_rowwin_fwd(amoe_ctx* ctx, const void* x, const void* w, const fl
   av.strides[3] = (uint64_t)H * row;
   return launch_generic(ctx, x, av, w, KH * BLOCK_K, scale, bias, nullptr, y, 1, 0, B, Ho, Wo, Cout, split_c, KH,
                         taps, 1, relu, 0, (cudaStream_t)stream);
+}
+
+int amoe_conv2d_dual_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale, const float* bias, void* y,
+                         const void* w_1x1, const float* scale2, const float* bias2, void* y2, int G, int B, int H, int W,
+                         int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, int relu, int relu2,
+                         int in_pad, int out_pad, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x && w && scale && bias && y && w_1x1 && scale2 && bias2 && y2, "amoe_conv2d_dual_fwd: NULL argument");
+  AMOE_REQUIRE(G >= 1 && B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && Ho > 0 && Wo > 0 &&
+                   in_pad >= 0 && out_pad >= 0, "amoe_conv2d_dual_fwd: bad shape");
+  AMOE_REQUIRE((Ho - 1) * stride - pad < H && (Wo - 1) * stride - pad < W && (Ho - 1) * stride < H && (Wo - 1) * stride < W,
+               "amoe_conv2d_dual_fwd: Ho/Wo inconsistent with input size");
+  AMOE_REQUIRE(tc::supported(H + 2 * in_pad, W + 2 * in_pad, Cin, Cout, stride, stride),
+               "amoe_conv2d_dual_fwd: the tcgen05 path does not take this shape");
+  Second second;
+  second.w = w_1x1; second.scale = scale2; second.bias = bias2; second.y = y2; second.relu = relu2;
+  return conv_tc_launch(ctx, x, w, scale, bias, nullptr, y, G, 0, B, H, W, Cin, Cout, KH, KW, stride, stride, pad, pad, Ho, Wo,
+                        relu, in_pad, out_pad, (cudaStream_t)stream, &second);
 }
 
 int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,

@@ -295,9 +295,12 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
         pad_out = 1 if (flat_ok and _ops.flat_supported(c2, h_out, w_out, pack.dtype)) else 0
         if pad and pad_out and c1.sh == 1 and _ops.flat_supported(c1, h_cur, w_cur, pack.dtype):
             out = _ops.conv3x3_flat(c1, y, B, h_cur, w_cur)
+            identity = y if dn is None else _ops.conv2d(dn, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out)
+        elif _ops.dual_supported(c1, dn, h_cur, w_cur, pad, pack.dtype):
+            out, identity = _ops.conv2d_dual(c1, dn, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out)   # stage entry: one launch
         else:
             out = _ops.conv2d(c1, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out, zero_border=True)
-        identity = y if dn is None else _ops.conv2d(dn, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out)
+            identity = y if dn is None else _ops.conv2d(dn, y, B, h_cur, w_cur, in_pad=pad, out_pad=pad_out)
         if pad_out:
             y = _ops.conv3x3_flat(c2, out, B, h_out, w_out, residual=identity)
         else:

@@ -221,6 +221,25 @@ def test_l2_chunked_stem_layer1_is_bit_identical(model_sd, monkeypatch):
         assert torch.equal(outs["0"]["expert_outputs"][0][k], outs["6"]["expert_outputs"][0][k])
 
 
+def test_dual_stage_entry_launch_is_bit_identical(model_sd, monkeypatch):
+    """Stage-entry conv1 (3x3/s2) + the block's 1x1/s2 downsample as ONE dual-problem launch of the tcgen05 kernel
+    (amoe_conv2d_dual_fwd) against the two separate launches: same MMAs in the same order -> the same bits, for the padded
+    (layer2, 256x256 frames), the unpadded and the odd-sized geometries."""
+    m, sd = model_sd
+    for B, H in ((16, 256), (3, 96), (2, 160)):
+        batch = _to(synth.synth_batch(B, H, H, seed=17), DEV)
+        outs = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("AMOE_DUAL", flag)
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                outs[flag] = m(batch)
+        for k in SMALL:
+            assert torch.equal(outs["0"][k], outs["1"][k]), (B, H, k)
+        for i in (1, 2):
+            assert torch.equal(outs["0"]["expert_outputs"][i], outs["1"]["expert_outputs"][i]), (B, H, i)
+        assert torch.equal(outs["0"]["expert_outputs"][0]["class_logits"], outs["1"]["expert_outputs"][0]["class_logits"])
+
+
 def test_cuda_graph_capture_replays_the_eager_forward(model_sd):
     """AutoMoE.capture(): replaying the captured graph on new inputs gives bit-identical outputs to the eager
     call (same kernels, same order; side-stream logit writers joined inside the graph)."""
