@@ -6,7 +6,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include <atomic>
+#include <utility>
 
 #include "../../include/automoe_b200.h"
 
@@ -63,6 +66,33 @@ struct amoe_device_scope {
   amoe_device_scope& operator=(const amoe_device_scope&) = delete;
 };
 #define AMOE_ENTER(ctx) amoe_device_scope _amoe_dev_scope(ctx)
+
+// AMOE_PDL=0 turns programmatic dependent launch of the tensor-core convolution chain off (A/B switch)
+static inline bool amoe_pdl_enabled() {
+  static const int on = [] {
+    const char* e = getenv("AMOE_PDL");
+    return (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }();
+  return on != 0;
+}
+
+// Launch `kern` so that it may start before the previous kernel of the stream has drained (see tc_common.cuh:
+// griddep_wait).  Only for kernels that call griddepcontrol.wait before their first dependent global access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t amoe_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = amoe_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -112,18 +112,21 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = tmem_holder;
   const int group_row0 = g * p.group_positions;  // first flattened position of this expert group
   const int wrow0 = g * N;                        // first weight row of this expert group
+  griddep_launch_dependents();                    // PDL: the next kernel of the chain may be scheduled (see tc_common.cuh)
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       if (p.w_resident) {
         // all chunks x taps weight tiles, once: tile j = chunk*9 + tap holds K columns tap*C + chunk*64 ...
+        // (constant weights: loaded while the previous kernel may still be running)
         mbar_arrive_expect_tx(bar_wfull, (uint32_t)(p.chunks * 9) * w_tile_bytes);
         for (int j = 0; j < p.chunks * 9; ++j) {
           const int chunk = j / 9, tap = j - chunk * 9;
           tma_load_2d(smem_w + (uint32_t)j * w_tile_bytes, &tmW, bar_wfull, tap * p.C + chunk * BLOCK_K, wrow0);
         }
       }
+      griddep_wait();                             // activations below are the previous kernel's output
       int as = 0, ws = 0;
       uint32_t aphase = 0, wphase = 0;
       const int half_rows = p.rows_pad >> 1;
@@ -211,6 +214,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Eight warps: warp (lg, hs) owns TMEM lane quarter lg of M-half hs.  (Measured with the epilogue body removed:
     // the N=128 kernel runs at 90 % tensor-busy, 156-166 us per layer2 convolution, against 70-76 % / 189-214 us with
     // four warps draining both halves one after the other - it was bound by this epilogue, not by its MMAs.)
+    griddep_wait();                      // residual reads / output writes only after the previous kernel is complete
     const int lg = warp & 3, hs = (warp - 3) >> 2;
     const int img = p.Hp * p.Wp;
     constexpr int NV = N / 8;            // 16-byte pieces per output row
@@ -783,9 +787,9 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
     kp.div_wp = fastdiv_init((uint32_t)p.Wp);
     conv3x3_flat_kw3_kernel<<<dim3(ctas, G), KW3_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, kp);
   } else if (Cout == 64)
-    conv3x3_flat_kernel<64><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<64>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
   else
-    conv3x3_flat_kernel<128><<<dim3(ctas, G), NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<128>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -133,6 +133,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  // PDL: everything above touched only kernel parameters and constant weights (folded BN); the next kernel of the chain
+  // may be scheduled now, and nothing below runs before the previous kernel's results are complete
+  griddep_launch_dependents();
+  griddep_wait();
 
   const int k_iters1 = p.num_taps * p.k_chunks;
 
@@ -437,7 +441,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   const int grid = std::min(p.total_tiles, ctx->sm_count);
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
   AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
-  conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmW, tmW2, p);
+  AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -360,12 +360,14 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
   const uint32_t tmem_base = tmem_holder;
   const uint32_t tile_bytes = (uint32_t)(p.KH * p.row_bytes);
   const Seq seq = make_seq(p.B * pp.Hp, pp.Hp);
+  griddep_launch_dependents();          // PDL: the next kernel of the chain may be scheduled (see tc_common.cuh)
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, (uint32_t)p.w_bytes);
-      for (int o = 0; o < p.w_bytes; o += 32768)
+      for (int o = 0; o < p.w_bytes; o += 32768)      // constant filters: loaded while the staging kernel may still run
         bulk_g2s(smem_w + (uint32_t)o, p.w + o, (uint32_t)std::min(32768, p.w_bytes - o), bar_w);
+      griddep_wait();                   // the staged frame is the previous kernel's output
       int stage = 0;
       uint32_t phase = 0;
       for (int k = 0; k < seq.n_tiles; ++k) {
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
     }
   } else {
     // ============================ epilogue + max-pool ============================
+    griddep_wait();                             // output buffers may still be read by the previous kernels of the stream
     const int lq = warp & 3;                    // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;            // chunk group
     const int ow = lq * 32 + lane;
@@ -619,9 +622,9 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
   AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
   if (scale == nullptr)
-    stem_pool_kernel<true><<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   else
-    stem_pool_kernel<false><<<grid, POOL_THREADS, smem, (cudaStream_t)stream>>>(pp);
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<false>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -124,6 +124,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// begin while its predecessor in the stream is still running - its CTAs take over SMs as the predecessor's CTAs retire
+// and run their prologue (barrier init, TMEM allocation, descriptor prefetch, constant weight loads) - but must not touch
+// anything the predecessor reads or writes before griddep_wait() returns (= predecessor complete, memory flushed).
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 B apart):
 // start address >>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 | SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
