@@ -398,6 +398,25 @@ int amoe_conv2d_bwd_weight(amoe_ctx*, const float* dy, const float* x, float* dw
                            int64_t workspace_floats, int B, int H, int W, int Cin, int Cout, int KH,
                            int KW, int stride_h, int stride_w, int pad_h, int pad_w, int Ho, int Wo,
                            void* stream);
+/* fp32-accurate training convolutions on the bf16 tensor cores (csrc/conv_tc.cu, "split operands"): every fp32 value is
+ * carried as three bf16 parts (24 significant bits), a product keeps its six leading terms, all accumulated in fp32 TMEM.
+ *   amoe_split3_bf16:              x [rows][C] fp32 -> [rows][3C] bf16 = (x1 | x2 | x3), C % 8 == 0
+ *   amoe_pack_conv_weight_split6:  OIHW fp32 -> [Cout][KH][KW][6][Cin] bf16 (transposed = 1: [Cin][KH][KW][6][Cout] for dgrad)
+ *   amoe_conv2d_fwd_f32tc:         y [B,Ho,Wo,Cout] fp32 = relu?(scale * conv(x) + bias)   (nn.Conv2d forward of the
+ *                                  ResNet-18 / EasyBackbone layers inside the training step; Cin % 64 == 0, Cout % 32 == 0)
+ *   amoe_conv2d_bwd_data_f32tc:    dx [B,H,W,Cin] fp32 from split dy [B,Ho,Wo,3*Cout] and the transposed split weights;
+ *                                  stride 2 runs one sub-convolution per input parity class (the caller zero-fills dx when a
+ *                                  class has no tap, i.e. 1x1 / stride 2); ones/zeros: Cin floats each. */
+int amoe_split3_bf16(amoe_ctx*, const float* x, void* out, int64_t rows, int C, void* stream);
+int amoe_pack_conv_weight_split6(amoe_ctx*, const float* w_oihw, void* dst, int Cout, int Cin, int KH,
+                                 int KW, int transposed, void* stream);
+int amoe_conv2d_f32tc_supported(int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int amoe_conv2d_fwd_f32tc(amoe_ctx*, const void* x_split, const void* w_split, const float* scale,
+                          const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
+                          int KW, int stride, int pad, int Ho, int Wo, int relu, void* stream);
+int amoe_conv2d_bwd_data_f32tc(amoe_ctx*, const void* dy_split, const void* wT_split, const float* ones,
+                               const float* zeros, float* dx, int B, int H, int W, int Cin, int Cout,
+                               int KH, int KW, int stride, int pad, int Ho, int Wo, void* stream);
 /* nn.AdaptiveAvgPool2d(1) on NHWC fp32: x [B,HW,C] -> out [B,C]; backward broadcasts dy/HW. */
 int amoe_gap_fwd(amoe_ctx*, const float* x, float* out, int B, int HW, int C, void* stream);
 int amoe_gap_bwd(amoe_ctx*, const float* dy, float* dx, int B, int HW, int C, void* stream);

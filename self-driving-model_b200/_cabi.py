@@ -45,6 +45,11 @@ SIGNATURES = {
     "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
     "amoe_conv2d_fwd": (_I, [_P] * 7 + [_I] * 20 + [_P]),
     "amoe_conv2d_dual_fwd": (_I, [_P] * 10 + [_I] * 16 + [_P]),
+    "amoe_split3_bf16": (_I, [_P, _P, _P, _L, _I, _P]),
+    "amoe_pack_conv_weight_split6": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "amoe_conv2d_f32tc_supported": (_I, [_I] * 7),
+    "amoe_conv2d_fwd_f32tc": (_I, [_P] * 6 + [_I] * 12 + [_P]),
+    "amoe_conv2d_bwd_data_f32tc": (_I, [_P] * 6 + [_I] * 11 + [_P]),
     "amoe_conv3x3_flat_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P]),
     "amoe_conv3x3_flat_fwd_strided": (_I, [_P] * 7 + [_I] * 7 + [C.c_int64, C.c_int64, _P]),
     "amoe_conv3x3_flat_supported": (_I, [_I] * 4),

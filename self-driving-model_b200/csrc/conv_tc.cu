@@ -24,7 +24,7 @@ namespace tc {
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_TAPS = 49;
+constexpr int MAX_TAPS = 64;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
@@ -32,6 +32,7 @@ constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct Tap {
   int c_off, dw, hp, dh;  // TMA start-coordinate offsets of this filter tap
+  int w_k;                // first K column of this tap's weights in the packed [rows][K] weight matrix
 };
 
 struct Params {
@@ -44,6 +45,9 @@ struct Params {
   int stages;
   int relu, x_shared;
   int out_pad;                      // output (and residual) tensors carry a physical border of out_pad pixels
+  int out_f32;                      // output tensor is fp32 (split-operand training convolutions), no residual
+  int o_hm, o_ha, o_wm, o_wa;       // output pixel (oh, ow) lands at row oh*o_hm + o_ha, column ow*o_wm + o_wa of an
+  int o_H, o_W;                     //   [N][o_H][o_W][C] tensor (dense: 1, out_pad, 1, out_pad, Ho+2*out_pad, Wo+2*out_pad)
   int split_c;                      // output sub-tensor width: channel ch of group g goes to tensor
                                     // (g*Cout/split_c + ch/split_c), channel ch%split_c (== Cout normally)
   int total_tiles;
@@ -158,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
             tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
                         tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW, bar_full + 8 * stage, kidx * BLOCK_K, wrow0);
+            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW, bar_full + 8 * stage, tp.w_k + kc * BLOCK_K, wrow0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -235,8 +239,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
       const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
       const int chn = tc_.nt * p.block_n;  // first channel of this tile inside its group
-      const int Hop = p.Ho + 2 * p.out_pad, Wop = p.Wo + 2 * p.out_pad;
-      const int64_t pix = ((int64_t)nl * Hop + oh + p.out_pad) * Wop + ow + p.out_pad;
+      const int Hop = p.o_H, Wop = p.o_W;
+      const int64_t pix = ((int64_t)nl * Hop + oh * p.o_hm + p.o_ha) * Wop + ow * p.o_wm + p.o_wa;
       const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
       const int nsplit = p.Cout / p.split_c;
       const bool use_res = p.residual != nullptr && valid && prob == 0;
@@ -289,15 +293,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(e_y + off + c0 + v * 8) = o;
+            if (p.out_f32) {
+              float* yf = reinterpret_cast<float*>(e_y) + off + c0 + v * 8;
+              *reinterpret_cast<float4*>(yf) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(yf + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(e_y + off + c0 + v * 8) = o;
+            }
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (p.out_pad == 1 && prob == 0 && valid) {
+        // Physical zero border of the padded output (the consumer's 3x3 taps read it as their padding): written by the
+        // threads that own the neighbouring interior pixels, for this tile's channels - no memset of the whole tensor.
+        const int dh0 = (oh == 0) ? -1 : 0, dh1 = (oh == p.Ho - 1) ? 1 : 0;
+        const int dw0 = (ow == 0) ? -1 : 0, dw1 = (ow == p.Wo - 1) ? 1 : 0;
+        if ((dh0 | dh1 | dw0 | dw1) != 0) {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          for (int dh = dh0; dh <= dh1; ++dh)
+            for (int dw = dw0; dw <= dw1; ++dw) {
+              if (dh == 0 && dw == 0) continue;
+              const int64_t pixb = pix + (int64_t)dh * Wop + dw;
+              for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                const int ch = chn + c0;
+                __nv_bfloat16* d = e_y + (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pixb * p.split_c + ch % p.split_c;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(d + v * 8) = z;
+              }
+            }
+        }
+      }
     }
   }
 
@@ -348,6 +378,12 @@ struct AView {
   uint64_t strides[4];
 };
 
+// where / how the output tile is stored when it is not the dense bf16 tensor (training convolutions: fp32, parity-strided)
+struct OutMap {
+  int f32 = 0;
+  int o_hm = 1, o_ha = 0, o_wm = 1, o_wa = 0, o_H = 0, o_W = 0;   // o_H == 0: dense addressing from out_pad
+};
+
 // second convolution of a dual launch (see Params::nprob): 1x1 weights [G*Cout][Cin], its folded BatchNorm and output
 struct Second {
   const void* w = nullptr;
@@ -362,7 +398,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
                           const float* scale, const float* bias, const void* residual, void* y, int G,
                           int x_shared, int B, int Ho, int Wo, int Cout, int split_c, int num_taps,
                           const tc::Tap* taps, int k_chunks, int relu, int out_pad, cudaStream_t st,
-                          const Second* second = nullptr) {
+                          const Second* second = nullptr, const OutMap* omap = nullptr) {
   using namespace tc;
   AMOE_REQUIRE(num_taps <= MAX_TAPS, "conv_tc: %d taps exceed the limit of %d", num_taps, MAX_TAPS);
   AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -393,6 +429,12 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
   for (int t = 0; t < num_taps; ++t) p.taps[t] = taps[t];
+  p.out_f32 = 0;
+  p.o_hm = 1; p.o_ha = out_pad; p.o_wm = 1; p.o_wa = out_pad; p.o_H = Ho + 2 * out_pad; p.o_W = Wo + 2 * out_pad;
+  if (omap != nullptr) {
+    p.out_f32 = omap->f32;
+    if (omap->o_H > 0) { p.o_hm = omap->o_hm; p.o_ha = omap->o_ha; p.o_wm = omap->o_wm; p.o_wa = omap->o_wa; p.o_H = omap->o_H; p.o_W = omap->o_W; }
+  }
   p.nprob = 1; p.relu2 = 0; p.tap2 = taps[0]; p.scale2 = nullptr; p.bias2 = nullptr; p.y2 = nullptr;
   if (second != nullptr) {
     AMOE_REQUIRE(second->w && second->scale && second->bias && second->y && split_c == Cout,
@@ -463,6 +505,7 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
       int ho = kh - ph, wo = kw - pw;
       if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
       if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
+      t.w_k = (kh * KW + kw) * Cin;
     }
   // parity view (inner -> outer): Cv = sw*Cin, Wv = W/sw, P = sh, Hv = H/sh, N
   const int NB = x_shared ? B : G * B;
@@ -477,9 +520,120 @@ static int conv_tc_launch(amoe_ctx* ctx, const void* x, const void* w, const flo
     const int ho = in_pad, wo = in_pad;      // ph, pw were shifted by in_pad above; a 1x1/p0 filter reads pixel (s*oh, s*ow)
     if (sh == 1) { t.dh = ho; t.hp = 0; } else { t.dh = floordiv2(ho); t.hp = ho - 2 * t.dh; }
     if (sw == 1) { t.dw = wo; t.c_off = 0; } else { t.dw = floordiv2(wo); t.c_off = (wo - 2 * t.dw) * Cin; }
+    t.w_k = 0;
   }
   return launch_generic(ctx, x, av, w, KH * KW * Cin, scale, bias, residual, y, G, x_shared, B, Ho, Wo, Cout,
                         Cout, KH * KW, taps, Cin / BLOCK_K, relu, out_pad, st, second);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32-accurate convolutions on the bf16 tensor cores (training path: the reference trains in fp32).
+//
+// Every fp32 value is split into three bf16 parts, v = v1 + v2 + v3 (each the bf16 rounding of what is left), which
+// carries 24 significant bits.  A product x*w keeps the six terms down to 2^-16 of its magnitude,
+//     x1 w1 + (x1 w2 + x2 w1) + (x1 w3 + x2 w2 + x3 w1),
+// all accumulated in the fp32 TMEM accumulator, so a dot product is as accurate as an fp32 FMA chain (what is dropped,
+// x2 w3 + x3 w2 + x3 w3, is below 2^-24).  The six terms ride through the SAME implicit-GEMM kernel as six K blocks per
+// filter tap: activations are stored once as [pixel][x1 | x2 | x3] (3C channels) and the taps address a part through
+// their channel offset; the weights are packed per tap as [w1 | w2 | w1 | w3 | w2 | w1].  Six bf16 MMAs per fp32 MAC is
+// ~230 TFLOP/s of fp32-accurate throughput against ~60 TFLOP/s of the FP32 pipe.
+namespace tc {
+
+constexpr int SPLIT_TERMS = 6;
+__device__ __constant__ int kTermXPart[SPLIT_TERMS] = {0, 0, 1, 0, 1, 2};   // activation part of each term
+__device__ __constant__ int kTermWPart[SPLIT_TERMS] = {0, 1, 0, 2, 1, 0};   // weight part of each term
+static const int hTermXPart[SPLIT_TERMS] = {0, 0, 1, 0, 1, 2};
+
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a);          // exact (Sterbenz-like: a is v rounded to 8 bits)
+  b = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b);         // exact
+  c = __float2bfloat16_rn(r2);
+}
+
+// x [rows][C] fp32 -> out [rows][3C] bf16 = (x1 | x2 | x3); C % 8 == 0; one thread = 8 channels
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C,
+                                                     int64_t total8) {
+  const int c8n = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c8n;
+    const int c0 = (int)(i - row * c8n) << 3;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(x + row * C + c0));
+    const float4 u1 = __ldg(reinterpret_cast<const float4*>(x + row * C + c0 + 4));
+    const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    __align__(16) __nv_bfloat16 a[8], b[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3(v[j], a[j], b[j], c[j]);
+    __nv_bfloat16* o = out + row * (3 * (int64_t)C) + c0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(b);
+    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(c);
+  }
+}
+
+// nn.Conv2d weight [Cout][Cin][KH][KW] fp32 -> six split terms per tap, K-major:
+//   transposed == 0 (forward):  dst[co][kh][kw][t][ci]            rows = Cout, K = KH*KW*6*Cin
+//   transposed == 1 (dgrad):    dst[ci][kh][kw][t][co]            rows = Cin,  K = KH*KW*6*Cout
+__global__ void __launch_bounds__(256) pack_split6_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout,
+                                                          int Cin, int KH, int KW, int transposed, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates (row, kh, kw, inner) without the term axis
+    const int inner_n = transposed ? Cout : Cin;
+    const int inner = (int)(i % inner_n);
+    int64_t r = i / inner_n;
+    const int kw = (int)(r % KW); r /= KW;
+    const int kh = (int)(r % KH); r /= KH;
+    const int row = (int)r;
+    const int co = transposed ? inner : row, ci = transposed ? row : inner;
+    const float v = w[(((int64_t)co * Cin + ci) * KH + kh) * KW + kw];
+    __nv_bfloat16 part[3];
+    split3(v, part[0], part[1], part[2]);
+    __nv_bfloat16* d = dst + ((((int64_t)row * KH + kh) * KW + kw) * SPLIT_TERMS) * inner_n + inner;
+#pragma unroll
+    for (int t = 0; t < SPLIT_TERMS; ++t) d[(int64_t)t * inner_n] = part[kTermWPart[t]];
+  }
+}
+
+}  // namespace tc
+
+static unsigned tc_grid(const amoe_ctx* ctx, int64_t items) {
+  const int64_t want = (items + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// Common launcher of the split-operand convolutions.  xs: [NB][Hin][Win][3*C] bf16 (split activations or split dy),
+// ws: packed split weights with `rows` output channels and K = ntap_spatial*6*C.  Spatial taps are given as
+// (dh, dw, weight tap index); stride applies to the INPUT view (1 for dgrad sub-convolutions).
+struct SpatialTap { int dh, dw, widx; };
+static int launch_split(amoe_ctx* ctx, const void* xs, const void* ws, const float* scale, const float* bias, float* y,
+                        int NB, int Hin, int Win, int C, int rows, int n_wtaps, const SpatialTap* st, int nst, int sh, int sw,
+                        int Ho, int Wo, int relu, const OutMap& om, cudaStream_t stream) {
+  using namespace tc;
+  AMOE_REQUIRE(C % BLOCK_K == 0 && rows % 32 == 0 && (rows <= 256 || rows % 256 == 0),
+               "split conv: needs C %% 64 == 0 and Cout %% 32 == 0 (C=%d Cout=%d)", C, rows);
+  AMOE_REQUIRE(nst * SPLIT_TERMS <= MAX_TAPS, "split conv: %d spatial taps x 6 terms exceed %d", nst, MAX_TAPS);
+  AMOE_REQUIRE((sh == 1 || (sh == 2 && Hin % 2 == 0)) && (sw == 1 || (sw == 2 && Win % 2 == 0)), "split conv: stride 2 needs even H, W");
+  Tap taps[MAX_TAPS];
+  int n = 0;
+  for (int i = 0; i < nst; ++i)
+    for (int t = 0; t < SPLIT_TERMS; ++t) {
+      Tap& tp = taps[n++];
+      const int ho = st[i].dh, wo = st[i].dw;
+      if (sh == 1) { tp.dh = ho; tp.hp = 0; } else { tp.dh = floordiv2(ho); tp.hp = ho - 2 * tp.dh; }
+      if (sw == 1) { tp.dw = wo; tp.c_off = 0; } else { tp.dw = floordiv2(wo); tp.c_off = (wo - 2 * tp.dw) * 3 * C; }
+      tp.c_off += hTermXPart[t] * C;
+      tp.w_k = (st[i].widx * SPLIT_TERMS + t) * C;
+    }
+  const int C3 = 3 * C;
+  AView av;
+  av.dims[0] = (uint64_t)sw * C3; av.dims[1] = (uint64_t)(Win / sw); av.dims[2] = (uint64_t)sh;
+  av.dims[3] = (uint64_t)(Hin / sh); av.dims[4] = (uint64_t)NB;
+  av.strides[0] = (uint64_t)sw * C3 * 2; av.strides[1] = (uint64_t)Win * C3 * 2;
+  av.strides[2] = (uint64_t)sh * Win * C3 * 2; av.strides[3] = (uint64_t)Hin * Win * C3 * 2;
+  return launch_generic(ctx, xs, av, ws, n_wtaps * SPLIT_TERMS * C, scale, bias, nullptr, y, 1, 0, NB, Ho, Wo, rows, rows, n,
+                        taps, C / BLOCK_K, relu, 0, stream, nullptr, &om);
 }
 
 extern "C" {
@@ -507,6 +661,7 @@ int amoe_conv2d_rowwin_fwd(amoe_ctx* ctx, const void* x, const void* w, const fl
     int ho = kh - pad_h;
     taps[kh].c_off = 0;
     taps[kh].dw = 0;
+    taps[kh].w_k = kh * BLOCK_K;
     if (stride_h == 1) { taps[kh].dh = ho; taps[kh].hp = 0; } else { taps[kh].dh = floordiv2(ho); taps[kh].hp = ho - 2 * taps[kh].dh; }
   }
   // overlapping windows: dim0 = 64 contiguous elements (win pixels), dim1 = output column (stride_w pixels apart)
@@ -536,6 +691,88 @@ int amoe_conv2d_dual_fwd(amoe_ctx* ctx, const void* x, const void* w, const floa
   second.w = w_1x1; second.scale = scale2; second.bias = bias2; second.y = y2; second.relu = relu2;
   return conv_tc_launch(ctx, x, w, scale, bias, nullptr, y, G, 0, B, H, W, Cin, Cout, KH, KW, stride, stride, pad, pad, Ho, Wo,
                         relu, in_pad, out_pad, (cudaStream_t)stream, &second);
+}
+
+
+int amoe_split3_bf16(amoe_ctx* ctx, const float* x, void* out, int64_t rows, int C, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && (rows == 0 || (x && out)), "amoe_split3_bf16: NULL argument");
+  AMOE_REQUIRE(C % 8 == 0 && C > 0 && rows >= 0, "amoe_split3_bf16: C must be a positive multiple of 8");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "amoe_split3_bf16: pointers must be 16-byte aligned");
+  const int64_t total8 = rows * (C / 8);
+  if (total8 == 0) return 0;
+  tc::split3_kernel<<<tc_grid(ctx, total8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, C, total8);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_pack_conv_weight_split6(amoe_ctx* ctx, const float* w_oihw, void* dst, int Cout, int Cin, int KH, int KW,
+                                 int transposed, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && w_oihw && dst, "amoe_pack_conv_weight_split6: NULL argument");
+  const int64_t total = (int64_t)Cout * Cin * KH * KW;
+  if (total == 0) return 0;
+  tc::pack_split6_kernel<<<tc_grid(ctx, total), 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin, KH, KW,
+                                                                                transposed ? 1 : 0, total);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_conv2d_f32tc_supported(int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  return (Cin % 64 == 0 && Cout % 32 == 0 && (Cout <= 256 || Cout % 256 == 0) && KH * KW * tc::SPLIT_TERMS <= tc::MAX_TAPS &&
+          (stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0))) ? 1 : 0;
+}
+
+int amoe_conv2d_fwd_f32tc(amoe_ctx* ctx, const void* x_split, const void* w_split, const float* scale, const float* bias, float* y,
+                          int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, int relu,
+                          void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x_split && w_split && scale && bias && y, "amoe_conv2d_fwd_f32tc: NULL argument");
+  AMOE_REQUIRE(amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride), "amoe_conv2d_fwd_f32tc: unsupported shape");
+  AMOE_REQUIRE((Ho - 1) * stride - pad < H && (Wo - 1) * stride - pad < W && Ho > 0 && Wo > 0, "amoe_conv2d_fwd_f32tc: bad Ho/Wo");
+  SpatialTap st[tc::MAX_TAPS];
+  int n = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) st[n++] = SpatialTap{kh - pad, kw - pad, kh * KW + kw};
+  OutMap om;
+  om.f32 = 1;
+  return launch_split(ctx, x_split, w_split, scale, bias, y, B, H, W, Cin, Cout, KH * KW, st, n, stride, stride, Ho, Wo, relu, om,
+                      (cudaStream_t)stream);
+}
+
+int amoe_conv2d_bwd_data_f32tc(amoe_ctx* ctx, const void* dy_split, const void* wT_split, const float* ones, const float* zeros,
+                               float* dx, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                               void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && dy_split && wT_split && ones && zeros && dx, "amoe_conv2d_bwd_data_f32tc: NULL argument");
+  // roles swap: the "input" is dy [B,Ho,Wo,3*Cout], the "output channels" are Cin
+  AMOE_REQUIRE(Cout % 64 == 0 && Cin % 32 == 0 && (Cin <= 256 || Cin % 256 == 0) && (stride == 1 || stride == 2),
+               "amoe_conv2d_bwd_data_f32tc: unsupported shape");
+  AMOE_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "amoe_conv2d_bwd_data_f32tc: stride 2 needs even H, W");
+  cudaStream_t st_ = (cudaStream_t)stream;
+  // dx[ih] = sum_kh dy[(ih + pad - kh) / stride] w[kh]  over the kh with (ih + pad - kh) % stride == 0
+  for (int a = 0; a < stride; ++a)
+    for (int b = 0; b < stride; ++b) {
+      SpatialTap st[tc::MAX_TAPS];
+      int n = 0;
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((a + pad - kh) % stride != 0) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          if ((b + pad - kw) % stride != 0) continue;
+          // C++ division of possibly negative numerators: (a + pad - kh) is a multiple of stride here
+          st[n++] = SpatialTap{(a + pad - kh) / stride, (b + pad - kw) / stride, kh * KW + kw};
+        }
+      }
+      const int Hs = (H - a + stride - 1) / stride, Ws = (W - b + stride - 1) / stride;   // rows / columns of this parity class
+      OutMap om;
+      om.f32 = 1; om.o_hm = stride; om.o_ha = a; om.o_wm = stride; om.o_wa = b; om.o_H = H; om.o_W = W;
+      if (n == 0) continue;     // no filter tap reaches this parity class: the caller zero-fills dx (1x1 / stride 2)
+      AMOE_REQUIRE(n * tc::SPLIT_TERMS <= tc::MAX_TAPS, "amoe_conv2d_bwd_data_f32tc: too many taps");
+      int rc = launch_split(ctx, dy_split, wT_split, ones, zeros, dx, B, Ho, Wo, Cout, Cin, KH * KW, st, n, 1, 1, Hs, Ws, 0, om, st_);
+      if (rc) return rc;
+    }
+  return 0;
 }
 
 int amoe_conv2d_fwd(amoe_ctx* ctx, const void* x, const void* w, const float* scale,

@@ -157,6 +157,45 @@ def _pack_w(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
 BN_NONE, BN_BATCH, BN_RUNNING = 0, 1, 2
 
 
+# ---- fp32-accurate convolutions on the bf16 tensor cores (csrc/conv_tc.cu: split operands) ----
+def train_tc() -> bool:
+    """Training convolutions with Cin % 64 == 0 run on tcgen05 with split bf16 operands (fp32-accurate: the 1e-4 parity
+    gates hold); AMOE_TRAIN_TC=0 keeps every convolution on the fp32 CUDA-core kernels."""
+    import os
+    return os.environ.get("AMOE_TRAIN_TC", "1") != "0"
+
+
+_split_w_cache: dict = {}
+
+
+def _split_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """Six-term split packing of an nn.Conv2d weight (cached until the tensor changes: frozen experts pack once)."""
+    key = (weight.data_ptr(), bool(transposed))
+    ver = weight._version
+    hit = _split_w_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1].device == weight.device:
+        return hit[1]
+    Cout, Cin, KH, KW = weight.shape
+    w = _f32c(weight.detach())
+    rows, inner = (Cin, Cout) if transposed else (Cout, Cin)
+    out = torch.empty((rows, KH, KW, 6, inner), device=w.device, dtype=torch.bfloat16)
+    check(lib().amoe_pack_conv_weight_split6(ctx(w.device), ptr(w), ptr(out), Cout, Cin, KH, KW, int(transposed),
+                                             stream_ptr(w.device)), "pack_conv_weight_split6")
+    if len(_split_w_cache) > 512:
+        _split_w_cache.clear()
+    _split_w_cache[key] = (ver, out)
+    return out
+
+
+def _split3(x: torch.Tensor) -> torch.Tensor:
+    """[..., C] fp32 -> [..., 3C] bf16 = (x1 | x2 | x3)."""
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    out = torch.empty(x.shape[:-1] + (3 * C_,), device=x.device, dtype=torch.bfloat16)
+    check(lib().amoe_split3_bf16(ctx(x.device), ptr(x), ptr(out), rows, C_, stream_ptr(x.device)), "split3_bf16")
+    return out
+
+
 class _ConvBNAct(torch.autograd.Function):
     """nn.Conv2d(stride, padding, bias?) [-> nn.BatchNorm2d] [-> nn.ReLU] on NHWC fp32 activations.
 
@@ -177,9 +216,15 @@ class _ConvBNAct(torch.autograd.Function):
         cb = _f32c(bias) if bias is not None else torch.zeros(Cout, device=dev, dtype=torch.float32)
         conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
         fuse_relu = int(relu and bn_mode == BN_NONE)
-        check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
-                                    stride, stride, padding, padding, Ho, Wo, fuse_relu, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
+        use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride))
+        if use_tc:
+            check(lib().amoe_conv2d_fwd_f32tc(h, ptr(_split3(x2)), ptr(_split_weight(weight, False)), ptr(ones), ptr(cb), ptr(conv),
+                                              B, H, W, Cin, Cout, KH, KW, stride, padding, Ho, Wo, fuse_relu, st), "conv2d_fwd_f32tc")
+        else:
+            check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
+                                        stride, stride, padding, padding, Ho, Wo, fuse_relu, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
         ctx_.cfg = (stride, padding, bn_mode, relu, Cin, bias is not None)
+        ctx_.weight_ref = weight if use_tc else None
         if bn_mode == BN_NONE:
             ctx_.save_for_backward(x2, wp, conv if relu else None)
             return conv
@@ -246,9 +291,22 @@ class _ConvBNAct(torch.autograd.Function):
             dw = dwp[..., :Cin].permute(0, 3, 1, 2).contiguous()   # packed [Cout,KH,KW,Cin] -> OIHW
         dx = None
         if ctx_.needs_input_grad[0]:
-            dx = torch.empty_like(x2)
-            check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
-                                             padding, padding, Ho, Wo, st), "conv2d_bwd_data")
+            w_ref = getattr(ctx_, "weight_ref", None)
+            # dgrad on the tensor cores: roles swap (input = dy with Cout channels, output channels = Cin)
+            tc_ok = (w_ref is not None and Cout % 64 == 0 and Cx % 32 == 0 and (Cx <= 256 or Cx % 256 == 0) and
+                     KH * KW * 6 <= 64 and (stride == 1 or (stride == 2 and H % 2 == 0 and W % 2 == 0)))
+            if tc_ok:
+                holes = stride == 2 and (KH < 2 or KW < 2)         # 1x1 / stride 2: three of four parity classes get no tap
+                dx = (torch.zeros_like if holes else torch.empty_like)(x2)
+                ones_i = torch.ones(Cx, device=dev, dtype=torch.float32)
+                zeros_i = torch.zeros(Cx, device=dev, dtype=torch.float32)
+                check(lib().amoe_conv2d_bwd_data_f32tc(h, ptr(_split3(dconv)), ptr(_split_weight(w_ref, True)), ptr(ones_i),
+                                                       ptr(zeros_i), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, padding, Ho, Wo, st),
+                      "conv2d_bwd_data_f32tc")
+            else:
+                dx = torch.empty_like(x2)
+                check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
+                                                 padding, padding, Ho, Wo, st), "conv2d_bwd_data")
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 

@@ -384,3 +384,45 @@ def test_train_step_reduces_loss_and_refreshes_inference_packs():
     assert (after - before).abs().max() > 1e-4                      # the fused inference path saw the new weights
     diff_path = m(batch)["waypoints"]                               # eval + grad enabled + frozen experts: autograd path
     assert diff_path.requires_grad and rel_err(after, diff_path.detach()) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,K,stride,pad", [
+    (2, 16, 16, 64, 64, 3, 1, 1), (3, 14, 18, 64, 128, 3, 2, 1), (2, 16, 12, 128, 128, 1, 2, 0), (1, 8, 8, 256, 512, 3, 1, 1),
+    (2, 8, 8, 512, 256, 3, 1, 1), (2, 23, 40, 128, 32, 3, 1, 1), (2, 10, 10, 64, 64, 1, 1, 0)])
+def test_split_operand_tensor_core_conv_is_fp32_accurate(B, H, W, Cin, Cout, K, stride, pad, monkeypatch):
+    """fp32-accurate convolution on the bf16 tensor cores (three-way operand split, six product terms, fp32 TMEM
+    accumulation): forward and data gradient against an fp64 evaluation - as close as torch's own fp32 convolution
+    (TF32 off) or within 2e-6 relative; the CUDA-core path (AMOE_TRAIN_TC=0) gives the same answer to fp32 rounding."""
+    import torch.nn.functional as F
+    from automoe_b200.training import functional as TF
+    torch.backends.cudnn.allow_tf32 = False
+    g = _gen(100 + Cin + Cout + K + stride)
+    conv = nn.Conv2d(Cin, Cout, K, stride, pad, bias=True).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (Cin * K * K)) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    x = torch.randn((B, H, W, Cin), generator=g).to(DEV)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AMOE_TRAIN_TC", flag)
+        conv.weight.grad = None
+        xi = x.clone().requires_grad_(True)
+        y = TF.conv_bn_act(xi, conv, None, relu=False)
+        gy = torch.randn(y.shape, generator=_gen(7)).to(DEV)
+        y.backward(gy)
+        res[flag] = (y.detach(), xi.grad.detach(), conv.weight.grad.detach().clone())
+    x64 = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    y64 = F.conv2d(x64, w64, conv.bias.detach().double(), stride, pad)
+    gy64 = gy.double().permute(0, 3, 1, 2)
+    y64.backward(gy64)
+    x32 = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    y32 = F.conv2d(x32, conv.weight.detach(), conv.bias.detach(), stride, pad)
+    y32.backward(gy.permute(0, 3, 1, 2).contiguous())
+    y_ref, dx_ref = y64.detach().permute(0, 2, 3, 1), x64.grad.permute(0, 2, 3, 1)
+    for name, ours, ref, torch32 in (("y", res["1"][0], y_ref, y32.detach().permute(0, 2, 3, 1)),
+                                     ("dx", res["1"][1], dx_ref, x32.grad.permute(0, 2, 3, 1))):
+        e, e32 = rel_err(ours, ref), rel_err(torch32, ref)
+        assert e < max(2e-6, 2.0 * e32), (name, e, e32)
+        assert rel_err(res["0"][0 if name == "y" else 1], ref) < 1e-5
+    assert rel_err(res["1"][2], w64.grad) < 1e-5            # weight gradient: CUDA-core kernel in both modes
