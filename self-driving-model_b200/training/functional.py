@@ -218,8 +218,10 @@ class _ConvBNAct(torch.autograd.Function):
         fuse_relu = int(relu and bn_mode == BN_NONE)
         use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride))
         if use_tc:
-            check(lib().amoe_conv2d_fwd_f32tc(h, ptr(_split3(x2)), ptr(_split_weight(weight, False)), ptr(ones), ptr(cb), ptr(conv),
+            xs, wsplit = _split3(x2), _split_weight(weight, False)     # named: they must outlive the launch that reads them
+            check(lib().amoe_conv2d_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv),
                                               B, H, W, Cin, Cout, KH, KW, stride, padding, Ho, Wo, fuse_relu, st), "conv2d_fwd_f32tc")
+            del xs
         else:
             check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
                                         stride, stride, padding, padding, Ho, Wo, fuse_relu, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
@@ -300,9 +302,10 @@ class _ConvBNAct(torch.autograd.Function):
                 dx = (torch.zeros_like if holes else torch.empty_like)(x2)
                 ones_i = torch.ones(Cx, device=dev, dtype=torch.float32)
                 zeros_i = torch.zeros(Cx, device=dev, dtype=torch.float32)
-                check(lib().amoe_conv2d_bwd_data_f32tc(h, ptr(_split3(dconv)), ptr(_split_weight(w_ref, True)), ptr(ones_i),
-                                                       ptr(zeros_i), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, padding, Ho, Wo, st),
-                      "conv2d_bwd_data_f32tc")
+                dys, wts = _split3(dconv), _split_weight(w_ref, True)  # named: they must outlive the launches that read them
+                check(lib().amoe_conv2d_bwd_data_f32tc(h, ptr(dys), ptr(wts), ptr(ones_i), ptr(zeros_i), ptr(dx), B, H, W, Cx, Cout,
+                                                       KH, KW, stride, padding, Ho, Wo, st), "conv2d_bwd_data_f32tc")
+                del dys
             else:
                 dx = torch.empty_like(x2)
                 check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
