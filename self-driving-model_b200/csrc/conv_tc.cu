@@ -617,8 +617,11 @@ static int launch_split(amoe_ctx* ctx, const void* xs, const void* ws, const flo
   AMOE_REQUIRE((sh == 1 || (sh == 2 && Hin % 2 == 0)) && (sw == 1 || (sw == 2 && Win % 2 == 0)), "split conv: stride 2 needs even H, W");
   Tap taps[MAX_TAPS];
   int n = 0;
-  for (int i = 0; i < nst; ++i)
-    for (int t = 0; t < SPLIT_TERMS; ++t) {
+  // Term-major, smallest terms first: the tensor core truncates (rounds toward zero) when it adds into the fp32
+  // accumulator, an error relative to the running sum - so the 2^-16 and 2^-8 terms are accumulated while the sum is
+  // still small, and only the nst*k_chunks*4 leading-term MMAs (what any bf16 GEMM pays) add into the full-size sum.
+  for (int t = SPLIT_TERMS - 1; t >= 0; --t)
+    for (int i = 0; i < nst; ++i) {
       Tap& tp = taps[n++];
       const int ho = st[i].dh, wo = st[i].dw;
       if (sh == 1) { tp.dh = ho; tp.hp = 0; } else { tp.dh = floordiv2(ho); tp.hp = ho - 2 * tp.dh; }

@@ -165,15 +165,18 @@ def train_tc() -> bool:
     return os.environ.get("AMOE_TRAIN_TC", "1") != "0"
 
 
-_split_w_cache: dict = {}
-
-
 def _split_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
-    """Six-term split packing of an nn.Conv2d weight (cached until the tensor changes: frozen experts pack once)."""
-    key = (weight.data_ptr(), bool(transposed))
-    ver = weight._version
-    hit = _split_w_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1].device == weight.device:
+    """Six-term split packing of an nn.Conv2d weight.  Cached ON the tensor object (an attribute dies with it; a cache keyed
+    by data_ptr would hand a new module the packed weights of a freed one) until its version changes: frozen experts pack once."""
+    cache = getattr(weight, "_amoe_split6", None)
+    if cache is None:
+        cache = {}
+        try:
+            weight._amoe_split6 = cache
+        except Exception:            # tensors that do not take attributes: pack every time
+            pass
+    hit = cache.get(bool(transposed))
+    if hit is not None and hit[0] == (weight._version, weight.data_ptr()):
         return hit[1]
     Cout, Cin, KH, KW = weight.shape
     w = _f32c(weight.detach())
@@ -181,9 +184,7 @@ def _split_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
     out = torch.empty((rows, KH, KW, 6, inner), device=w.device, dtype=torch.bfloat16)
     check(lib().amoe_pack_conv_weight_split6(ctx(w.device), ptr(w), ptr(out), Cout, Cin, KH, KW, int(transposed),
                                              stream_ptr(w.device)), "pack_conv_weight_split6")
-    if len(_split_w_cache) > 512:
-        _split_w_cache.clear()
-    _split_w_cache[key] = (ver, out)
+    cache[bool(transposed)] = ((weight._version, weight.data_ptr()), out)
     return out
 
 
