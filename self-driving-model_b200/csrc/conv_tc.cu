@@ -545,14 +545,6 @@ __device__ __constant__ int kTermXPart[SPLIT_TERMS] = {0, 0, 1, 0, 1, 2};   // a
 __device__ __constant__ int kTermWPart[SPLIT_TERMS] = {0, 1, 0, 2, 1, 0};   // weight part of each term
 static const int hTermXPart[SPLIT_TERMS] = {0, 0, 1, 0, 1, 2};
 
-__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
-  a = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(a);          // exact (Sterbenz-like: a is v rounded to 8 bits)
-  b = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b);         // exact
-  c = __float2bfloat16_rn(r2);
-}
-
 // x [rows][C] fp32 -> out [rows][3C] bf16 = (x1 | x2 | x3); C % 8 == 0; one thread = 8 channels
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C,
                                                      int64_t total8) {

@@ -16,6 +16,7 @@ void amoe_set_error(const char* fmt, ...) {
 int amoe_conv_tc_init(amoe_ctx* ctx);    // conv_tc.cu
 int amoe_conv_flat_init(amoe_ctx* ctx);  // conv_flat.cu
 int amoe_stem_init(amoe_ctx* ctx);       // stem_tc.cu
+int amoe_wgrad_tc_init(amoe_ctx* ctx);   // wgrad_tc.cu
 
 extern "C" {
 
@@ -44,7 +45,8 @@ int amoe_create(int device, amoe_ctx** out) {
     return -1;
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
-  if (amoe_conv_tc_init(ctx) != 0 || amoe_conv_flat_init(ctx) != 0 || amoe_stem_init(ctx) != 0) {
+  if (amoe_conv_tc_init(ctx) != 0 || amoe_conv_flat_init(ctx) != 0 || amoe_stem_init(ctx) != 0 ||
+      amoe_wgrad_tc_init(ctx) != 0) {
     delete ctx;
     return -1;
   }

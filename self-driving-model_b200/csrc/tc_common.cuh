@@ -150,4 +150,13 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// v = a + b + c with a, b, c bf16: the three-way split of the fp32-accurate training kernels (24 significant bits)
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a);          // exact: a is v rounded to 8 significant bits
+  b = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b);         // exact
+  c = __float2bfloat16_rn(r2);
+}
+
 }  // namespace tc

@@ -12,7 +12,15 @@
 namespace {
 
 constexpr int RED_THREADS = 256;
-constexpr int RED_ROWS = 1024;  // rows of [M, C] per CTA of the column reductions
+constexpr int RED_ROWS_MAX = 1024;
+// rows of [M, C] per CTA of the column reductions: enough CTAs to cover the GPU a few times (a fixed 1024 rows left the
+// deep layers - a few thousand rows of 512 channels - to two CTAs: 84 us per BatchNorm statistics pass on average)
+static inline int red_rows(int64_t M) {
+  int64_t r = (M + 591) / 592;
+  if (r < 16) r = 16;
+  if (r > RED_ROWS_MAX) r = RED_ROWS_MAX;
+  return (int)r;
+}
 
 // Column sums of up to two per-element quantities over the rows of an [M, C] fp32 matrix.
 //   MODE 0: s0 = sum x,           s1 = sum x*x                       (BatchNorm statistics)
@@ -26,11 +34,11 @@ __global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const fl
                                                                         const float* __restrict__ y,
                                                                         const float* __restrict__ mean,
                                                                         const float* __restrict__ rstd, int64_t M, int C,
-                                                                        double* __restrict__ partial) {
+                                                                        double* __restrict__ partial, int rows_per_cta) {
   __shared__ double sh0[RED_THREADS], sh1[RED_THREADS];
   const int cb = min(C, RED_THREADS);          // channels handled per pass (C is a multiple of cb or < 256)
   const int rl = threadIdx.x / cb, nrl = RED_THREADS / cb;
-  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS, r1 = min(M, r0 + RED_ROWS);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   for (int c0 = 0; c0 < C; c0 += cb) {
     const int c = c0 + threadIdx.x % cb;
     // double accumulators: these sums feed differences (variance; g - mean(g) in the BatchNorm backward,
@@ -373,7 +381,7 @@ int wgrad_slices(int sm_count, int Cout, int Kw, int64_t Mg, int* rows_per_slice
 extern "C" {
 
 // partial sums are doubles: 2 floats each, +2 so the caller's float buffer can be aligned up to 8 bytes
-int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { return ((M + RED_ROWS - 1) / RED_ROWS) * 4 * (int64_t)C + 2; }
+int64_t amoe_colreduce_workspace_floats(int64_t M, int C) { const int rr = red_rows(M); return ((M + rr - 1) / rr) * 4 * (int64_t)C + 2; }
 
 int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float momentum, float eps, float* y, float* save_mean, float* save_rstd,
@@ -384,8 +392,8 @@ int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const f
   AMOE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "amoe_bn_train_fwd: running stats come together");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<0><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace));
+  const int rr = red_rows(M), nblk = (int)((M + rr - 1) / rr);
+  colreduce_partial_kernel<0><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace), rr);
   AMOE_LAUNCH_OK(ctx);
   bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, M, C, eps, momentum, save_mean, save_rstd,
                                                         running_mean, running_var);
@@ -416,8 +424,8 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
   AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_bwd: C=%d must be a multiple of 4", C);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<1><<<nblk, RED_THREADS, 0, st>>>(x, dy, y_relu, mean, rstd, M, C, ws64(workspace));
+  const int rr = red_rows(M), nblk = (int)((M + rr - 1) / rr);
+  colreduce_partial_kernel<1><<<nblk, RED_THREADS, 0, st>>>(x, dy, y_relu, mean, rstd, M, C, ws64(workspace), rr);
   AMOE_LAUNCH_OK(ctx);
   colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, C, 1.f, dbeta, dgamma);
   AMOE_LAUNCH_OK(ctx);
@@ -436,8 +444,8 @@ int amoe_colsum(amoe_ctx* ctx, const float* x, float* out, float* workspace, int
   AMOE_REQUIRE(C >= 1, "amoe_colsum: C=%d", C);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = (int)((M + RED_ROWS - 1) / RED_ROWS);
-  colreduce_partial_kernel<2><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace));
+  const int rr = red_rows(M), nblk = (int)((M + rr - 1) / rr);
+  colreduce_partial_kernel<2><<<nblk, RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace), rr);
   AMOE_LAUNCH_OK(ctx);
   colreduce_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws64(workspace), nblk, C, scale, out, nullptr);
   AMOE_LAUNCH_OK(ctx);

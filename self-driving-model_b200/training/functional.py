@@ -211,13 +211,13 @@ class _ConvBNAct(torch.autograd.Function):
         Cout, Cin, KH, KW = weight.shape
         dev = x2.device
         h, st = ctx(dev), stream_ptr(dev)
-        wp = _pack_w(weight, Cx)
         Ho, Wo = (H + 2 * padding - KH) // stride + 1, (W + 2 * padding - KW) // stride + 1
         ones = torch.ones(Cout, device=dev, dtype=torch.float32)
         cb = _f32c(bias) if bias is not None else torch.zeros(Cout, device=dev, dtype=torch.float32)
         conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
         fuse_relu = int(relu and bn_mode == BN_NONE)
         use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride))
+        wp = None if use_tc else _pack_w(weight, Cx)       # CUDA-core layout; packed lazily in backward on the tensor-core path
         if use_tc:
             xs, wsplit = _split3(x2), _split_weight(weight, False)     # named: they must outlive the launch that reads them
             check(lib().amoe_conv2d_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv),
@@ -227,7 +227,8 @@ class _ConvBNAct(torch.autograd.Function):
             check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
                                         stride, stride, padding, padding, Ho, Wo, fuse_relu, _cabi.F32, 1, 0, 0, st), "conv2d_fwd")
         ctx_.cfg = (stride, padding, bn_mode, relu, Cin, bias is not None)
-        ctx_.weight_ref = weight if use_tc else None
+        ctx_.weight_ref = weight if train_tc() else None
+        ctx_.wshape = (Cout, KH, KW, Cx)
         if bn_mode == BN_NONE:
             ctx_.save_for_backward(x2, wp, conv if relu else None)
             return conv
@@ -279,22 +280,41 @@ class _ConvBNAct(torch.autograd.Function):
             check(lib().amoe_bn_bwd(h, ptr(dy), ptr(conv), ptr(y), ptr(g2), ptr(mean), ptr(rstd), ptr(dconv), ptr(dgamma),
                                     ptr(dbeta), ptr(ws), M, Cout, int(bn_mode == BN_BATCH), st), "bn_bwd")
         B, H, W, Cx = x2.shape
-        KH, KW = wp.shape[1], wp.shape[2]
+        KH, KW = ctx_.wshape[1], ctx_.wshape[2]
+        w_ref = getattr(ctx_, "weight_ref", None)
+
+        def packed_w():
+            return wp if wp is not None else _pack_w(w_ref, Cx)
         dbias = None
         if has_bias and ctx_.needs_input_grad[2]:
             dbias = torch.empty(Cout, device=dev, dtype=torch.float32)
             check(lib().amoe_colsum(h, ptr(dconv), ptr(dbias), ptr(ws), M, Cout, 1.0, st), "colsum")
         dw = None
-        if ctx_.needs_input_grad[1]:
+        wg_tc = (ctx_.needs_input_grad[1] and w_ref is not None and KH == 3 and KW == 3 and stride == 1 and padding == 1 and
+                 Cx == Cin and bool(lib().amoe_conv3x3_wgrad_f32tc_supported(Cx, Cout)))
+        if wg_tc:
+            # weight gradient on the tensor cores: a GEMM per tap over the padded position grid (csrc/wgrad_tc.cu)
+            Ppad = int(lib().amoe_wgrad_padded_positions(B, H, W, 1))
+            xT = torch.empty((3 * Cx, Ppad), device=dev, dtype=torch.bfloat16)
+            dyT = torch.empty((3 * Cout, Ppad), device=dev, dtype=torch.bfloat16)
+            check(lib().amoe_transpose_split3_padded(h, ptr(x2), ptr(xT), B, H, W, Cx, 1, Ppad, st), "transpose_split3_padded(x)")
+            check(lib().amoe_transpose_split3_padded(h, ptr(dconv), ptr(dyT), B, Ho, Wo, Cout, 1, Ppad, st), "transpose_split3_padded(dy)")
+            n_ws = int(lib().amoe_conv3x3_wgrad_f32tc_workspace_floats(h, Cx, Cout, Ppad))
+            ws2 = torch.empty(n_ws, device=dev, dtype=torch.float32)
+            dwp = torch.empty(ctx_.wshape, device=dev, dtype=torch.float32)
+            check(lib().amoe_conv3x3_wgrad_f32tc(h, ptr(dyT), ptr(xT), ptr(dwp), ptr(ws2), n_ws, W, Cx, Cout, Ppad, st),
+                  "conv3x3_wgrad_f32tc")
+            dw = dwp.permute(0, 3, 1, 2).contiguous()
+            del xT, dyT
+        elif ctx_.needs_input_grad[1]:
             n_ws = lib().amoe_conv2d_bwd_weight_workspace_floats(h, B, Cx, Cout, KH, KW, Ho, Wo)
             ws2 = torch.empty(max(1, n_ws), device=dev, dtype=torch.float32)
-            dwp = torch.empty_like(wp)
+            dwp = torch.empty(ctx_.wshape, device=dev, dtype=torch.float32)
             check(lib().amoe_conv2d_bwd_weight(h, ptr(dconv), ptr(x2), ptr(dwp), ptr(ws2), n_ws, B, H, W, Cx, Cout, KH, KW,
                                                stride, stride, padding, padding, Ho, Wo, st), "conv2d_bwd_weight")
             dw = dwp[..., :Cin].permute(0, 3, 1, 2).contiguous()   # packed [Cout,KH,KW,Cin] -> OIHW
         dx = None
         if ctx_.needs_input_grad[0]:
-            w_ref = getattr(ctx_, "weight_ref", None)
             # dgrad on the tensor cores: roles swap (input = dy with Cout channels, output channels = Cin)
             tc_ok = (w_ref is not None and Cout % 64 == 0 and Cx % 32 == 0 and (Cx <= 256 or Cx % 256 == 0) and
                      KH * KW * 6 <= 64 and (stride == 1 or (stride == 2 and H % 2 == 0 and W % 2 == 0)))
@@ -309,7 +329,8 @@ class _ConvBNAct(torch.autograd.Function):
                 del dys
             else:
                 dx = torch.empty_like(x2)
-                check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wp), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
+                wpk = packed_w()
+                check(lib().amoe_conv2d_bwd_data(h, ptr(dconv), ptr(wpk), ptr(dx), B, H, W, Cx, Cout, KH, KW, stride, stride,
                                                  padding, padding, Ho, Wo, st), "conv2d_bwd_data")
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
