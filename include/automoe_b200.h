@@ -418,19 +418,18 @@ int amoe_conv2d_bwd_data_f32tc(amoe_ctx*, const void* dy_split, const void* wT_s
                                const float* zeros, float* dx, int B, int H, int W, int Cin, int Cout,
                                int KH, int KW, int stride, int pad, int Ho, int Wo, void* stream);
 /* Weight gradient of a 3x3 / stride-1 / pad-1 convolution on the tensor cores, fp32-accurate (csrc/wgrad_tc.cu): a GEMM per
- * filter tap over the padded position grid as K, operands transposed and split in three bf16 parts:
- *   amoe_wgrad_padded_positions:    Ppad for a [NB,H,W,*] tensor with a border of `pad` pixels (whole 64-position chunks)
- *   amoe_transpose_split3_padded:   x [NB,H,W,C] fp32 -> [3*C][Ppad] bf16 (zero border / tail; one memset + one kernel)
- *   amoe_conv3x3_wgrad_f32tc:       dyT3 [3*Cout][Ppad], xT3 [3*Cin][Ppad] (both pad = 1) -> dw [Cout][3][3][Cin] fp32;
- *                                   K split over CTAs, partials summed in a fixed order (workspace size from
- *                                   amoe_conv3x3_wgrad_f32tc_workspace_floats).  Cin, Cout multiples of 64, <= 512. */
-int64_t amoe_wgrad_padded_positions(int NB, int H, int W, int pad);
-int amoe_transpose_split3_padded(amoe_ctx*, const float* x, void* out, int NB, int H, int W, int C,
-                                 int pad, int64_t Ppad, void* stream);
+ * filter tap with the padded position grid as K; the operands are the padded NHWC tensors themselves (MN-major UMMA
+ * operands), split in three bf16 parts per value:
+ *   amoe_split3_padded:        x [NB,H,W,C] fp32 -> [NB,H+2,W+2,3C] bf16 = (x1 | x2 | x3), zero border (memset + kernel)
+ *   amoe_conv3x3_wgrad_f32tc:  dy3 [NB,H+2,W+2,3*Cout], x3 [NB,H+2,W+2,3*Cin]; positions = NB*(H+2)*(W+2)
+ *                              -> dw [Cout][3][3][Cin] fp32; K split over CTAs, partials summed in a fixed order
+ *                              (workspace size from amoe_conv3x3_wgrad_f32tc_workspace_floats).
+ *   Cin, Cout multiples of 64, <= 512. */
+int amoe_split3_padded(amoe_ctx*, const float* x, void* out, int NB, int H, int W, int C, void* stream);
 int amoe_conv3x3_wgrad_f32tc_supported(int Cin, int Cout);
-int64_t amoe_conv3x3_wgrad_f32tc_workspace_floats(amoe_ctx*, int Cin, int Cout, int64_t Ppad);
-int amoe_conv3x3_wgrad_f32tc(amoe_ctx*, const void* dyT3, const void* xT3, float* dw, float* workspace,
-                             int64_t workspace_floats, int W, int Cin, int Cout, int64_t Ppad,
+int64_t amoe_conv3x3_wgrad_f32tc_workspace_floats(amoe_ctx*, int Cin, int Cout, int64_t positions);
+int amoe_conv3x3_wgrad_f32tc(amoe_ctx*, const void* dy3, const void* x3, float* dw, float* workspace,
+                             int64_t workspace_floats, int W, int Cin, int Cout, int64_t positions,
                              void* stream);
 /* nn.AdaptiveAvgPool2d(1) on NHWC fp32: x [B,HW,C] -> out [B,C]; backward broadcasts dy/HW. */
 int amoe_gap_fwd(amoe_ctx*, const float* x, float* out, int B, int HW, int C, void* stream);

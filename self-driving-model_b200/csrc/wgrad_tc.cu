@@ -5,10 +5,13 @@
 //
 // on the PHYSICALLY padded position grid (n, y, x) -> P = (n*Hp + y)*Wp + x with Hp = H+2, Wp = W+2 and zeros on the
 // border, so a filter tap is a pure shift along P.  That makes dW a plain GEMM per tap with the positions as the K
-// dimension: D[co][ci] = A[co][K] * B[ci][K + shift]^T.  Both operands are stored TRANSPOSED and split in three bf16
-// parts (amoe_transpose_split3_padded): dyT3 [3*Cout][Ppad], xT3 [3*Cin][Ppad] - K-major rows, so every operand tile is
-// one 2-D TMA box and the tap shift is just the box's start coordinate.  The six product terms of the three-way split
-// (see conv_tc.cu) are six passes over the same K range, smallest terms first; accumulation in fp32 TMEM.
+// dimension, D[co][ci] = sum_P A[P][co] * B[P + shift][ci], whose operands are the padded NHWC tensors THEMSELVES, read
+// as MN-major UMMA operands (M / N = channels contiguous, K = positions = rows): a TMA box of 64 positions x 64 channels
+// is one swizzled 8 KB block, a 128-wide M tile is two such blocks (descriptor LBO = 8 KB, SBO = 1 KB between 8-row
+// groups), and the tap shift is the box's ROW coordinate - no transposed copies.  (A K-major formulation needs the
+// shift on the contiguous axis; TMA rejects start coordinates that are not 16-byte aligned there.)
+// Both tensors are stored split in three bf16 parts per value, [P][x1 | x2 | x3] (amoe_split3_padded); the six product
+// terms of the split (see conv_tc.cu) are six passes over the same K range, smallest terms first, fp32 TMEM accumulation.
 //
 // K is huge (0.5 M positions for a 720x1280 batch of 8 at layer1) and dW tiny, so the work is split along K: a tile is
 // (k-split, tap, 128 output channels, <= 256 input channels); its partial D goes to a workspace
@@ -31,6 +34,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 200 * 1024;
 constexpr int TERMS = 6;
 
+constexpr int BLK_BYTES = BLOCK_K * 128;       // one 64-position x 64-channel operand block
+
 struct Params {
   int Cout, Cin, ntaps;
   int m_tiles, n_tiles, block_n;
@@ -40,6 +45,19 @@ struct Params {
   int shift[9];                                 // position shift of every tap
   float* partial;                               // [ksplit][ntaps][Cout][Cin]
 };
+
+// MN-major, 128B-swizzled operand: rows = K (positions), 128 bytes = 64 channels per row; 8-row groups 1024 B apart (SBO),
+// 64-channel blocks BLK_BYTES apart (LBO)
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(BLK_BYTES >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor of make_idesc with both operands MN-major (bits 15 / 16)
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 
 __device__ __constant__ int kXPart[TERMS] = {0, 0, 1, 0, 1, 2};   // dy part of term t (A operand)
 __device__ __constant__ int kWPart[TERMS] = {0, 1, 0, 2, 1, 0};   // x part of term t (B operand)
@@ -93,20 +111,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int kc0 = tl.ks * p.chunks_per_split, kc1 = min(kc0 + p.chunks_per_split, p.total_chunks);
         const int shift = p.shift[tl.tap];
         for (int term = TERMS - 1; term >= 0; --term) {       // smallest terms first (see conv_tc.cu)
-          const int arow = kXPart[term] * p.Cout + tl.mt * BLOCK_M;
-          const int brow = kWPart[term] * p.Cin + tl.nt * p.block_n;
+          const int acol = kXPart[term] * p.Cout + tl.mt * BLOCK_M;     // channel (column) offsets of this term's parts
+          const int bcol = kWPart[term] * p.Cin + tl.nt * p.block_n;
           for (int kc = kc0; kc < kc1; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
-            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kc * BLOCK_K, arow);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, bar_full + 8 * stage, kc * BLOCK_K + shift, brow);
+            const int row = kc * BLOCK_K;
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, acol, row);
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES + BLK_BYTES, &tmA, bar_full + 8 * stage, acol + 64, row);
+            for (int j = 0; j < p.block_n; j += 64)
+              tma_load_2d(smem_b + stage * b_stage_bytes + (uint32_t)(j >> 6) * BLK_BYTES, &tmB, bar_full + 8 * stage, bcol + j,
+                          row + shift);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(p.block_n);
+    const uint32_t idesc = make_idesc_mn(p.block_n);
     int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -121,11 +143,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();
-        const uint64_t a_desc = make_sw128_desc(smem_a + stage * A_STAGE_BYTES);
-        const uint64_t b_desc = make_sw128_desc(smem_b + stage * b_stage_bytes);
+        const uint64_t a_desc = make_mn_desc(smem_a + stage * A_STAGE_BYTES);
+        const uint64_t b_desc = make_mn_desc(smem_b + stage * b_stage_bytes);
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-          umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (uint32_t)((k | kk) != 0));
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)     // 16 positions = 16 rows of 128 bytes further: +2048 B = +128 in the >>4 field
+          umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 128), b_desc + (uint64_t)(kk * 128), idesc, (uint32_t)((k | kk) != 0));
         umma_commit(bar_empty + 8 * stage);
         if (k == k_iters - 1) umma_commit(bar_tfull + 8 * as);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -192,38 +214,29 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// x [NB][H][W][C] fp32 -> out [3*C][Ppad] bf16: out[part*C + c][(n*(H+2*pad) + y + pad)*(W+2*pad) + xw + pad] = part of x;
-// the caller zero-fills `out` first (borders and the tail up to Ppad stay zero).  One CTA = 64 positions of one image row
-// x 32 channels, transposed through shared memory (reads coalesced along c, writes along positions).
-__global__ void __launch_bounds__(256) transpose_split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int H, int W,
-                                                               int C, int pad, int64_t Ppad) {
-  __shared__ float tile[64][33];
-  const int c0 = blockIdx.y * 32;
-  const int wtiles = (W + 63) / 64;
-  const int64_t rowid = blockIdx.x / wtiles;          // n*H + y
-  const int w0 = (blockIdx.x % wtiles) * 64;
-  const int n = (int)(rowid / H), y = (int)(rowid % H);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-  for (int j = ty; j < 64; j += 8) {
-    const int w = w0 + j;
-    tile[j][tx] = (w < W && c0 + tx < C) ? __ldg(x + (rowid * W + w) * (int64_t)C + c0 + tx) : 0.f;
-  }
-  __syncthreads();
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const int64_t pbase = ((int64_t)n * Hp + y + pad) * Wp + pad + w0;
-  // thread -> (channel = ty + 8*i, positions 2*tx, 2*tx+1): 4-byte stores, 128 bytes per warp row
-  for (int cc = ty; cc < 32; cc += 8) {
-    const int c = c0 + cc;
-    if (c >= C) continue;
-    for (int half = 0; half < 2; ++half) {
-      const int j = half * 32 + tx;
-      if (w0 + j >= W) continue;
-      __nv_bfloat16 a, b, d;
-      tc::split3(tile[j][cc], a, b, d);
-      out[(int64_t)c * Ppad + pbase + j] = a;
-      out[((int64_t)C + c) * Ppad + pbase + j] = b;
-      out[((int64_t)2 * C + c) * Ppad + pbase + j] = d;
-    }
+// x [NB][H][W][C] fp32 -> out [NB][H+2][W+2][3C] bf16 = (x1 | x2 | x3) per pixel, physical zero border (the caller
+// zero-fills `out`); one thread = 8 channels of one pixel
+__global__ void __launch_bounds__(256) split3_padded_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int H, int W,
+                                                            int C, int64_t total8) {
+  const int c8n = C >> 3;
+  const int Hp = H + 2, Wp = W + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / c8n;
+    const int c0 = (int)(i - pix * c8n) << 3;
+    const int w = (int)(pix % W);
+    const int64_t r = pix / W;
+    const int y = (int)(r % H);
+    const int64_t n = r / H;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0));
+    const float4 u1 = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0 + 4));
+    const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    __align__(16) __nv_bfloat16 a[8], b[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tc::split3(v[j], a[j], b[j], c[j]);
+    __nv_bfloat16* o = out + ((n * Hp + y + 1) * Wp + w + 1) * (3 * (int64_t)C) + c0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(b);
+    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(c);
   }
 }
 
@@ -238,22 +251,17 @@ int amoe_wgrad_tc_init(amoe_ctx* ctx) {
 
 extern "C" {
 
-int64_t amoe_wgrad_padded_positions(int NB, int H, int W, int pad) {
-  const int64_t p = (int64_t)NB * (H + 2 * pad) * (W + 2 * pad);
-  return (p + 63) / 64 * 64 + 64;      // whole K chunks, plus one chunk of zeros behind the last shift
-}
-
-int amoe_transpose_split3_padded(amoe_ctx* ctx, const float* x, void* out, int NB, int H, int W, int C, int pad, int64_t Ppad,
-                                 void* stream) {
+int amoe_split3_padded(amoe_ctx* ctx, const float* x, void* out, int NB, int H, int W, int C, void* stream) {
   AMOE_ENTER(ctx);
-  AMOE_REQUIRE(ctx && x && out, "amoe_transpose_split3_padded: NULL argument");
-  AMOE_REQUIRE(NB > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && Ppad >= amoe_wgrad_padded_positions(NB, H, W, pad) && Ppad % 8 == 0,
-               "amoe_transpose_split3_padded: bad geometry");
+  AMOE_REQUIRE(ctx && x && out, "amoe_split3_padded: NULL argument");
+  AMOE_REQUIRE(NB > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "amoe_split3_padded: bad geometry (C %% 8 == 0)");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "amoe_split3_padded: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  AMOE_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)3 * C * Ppad * 2, st));
-  const int wtiles = (W + 63) / 64;
-  dim3 grid((unsigned)((int64_t)NB * H * wtiles), (unsigned)((C + 31) / 32));
-  wg::transpose_split3_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, H, W, C, pad, Ppad);
+  AMOE_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)NB * (H + 2) * (W + 2) * 3 * C * 2, st));
+  const int64_t total8 = (int64_t)NB * H * W * (C / 8);
+  const int64_t want = (total8 + 255) / 256;
+  wg::split3_padded_kernel<<<(unsigned)std::min<int64_t>(want, (int64_t)ctx->sm_count * 16), 256, 0, st>>>(x, (__nv_bfloat16*)out, H, W, C, total8);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
@@ -272,22 +280,24 @@ static void wgrad_split(const amoe_ctx* ctx, int Cin, int Cout, int64_t Ppad, in
   ksplit = (int)((chunks + chunks_per_split - 1) / chunks_per_split);
 }
 
-int64_t amoe_conv3x3_wgrad_f32tc_workspace_floats(amoe_ctx* ctx, int Cin, int Cout, int64_t Ppad) {
+int64_t amoe_conv3x3_wgrad_f32tc_workspace_floats(amoe_ctx* ctx, int Cin, int Cout, int64_t positions) {
   if (!ctx) return -1;
   int ksplit, cps;
-  wgrad_split(ctx, Cin, Cout, Ppad, ksplit, cps);
+  wgrad_split(ctx, Cin, Cout, (positions + 63) / 64 * 64, ksplit, cps);
   return (int64_t)ksplit * 9 * Cout * Cin;
 }
 
-// dyT3 [3*Cout][Ppad], xT3 [3*Cin][Ppad] (amoe_transpose_split3_padded with pad = 1 of dy / x of a 3x3, stride 1, pad 1
-// convolution) -> dw [Cout][3][3][Cin] fp32
-int amoe_conv3x3_wgrad_f32tc(amoe_ctx* ctx, const void* dyT3, const void* xT3, float* dw, float* workspace, int64_t workspace_floats,
-                             int W, int Cin, int Cout, int64_t Ppad, void* stream) {
+// dy3 [NB][H+2][W+2][3*Cout], x3 [NB][H+2][W+2][3*Cin] bf16 (amoe_split3_padded of dy / x of a 3x3, stride 1, pad 1
+// convolution); positions = NB*(H+2)*(W+2) -> dw [Cout][3][3][Cin] fp32
+int amoe_conv3x3_wgrad_f32tc(amoe_ctx* ctx, const void* dy3, const void* x3, float* dw, float* workspace, int64_t workspace_floats,
+                             int W, int Cin, int Cout, int64_t positions, void* stream) {
   AMOE_ENTER(ctx);
   using namespace wg;
-  AMOE_REQUIRE(ctx && dyT3 && xT3 && dw && workspace, "amoe_conv3x3_wgrad_f32tc: NULL argument");
-  AMOE_REQUIRE(amoe_conv3x3_wgrad_f32tc_supported(Cin, Cout) && Ppad % 64 == 0 && Ppad > 0, "amoe_conv3x3_wgrad_f32tc: unsupported shape");
-  AMOE_REQUIRE(workspace_floats >= amoe_conv3x3_wgrad_f32tc_workspace_floats(ctx, Cin, Cout, Ppad), "amoe_conv3x3_wgrad_f32tc: workspace too small");
+  AMOE_REQUIRE(ctx && dy3 && x3 && dw && workspace, "amoe_conv3x3_wgrad_f32tc: NULL argument");
+  AMOE_REQUIRE(amoe_conv3x3_wgrad_f32tc_supported(Cin, Cout) && positions > 0, "amoe_conv3x3_wgrad_f32tc: unsupported shape");
+  AMOE_REQUIRE(workspace_floats >= amoe_conv3x3_wgrad_f32tc_workspace_floats(ctx, Cin, Cout, positions), "amoe_conv3x3_wgrad_f32tc: workspace too small");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(dy3) & 15) == 0 && (reinterpret_cast<uintptr_t>(x3) & 15) == 0, "amoe_conv3x3_wgrad_f32tc: unaligned operand");
+  const int64_t Ppad = (positions + 63) / 64 * 64;
   Params p;
   p.Cout = Cout; p.Cin = Cin; p.ntaps = 9;
   p.m_tiles = (Cout + 127) / 128;
@@ -304,21 +314,21 @@ int amoe_conv3x3_wgrad_f32tc(amoe_ctx* ctx, const void* dyT3, const void* xT3, f
   p.stages = std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes);
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Ppad, (cuuint64_t)3 * Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)Ppad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M};
+    cuuint64_t dims[2] = {(cuuint64_t)3 * Cout, (cuuint64_t)positions};
+    cuuint64_t strides[1] = {(cuuint64_t)3 * Cout * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ctx->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dyT3), dims, strides, box, estr,
+    CUresult r = ctx->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy3), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_wgrad_f32tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Ppad, (cuuint64_t)3 * Cin};
-    cuuint64_t strides[1] = {(cuuint64_t)Ppad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    cuuint64_t dims[2] = {(cuuint64_t)3 * Cin, (cuuint64_t)positions};
+    cuuint64_t strides[1] = {(cuuint64_t)3 * Cin * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ctx->encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(xT3), dims, strides, box, estr,
+    CUresult r = ctx->encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x3), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_wgrad_f32tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);

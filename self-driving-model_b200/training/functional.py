@@ -294,18 +294,18 @@ class _ConvBNAct(torch.autograd.Function):
                  Cx == Cin and bool(lib().amoe_conv3x3_wgrad_f32tc_supported(Cx, Cout)))
         if wg_tc:
             # weight gradient on the tensor cores: a GEMM per tap over the padded position grid (csrc/wgrad_tc.cu)
-            Ppad = int(lib().amoe_wgrad_padded_positions(B, H, W, 1))
-            xT = torch.empty((3 * Cx, Ppad), device=dev, dtype=torch.bfloat16)
-            dyT = torch.empty((3 * Cout, Ppad), device=dev, dtype=torch.bfloat16)
-            check(lib().amoe_transpose_split3_padded(h, ptr(x2), ptr(xT), B, H, W, Cx, 1, Ppad, st), "transpose_split3_padded(x)")
-            check(lib().amoe_transpose_split3_padded(h, ptr(dconv), ptr(dyT), B, Ho, Wo, Cout, 1, Ppad, st), "transpose_split3_padded(dy)")
-            n_ws = int(lib().amoe_conv3x3_wgrad_f32tc_workspace_floats(h, Cx, Cout, Ppad))
+            P = B * (H + 2) * (W + 2)
+            x3 = torch.empty((B, H + 2, W + 2, 3 * Cx), device=dev, dtype=torch.bfloat16)
+            dy3 = torch.empty((B, H + 2, W + 2, 3 * Cout), device=dev, dtype=torch.bfloat16)
+            check(lib().amoe_split3_padded(h, ptr(x2), ptr(x3), B, H, W, Cx, st), "split3_padded(x)")
+            check(lib().amoe_split3_padded(h, ptr(dconv), ptr(dy3), B, Ho, Wo, Cout, st), "split3_padded(dy)")
+            n_ws = int(lib().amoe_conv3x3_wgrad_f32tc_workspace_floats(h, Cx, Cout, P))
             ws2 = torch.empty(n_ws, device=dev, dtype=torch.float32)
             dwp = torch.empty(ctx_.wshape, device=dev, dtype=torch.float32)
-            check(lib().amoe_conv3x3_wgrad_f32tc(h, ptr(dyT), ptr(xT), ptr(dwp), ptr(ws2), n_ws, W, Cx, Cout, Ppad, st),
+            check(lib().amoe_conv3x3_wgrad_f32tc(h, ptr(dy3), ptr(x3), ptr(dwp), ptr(ws2), n_ws, W, Cx, Cout, P, st),
                   "conv3x3_wgrad_f32tc")
             dw = dwp.permute(0, 3, 1, 2).contiguous()
-            del xT, dyT
+            del x3, dy3
         elif ctx_.needs_input_grad[1]:
             n_ws = lib().amoe_conv2d_bwd_weight_workspace_floats(h, B, Cx, Cout, KH, KW, Ho, Wo)
             ws2 = torch.empty(max(1, n_ws), device=dev, dtype=torch.float32)
