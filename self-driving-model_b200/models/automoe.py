@@ -208,6 +208,7 @@ class AutoMoE(nn.Module):
     # explicit opt-out: frozen experts keep their running statistics and run through the (much faster) inference
     # kernels - the numbers the reference gives after `model.experts.eval()`.
     frozen_experts_eval = False
+    _warned_eval_grad = False
 
     def _run_experts_train_mode(self, image: torch.Tensor):
         """Frozen experts exactly as the reference runs them inside model.train(): batch-statistics BatchNorm with
@@ -291,6 +292,10 @@ class AutoMoE(nn.Module):
             return self._forward_train(batch)
         if torch.is_grad_enabled() and any(wants_grad(m) for m in self._trainable_part()) and \
                 not any(p.requires_grad for p in self.experts.parameters()):
+            if not AutoMoE._warned_eval_grad:
+                AutoMoE._warned_eval_grad = True
+                warnings.warn("automoe_b200: eval-mode forward with autograd recording takes the differentiable fp32 path "
+                              "(training kernels); wrap inference in torch.no_grad() for the tensor-core inference kernels")
             return self._forward_train(batch)      # eval semantics, differentiable (frozen experts)
         image = batch['image']
         if not image.is_cuda:

@@ -70,7 +70,8 @@ def detection_losses(outputs: Dict[str, torch.Tensor], gt_boxes: torch.Tensor, g
         indices = matcher({'pred_logits': flat[..., :C].contiguous(), 'pred_boxes': flat[..., C:].contiguous()}, targets)
         tcls, tbox = build_targets(indices, targets, B, Q, num_classes, dev)
     losses = _DetLoss.apply(head, tcls, tbox, num_classes, bbox_loss_weight)
-    return {'total_loss': losses[0], 'class_loss': losses[1], 'bbox_loss': losses[2], 'num_matched': losses[3],
+    report = losses.detach()     # only total_loss carries a gradient (the fused kernel differentiates the total)
+    return {'total_loss': losses[0], 'class_loss': report[1], 'bbox_loss': report[2], 'num_matched': report[3],
             'indices': indices}
 
 

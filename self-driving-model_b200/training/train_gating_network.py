@@ -43,7 +43,10 @@ def compute_gating_losses(pred: Dict[str, torch.Tensor], target_wp: torch.Tensor
     tspd = target_spd if target_spd.dim() == 2 else target_spd.reshape(target_spd.size(0), -1)
     losses = _GatingLoss.apply(wp, spd, pred["expert_weights"], target_wp, tspd if mode else None, mode, coef,
                                bool(config.get('use_load_balancing', True)), bool(config.get('use_entropy_loss', True)))
-    return {name: losses[i] for i, name in enumerate(LOSS_NAMES)}
+    # total_loss is the differentiable output (what train_one_epoch back-propagates); the six terms are reported values
+    # (detached: differentiating one of them alone is not supported by the fused kernel and must not silently give zeros)
+    report = losses.detach()
+    return {name: (losses[0] if i == 0 else report[i]) for i, name in enumerate(LOSS_NAMES)}
 
 
 def allreduce_flat_(flat_grad: torch.Tensor, group=None) -> float:
@@ -101,7 +104,8 @@ class FlatAdamW:
                 p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
 
     def total_norm(self) -> torch.Tensor:
-        """Gradient norm of the last step() before clipping (after the all-reduce average)."""
+        """L2 norm of the SUMMED (all-reduced, not yet averaged) gradient of the last step(); the clip inside the fused
+        kernel applies to norm / world, the averaged gradient's norm."""
         return self._norm[1]
 
     @torch.no_grad()
@@ -124,6 +128,25 @@ class FlatAdamW:
         torch.autograd.graph.increment_version(self.params)
 
 
+def broadcast_buffers_(model, group=None, src: int = 0) -> None:
+    """What DistributedDataParallel(broadcast_buffers=True) does at the start of every forward: every rank takes rank 0's
+    module buffers (BatchNorm running statistics and step counters), so replicas cannot drift apart.  One coalesced broadcast
+    per dtype.  No-op outside torch.distributed / at world size 1."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+    for b in model.buffers():
+        by_dtype.setdefault(b.dtype, []).append(b)
+    with torch.no_grad():
+        for bufs in by_dtype.values():
+            flat = torch.cat([b.reshape(-1) for b in bufs])
+            dist.broadcast(flat, src, group=group)
+            off = 0
+            for b in bufs:
+                b.copy_(flat[off:off + b.numel()].view_as(b))
+                off += b.numel()
+
+
 def freeze_for_gating_training(model) -> List[torch.nn.Parameter]:
     """model.freeze_experts() + the list of parameters the gating trainer optimises (2,870,657 for the
     3-expert configuration)."""
@@ -135,6 +158,7 @@ def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, conf
     """One iteration of train_one_epoch (train_gating_network.py:93-105): zero_grad, forward, losses,
     backward, (all-reduce,) clip 1.0, AdamW.  Returns the loss dict (device tensors; no host sync)."""
     optimizer.zero_grad()
+    broadcast_buffers_(model, getattr(optimizer, "group", None))      # DDP's per-forward buffer sync (no-op on one rank)
     pred = model(batch)
     losses = compute_gating_losses(pred, batch["waypoints"], batch["speed"], config)
     losses["total_loss"].backward()
