@@ -413,6 +413,11 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   p.tiles_h = ceil_div(Ho, p.th);
   p.tiles_b = ceil_div(B, p.nb);
   p.block_n = Cout >= 256 ? 256 : Cout;
+  {
+    // experiment switch: N tile for wide layers (AMOE_TC_BLOCKN=128 trades operand re-reads for finer wave granularity)
+    static const int forced = [] { const char* e = getenv("AMOE_TC_BLOCKN"); return e ? atoi(e) : 0; }();
+    if (forced >= 32 && forced <= 256 && Cout % forced == 0 && Cout > forced) p.block_n = forced;
+  }
   AMOE_REQUIRE(Cout % p.block_n == 0 && p.block_n % 32 == 0, "conv_tc: unsupported channel tiling Cout=%d", Cout);
   p.n_tiles_n = Cout / p.block_n;
   p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c; p.out_pad = out_pad;

@@ -9,7 +9,7 @@
 
 #include "common.cuh"
 
-constexpr int MQ_TILE = 32;  // queries per CTA
+constexpr int MQ_TILE = 128;  // queries per CTA (the per-image target staging is amortised over 128 rows)
 
 // Non-contracted arithmetic: the reference evaluates each step as a separate rounded
 // fp32 elementwise op, so no FMA contraction here.
@@ -30,7 +30,7 @@ __device__ __forceinline__ void box_corners(const float* b, int D, float& x1, fl
   y2 = fadd(cy, hh);
 }
 
-// One CTA = 32 queries of one image.  Everything a (query, target) pair needs is staged in shared memory first
+// One CTA = 128 queries of one image.  Everything a (query, target) pair needs is staged in shared memory first
 // (class probabilities of the 32 queries; per-box corners and areas, computed ONCE per box instead of once per
 // pair), then warp w sweeps rows w, w+8, ... with its lanes along the target axis: conflict-free shared-memory
 // reads, no integer division, and every store instruction writes one contiguous run of the padded cost row.
@@ -80,7 +80,7 @@ __global__ __launch_bounds__(256) void hungarian_cost_kernel(
     for (int k = 0; k < D; ++k) sqb[r * D + k] = pb[k];
     if (giou_on) {
       const BoxPre v = box_pre(pb, D);
-      sqp[r] = v.x1; sqp[32 + r] = v.y1; sqp[64 + r] = v.x2; sqp[96 + r] = v.y2; sqp[128 + r] = v.area;
+      sqp[r] = v.x1; sqp[MQ_TILE + r] = v.y1; sqp[2 * MQ_TILE + r] = v.x2; sqp[3 * MQ_TILE + r] = v.y2; sqp[4 * MQ_TILE + r] = v.area;
     }
   }
   // softmax over classes, one warp per query row
@@ -106,7 +106,7 @@ __global__ __launch_bounds__(256) void hungarian_cost_kernel(
     if (q >= Q) break;
     float* crow = cost + ((int64_t)b * Q + q) * Nmax;
     float ax1 = 0.f, ay1 = 0.f, ax2 = 0.f, ay2 = 0.f, area1 = 0.f;
-    if (giou_on) { ax1 = sqp[r]; ay1 = sqp[32 + r]; ax2 = sqp[64 + r]; ay2 = sqp[96 + r]; area1 = sqp[128 + r]; }
+    if (giou_on) { ax1 = sqp[r]; ay1 = sqp[MQ_TILE + r]; ax2 = sqp[2 * MQ_TILE + r]; ay2 = sqp[3 * MQ_TILE + r]; area1 = sqp[4 * MQ_TILE + r]; }
     for (int n = lane; n < Nmax; n += 32) {
       float out = 0.f;
       if (n < nt) {
