@@ -414,6 +414,12 @@ int amoe_conv2d_f32tc_supported(int H, int W, int Cin, int Cout, int KH, int KW,
 int amoe_conv2d_fwd_f32tc(amoe_ctx*, const void* x_split, const void* w_split, const float* scale,
                           const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
                           int KW, int stride, int pad, int Ho, int Wo, int relu, void* stream);
+/* Same forward for G stacked convolutions (activations [G*B,...] or shared [B,...], weights [G*Cout][KH][KW][6][Cin]) with an
+ * optional fp32 residual added before the ReLU: the fp32 ("parity") inference mode of the ResNet trunks and heads. */
+int amoe_conv2d_fwd_f32tc_grouped(amoe_ctx*, const void* x_split, const void* w_split, const float* scale,
+                                  const float* bias, const float* residual, float* y, int G, int x_shared,
+                                  int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                                  int pad, int Ho, int Wo, int relu, void* stream);
 int amoe_conv2d_bwd_data_f32tc(amoe_ctx*, const void* dy_split, const void* wT_split, const float* ones,
                                const float* zeros, float* dx, int B, int H, int W, int Cin, int Cout,
                                int KH, int KW, int stride, int pad, int Ho, int Wo, void* stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "amoe_pack_conv_weight_split6": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "amoe_conv2d_f32tc_supported": (_I, [_I] * 7),
     "amoe_conv2d_fwd_f32tc": (_I, [_P] * 6 + [_I] * 12 + [_P]),
+    "amoe_conv2d_fwd_f32tc_grouped": (_I, [_P] * 7 + [_I] * 14 + [_P]),
     "amoe_conv2d_bwd_data_f32tc": (_I, [_P] * 6 + [_I] * 11 + [_P]),
     "amoe_split3_padded": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_conv3x3_wgrad_f32tc_supported": (_I, [_I, _I]),

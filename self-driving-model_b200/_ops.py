@@ -419,8 +419,31 @@ def pack_conv(convs, bns, dtype: torch.dtype, device, relu: bool, cin_pad: Optio
                                      ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
         # the temporaries above must outlive the async kernels that read them
         torch.cuda.current_stream(device).synchronize()
-    return PackedConv(wbuf, scale, bias, G, cin_k, cout, kh, kw_k, sh, sw_k, ph, pw_k, relu, pair,
-                      meta={"true_k": cin * kh * kw})
+    meta = {"true_k": cin * kh * kw}
+    if dtype == torch.float32 and f32_tc() and sh == sw and ph == pw and cin_k == cin and \
+            bool(lib().amoe_conv2d_f32tc_supported(64, 64, cin, cout, kh, kw, 1)):
+        # fp32 mode on the tensor cores: six-term split of the weights (csrc/conv_tc.cu, "split operands")
+        wsplit = torch.empty((G * cout, kh, kw, 6, cin), device=device, dtype=torch.bfloat16)
+        for g, conv in enumerate(convs):
+            w = conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            check(lib().amoe_pack_conv_weight_split6(h, ptr(w), ptr(wsplit[g * cout:]), cout, cin, kh, kw, 0, st), "pack_conv_weight_split6")
+            torch.cuda.current_stream(device).synchronize()
+        meta["w_split"] = wsplit
+    return PackedConv(wbuf, scale, bias, G, cin_k, cout, kh, kw_k, sh, sw_k, ph, pw_k, relu, pair, meta=meta)
+
+
+def f32_tc() -> bool:
+    """fp32 ("parity") mode: convolutions with Cin % 64 == 0 run fp32-accurate on the bf16 tensor cores (three-way split
+    operands, csrc/conv_tc.cu); AMOE_F32_TC=0 keeps them on the CUDA-core kernel."""
+    return os.environ.get("AMOE_F32_TC", "1") != "0"
+
+
+def split3(x: torch.Tensor) -> torch.Tensor:
+    """[..., C] fp32 -> [..., 3C] bf16 = (x1 | x2 | x3): the three-way split of the fp32-accurate tensor-core kernels."""
+    Cc = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (3 * Cc,), device=x.device, dtype=torch.bfloat16)
+    check(lib().amoe_split3_bf16(ctx(x.device), ptr(x), ptr(out), x.numel() // Cc, Cc, stream_ptr(x.device)), "split3_bf16")
+    return out
 
 
 def use_flat() -> bool:
@@ -453,13 +476,24 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().amoe_conv2d_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual), ptr(y),
-                                pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.sw,
-                                pc.ph, pc.pw, Ho, Wo, int(pc.relu if relu is None else relu), dtype_code(dtype),
-                                impl, in_pad, out_pad, stream_ptr(x.device)), "conv2d_fwd")
+    wsplit = pc.meta.get("w_split")
+    f32tc = (dtype == torch.float32 and wsplit is not None and impl == 0 and in_pad == 0 and out_pad == 0 and f32_tc() and
+             bool(lib().amoe_conv2d_f32tc_supported(H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh)))
+    if f32tc:
+        xs = split3(x.contiguous())       # named: must outlive the launch
+        check(lib().amoe_conv2d_fwd_f32tc_grouped(ctx(x.device), ptr(xs), ptr(wsplit), ptr(pc.scale), ptr(pc.bias), ptr(residual),
+                                                  ptr(y), pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh,
+                                                  pc.ph, Ho, Wo, int(pc.relu if relu is None else relu), stream_ptr(x.device)),
+              "conv2d_fwd_f32tc_grouped")
+        del xs
+    else:
+        check(lib().amoe_conv2d_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(residual), ptr(y),
+                                    pc.G, int(x_shared), B, H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.sw,
+                                    pc.ph, pc.pw, Ho, Wo, int(pc.relu if relu is None else relu), dtype_code(dtype),
+                                    impl, in_pad, out_pad, stream_ptr(x.device)), "conv2d_fwd")
     if prof is not None:
         ev1.record()
-        tc = dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H + 2 * in_pad, Wk + 2 * in_pad, pc.cin, pc.cout, pc.sh, pc.sw)
+        tc = f32tc or (dtype == torch.bfloat16 and impl != 1 and lib().amoe_conv2d_tc_supported(H + 2 * in_pad, Wk + 2 * in_pad, pc.cin, pc.cout, pc.sh, pc.sw))
         macs = pc.meta.get("true_k", pc.kh * pc.kw * pc.cin) * pc.cout * pc.G * B * Ho * Wo
         prof.append(("conv_tc_kernel" if tc else "conv2d_simt_kernel", 2.0 * macs, ev0, ev1))
     return y

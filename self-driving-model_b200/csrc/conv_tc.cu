@@ -244,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
       const int nsplit = p.Cout / p.split_c;
       const bool use_res = p.residual != nullptr && valid && prob == 0;
-      if (use_res) {
+      if (use_res && !p.out_f32) {
         // pull this row of the residual towards L2 while the MMAs of the tile are still running
         // (a residual implies split_c == Cout: the row's block_n channels are contiguous)
         const __nv_bfloat16* rrow = p.residual + (int64_t)tc_.g * sub_stride + pix * p.split_c + chn;
@@ -258,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ch = chn + c0;
         const int64_t off = (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pix * p.split_c + ch % p.split_c - c0;
         uint4 rr[4];
-        if (use_res) {  // issue the residual loads before the TMEM load so the latencies overlap
+        if (use_res && !p.out_f32) {  // issue the residual loads before the TMEM load so the latencies overlap
 #pragma unroll
           for (int v = 0; v < 4; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8));
         }
@@ -280,7 +280,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[5] = fmaf(__uint_as_float(acc[v * 8 + 5]), s1.y, b1.y);
             f[6] = fmaf(__uint_as_float(acc[v * 8 + 6]), s1.z, b1.z);
             f[7] = fmaf(__uint_as_float(acc[v * 8 + 7]), s1.w, b1.w);
-            if (use_res) {
+            if (use_res && p.out_f32) {     // fp32 tensors (split-operand path): the residual is fp32 too
+              const float* rf = reinterpret_cast<const float*>(p.residual) + off + c0 + v * 8;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rf)), r1 = __ldg(reinterpret_cast<const float4*>(rf + 4));
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+            } else if (use_res) {
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[v]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -606,7 +611,8 @@ static unsigned tc_grid(const amoe_ctx* ctx, int64_t items) {
 struct SpatialTap { int dh, dw, widx; };
 static int launch_split(amoe_ctx* ctx, const void* xs, const void* ws, const float* scale, const float* bias, float* y,
                         int NB, int Hin, int Win, int C, int rows, int n_wtaps, const SpatialTap* st, int nst, int sh, int sw,
-                        int Ho, int Wo, int relu, const OutMap& om, cudaStream_t stream) {
+                        int Ho, int Wo, int relu, const OutMap& om, cudaStream_t stream, int G = 1, int x_shared = 0,
+                        const float* residual = nullptr) {
   using namespace tc;
   AMOE_REQUIRE(C % BLOCK_K == 0 && rows % 32 == 0 && (rows <= 256 || rows % 256 == 0),
                "split conv: needs C %% 64 == 0 and Cout %% 32 == 0 (C=%d Cout=%d)", C, rows);
@@ -629,10 +635,10 @@ static int launch_split(amoe_ctx* ctx, const void* xs, const void* ws, const flo
   const int C3 = 3 * C;
   AView av;
   av.dims[0] = (uint64_t)sw * C3; av.dims[1] = (uint64_t)(Win / sw); av.dims[2] = (uint64_t)sh;
-  av.dims[3] = (uint64_t)(Hin / sh); av.dims[4] = (uint64_t)NB;
+  av.dims[3] = (uint64_t)(Hin / sh); av.dims[4] = (uint64_t)(x_shared ? NB : G * NB);
   av.strides[0] = (uint64_t)sw * C3 * 2; av.strides[1] = (uint64_t)Win * C3 * 2;
   av.strides[2] = (uint64_t)sh * Win * C3 * 2; av.strides[3] = (uint64_t)Hin * Win * C3 * 2;
-  return launch_generic(ctx, xs, av, ws, n_wtaps * SPLIT_TERMS * C, scale, bias, nullptr, y, 1, 0, NB, Ho, Wo, rows, rows, n,
+  return launch_generic(ctx, xs, av, ws, n_wtaps * SPLIT_TERMS * C, scale, bias, residual, y, G, x_shared, NB, Ho, Wo, rows, rows, n,
                         taps, C / BLOCK_K, relu, 0, stream, nullptr, &om);
 }
 
@@ -739,6 +745,24 @@ int amoe_conv2d_fwd_f32tc(amoe_ctx* ctx, const void* x_split, const void* w_spli
   om.f32 = 1;
   return launch_split(ctx, x_split, w_split, scale, bias, y, B, H, W, Cin, Cout, KH * KW, st, n, stride, stride, Ho, Wo, relu, om,
                       (cudaStream_t)stream);
+}
+
+int amoe_conv2d_fwd_f32tc_grouped(amoe_ctx* ctx, const void* x_split, const void* w_split, const float* scale, const float* bias,
+                                  const float* residual, float* y, int G, int x_shared, int B, int H, int W, int Cin, int Cout, int KH,
+                                  int KW, int stride, int pad, int Ho, int Wo, int relu, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x_split && w_split && scale && bias && y && G >= 1, "amoe_conv2d_fwd_f32tc_grouped: NULL argument");
+  AMOE_REQUIRE(amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride), "amoe_conv2d_fwd_f32tc_grouped: unsupported shape");
+  AMOE_REQUIRE((Ho - 1) * stride - pad < H && (Wo - 1) * stride - pad < W && Ho > 0 && Wo > 0, "amoe_conv2d_fwd_f32tc_grouped: bad Ho/Wo");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0, "amoe_conv2d_fwd_f32tc_grouped: residual must be 16-byte aligned");
+  SpatialTap st[tc::MAX_TAPS];
+  int n = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) st[n++] = SpatialTap{kh - pad, kw - pad, kh * KW + kw};
+  OutMap om;
+  om.f32 = 1;
+  return launch_split(ctx, x_split, w_split, scale, bias, y, B, H, W, Cin, Cout, KH * KW, st, n, stride, stride, Ho, Wo, relu, om,
+                      (cudaStream_t)stream, G, x_shared, residual);
 }
 
 int amoe_conv2d_bwd_data_f32tc(amoe_ctx* ctx, const void* dy_split, const void* wT_split, const float* ones, const float* zeros,

@@ -313,8 +313,13 @@ __device__ __forceinline__ void pack32(const uint32_t (&a)[32], uint4 (&q)[4]) {
 // FOLDED: the BatchNorm scale is folded into the packed filters and the bias rides on the frame's padding
 // channel (staged as 1.0; filter slots (kh=0, j=0/1, c=3) hold the bias split into two bf16 parts), so the
 // accumulator already is scale*conv+bias and the epilogue only packs, pools and applies the ReLU.
-template <bool FOLDED>
-__global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
+// NGRP: epilogue warp groups of four warps (one per TMEM lane quarter) that split the 32-channel chunks between them.
+// NGRP = 2 is the 8-warp epilogue of round 1 (3-4 chunks per warp, 162 registers); NGRP = 4 gives every warp at most two
+// chunks so that sixteen epilogue warps fit the register file (<= 112 registers per thread at 576 threads per CTA).
+template <bool FOLDED, int NGRP>
+__global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
+  constexpr int EPI_THREADS = NGRP * 128;
+  constexpr int MAXC = NGRP == 2 ? 3 : 2;      // pooled chunks owned by one warp
   const Params& p = pp.base;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * POOL_A_STAGES + 5];
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
   const uint32_t bar_w = smem_u32(&bars[2 * POOL_A_STAGES + 4]);
 
   if (!FOLDED) {
-    for (int i = threadIdx.x; i < p.n_total; i += POOL_THREADS) {
+    for (int i = threadIdx.x; i < p.n_total; i += 64 + EPI_THREADS) {
       s_scale[i] = __ldg(p.scale + i);
       s_bias[i] = __ldg(p.bias + i);
     }
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 8);
+      mbar_init(bar_tempty + 8 * a, NGRP * 4);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -414,17 +419,25 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
     const int grp = (warp - 2) >> 2;            // chunk group
     const int ow = lq * 32 + lane;
     const bool valid = ow < p.Wo;
-    const int te = threadIdx.x - 64;            // 0..255 among the epilogue threads
+    const int te = threadIdx.x - 64;            // index among the epilogue threads
     const int n_chunks = p.n_total >> 5;
     const int pool_chunks = pp.n_pool_ch >> 5;  // <= 6
-    const int h0 = (pool_chunks + 1) >> 1;
-    const int c_begin = grp ? h0 : 0;
-    const int c_cnt = grp ? pool_chunks - h0 : h0;  // <= 3 pooled chunks owned by this warp
+    int c_begin, c_cnt, rest_grp;
+    if (NGRP == 2) {
+      const int h0 = (pool_chunks + 1) >> 1;
+      c_begin = grp ? h0 : 0;
+      c_cnt = grp ? pool_chunks - h0 : h0;      // <= 3 pooled chunks owned by this warp
+      rest_grp = 1;
+    } else {
+      c_begin = (grp * pool_chunks) / NGRP;     // 6 chunks over 4 groups: 1, 2, 1, 2
+      c_cnt = ((grp + 1) * pool_chunks) / NGRP - c_begin;
+      rest_grp = 0;                             // the group with the fewest pooled chunks also stores the full-resolution ones
+    }
     const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
     const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
-    uint4 V[3][4];  // running vertical max of the owned chunks (registers)
+    uint4 V[MAXC][4];  // running vertical max of the owned chunks (registers)
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+    for (int ci = 0; ci < MAXC; ++ci)
 #pragma unroll
       for (int v = 0; v < 4; ++v) V[ci][v] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-      if (role == ROLE_ODD) asm volatile("bar.sync 1, 256;" ::: "memory");  // previous horizontal pass has left sR
+      if (role == ROLE_ODD) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // previous horizontal pass has left sR
       uint32_t a[32];
       if (FOLDED) {
         // 16-column TMEM loads, one always in flight behind the half-chunk being packed (same 32 registers as
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
         uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&a[16]);
         if (c_cnt > 0) tmem_ld_32x32b_x16(taddr + (uint32_t)(c_begin * 32), lo);
 #pragma unroll
-        for (int hc = 0; hc < 6; ++hc) {
+        for (int hc = 0; hc < 2 * MAXC; ++hc) {
           if (hc < 2 * c_cnt) {
             const int ci = hc >> 1, c = c_begin + ci, half = hc & 1;
             tmem_ld_wait();
@@ -472,7 +485,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
         }
       } else {
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
+        for (int ci = 0; ci < MAXC; ++ci) {
           if (ci < c_cnt) {
             const int c = c_begin + ci;
             tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
           }
         }
       }
-      if (grp == 1) {
+      if (grp == rest_grp) {
         // not pooled (policy conv1): full-resolution store; a carry row belongs to another CTA's range
         const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
         for (int c = pool_chunks; c < n_chunks; ++c) {
@@ -524,13 +537,13 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
       if (role != ROLE_ODD) continue;
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // vertical max of pooled row py staged
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // vertical max of pooled row py staged
       // horizontal 3-max at even columns, then the ReLU (max with 0 on the packed bf16 pairs).
       // mapping: thread -> (pixel lane, channel vector v); a pass covers px_per_pass pooled pixels.  The index
       // math is redone per pooled row on purpose: hoisting it out of the tile loop made ptxas spill it to local
       // memory, and those reloads (L1 misses under the streaming stores) cost more than the divisions.
       {
-        const int px_per_pass = POOL_EPI_THREADS / NV;          // 32 / 16 / 10 for 1 / 2 / 3 experts
+        const int px_per_pass = EPI_THREADS / NV;               // 256 threads: 32 / 16 / 10 for 1 / 2 / 3 experts
         const int h_px0 = te / NV, h_v = te - h_px0 * NV;
         if (h_px0 < px_per_pass) {
           __nv_bfloat16* g = pp.pooled + (((int64_t)(h_v >> 3) * p.B + b) * Hq + py + pp.out_pad) * (int64_t)Wq * 64 +
@@ -550,20 +563,20 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) stem_pool_kernel(const __grid
       if (pp.out_pad) {
         // zero border of the padded pooled tensor: left/right pixel of this row, plus the rows above/below the image
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int item = te; item < 2 * NV; item += POOL_EPI_THREADS) {
+        for (int item = te; item < 2 * NV; item += EPI_THREADS) {
           const int side = item / NV, v = item - side * NV, e = v >> 3, cv = v & 7;
           __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + 1) * Wq + (side ? Wq - 1 : 0)) * 64 + cv * 8;
           *reinterpret_cast<uint4*>(d) = z;
         }
         if (py == 0 || py == pp.Hp - 1) {
           const int row = (py == 0) ? 0 : Hq - 1;
-          for (int item = te; item < Wq * NV; item += POOL_EPI_THREADS) {
+          for (int item = te; item < Wq * NV; item += EPI_THREADS) {
             const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
             __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + row) * Wq + x) * 64 + cv * 8;
             *reinterpret_cast<uint4*>(d) = z;
           }
           if (pp.Hp == 1) {  // single pooled row: both borders
-            for (int item = te; item < Wq * NV; item += POOL_EPI_THREADS) {
+            for (int item = te; item < Wq * NV; item += EPI_THREADS) {
               const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
               __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + Hq - 1) * Wq + x) * 64 + cv * 8;
               *reinterpret_cast<uint4*>(d) = z;
@@ -588,8 +601,9 @@ int amoe_stem_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return 0;
 }
 
@@ -621,10 +635,13 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
                       (size_t)128 * R_PITCH + 256;
   AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
-  if (scale == nullptr)
-    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
+  static const int warps16 = [] { const char* e = getenv("AMOE_STEM_WARPS"); return (e != nullptr && atoi(e) == 16) ? 1 : 0; }();
+  if (scale == nullptr && warps16)
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 4>, dim3(grid), dim3(64 + 4 * 128), smem, (cudaStream_t)stream, pp));
+  else if (scale == nullptr)
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 2>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   else
-    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<false>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<false, 2>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
