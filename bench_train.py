@@ -183,6 +183,8 @@ def _gating(args, dev, world, rank, dist, barrier, steps, warmup, sampler, pk, m
     if not args.no_gpu_reference:
         gref = _stock_gating(B, dev, world, rank, dist, barrier, steps, warmup, model_config)
         gref["ours_over_gpu_reference"] = value / gref["value"]
+        # the stock step keeps the frozen experts on running statistics: the like-for-like comparison is our same-semantics variant
+        gref["ours_same_semantics_over_gpu_reference"] = gref["ms_per_step"] / ms_fast32
     if rank != 0:
         return None
     ach = value / world * GFLOP_GATING_PER_FRAME / 1e3

@@ -221,6 +221,22 @@ def test_l2_chunked_stem_layer1_is_bit_identical(model_sd, monkeypatch):
         assert torch.equal(outs["0"]["expert_outputs"][0][k], outs["6"]["expert_outputs"][0][k])
 
 
+def test_fp32_mode_tensor_core_and_cuda_core_paths_agree(model_sd, monkeypatch):
+    """fp32 (parity) mode: the split-operand tensor-core convolutions (AMOE_F32_TC=1, default) against the CUDA-core fp32
+    kernels on the same batch - both are fp32-accurate, so they agree to a few 1e-6 and give the same routing."""
+    m, sd = model_sd
+    batch = _to(synth.synth_batch(6, 128, 128, seed=23), DEV)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AMOE_F32_TC", flag)
+        with torch.no_grad():
+            outs[flag] = m(batch)
+    for k in SMALL:
+        assert rel_err(outs["1"][k], outs["0"][k]) < 2e-5, (k, rel_err(outs["1"][k], outs["0"][k]))
+    assert rel_err(outs["1"]["expert_outputs"][1], outs["0"]["expert_outputs"][1]) < 2e-5
+    assert torch.equal(outs["1"]["expert_weights"].argmax(1), outs["0"]["expert_weights"].argmax(1))
+
+
 def test_dual_stage_entry_launch_is_bit_identical(model_sd, monkeypatch):
     """Stage-entry conv1 (3x3/s2) + the block's 1x1/s2 downsample as ONE dual-problem launch of the tcgen05 kernel
     (amoe_conv2d_dual_fwd) against the two separate launches: same MMAs in the same order -> the same bits, for the padded
