@@ -408,10 +408,10 @@ def pack_conv(convs, bns, dtype: torch.dtype, device, relu: bool, cin_pad: Optio
         cb = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous() if conv.bias is not None else None
         bn = bns[g] if bns is not None else None
         if bn is not None:
-            gmm = bn.weight.detach().float().contiguous()
-            bta = bn.bias.detach().float().contiguous()
-            mean = bn.running_mean.detach().float().contiguous()
-            var = bn.running_var.detach().float().contiguous()
+            gmm = bn.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            bta = bn.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            mean = bn.running_mean.detach().to(device=device, dtype=torch.float32).contiguous()
+            var = bn.running_var.detach().to(device=device, dtype=torch.float32).contiguous()
             check(lib().amoe_fold_bn(h, ptr(gmm), ptr(bta), ptr(mean), ptr(var), float(bn.eps), ptr(cb), cout,
                                      ptr(scale[g * cout:]), ptr(bias[g * cout:]), st), "fold_bn")
         else:

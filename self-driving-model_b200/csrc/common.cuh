@@ -94,6 +94,27 @@ static inline cudaError_t amoe_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// Same, as thread-block clusters of cluster_x CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t amoe_launch_pdl_cluster(void (*kern)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem,
+                                                  cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = amoe_pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- dtype-generic scalar load/store (device) ----

@@ -59,7 +59,11 @@ constexpr int STG_BYTES = 8 * 32 * 64 * 2;   // N=64: 8 epilogue warps x 32 rows
 constexpr int STG_BYTES_128 = 8 * 32 * 128 * 2;   // N=128: 8 epilogue warps x 32 rows x 256 B
 constexpr int SMEM_BUDGET_128 = 160 * 1024;       // operand stages of the N=128 kernel (224 KB with its staging rows)
 
-template <int N>
+// CTAS = 2: the CTA-pair variant.  Clusters of two CTAs take two consecutive 256-position tiles; the leader (rank 0) issues
+// M = 256 MMAs (tcgen05.mma.cta_group::2) whose B operand is split over the pair - each CTA holds only N/2 rows of every
+// weight tile - so an MMA step reads 4 KB + N*16 B instead of 4 KB + N*32 B of shared memory per CTA (N = 64: 5 instead of
+// 6 KB per 32 tensor cycles), and the resident weights of layer1 shrink from 72 to 36 KB (one more activation stage).
+template <int N, int CTAS, int ISS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ Params p) {
@@ -71,9 +75,16 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int g = blockIdx.y;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * 128u;
-  constexpr uint32_t w_tile_bytes = (uint32_t)N * 128u;
+  constexpr uint32_t w_tile_bytes = (uint32_t)(N / CTAS) * 128u;   // this CTA's rows of a weight tile
   const uint32_t smem_a = smem_base;
   const uint32_t smem_w = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  // tiles of this CTA: t = t_first + k * t_step for k < n_iter (the two CTAs of a pair run the same number of iterations;
+  // an odd tile count leaves the last iteration of rank 1 without positions: it loads zeros and stores nothing)
+  const int t_first = CTAS == 2 ? (int)(blockIdx.x & ~1u) + (int)rank : (int)blockIdx.x;
+  const int t_step = (int)gridDim.x;
+  const int n_iter = CTAS == 2 ? ((p.tiles_per_group + 1) / 2 - (int)(blockIdx.x >> 1) + (int)(gridDim.x >> 1) - 1) / (int)(gridDim.x >> 1)
+                               : (p.tiles_per_group - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // folded-BN scale/bias of this expert group, staged once per CTA
   __shared__ __align__(16) float s_scale[128];
   __shared__ __align__(16) float s_bias[128];
@@ -93,26 +104,36 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmW);
     for (int s = 0; s < MAX_A_STAGES; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
-      mbar_init(bar_aempty + 8 * s, 2);   // both MMA issuers commit
+      mbar_init(bar_aempty + 8 * s, ISS);   // every MMA issuer commits
     }
     for (int s = 0; s < MAX_W_STAGES; ++s) {
       mbar_init(bar_wfull + 8 * s, 1);
-      mbar_init(bar_wempty + 8 * s, 2);
+      mbar_init(bar_wempty + 8 * s, ISS);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_tfull + 8 * a, 2);
-      mbar_init(bar_tempty + 8 * a, 8);    // one arrive per epilogue warp
+      mbar_init(bar_tfull + 8 * a, ISS);
+      mbar_init(bar_tempty + 8 * a, 8 * CTAS);   // one arrive per epilogue warp (of both CTAs: the leader's barrier is used)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair(smem_u32(&tmem_holder), TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();              // the peer's barriers are initialised before anything remote touches them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
   const int group_row0 = g * p.group_positions;  // first flattened position of this expert group
-  const int wrow0 = g * N;                        // first weight row of this expert group
+  const int wrow0 = g * N + (int)rank * (N / CTAS);   // first weight row of this expert group (of this CTA's half)
   griddep_launch_dependents();                    // PDL: the next kernel of the chain may be scheduled (see tc_common.cuh)
+  // "full" barriers live in the leader: both CTAs' loads complete there (shared::cluster address of rank 0's copy)
+  auto full_bar = [&](uint32_t bar) { return CTAS == 2 ? mapa_rank(bar, 0u) : bar; };
+  auto load2d = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    if (CTAS == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
+    else tma_load_2d(dst, m, bar, c0, c1);
+  };
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -120,30 +141,32 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.w_resident) {
         // all chunks x taps weight tiles, once: tile j = chunk*9 + tap holds K columns tap*C + chunk*64 ...
         // (constant weights: loaded while the previous kernel may still be running)
-        mbar_arrive_expect_tx(bar_wfull, (uint32_t)(p.chunks * 9) * w_tile_bytes);
+        if (rank == 0) mbar_arrive_expect_tx(bar_wfull, (uint32_t)(p.chunks * 9 * CTAS) * w_tile_bytes);
+        const uint32_t wf = full_bar(bar_wfull);
         for (int j = 0; j < p.chunks * 9; ++j) {
           const int chunk = j / 9, tap = j - chunk * 9;
-          tma_load_2d(smem_w + (uint32_t)j * w_tile_bytes, &tmW, bar_wfull, tap * p.C + chunk * BLOCK_K, wrow0);
+          load2d(smem_w + (uint32_t)j * w_tile_bytes, &tmW, wf, tap * p.C + chunk * BLOCK_K, wrow0);
         }
       }
       griddep_wait();                             // activations below are the previous kernel's output
       int as = 0, ws = 0;
       uint32_t aphase = 0, wphase = 0;
       const int half_rows = p.rows_pad >> 1;
-      for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x) {
-        const int row_start = group_row0 + t * TILE_P - p.Wp - 1;  // may be negative: TMA zero-fills
+      for (int k = 0, t = t_first; k < n_iter; ++k, t += t_step) {
+        const int row_start = group_row0 + t * TILE_P - p.Wp - 1;  // may be negative / past the end: TMA zero-fills
         for (int chunk = 0; chunk < p.chunks; ++chunk) {
           mbar_wait(bar_aempty + 8 * as, aphase ^ 1u);
-          mbar_arrive_expect_tx(bar_afull + 8 * as, a_stage_bytes);
+          if (rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * as, (uint32_t)CTAS * a_stage_bytes);
+          const uint32_t af = full_bar(bar_afull + 8 * as);
           const uint32_t dst = smem_a + (uint32_t)as * a_stage_bytes;
-          tma_load_2d(dst, &tmA, bar_afull + 8 * as, chunk * BLOCK_K, row_start);
-          tma_load_2d(dst + (uint32_t)half_rows * 128u, &tmA, bar_afull + 8 * as, chunk * BLOCK_K, row_start + half_rows);
+          load2d(dst, &tmA, af, chunk * BLOCK_K, row_start);
+          load2d(dst + (uint32_t)half_rows * 128u, &tmA, af, chunk * BLOCK_K, row_start + half_rows);
           if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
           if (!p.w_resident) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_wempty + 8 * ws, wphase ^ 1u);
-              mbar_arrive_expect_tx(bar_wfull + 8 * ws, w_tile_bytes);
-              tma_load_2d(smem_w + (uint32_t)ws * w_tile_bytes, &tmW, bar_wfull + 8 * ws, tap * p.C + chunk * BLOCK_K, wrow0);
+              if (rank == 0) mbar_arrive_expect_tx(bar_wfull + 8 * ws, (uint32_t)CTAS * w_tile_bytes);
+              load2d(smem_w + (uint32_t)ws * w_tile_bytes, &tmW, full_bar(bar_wfull + 8 * ws), tap * p.C + chunk * BLOCK_K, wrow0);
               if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
             }
           }
@@ -151,32 +174,44 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp <= 2) {
-    // ============================ MMA issuers =============================
+    if (rank == 0 && warp <= ISS) {
+    // ============================ MMA issuers (leader CTA only) ===========
     // An N=64 MMA occupies the tensor pipe for 32 cycles, but computing its descriptors and moving
     // them to uniform registers costs one warp ~19 issue slots, so the two M-halves of a tile are
     // issued by two warps on different SM sub-partitions; each commits to the shared barriers itself.
     // (Measured on B200: what then bounds the N=64 layers is shared-memory bandwidth - every
     // 128x64x16 MMA reads 4 KB of A and 2 KB of B from smem, 432 KB per 256-position tile, ~4300
     // cycles at 128 B/clk against 2304 cycles of tensor time; row-unaligned tap shifts cost nothing.)
-    const int half = warp - 1;
-    const uint32_t idesc = make_idesc(N);
-    int as = 0, ws = 0, it = 0;
+    // ISS = 1: one warp issues both halves (MMAs of a CTA pair arrive at the peer SM as one ordered stream)
+    constexpr int NH = 3 - ISS;          // M-halves issued by this warp
+    const int half0 = ISS == 2 ? warp - 1 : 0;
+    const uint32_t idesc = CTAS == 2 ? make_idesc_pair(N) : make_idesc(N);
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
+      if (CTAS == 2) umma_bf16_pair(d, a, b, idesc, accum);
+      else umma_bf16(d, a, b, idesc, accum);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (CTAS == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
+    int as = 0, ws = 0;
     uint32_t aphase = 0, wphase = 0;
     if (p.w_resident) {
       mbar_wait(bar_wfull, 0);
       tcgen05_fence_after();
     }
     const uint32_t wp128 = (uint32_t)p.Wp * 128u;
-    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+    for (int it = 0; it < n_iter; ++it) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
+      if (CTAS == 2) mbar_wait_cluster(bar_tempty + 8 * acc, tphase ^ 1u);
+      else mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
       tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE + half * N);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE + half0 * N);
       for (int chunk = 0; chunk < p.chunks; ++chunk) {
         mbar_wait(bar_afull + 8 * as, aphase);
         tcgen05_fence_after();
-        const uint32_t a_half = smem_a + (uint32_t)as * a_stage_bytes + (uint32_t)half * (BLOCK_M * 128u);
+        const uint32_t a_half = smem_a + (uint32_t)as * a_stage_bytes + (uint32_t)half0 * (BLOCK_M * 128u);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           uint32_t w_addr;
@@ -190,18 +225,21 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t a_desc = make_sw128_desc(a_half + (uint32_t)(tap / 3) * wp128 + (uint32_t)(tap % 3) * 128u);  // row shift of this tap
           const uint64_t b_desc = make_sw128_desc(w_addr);
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                      (uint32_t)((chunk | tap | kk) != 0));
+          for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+              mma(d_tmem + (uint32_t)(h * N), a_desc + (uint64_t)(h * (BLOCK_M * 128 / 16) + kk * 2), b_desc + (uint64_t)(kk * 2),
+                  (uint32_t)((chunk | tap | kk) != 0));
           if (!p.w_resident) {
-            umma_commit(bar_wempty + 8 * ws);
+            commit(bar_wempty + 8 * ws);
             if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
           }
         }
-        umma_commit(bar_aempty + 8 * as);
-        if (chunk == p.chunks - 1) umma_commit(bar_tfull + 8 * acc);
+        commit(bar_aempty + 8 * as);
+        if (chunk == p.chunks - 1) commit(bar_tfull + 8 * acc);
         if (++as == p.a_stages) { as = 0; aphase ^= 1u; }
       }
+    }
     }
   } else {
     // ============================ epilogue ================================
@@ -224,8 +262,8 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stg_warp_s = smem_base + stg_off_w;
     const bool has_res = p.residual != nullptr;
     uint8_t* my_row = stg_warp + (size_t)lane * ROWB;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.tiles_per_group; t += gridDim.x, ++it) {
+    const uint32_t tempty_leader = CTAS == 2 ? mapa_rank(bar_tempty, 0u) : bar_tempty;
+    for (int it = 0, t = t_first; it < n_iter; ++it, t += t_step) {
       const int acc = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       const int q0 = t * TILE_P + hs * BLOCK_M + lg * 32;  // first position of this warp inside the group
@@ -250,7 +288,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // The residual was last touched a whole convolution ago (long evicted from L2), so the cp.async above pays an
         // HBM round trip that the ~1.4 us of MMAs per tile only partly cover: ask L2 for the NEXT tile's rows now.
         if (p.res_prefetch) {
-          const int tn = t + (int)gridDim.x;
+          const int tn = t + t_step;
           if (tn < p.tiles_per_group) {
             const int q0n = tn * TILE_P + hs * BLOCK_M + lg * 32;
             const int bytes = min(32, max(0, p.group_positions - q0n)) * ROWB;
@@ -276,7 +314,10 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // this warp's part of the accumulator is in registers now: hand it back before the math and the stores
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+            else mbar_arrive(bar_tempty + 8 * acc);
+          }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -334,10 +375,12 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // nothing of the peer (multicast commits, remote arrives, its TMEM half) is in flight
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -670,6 +713,14 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // epilogue is bound by instruction issue as a whole.  Making everything sub-tile-independent a per-thread constant
 // (this version, ~250 instructions) recovered two thirds of the gap.  What is left is inherent to the shift
 // (32 shuffles, the exchange and its barrier, eight warps' fixed overhead); the 171 us bound stays the target.
+static bool pair_enabled(int cout) {
+  // default: pairs for the N = 128 kernel only.  Measured on B200 (tools/flat_bench.py, 3 x 256 frames): layer2 195 -> 180 us
+  // (215 -> 198 us with residual), but layer1 (N = 64) 232 -> 303 us - a pair MMA reads its operands at ~64 B/clk per SM
+  // (88 cycles per N=64 step, 98 per N=128 step), so it only pays where an MMA step is long enough to cover 4 KB of A.
+  const char* e = getenv("AMOE_FLAT_PAIR");
+  if (e == nullptr) return cout == 128;
+  return atoi(e) != 0;
+}
 static bool kw3_enabled() {
   const char* e = getenv("AMOE_FLAT_KW3");
   return e != nullptr && atoi(e) != 0;
@@ -687,12 +738,20 @@ static bool supported(int H, int W, int C, int N) {
 int amoe_conv_flat_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET_128 + flat::STG_BYTES_128 + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET_128 + flat::STG_BYTES_128 + 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kw3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        flat::SMEM_BUDGET - flat::KW3_STATIC + flat::STG_BYTES + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET + flat::STG_BYTES + 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(flat::conv3x3_flat_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flat::SMEM_BUDGET_128 + flat::STG_BYTES_128 + 1024));
   return 0;
 }
 
@@ -735,8 +794,10 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   p.scale = scale; p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.y = (__nv_bfloat16*)y;
+  // CTA pairs (cta_group::2 MMAs, weights split over the pair): AMOE_FLAT_PAIR=0 restores one CTA per tile
+  const bool pair = !kw3 && pair_enabled(Cout) && p.tiles_per_group >= 2 && ctx->sm_count / G >= 2;
   const int a_stage = p.rows_pad * 128;
-  const int w_tile = Cout * 128;
+  const int w_tile = (pair ? Cout / 2 : Cout) * 128;     // rows of a weight tile held by one CTA
   const int w_all = p.chunks * 9 * w_tile;
   const int budget = Cout == 128 ? SMEM_BUDGET_128 : SMEM_BUDGET;     // operand stages; the staging rows come on top
   const int stg_bytes = Cout == 128 ? STG_BYTES_128 : STG_BYTES;
@@ -769,14 +830,15 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   {
     cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)G * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)Cout};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pair ? Cout / 2 : Cout)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box,
                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "amoe_conv3x3_flat_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
-  const int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
+  int ctas = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / G));
+  if (pair) ctas = std::min((ctx->sm_count / G) & ~1, 2 * ((p.tiles_per_group + 1) / 2));
   p.stg_off = (uint32_t)(p.a_stages * a_stage + w_bytes);
   const size_t smem = (size_t)p.a_stages * a_stage + w_bytes + stg_bytes + 1024;
   if (kw3) {
@@ -786,10 +848,21 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
     kp.div_img = fastdiv_init((uint32_t)(p.Hp * p.Wp));
     kp.div_wp = fastdiv_init((uint32_t)p.Wp);
     conv3x3_flat_kw3_kernel<<<dim3(ctas, G), KW3_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmW, kp);
+  } else if (pair) {
+    const char* e = getenv("AMOE_FLAT_PAIR_ISS");
+    const int iss = e ? atoi(e) : 2;
+    if (Cout == 64 && iss == 1)
+      AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv3x3_flat_kernel<64, 2, 1>, 2, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
+    else if (Cout == 64)
+      AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv3x3_flat_kernel<64, 2, 2>, 2, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
+    else if (iss == 1)
+      AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv3x3_flat_kernel<128, 2, 1>, 2, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
+    else
+      AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv3x3_flat_kernel<128, 2, 2>, 2, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
   } else if (Cout == 64)
-    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<64>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<64, 1, 2>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
   else
-    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<128>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv3x3_flat_kernel<128, 1, 2>, dim3(ctas, G), dim3(NUM_THREADS), smem, (cudaStream_t)stream, tmA, tmW, p));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -226,6 +226,8 @@ struct PoolParams {
   int n_pool_ch;          // leading channels that are max-pooled (multiple of 64)
   int Hp, Wp, out_pad;    // pooled size, border of the pooled output tensor
   __nv_bfloat16* pooled;  // [n_pool_ch/64 * B][Hp+2*out_pad][Wp+2*out_pad][64]
+  int dbg;                // AMOE_STEM_DBG experiment bits (results wrong on purpose): 1 no horizontal pass, 2 no full-resolution
+                          // stores, 4 no staging stores, 8 no border zeroing, 16 no CTA-wide barriers
 };
 
 enum { ROLE_CARRY = 0, ROLE_EVEN = 1, ROLE_ODD = 2 };
@@ -303,6 +305,113 @@ __device__ __forceinline__ void pack32(const uint32_t (&a)[32], uint4 (&q)[4]) {
                       pack_bf16x2(__uint_as_float(a[v * 8 + 6]), __uint_as_float(a[v * 8 + 7])));
 }
 
+// Horizontal 3-max at even columns of the staged vertical max (sR: [128 conv columns][R_PITCH]), ReLU, store of pooled row
+// (b, py); then the zero border of the padded pooled tensor around that row.  Executed by `nthr` threads (index te) of one role.
+template <bool RUNS>
+__device__ __forceinline__ void pool_row_out(const PoolParams& pp, const uint8_t* sR, int b, int py, int te, int nthr, int dbg) {
+  const Params& p = pp.base;
+  const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
+  const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
+  if (!(dbg & 1)) {
+    // mapping: thread -> (pixel lane, channel vector v).  RUNS: a pixel lane owns a contiguous run of pooled pixels and
+    // carries the odd column 2px+1 over to pixel px+1 - two staged vectors read per output instead of three (the staging
+    // traffic competes with the MMAs' operand reads for shared-memory bandwidth).
+    const int px_lanes = nthr / NV;                  // 128 threads: 16 / 8 / 5 for 1 / 2 / 3 experts
+    const int h_px0 = te / NV, h_v = te - h_px0 * NV;
+    if (h_px0 < px_lanes) {
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      if (RUNS) {
+        const int run = (pp.Wp + px_lanes - 1) / px_lanes;
+        const int px_lo = h_px0 * run, px_hi = min(pp.Wp, px_lo + run);
+        if (px_lo < px_hi) {
+          __nv_bfloat16* g = pp.pooled + (((int64_t)(h_v >> 3) * p.B + b) * Hq + py + pp.out_pad) * (int64_t)Wq * 64 +
+                             (px_lo + pp.out_pad) * 64 + (h_v & 7) * 8;
+          const uint8_t* r0 = sR + (2 * px_lo) * R_PITCH + h_v * 16;
+          uint4 prev = px_lo > 0 ? *reinterpret_cast<const uint4*>(r0 - R_PITCH) : zero;   // packed bf16: 0 is only used when ...
+          const bool has_prev0 = px_lo > 0;
+#pragma unroll 4
+          for (int px = px_lo; px < px_hi; ++px, r0 += 2 * R_PITCH, g += 64) {
+            const uint4 e = *reinterpret_cast<const uint4*>(r0), o = *reinterpret_cast<const uint4*>(r0 + R_PITCH);
+            uint4 m = hmax8(e, o);
+            if (px > px_lo || has_prev0) m = hmax8(m, prev);   // ... a left neighbour exists
+            prev = o;
+            if (p.relu) m = hmax8(m, zero);
+            *reinterpret_cast<uint4*>(g) = m;
+          }
+        }
+      } else {
+        __nv_bfloat16* g = pp.pooled + (((int64_t)(h_v >> 3) * p.B + b) * Hq + py + pp.out_pad) * (int64_t)Wq * 64 +
+                           (h_px0 + pp.out_pad) * 64 + (h_v & 7) * 8;
+        const uint8_t* r0 = sR + (2 * h_px0) * R_PITCH + h_v * 16;
+        const int h_rstep = 2 * px_lanes * R_PITCH, h_gstep = px_lanes * 64;
+#pragma unroll 2
+        for (int px = h_px0; px < pp.Wp; px += px_lanes, r0 += h_rstep, g += h_gstep) {
+          uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
+          if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
+          if (p.relu) m = hmax8(m, zero);
+          *reinterpret_cast<uint4*>(g) = m;
+        }
+      }
+    }
+  }
+}
+__device__ __forceinline__ void pool_row_border(const PoolParams& pp, int b, int py, int te, int nthr) {
+  const Params& p = pp.base;
+  const int NV = pp.n_pool_ch >> 3;
+  const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
+  // zero border of the padded pooled tensor: left/right pixel of this row, plus the rows above/below the image
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int item = te; item < 2 * NV; item += nthr) {
+    const int side = item / NV, v = item - side * NV, e = v >> 3, cv = v & 7;
+    __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + 1) * Wq + (side ? Wq - 1 : 0)) * 64 + cv * 8;
+    *reinterpret_cast<uint4*>(d) = z;
+  }
+  if (py == 0 || py == pp.Hp - 1) {
+    const int row = (py == 0) ? 0 : Hq - 1;
+    for (int item = te; item < Wq * NV; item += nthr) {
+      const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
+      __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + row) * Wq + x) * 64 + cv * 8;
+      *reinterpret_cast<uint4*>(d) = z;
+    }
+    if (pp.Hp == 1) {  // single pooled row: both borders
+      for (int item = te; item < Wq * NV; item += nthr) {
+        const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
+        __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + Hq - 1) * Wq + x) * 64 + cv * 8;
+        *reinterpret_cast<uint4*>(d) = z;
+      }
+    }
+  }
+}
+
+// Channels that are not pooled (policy conv1): full-resolution store of this warp's 32 output pixels of conv row (b, oh)
+template <bool FOLDED>
+__device__ __forceinline__ void store_rest_chunks(const Params& p, uint32_t taddr, int pool_chunks, int n_chunks, int b, int oh, int ow,
+                                                  bool store, const float* s_scale, const float* s_bias) {
+  const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
+  uint32_t a[32];
+  for (int c = pool_chunks; c < n_chunks; ++c) {
+    tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+    tmem_ld_wait();
+    if (store) {
+      uint4 q[4];
+      if (FOLDED) {
+        pack32(a, q);
+        if (p.relu) {
+          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) q[v] = hmax8(q[v], zero);
+        }
+      } else if (p.relu) {
+        bn_pack32<true>(a, s_scale + c * 32, s_bias + c * 32, q);
+      } else {
+        bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = q[v];
+    }
+  }
+}
+
 // Epilogue organisation: the eight epilogue warps form two groups; warps g*4+lq of both groups read
 // TMEM lane quarter lq (output pixels 32*lq..+31) and split the 32-channel chunks between them
 // (group 0: first half of the pooled chunks; group 1: second half + the full-resolution chunks).
@@ -316,9 +425,18 @@ __device__ __forceinline__ void pack32(const uint32_t (&a)[32], uint4 (&q)[4]) {
 // NGRP: epilogue warp groups of four warps (one per TMEM lane quarter) that split the 32-channel chunks between them.
 // NGRP = 2 is the 8-warp epilogue of round 1 (3-4 chunks per warp, 162 registers); NGRP = 4 gives every warp at most two
 // chunks so that sixteen epilogue warps fit the register file (<= 112 registers per thread at 576 threads per CTA).
-template <bool FOLDED, int NGRP>
-__global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
+// POOLW: warps (0 or 4) that take the horizontal pass + stores of the pooled rows off the draining warps: the drain warps
+// stage the vertical max of pooled row py (bar.arrive "full"), the pooling warps turn it into the output row and hand the
+// staging buffer back (bar.arrive "empty") while the next two conv rows are drained.  Measured on B200 (tools/stem_bench.py):
+// the in-line horizontal pass costs 108 of the kernel's 450 us.
+// (Measured and removed: the horizontal 3-max in registers - two warp shuffles per packed register, even lanes storing pooled
+// pixels straight to global memory, only the lane-quarter boundary columns through shared memory.  Bit-identical, but 654 us
+// against 337 us: ~100 more instructions per half-chunk on the two draining warps of a sub-partition, whose issue latency
+// is what the TMEM drain hides behind, and 16-byte stores at a 128-byte stride.)
+template <bool FOLDED, int NGRP, int POOLW>
+__global__ void __launch_bounds__(64 + NGRP * 128 + POOLW * 32, 1) stem_pool_kernel(const __grid_constant__ PoolParams pp) {
   constexpr int EPI_THREADS = NGRP * 128;
+  constexpr int SYNC_THREADS = EPI_THREADS + POOLW * 32;   // participants of the staging-buffer barriers
   constexpr int MAXC = NGRP == 2 ? 3 : 2;      // pooled chunks owned by one warp
   const Params& p = pp.base;
   extern __shared__ uint8_t smem_raw[];
@@ -341,7 +459,7 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
   const uint32_t bar_w = smem_u32(&bars[2 * POOL_A_STAGES + 4]);
 
   if (!FOLDED) {
-    for (int i = threadIdx.x; i < p.n_total; i += 64 + EPI_THREADS) {
+    for (int i = threadIdx.x; i < p.n_total; i += 64 + SYNC_THREADS) {
       s_scale[i] = __ldg(p.scale + i);
       s_bias[i] = __ldg(p.bias + i);
     }
@@ -353,7 +471,7 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, NGRP * 4);
+      mbar_init(bar_tempty + 8 * a, NGRP * 4 + (POOLW ? 4 : 0));
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -412,6 +530,35 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
       umma_commit(bar_tfull + 8 * acc);
       if (++stage == POOL_A_STAGES) { stage = 0; phase ^= 1u; }
     }
+  } else if (warp >= 2 + NGRP * 4) {
+    // ============================ pooling warps (POOLW > 0) ======================
+    griddep_wait();
+    // They also drain and store the channels that are not pooled (policy conv1) of every conv row - warp w may read TMEM
+    // lane quarter w % 4 - so that every draining warp owns the same number of chunks.
+    const int te = threadIdx.x - (64 + EPI_THREADS);
+    const int lq = warp & 3, ow = lq * 32 + lane;
+    asm volatile("bar.arrive 2, %0;" ::"n"(SYNC_THREADS) : "memory");          // staging buffer starts empty
+    for (int k = 0; k < seq.n_tiles; ++k) {
+      const int acc = k & 1;
+      const uint32_t tphase = (uint32_t)(k >> 1) & 1u;
+      int b, py, oh, role;
+      tile_at(seq, k, pp.Hp, b, py, oh, role);
+      if (warp < 2 + NGRP * 4 + 4) {   // the first four pooling warps (one per TMEM lane quarter)
+        mbar_wait(bar_tfull + 8 * acc, tphase);
+        tcgen05_fence_after();
+        store_rest_chunks<FOLDED>(p, tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), pp.n_pool_ch >> 5, p.n_total >> 5,
+                                  b, oh, ow, ow < p.Wo && role != ROLE_CARRY && !(pp.dbg & 2), s_scale, s_bias);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      }
+      if (role != ROLE_ODD) continue;
+      asm volatile("bar.sync 1, %0;" ::"n"(SYNC_THREADS) : "memory");          // vertical max of pooled row py staged
+      if (pp.dbg & 128) pool_row_out<false>(pp, sR, b, py, te, POOLW * 32, pp.dbg);
+      else pool_row_out<true>(pp, sR, b, py, te, POOLW * 32, pp.dbg);
+      if (k != seq.n_tiles - 1) asm volatile("bar.arrive 2, %0;" ::"n"(SYNC_THREADS) : "memory");   // staging buffer free again
+      if (pp.out_pad && !(pp.dbg & 8)) pool_row_border(pp, b, py, te, POOLW * 32);
+    }
   } else {
     // ============================ epilogue + max-pool ============================
     griddep_wait();                             // output buffers may still be read by the previous kernels of the stream
@@ -433,8 +580,6 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
       c_cnt = ((grp + 1) * pool_chunks) / NGRP - c_begin;
       rest_grp = 0;                             // the group with the fewest pooled chunks also stores the full-resolution ones
     }
-    const int NV = pp.n_pool_ch >> 3;           // 16-byte channel vectors per pooled pixel
-    const int Hq = pp.Hp + 2 * pp.out_pad, Wq = pp.Wp + 2 * pp.out_pad;
     uint4 V[MAXC][4];  // running vertical max of the owned chunks (registers)
 #pragma unroll
     for (int ci = 0; ci < MAXC; ++ci)
@@ -450,7 +595,10 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
       mbar_wait(bar_tfull + 8 * acc, tphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-      if (role == ROLE_ODD) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // previous horizontal pass has left sR
+      if (role == ROLE_ODD && !(pp.dbg & 16)) {   // previous horizontal pass has left sR
+        if (POOLW) asm volatile("bar.sync 2, %0;" ::"n"(SYNC_THREADS) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
       uint32_t a[32];
       if (FOLDED) {
         // 16-column TMEM loads, one always in flight behind the half-chunk being packed (same 32 registers as
@@ -477,7 +625,7 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
               } else if (role == ROLE_EVEN) {
                 V[ci][v] = hmax8(V[ci][v], q);
               } else {
-                *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q);
+                if (!(pp.dbg & 4)) *reinterpret_cast<uint4*>(sR + ow * R_PITCH + c * 64 + v * 16) = hmax8(V[ci][v], q);
                 V[ci][v] = q;   // conv row 2py+1 is row 2(py+1)-1 of the next pooled row
               }
             }
@@ -508,82 +656,22 @@ __global__ void __launch_bounds__(64 + NGRP * 128, 1) stem_pool_kernel(const __g
           }
         }
       }
-      if (grp == rest_grp) {
-        // not pooled (policy conv1): full-resolution store; a carry row belongs to another CTA's range
-        const int64_t pix = ((int64_t)b * p.Ho + oh) * p.Wo + ow;
-        for (int c = pool_chunks; c < n_chunks; ++c) {
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
-          tmem_ld_wait();
-          if (valid && role != ROLE_CARRY) {
-            uint4 q[4];
-            if (FOLDED) {
-              pack32(a, q);
-              if (p.relu) {
-                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) q[v] = hmax8(q[v], zero);
-              }
-            } else if (p.relu) {
-              bn_pack32<true>(a, s_scale + c * 32, s_bias + c * 32, q);
-            } else {
-              bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
-            }
-#pragma unroll
-            for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = q[v];
-          }
-        }
+      if (POOLW == 0 && grp == rest_grp) {   // not pooled      } else if (POOLW == 0 && grp == rest_grp) {   // not pooled (policy conv1); a carry row belongs to another CTA's range
+        store_rest_chunks<FOLDED>(p, taddr, pool_chunks, n_chunks, b, oh, ow, valid && role != ROLE_CARRY && !(pp.dbg & 2), s_scale, s_bias);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator drained: the MMA warp may reuse it
       if (role != ROLE_ODD) continue;
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // vertical max of pooled row py staged
-      // horizontal 3-max at even columns, then the ReLU (max with 0 on the packed bf16 pairs).
-      // mapping: thread -> (pixel lane, channel vector v); a pass covers px_per_pass pooled pixels.  The index
-      // math is redone per pooled row on purpose: hoisting it out of the tile loop made ptxas spill it to local
+      if (POOLW) {
+        asm volatile("bar.arrive 1, %0;" ::"n"(SYNC_THREADS) : "memory");   // vertical max of pooled row py staged: over to the pooling warps
+        continue;
+      }
+      if (!(pp.dbg & 16)) asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // vertical max of pooled row py staged
+      // The index math is redone per pooled row on purpose: hoisting it out of the tile loop made ptxas spill it to local
       // memory, and those reloads (L1 misses under the streaming stores) cost more than the divisions.
-      {
-        const int px_per_pass = EPI_THREADS / NV;               // 256 threads: 32 / 16 / 10 for 1 / 2 / 3 experts
-        const int h_px0 = te / NV, h_v = te - h_px0 * NV;
-        if (h_px0 < px_per_pass) {
-          __nv_bfloat16* g = pp.pooled + (((int64_t)(h_v >> 3) * p.B + b) * Hq + py + pp.out_pad) * (int64_t)Wq * 64 +
-                             (h_px0 + pp.out_pad) * 64 + (h_v & 7) * 8;
-          const uint8_t* r0 = sR + (2 * h_px0) * R_PITCH + h_v * 16;
-          const int h_rstep = 2 * px_per_pass * R_PITCH, h_gstep = px_per_pass * 64;
-          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 2
-          for (int px = h_px0; px < pp.Wp; px += px_per_pass, r0 += h_rstep, g += h_gstep) {
-            uint4 m = hmax8(*reinterpret_cast<const uint4*>(r0), *reinterpret_cast<const uint4*>(r0 + R_PITCH));
-            if (px > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r0 - R_PITCH));
-            if (p.relu) m = hmax8(m, zero);
-            *reinterpret_cast<uint4*>(g) = m;
-          }
-        }
-      }
-      if (pp.out_pad) {
-        // zero border of the padded pooled tensor: left/right pixel of this row, plus the rows above/below the image
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int item = te; item < 2 * NV; item += EPI_THREADS) {
-          const int side = item / NV, v = item - side * NV, e = v >> 3, cv = v & 7;
-          __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + py + 1) * Wq + (side ? Wq - 1 : 0)) * 64 + cv * 8;
-          *reinterpret_cast<uint4*>(d) = z;
-        }
-        if (py == 0 || py == pp.Hp - 1) {
-          const int row = (py == 0) ? 0 : Hq - 1;
-          for (int item = te; item < Wq * NV; item += EPI_THREADS) {
-            const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
-            __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + row) * Wq + x) * 64 + cv * 8;
-            *reinterpret_cast<uint4*>(d) = z;
-          }
-          if (pp.Hp == 1) {  // single pooled row: both borders
-            for (int item = te; item < Wq * NV; item += EPI_THREADS) {
-              const int x = item / NV, v = item - x * NV, e = v >> 3, cv = v & 7;
-              __nv_bfloat16* d = pp.pooled + ((((int64_t)e * p.B + b) * Hq + Hq - 1) * Wq + x) * 64 + cv * 8;
-              *reinterpret_cast<uint4*>(d) = z;
-            }
-          }
-        }
-      }
+      pool_row_out<false>(pp, sR, b, py, te, EPI_THREADS, pp.dbg);
+      if (pp.out_pad && !(pp.dbg & 8)) pool_row_border(pp, b, py, te, EPI_THREADS);
     }
   }
 
@@ -601,9 +689,9 @@ int amoe_stem_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return 0;
 }
 
@@ -629,19 +717,22 @@ extern "C" int amoe_stem_pool_fwd(amoe_ctx* ctx, const void* x_pad, const void* 
   pp.n_pool_ch = n_pool_ch;
   pp.Hp = H / 4; pp.Wp = W / 4; pp.out_pad = out_pad;
   pp.pooled = (__nv_bfloat16*)pooled;
+  { const char* e = getenv("AMOE_STEM_DBG"); pp.dbg = e ? atoi(e) : 0; }
   const int p_total = B * pp.Hp;
   if (p_total == 0) return 0;
   const size_t smem = ((size_t)pp.base.w_bytes + 127) / 128 * 128 + (size_t)POOL_A_STAGES * pp.base.a_stage_bytes +
                       (size_t)128 * R_PITCH + 256;
   AMOE_REQUIRE(smem <= 224 * 1024, "amoe_stem_pool_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p_total, ctx->sm_count);
-  static const int warps16 = [] { const char* e = getenv("AMOE_STEM_WARPS"); return (e != nullptr && atoi(e) == 16) ? 1 : 0; }();
-  if (scale == nullptr && warps16)
-    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 4>, dim3(grid), dim3(64 + 4 * 128), smem, (cudaStream_t)stream, pp));
+  // AMOE_STEM_POOLW=0: the round-1 epilogue (draining warps also run the horizontal pass)
+  const char* pw = getenv("AMOE_STEM_POOLW");
+  const int poolw = pw ? atoi(pw) : 4;
+  if (scale == nullptr && poolw == 4)
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 2, 4>, dim3(grid), dim3(POOL_THREADS + 128), smem, (cudaStream_t)stream, pp));
   else if (scale == nullptr)
-    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 2>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<true, 2, 0>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   else
-    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<false, 2>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(stem_pool_kernel<false, 2, 0>, dim3(grid), dim3(POOL_THREADS), smem, (cudaStream_t)stream, pp));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

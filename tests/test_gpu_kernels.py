@@ -314,16 +314,18 @@ FLAT_SHAPES = [
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("kw3", ["0", "1"])
+@pytest.mark.parametrize("kw3", ["0", "1", "pair"])
 @pytest.mark.parametrize("shape", FLAT_SHAPES)
 def test_conv_flat_bf16(shape, kw3, monkeypatch):
     """Halo-reuse 3x3/s1 kernel on physically padded activations (csrc/conv_flat.cu).  kw3=1: the opt-in
-    64->64 variant that multiplies two horizontal taps per MMA and shifts rows in the epilogue."""
+    64->64 variant that multiplies two horizontal taps per MMA and shifts rows in the epilogue; pair: CTA pairs
+    issuing M=256 tcgen05.mma.cta_group::2 with the weight tiles split over the two CTAs."""
     from automoe_b200 import _ops
     G, B, H, W, C, N, residual = shape
     if kw3 == "1" and (C != 64 or N != 64):
         pytest.skip("kw-fused kernel is 64 -> 64 channels only")
-    monkeypatch.setenv("AMOE_FLAT_KW3", kw3)
+    monkeypatch.setenv("AMOE_FLAT_KW3", "1" if kw3 == "1" else "0")
+    monkeypatch.setenv("AMOE_FLAT_PAIR", "1" if kw3 == "pair" else "0")
     g = torch.Generator().manual_seed(6)
     convs, bns = _mk_conv_bn(C, N, 3, 1, 1, g, n=G)
     x = torch.randn((G * B, C, H, W), generator=g).bfloat16().float().to(DEV)
