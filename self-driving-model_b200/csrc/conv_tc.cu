@@ -51,6 +51,11 @@ struct Params {
   int split_c;                      // output sub-tensor width: channel ch of group g goes to tensor
                                     // (g*Cout/split_c + ch/split_c), channel ch%split_c (== Cout normally)
   int total_tiles;
+  // Tail splitting (nprob == 1): the persistent grid walks `total_units` work units.  The first `full_units` (a multiple of
+  // the grid size) are whole tiles; each of the remaining tiles - the partial last wave, where most SMs would idle for a
+  // whole tile time (layer4: 768 tiles on 148 SMs = 5.19 waves) - is cut into `split` units of sub_n = block_n / split
+  // channels (their weight boxes come through tmW2), so the last wave costs 1/split of a tile time.
+  int total_units, full_units, split, sub_n;
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
   const float* scale;
   const float* bias;
@@ -83,6 +88,22 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
   c.bt = t % p.tiles_b;
   c.g = t / p.tiles_b;
   return c;
+}
+
+struct Unit {
+  int tile, n_off, bn;
+};
+__device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
+  Unit r;
+  if (u < p.full_units) {
+    r.tile = u; r.n_off = 0; r.bn = p.block_n;
+  } else {
+    const int k = u - p.full_units;
+    r.tile = p.full_units + k / p.split;
+    r.n_off = (k % p.split) * p.sub_n;
+    r.bn = p.sub_n;
+  }
+  return r;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -121,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
-    if (p.nprob == 2) prefetch_tmap(&tmW2);
+    if (p.nprob == 2 || p.split > 1) prefetch_tmap(&tmW2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -149,20 +170,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc_ = decode_tile(p, t);
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const Unit un = decode_unit(p, u);
+        const TileCoord tc_ = decode_tile(p, un.tile);
         const int n0 = (p.x_shared ? 0 : tc_.g * p.B) + tc_.bt * p.nb;
         const int oh0 = tc_.ht * p.th, ow0 = tc_.wt * p.tw;
-        const int wrow0 = tc_.g * p.Cout + tc_.nt * p.block_n;
+        const int wrow0 = tc_.g * p.Cout + tc_.nt * p.block_n + un.n_off;
+        const CUtensorMap* wmap = un.bn == p.block_n ? &tmW : &tmW2;      // sub-tile units: the narrow weight box
+        const uint32_t unit_b_bytes = (uint32_t)un.bn * 128u;
         int kidx = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const Tap tp = p.taps[tap];
           for (int kc = 0; kc < p.k_chunks; ++kc, ++kidx) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + unit_b_bytes);
             tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
                         tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW, bar_full + 8 * stage, tp.w_k + kc * BLOCK_K, wrow0);
+            tma_load_2d(smem_b + stage * b_stage_bytes, wmap, bar_full + 8 * stage, tp.w_k + kc * BLOCK_K, wrow0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -187,12 +211,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    const uint32_t idesc = make_idesc(p.block_n);
+    const uint32_t idesc_full = make_idesc(p.block_n), idesc_sub = make_idesc(p.sub_n);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
     for (int prob = 0; prob < p.nprob; ++prob, ++it) {
+      const uint32_t idesc = u < p.full_units ? idesc_full : idesc_sub;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);  // epilogue has drained this accumulator
@@ -226,19 +251,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = lg * 32 + lane;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
     for (int prob = 0; prob < p.nprob; ++prob, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const TileCoord tc_ = decode_tile(p, t);
+      const Unit un = decode_unit(p, u);
+      const TileCoord tc_ = decode_tile(p, un.tile);
       const float* e_scale = prob ? s_scale2 : s_scale;
       const float* e_bias = prob ? s_bias2 : s_bias;
       __nv_bfloat16* e_y = prob ? p.y2 : p.y;
       const int e_relu = prob ? p.relu2 : p.relu;
       const int nl = tc_.bt * p.nb + bi, oh = tc_.ht * p.th + hi, ow = tc_.wt * p.tw + wi;
       const bool valid = nl < p.B && oh < p.Ho && ow < p.Wo;
-      const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n;  // index into scale/bias
-      const int chn = tc_.nt * p.block_n;  // first channel of this tile inside its group
+      const int ch0 = tc_.g * p.Cout + tc_.nt * p.block_n + un.n_off;  // index into scale/bias
+      const int chn = tc_.nt * p.block_n + un.n_off;  // first channel of this unit inside its group
       const int Hop = p.o_H, Wop = p.o_W;
       const int64_t pix = ((int64_t)nl * Hop + oh * p.o_hm + p.o_ha) * Wop + ow * p.o_wm + p.o_wa;
       const int64_t sub_stride = (int64_t)p.B * Hop * Wop * p.split_c;
@@ -248,12 +274,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // pull this row of the residual towards L2 while the MMAs of the tile are still running
         // (a residual implies split_c == Cout: the row's block_n channels are contiguous)
         const __nv_bfloat16* rrow = p.residual + (int64_t)tc_.g * sub_stride + pix * p.split_c + chn;
-        for (int l = 0; l < p.block_n * 2; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + l / 2));
+        for (int l = 0; l < un.bn * 2; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + l / 2));
       }
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = 0; c0 < un.bn; c0 += 32) {
         // a 32-channel chunk never straddles output sub-tensors (split_c % 32 == 0)
         const int ch = chn + c0;
         const int64_t off = (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pix * p.split_c + ch % p.split_c - c0;
@@ -324,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int dw = dw0; dw <= dw1; ++dw) {
               if (dh == 0 && dw == 0) continue;
               const int64_t pixb = pix + (int64_t)dh * Wop + dw;
-              for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+              for (int c0 = 0; c0 < un.bn; c0 += 32) {
                 const int ch = chn + c0;
                 __nv_bfloat16* d = e_y + (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pixb * p.split_c + ch % p.split_c;
 #pragma unroll
@@ -455,6 +481,32 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
     p.y2 = (__nv_bfloat16*)second->y;
   }
   if (total == 0) return 0;
+  const int grid = std::min(p.total_tiles, ctx->sm_count);
+  p.total_units = p.total_tiles; p.full_units = p.total_tiles; p.split = 1; p.sub_n = p.block_n;
+  {
+    // tail splitting (see Params): only for long-K single-problem launches whose last wave is partial
+    const char* e_ts = getenv("AMOE_TC_TAIL_SPLIT");
+    const int tail_on = (e_ts == nullptr || atoi(e_ts) != 0) ? 1 : 0;
+    const int rem = p.total_tiles % grid;
+    if (tail_on && second == nullptr && p.total_tiles > grid && rem != 0 && num_taps * k_chunks >= 16) {
+      int best = 1;
+      double best_cost = 1.0;                       // time of the tail in tile times
+      for (int sp = 2; sp <= 4; sp *= 2) {
+        if (p.block_n % (32 * sp) != 0) continue;
+        // narrow units pay for their share of the tile more than once: every unit re-reads the activation boxes, and an
+        // N = 64 MMA step is shared-memory-bound (measured, tools/tc_bench.py: the 512->256 head, 88 tiles in the tail,
+        // got slower with four N = 64 units per tile: 86 -> 101 us; layer4, 28 tiles in the tail: 168 -> 163 us)
+        const double penalty = p.block_n / sp >= 128 ? 1.25 : 1.9;
+        const double cost = (double)ceil_div(rem * sp, grid) / sp * penalty;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+      }
+      if (best > 1) {
+        p.split = best; p.sub_n = p.block_n / best;
+        p.full_units = p.total_tiles - rem;
+        p.total_units = p.full_units + rem * best;
+      }
+    }
+  }
 
   CUtensorMap tmA, tmW;
   {
@@ -479,6 +531,16 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
   CUtensorMap tmW2 = tmW;
+  if (p.split > 1) {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)G * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.sub_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(sub-tile weights) failed with %d", (int)r);
+  }
   if (second != nullptr) {
     const int K2 = k_chunks * BLOCK_K;          // 1x1 filter: K = Cin
     cuuint64_t dims[2] = {(cuuint64_t)K2, (cuuint64_t)G * Cout};
@@ -490,7 +552,6 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(second weights) failed with %d", (int)r);
   }
-  const int grid = std::min(p.total_tiles, ctx->sm_count);
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
   AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
   AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
