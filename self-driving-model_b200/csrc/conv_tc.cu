@@ -29,6 +29,7 @@ constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_RESIDENT = 212 * 1024;   // operand bytes of the resident-weight mode (scale/bias staging comes on top)
 
 struct Tap {
   int c_off, dw, hp, dh;  // TMA start-coordinate offsets of this filter tap
@@ -56,6 +57,17 @@ struct Params {
   // whole tile time (layer4: 768 tiles on 148 SMs = 5.19 waves) - is cut into `split` units of sub_n = block_n / split
   // channels (their weight boxes come through tmW2), so the last wave costs 1/split of a tile time.
   int total_units, full_units, split, sub_n;
+  // Resident weights (short-K stage entries: Cin = 64, one N tile): every tap's weight box of the CTA's expert group - and
+  // the second problem's - is loaded ONCE into shared memory, the ring then carries activation boxes only (the launch was
+  // bound by L2->SMEM traffic: 16 KB of weights per 16 KB activation box).  The grid is (CTAs per group, G): a CTA stays
+  // inside one expert group, tiles_per_group tiles each.
+  int w_resident, tiles_per_group;
+  // (Measured and removed: cp.async.bulk.prefetch.tensor of the next unit's activation boxes into L2 when a unit starts -
+  // every launch got slower, layer2 entry 150 -> 193 us, layer4 147 -> 178 us: the prefetches queue in front of the loads.)
+  // Neither did plain prefetch.global.L2 of the unit after the next one's input region by the idle lanes of the producer warp
+  // (layer2 entry 159 -> 259 us).  The stage entries are HBM-bound, not latency-bound: the layer2 entry reads 403 MB and
+  // writes 168 MB (two outputs in the dual launch: 374 MB) of DRAM, 4.8 TB/s when its epilogue only drains.
+  int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
   const float* scale;
   const float* bias;
@@ -77,7 +89,10 @@ struct Params {
 struct TileCoord {
   int g, bt, ht, wt, nt;
 };
-__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+// CTAS = 2 (CTA pairs): `t` numbers PAIRS of M tiles - p.tiles_b counts pairs of image tiles, the CTA of cluster rank r
+// takes image tile 2*bt + r (an odd image-tile count leaves the last tile of rank 1 out of bounds: zeros in, nothing out)
+template <int CTAS>
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int rank) {
   TileCoord c;
   c.nt = t % p.n_tiles_n;
   t /= p.n_tiles_n;
@@ -85,7 +100,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
   t /= p.tiles_w;
   c.ht = t % p.tiles_h;
   t /= p.tiles_h;
-  c.bt = t % p.tiles_b;
+  c.bt = (t % p.tiles_b) * CTAS + rank;
   c.g = t / p.tiles_b;
   return c;
 }
@@ -106,21 +121,33 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
   return r;
 }
 
+// CTAS = 2: clusters of two CTAs work on two M tiles (adjacent image tiles) of the same N tile; the leader issues M = 256
+// tcgen05.mma.cta_group::2 whose B operand is split over the pair - each CTA loads and holds only HALF of every weight box
+// (16 instead of 32 KB per K chunk at N = 256: a third less L2->SMEM traffic per CTA, half the B reads per MMA step).
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B needs 1024 B alignment
-  const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t b_stage_bytes = (uint32_t)(p.block_n / CTAS) * 128u;   // this CTA's rows of a weight box
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int u_first = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // work units of this CTA (pair)
+  const int u_step = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // work units of this CTA: u = u_lo + u_first, + u_step, ... < u_hi
+  const int u_lo = p.w_resident ? (int)blockIdx.y * p.tiles_per_group : 0;
+  const int u_hi = p.w_resident ? u_lo + p.tiles_per_group : p.total_units;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + (uint32_t)p.stages * A_STAGE_BYTES;
+  const uint32_t smem_b = smem_base + (uint32_t)p.stages * A_STAGE_BYTES;   // weight stages, or the resident weight boxes
+  const uint32_t w_boxes = (uint32_t)(p.num_taps * p.k_chunks + (p.nprob == 2 ? p.k_chunks : 0));   // resident boxes
   // folded-BN scale/bias of every group, staged once per CTA (the epilogue reads them with LDS.128)
   float* s_scale = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
-                                            (size_t)p.stages * (A_STAGE_BYTES + b_stage_bytes));
+                                            (p.w_resident ? (size_t)p.stages * A_STAGE_BYTES + (size_t)w_boxes * b_stage_bytes
+                                                          : (size_t)p.stages * (A_STAGE_BYTES + b_stage_bytes)));
   float* s_bias = s_scale + p.n_ch_total;
   for (int i = threadIdx.x; i < p.n_ch_total; i += NUM_THREADS) {
     s_scale[i] = __ldg(p.scale + i);
@@ -138,6 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_STAGES]);
   const uint32_t bar_tempty = smem_u32(&bars[2 * MAX_STAGES + 2]);
+  const uint32_t bar_w = smem_u32(&bars[2 * MAX_STAGES + 4]);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -149,44 +177,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * a, 4 * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
+    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair(smem_u32(&tmem_holder), TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
   // PDL: everything above touched only kernel parameters and constant weights (folded BN); the next kernel of the chain
   // may be scheduled now, and nothing below runs before the previous kernel's results are complete
   griddep_launch_dependents();
+  if (p.w_resident && warp == 0 && lane == 0) {
+    // constant weights: loaded while the previous kernel of the stream may still be running
+    const int wrow = (int)blockIdx.y * p.Cout + (int)rank * (p.block_n / CTAS);
+    const uint32_t wf = CTAS == 2 ? mapa_rank(bar_w, 0u) : bar_w;
+    if (rank == 0) mbar_arrive_expect_tx(bar_w, (uint32_t)CTAS * w_boxes * b_stage_bytes);
+    for (int j = 0; j < p.num_taps * p.k_chunks; ++j) {
+      const int tap = j / p.k_chunks, kc = j - tap * p.k_chunks;
+      if (CTAS == 2) tma_load_2d_pair(smem_b + (uint32_t)j * b_stage_bytes, &tmW, wf, p.taps[tap].w_k + kc * BLOCK_K, wrow);
+      else tma_load_2d(smem_b + (uint32_t)j * b_stage_bytes, &tmW, wf, p.taps[tap].w_k + kc * BLOCK_K, wrow);
+    }
+    if (p.nprob == 2)
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const uint32_t dst = smem_b + (uint32_t)(p.num_taps * p.k_chunks + kc) * b_stage_bytes;
+        if (CTAS == 2) tma_load_2d_pair(dst, &tmW2, wf, kc * BLOCK_K, wrow);
+        else tma_load_2d(dst, &tmW2, wf, kc * BLOCK_K, wrow);
+      }
+  }
   griddep_wait();
 
   const int k_iters1 = p.num_taps * p.k_chunks;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+    int stage = 0;
+    uint32_t phase = 0;
+    auto full_bar = [&](uint32_t bar) { return CTAS == 2 ? mapa_rank(bar, 0u) : bar; };
+    auto load_a = [&](uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+      if (CTAS == 2) tma_load_5d_pair(dst, &tmA, bar, c0, c1, c2, c3, c4);
+      else tma_load_5d(dst, &tmA, bar, c0, c1, c2, c3, c4);
+    };
+    auto load_w = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+      if (CTAS == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
+      else tma_load_2d(dst, m, bar, c0, c1);
+    };
+    for (int u = u_lo + u_first; u < u_hi; u += u_step) {
+      if (lane == 0) {
         const Unit un = decode_unit(p, u);
-        const TileCoord tc_ = decode_tile(p, un.tile);
-        const int n0 = (p.x_shared ? 0 : tc_.g * p.B) + tc_.bt * p.nb;
+        const TileCoord tc_ = decode_tile<CTAS>(p, un.tile, (int)rank);
+        // an image tile past the batch (rank 1 of the last pair) starts at an image index TMA treats as out of bounds: zeros
+        const int n0 = (p.x_shared ? 0 : tc_.g * p.B) + tc_.bt * p.nb + ((CTAS == 2 && tc_.bt * p.nb >= p.B) ? (1 << 28) : 0);
         const int oh0 = tc_.ht * p.th, ow0 = tc_.wt * p.tw;
-        const int wrow0 = tc_.g * p.Cout + tc_.nt * p.block_n + un.n_off;
+        const int wrow0 = tc_.g * p.Cout + tc_.nt * p.block_n + un.n_off + (int)rank * (un.bn / CTAS);
         const CUtensorMap* wmap = un.bn == p.block_n ? &tmW : &tmW2;      // sub-tile units: the narrow weight box
-        const uint32_t unit_b_bytes = (uint32_t)un.bn * 128u;
-        int kidx = 0;
+        const uint32_t unit_b_bytes = (uint32_t)(un.bn / CTAS) * 128u;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const Tap tp = p.taps[tap];
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++kidx) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + unit_b_bytes);
-            tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
-                        tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
-            tma_load_2d(smem_b + stage * b_stage_bytes, wmap, bar_full + 8 * stage, tp.w_k + kc * BLOCK_K, wrow0);
+            if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)CTAS * (A_STAGE_BYTES + (p.w_resident ? 0u : unit_b_bytes)));
+            const uint32_t fb = full_bar(bar_full + 8 * stage);
+            load_a(smem_a + stage * A_STAGE_BYTES, fb, tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
+            if (!p.w_resident) load_w(smem_b + stage * b_stage_bytes, wmap, fb, tp.w_k + kc * BLOCK_K, wrow0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -197,10 +256,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const Tap tp = p.tap2;
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + b_stage_bytes);
-            tma_load_5d(smem_a + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage,
-                        tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
-            tma_load_2d(smem_b + stage * b_stage_bytes, &tmW2, bar_full + 8 * stage, kc * BLOCK_K, wrow0);
+            if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)CTAS * (A_STAGE_BYTES + (p.w_resident ? 0u : b_stage_bytes)));
+            const uint32_t fb = full_bar(bar_full + 8 * stage);
+            load_a(smem_a + stage * A_STAGE_BYTES, fb, tp.c_off + kc * BLOCK_K, ow0 + tp.dw, tp.hp, oh0 + tp.dh, n0);
+            if (!p.w_resident) load_w(smem_b + stage * b_stage_bytes, &tmW2, fb, kc * BLOCK_K, wrow0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -210,17 +269,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
-    const uint32_t idesc_full = make_idesc(p.block_n), idesc_sub = make_idesc(p.sub_n);
+    // ============================ MMA issuer (pairs: the leader CTA only) =
+    if (rank == 0) {
+    const uint32_t idesc_full = CTAS == 2 ? make_idesc_pair(p.block_n) : make_idesc(p.block_n);
+    const uint32_t idesc_sub = CTAS == 2 ? make_idesc_pair(p.sub_n) : make_idesc(p.sub_n);
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+      if (CTAS == 2) umma_bf16_pair(d, a, b, id, accum);
+      else umma_bf16(d, a, b, id, accum);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (CTAS == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
+    if (p.w_resident) {
+      mbar_wait(bar_w, 0);
+      tcgen05_fence_after();
+    }
+    for (int u = u_lo + u_first; u < u_hi; u += u_step)
     for (int prob = 0; prob < p.nprob; ++prob, ++it) {
       const uint32_t idesc = u < p.full_units ? idesc_full : idesc_sub;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);  // epilogue has drained this accumulator
+      if (CTAS == 2) mbar_wait_cluster(bar_tempty + 8 * as, aphase ^ 1u);
+      else mbar_wait(bar_tempty + 8 * as, aphase ^ 1u);  // epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_STRIDE);
       const int k_iters = prob ? p.k_chunks : k_iters1;
@@ -229,15 +303,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         {
           const uint64_t a_desc = make_sw128_desc(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t b_desc = make_sw128_desc(smem_b + stage * b_stage_bytes);
+          const uint64_t b_desc = make_sw128_desc(smem_b + (p.w_resident ? (uint32_t)(prob ? k_iters1 + k : k) : (uint32_t)stage) * b_stage_bytes);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
             // advance 32 bytes (16 bf16) inside the 128B swizzle row: +2 in the >>4 address field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                      (uint32_t)((k | kk) != 0));
+            mma(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (uint32_t)((k | kk) != 0));
           }
-          umma_commit(bar_empty + 8 * stage);                     // frees the smem slot
-          if (k == k_iters - 1) umma_commit(bar_tfull + 8 * as);  // accumulator ready
+          commit(bar_empty + 8 * stage);                     // frees the smem slot
+          if (k == k_iters - 1) commit(bar_tfull + 8 * as);  // accumulator ready
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -245,18 +318,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   } else {
     // ============================ epilogue ================================
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
     const int row = lg * 32 + lane;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     int it = 0;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x)
+    const uint32_t tempty_leader = CTAS == 2 ? mapa_rank(bar_tempty, 0u) : bar_tempty;
+    for (int u = u_lo + u_first; u < u_hi; u += u_step)
     for (int prob = 0; prob < p.nprob; ++prob, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const Unit un = decode_unit(p, u);
-      const TileCoord tc_ = decode_tile(p, un.tile);
+      const TileCoord tc_ = decode_tile<CTAS>(p, un.tile, (int)rank);
       const float* e_scale = prob ? s_scale2 : s_scale;
       const float* e_bias = prob ? s_bias2 : s_bias;
       __nv_bfloat16* e_y = prob ? p.y2 : p.y;
@@ -291,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, acc);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.dbg & 1)) {
           const float4* sc4 = reinterpret_cast<const float4*>(e_scale + ch0 + c0);
           const float4* bs4 = reinterpret_cast<const float4*>(e_bias + ch0 + c0);
 #pragma unroll
@@ -338,7 +413,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tempty_leader + 8 * as);
+        else mbar_arrive(bar_tempty + 8 * as);
+      }
       if (p.out_pad == 1 && prob == 0 && valid) {
         // Physical zero border of the padded output (the consumer's 3x3 taps read it as their padding): written by the
         // threads that own the neighbouring interior pixels, for this tile's channels - no memset of the whole tensor.
@@ -363,10 +441,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -392,7 +472,9 @@ static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
 int amoe_conv_tc_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tc::SMEM_BUDGET + 1024 + 24 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        tc::SMEM_BUDGET + 1024 + 24 * 1024));
   return 0;
 }
@@ -451,11 +533,39 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   }
   AMOE_REQUIRE(Cout % p.block_n == 0 && p.block_n % 32 == 0, "conv_tc: unsupported channel tiling Cout=%d", Cout);
   p.n_tiles_n = Cout / p.block_n;
+  // CTA pairs (see the kernel): AMOE_TC_PAIR = 0 off, 1 wherever possible, unset: the N = 256 tiles of single-problem launches
+  bool pair;
+  {
+    const char* e = getenv("AMOE_TC_PAIR");
+    const int mode = e ? atoi(e) : -1;
+    pair = mode == 1 ? (p.block_n >= 64) : (mode == -1 ? (p.block_n == 256 && second == nullptr) : false);
+    if (p.tiles_b < 2 || ctx->sm_count < 2) pair = false;
+  }
+  // resident weights (see Params): short-K launches with one N tile whose weight boxes fit beside >= 4 activation stages;
+  // CTA pairs halve what each CTA holds.  AMOE_TC_WRES=0 switches it off.
+  p.w_resident = 0;
+  {
+    const char* e = getenv("AMOE_TC_WRES");
+    const char* ep = getenv("AMOE_TC_PAIR");
+    const bool pair_allowed = ep == nullptr || atoi(ep) != 0;
+    const int boxes = num_taps * k_chunks + (second != nullptr ? k_chunks : 0);
+    const bool wanted = e != nullptr ? atoi(e) != 0 : num_taps * k_chunks <= 12;   // long K: the weight stream is amortised
+    if (wanted && p.n_tiles_n == 1 && p.block_n >= 64 && omap == nullptr && p.tiles_b >= 2 && ctx->sm_count / G >= 2) {
+      // (CTA pairs would halve the resident bytes, but an N = 128 pair MMA step takes ~98 instead of 64 cycles: measured
+      // slower - layer2 entry 156 -> 184 us, policy conv3 53 -> 61 us - so the boxes must fit one CTA, beside >= 3 stages)
+      (void)pair_allowed;
+      if (boxes * (p.block_n / (pair ? 2 : 1)) * 128 + 3 * A_STAGE_BYTES <= SMEM_RESIDENT) p.w_resident = 1;
+    }
+  }
+  const int ctas = pair ? 2 : 1;
+  if (pair) p.tiles_b = ceil_div(p.tiles_b, 2);     // pairs of image tiles
   p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c; p.out_pad = out_pad;
+  { const char* e = getenv("AMOE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.num_taps = num_taps;
   p.k_chunks = k_chunks;
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
-  p.stages = std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes);
+  const int stage_bytes = p.w_resident ? A_STAGE_BYTES : A_STAGE_BYTES + (p.block_n / ctas) * 128;
+  const int w_res_bytes = p.w_resident ? (num_taps * k_chunks + (second != nullptr ? k_chunks : 0)) * (p.block_n / ctas) * 128 : 0;
+  p.stages = std::min(MAX_STAGES, ((p.w_resident ? SMEM_RESIDENT : SMEM_BUDGET) - w_res_bytes) / stage_bytes);
   p.relu = relu; p.x_shared = x_shared;
   int64_t total = (int64_t)G * p.tiles_b * p.tiles_h * p.tiles_w * p.n_tiles_n;
   AMOE_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
@@ -481,14 +591,16 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
     p.y2 = (__nv_bfloat16*)second->y;
   }
   if (total == 0) return 0;
-  const int grid = std::min(p.total_tiles, ctx->sm_count);
+  int grid = std::min(p.total_tiles, ctx->sm_count / ctas);    // CTAs, or CTA pairs
+  p.tiles_per_group = p.total_tiles / G;
+  if (p.w_resident) grid = std::max(1, std::min(p.tiles_per_group, ctx->sm_count / ctas / G));   // per expert group (grid.y = G)
   p.total_units = p.total_tiles; p.full_units = p.total_tiles; p.split = 1; p.sub_n = p.block_n;
   {
     // tail splitting (see Params): only for long-K single-problem launches whose last wave is partial
     const char* e_ts = getenv("AMOE_TC_TAIL_SPLIT");
     const int tail_on = (e_ts == nullptr || atoi(e_ts) != 0) ? 1 : 0;
     const int rem = p.total_tiles % grid;
-    if (tail_on && second == nullptr && p.total_tiles > grid && rem != 0 && num_taps * k_chunks >= 16) {
+    if (tail_on && !p.w_resident && second == nullptr && p.total_tiles > grid && rem != 0 && num_taps * k_chunks >= 16) {
       int best = 1;
       double best_cost = 1.0;                       // time of the tail in tile times
       for (int sp = 2; sp <= 4; sp *= 2) {
@@ -523,7 +635,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)G * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.block_n / ctas)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -534,7 +646,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   if (p.split > 1) {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)G * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.sub_n};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.sub_n / ctas)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -545,16 +657,20 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
     const int K2 = k_chunks * BLOCK_K;          // 1x1 filter: K = Cin
     cuuint64_t dims[2] = {(cuuint64_t)K2, (cuuint64_t)G * Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K2 * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.block_n / ctas)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(second->w), dims, strides,
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(second weights) failed with %d", (int)r);
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
-  AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage");
-  AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
+  const size_t smem = (size_t)p.stages * stage_bytes + w_res_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
+  AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage (%zu bytes)", smem);
+  const int gy = p.w_resident ? G : 1;
+  if (pair)
+    AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2>, 2, dim3(2 * grid, gy), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
+  else
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1>, dim3(grid, gy), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

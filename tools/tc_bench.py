@@ -21,6 +21,7 @@ CASES = [  # name, G, B, H, W, Cin, Cout, k, stride, residual
     ("layer4 3x3+res", 3, 256, 8, 8, 512, 512, 3, 1, True),
     ("head 3x3", 3, 256, 8, 8, 512, 256, 3, 1, False),
     ("layer4 entry s2", 3, 256, 16, 16, 256, 512, 3, 2, False),
+    ("layer2 entry s2", 3, 256, 64, 64, 64, 128, 3, 2, False),
     ("policy conv3 s2", 1, 256, 64, 64, 64, 128, 3, 2, False),
     ("policy conv4 s2", 1, 256, 32, 32, 128, 256, 3, 2, False),
 ]
@@ -28,7 +29,10 @@ CASES = [  # name, G, B, H, W, Cin, Cout, k, stride, residual
 
 def main(settings):
     torch.manual_seed(0)
+    only = os.environ.get("TC_BENCH_ONLY")
     for name, G, B, H, W, C, N, k, s, res in CASES:
+        if only and only not in name:
+            continue
         convs = [nn.Conv2d(C, N, k, s, k // 2, bias=False).to(DEV) for _ in range(G)]
         bns = [nn.BatchNorm2d(N).to(DEV).eval() for _ in range(G)]
         pc = _ops.pack_conv(convs, bns, torch.bfloat16, DEV, relu=True)
