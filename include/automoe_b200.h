@@ -46,6 +46,11 @@ int amoe_sm_count(amoe_ctx* ctx);
 /* number of kernels launched through this context since creation (bench.py's
  * "gpu_launches" counter) */
 int64_t amoe_launch_count(amoe_ctx* ctx);
+/* Tile walk direction of the tensor-core convolutions launched through this context from now on (0: front to back,
+ * 1: back to front).  Results do not depend on it.  A chain of convolutions that alternates the direction starts every
+ * layer on the part of its input (and residual) the previous layer touched last - the part still in L2; the reference has
+ * no counterpart (cuDNN schedules its own grids). */
+int amoe_set_walk_reverse(amoe_ctx* ctx, int reverse);
 
 /* ---- layout / weight packing ------------------------------------------- */
 /* batch['image'] [B,C,H,W] fp32 NCHW (models/automoe.py:212-218 consumers) ->

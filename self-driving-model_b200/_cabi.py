@@ -32,6 +32,7 @@ SIGNATURES = {
     "amoe_destroy": (_I, [_P]),
     "amoe_sm_count": (_I, [_P]),
     "amoe_launch_count": (_L, [_P]),
+    "amoe_set_walk_reverse": (_I, [_P, _I]),
     "amoe_image_nchw_to_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_image_nchw_to_nhwc_padded": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_image_nchw_to_nhwc_padded_v": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -204,6 +204,7 @@ def stem_pool_forward(ps: PackedStem, x_pad: torch.Tensor, B: int, H: int, W: in
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     fold = ps.w_folded is not None and stem_fold()
+    walk_reset(dev, 1)          # the stem writes front to back: the convolution behind it starts at the back
     check(lib().amoe_stem_pool_fwd(ctx(dev), ptr(x_pad), ptr(ps.w_folded if fold else ps.w), None if fold else ptr(ps.scale),
                                    None if fold else ptr(ps.bias), B, H, W, x_pad.shape[2],
                                    STEM_KH, ps.n_total, int(ps.relu), n_pool * 64, ptr(pooled), out_pad, dst, dst_c,
@@ -260,6 +261,30 @@ def l2_chunk_images() -> int:
     AMOE_L2_CHUNK=<n> turns it on (kept for larger-L2 / lower-HBM parts and as a tested path)."""
     import os
     return int(os.environ.get("AMOE_L2_CHUNK", "0"))
+
+
+_WALK = {}   # device index -> direction (0 / 1) of the next tensor-core convolution
+
+
+def walk_alternate() -> bool:
+    """Consecutive tensor-core convolutions walk their tiles in alternating directions (AMOE_WALK_ALT=0: always front to
+    back), so each layer starts on the part of its input / residual the previous layer touched last - what is still in L2.
+    Results do not depend on the direction (tests run both)."""
+    import os
+    return os.environ.get("AMOE_WALK_ALT", "1") != "0"
+
+
+def walk_reset(device, first: int = 0) -> None:
+    """Start of a chain (the stem writes front to back): the next convolution walks in direction `first`."""
+    _WALK[torch.device(device).index or 0] = first
+
+
+def _walk_step(device) -> None:
+    """Set the direction of the convolution about to be launched on `device`, then flip it for the next one."""
+    idx = torch.device(device).index or 0
+    d = _WALK.get(idx, 0) if walk_alternate() else 0
+    check(lib().amoe_set_walk_reverse(ctx(device), d), "set_walk_reverse")
+    _WALK[idx] = d ^ 1
 
 
 def overlap_outputs() -> bool:
@@ -476,6 +501,7 @@ def conv2d(pc: PackedConv, x: torch.Tensor, B: int, H: int, W: int, residual: Op
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    _walk_step(x.device)
     wsplit = pc.meta.get("w_split")
     f32tc = (dtype == torch.float32 and wsplit is not None and impl == 0 and in_pad == 0 and out_pad == 0 and f32_tc() and
              bool(lib().amoe_conv2d_f32tc_supported(H, Wk, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh)))
@@ -520,6 +546,7 @@ def conv2d_dual(pc: PackedConv, pd: PackedConv, x: torch.Tensor, B: int, H: int,
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    _walk_step(x.device)
     check(lib().amoe_conv2d_dual_fwd(ctx(x.device), ptr(x), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), ptr(y), ptr(pd.w), ptr(pd.scale),
                                      ptr(pd.bias), ptr(y2), pc.G, B, H, W, pc.cin, pc.cout, pc.kh, pc.kw, pc.sh, pc.ph, Ho, Wo,
                                      int(pc.relu), int(pd.relu), in_pad, out_pad, stream_ptr(x.device)), "conv2d_dual_fwd")
@@ -552,6 +579,7 @@ def conv3x3_flat(pc: PackedConv, x_pad: torch.Tensor, B: int, H: int, W: int,
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    _walk_step(x_pad.device)
     check(lib().amoe_conv3x3_flat_fwd_strided(ctx(x_pad.device), ptr(x_pad), ptr(pc.w), ptr(pc.scale), ptr(pc.bias),
                                               ptr(residual), ptr(y), pc.G, B, H, W, pc.cin, pc.cout, int(pc.relu),
                                               int(out_group_images), 0, stream_ptr(x_pad.device)),

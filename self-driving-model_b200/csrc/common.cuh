@@ -17,6 +17,7 @@ struct amoe_ctx {
   int device;
   int sm_count;
   std::atomic<int64_t> launches;
+  int walk_reverse;   // tcgen05 convolutions walk their tiles back to front (amoe_set_walk_reverse)
   // cuTensorMapEncodeTiled resolved through the runtime (no -lcuda needed)
   CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                            const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

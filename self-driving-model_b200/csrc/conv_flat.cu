@@ -47,6 +47,7 @@ struct Params {
   int tiles_per_group;   // ceil(B*Hp*Wp / TILE_P)
   int group_positions;   // B*Hp*Wp
   int relu;
+  int reverse;           // walk the tiles back to front (amoe_set_walk_reverse)
   int res_prefetch;      // epilogue prefetches the next tile's residual rows into L2 (AMOE_FLAT_RES_PREFETCH=0 disables)
   int64_t y_group_elems, res_group_elems;  // element distance between the expert groups of y / residual
   const float* scale;
@@ -81,8 +82,11 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
   // tiles of this CTA: t = t_first + k * t_step for k < n_iter (the two CTAs of a pair run the same number of iterations;
   // an odd tile count leaves the last iteration of rank 1 without positions: it loads zeros and stores nothing)
-  const int t_first = CTAS == 2 ? (int)(blockIdx.x & ~1u) + (int)rank : (int)blockIdx.x;
-  const int t_step = (int)gridDim.x;
+  // (reverse walk: the same set of iterations, mirrored - pair p of the forward walk takes the tiles of pair n_pairs-1-p)
+  const int tiles_even = CTAS == 2 ? 2 * ((p.tiles_per_group + 1) / 2) : p.tiles_per_group;
+  const int t_first = p.reverse ? (CTAS == 2 ? tiles_even - 2 - (int)(blockIdx.x & ~1u) + (int)rank : tiles_even - 1 - (int)blockIdx.x)
+                                : (CTAS == 2 ? (int)(blockIdx.x & ~1u) + (int)rank : (int)blockIdx.x);
+  const int t_step = p.reverse ? -(int)gridDim.x : (int)gridDim.x;
   const int n_iter = CTAS == 2 ? ((p.tiles_per_group + 1) / 2 - (int)(blockIdx.x >> 1) + (int)(gridDim.x >> 1) - 1) / (int)(gridDim.x >> 1)
                                : (p.tiles_per_group - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // folded-BN scale/bias of this expert group, staged once per CTA
@@ -289,7 +293,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // HBM round trip that the ~1.4 us of MMAs per tile only partly cover: ask L2 for the NEXT tile's rows now.
         if (p.res_prefetch) {
           const int tn = t + t_step;
-          if (tn < p.tiles_per_group) {
+          if (tn >= 0 && tn < p.tiles_per_group) {
             const int q0n = tn * TILE_P + hs * BLOCK_M + lg * 32;
             const int bytes = min(32, max(0, p.group_positions - q0n)) * ROWB;
             const uint8_t* srcn = reinterpret_cast<const uint8_t*>(p.residual + (int64_t)g * p.res_group_elems + (int64_t)q0n * N);
@@ -788,6 +792,7 @@ int amoe_conv3x3_flat_fwd_strided(amoe_ctx* ctx, const void* x, const void* w, c
   p.group_positions = (int)gp;
   p.tiles_per_group = (int)((gp + tile_p - 1) / tile_p);
   p.relu = relu;
+  p.reverse = ctx->walk_reverse;
   { const char* e = getenv("AMOE_FLAT_RES_PREFETCH"); p.res_prefetch = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
   p.y_group_elems = (y_group_images > 0 ? y_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;
   p.res_group_elems = (res_group_images > 0 ? res_group_images : B) * (int64_t)p.Hp * p.Wp * Cout;

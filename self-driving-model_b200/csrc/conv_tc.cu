@@ -25,7 +25,8 @@ namespace tc {
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_TAPS = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;       // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int NUM_THREADS_EPI8 = 320;  // ... plus warps 6-9: a second set of epilogue warps taking the upper half of a tile's columns
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -67,6 +68,7 @@ struct Params {
   // Neither did plain prefetch.global.L2 of the unit after the next one's input region by the idle lanes of the producer warp
   // (layer2 entry 159 -> 259 us).  The stage entries are HBM-bound, not latency-bound: the layer2 entry reads 403 MB and
   // writes 168 MB (two outputs in the dual launch: 374 MB) of DRAM, 4.8 TB/s when its epilogue only drains.
+  int reverse;   // walk the whole tiles back to front (amoe_set_walk_reverse); tail-split units stay last
   int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
   const float* scale;
@@ -111,7 +113,10 @@ struct Unit {
 __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
   Unit r;
   if (u < p.full_units) {
-    r.tile = u; r.n_off = 0; r.bn = p.block_n;
+    r.n_off = 0; r.bn = p.block_n;
+    if (!p.reverse) r.tile = u;
+    else if (p.w_resident) { const int g = u / p.tiles_per_group; r.tile = (2 * g + 1) * p.tiles_per_group - 1 - u; }   // inside its group
+    else r.tile = p.full_units - 1 - u;
   } else {
     const int k = u - p.full_units;
     r.tile = p.full_units + k / p.split;
@@ -125,7 +130,7 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
 // tcgen05.mma.cta_group::2 whose B operand is split over the pair - each CTA loads and holds only HALF of every weight box
 // (16 instead of 32 KB per K chunk at N = 256: a third less L2->SMEM traffic per CTA, half the B reads per MMA step).
 template <int CTAS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS_EPI8, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -149,14 +154,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                             (p.w_resident ? (size_t)p.stages * A_STAGE_BYTES + (size_t)w_boxes * b_stage_bytes
                                                           : (size_t)p.stages * (A_STAGE_BYTES + b_stage_bytes)));
   float* s_bias = s_scale + p.n_ch_total;
-  for (int i = threadIdx.x; i < p.n_ch_total; i += NUM_THREADS) {
+  for (int i = threadIdx.x; i < p.n_ch_total; i += (int)blockDim.x) {
     s_scale[i] = __ldg(p.scale + i);
     s_bias[i] = __ldg(p.bias + i);
   }
   float* s_scale2 = s_bias + p.n_ch_total;      // second problem (nprob == 2)
   float* s_bias2 = s_scale2 + p.n_ch_total;
   if (p.nprob == 2) {
-    for (int i = threadIdx.x; i < p.n_ch_total; i += NUM_THREADS) {
+    for (int i = threadIdx.x; i < p.n_ch_total; i += (int)blockDim.x) {
       s_scale2[i] = __ldg(p.scale2 + i);
       s_bias2[i] = __ldg(p.bias2 + i);
     }
@@ -177,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4 * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
+      mbar_init(bar_tempty + 8 * a, (blockDim.x - 64u) / 32u * CTAS);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -321,7 +326,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ============================ epilogue ================================
+    // Short-K launches (stage entries, 1x1 convolutions) are bound by this epilogue, one warp per SM sub-partition working
+    // through ~250 dependent instructions per 32-column chunk (measured with the body removed: layer2 entry 246 -> 165 us,
+    // layer3 entry 150 -> 98 us); they run with a second set of four warps that takes the upper half of the columns.
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    const int n_sets = ((int)blockDim.x - 64) >> 7, eset = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     int it = 0;
@@ -354,7 +363,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * ACC_STRIDE);
-      for (int c0 = 0; c0 < un.bn; c0 += 32) {
+      // columns of this warp: a multiple of 32 per set
+      const int c_per = n_sets == 1 ? un.bn : (((un.bn >> 5) + 1) >> 1) << 5;
+      const int c_lo = eset * c_per, c_hi = min(un.bn, c_lo + c_per);
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         // a 32-channel chunk never straddles output sub-tensors (split_c % 32 == 0)
         const int ch = chn + c0;
         const int64_t off = (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pix * p.split_c + ch % p.split_c - c0;
@@ -428,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int dw = dw0; dw <= dw1; ++dw) {
               if (dh == 0 && dw == 0) continue;
               const int64_t pixb = pix + (int64_t)dh * Wop + dw;
-              for (int c0 = 0; c0 < un.bn; c0 += 32) {
+              for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                 const int ch = chn + c0;
                 __nv_bfloat16* d = e_y + (int64_t)(tc_.g * nsplit + ch / p.split_c) * sub_stride + pixb * p.split_c + ch % p.split_c;
 #pragma unroll
@@ -561,6 +573,7 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   if (pair) p.tiles_b = ceil_div(p.tiles_b, 2);     // pairs of image tiles
   p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c; p.out_pad = out_pad;
   { const char* e = getenv("AMOE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.reverse = ctx->walk_reverse;
   p.num_taps = num_taps;
   p.k_chunks = k_chunks;
   const int stage_bytes = p.w_resident ? A_STAGE_BYTES : A_STAGE_BYTES + (p.block_n / ctas) * 128;
@@ -667,10 +680,13 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   const size_t smem = (size_t)p.stages * stage_bytes + w_res_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
   AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage (%zu bytes)", smem);
   const int gy = p.w_resident ? G : 1;
+  // eight epilogue warps where a tile's MMAs (K iterations x block_n cycles) are short against its drain: AMOE_TC_EPI8 = 0 / 1 forces
+  int threads = (num_taps * k_chunks <= 24 && p.block_n >= 64) ? NUM_THREADS_EPI8 : NUM_THREADS;
+  { const char* e = getenv("AMOE_TC_EPI8"); if (e != nullptr) threads = atoi(e) != 0 && p.block_n >= 64 ? NUM_THREADS_EPI8 : NUM_THREADS; }
   if (pair)
-    AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2>, 2, dim3(2 * grid, gy), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
+    AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2>, 2, dim3(2 * grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
   else
-    AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1>, dim3(grid, gy), dim3(NUM_THREADS), smem, st, tmA, tmW, tmW2, p));
+    AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1>, dim3(grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

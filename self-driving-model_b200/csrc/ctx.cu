@@ -36,6 +36,7 @@ int amoe_create(int device, amoe_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->launches.store(0);
+  ctx->walk_reverse = 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -51,6 +52,12 @@ int amoe_create(int device, amoe_ctx** out) {
     return -1;
   }
   *out = ctx;
+  return 0;
+}
+
+int amoe_set_walk_reverse(amoe_ctx* ctx, int reverse) {
+  AMOE_REQUIRE(ctx != nullptr, "amoe_set_walk_reverse: NULL ctx");
+  ctx->walk_reverse = reverse ? 1 : 0;
   return 0;
 }
 

@@ -141,6 +141,44 @@ def test_conv_tc_bf16(shape):
 
 
 @pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [
+    # G, B, H, W, Cin, Cout, k, s
+    (3, 64, 8, 8, 512, 512, 3, 1),      # 192 pair-tiles of N=256 on 74 CTA pairs: partial last wave -> tail splitting
+    (3, 40, 16, 16, 256, 256, 3, 1),    # CTA pairs, one N tile
+    (2, 40, 32, 32, 64, 128, 3, 2),     # stage entry geometry: resident weights, grid (CTAs, G)
+    (1, 300, 8, 8, 128, 64, 1, 1),      # 1x1
+])
+def test_conv_tc_walk_direction_and_schedules(case, monkeypatch):
+    """The tile schedule of csrc/conv_tc.cu (walk direction, CTA pairs, tail splitting, resident weights) never changes a
+    result bit: every variant against the plain one-CTA-per-tile front-to-back launch."""
+    from automoe_b200 import _ops
+    G, B, H, W, Cin, Cout, k, s = case
+    g = torch.Generator().manual_seed(21)
+    convs, bns = _mk_conv_bn(Cin, Cout, k, s, k // 2, g, n=G)
+    x = torch.randn((G * B, H, W, Cin), generator=g).to(DEV).bfloat16()
+    pc = _ops.pack_conv(convs, bns, torch.bfloat16, torch.device(DEV), relu=True)
+    for key in ("AMOE_TC_PAIR", "AMOE_TC_TAIL_SPLIT", "AMOE_TC_WRES"):
+        monkeypatch.setenv(key, "0")
+    _ops.walk_reset(DEV, 0)
+    ref = _ops.conv2d(pc, x, B, H, W)
+    for key in ("AMOE_TC_PAIR", "AMOE_TC_TAIL_SPLIT", "AMOE_TC_WRES"):
+        monkeypatch.delenv(key)
+    for first in (0, 1):
+        _ops.walk_reset(DEV, first)
+        y = _ops.conv2d(pc, x, B, H, W)
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref), (first, (y.float() - ref.float()).abs().max().item())
+    monkeypatch.setenv("AMOE_TC_PAIR", "1")          # pairs wherever the kernel takes them
+    _ops.walk_reset(DEV, 1)
+    y = _ops.conv2d(pc, x, B, H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    with torch.no_grad():
+        want = torch.cat([F.relu(bns[i](convs[i](x[i * B:(i + 1) * B].float().permute(0, 3, 1, 2)))) for i in range(G)], 0)
+    assert rel_err(y.float().permute(0, 3, 1, 2), want) < 8e-3
+
+
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("case", [("stem", 3, 2, 64, 64), ("stem", 3, 3, 256, 256), ("stem", 1, 2, 224, 224),
                                   ("policy", 1, 2, 64, 64), ("policy", 1, 3, 256, 256)])
 def test_conv_tc_rowwin(case):
@@ -334,8 +372,11 @@ def test_conv_flat_bf16(shape, kw3, monkeypatch):
     assert _ops.flat_supported(pc, H, W, torch.bfloat16)
     xp = _pad_nhwc(x, torch.bfloat16)
     rp = _pad_nhwc(res, torch.bfloat16) if residual else None
+    _ops.walk_reset(DEV, 0)
     y = _ops.conv3x3_flat(pc, xp, B, H, W, residual=rp)
+    y_rev = _ops.conv3x3_flat(pc, xp, B, H, W, residual=rp)      # the next launch walks its tiles back to front
     torch.cuda.synchronize()
+    assert torch.equal(y, y_rev)
     with torch.no_grad():
         ref = torch.cat([F.relu(bns[i](convs[i](x[i * B:(i + 1) * B])) + (res[i * B:(i + 1) * B] if residual else 0))
                          for i in range(G)], 0)
