@@ -253,6 +253,9 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // memory: residual rows arrive there by cp.async (issued before the accumulator is ready),
     // every thread updates its row in place, and the warp then streams the 32 x N block - which is
     // contiguous in the flattened [P][N] output - with fully coalesced 16-byte stores.
+    // (Measured and removed: every thread reading its residual row straight from global memory into registers before the
+    // accumulator is ready, no staging - layer1 275 -> 300 us.  The residual convolutions of layer1 move 1.25 GB of DRAM
+    // in 275 us = 4.5 TB/s: they are HBM-bound, the staging is not what they wait for.)
     // Eight warps: warp (lg, hs) owns TMEM lane quarter lg of M-half hs.  (Measured with the epilogue body removed:
     // the N=128 kernel runs at 90 % tensor-busy, 156-166 us per layer2 convolution, against 70-76 % / 189-214 us with
     // four warps draining both halves one after the other - it was bound by this epilogue, not by its MMAs.)

@@ -68,6 +68,10 @@ struct Params {
   // Neither did plain prefetch.global.L2 of the unit after the next one's input region by the idle lanes of the producer warp
   // (layer2 entry 159 -> 259 us).  The stage entries are HBM-bound, not latency-bound: the layer2 entry reads 403 MB and
   // writes 168 MB (two outputs in the dual launch: 374 MB) of DRAM, 4.8 TB/s when its epilogue only drains.
+  // (Measured and removed, twice - rounds 1 and 2: a write-out staged through swizzled shared memory, 4 complete 128-byte row
+  // pieces per store instruction instead of 32 16-byte pieces.  Bit-identical, slower everywhere it was on: layer2 entry
+  // 296 -> 415 us, layer3 entry 156 -> 198 us, policy conv3 57 -> 72 us - N <= 128 MMA steps already read their operands at
+  // the shared-memory bandwidth limit, the staging traffic comes out of the same budget.)
   int reverse;   // walk the whole tiles back to front (amoe_set_walk_reverse); tail-split units stay last
   int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
@@ -578,7 +582,17 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   p.k_chunks = k_chunks;
   const int stage_bytes = p.w_resident ? A_STAGE_BYTES : A_STAGE_BYTES + (p.block_n / ctas) * 128;
   const int w_res_bytes = p.w_resident ? (num_taps * k_chunks + (second != nullptr ? k_chunks : 0)) * (p.block_n / ctas) * 128 : 0;
-  p.stages = std::min(MAX_STAGES, ((p.w_resident ? SMEM_RESIDENT : SMEM_BUDGET) - w_res_bytes) / stage_bytes);
+  // eight epilogue warps (AMOE_TC_EPI8 = 1; measured neutral, off by default)
+  int threads = NUM_THREADS;
+  { const char* e = getenv("AMOE_TC_EPI8"); if (e != nullptr && atoi(e) != 0 && p.block_n >= 64) threads = NUM_THREADS_EPI8; }
+  const int stg_bytes = 0;
+  const int sb_bytes = (second != nullptr ? 4 : 2) * G * Cout * (int)sizeof(float);
+  {
+    const int limit = SMEM_BUDGET + 24 * 1024;          // dynamic shared memory the kernel may use (+ 1 KB alignment slack)
+    const int normal = (p.w_resident ? SMEM_RESIDENT : SMEM_BUDGET) - w_res_bytes;
+    p.stages = std::min(MAX_STAGES, std::min(normal, limit - w_res_bytes - sb_bytes - stg_bytes) / stage_bytes);
+    AMOE_REQUIRE(p.stages >= 2, "conv_tc: shared memory budget exceeded");
+  }
   p.relu = relu; p.x_shared = x_shared;
   int64_t total = (int64_t)G * p.tiles_b * p.tiles_h * p.tiles_w * p.n_tiles_n;
   AMOE_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
@@ -677,12 +691,9 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMOE_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(second weights) failed with %d", (int)r);
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + w_res_bytes + 1024 + (size_t)(2 * p.nprob) * p.n_ch_total * sizeof(float);
+  const size_t smem = (size_t)p.stages * stage_bytes + w_res_bytes + 1024 + (size_t)sb_bytes + stg_bytes;
   AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage (%zu bytes)", smem);
   const int gy = p.w_resident ? G : 1;
-  // eight epilogue warps where a tile's MMAs (K iterations x block_n cycles) are short against its drain: AMOE_TC_EPI8 = 0 / 1 forces
-  int threads = (num_taps * k_chunks <= 24 && p.block_n >= 64) ? NUM_THREADS_EPI8 : NUM_THREADS;
-  { const char* e = getenv("AMOE_TC_EPI8"); if (e != nullptr) threads = atoi(e) != 0 && p.block_n >= 64 ? NUM_THREADS_EPI8 : NUM_THREADS; }
   if (pair)
     AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2>, 2, dim3(2 * grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
   else
