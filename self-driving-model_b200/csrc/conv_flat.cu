@@ -336,32 +336,23 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint4* slot = reinterpret_cast<uint4*>(my_row + (((j & ~7) | ((j ^ lane) & 7)) * 16));
             uint4 o = make_uint4(0u, 0u, 0u, 0u);  // border positions stay zero
             if (interior) {
+              // two-lane FMAs / adds and the ReLU on the packed pairs (tc_common.cuh): the bits of the scalar sequence
               const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
               float f[8];
-              f[0] = fmaf(__uint_as_float(a[h][v * 8 + 0]), s0.x, b0.x);
-              f[1] = fmaf(__uint_as_float(a[h][v * 8 + 1]), s0.y, b0.y);
-              f[2] = fmaf(__uint_as_float(a[h][v * 8 + 2]), s0.z, b0.z);
-              f[3] = fmaf(__uint_as_float(a[h][v * 8 + 3]), s0.w, b0.w);
-              f[4] = fmaf(__uint_as_float(a[h][v * 8 + 4]), s1.x, b1.x);
-              f[5] = fmaf(__uint_as_float(a[h][v * 8 + 5]), s1.y, b1.y);
-              f[6] = fmaf(__uint_as_float(a[h][v * 8 + 6]), s1.z, b1.z);
-              f[7] = fmaf(__uint_as_float(a[h][v * 8 + 7]), s1.w, b1.w);
+              ffma2(f[0], f[1], a[h][v * 8 + 0], a[h][v * 8 + 1], s0.x, s0.y, b0.x, b0.y);
+              ffma2(f[2], f[3], a[h][v * 8 + 2], a[h][v * 8 + 3], s0.z, s0.w, b0.z, b0.w);
+              ffma2(f[4], f[5], a[h][v * 8 + 4], a[h][v * 8 + 5], s1.x, s1.y, b1.x, b1.y);
+              ffma2(f[6], f[7], a[h][v * 8 + 6], a[h][v * 8 + 7], s1.z, s1.w, b1.z, b1.w);
               if (has_res) {
                 const uint4 rr = *slot;
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  float2 rf = __bfloat1622float2(r2[jj]);
-                  f[2 * jj] += rf.x;
-                  f[2 * jj + 1] += rf.y;
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+                add_bf16x2(f[0], f[1], rr.x);
+                add_bf16x2(f[2], f[3], rr.y);
+                add_bf16x2(f[4], f[5], rr.z);
+                add_bf16x2(f[6], f[7], rr.w);
               }
               o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                              pack_bf16x2(f[6], f[7]));
+              if (p.relu) o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
             }
             *slot = o;
           }

@@ -72,6 +72,9 @@ struct Params {
   // pieces per store instruction instead of 32 16-byte pieces.  Bit-identical, slower everywhere it was on: layer2 entry
   // 296 -> 415 us, layer3 entry 156 -> 198 us, policy conv3 57 -> 72 us - N <= 128 MMA steps already read their operands at
   // the shared-memory bandwidth limit, the staging traffic comes out of the same budget.)
+  // (Measured and removed, round 2 session 3: only the FOUR plane-opening boxes of the next unit prefetched a unit ahead
+  // (stride-2 resident-weight launches, 3-box ring): layer2 entry dual 224 -> 247 us, single 157 -> 199 us, policy conv3
+  // 56 -> 68 us, layer3/4 entries unchanged.  Any cp.async.bulk.prefetch.tensor traffic slows these launches down.)
   int reverse;   // walk the whole tiles back to front (amoe_set_walk_reverse); tail-split units stay last
   int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
@@ -130,10 +133,46 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
   return r;
 }
 
+// ---- lean bf16 epilogue (LEAN = true): the common inference case - bf16 output, one output tensor per group (split_c == Cout) ----
+// The generic epilogue below spends ~250 instructions per 32-column chunk (an integer division for the sub-tensor split,
+// the fp32 / bf16 output and residual variants, scalar FFMA / FMNMX); short-K launches (stage entries, 1x1 convolutions, the
+// policy backbone) are bound by it.  Here a chunk is: 16 LDS.128 (scale / bias), 16 two-lane FMAs (fma.rn.f32x2, per-element
+// IEEE: the bits of fmaf), 16 packs, the ReLU on the packed pairs (max(bf16(x), 0) == bf16(max(x, 0))), 4 16-byte stores.
+// one 32-column chunk: acc -> scale/bias (+ residual) -> bf16 (-> ReLU) -> four 16-byte stores at dst
+template <bool RES>
+__device__ __forceinline__ void lean_chunk(const uint32_t (&acc)[32], const float* sc, const float* bs, const __nv_bfloat16* res,
+                                           __nv_bfloat16* dst, bool relu) {
+  const float4* sc4 = reinterpret_cast<const float4*>(sc);
+  const float4* bs4 = reinterpret_cast<const float4*>(bs);
+  uint4 rr[4];
+  if (RES) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+    float f[8];
+    ffma2(f[0], f[1], acc[v * 8 + 0], acc[v * 8 + 1], s0.x, s0.y, b0.x, b0.y);
+    ffma2(f[2], f[3], acc[v * 8 + 2], acc[v * 8 + 3], s0.z, s0.w, b0.z, b0.w);
+    ffma2(f[4], f[5], acc[v * 8 + 4], acc[v * 8 + 5], s1.x, s1.y, b1.x, b1.y);
+    ffma2(f[6], f[7], acc[v * 8 + 6], acc[v * 8 + 7], s1.z, s1.w, b1.z, b1.w);
+    if (RES) {
+      add_bf16x2(f[0], f[1], rr[v].x);
+      add_bf16x2(f[2], f[3], rr[v].y);
+      add_bf16x2(f[4], f[5], rr[v].z);
+      add_bf16x2(f[6], f[7], rr[v].w);
+    }
+    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    if (relu) o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
+    *reinterpret_cast<uint4*>(dst + v * 8) = o;
+  }
+}
+
 // CTAS = 2: clusters of two CTAs work on two M tiles (adjacent image tiles) of the same N tile; the leader issues M = 256
 // tcgen05.mma.cta_group::2 whose B operand is split over the pair - each CTA loads and holds only HALF of every weight box
 // (16 instead of 32 KB per K chunk at N = 256: a third less L2->SMEM traffic per CTA, half the B reads per MMA step).
-template <int CTAS>
+template <int CTAS, bool LEAN>
 __global__ void __launch_bounds__(NUM_THREADS_EPI8, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ Params p) {
@@ -370,6 +409,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // columns of this warp: a multiple of 32 per set
       const int c_per = n_sets == 1 ? un.bn : (((un.bn >> 5) + 1) >> 1) << 5;
       const int c_lo = eset * c_per, c_hi = min(un.bn, c_lo + c_per);
+      bool handed_back = false;   // LEAN: the accumulator is released as soon as its last chunk is in registers
+      if constexpr (LEAN) {
+        // two TMEM loads in flight: the next chunk's load is issued before the current chunk's arithmetic
+        const float* sc = e_scale + ch0;
+        const float* bs = e_bias + ch0;
+        __nv_bfloat16* yrow = e_y + (int64_t)tc_.g * sub_stride + pix * p.Cout + chn;
+        const __nv_bfloat16* rrow = p.residual + (int64_t)tc_.g * sub_stride + pix * p.Cout + chn;
+        auto hand_back = [&]() {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(tempty_leader + 8 * as);
+            else mbar_arrive(bar_tempty + 8 * as);
+          }
+          handed_back = true;
+        };
+        uint32_t accA[32], accB[32];
+        if (c_lo < c_hi) tmem_ld_32x32b_x32(taddr + (uint32_t)c_lo, accA);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+          const bool has_b = c0 + 32 < c_hi, has_next = c0 + 64 < c_hi;
+          tmem_ld_wait();
+          if (has_b) tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 32), accB);
+          else hand_back();
+          if (valid) {
+            if (use_res) lean_chunk<true>(accA, sc + c0, bs + c0, rrow + c0, yrow + c0, e_relu != 0);
+            else lean_chunk<false>(accA, sc + c0, bs + c0, nullptr, yrow + c0, e_relu != 0);
+          }
+          if (has_b) {
+            tmem_ld_wait();
+            if (has_next) tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 64), accA);
+            else hand_back();
+            if (valid) {
+              if (use_res) lean_chunk<true>(accB, sc + c0 + 32, bs + c0 + 32, rrow + c0 + 32, yrow + c0 + 32, e_relu != 0);
+              else lean_chunk<false>(accB, sc + c0 + 32, bs + c0 + 32, nullptr, yrow + c0 + 32, e_relu != 0);
+            }
+          }
+        }
+      } else
       for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         // a 32-channel chunk never straddles output sub-tensors (split_c % 32 == 0)
         const int ch = chn + c0;
@@ -427,11 +504,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_cluster(tempty_leader + 8 * as);
-        else mbar_arrive(bar_tempty + 8 * as);
+      if (!handed_back) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(tempty_leader + 8 * as);
+          else mbar_arrive(bar_tempty + 8 * as);
+        }
       }
       if (p.out_pad == 1 && prob == 0 && valid) {
         // Physical zero border of the padded output (the consumer's 3x3 taps read it as their padding): written by the
@@ -488,10 +567,11 @@ static bool supported(int H, int W, int Cin, int Cout, int sh, int sw) {
 int amoe_conv_tc_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc::SMEM_BUDGET + 1024 + 24 * 1024));
-  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc::SMEM_BUDGET + 1024 + 24 * 1024));
+  const int smem_max = tc::SMEM_BUDGET + 1024 + 24 * 1024;
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   return 0;
 }
 
@@ -694,10 +774,16 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   const size_t smem = (size_t)p.stages * stage_bytes + w_res_bytes + 1024 + (size_t)sb_bytes + stg_bytes;
   AMOE_REQUIRE(smem <= (size_t)SMEM_BUDGET + 1024 + 24 * 1024, "conv_tc: too many channels for the shared-memory scale/bias stage (%zu bytes)", smem);
   const int gy = p.w_resident ? G : 1;
-  if (pair)
-    AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2>, 2, dim3(2 * grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
-  else
-    AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1>, dim3(grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
+  // lean bf16 epilogue (see lean_chunk) wherever it applies; AMOE_TC_LEAN=0 keeps the generic one (A/B switch)
+  const bool lean_on = [] { const char* e = getenv("AMOE_TC_LEAN"); return e == nullptr || atoi(e) != 0; }();
+  const bool lean = lean_on && !p.out_f32 && split_c == Cout && p.dbg == 0;
+  if (pair) {
+    if (lean) AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2, true>, 2, dim3(2 * grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
+    else AMOE_CHECK_CUDA(amoe_launch_pdl_cluster(conv_tc_kernel<2, false>, 2, dim3(2 * grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
+  } else {
+    if (lean) AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1, true>, dim3(grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
+    else AMOE_CHECK_CUDA(amoe_launch_pdl(conv_tc_kernel<1, false>, dim3(grid, gy), dim3(threads), smem, st, tmA, tmW, tmW2, p));
+  }
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

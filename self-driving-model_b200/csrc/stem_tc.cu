@@ -261,19 +261,6 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
   for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
   return r;
 }
-// two fp32 FMAs in one instruction (Blackwell fma.rn.f32x2; per-element IEEE, same bits as fmaf)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, uint32_t a0, uint32_t a1, float s0, float s1, float b0, float b1) {
-  asm("{\n"
-      ".reg .b64 ra, rs, rb, rd;\n"
-      "mov.b64 ra, {%2, %3};\n"
-      "mov.b64 rs, {%4, %5};\n"
-      "mov.b64 rb, {%6, %7};\n"
-      "fma.rn.f32x2 rd, ra, rs, rb;\n"
-      "mov.b64 {%0, %1}, rd;\n"
-      "}\n"
-      : "=f"(d0), "=f"(d1)
-      : "r"(a0), "r"(a1), "f"(s0), "f"(s1), "f"(b0), "f"(b1));
-}
 // folded BN (+ optional ReLU) of 32 accumulator columns -> 4 x 8 packed bf16
 template <bool RELU>
 __device__ __forceinline__ void bn_pack32(const uint32_t (&a)[32], const float* s_scale, const float* s_bias, uint4 (&q)[4]) {

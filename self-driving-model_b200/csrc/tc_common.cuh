@@ -124,6 +124,39 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- two-lane fp32 arithmetic for the bf16 epilogues (Blackwell fma/add.rn.f32x2: per-element IEEE, the bits of fmaf / +) ----
+__device__ __forceinline__ void ffma2(float& d0, float& d1, uint32_t a0, uint32_t a1, float s0, float s1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 ra, rs, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rs, {%4, %5};\n"
+      "mov.b64 rb, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rs, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "r"(a0), "r"(a1), "f"(s0), "f"(s1), "f"(b0), "f"(b1));
+}
+// (f0, f1) += the two bf16 halves of r (low half = first channel)
+__device__ __forceinline__ void add_bf16x2(float& f0, float& f1, uint32_t r) {
+  asm("{\n"
+      ".reg .b64 ra, rb;\n"
+      ".reg .b32 lo, hi;\n"
+      "shl.b32 lo, %2, 16;\n"
+      "and.b32 hi, %2, 0xffff0000;\n"
+      "mov.b64 ra, {%0, %1};\n"
+      "mov.b64 rb, {lo, hi};\n"
+      "add.rn.f32x2 ra, ra, rb;\n"
+      "mov.b64 {%0, %1}, ra;\n"
+      "}\n"
+      : "+f"(f0), "+f"(f1)
+      : "r"(r));
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+  return r;
+}
 // Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // begin while its predecessor in the stream is still running - its CTAs take over SMs as the predecessor's CTAs retire
 // and run their prologue (barrier init, TMEM allocation, descriptor prefetch, constant weight loads) - but must not touch
