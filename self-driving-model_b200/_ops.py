@@ -287,6 +287,13 @@ def _walk_step(device) -> None:
     _WALK[idx] = d ^ 1
 
 
+def overlap_tail() -> bool:
+    """Run the policy backbone (independent of the experts) on a second stream beside the head / gate kernels
+    (AMOE_TAIL_OVERLAP=0 keeps it behind the gate on the main stream)."""
+    import os
+    return os.environ.get("AMOE_TAIL_OVERLAP", "1") != "0"
+
+
 def overlap_outputs() -> bool:
     """Fork the full-resolution logit writers onto a side stream (AMOE_OVERLAP=0 keeps one stream)."""
     import os
@@ -680,7 +687,7 @@ def policy_head(x, cvec, params, backbone_dim, ctx_dim, hidden, horizon, params_
     spd = torch.empty((B, horizon), device=dev, dtype=torch.float32)
     if params_bf16 is not None and B >= 16:
         assert params_bf16.dtype == torch.bfloat16 and params_bf16.numel() == params.numel()
-        if x.dtype == torch.bfloat16 and Cf % 8 == 0:
+        if x.dtype == torch.bfloat16 and Cf % 8 == 0:     # (already pooled by TrajectoryPolicy.backbone_features otherwise)
             x = mean_hw_nhwc(x).view(B, 1, 1, Cf)
             h = w = 1
     else:

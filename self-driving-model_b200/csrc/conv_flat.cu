@@ -259,6 +259,11 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Eight warps: warp (lg, hs) owns TMEM lane quarter lg of M-half hs.  (Measured with the epilogue body removed:
     // the N=128 kernel runs at 90 % tensor-busy, 156-166 us per layer2 convolution, against 70-76 % / 189-214 us with
     // four warps draining both halves one after the other - it was bound by this epilogue, not by its MMAs.)
+    // (Measured and removed: lane 0 alone polling the mbarriers + __syncwarp.  ncu --set full counts ~29 M shared-memory "bank
+    // conflicts" per layer1 launch - 32 lanes of a try_wait hitting one word, the LSU shared pipe 77 % busy beside the tensor
+    // core's operand pipe at 82 % - but they cost nothing: epilogue warps polling with one lane is neutral (222/273 us either
+    // way), and in the MMA issuer warps it is slower (layer2 pair kernel 186 -> 463 us: a lane-0 branch next to the elected
+    // MMA issue takes the descriptors off the uniform datapath).)
     griddep_wait();                      // residual reads / output writes only after the previous kernel is complete
     const int lg = warp & 3, hs = (warp - 3) >> 2;
     const int img = p.Hp * p.Wp;
@@ -711,6 +716,11 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // epilogue is bound by instruction issue as a whole.  Making everything sub-tile-independent a per-thread constant
 // (this version, ~250 instructions) recovered two thirds of the gap.  What is left is inherent to the shift
 // (32 shuffles, the exchange and its barrier, eight warps' fixed overhead); the 171 us bound stays the target.
+// Round 2, session 3: sixteen epilogue warps of 16 channels each (88 registers, two pieces per thread, bit-identical to
+// the eight-warp version): 272 / 320 us against 271 / 313 us - the epilogue is not bound by latency hiding either.
+// tcgen05.shift.down (tools/probe_shift.cu: moves 8 columns of ALL 128 lanes by one lane towards lane 0 inside each
+// 32-lane block, lane 31 of a block keeps its value; ~70 cycles per instruction) cannot replace the shuffles: 8 shifts
+// per 64-column accumulator are ~560 tensor-pipe cycles per sub-tile and the block boundary still needs the exchange.
 static bool pair_enabled(int cout) {
   // default: pairs for the N = 128 kernel only.  Measured on B200 (tools/flat_bench.py, 3 x 256 frames): layer2 195 -> 180 us
   // (215 -> 198 us with residual), but layer1 (N = 64) 232 -> 303 us - a pair MMA reads its operands at ~64 B/clk per SM

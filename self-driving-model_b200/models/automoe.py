@@ -23,7 +23,7 @@ from ._gatepack import pack_gate_params, require_eval
 from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert, NuScenesExpert
-from .experts._base import BDDExpertBase, get_trunk_pack, run_experts
+from .experts._base import BDDExpertBase, get_trunk_pack, run_experts, side_stream
 from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, run_trunk_train,
                              stage_image, trunk_pool_pad)
 from .experts.expert_extractors import create_expert_extractors
@@ -327,9 +327,25 @@ class AutoMoE(nn.Module):
             else:
                 stem_out, pol1 = _ops.stem_forward(fs, x_nhwc, Bn, Hn, Wn, groups=[len(bdd), 1])
 
+        # The policy backbone (conv2-4 + pooling) depends on the stem only: it is forked onto a second stream right behind the
+        # last tensor-bound expert launch, beside the 1x1 heads and the gate kernel (latency-bound, 64 CTAs), and the policy
+        # heads join it behind the gate.
+        pol = {}
+
+        def fork_policy_backbone():
+            main = torch.cuda.current_stream(image.device)
+            ps = side_stream(image.device, 1)
+            ps.wait_stream(main)
+            with torch.cuda.stream(ps):
+                pol['feat'] = self.policy_head.backbone_features(image, _dtype=dtype, _conv1=pol1)
+            pol1.record_stream(ps)
+            pol['feat'].record_stream(main)
+            pol['stream'] = ps
+
         expert_outputs, aux = run_experts(self._bdd_experts(), image, dtype, self._expert_packs, x_nhwc=x_nhwc,
                                           stem_out=stem_out, stem_pooled=pooled, layer1_out=layer1,
-                                          overlap_outputs=_ops.overlap_outputs())
+                                          overlap_outputs=_ops.overlap_outputs(),
+                                          after_head3=fork_policy_backbone if (pol1 is not None and _ops.overlap_tail()) else None)
         expert_outputs, n_ch, ext = self._other_expert_features(image, dtype, x_nhwc, expert_outputs, aux['n_ch'])
 
         gn = self.gating_network
@@ -338,7 +354,10 @@ class AutoMoE(nn.Module):
                       self.context_extractor.context_dim, gn.hidden_dim, gn.temperature, mode=gn._gate_kind(),
                       params_bf16=gflat16 if _ops.mlp_tc(dtype) else None, ext_features=ext)
 
-        policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1)
+        if pol.get('stream') is not None:
+            torch.cuda.current_stream(image.device).wait_stream(pol['stream'])
+        policy_output = self.policy_head(image, context=g['combined'], _x_nhwc=x_nhwc, _dtype=dtype, _conv1=pol1,
+                                         _feat=pol.get('feat'))
         if aux.get('join') is not None:      # full-resolution logits were written on the side stream
             torch.cuda.current_stream(image.device).wait_stream(aux['join'])
         speed_seq = policy_output.get('speed')

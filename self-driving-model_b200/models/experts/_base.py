@@ -73,9 +73,10 @@ def get_trunk_pack(experts, dtype, device, cache: dict, with_head: bool = True) 
 _SIDE_STREAMS: dict = {}
 
 
-def side_stream(device: torch.device) -> torch.cuda.Stream:
-    """One auxiliary stream per device for work that overlaps the gate/policy tail of the forward."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+def side_stream(device: torch.device, which: int = 0) -> torch.cuda.Stream:
+    """Auxiliary streams per device for work that overlaps the gate/policy tail of the forward
+    (0: full-resolution logit writers, 1: policy backbone)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), which)
     s = _SIDE_STREAMS.get(key)
     if s is None:
         s = torch.cuda.Stream(device=device)
@@ -91,7 +92,7 @@ def _tensors_of(out):
 
 def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.dtype, cache: dict, x_nhwc=None,
                 stem_out=None, stem_pooled=None, layer1_out=None, overlap_outputs: bool = False,
-                frozen_eval: bool = False):
+                frozen_eval: bool = False, after_head3=None):
     """Run G experts on the same image batch in grouped launches.
 
     Returns (expert_outputs in the reference's format, dict(pooled=[B,sumC], n_ch=[...], exact_pool=bool)).
@@ -108,7 +109,7 @@ def run_experts(experts: List[BDDExpertBase], image: torch.Tensor, dtype: torch.
         _check_eval(experts)
     pack = get_trunk_pack(experts, dtype, image.device, cache)
     B, _, H, W = image.shape
-    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled, layer1_out)
+    lows, pooled, (h, w) = run_trunks(pack, image, x_nhwc, stem_out, stem_pooled, layer1_out, after_head3=after_head3)
     exact_pool = all((not e.upsample_to_input) or (H % h == 0 and W % w == 0) for e in experts)
     join = None
     if overlap_outputs and exact_pool:

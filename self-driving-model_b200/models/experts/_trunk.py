@@ -244,8 +244,10 @@ def run_stem_layer1_chunked(pack: TrunkPack, fused_stem, x_nhwc: torch.Tensor, B
 
 def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tensor] = None,
                stem_out: Optional[torch.Tensor] = None, stem_pooled: Optional[torch.Tensor] = None,
-               layer1_out: Optional[torch.Tensor] = None, features_only: bool = False):
+               layer1_out: Optional[torch.Tensor] = None, features_only: bool = False, after_head3=None):
     """image: [B,3,H,W] fp32 NCHW.  Returns (low_res list of [B,h,w,N_e] fp32, pooled [B,sumC] fp32, (h,w)).
+    after_head3: optional callable invoked once the last tensor-bound launch (the heads' 3x3 convolution) is enqueued -
+    the point where AutoMoE.forward forks the policy backbone onto its own stream.
 
     Follows torchvision ResNet._forward_impl up to layer4 and BasicBlock.forward
     (conv-bn-relu-conv-bn + identity/downsample, add, relu), then the expert head
@@ -310,6 +312,8 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
     if features_only:
         return y                                                         # [G*B,h,w,512] (layer4 is never stored padded)
     hid = _ops.conv2d(pack.head3, y, B, h, w)                            # [G*B,h,w,256]
+    if after_head3 is not None:
+        after_head3()
     pooled = torch.empty((B, sum(pack.n_ch)), device=image.device, dtype=torch.float32)
     lows, off = [], 0
     for g in range(G):

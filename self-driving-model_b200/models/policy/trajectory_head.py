@@ -80,13 +80,10 @@ class TrajectoryPolicy(nn.Module):
             p["convs"][0][mode] = first
         return first
 
-    def forward(self, image: torch.Tensor, context: Optional[torch.Tensor] = None, _x_nhwc=None,
-                _dtype=None, _conv1=None) -> Dict[str, torch.Tensor]:
-        from .._train_forward import policy_forward, wants_grad
-        if wants_grad(self):
-            return policy_forward(self, image, context)
-        if not image.is_cuda:
-            raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+    def backbone_features(self, image: torch.Tensor, _x_nhwc=None, _dtype=None, _conv1=None) -> torch.Tensor:
+        """EasyBackbone.net (trajectory_head.py:8-21) on the inference kernels: the last convolution's NHWC map, or - bf16
+        tensor-core mode - its spatial mean [B,1,1,256] fp32 (the pooling the head would run first).  Independent of the
+        gate, so AutoMoE.forward can run it on a second stream beside the gating kernel."""
         dtype = _dtype or resolve_dtype(self.precision)
         p = self._pack(dtype, image.device)
         B, _, H, W = image.shape
@@ -105,6 +102,20 @@ class TrajectoryPolicy(nn.Module):
             else:
                 x = _ops.conv2d(pc, x, B, h, w)
             h, w = x.shape[1], x.shape[2]
+        if _ops.mlp_tc(dtype) and B >= 16 and x.dtype == torch.bfloat16 and x.shape[3] % 8 == 0:
+            x = _ops.mean_hw_nhwc(x).view(B, 1, 1, x.shape[3])
+        return x
+
+    def forward(self, image: torch.Tensor, context: Optional[torch.Tensor] = None, _x_nhwc=None,
+                _dtype=None, _conv1=None, _feat=None) -> Dict[str, torch.Tensor]:
+        from .._train_forward import policy_forward, wants_grad
+        if wants_grad(self):
+            return policy_forward(self, image, context)
+        if not image.is_cuda:
+            raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
+        dtype = _dtype or resolve_dtype(self.precision)
+        p = self._pack(dtype, image.device)
+        x = _feat if _feat is not None else self.backbone_features(image, _x_nhwc, dtype, _conv1)
         if context is not None:
             if self.context_dim == 0:
                 raise ValueError("TrajectoryPolicy was built with context_dim=0 but a context was given")
