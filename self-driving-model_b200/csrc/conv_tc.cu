@@ -76,6 +76,7 @@ struct Params {
   // (stride-2 resident-weight launches, 3-box ring): layer2 entry dual 224 -> 247 us, single 157 -> 199 us, policy conv3
   // 56 -> 68 us, layer3/4 entries unchanged.  Any cp.async.bulk.prefetch.tensor traffic slows these launches down.)
   int reverse;   // walk the whole tiles back to front (amoe_set_walk_reverse); tail-split units stay last
+  int wide32;   // lean epilogue: 32-byte stores / residual loads (y and residual 32-byte aligned; AMOE_TC_W32=0 -> 16-byte)
   int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
   int n_ch_total;                   // G*Cout: scale/bias entries staged in shared memory
   const float* scale;
@@ -138,17 +139,35 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
 // the fp32 / bf16 output and residual variants, scalar FFMA / FMNMX); short-K launches (stage entries, 1x1 convolutions, the
 // policy backbone) are bound by it.  Here a chunk is: 16 LDS.128 (scale / bias), 16 two-lane FMAs (fma.rn.f32x2, per-element
 // IEEE: the bits of fmaf), 16 packs, the ReLU on the packed pairs (max(bf16(x), 0) == bf16(max(x, 0))), 4 16-byte stores.
-// one 32-column chunk: acc -> scale/bias (+ residual) -> bf16 (-> ReLU) -> four 16-byte stores at dst
+// 32-byte global accesses (Blackwell: LDG/STG.256): one full sector per thread and instruction
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+// one 32-column chunk: acc -> scale/bias (+ residual) -> bf16 (-> ReLU) -> two 32-byte stores at dst (32-byte aligned:
+// channel offsets are multiples of 32, rows of Cout % 32 == 0 channels, tensors from 32-byte aligned allocations)
 template <bool RES>
 __device__ __forceinline__ void lean_chunk(const uint32_t (&acc)[32], const float* sc, const float* bs, const __nv_bfloat16* res,
-                                           __nv_bfloat16* dst, bool relu) {
+                                           __nv_bfloat16* dst, bool relu, bool wide) {
   const float4* sc4 = reinterpret_cast<const float4*>(sc);
   const float4* bs4 = reinterpret_cast<const float4*>(bs);
   uint4 rr[4];
   if (RES) {
+    if (wide) {
+      ldg256_nc(res, rr[0], rr[1]);
+      ldg256_nc(res + 16, rr[2], rr[3]);
+    } else {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
+      for (int v = 0; v < 4; ++v) rr[v] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
+    }
   }
+  uint4 o[4];
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
     const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
@@ -163,9 +182,15 @@ __device__ __forceinline__ void lean_chunk(const uint32_t (&acc)[32], const floa
       add_bf16x2(f[4], f[5], rr[v].z);
       add_bf16x2(f[6], f[7], rr[v].w);
     }
-    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-    if (relu) o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
-    *reinterpret_cast<uint4*>(dst + v * 8) = o;
+    o[v] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    if (relu) o[v] = make_uint4(relu_bf16x2(o[v].x), relu_bf16x2(o[v].y), relu_bf16x2(o[v].z), relu_bf16x2(o[v].w));
+  }
+  if (wide) {
+    stg256(dst, o[0], o[1]);
+    stg256(dst + 16, o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(dst + v * 8) = o[v];
   }
 }
 
@@ -416,6 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* bs = e_bias + ch0;
         __nv_bfloat16* yrow = e_y + (int64_t)tc_.g * sub_stride + pix * p.Cout + chn;
         const __nv_bfloat16* rrow = p.residual + (int64_t)tc_.g * sub_stride + pix * p.Cout + chn;
+        const bool wide = p.wide32 != 0;
         auto hand_back = [&]() {
           tcgen05_fence_before();
           __syncwarp();
@@ -433,16 +459,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (has_b) tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 32), accB);
           else hand_back();
           if (valid) {
-            if (use_res) lean_chunk<true>(accA, sc + c0, bs + c0, rrow + c0, yrow + c0, e_relu != 0);
-            else lean_chunk<false>(accA, sc + c0, bs + c0, nullptr, yrow + c0, e_relu != 0);
+            if (use_res) lean_chunk<true>(accA, sc + c0, bs + c0, rrow + c0, yrow + c0, e_relu != 0, wide);
+            else lean_chunk<false>(accA, sc + c0, bs + c0, nullptr, yrow + c0, e_relu != 0, wide);
           }
           if (has_b) {
             tmem_ld_wait();
             if (has_next) tmem_ld_32x32b_x32(taddr + (uint32_t)(c0 + 64), accA);
             else hand_back();
             if (valid) {
-              if (use_res) lean_chunk<true>(accB, sc + c0 + 32, bs + c0 + 32, rrow + c0 + 32, yrow + c0 + 32, e_relu != 0);
-              else lean_chunk<false>(accB, sc + c0 + 32, bs + c0 + 32, nullptr, yrow + c0 + 32, e_relu != 0);
+              if (use_res) lean_chunk<true>(accB, sc + c0 + 32, bs + c0 + 32, rrow + c0 + 32, yrow + c0 + 32, e_relu != 0, wide);
+              else lean_chunk<false>(accB, sc + c0 + 32, bs + c0 + 32, nullptr, yrow + c0 + 32, e_relu != 0, wide);
             }
           }
         }
@@ -629,12 +655,14 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   }
   AMOE_REQUIRE(Cout % p.block_n == 0 && p.block_n % 32 == 0, "conv_tc: unsupported channel tiling Cout=%d", Cout);
   p.n_tiles_n = Cout / p.block_n;
-  // CTA pairs (see the kernel): AMOE_TC_PAIR = 0 off, 1 wherever possible, unset: the N = 256 tiles of single-problem launches
+  // CTA pairs (see the kernel): AMOE_TC_PAIR = 0 off, 1 wherever possible, unset: the N = 256 tiles
   bool pair;
   {
     const char* e = getenv("AMOE_TC_PAIR");
     const int mode = e ? atoi(e) : -1;
-    pair = mode == 1 ? (p.block_n >= 64) : (mode == -1 ? (p.block_n == 256 && second == nullptr) : false);
+    // (dual stage-entry launches too, since the lean epilogue: layer3 entry 144 -> 138 us, layer4 entry 118 -> 110 us; N = 128
+    // pairs stay off - layer2 entry 222 -> 322 us, an N = 128 pair MMA step takes ~98 instead of 64 cycles)
+    pair = mode == 1 ? (p.block_n >= 64) : (mode == -1 ? (p.block_n == 256) : false);
     if (p.tiles_b < 2 || ctx->sm_count < 2) pair = false;
   }
   // resident weights (see Params): short-K launches with one N tile whose weight boxes fit beside >= 4 activation stages;
@@ -657,6 +685,12 @@ static int launch_generic(amoe_ctx* ctx, const void* x, const AView& av, const v
   if (pair) p.tiles_b = ceil_div(p.tiles_b, 2);     // pairs of image tiles
   p.G = G; p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.split_c = split_c; p.out_pad = out_pad;
   { const char* e = getenv("AMOE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  {
+    const char* e = getenv("AMOE_TC_W32");
+    const bool al32 = (reinterpret_cast<uintptr_t>(y) & 31) == 0 && (reinterpret_cast<uintptr_t>(residual) & 31) == 0 &&
+                      (second == nullptr || (reinterpret_cast<uintptr_t>(second->y) & 31) == 0);
+    p.wide32 = ((e == nullptr || atoi(e) != 0) && al32) ? 1 : 0;
+  }
   p.reverse = ctx->walk_reverse;
   p.num_taps = num_taps;
   p.k_chunks = k_chunks;
