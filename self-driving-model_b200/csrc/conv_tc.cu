@@ -139,17 +139,6 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
 // the fp32 / bf16 output and residual variants, scalar FFMA / FMNMX); short-K launches (stage entries, 1x1 convolutions, the
 // policy backbone) are bound by it.  Here a chunk is: 16 LDS.128 (scale / bias), 16 two-lane FMAs (fma.rn.f32x2, per-element
 // IEEE: the bits of fmaf), 16 packs, the ReLU on the packed pairs (max(bf16(x), 0) == bf16(max(x, 0))), 4 16-byte stores.
-// 32-byte global accesses (Blackwell: LDG/STG.256): one full sector per thread and instruction
-__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
-               "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-}
-__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-               : "l"(p));
-}
 // one 32-column chunk: acc -> scale/bias (+ residual) -> bf16 (-> ReLU) -> two 32-byte stores at dst (32-byte aligned:
 // channel offsets are multiples of 32, rows of Cout % 32 == 0 channels, tensors from 32-byte aligned allocations)
 template <bool RES>

@@ -393,8 +393,15 @@ __device__ __forceinline__ void store_rest_chunks(const Params& p, uint32_t tadd
       } else {
         bn_pack32<false>(a, s_scale + c * 32, s_bias + c * 32, q);
       }
+      // 32-byte stores: with 16-byte ones every instruction writes half sectors at a 64-byte stride (32-channel pixels)
+      __nv_bfloat16* d = p.dst[c] + pix * p.dst_c[c];
+      if ((reinterpret_cast<uintptr_t>(d) & 31) == 0) {
+        stg256(d, q[0], q[1]);
+        stg256(d + 16, q[2], q[3]);
+      } else {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(p.dst[c] + pix * p.dst_c[c] + v * 8) = q[v];
+        for (int v = 0; v < 4; ++v) *reinterpret_cast<uint4*>(d + v * 8) = q[v];
+      }
     }
   }
 }

@@ -157,6 +157,17 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
   return r;
 }
+// 32-byte global accesses (Blackwell: LDG/STG.256): one full sector per thread and instruction
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 // Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // begin while its predecessor in the stream is still running - its CTAs take over SMs as the predecessor's CTAs retire
 // and run their prologue (barrier init, TMEM allocation, descriptor prefetch, constant weight loads) - but must not touch
