@@ -75,6 +75,10 @@ struct Params {
   // (Measured and removed, round 2 session 3: only the FOUR plane-opening boxes of the next unit prefetched a unit ahead
   // (stride-2 resident-weight launches, 3-box ring): layer2 entry dual 224 -> 247 us, single 157 -> 199 us, policy conv3
   // 56 -> 68 us, layer3/4 entries unchanged.  Any cp.async.bulk.prefetch.tensor traffic slows these launches down.)
+  // (Measured and removed, same session: four accumulator buffers of 128 columns for N <= 128 tiles, so that the short 1x1 tile of
+  // a dual launch never waits for the 3x3 tile's epilogue - layer2 entry 207.0 -> 206.1 us, everything else unchanged: the
+  // stage entries are bound by the activation boxes coming through TMA from L2/HBM (~5.5 TB/s of A operand traffic, the same
+  // rate the layer3 convolutions see), not by accumulator hand-over.)
   int reverse;   // walk the whole tiles back to front (amoe_set_walk_reverse); tail-split units stay last
   int wide32;   // lean epilogue: 32-byte stores / residual loads (y and residual 32-byte aligned; AMOE_TC_W32=0 -> 16-byte)
   int dbg;   // AMOE_TC_DBG experiment bits (results wrong on purpose): 1 = the epilogue only drains the accumulator
