@@ -622,18 +622,25 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * sub);
-        // Row at the upper edge of the lane quarter: lane 31 publishes its D0 row for the next warp.  Nobody inside
-        // the warp needs lane 31's D0, so after the barrier that register takes the PREVIOUS warp's row and the
-        // one-row shift becomes a plain rotate (lane 0 receives D0[r-1] from lane 31).  MMA row 0 is halo.
+        // One-row shift of D0 (out[Q] = D0[Q-1] + D1[Q]): a warp rotate, plus the row at the lower edge of the lane quarter, which
+        // comes from lane 31 of the PREVIOUS lane quarter's warp through shared memory.  Lane 31 publishes its row, then every lane
+        // rotates - before the exchange barrier, so the 32 shuffles are off the path behind it - and lane 0 replaces what the
+        // rotate gave it (its own warp's lane 31) by the published row.  MMA row 0 is halo.
+        // (A clock64 trace of this epilogue showed ~580-1100 cycles for the arithmetic of one sub-tile: the shared-memory
+        // accesses were asm volatile with a memory clobber, which kept the four 8-channel groups strictly one after the other -
+        // LDS -> add/FMA -> pack -> STS chains of ~140 cycles each.  Now: all loads, then the arithmetic, then all stores; the
+        // shared-memory asm statements are volatile (ordered among themselves and against the barriers) without the clobber.)
         if (lane == 31) {
 #pragma unroll
           for (int v = 0; v < 8; ++v)
             *reinterpret_cast<uint4*>(&xch[xi][c][lg][v * 4]) = make_uint4(a0[v * 4], a0[v * 4 + 1], a0[v * 4 + 2], a0[v * 4 + 3]);
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a0[i] = __shfl_sync(0xffffffffu, a0[i], up);
         // the four lane-quarter warps of this channel half
         if (c == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (lane == 31) {
+        if (lane == 0) {
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const uint4 t4 = *reinterpret_cast<const uint4*>(&xch[xi][c][(lg + 3) & 3][v * 4]);
@@ -641,10 +648,17 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
         }
         xi ^= 1;
+        uint4 rr[4];
         if (has_res) {
           asm volatile("cp.async.wait_group 1;" ::: "memory");   // this sub-tile's residual landed (the next one may be in flight)
           __syncwarp();
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t slot = my_row_s + stg_sub + (((uint32_t)v ^ my_sw) & 3u) * 16u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[v].x), "=r"(rr[v].y), "=r"(rr[v].z), "=r"(rr[v].w) : "r"(slot));
+          }
         }
+        uint4 o[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           float h[8];
@@ -654,29 +668,22 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int jj = 0; jj < 8; jj += 2) {
             const int i = v * 8 + jj;
-            const uint32_t u0 = __shfl_sync(0xffffffffu, a0[i], up), u1 = __shfl_sync(0xffffffffu, a0[i + 1], up);
-            add_scale2(h[jj], h[jj + 1], u0, u1, a1[i], a1[i + 1], scv[jj], scv[jj + 1], bsv[jj], bsv[jj + 1]);
+            add_scale2(h[jj], h[jj + 1], a0[i], a0[i + 1], a1[i], a1[i + 1], scv[jj], scv[jj + 1], bsv[jj], bsv[jj + 1]);
           }
-          const uint32_t slot = my_row_s + stg_sub + (((uint32_t)v ^ my_sw) & 3u) * 16u;
           if (has_res) {
-            uint4 rr;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(slot) : "memory");
-            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {   // bf16 pair -> two fp32: low half << 16, high half masked
-              h[2 * jj] += __uint_as_float(rw[jj] << 16);
-              h[2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
-            }
+            add_bf16x2(h[0], h[1], rr[v].x);
+            add_bf16x2(h[2], h[3], rr[v].y);
+            add_bf16x2(h[4], h[5], rr[v].z);
+            add_bf16x2(h[6], h[7], rr[v].w);
           }
-          uint4 o = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-          if (p.relu) {   // max(bf16(x), 0) == bf16(max(x, 0))
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-            const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+          o[v] = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          if (p.relu) o[v] = make_uint4(relu_bf16x2(o[v].x), relu_bf16x2(o[v].y), relu_bf16x2(o[v].z), relu_bf16x2(o[v].w));   // max(bf16(x), 0) == bf16(max(x, 0))
+          if (!interior) o[v] = make_uint4(0u, 0u, 0u, 0u);   // border / halo positions stay zero
+        }
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) o2[jj] = __hmax2(o2[jj], z);
-          }
-          if (!interior) o = make_uint4(0u, 0u, 0u, 0u);   // border / halo positions stay zero
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(slot), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t slot = my_row_s + stg_sub + (((uint32_t)v ^ my_sw) & 3u) * 16u;
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(slot), "r"(o[v].x), "r"(o[v].y), "r"(o[v].z), "r"(o[v].w));
         }
         __syncwarp();
         // write-out: piece i of this thread = row 8i + lane/4 of the block, 16 bytes at byte 16*(lane%4) of its 64
@@ -684,14 +691,13 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           uint8_t* dst = y_base + (int64_t)q0 * (N * 2);
           const int rows = p.group_positions - q0 - rl;
           const uint32_t src = piece_s + stg_sub;
+          uint4 v4[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i >= i0_lo && 8 * i < rows) {
-              uint4 v4;
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "r"(src + i * 8 * HROWB) : "memory");
-              *reinterpret_cast<uint4*>(dst + i * 8 * (N * 2)) = v4;
-            }
-          }
+          for (int i = 0; i < 4; ++i)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v4[i].x), "=r"(v4[i].y), "=r"(v4[i].z), "=r"(v4[i].w) : "r"(src + i * 8 * HROWB));
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i >= i0_lo && 8 * i < rows) *reinterpret_cast<uint4*>(dst + i * 8 * (N * 2)) = v4[i];
         }
         __syncwarp();   // staging rows of this sub-tile are rewritten by the next tile's residual fetch
       }
@@ -716,7 +722,14 @@ conv3x3_flat_kw3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // epilogue is bound by instruction issue as a whole.  Making everything sub-tile-independent a per-thread constant
 // (this version, ~250 instructions) recovered two thirds of the gap.  What is left is inherent to the shift
 // (32 shuffles, the exchange and its barrier, eight warps' fixed overhead); the 171 us bound stays the target.
-// Round 2, session 3: sixteen epilogue warps of 16 channels each (88 registers, two pieces per thread, bit-identical to
+// Round 2, session 3: a clock64 trace of one epilogue warp (phases per 127-output sub-tile, cycles): index arithmetic ~150,
+// try_wait on a ready barrier ~155, TMEM load 30, exchange (lane-31 row, barrier, 32 shuffles) ~400, arithmetic ~400 when the
+// warp has its scheduler to itself and ~1000 when its partner warp is in the same phase, write-out ~170-250: ~1350-2300 per
+// sub-tile against 1152 cycles of MMAs.  Batching loads / arithmetic / stores (no memory clobbers between the 8-channel
+// groups) took it from 267 / 315 us to 260 / 304 us; the ~380 instructions per warp and sub-tile (many of them half-rate:
+// f32x2, F2FP, SHFL, LDS) are ~1400 scheduler cycles per sub-tile for the two warps of a scheduler - more than the MMAs
+// take, so even a perfect schedule stays epilogue-bound at ~210 us against 228 us of the default kernel.  Not pursued further.
+// Sixteen epilogue warps of 16 channels each (88 registers, two pieces per thread, bit-identical to
 // the eight-warp version): 272 / 320 us against 271 / 313 us - the epilogue is not bound by latency hiding either.
 // tcgen05.shift.down (tools/probe_shift.cu: moves 8 columns of ALL 128 lanes by one lane towards lane 0 inside each
 // 32-lane block, lane 31 of a block keeps its value; ~70 cycles per instruction) cannot replace the shuffles: 8 shifts
