@@ -256,6 +256,30 @@ def test_dual_stage_entry_launch_is_bit_identical(model_sd, monkeypatch):
         assert torch.equal(outs["0"]["expert_outputs"][0]["class_logits"], outs["1"]["expert_outputs"][0]["class_logits"])
 
 
+def test_policy_backbone_on_second_stream_is_bit_identical(model_sd, monkeypatch):
+    """The policy backbone forked onto its own stream behind the experts' last tensor-bound launch (AMOE_TAIL_OVERLAP, default
+    on) runs the same kernels on the same data as the single-stream order: identical bits, eager and through a CUDA graph."""
+    m, sd = model_sd
+    for B, H in ((16, 256), (3, 96)):
+        batch = _to(synth.synth_batch(B, H, H, seed=23), DEV)
+        outs = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("AMOE_TAIL_OVERLAP", flag)
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                outs[flag] = m(batch)
+            torch.cuda.synchronize()
+        for k in SMALL:
+            assert torch.equal(outs["0"][k], outs["1"][k]), (B, H, k)
+        for i in (1, 2):
+            assert torch.equal(outs["0"]["expert_outputs"][i], outs["1"]["expert_outputs"][i]), (B, H, i)
+    monkeypatch.setenv("AMOE_TAIL_OVERLAP", "1")
+    g = m.capture(batch)
+    out = g(batch)
+    torch.cuda.synchronize()
+    for k in SMALL:
+        assert torch.equal(out[k], outs["0"][k]), k
+
+
 def test_cuda_graph_capture_replays_the_eager_forward(model_sd):
     """AutoMoE.capture(): replaying the captured graph on new inputs gives bit-identical outputs to the eager
     call (same kernels, same order; side-stream logit writers joined inside the graph)."""

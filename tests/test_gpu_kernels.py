@@ -179,6 +179,39 @@ def test_conv_tc_walk_direction_and_schedules(case, monkeypatch):
 
 
 @pytest.mark.timeout(180)
+@pytest.mark.parametrize("case", [
+    # G, B, H, W, Cin, Cout, k, s, residual
+    (3, 6, 8, 8, 512, 512, 3, 1, True),       # layer4 block conv2: N = 256 tiles, CTA pairs, bf16 residual
+    (2, 9, 32, 32, 64, 128, 3, 2, False),     # stage entry geometry: resident weights, N = 128
+    (1, 7, 16, 16, 128, 64, 1, 1, True),      # 1x1, N = 64 (one 64-column pass of the chunk loop)
+    (2, 2, 4, 4, 256, 192, 3, 1, False),      # N = 192: an odd number of 32-column chunks
+])
+def test_conv_tc_lean_epilogue_is_bit_identical(case, monkeypatch):
+    """The bf16 inference epilogue of csrc/conv_tc.cu (two-lane FMAs, ReLU on packed pairs, 32-byte stores and residual
+    loads) writes the bits of the generic epilogue (scalar FFMA / FMNMX, 16-byte accesses)."""
+    from automoe_b200 import _ops
+    G, B, H, W, Cin, Cout, k, s, residual = case
+    g = torch.Generator().manual_seed(33)
+    convs, bns = _mk_conv_bn(Cin, Cout, k, s, k // 2, g, n=G)
+    x = torch.randn((G * B, H, W, Cin), generator=g).to(DEV).bfloat16()
+    Ho, Wo = H // s, W // s
+    res = torch.randn((G * B, Ho, Wo, Cout), generator=g).to(DEV).bfloat16() if residual else None
+    pc = _ops.pack_conv(convs, bns, torch.bfloat16, torch.device(DEV), relu=True)
+    monkeypatch.setenv("AMOE_TC_LEAN", "0")
+    _ops.walk_reset(DEV, 0)
+    ref = _ops.conv2d(pc, x, B, H, W, residual=res)
+    for lean, w32 in (("1", "0"), ("1", "1")):
+        monkeypatch.setenv("AMOE_TC_LEAN", lean)
+        monkeypatch.setenv("AMOE_TC_W32", w32)
+        _ops.walk_reset(DEV, 0)
+        y = _ops.conv2d(pc, x, B, H, W, residual=res)
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref), (lean, w32, (y.float() - ref.float()).abs().max().item())
+    assert (ref.float() < 0).sum() == 0        # ReLU on the packed pairs never leaves a negative (or -0 -> sign bit) value
+    assert (ref.view(torch.int16) < 0).sum() == 0
+
+
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("case", [("stem", 3, 2, 64, 64), ("stem", 3, 3, 256, 256), ("stem", 1, 2, 224, 224),
                                   ("policy", 1, 2, 64, 64), ("policy", 1, 3, 256, 256)])
 def test_conv_tc_rowwin(case):
