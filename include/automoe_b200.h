@@ -97,6 +97,16 @@ int amoe_resample_u8_fwd(amoe_ctx*, const void* src_u8, void* dst_u8, const int*
 int amoe_stem_fwd(amoe_ctx*, const void* x_pad, const void* w_img, const float* scale,
                   const float* bias, int B, int H, int W, int Wpad, int KH, int n_total, int relu,
                   void* const* dst_host, const int* dst_c_host, void* stream);
+/* fp32-accurate variant for the training forward (the reference trains in fp32: resnet.py:197 conv1 and
+ * models/policy/trajectory_head.py:10 inside training/train_gating_network.py:96): split bf16 operands (three parts each, six
+ * product terms, fp32 accumulation).  x3_pad: the three parts of the padded frame stacked on the batch axis
+ * [3][B][H+6][Wpad][4] bf16 (4th channel zero); w3_img: three filter images [3][KH*4][n_total][8] bf16 in the layout of
+ * amoe_stem_fwd; y: [B][H/2][W/2][n_total] fp32 = conv * scale + bias (+ ReLU).  Wpad = (W + 13) & ~7. */
+int amoe_stem_fwd_f32tc_supported(int H, int W, int KH, int n_total);
+/* [B][H][W][4] fp32 NHWC frame (amoe_image_nchw_to_nhwc, Cp = 4) -> x3_pad of amoe_stem_fwd_f32tc (borders written as zeros) */
+int amoe_stem_split_frame(amoe_ctx*, const float* x_nhwc4, void* x3_pad, int B, int H, int W, int Wpad, void* stream);
+int amoe_stem_fwd_f32tc(amoe_ctx*, const void* x3_pad, const void* w3_img, const float* scale, const float* bias,
+                        float* y, int B, int H, int W, int Wpad, int KH, int n_total, int relu, void* stream);
 /* Same GEMM with nn.MaxPool2d(3, stride 2, pad 1) fused behind the first n_pool_ch channels (the
  * expert stems: resnet conv1+bn1+relu+maxpool in one kernel, the full-resolution stem output never
  * reaches HBM).  pooled: [n_pool_ch/64 * B][H/4+2*out_pad][W/4+2*out_pad][64] bf16; with

@@ -41,6 +41,9 @@ SIGNATURES = {
     "amoe_resample_u8_fwd": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P]),
     "amoe_stem_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, C.POINTER(_P), C.POINTER(_I), _P]),
     "amoe_stem_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_P), C.POINTER(_I), _P]),
+    "amoe_stem_fwd_f32tc_supported": (_I, [_I] * 4),
+    "amoe_stem_split_frame": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "amoe_stem_fwd_f32tc": (_I, [_P] * 6 + [_I] * 7 + [_P]),
     "amoe_conv2d_rowwin_fwd": (_I, [_P] * 6 + [_I] * 13 + [_P]),
     "amoe_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "amoe_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),

@@ -211,6 +211,172 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) stem_tc_kernel(const __grid_co
 
 
 // ------------------------------------------------------------------------------------------------
+// fp32-accurate variant for the training forward (the reference trains in fp32): the same Toeplitz GEMM with every operand
+// split into three bf16 parts (v = v1 + v2 + v3, tc_common.cuh split3) and the six leading product terms accumulated in the
+// fp32 TMEM accumulator, smallest terms first - the scheme of the split-operand convolutions in conv_tc.cu.  The frame parts
+// are three padded bf16 frames stacked on the batch axis, the filter parts three [K/8][N][8] images; a tile (one output row)
+// stages 3 x KH image rows and runs 6 x KH x 2 MMAs.  fp32 output [B][Ho][Wo][N], scale/bias applied in fp32.
+constexpr int F32_TERMS = 6;
+__device__ __constant__ int kStemXPart[F32_TERMS] = {0, 0, 1, 0, 1, 2};
+__device__ __constant__ int kStemWPart[F32_TERMS] = {0, 1, 0, 2, 1, 0};
+
+struct F32Params {
+  Params base;             // dst[] unused
+  int stages;              // activation stages (each holds the three parts)
+  int64_t part_bytes;      // distance between the frame parts: B * Hpad * row_bytes
+  float* y;                // [B][Ho][Wo][n_total] fp32
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) stem_tc_f32_kernel(const __grid_constant__ F32Params fp) {
+  const Params& p = fp.base;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 5];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_scale[256];
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t w_part = (uint32_t)((p.w_bytes + 127) & ~127);
+  const uint32_t smem_w = smem_base;
+  const uint32_t smem_a = smem_base + 3u * w_part;
+  const uint32_t stage_bytes = 3u * (uint32_t)p.a_stage_bytes;
+  const uint32_t bar_afull = smem_u32(&bars[0]);
+  const uint32_t bar_aempty = smem_u32(&bars[A_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * A_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * A_STAGES + 2]);
+  const uint32_t bar_w = smem_u32(&bars[2 * A_STAGES + 4]);
+
+  for (int i = threadIdx.x; i < p.n_total; i += NUM_THREADS) {
+    s_scale[i] = __ldg(p.scale + i);
+    s_bias[i] = __ldg(p.bias + i);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_holder), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const uint32_t tile_bytes = (uint32_t)(p.KH * p.row_bytes);
+
+  if (warp == 0) {
+    // ============================ producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 3u * (uint32_t)p.w_bytes);
+      for (int part = 0; part < 3; ++part)
+        for (int o = 0; o < p.w_bytes; o += 32768)
+          bulk_g2s(smem_w + (uint32_t)part * w_part + (uint32_t)o, p.w + (size_t)part * p.w_bytes + o,
+                   (uint32_t)std::min(32768, p.w_bytes - o), bar_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int b = t / p.Ho, oh = t - b * p.Ho;
+        mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
+        mbar_arrive_expect_tx(bar_afull + 8 * stage, 3u * tile_bytes);
+        for (int part = 0; part < 3; ++part)
+          bulk_g2s(smem_a + (uint32_t)stage * stage_bytes + (uint32_t)part * p.a_stage_bytes,
+                   p.x + (int64_t)part * fp.part_bytes + ((int64_t)b * p.Hpad + 2 * oh) * p.row_bytes, tile_bytes, bar_afull + 8 * stage);
+        if (++stage == fp.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==========================
+    const uint32_t idesc = make_idesc(p.n_total);
+    const uint32_t lbo_b = (uint32_t)p.n_total * 16u;
+    mbar_wait(bar_w, 0);
+    tcgen05_fence_after();
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * acc, tphase ^ 1u);
+      mbar_wait(bar_afull + 8 * stage, phase);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+      const uint32_t a_stage = smem_a + (uint32_t)stage * stage_bytes;
+      // the tensor core truncates when it adds into the accumulator: the 2^-16 and 2^-8 terms go in while the sum is small
+      for (int term = F32_TERMS - 1; term >= 0; --term) {
+        const uint32_t a_base = a_stage + (uint32_t)kStemXPart[term] * (uint32_t)p.a_stage_bytes;
+        const uint32_t w_base = smem_w + (uint32_t)kStemWPart[term] * w_part;
+        for (int kh = 0; kh < p.KH; ++kh) {
+#pragma unroll
+          for (int ks = 0; ks < WIN_K / UMMA_K; ++ks) {
+            const uint64_t a_desc = make_nosw_desc(a_base + (uint32_t)(kh * p.row_bytes + ks * 32), 16u, 128u);
+            const uint64_t b_desc = make_nosw_desc(w_base + (uint32_t)(kh * 4 + ks * 2) * lbo_b, lbo_b, 128u);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)((term != F32_TERMS - 1) | kh | ks));
+          }
+        }
+      }
+      umma_commit(bar_aempty + 8 * stage);
+      umma_commit(bar_tfull + 8 * acc);
+      if (++stage == fp.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int lg = warp & 3;
+    const int ow = lg * 32 + lane;
+    const bool valid = ow < p.Wo;
+    const int n_chunks = p.n_total >> 5;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const int64_t pix = (int64_t)t * p.Wo + ow;  // (b*Ho + oh)*Wo + ow
+      mbar_wait(bar_tfull + 8 * acc, tphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), a);
+        tmem_ld_wait();
+        if (valid) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+          const float4* bs4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+          float* o = fp.y + pix * p.n_total + c * 32;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 s0 = sc4[2 * v], s1 = sc4[2 * v + 1], b0 = bs4[2 * v], b1 = bs4[2 * v + 1];
+            float f[8];
+            ffma2(f[0], f[1], a[v * 8 + 0], a[v * 8 + 1], s0.x, s0.y, b0.x, b0.y);
+            ffma2(f[2], f[3], a[v * 8 + 2], a[v * 8 + 3], s0.z, s0.w, b0.z, b0.w);
+            ffma2(f[4], f[5], a[v * 8 + 4], a[v * 8 + 5], s1.x, s1.y, b1.x, b1.y);
+            ffma2(f[6], f[7], a[v * 8 + 6], a[v * 8 + 7], s1.z, s1.w, b1.z, b1.w);
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            stg256(o + v * 8, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])),
+                   make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Variant with the ResNet max-pool (3x3, stride 2, pad 1) fused behind the stem: the first
 // n_pool_ch channels (expert stems) never reach HBM at full resolution.  A CTA owns a contiguous
 // range of POOLED rows and walks the conv rows they need in order (2py-1 once as "carry", then
@@ -683,6 +849,7 @@ int amoe_stem_init(amoe_ctx* ctx) {
   AMOE_ENTER(ctx);
   (void)ctx;
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_tc_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<false, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   AMOE_CHECK_CUDA(cudaFuncSetAttribute(stem::stem_pool_kernel<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -746,6 +913,81 @@ extern "C" int amoe_stem_fwd(amoe_ctx* ctx, const void* x_pad, const void* w_img
   AMOE_REQUIRE(smem <= 220 * 1024, "amoe_stem_fwd: shared memory budget exceeded (%zu bytes)", smem);
   const int grid = std::min(p.total_tiles, ctx->sm_count);
   stem_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// [B][H][W][4] fp32 NHWC (4th channel zero) -> the padded frame of the stem kernels, [3][B][H+6][Wpad][4] bf16: 3 zero rows above
+// and below, 4 zero pixels left, zeros right, as the three bf16 parts of every value.  One thread per padded pixel.
+__global__ void __launch_bounds__(256) stem_split_frame_kernel(const float4* __restrict__ x, uint2* __restrict__ out, int B, int H, int W,
+                                                               int Wpad, int64_t total) {
+  const int Hpad = H + 6;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % Wpad);
+    const int64_t r = i / Wpad;
+    const int yp = (int)(r % Hpad);
+    const int b = (int)(r / Hpad);
+    const int xx = xp - 4, yy = yp - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xx >= 0 && xx < W && yy >= 0 && yy < H) v = __ldg(x + ((int64_t)b * H + yy) * W + xx);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 p0[4], p1[4], p2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tc::split3(f[c], p0[c], p1[c], p2[c]);
+    out[i] = *reinterpret_cast<const uint2*>(p0);
+    out[i + total] = *reinterpret_cast<const uint2*>(p1);
+    out[i + 2 * total] = *reinterpret_cast<const uint2*>(p2);
+  }
+}
+
+extern "C" int amoe_stem_split_frame(amoe_ctx* ctx, const float* x_nhwc4, void* out3, int B, int H, int W, int Wpad, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x_nhwc4 && out3, "amoe_stem_split_frame: NULL argument");
+  AMOE_REQUIRE(B >= 0 && H > 0 && W > 0 && Wpad >= W + 6, "amoe_stem_split_frame: bad shape");
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(x_nhwc4) & 15) == 0 && (reinterpret_cast<uintptr_t>(out3) & 7) == 0,
+               "amoe_stem_split_frame: pointers must be 16-byte (input) / 8-byte (output) aligned");
+  const int64_t total = (int64_t)B * (H + 6) * Wpad;
+  if (total == 0) return 0;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+  stem_split_frame_kernel<<<(unsigned)std::min(want, cap), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x_nhwc4), reinterpret_cast<uint2*>(out3), B, H, W, Wpad, total);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int amoe_stem_fwd_f32tc_supported(int H, int W, int KH, int n_total) {
+  if (H <= 0 || W <= 0 || (H & 1) || (W & 1) || W / 2 > 128 || KH < 1 || KH > 7) return 0;
+  if (n_total % 32 != 0 || n_total < 32 || n_total > 256) return 0;
+  const int Wpad = (W + 6 + 7) & ~7;
+  const size_t a_stage = (size_t)((KH * Wpad * 8 + 16 * 128 + 64 + 127) & ~127);
+  const size_t w_part = (size_t)((KH * 4 * n_total * 16 + 127) & ~127);
+  return (3 * w_part + 2 * 3 * a_stage + 256 <= 224u * 1024u) ? 1 : 0;   // weights + two activation stages
+}
+
+extern "C" int amoe_stem_fwd_f32tc(amoe_ctx* ctx, const void* x3_pad, const void* w3_img, const float* scale, const float* bias,
+                                   float* y, int B, int H, int W, int Wpad, int KH, int n_total, int relu, void* stream) {
+  AMOE_ENTER(ctx);
+  using namespace stem;
+  AMOE_REQUIRE(ctx && x3_pad && w3_img && scale && bias && y, "amoe_stem_fwd_f32tc: NULL argument");
+  AMOE_REQUIRE(amoe_stem_fwd_f32tc_supported(H, W, KH, n_total), "amoe_stem_fwd_f32tc: unsupported shape H=%d W=%d KH=%d N=%d", H, W, KH, n_total);
+  AMOE_REQUIRE(Wpad == ((W + 6 + 7) & ~7), "amoe_stem_fwd_f32tc: Wpad=%d, expected %d", Wpad, (W + 6 + 7) & ~7);
+  AMOE_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, "amoe_stem_fwd_f32tc: y must be 32-byte aligned");
+  F32Params fp;
+  void* dummy_dst[MAX_CHUNKS];
+  int dummy_c[MAX_CHUNKS];
+  for (int c = 0; c < MAX_CHUNKS; ++c) { dummy_dst[c] = y; dummy_c[c] = 8; }
+  int rc = stem_fill(fp.base, x3_pad, w3_img, scale, bias, B, H, W, Wpad, KH, n_total, relu, dummy_dst, dummy_c, 0);
+  if (rc) return rc;
+  if (fp.base.total_tiles == 0) return 0;
+  fp.y = y;
+  fp.part_bytes = (int64_t)B * fp.base.Hpad * fp.base.row_bytes;
+  const size_t w_part = ((size_t)fp.base.w_bytes + 127) / 128 * 128;
+  const size_t stage = 3 * (size_t)fp.base.a_stage_bytes;
+  fp.stages = (int)std::min<size_t>(A_STAGES, (224 * 1024 - 256 - 3 * w_part) / stage);
+  AMOE_REQUIRE(fp.stages >= 2, "amoe_stem_fwd_f32tc: shared memory budget exceeded");
+  const size_t smem = 3 * w_part + (size_t)fp.stages * stage + 256;
+  const int grid = std::min(fp.base.total_tiles, ctx->sm_count);
+  stem_tc_f32_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(fp);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

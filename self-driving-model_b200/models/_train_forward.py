@@ -72,7 +72,7 @@ def policy_forward(pol, image: torch.Tensor, context: Optional[torch.Tensor]) ->
     """EasyBackbone (4 x conv s2 + BatchNorm + ReLU, GAP, fc) + both TrajectoryPolicy heads."""
     if not image.is_cuda:
         raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
-    x = _ops.image_to_nhwc(image, 4, torch.float32)                   # [B,H,W,4], zero 4th channel
+    x = TF.image_nhwc4(image)                                         # [B,H,W,4], zero 4th channel
     net = pol.backbone.net
     for ci, bi in ((0, 1), (3, 4), (6, 7), (9, 10)):
         x = TF.conv_bn_relu(x, net[ci], net[bi], batch_stats=net[bi].training)

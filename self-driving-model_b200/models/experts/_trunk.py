@@ -158,7 +158,7 @@ def run_trunk_train(expert, image: torch.Tensor, with_head: bool = True) -> torc
     if not image.is_cuda:
         raise RuntimeError("automoe_b200 has no CPU path: move the model and the batch to a CUDA (sm_100a) device")
     bb = expert.backbone
-    x = _ops.image_to_nhwc(image, 4, torch.float32)
+    x = TF.image_nhwc4(image)
     y = TF.conv_bn_act(x, bb[0], bb[1], relu=True)
     y = TF.max_pool3x3s2(y)
     for li in range(4, 8):

@@ -197,6 +197,85 @@ def _split3(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ---- Cin = 3 first layers (ResNet stem 7x7/s2/p3, EasyBackbone conv1 5x5/s2/p2): fp32-accurate Toeplitz GEMM (csrc/stem_tc.cu) ----
+def _split3_parts(t: torch.Tensor):
+    """fp32 -> (t1, t2, t3) bf16 with t == t1 + t2 + t3 to 24 bits: each part the bf16 rounding of what is left (the differences
+    are exact).  Operand preparation of the first layer: one padded frame per step, one filter image per weight version."""
+    t1 = t.to(torch.bfloat16)
+    r1 = t - t1.float()
+    t2 = r1.to(torch.bfloat16)
+    t3 = (r1 - t2.float()).to(torch.bfloat16)
+    return t1, t2, t3
+
+
+def image_nhwc4(image: torch.Tensor) -> torch.Tensor:
+    """[B,3,H,W] NCHW -> [B,H,W,4] fp32 NHWC (zero 4th channel), cached on the image tensor object: the frozen experts and the
+    policy backbone of one training step stage (and split, see _stem_split_frame) the same frame once."""
+    from .. import _ops
+    key = (image._version, image.data_ptr(), tuple(image.shape))
+    cache = getattr(image, "_amoe_nhwc4", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    out = _ops.image_to_nhwc(image, 4, torch.float32)
+    try:
+        image._amoe_nhwc4 = (key, out)
+    except Exception:
+        pass
+    return out
+
+
+def _stem_tc_ok(Cx: int, Cin: int, Cout: int, KH: int, KW: int, stride: int, padding: int, H: int, W: int) -> bool:
+    from .. import _ops
+    if not train_tc() or Cx != 4 or Cin > 3 or stride != 2:
+        return False
+    if _ops.STEM_TOP - padding < 0 or _ops.STEM_LEFT - padding < 0 or KH - padding + _ops.STEM_TOP > _ops.STEM_KH or \
+            KW - padding + _ops.STEM_LEFT > 8:
+        return False
+    return bool(lib().amoe_stem_fwd_f32tc_supported(H, W, _ops.STEM_KH, Cout))
+
+
+def _stem_split_weight(weight: torch.Tensor, padding: int) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,Cin<=3,KH,KW] -> three filter images [3][STEM_KH*4][Cout][8] bf16 (layout of _ops.pack_stem: K index
+    kh*32 + j*4 + c = padded row 2*oh+kh, padded pixel 2*ow+j, channel c).  Cached on the tensor until its version changes."""
+    from .. import _ops
+    key = (weight._version, weight.data_ptr(), padding)
+    cache = getattr(weight, "_amoe_stem3", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    Cout, Cin, KH, KW = weight.shape
+    w = _f32c(weight.detach())
+    wk = w.new_zeros((Cout, _ops.STEM_KH, 8, 4))                                  # [n][kh][j][c]
+    r0, j0 = _ops.STEM_TOP - padding, _ops.STEM_LEFT - padding
+    wk[:, r0:r0 + KH, j0:j0 + KW, :Cin] = w.permute(0, 2, 3, 1)
+    img = wk.reshape(Cout, _ops.STEM_KH * 4, 8).permute(1, 0, 2).contiguous()    # [k/8][n][8]
+    out = torch.stack(_split3_parts(img), dim=0).contiguous()
+    try:
+        weight._amoe_stem3 = (key, out)
+    except Exception:
+        pass
+    return out
+
+
+def _stem_split_frame(x2: torch.Tensor) -> torch.Tensor:
+    """[B,H,W,4] fp32 NHWC (4th channel zero) -> [3B,H+6,Wpad,4] bf16: the padded frame of the stem kernels (3 zero rows above and
+    below, 4 zero pixels left) as its three bf16 parts stacked on the batch axis.  Cached on the tensor object: the three
+    expert stems and the policy conv1 of one step read the same frame."""
+    from .. import _ops
+    key = (x2._version, x2.data_ptr())
+    cache = getattr(x2, "_amoe_stem_frame3", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    B, H, W, Cx = x2.shape
+    out = torch.empty((3 * B, H + 6, _ops.stem_wpad(W), Cx), device=x2.device, dtype=torch.bfloat16)
+    check(lib().amoe_stem_split_frame(ctx(x2.device), ptr(x2), ptr(out), B, H, W, out.shape[2], stream_ptr(x2.device)),
+          "stem_split_frame")
+    try:
+        x2._amoe_stem_frame3 = (key, out)
+    except Exception:
+        pass
+    return out
+
+
 class _ConvBNAct(torch.autograd.Function):
     """nn.Conv2d(stride, padding, bias?) [-> nn.BatchNorm2d] [-> nn.ReLU] on NHWC fp32 activations.
 
@@ -217,8 +296,16 @@ class _ConvBNAct(torch.autograd.Function):
         conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
         fuse_relu = int(relu and bn_mode == BN_NONE)
         use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride))
-        wp = None if use_tc else _pack_w(weight, Cx)       # CUDA-core layout; packed lazily in backward on the tensor-core path
-        if use_tc:
+        # (first layers whose weight is trained stay on the CUDA-core kernel: the gradient goldens of the policy backbone are
+        # held to 5e-4 and move by 8e-4 with the - more accurate - tensor-core forward: ReLU units within rounding of zero)
+        use_stem = (not use_tc) and (not ctx_.needs_input_grad[1]) and _stem_tc_ok(Cx, Cin, Cout, KH, KW, stride, padding, H, W)
+        wp = None if (use_tc or use_stem) else _pack_w(weight, Cx)   # CUDA-core layout; packed lazily in backward on the tensor-core paths
+        if use_stem:
+            from .. import _ops
+            xs, wsplit = _stem_split_frame(x2), _stem_split_weight(weight, padding)
+            check(lib().amoe_stem_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv), B, H, W, xs.shape[2],
+                                            _ops.STEM_KH, Cout, fuse_relu, st), "stem_fwd_f32tc")
+        elif use_tc:
             xs, wsplit = _split3(x2), _split_weight(weight, False)     # named: they must outlive the launch that reads them
             check(lib().amoe_conv2d_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv),
                                               B, H, W, Cin, Cout, KH, KW, stride, padding, Ho, Wo, fuse_relu, st), "conv2d_fwd_f32tc")

@@ -386,6 +386,49 @@ def test_train_step_reduces_loss_and_refreshes_inference_packs():
     assert diff_path.requires_grad and rel_err(after, diff_path.detach()) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W,Cout,K,pad,bias", [(3, 64, 64, 64, 7, 3, False), (2, 256, 256, 64, 7, 3, False), (5, 96, 160, 32, 5, 2, True),
+                                                  (2, 90, 122, 64, 7, 3, False), (2, 64, 320, 64, 7, 3, False)])
+def test_first_layer_tensor_core_conv_is_fp32_accurate(B, H, W, Cout, K, pad, bias, monkeypatch):
+    """Cin = 3 first layers (ResNet stem 7x7/s2/p3, EasyBackbone conv1 5x5/s2/p2) of the training forward: the Toeplitz GEMM of
+    csrc/stem_tc.cu with split operands (amoe_stem_fwd_f32tc) against fp64 and against the CUDA-core kernel; frames it does not
+    take (W/2 > 128) fall back to the CUDA cores; the weight gradient (CUDA cores in both modes) is unchanged."""
+    import torch.nn.functional as F
+    from automoe_b200.training import functional as TF
+    torch.backends.cudnn.allow_tf32 = False
+    g = _gen(300 + H + K)
+    conv = nn.Conv2d(3, Cout, K, 2, pad, bias=bias).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (3 * K * K)) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+    img = torch.randn((B, 3, H, W), generator=g).to(DEV)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AMOE_TRAIN_TC", flag)
+        conv.requires_grad_(False)                       # frozen first layer (the experts' stems): tensor-core forward
+        y_frozen = TF.conv_bn_act(TF.image_nhwc4(img), conv, None, relu=False)
+        conv.requires_grad_(True)                        # trained first layer (policy conv1): CUDA-core forward and weight gradient
+        conv.weight.grad = None
+        y = TF.conv_bn_act(TF.image_nhwc4(img), conv, None, relu=False)
+        gy = torch.randn(y.shape, generator=_gen(9)).to(DEV)
+        y.backward(gy)
+        res[flag] = (y_frozen.detach(), conv.weight.grad.detach().clone(), y.detach())
+    monkeypatch.setenv("AMOE_TRAIN_TC", "1")
+    assert TF._stem_tc_ok(4, 3, Cout, K, K, 2, pad, H, W) == (W // 2 <= 128)
+    assert torch.equal(res["1"][2], res["0"][2]) and torch.equal(res["0"][0], res["0"][2])
+    if W // 2 <= 128:
+        assert not torch.equal(res["1"][0], res["0"][0])      # the tensor-core path was taken
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    y64 = F.conv2d(img.double(), w64, conv.bias.detach().double() if bias else None, 2, pad)
+    y64.backward(gy.double().permute(0, 3, 1, 2))
+    y32 = F.conv2d(img, conv.weight.detach(), conv.bias.detach() if bias else None, 2, pad)
+    ref = y64.detach().permute(0, 2, 3, 1)
+    e, e0, e32 = rel_err(res["1"][0], ref), rel_err(res["0"][0], ref), rel_err(y32.permute(0, 2, 3, 1), ref)
+    print("first layer on the tensor cores vs fp64:", e, " CUDA cores:", e0, " torch fp32:", e32)
+    assert e < 1e-5 and e0 < 1e-5, (e, e0, e32)
+    assert rel_err(res["1"][1], w64.grad) < 1e-5 and torch.equal(res["1"][1], res["0"][1])
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,K,stride,pad", [
     (2, 16, 16, 64, 64, 3, 1, 1), (3, 14, 18, 64, 128, 3, 2, 1), (2, 16, 12, 128, 128, 1, 2, 0), (1, 8, 8, 256, 512, 3, 1, 1),
     (2, 8, 8, 512, 256, 3, 1, 1), (2, 23, 40, 128, 32, 3, 1, 1), (2, 10, 10, 64, 64, 1, 1, 0)])
