@@ -56,6 +56,20 @@ __global__ __launch_bounds__(256) void conv2d_simt_kernel(ConvSimtParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // k -> (kh, kw, channel) once per CTA instead of two integer divisions per gathered element (small-Cin first layers:
+  // the index arithmetic of the gather was as long as the FMAs of its tile); longer K falls back to the divisions
+  constexpr int KTAB = 1024;
+  __shared__ int s_kinfo[KTAB];
+  const bool use_tab = Ktot <= KTAB;
+  if (use_tab) {
+    for (int kk = tid; kk < Ktot; kk += 256) {
+      const int tap = kk / p.Cin, c = kk - tap * p.Cin;
+      const int kh = tap / p.KW, kw = tap - kh * p.KW;
+      s_kinfo[kk] = (kh << 20) | (kw << 12) | c;
+    }
+    __syncthreads();
+  }
+
   for (int kk0 = 0; kk0 < Ktot; kk0 += SBK) {
     float a[4], b[4];
 #pragma unroll
@@ -63,10 +77,16 @@ __global__ __launch_bounds__(256) void conv2d_simt_kernel(ConvSimtParams p) {
       int kk = kk0 + lk + j;
       float av = 0.f, bv = 0.f;
       if (kk < Ktot) {
-        int tap = kk / p.Cin;
-        int c = kk - tap * p.Cin;
-        int kh = tap / p.KW;
-        int kw = tap - kh * p.KW;
+        int c, kh, kw;
+        if (use_tab) {
+          const int info = s_kinfo[kk];
+          kh = info >> 20; kw = (info >> 12) & 255; c = info & 4095;
+        } else {
+          const int tap = kk / p.Cin;
+          c = kk - tap * p.Cin;
+          kh = tap / p.KW;
+          kw = tap - kh * p.KW;
+        }
         int ih = ih0 + kh, iw = iw0 + kw;
         if (m_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
           av = ld_as_float<T>(x + (((int64_t)n_img * p.H + ih) * p.W + iw) * p.Cin + c);

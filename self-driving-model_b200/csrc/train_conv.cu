@@ -216,17 +216,32 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // k -> (kh, kw, co) once per CTA (two integer divisions per gathered element otherwise), strides 1 / 2 as shifts
+  constexpr int KTAB = 4608;              // 3x3 x 512 channels
+  __shared__ int s_kinfo[KTAB];
+  const bool use_tab = Ktot <= KTAB && p.Cout <= 4096;
+  if (use_tab) {
+    for (int k = tid; k < Ktot; k += 256) {
+      const int tap = k / p.Cout, co = k - tap * p.Cout;
+      const int kh = tap / p.KW, kw = tap - kh * p.KW;
+      s_kinfo[k] = (kh << 20) | (kw << 12) | co;
+    }
+    __syncthreads();
+  }
+  const bool pow2 = (p.sh == 1 || p.sh == 2) && (p.sw == 1 || p.sw == 2);
+  const int shh = p.sh - 1, sww = p.sw - 1;   // shift amounts / parity masks when pow2
   for (int k0 = 0; k0 < Ktot; k0 += TBK) {
     // A: this thread's pixel, 4 consecutive k (one 16-byte load when Cout % 4 == 0: same tap, aligned)
     if ((p.Cout & 3) == 0) {
       const int k = k0 + lk;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m_ok && k < Ktot) {
-        const int tap = k / p.Cout, co = k - tap * p.Cout;
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        int co, kh, kw;
+        if (use_tab) { const int info = s_kinfo[k]; kh = info >> 20; kw = (info >> 12) & 255; co = info & 4095; }
+        else { const int tap = k / p.Cout; co = k - tap * p.Cout; kh = tap / p.KW; kw = tap - kh * p.KW; }
         const int th = ih + p.ph - kh, tw = iw + p.pw - kw;
-        if (th >= 0 && tw >= 0 && th % p.sh == 0 && tw % p.sw == 0) {
-          const int oh = th / p.sh, ow = tw / p.sw;
+        if (th >= 0 && tw >= 0 && (pow2 ? ((th & shh) | (tw & sww)) == 0 : (th % p.sh == 0 && tw % p.sw == 0))) {
+          const int oh = pow2 ? th >> shh : th / p.sh, ow = pow2 ? tw >> sww : tw / p.sw;
           if (oh < p.Ho && ow < p.Wo)
             a = *reinterpret_cast<const float4*>(p.dy + (((int64_t)n_img * p.Ho + oh) * p.Wo + ow) * p.Cout + co);
         }
@@ -255,7 +270,9 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
       const int k = k0 + kk, ci = n0 + c;
       float v = 0.f;
       if (k < Ktot && ci < p.Cin) {
-        const int tap = k / p.Cout, co = k - tap * p.Cout;
+        int tap, co;
+        if (use_tab) { const int info = s_kinfo[k]; co = info & 4095; tap = (info >> 20) * p.KW + ((info >> 12) & 255); }
+        else { tap = k / p.Cout; co = k - tap * p.Cout; }
         v = p.w[(int64_t)co * Kw + tap * p.Cin + ci];
       }
       Bs[kk][c] = v;
@@ -301,28 +318,46 @@ __global__ __launch_bounds__(256) void conv_bwd_weight_kernel(ConvBwdParams p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // The gather of the x window used four integer divisions per loaded element (pixel -> image/row/column, k -> tap/channel);
+  // a thread always loads the same k column (c = tid % TBN), so its tap decomposition is hoisted, and the 16 pixels of an
+  // iteration are decomposed once, by 16 threads, into shared memory.  Same elements, same order: the sums are unchanged.
+  static_assert(256 % TBN == 0 && TBK % (256 / TBN) == 0, "gather mapping: fixed k column per thread");
+  __shared__ int s_img[TBK], s_ih0[TBK], s_iw0[TBK];
+  const int c_fix = tid % TBN, rr0 = tid / TBN;
+  const int kfix = k0 + c_fix;
+  const bool k_ok = kfix < Kw;
+  const int tap_f = k_ok ? kfix / p.Cin : 0, ci_f = k_ok ? kfix - tap_f * p.Cin : 0;
+  const int kh_f = tap_f / p.KW, kw_f = tap_f - kh_f * p.KW;
+  const int HoWo = p.Ho * p.Wo;
   for (int64_t rb = r0; rb < r1; rb += TBK) {
+    if (tid < TBK) {
+      const int64_t r = rb + tid;
+      int n_img = -1, ih0 = 0, iw0 = 0;
+      if (r < r1) {
+        n_img = (int)(r / HoWo);
+        const int rem = (int)(r - (int64_t)n_img * HoWo);
+        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+        ih0 = oh * p.sh - p.ph; iw0 = ow * p.sw - p.pw;
+      }
+      s_img[tid] = n_img; s_ih0[tid] = ih0; s_iw0[tid] = iw0;
+    }
     for (int e = tid; e < TBK * TBM; e += 256) {
       const int rr = e / TBM, c = e - rr * TBM;
       const int64_t r = rb + rr;
       const int co = co0 + c;
       As[rr][c] = (r < r1 && co < p.Cout) ? p.dy[r * p.Cout + co] : 0.f;
     }
-    for (int e = tid; e < TBK * TBN; e += 256) {
-      const int rr = e / TBN, c = e - rr * TBN;
-      const int64_t r = rb + rr;
-      const int k = k0 + c;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TBK / (256 / TBN); ++i) {
+      const int rr = rr0 + i * (256 / TBN);
+      const int n_img = s_img[rr];
       float v = 0.f;
-      if (r < r1 && k < Kw) {
-        const int n_img = (int)(r / ((int64_t)p.Ho * p.Wo));
-        const int rem = (int)(r - (int64_t)n_img * p.Ho * p.Wo);
-        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-        const int tap = k / p.Cin, ci = k - tap * p.Cin;
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-        const int ih = oh * p.sh - p.ph + kh, iw = ow * p.sw - p.pw + kw;
-        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[(((int64_t)n_img * p.H + ih) * p.W + iw) * p.Cin + ci];
+      if (n_img >= 0 && k_ok) {
+        const int ih = s_ih0[rr] + kh_f, iw = s_iw0[rr] + kw_f;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = __ldg(p.x + (((int64_t)n_img * p.H + ih) * p.W + iw) * p.Cin + ci_f);
       }
-      Bs[rr][c] = v;
+      Bs[rr][c_fix] = v;
     }
     __syncthreads();
 #pragma unroll
