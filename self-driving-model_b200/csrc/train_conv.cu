@@ -194,8 +194,8 @@ constexpr int TBM = 64, TBN = 64, TBK = 16;
 
 // dx[m=(n,ih,iw), ci] = sum_{kh,kw,co} dy[n, (ih+ph-kh)/sh, (iw+pw-kw)/sw, co] * w[co,kh,kw,ci]
 __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
-  __shared__ float As[TBK][TBM + 4];
-  __shared__ float Bs[TBK][TBN + 4];
+  __shared__ __align__(16) float As[TBK][TBM + 4];
+  __shared__ __align__(16) float Bs[TBK][TBN + 4];
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int Ktot = p.KH * p.KW * p.Cout;   // reduction index k = tap*Cout + co
   const int Kw = p.KH * p.KW * p.Cin;      // row length of the packed weights
@@ -280,11 +280,10 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TBK; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      // one 16-byte shared-memory load per operand (rows are 16-byte aligned: pitch TBM + 4 floats)
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -306,8 +305,8 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
 
 // partial dW[s][co][k=(kh,kw,ci)] = sum over the output pixels of slice s of dy[pix,co] * x[window(pix,k)]
 __global__ __launch_bounds__(256) void conv_bwd_weight_kernel(ConvBwdParams p) {
-  __shared__ float As[TBK][TBM + 4];   // [pixel][co]
-  __shared__ float Bs[TBK][TBN + 4];   // [pixel][k]
+  __shared__ __align__(16) float As[TBK][TBM + 4];   // [pixel][co]
+  __shared__ __align__(16) float Bs[TBK][TBN + 4];   // [pixel][k]
   const int Kw = p.KH * p.KW * p.Cin;
   const int64_t Mg = (int64_t)p.B * p.Ho * p.Wo;
   const int co0 = blockIdx.x * TBM, k0 = blockIdx.y * TBN, s = blockIdx.z;
@@ -362,11 +361,10 @@ __global__ __launch_bounds__(256) void conv_bwd_weight_kernel(ConvBwdParams p) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TBK; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      // one 16-byte shared-memory load per operand (rows are 16-byte aligned: pitch TBM + 4 floats)
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
