@@ -321,6 +321,12 @@ int amoe_lsap_batched_host(const float* cost_host, const int32_t* n_tgt_host, in
 int amoe_linear_fwd(amoe_ctx*, const float* x, int ldx, const float* W, const float* b, float* y,
                     int ldy, int B, int in_dim, int out_dim, int relu, float drop_p, uint64_t seed,
                     void* stream);
+/* The same with the per-step part of the dropout key on the device: the mask is keyed by (seed + *seed_dev, b*out+o), so a
+ * captured training step (CUDA graph) draws a new mask on every replay once amoe_train_tick has advanced *seed_dev
+ * (train_gating_network.py:85 - model.train() keeps Dropout(0.1) active in every step). */
+int amoe_linear_fwd_dseed(amoe_ctx*, const float* x, int ldx, const float* W, const float* b, float* y,
+                          int ldy, int B, int in_dim, int out_dim, int relu, float drop_p, uint64_t seed,
+                          const uint64_t* seed_dev, void* stream);
 /* Gradients of the above.  With relu!=0 the mask of ReLU and Dropout together is y > 0 (g_tmp [B,out]
  * receives dy*[y>0]/(1-p)).  Any of dx/dW/db may be NULL.  dW [out,in], db [out]: overwritten. */
 int amoe_linear_bwd(amoe_ctx*, const float* dy, int lddy, const float* y, int ldy, const float* x,
@@ -380,6 +386,15 @@ int amoe_fused_clip_adamw(amoe_ctx*, float* params, const float* grads, float* e
                           float* exp_avg_sq, int64_t n, const float* norm2, float grad_scale,
                           float max_norm, float lr, float beta1, float beta2, float eps,
                           float weight_decay, int step, void* stream);
+/* The same with the step count read from device memory (*step_dev >= 1), for a step replayed as a CUDA graph
+ * (train_gating_network.py:103-105: clip_grad_norm_ + optimizer.step() once per iteration). */
+int amoe_fused_clip_adamw_dstep(amoe_ctx*, float* params, const float* grads, float* exp_avg,
+                                float* exp_avg_sq, int64_t n, const float* norm2, float grad_scale,
+                                float max_norm, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, const int* step_dev, void* stream);
+/* Advances the device-side counters of a training step by one: *step_dev += 1 (AdamW bias correction) and
+ * *seed_dev += an odd 64-bit constant (dropout key); either may be NULL.  One single-thread launch. */
+int amoe_train_tick(amoe_ctx*, int* step_dev, uint64_t* seed_dev, void* stream);
 /* nn.BatchNorm2d in training mode on NHWC fp32 x [M = N*H*W, C]: batch statistics (biased variance for
  * the normalisation, unbiased for running_var), running stats updated in place with `momentum`
  * (NULL: not tracked), y = ReLU?(gamma * xhat + beta).  save_mean/save_rstd [C] feed the backward.

@@ -78,6 +78,7 @@ SIGNATURES = {
     "amoe_lsap_batched_host": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I]),
     # training step (gating + policy)
     "amoe_linear_fwd": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, C.c_uint64, _P]),
+    "amoe_linear_fwd_dseed": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, C.c_uint64, _P, _P]),
     "amoe_linear_bwd": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P]),
     "amoe_layernorm_fwd": (_I, [_P] * 7 + [_I, _I, _F, _P]),
     "amoe_layernorm_bwd": (_I, [_P] * 9 + [_I, _I, _P]),
@@ -88,6 +89,8 @@ SIGNATURES = {
     "amoe_gating_loss_fwd_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, C.POINTER(_F), _I, _I, _P, _P, _P, _P, _P]),
     "amoe_sq_norm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "amoe_fused_clip_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P] + [_F] * 7 + [_I, _P]),
+    "amoe_fused_clip_adamw_dstep": (_I, [_P, _P, _P, _P, _P, _L, _P] + [_F] * 7 + [_P, _P]),
+    "amoe_train_tick": (_I, [_P, _P, _P, _P]),
     "amoe_colreduce_workspace_floats": (_L, [_L, _I]),
     "amoe_bn_train_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
     "amoe_bn_apply_fwd": (_I, [_P] * 7 + [_L, _I, _I, _P]),

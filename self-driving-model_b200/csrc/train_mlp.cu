@@ -32,7 +32,7 @@ template <bool TA, bool TB>
 __global__ __launch_bounds__(256) void sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                     float* __restrict__ C, int M, int N, int K, int lda, int ldb,
                                                     int ldc, const float* __restrict__ bias, int relu, float drop_p,
-                                                    uint64_t seed) {
+                                                    uint64_t seed, const uint64_t* __restrict__ seed_dev) {
   __shared__ float As[GBK][GBM + 4];
   __shared__ float Bs[GBK][GBN + 4];
   const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
@@ -76,6 +76,7 @@ __global__ __launch_bounds__(256) void sgemm_kernel(const float* __restrict__ A,
     __syncthreads();
   }
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (drop_p > 0.f && seed_dev) seed += *seed_dev;     // per-step part of the key, advanced on the device (amoe_train_tick)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -91,6 +92,91 @@ __global__ __launch_bounds__(256) void sgemm_kernel(const float* __restrict__ A,
       C[(int64_t)m * ldc + n] = v;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same product for the shapes the gating / policy MLPs have in training: M = the per-GPU batch (32), N and K a few
+// hundred.  The 64x64 tiles above leave such a launch with N/64 CTAs that each walk all of K behind two barriers per 16
+// columns (58 us for 32x768 -> 512).  Here a CTA owns SK_TN output columns of 32 rows, lane = row, and the reduction axis
+// is split over its eight warps: every warp stages its slice of B once (coalesced), every lane streams its own row of A
+// with 16-byte loads, and the eight partial sums meet in shared memory in a fixed order (deterministic).  N/8 CTAs, one
+// round trip to memory each.  TA = false only (the weight gradient has M = out_dim and stays on the tiled kernel).
+constexpr int SK_TN = 8, SK_WARPS = 8, SK_KC = 128;
+
+template <bool TB>
+__global__ __launch_bounds__(SK_WARPS * 32) void skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                    float* __restrict__ C, int M, int N, int K, int lda,
+                                                                    int ldb, int ldc, const float* __restrict__ bias, int relu,
+                                                                    float drop_p, uint64_t seed,
+                                                                    const uint64_t* __restrict__ seed_dev, int a_vec) {
+  __shared__ __align__(16) float Bs[SK_WARPS][SK_KC][SK_TN];
+  __shared__ float red[SK_WARPS][32 * SK_TN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * SK_TN, m0 = blockIdx.y * 32;
+  const int m_ld = min(m0 + lane, M - 1);                       // rows past M read the last row and store nothing
+  const float* __restrict__ arow = A + (int64_t)m_ld * lda;
+  const int kslice = (((K + 3) >> 2) + SK_WARPS - 1) / SK_WARPS * 4;   // multiple of 4: 16-byte loads never straddle slices
+  const int kb = warp * kslice, ke = min(K, kb + kslice);
+  float acc[SK_TN];
+#pragma unroll
+  for (int j = 0; j < SK_TN; ++j) acc[j] = 0.f;
+  for (int kc = kb; kc < ke; kc += SK_KC) {
+    const int len = min(SK_KC, ke - kc);
+    const int len4 = (len + 3) & ~3;
+    // this warp's [len x SK_TN] block of B -> Bs[r][j]; rows past len are zero so the 4-wide steps below may run over
+    if (TB) {
+#pragma unroll
+      for (int j = 0; j < SK_TN; ++j) {
+        const bool col = n0 + j < N;
+        const float* __restrict__ brow = B + (int64_t)(n0 + j) * ldb + kc;
+        for (int r = lane; r < len4; r += 32) Bs[warp][r][j] = (col && r < len) ? __ldg(brow + r) : 0.f;
+      }
+    } else {
+      for (int e = lane; e < len4 * SK_TN; e += 32) {
+        const int r = e / SK_TN, j = e % SK_TN;
+        (&Bs[warp][0][0])[e] = (r < len && n0 + j < N) ? __ldg(B + (int64_t)(kc + r) * ldb + n0 + j) : 0.f;
+      }
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < len4; r += 4) {
+      float a[4];
+      if (a_vec && kc + r + 3 < K) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(arow + kc + r));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = (kc + r + q < K) ? __ldg(arow + kc + r + q) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[warp][r + q][0]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[warp][r + q][4]);
+        acc[0] = fmaf(a[q], b0.x, acc[0]); acc[1] = fmaf(a[q], b0.y, acc[1]);
+        acc[2] = fmaf(a[q], b0.z, acc[2]); acc[3] = fmaf(a[q], b0.w, acc[3]);
+        acc[4] = fmaf(a[q], b1.x, acc[4]); acc[5] = fmaf(a[q], b1.y, acc[5]);
+        acc[6] = fmaf(a[q], b1.z, acc[6]); acc[7] = fmaf(a[q], b1.w, acc[7]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < SK_TN; ++j) red[warp][lane * SK_TN + j] = acc[j];
+  __syncthreads();
+  // thread t finishes output (row t / 8, column t % 8): a row's eight columns are one 32-byte store segment
+  const int t = threadIdx.x;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < SK_WARPS; ++w) v += red[w][t];
+  const int m = m0 + t / SK_TN, n = n0 + t % SK_TN;
+  if (m >= M || n >= N) return;
+  if (bias) v += bias[n];
+  if (relu) v = fmaxf(v, 0.f);
+  if (drop_p > 0.f) {
+    if (seed_dev) seed += *seed_dev;
+    v = (u01_hash(seed, (uint64_t)m * N + n) >= drop_p) ? v * (1.f / (1.f - drop_p)) : 0.f;
+  }
+  C[(int64_t)m * ldc + n] = v;
 }
 
 // g = dy * [y > 0] * keep_scale  (gradient through Dropout(ReLU(.)): a kept, active unit has y > 0)
@@ -419,12 +505,24 @@ __global__ void sq_norm_final_kernel(const float* __restrict__ partial, int n, f
     out[1] = sqrtf(s);
   }
 }
+// One training step further: the optimizer's step count and the per-step part of the dropout key.  They live on the device
+// so that a captured step (GraphedTrainStep) advances them on replay.
+__global__ void train_tick_kernel(int* __restrict__ step_dev, uint64_t* __restrict__ seed_dev) {
+  if (step_dev) *step_dev += 1;
+  if (seed_dev) *seed_dev += 0xD1B54A32D192ED03ull;
+}
+
 // p, m, v updated in place.  grad is scaled by grad_scale (e.g. 1/world_size after an all-reduce SUM)
 // and by the clip coefficient min(1, max_norm / (norm*grad_scale + 1e-6)) with norm read from device.
 __global__ void clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                   float* __restrict__ v, int64_t n, const float* __restrict__ norm, float grad_scale,
                                   float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                  float bc1, float bc2) {
+                                  float bc1, float bc2, const int* __restrict__ step_dev) {
+  if (step_dev) {      // replayed CUDA graph: the step count lives on the device (amoe_train_tick advances it)
+    const float t = (float)*step_dev;
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
   float clip = 1.f;
   if (max_norm > 0.f && norm) {
     const float total = norm[1] * grad_scale;
@@ -446,9 +544,18 @@ __global__ void clip_adamw_kernel(float* __restrict__ p, const float* __restrict
 
 template <bool TA, bool TB>
 int launch_sgemm(amoe_ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
-                 const float* bias, int relu, float drop_p, uint64_t seed, cudaStream_t st) {
+                 const float* bias, int relu, float drop_p, uint64_t seed, cudaStream_t st, const uint64_t* seed_dev = nullptr) {
+  if constexpr (!TA) {
+    if (M <= 64) {      // the training batch: column-tile x split-K kernel (see skinny_gemm_kernel)
+      const int a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (lda & 3) == 0) ? 1 : 0;
+      skinny_gemm_kernel<TB><<<dim3(ceil_div(N, SK_TN), ceil_div(M, 32)), SK_WARPS * 32, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, bias,
+                                                                                               relu, drop_p, seed, seed_dev, a_vec);
+      AMOE_LAUNCH_OK(ctx);
+      return 0;
+    }
+  }
   dim3 grid(ceil_div(M, GBM), ceil_div(N, GBN));
-  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, bias, relu, drop_p, seed);
+  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, bias, relu, drop_p, seed, seed_dev);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }
@@ -495,6 +602,17 @@ int amoe_linear_fwd(amoe_ctx* ctx, const float* x, int ldx, const float* W, cons
   // y[B,out] = x[B,in] * W[out,in]^T
   return launch_sgemm<false, true>(ctx, x, W, y, B, out_dim, in_dim, ldx, in_dim, ldy, b, relu, drop_p, seed,
                                    (cudaStream_t)stream);
+}
+
+int amoe_linear_fwd_dseed(amoe_ctx* ctx, const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int B,
+                          int in_dim, int out_dim, int relu, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x && W && y && seed_dev, "amoe_linear_fwd_dseed: NULL argument");
+  AMOE_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "amoe_linear_fwd_dseed: dropout p=%f out of [0,1)", drop_p);
+  AMOE_REQUIRE(ldx >= in_dim && ldy >= out_dim, "amoe_linear_fwd_dseed: leading dimension too small");
+  if (B == 0) return 0;
+  return launch_sgemm<false, true>(ctx, x, W, y, B, out_dim, in_dim, ldx, in_dim, ldy, b, relu, drop_p, seed,
+                                   (cudaStream_t)stream, seed_dev);
 }
 
 int amoe_linear_bwd(amoe_ctx* ctx, const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
@@ -644,7 +762,28 @@ int amoe_fused_clip_adamw(amoe_ctx* ctx, float* params, const float* grads, floa
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   const int blocks = (int)std::min<int64_t>(8 * ctx->sm_count, (n + 255) / 256);
   clip_adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, norm2, grad_scale,
-                                                             max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+                                                             max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2, nullptr);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_fused_clip_adamw_dstep(amoe_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const float* norm2, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, const int* step_dev, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq && step_dev, "amoe_fused_clip_adamw_dstep: NULL argument");
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<int64_t>(8 * ctx->sm_count, (n + 255) / 256);
+  clip_adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, norm2, grad_scale,
+                                                             max_norm, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, step_dev);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_train_tick(amoe_ctx* ctx, int* step_dev, uint64_t* seed_dev, void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && (step_dev || seed_dev), "amoe_train_tick: NULL argument");
+  train_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, seed_dev);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

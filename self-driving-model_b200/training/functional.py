@@ -32,6 +32,29 @@ def next_seed() -> int:
     return int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFFFFFFFFFF
 
 
+# Per-step part of the dropout key on the device (a one-element int64 tensor) while a training step is captured as a CUDA
+# graph: the host seed drawn per call is baked into the graph, the device part advances on every replay (amoe_train_tick),
+# so every replay draws new masks.  None: eager mode, the key is the host seed alone.
+_DEVICE_SEED: Optional[torch.Tensor] = None
+
+
+class device_dropout_seed:
+    """Context manager: dropout layers executed inside key their masks by (host seed + *seed_dev)."""
+
+    def __init__(self, seed_dev: Optional[torch.Tensor]):
+        self.seed_dev = seed_dev
+
+    def __enter__(self):
+        global _DEVICE_SEED
+        self.prev, _DEVICE_SEED = _DEVICE_SEED, self.seed_dev
+        return self
+
+    def __exit__(self, *exc):
+        global _DEVICE_SEED
+        _DEVICE_SEED = self.prev
+        return False
+
+
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     """y = Dropout_p(ReLU?(x W^T + b)) — nn.Linear [+ nn.ReLU [+ nn.Dropout]] fused."""
@@ -43,8 +66,13 @@ class _Linear(torch.autograd.Function):
         B, in_dim = x2.shape
         out_dim = W2.shape[0]
         y = torch.empty((B, out_dim), device=x2.device, dtype=torch.float32)
-        check(lib().amoe_linear_fwd(ctx(x2.device), ptr(x2), in_dim, ptr(W2), ptr(b2), ptr(y), out_dim, B, in_dim, out_dim,
-                                    int(relu), float(drop_p), seed, stream_ptr(x2.device)), "linear_fwd")
+        if drop_p > 0.0 and _DEVICE_SEED is not None:
+            check(lib().amoe_linear_fwd_dseed(ctx(x2.device), ptr(x2), in_dim, ptr(W2), ptr(b2), ptr(y), out_dim, B, in_dim, out_dim,
+                                              int(relu), float(drop_p), seed, ptr(_DEVICE_SEED), stream_ptr(x2.device)),
+                  "linear_fwd_dseed")
+        else:
+            check(lib().amoe_linear_fwd(ctx(x2.device), ptr(x2), in_dim, ptr(W2), ptr(b2), ptr(y), out_dim, B, in_dim, out_dim,
+                                        int(relu), float(drop_p), seed, stream_ptr(x2.device)), "linear_fwd")
         ctx_.save_for_backward(x2, W2, y if relu else None)
         ctx_.cfg = (relu, float(drop_p), b is not None)
         return y

@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 from .._cabi import check, ctx, lib
 from .._ops import ptr, stream_ptr
-from .functional import LOSS_NAMES, _GatingLoss
+from .functional import LOSS_NAMES, _GatingLoss, device_dropout_seed
 
 
 def compute_gating_losses(pred: Dict[str, torch.Tensor], target_wp: torch.Tensor, target_spd: torch.Tensor,
@@ -96,6 +96,22 @@ class FlatAdamW:
         self._ws = torch.empty(4 * 148, device=dev, dtype=torch.float32)
         self._norm = torch.zeros(2, device=dev, dtype=torch.float32)
         self.step_count = 0
+        self._step_dev: Optional[torch.Tensor] = None      # device-side step count / dropout key (GraphedTrainStep)
+        self._seed_dev: Optional[torch.Tensor] = None
+
+    def enable_device_counters(self) -> None:
+        """Keep the step count (AdamW bias correction) and the per-step part of the dropout key in device memory, advanced by
+        tick(): what a step replayed as a CUDA graph needs (host integers would be frozen into the graph)."""
+        if self._step_dev is None:
+            dev = self.flat_param.device
+            self._step_dev = torch.tensor([self.step_count], device=dev, dtype=torch.int32)
+            self._seed_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+
+    def tick(self) -> None:
+        """Start of a step: advance the device-side counters (no-op without enable_device_counters)."""
+        if self._step_dev is not None:
+            dev = self.flat_param.device
+            check(lib().amoe_train_tick(ctx(dev), ptr(self._step_dev), ptr(self._seed_dev), stream_ptr(dev)), "train_tick")
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_grad.zero_()
@@ -120,10 +136,16 @@ class FlatAdamW:
         self.step_count += 1
         clip = self.max_norm is not None and self.max_norm > 0
         check(lib().amoe_sq_norm(h, ptr(self.flat_grad), self.n, ptr(self._ws), self._ws.numel(), ptr(self._norm), st), "sq_norm")
-        check(lib().amoe_fused_clip_adamw(h, ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                          self.n, ptr(self._norm), scale, float(self.max_norm) if clip else 0.0, self.lr,
-                                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, st),
-              "fused_clip_adamw")
+        if self._step_dev is not None:
+            check(lib().amoe_fused_clip_adamw_dstep(h, ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg),
+                                                    ptr(self.exp_avg_sq), self.n, ptr(self._norm), scale,
+                                                    float(self.max_norm) if clip else 0.0, self.lr, self.betas[0], self.betas[1],
+                                                    self.eps, self.weight_decay, ptr(self._step_dev), st), "fused_clip_adamw_dstep")
+        else:
+            check(lib().amoe_fused_clip_adamw(h, ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                              self.n, ptr(self._norm), scale, float(self.max_norm) if clip else 0.0, self.lr,
+                                              self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, st),
+                  "fused_clip_adamw")
         # the kernel wrote through raw pointers: tell torch (cached weight packs key on Tensor._version)
         torch.autograd.graph.increment_version(self.params)
 
@@ -158,9 +180,78 @@ def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, conf
     """One iteration of train_one_epoch (train_gating_network.py:93-105): zero_grad, forward, losses,
     backward, (all-reduce,) clip 1.0, AdamW.  Returns the loss dict (device tensors; no host sync)."""
     optimizer.zero_grad()
+    optimizer.tick()
     broadcast_buffers_(model, getattr(optimizer, "group", None))      # DDP's per-forward buffer sync (no-op on one rank)
-    pred = model(batch)
+    with device_dropout_seed(optimizer._seed_dev):
+        pred = model(batch)
     losses = compute_gating_losses(pred, batch["waypoints"], batch["speed"], config)
     losses["total_loss"].backward()
     optimizer.step()
     return {k: v.detach() for k, v in losses.items()}
+
+
+class GraphedTrainStep:
+    """train_step captured ONCE as a CUDA graph and replayed: forward in train mode, fused losses, backward,
+    gradient all-reduce, clip + AdamW - about 540 launches per step whose enqueue costs the host as long as they run.
+
+    What a replay cannot take from the host lives on the device: the optimizer's step count and the per-step part of the
+    dropout key (FlatAdamW.enable_device_counters; amoe_train_tick advances both inside the graph), so bias correction and
+    dropout masks differ from step to step exactly as in eager mode.  Construction runs `warmup` eager steps on `batch` (weight
+    packs, allocator, NCCL) and then restores parameters, moments, module buffers and counters, so building the graph leaves
+    the training state untouched.  Inputs are copied into static buffers per call; the returned loss dict aliases static
+    device tensors (overwritten by the next call).  Shapes and the module's train/eval flags are fixed at capture time.
+    """
+
+    def __init__(self, model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, config: Dict, warmup: int = 3,
+                 autocast_dtype: Optional[torch.dtype] = None):
+        from .._cabi import launch_count
+        dev = optimizer.flat_param.device
+        self.model, self.optimizer, self.config, self.autocast_dtype = model, optimizer, config, autocast_dtype
+        self.static_in = {k: v.to(dev).clone() for k, v in batch.items() if torch.is_tensor(v)}
+        optimizer.enable_device_counters()
+        saved = [t.clone() for t in (optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer._step_dev,
+                                     optimizer._seed_dev)]
+        buffers = [(b, b.clone()) for b in model.buffers()]
+        step_count = optimizer.step_count
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # staging caches keyed on Tensor._version must miss during capture, or the replay would keep the warm-up's frames
+        torch.autograd.graph.increment_version(list(self.static_in.values()))
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count(dev)
+        with torch.cuda.graph(self.graph):
+            self.losses = self._eager()
+        self.launches_per_replay = launch_count(dev) - n0
+        with torch.no_grad():                       # nothing of the above counts as training
+            for t, s in zip((optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer._step_dev,
+                             optimizer._seed_dev), saved):
+                t.copy_(s)
+            for b, s in buffers:
+                b.copy_(s)
+            optimizer.flat_grad.zero_()
+        optimizer.step_count = step_count
+        torch.autograd.graph.increment_version(optimizer.params)
+
+    def _eager(self):
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                return train_step(self.model, self.static_in, self.optimizer, self.config)
+        return train_step(self.model, self.static_in, self.optimizer, self.config)
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for k, dst in self.static_in.items():
+            src = batch[k]
+            if src.shape != dst.shape:
+                raise ValueError(f"GraphedTrainStep was captured with {k}{tuple(dst.shape)}, got {tuple(src.shape)}")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.optimizer.step_count += 1
+        # the replay wrote parameters through raw pointers: cached weight packs key on Tensor._version
+        torch.autograd.graph.increment_version(self.optimizer.params)
+        return dict(self.losses)

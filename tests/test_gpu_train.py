@@ -27,7 +27,7 @@ def _gen(seed):
 
 
 @pytest.mark.parametrize("B,i,o,relu", [(32, 896, 128, True), (5, 4, 32, True), (32, 768, 512, False), (3, 128, 3, False),
-                                        (70, 130, 66, True)])
+                                        (70, 130, 66, True), (64, 260, 24, True), (33, 1030, 9, False), (1, 2050, 130, True)])
 def test_linear_fwd_bwd(B, i, o, relu):
     from automoe_b200.training import functional as TF
     g = _gen(1)
@@ -43,6 +43,25 @@ def test_linear_fwd_bwd(B, i, o, relu):
     yr.backward(dy)
     for a, b in zip(got, (yr.detach(), x.grad, lin.weight.grad, lin.bias.grad)):
         assert rel_err(a, b) < TOL, rel_err(a, b)
+
+
+def test_linear_on_row_slices_of_wider_buffers():
+    """The C entry takes row strides: x / y as column slices of wider buffers whose start is not 16-byte aligned (the
+    small-batch kernel then falls back from 16-byte to scalar loads of x) - straight through the C-ABI."""
+    from automoe_b200._cabi import check, ctx, lib
+    from automoe_b200._ops import ptr, stream_ptr
+    g = _gen(3)
+    B, i, o = 32, 70, 20
+    xw = torch.randn((B, 100), generator=g).to(DEV)
+    yw = torch.zeros((B, 50), device=DEV)
+    W = torch.randn((o, i), generator=g).to(DEV)
+    b = torch.randn(o, generator=g).to(DEV)
+    x, y = xw[:, 3:3 + i], yw[:, 5:5 + o]
+    dev = torch.device(DEV)
+    check(lib().amoe_linear_fwd(ctx(dev), x.data_ptr(), 100, ptr(W), ptr(b), y.data_ptr(), 50, B, i, o, 1, 0.0, 0, stream_ptr(dev)),
+          "linear_fwd")
+    assert rel_err(y, F.relu(F.linear(x, W, b))) < TOL
+    assert yw[:, :5].abs().max() == 0 and yw[:, 5 + o:].abs().max() == 0      # nothing outside the slice was written
 
 
 def test_linear_dropout_mask_and_scale():
@@ -384,6 +403,72 @@ def test_train_step_reduces_loss_and_refreshes_inference_packs():
     assert (after - before).abs().max() > 1e-4                      # the fused inference path saw the new weights
     diff_path = m(batch)["waypoints"]                               # eval + grad enabled + frozen experts: autograd path
     assert diff_path.requires_grad and rel_err(after, diff_path.detach()) < 1e-4
+
+
+def _graph_models():
+    from automoe_b200.training.train_gating_network import FlatAdamW, freeze_for_gating_training
+    out = []
+    for _ in range(2):
+        m, _sd = build_b200_model(DEV, "fp32")
+        opt = FlatAdamW(freeze_for_gating_training(m), lr=1e-3, weight_decay=1e-4, max_norm=1.0)
+        m.train()
+        out.append((m, opt))
+    return out
+
+
+def _train_batch(B, H, seed):
+    batch = {k: v.to(DEV) for k, v in synth.synth_batch(B, H, H, seed=seed, speed_seq=1).items()}
+    wp, spd = _targets(B, 10, seed + 1)
+    batch["waypoints"], batch["speed"] = wp.to(DEV), spd.to(DEV)
+    return batch
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """train_step captured once as a CUDA graph (GraphedTrainStep) and replayed on three different batches
+    against three eager steps from the same initial state (Dropout p = 0 so both draw no masks): same losses, parameters,
+    Adam moments and BatchNorm running statistics; building the graph leaves the training state untouched."""
+    from automoe_b200.training.train_gating_network import GraphedTrainStep, train_step
+    (ma, oa), (mb, ob) = _graph_models()
+    for m in (ma, mb):
+        for mod in m.modules():
+            if isinstance(mod, nn.Dropout):
+                mod.p = 0.0
+    batches = [_train_batch(4, 64, 30 + 2 * i) for i in range(3)]
+    p0 = ob.flat_param.clone()
+    bufs0 = [b.clone() for b in mb.buffers()]
+    step = GraphedTrainStep(mb, batches[0], ob, {})
+    assert torch.equal(ob.flat_param, p0) and ob.step_count == 0 and int(ob._step_dev.item()) == 0
+    assert all(torch.equal(b, c) for b, c in zip(mb.buffers(), bufs0))
+    assert step.launches_per_replay > 100
+    for i, b in enumerate(batches):
+        le = train_step(ma, b, oa, {})
+        lg = step(b)
+        for k in le:
+            assert abs(le[k].item() - lg[k].item()) <= 1e-5 * max(1.0, abs(le[k].item())), (i, k, le[k].item(), lg[k].item())
+        assert rel_err(ob.flat_param, oa.flat_param) < 1e-6, (i, rel_err(ob.flat_param, oa.flat_param))
+        assert rel_err(ob.flat_grad, oa.flat_grad) < 1e-5
+    assert ob.step_count == 3 and int(ob._step_dev.item()) == 3
+    assert rel_err(ob.exp_avg, oa.exp_avg) < 1e-5 and rel_err(ob.exp_avg_sq, oa.exp_avg_sq) < 1e-5
+    for (ka, a), (_, b) in zip(ma.named_buffers(), mb.named_buffers()):
+        assert rel_err(b.float(), a.float()) < 1e-5, ka
+    # eval forward after graphed training sees the updated weights (cached packs invalidated by the version bump)
+    ma.eval(); mb.eval()
+    with torch.no_grad():
+        assert rel_err(mb(batches[0])["waypoints"], ma(batches[0])["waypoints"]) < 1e-5
+
+
+def test_graphed_train_step_draws_new_dropout_masks_per_replay():
+    """Dropout(0.1) stays active in a replayed step: with lr = 0 the parameters stay put, so two replays on one batch differ
+    only by their masks - the per-step part of the key lives on the device and advances inside the graph."""
+    from automoe_b200.training.train_gating_network import FlatAdamW, GraphedTrainStep, freeze_for_gating_training
+    m, _sd = build_b200_model(DEV, "fp32")
+    opt = FlatAdamW(freeze_for_gating_training(m), lr=0.0, weight_decay=0.0, max_norm=1.0)
+    m.train()
+    batch = _train_batch(8, 64, 40)
+    step = GraphedTrainStep(m, batch, opt, {})
+    losses = [step(batch)["total_loss"].item() for _ in range(4)]
+    assert len({round(l, 6) for l in losses}) == 4, losses
+    assert max(losses) - min(losses) < 0.2 * abs(losses[0])         # same batch, same weights: masks are the only difference
 
 
 @pytest.mark.parametrize("B,H,W,Cout,K,pad,bias", [(3, 64, 64, 64, 7, 3, False), (2, 256, 256, 64, 7, 3, False), (5, 96, 160, 32, 5, 2, True),

@@ -61,6 +61,12 @@ def main():
             t = rows.setdefault(e.name[:110], [0.0, 0])
             t[0] += e.device_time
             t[1] += 1
+    detail = {}
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA and any(k in e.name for k in ("conv2d_simt", "conv_bwd_weight", "conv_bwd_data")):
+            detail.setdefault(e.name[:60], []).append(round(e.device_time))
+    for name, ts in detail.items():      # per-launch times (us) of the CUDA-core convolutions, in launch order, last profiled step
+        print(f"#   {name}: {ts[-(len(ts) // 3):]}")
     tot = sum(v[0] for v in rows.values())
     print(f"# {mode}: {tot / 3 / 1e3:.2f} ms of kernel time per step")
     for name, (t, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:28]:
