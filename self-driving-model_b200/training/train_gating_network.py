@@ -156,9 +156,15 @@ def broadcast_buffers_(model, group=None, src: int = 0) -> None:
     per dtype.  No-op outside torch.distributed / at world size 1."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
+    # Frozen experts on running statistics (frozen_experts_eval) never write their buffers: replicas cannot drift there, and
+    # copying them would bump Tensor._version every step - the cached inference packs of the experts would be rebuilt per step
+    skip = set()
+    if getattr(model, "frozen_experts_eval", False) and hasattr(model, "experts"):
+        skip = {id(b) for b in model.experts.buffers()}
     by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
     for b in model.buffers():
-        by_dtype.setdefault(b.dtype, []).append(b)
+        if id(b) not in skip:
+            by_dtype.setdefault(b.dtype, []).append(b)
     with torch.no_grad():
         for bufs in by_dtype.values():
             flat = torch.cat([b.reshape(-1) for b in bufs])

@@ -108,3 +108,53 @@ def test_allreduce_flat_single_process_is_identity():
     from automoe_b200.training.train_gating_network import allreduce_flat_
     t = torch.ones(4)
     assert allreduce_flat_(t) == 1.0 and t.tolist() == [1.0] * 4
+
+
+def _buffer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import torch.nn as nn
+    from automoe_b200.training.train_gating_network import broadcast_buffers_
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Toy(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.experts = nn.ModuleList([nn.BatchNorm2d(4)])
+                self.policy = nn.BatchNorm2d(4)
+        out = []
+        for frozen_eval in (False, True):
+            m = Toy()
+            m.frozen_experts_eval = frozen_eval
+            with torch.no_grad():
+                for b in m.buffers():
+                    b.fill_(rank + 1)                   # replicas drifted apart: rank 0 holds 1, rank 1 holds 2
+            v0 = m.experts[0].running_mean._version
+            broadcast_buffers_(m)
+            out.append((m.policy.running_mean.tolist(), int(m.policy.num_batches_tracked), m.experts[0].running_mean.tolist(),
+                        m.experts[0].running_mean._version - v0))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_buffers_world2():
+    """DDP-style per-step buffer sync: every rank takes rank 0's BatchNorm statistics and counters.  With the frozen experts on
+    running statistics (frozen_experts_eval) their buffers are constants: they are left alone, so their Tensor._version - the
+    key of the cached inference packs - does not move every step."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_buffer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, (plain, frozen) in res:
+        assert plain[0] == [1.0] * 4 and plain[1] == 1 and plain[2] == [1.0] * 4 and plain[3] >= 1
+        assert frozen[0] == [1.0] * 4 and frozen[1] == 1
+        assert frozen[2] == [float(rank + 1)] * 4 and frozen[3] == 0       # untouched, version unchanged
