@@ -404,6 +404,15 @@ int amoe_bn_train_fwd(amoe_ctx*, const float* x, const float* gamma, const float
                       float* running_mean, float* running_var, float momentum, float eps, float* y,
                       float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
                       int relu, void* stream);
+/* G (<= 4) BatchNorm layers of one shape in one launch per pass: x / y [G][M][C], gamma / beta / running_mean / running_var
+ * are HOST arrays of G device pointers (the layers' own parameter and buffer tensors; running_* may be NULL),
+ * save_mean / save_rstd [G*C], workspace: G * amoe_colreduce_workspace_floats(M, C) floats.  Same arithmetic as G calls of
+ * amoe_bn_train_fwd (bit-identical).  The frozen experts of a gating-training step in the reference's train mode
+ * (train_gating_network.py:85; torchvision resnet.py BasicBlock BatchNorm2d layers) run layer by layer in lockstep. */
+int amoe_bn_train_fwd_grouped(amoe_ctx*, const float* x, const float* const* gamma, const float* const* beta,
+                              float* const* running_mean, float* const* running_var, float momentum, float eps,
+                              float* y, float* save_mean, float* save_rstd, float* workspace, int G, int64_t M,
+                              int C, int relu, void* stream);
 /* y = ReLU?(gamma*(x-mean)*rstd + beta) with given statistics (eval-mode BN kept differentiable). */
 int amoe_bn_apply_fwd(amoe_ctx*, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, float* y, int64_t M, int C, int relu,

@@ -7,7 +7,8 @@ Each rank takes half of a 16-frame batch, runs forward/backward through the sm_1
 FlatAdamW.step() all-reduces the ONE flat gradient buffer over NCCL (NVLink), clips by the global norm and
 applies AdamW in one kernel.  Checks: (1) parameters stay bit-identical across ranks, (2) the averaged
 gradient equals the full-batch gradient computed on one GPU (eval-mode semantics so BatchNorm statistics do
-not depend on the shard), (3) reports the step time at 32 frames per GPU, 256x256.
+not depend on the shard), (3) reports the step time at 32 frames per GPU, 256x256, (4) replays the same step as one CUDA graph
+(GraphedTrainStep: NCCL all-reduce and buffer broadcast captured) and checks parameters and buffers stay identical across ranks.
 """
 import os
 import sys
@@ -94,10 +95,29 @@ def main():
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # ---- (4) the same step captured as one CUDA graph (all-reduce and buffer broadcast inside): replicas stay identical ----
+    from automoe_b200.training.train_gating_network import GraphedTrainStep
+    graphed = GraphedTrainStep(m, b32, opt, {})
+    for _ in range(3):
+        graphed(b32)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        graphed(b32)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_g = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    dist.all_reduce(ms_g, op=dist.ReduceOp.MAX)
+    mine = torch.cat([opt.flat_param] + [b.reshape(-1).float() for b in m.buffers()])
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    same_g = bool(torch.equal(mine, ref)) and bool(torch.isfinite(mine).all())
     if rank == 0:
         print({"world": world, "avg_shard_grad_vs_full_batch_rel_err": err, "params_identical_across_ranks": same,
-               "train_step_ms_b32_per_gpu": ms.item(), "frames_per_s": world * 32 / (ms.item() / 1e3)}, flush=True)
-    ok = torch.tensor([int(same and err < 1e-4)], device=dev)
+               "train_step_ms_b32_per_gpu": ms.item(), "frames_per_s": world * 32 / (ms.item() / 1e3),
+               "graphed_step_ms_b32_per_gpu": ms_g.item(), "graphed_frames_per_s": world * 32 / (ms_g.item() / 1e3),
+               "graphed_params_and_buffers_identical_across_ranks": same_g}, flush=True)
+    ok = torch.tensor([int(same and same_g and err < 1e-4)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if ok.item() == 1 else 1)

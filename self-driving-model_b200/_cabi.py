@@ -93,6 +93,7 @@ SIGNATURES = {
     "amoe_train_tick": (_I, [_P, _P, _P, _P]),
     "amoe_colreduce_workspace_floats": (_L, [_L, _I]),
     "amoe_bn_train_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "amoe_bn_train_fwd_grouped": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _L, _I, _I, _P]),
     "amoe_bn_apply_fwd": (_I, [_P] * 7 + [_L, _I, _I, _P]),
     "amoe_bn_bwd": (_I, [_P] * 11 + [_L, _I, _I, _P]),
     "amoe_colsum": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),

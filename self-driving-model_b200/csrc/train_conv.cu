@@ -39,6 +39,9 @@ __global__ __launch_bounds__(RED_THREADS) void colreduce_partial_kernel(const fl
   const int cb = min(C, RED_THREADS);          // channels handled per pass (C is a multiple of cb or < 256)
   const int rl = threadIdx.x / cb, nrl = RED_THREADS / cb;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  // grouped launches (MODE 0 only, amoe_bn_train_fwd_grouped): blockIdx.y = group, x = [G][M][C], partial = [G][gridDim.x][2][C]
+  x += (int64_t)blockIdx.y * M * C;
+  partial += (int64_t)blockIdx.y * gridDim.x * 2 * C;
   for (int c0 = 0; c0 < C; c0 += cb) {
     const int c = c0 + threadIdx.x % cb;
     // double accumulators: these sums feed differences (variance; g - mean(g) in the BatchNorm backward,
@@ -146,6 +149,64 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
   reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
+// The same two kernels for G independent BatchNorm layers of one shape in ONE launch each (blockIdx.y = layer): the frozen
+// experts of a gating-training step run the same ResNet-18 layer by layer, so their statistics passes are grouped like their
+// convolutions.  Same arithmetic in the same order as the single-layer kernels (results are bit-identical).
+constexpr int BN_MAX_GROUPS = 4;
+struct BnGroupPtrs {
+  const float* gamma[BN_MAX_GROUPS];
+  const float* beta[BN_MAX_GROUPS];
+  float* running_mean[BN_MAX_GROUPS];
+  float* running_var[BN_MAX_GROUPS];
+};
+
+__global__ void bn_stats_final_grouped_kernel(const double* __restrict__ partial, int nblk, int64_t M, int C, float eps,
+                                              float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                              const BnGroupPtrs gp) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, g = blockIdx.y;
+  if (c >= C) return;
+  partial += (int64_t)g * nblk * 2 * C;
+  double s = 0.0, ss = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    s += partial[((int64_t)b * 2 + 0) * C + c];
+    ss += partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  warp_sum2(s, ss);
+  if (lane != 0) return;
+  const double mu = s / (double)M;
+  double var = ss / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[g * C + c] = (float)mu;
+  rstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  float* rm = gp.running_mean[g];
+  float* rv = gp.running_var[g];
+  if (rm) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mu;
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_apply_grouped_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const BnGroupPtrs gp, float* __restrict__ y, int64_t n4, int C, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int g = blockIdx.y;
+  const int c = (int)((i * 4) % C);
+  const float* __restrict__ gamma = gp.gamma[g];
+  const float* __restrict__ beta = gp.beta[g];
+  mean += g * C;
+  rstd += g * C;
+  const float4 v = reinterpret_cast<const float4*>(x)[(int64_t)g * n4 + i];
+  float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[j] = (o[j] - mean[c + j]) * rstd[c + j] * gamma[c + j] + beta[c + j];
+    if (relu) o[j] = fmaxf(o[j], 0.f);
+  }
+  reinterpret_cast<float4*>(y)[(int64_t)g * n4 + i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // train: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M);  eval (batch_stats = 0): dx = gamma*rstd*g
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -447,6 +508,38 @@ int amoe_bn_train_fwd(amoe_ctx* ctx, const float* x, const float* gamma, const f
   AMOE_LAUNCH_OK(ctx);
   const int64_t n4 = M * C / 4;
   bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, save_mean, save_rstd, gamma, beta, y, n4, C, relu);
+  AMOE_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int amoe_bn_train_fwd_grouped(amoe_ctx* ctx, const float* x, const float* const* gamma, const float* const* beta,
+                              float* const* running_mean, float* const* running_var, float momentum, float eps, float* y,
+                              float* save_mean, float* save_rstd, float* workspace, int G, int64_t M, int C, int relu,
+                              void* stream) {
+  AMOE_ENTER(ctx);
+  AMOE_REQUIRE(ctx && x && gamma && beta && y && save_mean && save_rstd && workspace, "amoe_bn_train_fwd_grouped: NULL argument");
+  AMOE_REQUIRE(G >= 1 && G <= BN_MAX_GROUPS, "amoe_bn_train_fwd_grouped: G=%d out of [1,%d]", G, BN_MAX_GROUPS);
+  AMOE_REQUIRE(C % 4 == 0 && C >= 4, "amoe_bn_train_fwd_grouped: C=%d must be a multiple of 4", C);
+  AMOE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "amoe_bn_train_fwd_grouped: running stats come together");
+  BnGroupPtrs gp{};
+  for (int g = 0; g < G; ++g) {
+    AMOE_REQUIRE(gamma[g] && beta[g], "amoe_bn_train_fwd_grouped: NULL gamma/beta of group %d", g);
+    gp.gamma[g] = gamma[g];
+    gp.beta[g] = beta[g];
+    gp.running_mean[g] = running_mean ? running_mean[g] : nullptr;
+    gp.running_var[g] = running_var ? running_var[g] : nullptr;
+    AMOE_REQUIRE((gp.running_mean[g] == nullptr) == (gp.running_var[g] == nullptr), "amoe_bn_train_fwd_grouped: running stats come together");
+  }
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rr = red_rows(M), nblk = (int)((M + rr - 1) / rr);
+  colreduce_partial_kernel<0><<<dim3(nblk, G), RED_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, M, C, ws64(workspace), rr);
+  AMOE_LAUNCH_OK(ctx);
+  bn_stats_final_grouped_kernel<<<dim3(ceil_div(C, 4), G), 128, 0, st>>>(ws64(workspace), nblk, M, C, eps, momentum, save_mean,
+                                                                        save_rstd, gp);
+  AMOE_LAUNCH_OK(ctx);
+  const int64_t n4 = M * C / 4;
+  bn_apply_grouped_kernel<<<dim3((unsigned)((n4 + 255) / 256), G), 256, 0, st>>>(x, save_mean, save_rstd, gp, y, n4, C, relu);
   AMOE_LAUNCH_OK(ctx);
   return 0;
 }

@@ -24,8 +24,8 @@ from ._precision import resolve_dtype
 from .context.context_features import create_context_extractor
 from .experts import BDDDetectionExpert, BDDDrivableExpert, BDDSegmentationExpert, NuScenesExpert
 from .experts._base import BDDExpertBase, get_trunk_pack, run_experts, side_stream
-from .experts._trunk import (chunked_stem_layer1_supported, params_stamp, run_stem_layer1_chunked, run_trunk_train,
-                             stage_image, trunk_pool_pad)
+from .experts._trunk import (chunked_stem_layer1_supported, grouped_train_supported, params_stamp, run_stem_layer1_chunked,
+                             run_trunk_train, run_trunks_train_grouped, stage_image, trunk_pool_pad)
 from .experts.expert_extractors import create_expert_extractors
 from .gating.gating_network import GatingNetwork
 from .policy.trajectory_head import TrajectoryPolicy
@@ -215,9 +215,12 @@ class AutoMoE(nn.Module):
         running-stat updates (fp32 training kernels, no autograd graph).  Returns (expert_outputs, pooled, n_ch)."""
         outs, pooled = [], []
         H, W = image.shape[2], image.shape[3]
+        bdd = self._bdd_experts()
         with torch.no_grad():
-            for e in self._bdd_experts():
-                low = run_trunk_train(e, image)                          # [B,h,w,N] NHWC fp32
+            # same-geometry experts advance layer by layer in grouped launches (one conv / BatchNorm pass for all of them)
+            lows = run_trunks_train_grouped(bdd, image) if grouped_train_supported(bdd, image) else None
+            for gi, e in enumerate(bdd):
+                low = lows[gi] if lows is not None else run_trunk_train(e, image)      # [B,h,w,N] NHWC fp32
                 out = e.format_output_train(low, H, W)
                 outs.append({k: v for k, v in out.items() if not k.startswith('_')} if isinstance(out, dict) else out)
                 h, w = low.shape[1], low.shape[2]

@@ -15,6 +15,8 @@ import torch
 import torch.nn as nn
 
 from ... import _ops
+from ..._cabi import check, ctx, lib
+from ..._ops import ptr, stream_ptr
 
 
 class ParamHolder(nn.Sequential):
@@ -172,6 +174,156 @@ def run_trunk_train(expert, image: torch.Tensor, with_head: bool = True) -> torc
     head = expert.head_module()
     h = TF.conv_bn_act(y, head[0], None, relu=True)
     return TF.conv_bn_act(h, head[2], None, relu=False)
+
+
+# ---- frozen experts in the reference's train mode, G experts in lockstep ---------------------------------------------------
+_CONST_CACHE: dict = {}
+
+
+def _const_vec(device: torch.device, n: int, value: float) -> torch.Tensor:
+    """ones / zeros [n] fp32 (identity scale / zero bias of a plain convolution), one allocation per (device, n, value)."""
+    key = (device.index, n, value)
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.full((n,), value, device=device, dtype=torch.float32)
+        _CONST_CACHE[key] = t
+    return t
+
+
+def _grouped_split_weight(convs) -> torch.Tensor:
+    """[G*Cout, KH, KW, 6, Cin] bf16: the six-term split packs (training/functional._split_weight) of G same-shape convolutions
+    back to back - the weight layout of amoe_conv2d_fwd_f32tc_grouped.  Cached on the first weight until any of them changes."""
+    from ...training import functional as TF
+    ws = [c.weight for c in convs]
+    key = tuple((w._version, w.data_ptr()) for w in ws)
+    hit = getattr(ws[0], "_amoe_split6_grouped", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    out = torch.cat([TF._split_weight(w, False) for w in ws], dim=0).contiguous()
+    try:
+        ws[0]._amoe_split6_grouped = (key, out)
+    except Exception:
+        pass
+    return out
+
+
+def grouped_train_supported(experts, image: torch.Tensor) -> bool:
+    """True when run_trunks_train_grouped takes these experts: at least two ResNet-18 experts of one geometry, frames whose
+    stage inputs stay even (every convolution behind the stem is then a split-operand tensor-core launch)."""
+    from ...training import functional as TF
+    if len(experts) < 2 or len(experts) > 4 or not TF.train_tc() or image.dim() != 4:
+        return False
+    H, W = image.shape[2], image.shape[3]
+    if H % 32 != 0 or W % 32 != 0:
+        return False
+    bb0 = experts[0].backbone
+    for e in experts:
+        bb = e.backbone
+        if any(p.requires_grad for p in e.parameters()):
+            return False
+        for li in range(4, 8):
+            if len(bb[li]) != len(bb0[li]):
+                return False
+            for blk, blk0 in zip(bb[li], bb0[li]):
+                if blk.conv1.weight.shape != blk0.conv1.weight.shape or (blk.downsample is None) != (blk0.downsample is None):
+                    return False
+                if not (blk.bn1.training and blk.bn2.training):
+                    return False
+        if e.head_module()[0].weight.shape != experts[0].head_module()[0].weight.shape:
+            return False
+    return True
+
+
+def _conv_grouped(x: torch.Tensor, convs, relu: bool = False) -> torch.Tensor:
+    """G same-shape nn.Conv2d layers on x [G,B,H,W,Cin] fp32 -> [G,B,Ho,Wo,Cout] fp32: ONE split-operand tensor-core launch
+    (csrc/conv_tc.cu, fp32-accurate); bias (+ReLU) in the epilogue when the layers have one."""
+    from ...training import functional as TF
+    G, B, H, W, Cin = x.shape
+    c0 = convs[0]
+    Cout, _, KH, KW = c0.weight.shape
+    stride, pad = c0.stride[0], c0.padding[0]
+    if not lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride):
+        raise NotImplementedError(f"grouped training convolution {Cin}->{Cout} {KH}x{KW}/s{stride} on {H}x{W}")
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    dev = x.device
+    xs, wsplit = TF._split3(x), _grouped_split_weight(convs)          # named: they outlive the launch
+    if c0.bias is not None:
+        bias = torch.cat([c.bias.detach().float() for c in convs]).contiguous()
+    else:
+        bias = _const_vec(dev, G * Cout, 0.0)
+    y = torch.empty((G, B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
+    check(lib().amoe_conv2d_fwd_f32tc_grouped(ctx(dev), ptr(xs), ptr(wsplit), ptr(_const_vec(dev, G * Cout, 1.0)), ptr(bias), None,
+                                              ptr(y), G, 0, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, int(relu),
+                                              stream_ptr(dev)), "conv2d_fwd_f32tc_grouped")
+    del xs
+    return y
+
+
+def _bn_train_grouped(x: torch.Tensor, bns, relu: bool) -> torch.Tensor:
+    """G train-mode nn.BatchNorm2d layers on x [G,B,H,W,C]: batch statistics, running statistics of every layer updated in
+    place (momentum of the layer), one launch per pass for all G (amoe_bn_train_fwd_grouped)."""
+    import ctypes as C_
+    G, B, H, W, C = x.shape
+    M = B * H * W
+    dev = x.device
+    b0 = bns[0]
+    if any(bn.momentum is None or bn.momentum != b0.momentum or bn.eps != b0.eps or not bn.track_running_stats or
+           bn.weight is None for bn in bns):
+        raise NotImplementedError("grouped BatchNorm needs affine layers with one momentum / eps and tracked running statistics")
+
+    def arr(ts):
+        for t in ts:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise RuntimeError("grouped BatchNorm takes contiguous fp32 parameters / buffers on the activation's device")
+        return (C_.c_void_p * G)(*[t.data_ptr() for t in ts])
+    y = torch.empty_like(x)
+    ws = torch.empty(G * max(1, lib().amoe_colreduce_workspace_floats(M, C)), device=dev, dtype=torch.float32)
+    mean = torch.empty(G * C, device=dev, dtype=torch.float32)
+    rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
+    check(lib().amoe_bn_train_fwd_grouped(ctx(dev), ptr(x), arr([bn.weight.detach() for bn in bns]), arr([bn.bias.detach() for bn in bns]),
+                                          arr([bn.running_mean for bn in bns]), arr([bn.running_var for bn in bns]),
+                                          float(b0.momentum), float(b0.eps), ptr(y), ptr(mean), ptr(rstd), ptr(ws), G, M, C, int(relu),
+                                          stream_ptr(dev)), "bn_train_fwd_grouped")
+    for bn in bns:      # the kernel wrote the running statistics through raw pointers
+        torch.autograd.graph.increment_version([bn.running_mean, bn.running_var])
+    return y
+
+
+def run_trunks_train_grouped(experts, image: torch.Tensor):
+    """Frozen ResNet-18 experts exactly as the reference runs them inside model.train() (training/train_gating_network.py:85:
+    batch-statistics BatchNorm, running statistics and num_batches_tracked updated) - all G experts layer by layer in
+    LOCKSTEP: behind the per-expert first layers every convolution, BatchNorm pass and residual add is one launch over
+    [G,B,H,W,C].  At 32 frames per GPU a layer3 / layer4 convolution of ONE expert has 64 / 32 output tiles for 148 SMs;
+    grouped, three experts cost little more than one.  No autograd graph (the experts are frozen); same kernels and arithmetic
+    as run_trunk_train, expert by expert.  Returns the head outputs [B,h,w,N_g] (NHWC fp32), one per expert.
+
+    torchvision ResNet._forward_impl / BasicBlock.forward (resnet.py:89-105,266-278), bdd_*_expert.py:12-24."""
+    from ...training import functional as TF
+    G = len(experts)
+    bbs = [e.backbone for e in experts]
+    tracked = []
+    with torch.no_grad():
+        x = TF.image_nhwc4(image)
+        pooled = [TF.max_pool3x3s2(TF.conv_bn_act(x, bb[0], bb[1], relu=True)) for bb in bbs]     # first layers: per expert
+        y = torch.stack(pooled, dim=0)                                                           # [G,B,H/4,W/4,64]
+        del pooled
+        for li in range(4, 8):
+            for bi in range(len(bbs[0][li])):
+                blks = [bb[li][bi] for bb in bbs]
+                out = _bn_train_grouped(_conv_grouped(y, [b.conv1 for b in blks]), [b.bn1 for b in blks], relu=True)
+                out = _bn_train_grouped(_conv_grouped(out, [b.conv2 for b in blks]), [b.bn2 for b in blks], relu=False)
+                tracked += [b.bn1 for b in blks] + [b.bn2 for b in blks]
+                if blks[0].downsample is not None:
+                    idn = _bn_train_grouped(_conv_grouped(y, [b.downsample[0] for b in blks]), [b.downsample[1] for b in blks],
+                                            relu=False)
+                    tracked += [b.downsample[1] for b in blks]
+                else:
+                    idn = y
+                y = TF.add_relu(out, idn)
+        torch._foreach_add_([bn.num_batches_tracked for bn in tracked], 1)       # what 3 x 19 BatchNorm forwards do one by one
+        heads = [e.head_module() for e in experts]
+        h = _conv_grouped(y, [hd[0] for hd in heads], relu=True)                 # 3x3 512 -> 256 + bias + ReLU
+        return [TF.conv_bn_act(h[g], heads[g][2], None, relu=False) for g in range(G)]   # 1x1 heads: one channel count each
 
 
 def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

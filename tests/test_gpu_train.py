@@ -405,6 +405,36 @@ def test_train_step_reduces_loss_and_refreshes_inference_packs():
     assert diff_path.requires_grad and rel_err(after, diff_path.detach()) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W", [(4, 64, 64), (3, 96, 160)])
+def test_grouped_frozen_expert_train_forward_equals_expert_by_expert(B, H, W):
+    """Frozen experts in the reference's train mode (batch-statistics BatchNorm, running statistics and counters updated):
+    the lockstep path - one convolution / BatchNorm launch per layer for all three experts - against the same kernels run
+    expert by expert: head outputs, running statistics and num_batches_tracked of every BatchNorm layer."""
+    from automoe_b200.models.experts._trunk import grouped_train_supported, run_trunk_train, run_trunks_train_grouped
+    ma, _ = build_b200_model(DEV, "fp32")
+    mb, _ = build_b200_model(DEV, "fp32")
+    for m in (ma, mb):
+        m.freeze_experts()
+        m.train()
+    img = torch.randn((B, 3, H, W), generator=_gen(50)).to(DEV)
+    ea, eb = ma._bdd_experts(), mb._bdd_experts()
+    assert grouped_train_supported(eb, img)
+    for _ in range(2):                               # two steps: the running statistics accumulate
+        with torch.no_grad():
+            ref = [run_trunk_train(e, img) for e in ea]
+        got = run_trunks_train_grouped(eb, img)
+    for r, g in zip(ref, got):
+        assert r.shape == g.shape and rel_err(g, r) < 1e-6, rel_err(g, r)
+    sa, sb = dict(ma.experts.named_buffers()), dict(mb.experts.named_buffers())
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) == 2, k
+        else:
+            assert rel_err(sb[k], sa[k]) < 1e-6, (k, rel_err(sb[k], sa[k]))
+    assert not grouped_train_supported(eb, torch.zeros((2, 3, 90, 122), device=DEV))      # odd stage sizes: expert by expert
+
+
 def _graph_models():
     from automoe_b200.training.train_gating_network import FlatAdamW, freeze_for_gating_training
     out = []

@@ -12,13 +12,14 @@ sys.path.insert(0, str(ROOT))
 def main():
     import bench
     import bench_train as BT
-    mode = sys.argv[1] if len(sys.argv) > 1 else "gating"
+    argv = [a for a in sys.argv if not a.startswith("--")]
+    mode = argv[1] if len(argv) > 1 else "gating"
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     if mode.startswith("gating"):
         from automoe_b200.models.automoe import create_automoe_model
         from automoe_b200.training.train_gating_network import FlatAdamW, freeze_for_gating_training, train_step
-        B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+        B = int(argv[2]) if len(argv) > 2 else 32
         model = create_automoe_model(bench.model_config(), "cpu")
         bench.randomize_norm_stats(model)
         model = model.to(dev)
@@ -37,7 +38,7 @@ def main():
         from automoe_b200.training.hungarian_matcher import HungarianMatcher
         from automoe_b200.training.train_bdd100k import train_detection_batch
         from automoe_b200.training.train_gating_network import FlatAdamW
-        B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+        B = int(argv[2]) if len(argv) > 2 else 8
         model = BDDDetectionExpert(num_classes=10, pretrained_backbone=False).to(dev).train()
         opt = FlatAdamW(list(model.parameters()), lr=1e-4, weight_decay=1e-4, max_norm=1.0)
         matcher = HungarianMatcher()
@@ -67,6 +68,11 @@ def main():
             detail.setdefault(e.name[:60], []).append(round(e.device_time))
     for name, ts in detail.items():      # per-launch times (us) of the CUDA-core convolutions, in launch order, last profiled step
         print(f"#   {name}: {ts[-(len(ts) // 3):]}")
+    if "--trace" in sys.argv:            # every kernel of the last profiled step in launch order (us)
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        evs = evs[-(len(evs) // 3):]
+        for e in evs:
+            print(f"T {e.device_time:8.1f}  {e.name[:90]}")
     tot = sum(v[0] for v in rows.values())
     print(f"# {mode}: {tot / 3 / 1e3:.2f} ms of kernel time per step")
     for name, (t, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:28]:
