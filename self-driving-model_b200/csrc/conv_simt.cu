@@ -70,8 +70,10 @@ __global__ __launch_bounds__(256) void conv2d_simt_kernel(ConvSimtParams p) {
     __syncthreads();
   }
 
-  for (int kk0 = 0; kk0 < Ktot; kk0 += SBK) {
-    float a[4], b[4];
+  // Software pipeline: the operands of k-block i+1 are loaded into registers before the FMAs of block i, so the gather latency
+  // overlaps the arithmetic instead of sitting between the two barriers.  Same elements, same accumulation order.
+  float a[4], b[4];
+  auto fetch = [&](int kk0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int kk = kk0 + lk + j;
@@ -95,12 +97,16 @@ __global__ __launch_bounds__(256) void conv2d_simt_kernel(ConvSimtParams p) {
       a[j] = av;
       b[j] = bv;
     }
+  };
+  fetch(0);
+  for (int kk0 = 0; kk0 < Ktot; kk0 += SBK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       As[lk + j][lrow] = a[j];
       Bs[lk + j][lrow] = b[j];
     }
     __syncthreads();
+    if (kk0 + SBK < Ktot) fetch(kk0 + SBK);
 #pragma unroll
     for (int k = 0; k < SBK; ++k) {
       float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);

@@ -291,7 +291,10 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
   }
   const bool pow2 = (p.sh == 1 || p.sh == 2) && (p.sw == 1 || p.sw == 2);
   const int shh = p.sh - 1, sww = p.sw - 1;   // shift amounts / parity masks when pow2
-  for (int k0 = 0; k0 < Ktot; k0 += TBK) {
+  // Software pipeline (as in conv_bwd_weight_kernel): operands of k-block i+1 go to registers before the FMAs of block i.
+  constexpr int B_PER = TBK * TBN / 256;
+  float a_reg[4], b_reg[B_PER];
+  auto fetch = [&](int k0) {
     // A: this thread's pixel, 4 consecutive k (one 16-byte load when Cout % 4 == 0: same tap, aligned)
     if ((p.Cout & 3) == 0) {
       const int k = k0 + lk;
@@ -307,7 +310,7 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
             a = *reinterpret_cast<const float4*>(p.dy + (((int64_t)n_img * p.Ho + oh) * p.Wo + ow) * p.Cout + co);
         }
       }
-      As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
+      a_reg[0] = a.x; a_reg[1] = a.y; a_reg[2] = a.z; a_reg[3] = a.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -322,11 +325,13 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
             if (oh < p.Ho && ow < p.Wo) a = p.dy[(((int64_t)n_img * p.Ho + oh) * p.Wo + ow) * p.Cout + co];
           }
         }
-        As[lk + j][lrow] = a;
+        a_reg[j] = a;
       }
     }
     // B: 16 k x 64 ci; element (k, ci) = w[co][tap][ci]; consecutive threads walk ci
-    for (int e = tid; e < TBK * TBN; e += 256) {
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + i * 256;
       const int kk = e / TBN, c = e - kk * TBN;
       const int k = k0 + kk, ci = n0 + c;
       float v = 0.f;
@@ -336,9 +341,20 @@ __global__ __launch_bounds__(256) void conv_bwd_data_kernel(ConvBwdParams p) {
         else { tap = k / p.Cout; co = k - tap * p.Cout; }
         v = p.w[(int64_t)co * Kw + tap * p.Cin + ci];
       }
-      Bs[kk][c] = v;
+      b_reg[i] = v;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < Ktot; k0 += TBK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[lk + j][lrow] = a_reg[j];
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + i * 256;
+      Bs[e / TBN][e % TBN] = b_reg[i];
     }
     __syncthreads();
+    if (k0 + TBK < Ktot) fetch(k0 + TBK);
 #pragma unroll
     for (int k = 0; k < TBK; ++k) {
       // one 16-byte shared-memory load per operand (rows are 16-byte aligned: pitch TBM + 4 floats)
