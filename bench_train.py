@@ -223,7 +223,7 @@ def _gating(args, dev, world, rank, dist, barrier, steps, warmup, sampler, pk, m
                                                            "eager_ms_per_step": ms_fast16,
                                                            "note": "frozen experts through the tcgen05 inference kernels; trainable part fp32"}},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                     "traffic": None, "kernel": "fp32 CUDA-core training kernels (conv2d_simt / sgemm): parity-first, not tensor-core yet",
+                     "traffic": None, "kernel": "fp32-accurate split-operand tcgen05 convolutions (conv_tc_kernel: six bf16 MMAs per fp32 MAC, so the bf16 peak overstates the reachable rate 6x) + CUDA-core remainder (policy first layers, stride-2 weight gradients, small-batch MLP GEMMs)",
                      "algorithmic_gflop_per_frame": GFLOP_GATING_PER_FRAME},
         "cpu_baseline": None, "gpu_reference": gref,
     }
@@ -322,7 +322,7 @@ def _detection(args, dev, world, rank, dist, barrier, steps, warmup, sampler, pk
         "gpu_launches": launches, "clocks": clocks,
         "allreduce": {"bytes": 12360014 * 4, "us": ar_us, "share_of_step": ar_us / 1e3 / ms},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                     "traffic": None, "kernel": "fp32 CUDA-core training kernels (conv2d_simt fwd / dgrad / wgrad): parity-first, not tensor-core yet",
+                     "traffic": None, "kernel": "fp32-accurate split-operand tcgen05 convolutions (conv_tc_kernel fwd / dgrad, wgrad_tc_kernel: six bf16 MMAs per fp32 MAC, so the bf16 peak overstates the reachable rate 6x) + CUDA-core remainder (720p stem, stride-2 weight gradients, odd-height stride-2 layers)",
                      "algorithmic_gflop_per_image": GFLOP_DET_PER_IMAGE * (H * W) / (720 * 1280)},
         "cpu_baseline": None, "gpu_reference": gref,
     }

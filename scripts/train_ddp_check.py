@@ -97,6 +97,9 @@ def main():
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     # ---- (4) the same step captured as one CUDA graph (all-reduce and buffer broadcast inside): replicas stay identical ----
     from automoe_b200.training.train_gating_network import GraphedTrainStep
+    import gc
+    del losses, l2          # autograd graphs of the eager checks above: their AccumulateGrad nodes sit on the default stream
+    gc.collect()
     graphed = GraphedTrainStep(m, b32, opt, {})
     for _ in range(3):
         graphed(b32)
@@ -117,6 +120,9 @@ def main():
                "train_step_ms_b32_per_gpu": ms.item(), "frames_per_s": world * 32 / (ms.item() / 1e3),
                "graphed_step_ms_b32_per_gpu": ms_g.item(), "graphed_frames_per_s": world * 32 / (ms_g.item() / 1e3),
                "graphed_params_and_buffers_identical_across_ranks": same_g}, flush=True)
+    del graphed             # the captured graph holds the NCCL communicator: release it before the process group goes away
+    gc.collect()
+    torch.cuda.synchronize()
     ok = torch.tensor([int(same and same_g and err < 1e-4)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

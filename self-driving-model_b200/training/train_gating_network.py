@@ -206,6 +206,7 @@ class GraphedTrainStep:
     packs, allocator, NCCL) and then restores parameters, moments, module buffers and counters, so building the graph leaves
     the training state untouched.  Inputs are copied into static buffers per call; the returned loss dict aliases static
     device tensors (overwritten by the next call).  Shapes and the module's train/eval flags are fixed at capture time.
+    Autograd graphs of earlier eager steps must be released before construction (see the error raised when capture fails).
     """
 
     def __init__(self, model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, config: Dict, warmup: int = 3,
@@ -230,8 +231,15 @@ class GraphedTrainStep:
         torch.autograd.graph.increment_version(list(self.static_in.values()))
         self.graph = torch.cuda.CUDAGraph()
         n0 = launch_count(dev)
-        with torch.cuda.graph(self.graph):
-            self.losses = self._eager()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.losses = self._eager()
+        except Exception as e:
+            raise RuntimeError(
+                "GraphedTrainStep: capturing the training step failed.  The usual cause is an autograd graph of an EARLIER eager "
+                "step that is still alive (a kept loss / prediction tensor): its AccumulateGrad nodes stay bound to the stream "
+                "they were created on, and the captured backward may not synchronise with the legacy default stream.  Drop those "
+                "references (del loss, pred; gc.collect()) before building the graph.") from e
         self.launches_per_replay = launch_count(dev) - n0
         with torch.no_grad():                       # nothing of the above counts as training
             for t, s in zip((optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer._step_dev,
