@@ -377,6 +377,44 @@ def hbm_legs(model, dev, B, pk):
 
 
 # ------------------------------------------------------------------ the headline arm
+def latency_leg(model, dev, batches=(1, 64), reps=60):
+    """Host wall-clock time of one inference tick through the module API at small batch: pinned uint8 camera frame(s) in,
+    H2D copy, device staging, AutoMoE.capture() replay, waypoints / speed / expert weights back on the host, synchronised -
+    what the reference's control loop waits for per frame (inference/run_automoe.py:34-53,253).  Median and p90 over `reps`."""
+    out = {}
+    for b in batches:
+        pinned = {k: v.pin_memory() for k, v in host_batch_u8(b, 500 + b).items()}
+        slot = {k: torch.empty_like(v, device=dev) for k, v in pinned.items()}
+        res = [torch.empty((b, 10, 2)).pin_memory(), torch.empty((b, 1)).pin_memory(), torch.empty((b, 3)).pin_memory()]
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            model(slot)
+        torch.cuda.synchronize()
+        g = model.capture(slot, clone_inputs=False)
+
+        def tick():
+            for k, v in pinned.items():
+                slot[k].copy_(v, non_blocking=True)
+            o = g()
+            res[0].copy_(o["waypoints"], non_blocking=True)
+            res[1].copy_(o["speed"], non_blocking=True)
+            res[2].copy_(o["expert_weights"], non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(10):
+            tick()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            tick()
+            ts.append((time.perf_counter() - t) * 1e3)
+        ts.sort()
+        out[f"b{b}"] = {"latency_ms_median": ts[len(ts) // 2], "latency_ms_p90": ts[int(len(ts) * 0.9)],
+                        "frames_per_s": b / (ts[len(ts) // 2] / 1e3), "launches_per_tick": g.launches_per_replay}
+        del g
+    out["what"] = ("host wall clock per tick, synchronised: pinned uint8 frame(s) -> H2D -> staging -> CUDA-graph replay -> "
+                   "waypoints/speed/expert_weights on the host; bf16; compare cpu_baseline.b1 / .b64")
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -543,6 +581,11 @@ def run_b200(args):
                "numa": numa}
         del pinned, slots
 
+    # ---------------- latency of ONE control tick (BASELINE configs[0] is batch 1: the shape inference/run_automoe.py runs) ----------------
+    latency = None
+    if rank == 0 and world == 1 and not args.no_legs and not args.no_e2e:
+        latency = latency_leg(model, dev)
+
     # ---------------- roofline of the dominant kernels (tcgen05 convs), measured live ----------------
     pk = peaks()
     roof = None
@@ -615,6 +658,7 @@ def run_b200(args):
                        "preheat_s": args.preheat, "preheat_steps": heat_steps, "replay_equals_eager_checked": replay_checked,
                        "l2_chunk_images": _ops.l2_chunk_images(), "side_stream_outputs": _ops.overlap_outputs()},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gref,
+            "latency": latency,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
