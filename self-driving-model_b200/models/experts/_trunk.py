@@ -326,6 +326,33 @@ def run_trunks_train_grouped(experts, image: torch.Tensor):
         return [TF.conv_bn_act(h[g], heads[g][2], None, relu=False) for g in range(G)]   # 1x1 heads: one channel count each
 
 
+def _stem_f32_tc(pack: TrunkPack, stem, x_nhwc: torch.Tensor, B: int, H: int, W: int) -> Optional[torch.Tensor]:
+    """fp32 (parity) mode: the Cin = 3 first layers of all experts fp32-accurate on the tensor cores - the Toeplitz GEMM with
+    three-way split operands the training forward uses (stem_tc_f32_kernel, csrc/stem_tc.cu; 2.5-3.2e-7 against fp64), with the
+    folded BatchNorm scale / bias and the ReLU in its epilogue.  One launch per expert on one shared split frame.  Returns
+    [G*B,H/2,W/2,Cout] fp32, or None for shapes the kernel does not take (the CUDA-core convolution then runs: 1.6 ms for three
+    experts at 32 frames against 3 x 0.1 ms)."""
+    from ...training import functional as TF
+    convs = pack.stem_src[0]
+    c0 = convs[0]
+    Cout, Cin, KH, KW = c0.weight.shape
+    if pack.dtype != torch.float32 or not _ops.f32_tc() or x_nhwc.dtype != torch.float32 or x_nhwc.dim() != 4 or x_nhwc.shape[-1] != 4:
+        return None
+    if c0.stride[0] != c0.stride[1] or c0.padding[0] != c0.padding[1] or \
+            not TF._stem_tc_ok(4, Cin, Cout, KH, KW, c0.stride[0], c0.padding[0], H, W):
+        return None
+    dev = x_nhwc.device
+    Ho, Wo = (H + 2 * c0.padding[0] - KH) // 2 + 1, (W + 2 * c0.padding[0] - KW) // 2 + 1
+    xs = TF._stem_split_frame(x_nhwc.contiguous())                       # named: read by every launch below
+    y = torch.empty((len(convs) * B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
+    for g, conv in enumerate(convs):
+        ws = TF._stem_split_weight(conv.weight, conv.padding[0])
+        check(lib().amoe_stem_fwd_f32tc(ctx(dev), ptr(xs), ptr(ws), ptr(stem.scale[g * Cout:]), ptr(stem.bias[g * Cout:]),
+                                        ptr(y[g * B:]), B, H, W, xs.shape[2], _ops.STEM_KH, Cout, int(stem.relu), stream_ptr(dev)),
+              "stem_fwd_f32tc")
+    return y
+
+
 def stage_image(image: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCHW fp32 frame -> the NHWC layout the first convolutions read (see _ops.stem_mode): the
     physically padded bf16 frame of the tensor-core stem, padded rows for the row-window variant, or
@@ -429,7 +456,9 @@ def run_trunks(pack: TrunkPack, image: torch.Tensor, x_nhwc: Optional[torch.Tens
         elif isinstance(stem, _ops.PackedRowwin):
             y = _ops.conv2d_rowwin(stem, x_nhwc, B, H, W)
         else:
-            y = _ops.conv2d(stem, x_nhwc, B, H, W, x_shared=True)
+            y = _stem_f32_tc(pack, stem, x_nhwc, B, H, W)                  # fp32 mode: split-operand Toeplitz GEMM when it applies
+            if y is None:
+                y = _ops.conv2d(stem, x_nhwc, B, H, W, x_shared=True)
     # Activations of the 64/128-channel stages live in a physically padded layout (zero border of one
     # pixel) when their 3x3/s1 convolutions run through the halo-reuse kernel; `pad` tracks the layout.
     flat_ok = pack.dtype == torch.bfloat16 and _ops.use_flat()
