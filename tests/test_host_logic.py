@@ -136,3 +136,32 @@ def test_stem_mode_follows_geometry(monkeypatch):
     assert _ops.stem_mode(torch.float32, 256, 256) == "simt"
     monkeypatch.setenv("AMOE_STEM", "rowwin")
     assert _ops.stem_mode(torch.bfloat16, 256, 256) == "rowwin"
+
+
+def test_grouped_train_forward_selection(model):
+    """Which frozen-expert train-mode forwards take the lockstep (grouped) path: same-geometry frozen ResNet-18 experts in
+    train mode on frames whose stage inputs stay even; anything else runs expert by expert (host logic only)."""
+    import copy
+    from automoe_b200.models.experts._trunk import grouped_train_supported
+    m = copy.deepcopy(model)
+    m.freeze_experts()
+    m.train()
+    ex = m._bdd_experts()
+    assert grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))
+    assert grouped_train_supported(ex, torch.zeros(2, 3, 96, 160))
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 90, 122))        # odd stage sizes
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 720, 1280))      # 720 / 16 = 45 rows into layer4
+    assert not grouped_train_supported(ex[:1], torch.zeros(2, 3, 256, 256))   # one expert: nothing to group
+    ex[1].backbone[5][0].bn1.eval()
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # a BatchNorm on running statistics
+    ex[1].backbone[5][0].bn1.train()
+    next(ex[2].parameters()).requires_grad_(True)
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # an expert that trains needs the autograd path
+
+
+def test_graphed_train_step_and_device_counters_need_cuda():
+    """No CPU fallback: the flat optimizer (and with it the graphed step) refuses CPU parameters."""
+    from automoe_b200.training.train_gating_network import FlatAdamW
+    lin = torch.nn.Linear(4, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FlatAdamW(lin.parameters())
