@@ -304,6 +304,17 @@ def _stem_split_frame(x2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _even_size(H: int, W: int, KH: int, KW: int, stride: int, padding: int, Ho: int, Wo: int) -> Tuple[int, int]:
+    """(H, W) rounded up to even for a stride-2 convolution when that leaves the output size unchanged (3x3/p1, 1x1/p0, ...):
+    the extra zero row / column only stands where the zero padding already is."""
+    if stride != 2:
+        return H, W
+    Hk, Wk = H + (H & 1), W + (W & 1)
+    if (Hk + 2 * padding - KH) // 2 + 1 != Ho or (Wk + 2 * padding - KW) // 2 + 1 != Wo:
+        return H, W
+    return Hk, Wk
+
+
 class _ConvBNAct(torch.autograd.Function):
     """nn.Conv2d(stride, padding, bias?) [-> nn.BatchNorm2d] [-> nn.ReLU] on NHWC fp32 activations.
 
@@ -324,6 +335,13 @@ class _ConvBNAct(torch.autograd.Function):
         conv = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.float32)
         fuse_relu = int(relu and bn_mode == BN_NONE)
         use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(H, W, Cin, Cout, KH, KW, stride))
+        # Stride 2 on an odd height / width (720p detection: 45 rows into layer4): the tensor-core kernels take even sizes, and
+        # one appended zero row / column is exactly what the zero padding supplies there - same output, same gradient
+        Hk, Wk = _even_size(H, W, KH, KW, stride, padding, Ho, Wo)
+        if not use_tc and (Hk, Wk) != (H, W):
+            use_tc = train_tc() and Cx == Cin and bool(lib().amoe_conv2d_f32tc_supported(Hk, Wk, Cin, Cout, KH, KW, stride))
+        if not use_tc:
+            Hk, Wk = H, W
         # (first layers whose weight is trained stay on the CUDA-core kernel: the gradient goldens of the policy backbone are
         # held to 5e-4 and move by 8e-4 with the - more accurate - tensor-core forward: ReLU units within rounding of zero)
         use_stem = (not use_tc) and (not ctx_.needs_input_grad[1]) and _stem_tc_ok(Cx, Cin, Cout, KH, KW, stride, padding, H, W)
@@ -334,9 +352,11 @@ class _ConvBNAct(torch.autograd.Function):
             check(lib().amoe_stem_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv), B, H, W, xs.shape[2],
                                             _ops.STEM_KH, Cout, fuse_relu, st), "stem_fwd_f32tc")
         elif use_tc:
-            xs, wsplit = _split3(x2), _split_weight(weight, False)     # named: they must outlive the launch that reads them
+            xin = x2 if (Hk, Wk) == (H, W) else torch.nn.functional.pad(x2, (0, 0, 0, Wk - W, 0, Hk - H))
+            xs, wsplit = _split3(xin), _split_weight(weight, False)    # named: they must outlive the launch that reads them
             check(lib().amoe_conv2d_fwd_f32tc(h, ptr(xs), ptr(wsplit), ptr(ones), ptr(cb), ptr(conv),
-                                              B, H, W, Cin, Cout, KH, KW, stride, padding, Ho, Wo, fuse_relu, st), "conv2d_fwd_f32tc")
+                                              B, Hk, Wk, Cin, Cout, KH, KW, stride, padding, Ho, Wo, fuse_relu, st), "conv2d_fwd_f32tc")
+            del xin
             del xs
         else:
             check(lib().amoe_conv2d_fwd(h, ptr(x2), ptr(wp), ptr(ones), ptr(cb), None, ptr(conv), 1, 0, B, H, W, Cx, Cout, KH, KW,
@@ -431,17 +451,20 @@ class _ConvBNAct(torch.autograd.Function):
         dx = None
         if ctx_.needs_input_grad[0]:
             # dgrad on the tensor cores: roles swap (input = dy with Cout channels, output channels = Cin)
+            Hk, Wk = _even_size(H, W, KH, KW, stride, padding, Ho, Wo)          # odd sizes: one zero row / column appended
             tc_ok = (w_ref is not None and Cout % 64 == 0 and Cx % 32 == 0 and (Cx <= 256 or Cx % 256 == 0) and
-                     KH * KW * 6 <= 64 and (stride == 1 or (stride == 2 and H % 2 == 0 and W % 2 == 0)))
+                     KH * KW * 6 <= 64 and (stride == 1 or (stride == 2 and Hk % 2 == 0 and Wk % 2 == 0)))
             if tc_ok:
                 holes = stride == 2 and (KH < 2 or KW < 2)         # 1x1 / stride 2: three of four parity classes get no tap
-                dx = (torch.zeros_like if holes else torch.empty_like)(x2)
+                dx = (torch.zeros if holes else torch.empty)((B, Hk, Wk, Cx), device=dev, dtype=torch.float32)
                 ones_i = torch.ones(Cx, device=dev, dtype=torch.float32)
                 zeros_i = torch.zeros(Cx, device=dev, dtype=torch.float32)
                 dys, wts = _split3(dconv), _split_weight(w_ref, True)  # named: they must outlive the launches that read them
-                check(lib().amoe_conv2d_bwd_data_f32tc(h, ptr(dys), ptr(wts), ptr(ones_i), ptr(zeros_i), ptr(dx), B, H, W, Cx, Cout,
+                check(lib().amoe_conv2d_bwd_data_f32tc(h, ptr(dys), ptr(wts), ptr(ones_i), ptr(zeros_i), ptr(dx), B, Hk, Wk, Cx, Cout,
                                                        KH, KW, stride, padding, Ho, Wo, st), "conv2d_bwd_data_f32tc")
                 del dys
+                if (Hk, Wk) != (H, W):
+                    dx = dx[:, :H, :W, :].contiguous()              # the appended row / column is not an input: its gradient is dropped
             else:
                 dx = torch.empty_like(x2)
                 wpk = packed_w()

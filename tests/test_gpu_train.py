@@ -546,7 +546,8 @@ def test_first_layer_tensor_core_conv_is_fp32_accurate(B, H, W, Cout, K, pad, bi
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,K,stride,pad", [
     (2, 16, 16, 64, 64, 3, 1, 1), (3, 14, 18, 64, 128, 3, 2, 1), (2, 16, 12, 128, 128, 1, 2, 0), (1, 8, 8, 256, 512, 3, 1, 1),
-    (2, 8, 8, 512, 256, 3, 1, 1), (2, 23, 40, 128, 32, 3, 1, 1), (2, 10, 10, 64, 64, 1, 1, 0)])
+    (2, 8, 8, 512, 256, 3, 1, 1), (2, 23, 40, 128, 32, 3, 1, 1), (2, 10, 10, 64, 64, 1, 1, 0),
+    (2, 45, 80, 256, 512, 3, 2, 1), (2, 45, 80, 256, 512, 1, 2, 0), (1, 13, 11, 64, 64, 3, 2, 1)])     # odd sizes at stride 2 (720p layer4)
 def test_split_operand_tensor_core_conv_is_fp32_accurate(B, H, W, Cin, Cout, K, stride, pad, monkeypatch):
     """fp32-accurate convolution on the bf16 tensor cores (three-way operand split, six product terms, fp32 TMEM
     accumulation): forward and data gradient against an fp64 evaluation, within 1e-5 relative (max-norm) - the tensor core
