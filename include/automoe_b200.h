@@ -487,6 +487,11 @@ int amoe_gap_bwd(amoe_ctx*, const float* dy, float* dx, int B, int HW, int C, vo
  * Arg-max rule of torch (first strictly greater element in kh-major scan order). */
 int amoe_maxpool3x3s2_bwd(amoe_ctx*, const float* x, const float* dy, float* dx, int NB, int H,
                           int W, int C, void* stream);
+/* The same gradient in two passes through a caller-owned workspace of NB*Ho*Wo*C bytes (Ho = (H-1)/2+1): the arg-max tap of
+ * every window, then one comparison per (input pixel, containing window).  Bit-identical to amoe_maxpool3x3s2_bwd, 5x fewer
+ * loads (torchvision resnet.py:199 maxpool inside training/train_bdd100k_ddp.py:117-186). */
+int amoe_maxpool3x3s2_bwd_ws(amoe_ctx*, const float* x, const float* dy, float* dx, void* argmax_ws, int NB,
+                             int H, int W, int C, void* stream);
 /* BasicBlock tail: y = relu(a + b) (n % 4 == 0); g = dy * [y > 0] (the gradient of both addends). */
 int amoe_add_relu_fwd(amoe_ctx*, const float* a, const float* b, float* y, int64_t n, void* stream);
 int amoe_relu_bwd(amoe_ctx*, const float* dy, const float* y, float* g, int64_t n, void* stream);

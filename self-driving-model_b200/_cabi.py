@@ -104,6 +104,7 @@ SIGNATURES = {
     "amoe_gap_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     # detection-expert training step
     "amoe_maxpool3x3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "amoe_maxpool3x3s2_bwd_ws": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "amoe_add_relu_fwd": (_I, [_P, _P, _P, _P, _L, _P]),
     "amoe_relu_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
     "amoe_upsample_bilinear_nchw_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -519,8 +519,9 @@ class _MaxPool3x3s2(torch.autograd.Function):
         dy = _f32c(dy)
         B, H, W, Cc = x2.shape
         dx = torch.empty_like(x2)
-        check(lib().amoe_maxpool3x3s2_bwd(ctx(x2.device), ptr(x2), ptr(dy), ptr(dx), B, H, W, Cc, stream_ptr(x2.device)),
-              "maxpool3x3s2_bwd")
+        ws = torch.empty(dy.shape, device=x2.device, dtype=torch.uint8)      # arg-max tap of every pooling window
+        check(lib().amoe_maxpool3x3s2_bwd_ws(ctx(x2.device), ptr(x2), ptr(dy), ptr(dx), ptr(ws), B, H, W, Cc, stream_ptr(x2.device)),
+              "maxpool3x3s2_bwd_ws")
         return dx
 
 

@@ -25,7 +25,7 @@ def _gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 7, 9, 64), (3, 8, 6, 4), (2, 1, 1, 8)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 7, 9, 64), (3, 8, 6, 4), (2, 1, 1, 8), (2, 45, 80, 64), (1, 2, 3, 4)])
 def test_maxpool_fwd_bwd_including_ties(shape):
     from automoe_b200.training import functional as TF
     B, H, W, C = shape
@@ -40,6 +40,13 @@ def test_maxpool_fwd_bwd_including_ties(shape):
     yr.backward(dy.permute(0, 3, 1, 2))
     assert torch.equal(y.detach().permute(0, 3, 1, 2), yr.detach())
     assert rel_err(x.grad.permute(0, 3, 1, 2), xr.grad) < 1e-6     # tie routing identical to torch
+    # the one-pass kernel (window rescan per input pixel) and the two-pass one (arg-max taps, then comparisons) agree bit for bit
+    from automoe_b200._cabi import check, ctx, lib
+    from automoe_b200._ops import ptr, stream_ptr
+    dev = torch.device(DEV)
+    xd, dx1 = x.detach().contiguous(), torch.empty_like(x.detach())
+    check(lib().amoe_maxpool3x3s2_bwd(ctx(dev), ptr(xd), ptr(dy), ptr(dx1), B, H, W, C, stream_ptr(dev)), "maxpool3x3s2_bwd")
+    assert torch.equal(dx1, x.grad)
 
 
 def test_add_relu_fwd_bwd():
