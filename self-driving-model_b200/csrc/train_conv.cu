@@ -236,37 +236,51 @@ __global__ __launch_bounds__(256) void bn_apply_grouped_kernel(const float* __re
 }
 
 // train: dx = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M);  eval (batch_stats = 0): dx = gamma*rstd*g
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sum_g,
-                                    const float* __restrict__ sum_gx, float* __restrict__ dx, int64_t n4, int C,
-                                    float inv_M, int batch_stats) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)((i * 4) % C);
-  const float4 d4 = reinterpret_cast<const float4*>(dy)[i];
-  const float4 x4 = reinterpret_cast<const float4*>(x)[i];
-  float g[4] = {d4.x, d4.y, d4.z, d4.w};
-  const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-  if (y) {
-    const float4 y4 = reinterpret_cast<const float4*>(y)[i];
-    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+// (two 16-byte elements per thread and all loads first, as in bn_apply_kernel: up to six independent loads in flight)
+constexpr int BN_BWD_PER = 2;
+__global__ __launch_bounds__(256) void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                                           float* __restrict__ dx, int64_t n4, int C, float inv_M,
+                                                           int batch_stats) {
+  const int64_t i0 = (int64_t)blockIdx.x * (256 * BN_BWD_PER) + threadIdx.x;
+  float4 d4[BN_BWD_PER], x4[BN_BWD_PER], y4[BN_BWD_PER];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (!(yv[j] > 0.f)) g[j] = 0.f;
-  }
-  float o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float k = gamma[c + j] * rstd[c + j];
-    if (batch_stats) {
-      const float xh = (xv[j] - mean[c + j]) * rstd[c + j];
-      o[j] = k * (g[j] - sum_g[c + j] * inv_M - xh * sum_gx[c + j] * inv_M);
-    } else {
-      o[j] = k * g[j];
+  for (int u = 0; u < BN_BWD_PER; ++u) {
+    const int64_t i = i0 + u * 256;
+    if (i < n4) {
+      d4[u] = reinterpret_cast<const float4*>(dy)[i];
+      x4[u] = reinterpret_cast<const float4*>(x)[i];
+      if (y) y4[u] = reinterpret_cast<const float4*>(y)[i];
     }
   }
-  reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+  for (int u = 0; u < BN_BWD_PER; ++u) {
+    const int64_t i = i0 + u * 256;
+    if (i >= n4) continue;
+    const int c = (int)((i * 4) % C);
+    float g[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+    const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+    if (y) {
+      const float yv[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(yv[j] > 0.f)) g[j] = 0.f;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float k = gamma[c + j] * rstd[c + j];
+      if (batch_stats) {
+        const float xh = (xv[j] - mean[c + j]) * rstd[c + j];
+        o[j] = k * (g[j] - sum_g[c + j] * inv_M - xh * sum_gx[c + j] * inv_M);
+      } else {
+        o[j] = k * g[j];
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -637,7 +651,7 @@ int amoe_bn_bwd(amoe_ctx* ctx, const float* dy, const float* x, const float* y_r
   AMOE_LAUNCH_OK(ctx);
   if (dx) {
     const int64_t n4 = M * C / 4;
-    bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dy, x, y_relu, mean, rstd, gamma, dbeta, dgamma, dx, n4,
+    bn_bwd_apply_kernel<<<(unsigned)((n4 + 256 * BN_BWD_PER - 1) / (256 * BN_BWD_PER)), 256, 0, st>>>(dy, x, y_relu, mean, rstd, gamma, dbeta, dgamma, dx, n4,
                                                                     C, 1.f / (float)M, batch_stats);
     AMOE_LAUNCH_OK(ctx);
   }
