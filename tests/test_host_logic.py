@@ -165,3 +165,21 @@ def test_graphed_train_step_and_device_counters_need_cuda():
     lin = torch.nn.Linear(4, 4)
     with pytest.raises(RuntimeError, match="no CPU path"):
         FlatAdamW(lin.parameters())
+
+
+def test_even_size_rule_for_stride2_training_convs():
+    """Stride-2 training convolutions on odd sizes run on the tensor cores with one zero row / column appended - only where the
+    output size stays what nn.Conv2d gives (the extra row then stands where the zero padding is)."""
+    import torch.nn.functional as F
+    from automoe_b200.training.functional import _even_size
+    for (H, W, K, p) in [(45, 80, 3, 1), (45, 80, 1, 0), (13, 11, 3, 1), (45, 81, 7, 3), (9, 9, 5, 2), (44, 80, 3, 1)]:
+        Ho, Wo = (H + 2 * p - K) // 2 + 1, (W + 2 * p - K) // 2 + 1
+        Hk, Wk = _even_size(H, W, K, K, 2, p, Ho, Wo)
+        assert Hk % 2 == 0 and Wk % 2 == 0 and Hk - H in (0, 1) and Wk - W in (0, 1)
+        x = torch.randn(1, 2, H, W)
+        w = torch.randn(3, 2, K, K)
+        ref = F.conv2d(x, w, None, 2, p)
+        padded = F.conv2d(F.pad(x, (0, Wk - W, 0, Hk - H)), w, None, 2, p)
+        assert ref.shape == padded.shape == (1, 3, Ho, Wo) and torch.allclose(ref, padded, atol=1e-5)
+    assert _even_size(45, 80, 3, 3, 1, 1, 45, 80) == (45, 80)           # stride 1: untouched
+    assert _even_size(45, 80, 2, 2, 2, 0, 22, 40) == (45, 80)           # 2x2/s2/p0: one more row would add an output row
