@@ -217,17 +217,22 @@ def grouped_train_supported(experts, image: torch.Tensor) -> bool:
     if H % 32 != 0 or W % 32 != 0:
         return False
     bb0 = experts[0].backbone
+    bn0 = bb0[1]
     for e in experts:
         bb = e.backbone
         if any(p.requires_grad for p in e.parameters()):
             return False
+        # every BatchNorm of the trunk on batch statistics, affine, tracked, one momentum / eps: what the grouped passes compute
+        # (anything else - a layer left in eval mode, momentum=None - keeps the layer-by-layer path that reads each module's flags)
+        for m in bb.modules():
+            if isinstance(m, nn.BatchNorm2d) and not (m.training and m.affine and m.track_running_stats and m.momentum is not None
+                                                      and m.momentum == bn0.momentum and m.eps == bn0.eps):
+                return False
         for li in range(4, 8):
             if len(bb[li]) != len(bb0[li]):
                 return False
             for blk, blk0 in zip(bb[li], bb0[li]):
                 if blk.conv1.weight.shape != blk0.conv1.weight.shape or (blk.downsample is None) != (blk0.downsample is None):
-                    return False
-                if not (blk.bn1.training and blk.bn2.training):
                     return False
         if e.head_module()[0].weight.shape != experts[0].head_module()[0].weight.shape:
             return False

@@ -155,6 +155,13 @@ def test_grouped_train_forward_selection(model):
     ex[1].backbone[5][0].bn1.eval()
     assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # a BatchNorm on running statistics
     ex[1].backbone[5][0].bn1.train()
+    ex[0].backbone[6][0].downsample[1].eval()
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # ... also a downsample BatchNorm
+    ex[0].backbone[6][0].downsample[1].train()
+    ex[2].backbone[7][1].bn2.momentum = None
+    assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # cumulative average: not what the grouped pass computes
+    ex[2].backbone[7][1].bn2.momentum = 0.1
+    assert grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))
     next(ex[2].parameters()).requires_grad_(True)
     assert not grouped_train_supported(ex, torch.zeros(2, 3, 256, 256))       # an expert that trains needs the autograd path
 
