@@ -207,6 +207,7 @@ class GraphedTrainStep:
     the training state untouched.  Inputs are copied into static buffers per call; the returned loss dict aliases static
     device tensors (overwritten by the next call).  Shapes and the module's train/eval flags are fixed at capture time.
     Autograd graphs of earlier eager steps must be released before construction (see the error raised when capture fails).
+    Frozen-expert weights enter the graph as packed at capture time: build a new GraphedTrainStep after loading other experts.
     """
 
     def __init__(self, model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, config: Dict, warmup: int = 3,
@@ -241,6 +242,17 @@ class GraphedTrainStep:
                 "they were created on, and the captured backward may not synchronise with the legacy default stream.  Drop those "
                 "references (del loss, pred; gc.collect()) before building the graph.") from e
         self.launches_per_replay = launch_count(dev) - n0
+        # The graph reads tensors that live outside its memory pool and are owned by caches: packed / split weights of the frozen
+        # experts (their VALUES are baked into the graph as packed now: re-capture after loading other expert weights).  A later
+        # eager forward may rebuild such a cache entry and drop the old tensors; holding them here keeps replays from reading
+        # freed memory.
+        self._keepalive = [dict(getattr(model, "_expert_packs", {}) or {})]
+        self._keepalive += [dict(m._packs) for m in model.modules() if isinstance(getattr(m, "_packs", None), dict)]
+        for p in model.parameters():
+            for attr in ("_amoe_split6", "_amoe_split6_grouped", "_amoe_stem3"):
+                c = getattr(p, attr, None)
+                if c is not None:
+                    self._keepalive.append(dict(c) if isinstance(c, dict) else c)
         with torch.no_grad():                       # nothing of the above counts as training
             for t, s in zip((optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer._step_dev,
                              optimizer._seed_dev), saved):
