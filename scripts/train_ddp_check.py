@@ -12,7 +12,6 @@ not depend on the shard), (3) reports the step time at 32 frames per GPU, 256x25
 """
 import os
 import sys
-import time
 from pathlib import Path
 
 import torch
